@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- observations binned per second on the BASELINE.json workload.
+
+A "step" is one pass of the hot path over one month of synthetic conventional ODS columns
+(BASELINE.json configs[1]: 124 six-hourly files x ~1.21 M obs, omf+oma in one pass, 1x1 deg x 26
+levels, 16 (kt,kx) grids): zero the accumulators, accumulate every file (QC filter + box index +
+count/sum/sum-of-squares, fused kernel), [all-reduce the partial grids over ranks], finalize
+mean / rms / stdv.  With N ranks every rank processes its own month (weak scaling) and the grids
+are summed with one NCCL all-reduce before the finalize.
+
+  value  : whole-job obs/s with the columns already resident in HBM (CUDA events on the library stream)
+  e2e    : same step through the C ABI with pinned HOST columns (H2D inside) and the finalized
+           grids copied back to pinned host arrays (D2H inside)
+  --impl reference : the CPU restatement of the reference loops (oracle/, the reference itself cannot
+           be built here: Fortran + un-vendored GMAO_Shared), file-sharded over the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "observations_binned_per_sec"
+UNIT = "obs/s"
+COLS_F64 = ("lat", "lon", "lev", "omf", "oma")
+COLS_I32 = ("kt", "kx", "qcexcl")
+B_OBS = 36 + 8 * 2  # algorithmic bytes per observation at nr=2 (SURVEY.md 8d / BASELINE.md 3)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--files", type=int, default=0, help="override the number of files (debug)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink obs per file (debug)")
+    ap.add_argument("--mode", default="fast", choices=["fast", "deterministic"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def gen_files(cfg, first, count, workers=8):
+    from gritas_b200 import synth
+
+    def one(i):
+        c = synth.make_file(cfg, first + i)
+        return {k: np.ascontiguousarray(c[k]) for k in COLS_F64 + COLS_I32}
+    with ThreadPoolExecutor(max_workers=max(1, min(workers, os.cpu_count() or 1))) as ex:
+        return list(ex.map(one, range(count)))
+
+
+def workload_name(cfg, nfiles):
+    return (f"{cfg.name}: {nfiles} files x {cfg.nobs_per_file} obs, omf+oma (nr=2), {cfg.im}x{cfg.jm}x{cfg.km}, "
+            f"{len(cfg.kt_list)} (kt,kx) grids")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_ev = threading.Event()
+        self.sm, self.reasons, self.max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, n): n[len("nvmlClocksEventReason"):] for n in dir(nv)
+                     if n.startswith("nvmlClocksEventReason") and isinstance(getattr(nv, n), int)}
+            if not names:
+                names = {getattr(nv, n): n[len("nvmlClocksThrottleReason"):] for n in dir(nv)
+                         if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int)}
+            while not self.stop_ev.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if bit and (r & bit) and nm not in ("None", "All"):
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def result(self):
+        self.stop_ev.set()
+        self.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.max,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(cfg, files, table, l2d, l3d, p1, p2, nthreads, grids):
+    """One CPU step: the files sharded over `nthreads` workers (private grids each, like independent
+    gritas.x processes), QC filter + GrITAS_Accum per file, partial grids summed, GrITAS_Norm."""
+    from gritas_b200 import synth
+    from oracle import oracle
+
+    def work(t):
+        g = grids[t]
+        for a in (g.bias_3d, g.rtms_3d, g.xcov_3d, g.nobs_3d, g.bias_2d, g.rtms_2d, g.xcov_2d, g.nobs_2d):
+            a[...] = 0.0
+        for c in files[t::nthreads]:
+            fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=101, x_passive=synth.X_PASSIVE,
+                                     x_pre_bad=synth.X_PRE_BAD)
+            oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], c["del"], table, p1, p2, fl)
+    if nthreads == 1:
+        work(0)
+    else:
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(work, range(nthreads)))
+        g0 = grids[0]
+
+        def red(name):
+            a = getattr(g0, name)
+            for t in range(1, nthreads):
+                np.add(a, getattr(grids[t], name), out=a)
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(red, ["bias_3d", "rtms_3d", "xcov_3d", "nobs_3d", "bias_2d", "rtms_2d", "xcov_2d", "nobs_2d"]))
+    oracle.norm(grids[0], cfg.nlevs, True, 0)
+
+
+def prepare_cpu_files(files):
+    out = []
+    for c in files:
+        n = len(c["lat"])
+        d = np.zeros((n, 2), order="F")
+        d[:, 0], d[:, 1] = c["omf"], c["oma"]      # gritas.f:562-587 (omf, oma)
+        cc = dict(c)
+        cc["del"] = d
+        cc["time"] = np.zeros(n, np.int32)
+        out.append(cc)
+    return out
+
+
+def time_cpu(cfg, files, nthreads, steps, warmup):
+    from gritas_b200 import synth
+    from oracle import oracle
+    table, l2d, l3d = synth.kxkt_table(cfg)
+    p1, p2 = oracle.pint(cfg.plevs)
+    grids = [oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 2) for _ in range(nthreads)]
+    cf = prepare_cpu_files(files)
+    nobs = sum(len(c["lat"]) for c in cf)
+    for _ in range(warmup):
+        cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids)
+    dt = (time.perf_counter() - t0) / steps
+    return nobs / dt, dt, nobs
+
+
+def run_reference(args):
+    """--impl reference: CPU restatement of the reference loops on the host cores (kind = "port":
+    gritas.x itself needs a Fortran compiler and un-vendored GMAO_Shared, neither is in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gritas_b200 import synth
+    cfg = synth.get_config(args.config, args.scale)
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 16 << 30
+    per_thread = 8 * cfg.im * cfg.jm * cfg.km * len(cfg.kt_list) * 9 + (1 << 28)
+    nthreads = int(max(1, min(cores, 16, (avail // 2) // per_thread)))
+    # bounded sample: about 4 s of CPU work per step (0.33 s per 1.21 M-obs file and thread here)
+    nfiles = args.files or int(min(cfg.nfiles, max(nthreads, (4.0 / 0.35) * nthreads * (1.21e6 / cfg.nobs_per_file))))
+    nfiles = max(nthreads, (nfiles // nthreads) * nthreads)
+    files = gen_files(cfg, 0, nfiles)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    v, dt, nobs = time_cpu(cfg, files, nthreads, steps, warmup)
+    sample = (f"{nfiles} of {cfg.nfiles} files ({nobs} obs) per step, sharded over {nthreads} threads with private "
+              f"grids, partial grids summed, then Norm; pre-sort (gritas.f:499-523) not included")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, cfg.nfiles), "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from gritas_b200 import cabi, synth
+    from gritas_b200.m_gritas_grids import Grids, nccl_unique_id
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: gritas_b200 has no CPU fallback")
+    cabi.load(build_if_missing=True)
+
+    cfg = synth.get_config(args.config, args.scale)
+    nfiles = args.files or cfg.nfiles
+    files = gen_files(cfg, rank * cfg.nfiles, nfiles)        # before CUDA work: numpy threads only
+    nobs_rank = sum(len(c["lat"]) for c in files)
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    table, l2d, l3d = synth.kxkt_table(cfg)
+    mode = (cabi.MODE_FAST if args.mode == "fast" else cabi.MODE_DETERMINISTIC) | cabi.FLAG_ASYNC | cabi.FLAG_HOLD_INPUTS
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode, device=local)
+    p1, p2 = G.GrITAS_Pint()
+    G._ensure(2, table, p1, p2, l2d, l3d)
+    if world > 1:
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        G.comm_init(world, rank, ids[0])
+    L = cabi.load()
+    stream = torch.cuda.ExternalStream(G.stream(), device=torch.device("cuda", local))
+
+    dev_files = [{k: torch.from_numpy(v).cuda() for k, v in c.items()} for c in files]
+    torch.cuda.synchronize()
+    import ctypes
+
+    def calls_of(cols):
+        # argument tuples of gritas_b200_accum_ods, built once: the timed loop is then what a compiled
+        # driver's loop over synoptic times would be (one C call per file)
+        out = []
+        for c in cols:
+            p = lambda k: cabi.ptr(c[k])
+            out.append((G.handle, int(c["lat"].shape[0]), p("lat"), p("lon"), p("lev"), None, p("kt"), p("kx"),
+                        p("qcexcl"), p("omf"), p("oma"), None, None, cabi.IOPT_OMF_OMA, 0, cabi.IOPT_OMF_OMA, 0, -1,
+                        -999.0, 999.0, synth.X_PASSIVE, synth.X_PRE_BAD, None, None))
+        return out
+    dptr = [C_void() for _ in range(10)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(cols, host_out=None, marks=None):
+        G.reset()
+        if marks is not None:
+            marks[0].record(stream)
+        for a in cols:
+            rc = L.gritas_b200_accum_ods(*a)
+            if rc:
+                raise RuntimeError(f"accum_ods rc={rc}: {G._err()}")
+        if marks is not None:
+            marks[1].record(stream)
+        if world > 1:
+            G.allreduce()
+        if host_out is None:
+            rc = L.gritas_b200_norm_device(G.handle, 1, -1, *[None] * 5, *dptr[5:])
+            if rc:
+                raise RuntimeError(f"norm_device rc={rc}")
+        else:
+            G.norm_into(host_out)
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    dev_calls = calls_of(dev_files)
+    for _ in range(max(3, args.warmup)):
+        step(dev_calls)
+    c0 = G.counters()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = ev(), ev()
+    marks = [(ev(), ev()) for _ in range(args.steps)]
+    e0.record(stream)
+    for s in range(args.steps):
+        step(dev_calls, marks=marks[s])
+    e1.record(stream)
+    barrier()
+    clocks = sampler.result()
+    c1 = G.counters()
+    ms = e0.elapsed_time(e1) / args.steps
+    accum_ms = float(np.mean([a.elapsed_time(b) for a, b in marks]))
+    t = torch.tensor([ms, accum_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, accum_ms = float(t[0]), float(t[1])
+    launches_per_step = (c1["launches"] - c0["launches"]) // args.steps
+    value = nobs_rank * world / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host columns in, finalized grids out to pinned host arrays ----
+    e2e = None
+    if not args.no_e2e:
+        pin_files = [{k: torch.from_numpy(v).pin_memory() for k, v in c.items()} for c in files]
+        host_out = G.alloc_grids(pinned=True)
+        pin_calls = calls_of(pin_files)
+        step(pin_calls, host_out)
+        b0 = G.counters()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step(pin_calls, host_out)
+        G.sync()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        b1 = G.counters()
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": nobs_rank * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "h2d_bytes_per_step": (b1["h2d"] - b0["h2d"]) // args.e2e_steps,
+               "d2h_bytes_per_step": (b1["d2h"] - b0["d2h"]) // args.e2e_steps,
+               "note": "per rank bytes; pinned host columns -> C ABI -> pinned host mean/rms/stdv/xcov/nobs grids"}
+        del pin_files
+
+    # ---- roofline of the dominant kernel (fused filter + box index + accumulate) -----------------
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    nbox = cfg.im * cfg.jm * cfg.km * l3d + cfg.im * cfg.jm * l2d
+    grid_bytes = 8 * (1 + 2 * 2) * nbox                      # written once per pass
+    alg_bytes_per_launch = (nobs_rank * B_OBS + grid_bytes) / nfiles
+    launch_ms = accum_ms / nfiles
+    achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_accum_fast<2>" if args.mode == "fast" else "k_box_keys+sort+k_segment_sum",
+                "peak_source": peak_src, "avg_launch_ms": launch_ms,
+                "alg_bytes_per_launch": alg_bytes_per_launch,
+                "note": f"{B_OBS} B/obs x obs per file + (8*(1+2*nr)*boxes)/files; launch time = accumulate region "
+                        f"({nfiles} back-to-back launches, CUDA events on the library stream) / {nfiles}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
+                       "per_rank": "each rank bins its own month; one NCCL all-reduce of the partial grids, then finalize",
+                       "l2": "inputs (7.8 GB/step) and accumulators (1.7 GB) both exceed the 126 MB L2; no flush needed"},
+            "accumulate_ms_per_step": accum_ms, "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): single thread, like gritas.x ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = min(nfiles, 32)
+        v, dt, nobs = time_cpu(cfg, files[:ns], 1, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{ns} of {nfiles} files ({nobs} obs): QC filter + GrITAS_Accum per file, "
+                                          f"then GrITAS_Norm, single thread (the reference is serial); its 8-key "
+                                          f"pre-sort (gritas.f:499-523) is not included",
+                                "host_cores": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    G.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def C_void():
+    import ctypes
+    return ctypes.pointer(ctypes.c_void_p())
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

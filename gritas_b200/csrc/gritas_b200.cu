@@ -1,0 +1,803 @@
+// gritas_b200.cu -- host side of the C ABI declared in include/gritas_b200.h.
+//
+// One context per process/GPU.  The count / sum / sum-of-squares accumulators live in HBM for
+// the whole run (the reference keeps them in host arrays passed inout to every
+// GrITAS_Accum_ call, m_gritas_grids.f:307-311); observation columns are staged through
+// double-buffered pinned + device slots so the copy of synoptic time n+1 overlaps the kernel of
+// time n (gritas.f:389-808 is the loop this sits in).  There is no CPU implementation of any
+// entry point in this file: without a CUDA device create() fails.
+#include "../../include/gritas_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+using namespace gb200;
+
+namespace {
+
+constexpr int NSLOT = 2;   // staging slots (double buffering)
+constexpr int NCOL = 12;   // staged columns per slot
+enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME };
+
+// --- NCCL through dlopen: the library has no link-time dependency on it ------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void *so = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (so) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (so) break;
+    }
+    if (!so) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(so, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(so, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(so, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
+constexpr int NCCL_SUM = 0;      // ncclSum
+
+struct Slot {
+  void *dev[NCOL] = {};
+  void *pin[NCOL] = {};
+  size_t dev_cap[NCOL] = {};
+  size_t pin_cap[NCOL] = {};
+  int *flag_out = nullptr;
+  size_t flag_out_cap = 0;
+  cudaEvent_t consumed = nullptr;  // kernel that read this slot has finished
+  cudaEvent_t copied = nullptr;    // H2D copies into this slot have finished
+};
+
+}  // namespace
+
+struct gritas_b200_ctx {
+  int device = 0;
+  int mode = 0, flags = 0;
+  GridDesc g = {};
+  size_t nrec = 0;
+  int *d_table = nullptr;
+  double *d_p1 = nullptr, *d_p2 = nullptr;
+  Status *d_status = nullptr;
+  Status *h_status = nullptr;  // pinned
+  cudaStream_t compute = nullptr, copy = nullptr;
+  bool own_compute = true;
+  Slot slot[NSLOT];
+  int next_slot = 0;
+  unsigned call_seq = 0;
+  // deterministic path scratch
+  unsigned *keys = nullptr, *idx = nullptr, *keys2 = nullptr, *idx2 = nullptr;
+  size_t sort_cap = 0;
+  void *cub_tmp = nullptr;
+  size_t cub_cap = 0;
+  int key_bits = 32;
+  // finalize scratch (reference-layout planes on the device)
+  double *out = nullptr;
+  size_t out_cap = 0;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  // counters
+  uint64_t launches = 0, h2d = 0, d2h = 0;
+  char err[512] = {0};
+};
+
+namespace {
+
+int fail(gritas_b200_handle h, int rc, const char *fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return rc;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(h, GRITAS_B200_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// Where does a caller pointer live?  0 pageable host, 1 pinned host, 2 device / managed.
+int mem_kind(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 2;
+  if (a.type == cudaMemoryTypeHost) return 1;
+  return 0;
+}
+
+int grow_dev(gritas_b200_handle h, void **p, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) CU(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CU(cudaMalloc(p, want));
+  *cap = want;
+  return 0;
+}
+
+int grow_pin(gritas_b200_handle h, void **p, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) CU(cudaFreeHost(*p));
+  *p = nullptr;
+  *cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CU(cudaMallocHost(p, want));
+  *cap = want;
+  return 0;
+}
+
+// Makes column `c` of this call available on the device; returns the device pointer in *out.
+// Device-resident inputs are used in place.  Pinned inputs are DMA'd straight from the caller's
+// array; pageable inputs go through the slot's pinned buffer.
+int stage(gritas_b200_handle h, Slot &s, int c, const void *src, size_t bytes, const void **out, bool *any_copy) {
+  if (!src || bytes == 0) { *out = src ? src : nullptr; return 0; }
+  const int kind = mem_kind(src);
+  if (kind == 2) { *out = src; return 0; }
+  int rc = grow_dev(h, &s.dev[c], &s.dev_cap[c], bytes);
+  if (rc) return rc;
+  const void *from = src;
+  if (kind == 0) {
+    rc = grow_pin(h, &s.pin[c], &s.pin_cap[c], bytes);
+    if (rc) return rc;
+    memcpy(s.pin[c], src, bytes);
+    from = s.pin[c];
+  }
+  CU(cudaMemcpyAsync(s.dev[c], from, bytes, cudaMemcpyHostToDevice, h->copy));
+  h->h2d += bytes;
+  *any_copy = true;
+  *out = s.dev[c];
+  return 0;
+}
+
+bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
+
+int clear_status(gritas_b200_handle h) {
+  Status st;
+  st.first_bad = BAD_NONE;
+  st.bad_lev = 0.0;
+  st.ticket = 0;
+  st.pad = 0;
+  CU(cudaMemcpyAsync(h->d_status, &st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+// Waits for the compute stream and converts a recorded level miss into the return code.
+int drain(gritas_b200_handle h, double *bad_lev) {
+  CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  if (h->h_status->first_bad != BAD_NONE) {
+    const double lev = h->h_status->bad_lev;
+    const unsigned long long fb = h->h_status->first_bad;
+    if (bad_lev) *bad_lev = lev;
+    int rc = clear_status(h);
+    if (rc) return rc;
+    return fail(h, GRITAS_B200_ERR_LEVEL, "Accum: obs level is %.17g hPa; Accum: could not find level (call %u, obs %u)",
+                lev, (unsigned)(fb >> 32), (unsigned)fb + 1u);
+  }
+  return 0;
+}
+
+int grid_for(size_t work, int threads, int per_sm) {
+  size_t b = (work + threads - 1) / threads;
+  size_t cap = (size_t)148 * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+template <int NR>
+void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
+  if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
+    k_accum_fast<NR, false><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+  else
+    k_accum_fast<NR, true><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+}
+
+template <int NR>
+void launch_segsum(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, const unsigned *keys,
+                   const unsigned *idx, int n) {
+  k_segment_sum<NR><<<(n + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, h->compute>>>(h->g, c, f, keys, idx, n,
+                                                                                         (unsigned)h->nrec);
+}
+
+// The common back half of accum / accum_ods once the column pointers are on the device.
+int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, bool any_copy, int32_t *flag_host_or_dev,
+              double *bad_lev) {
+  const int n = c.n;
+  // ob_flag write-back target
+  bool flag_to_host = false;
+  if (flag_host_or_dev) {
+    if (mem_kind(flag_host_or_dev) == 2) {
+      c.flag_out = flag_host_or_dev;
+    } else {
+      int rc = grow_dev(h, (void **)&s.flag_out, &s.flag_out_cap, sizeof(int) * (size_t)n);
+      if (rc) return rc;
+      c.flag_out = s.flag_out;
+      flag_to_host = true;
+    }
+  }
+  c.aligned = aligned16(c.lat) && aligned16(c.lon) && aligned16(c.lev) && aligned16(c.kx) && aligned16(c.kt) &&
+              aligned16(c.flag) && aligned16(c.time) && aligned16(c.flag_out);
+  for (int ir = 0; ir < h->g.nr; ++ir) c.aligned = c.aligned && aligned16(c.d[ir]);
+
+  if (any_copy) {
+    CU(cudaEventRecord(s.copied, h->copy));
+    CU(cudaStreamWaitEvent(h->compute, s.copied, 0));
+  }
+  const size_t smem = h->g.p2_in_smem ? sizeof(double) * (size_t)h->g.nlevs : 0;
+  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
+    const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
+    const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
+    switch (h->g.nr) {
+      case 1: launch_fast<1>(h, c, f, nblk, smem); break;
+      case 2: launch_fast<2>(h, c, f, nblk, smem); break;
+      default: launch_fast<3>(h, c, f, nblk, smem); break;
+    }
+    h->launches += 1;
+  } else {
+    // K1 keys -> stable LSD radix sort of (key, obs index) -> in-order segment sums
+    if (h->sort_cap < (size_t)n) {
+      for (unsigned **p : {&h->keys, &h->idx, &h->keys2, &h->idx2}) {
+        if (*p) CU(cudaFree(*p));
+        *p = nullptr;
+      }
+      size_t want = (size_t)n + (size_t)n / 8 + 1024;
+      CU(cudaMalloc(&h->keys, want * 4));
+      CU(cudaMalloc(&h->idx, want * 4));
+      CU(cudaMalloc(&h->keys2, want * 4));
+      CU(cudaMalloc(&h->idx2, want * 4));
+      h->sort_cap = want;
+    }
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, h->keys, h->keys2, h->idx, h->idx2, n, 0, h->key_bits, h->compute);
+    if (grow_dev(h, &h->cub_tmp, &h->cub_cap, need)) return GRITAS_B200_ERR_CUDA;
+    k_box_keys<<<grid_for((size_t)n, ACC_THREADS, 8), ACC_THREADS, smem, h->compute>>>(
+        h->g, c, f, h->d_status, h->call_seq, h->keys, h->idx, (unsigned)h->nrec);
+    size_t tmp = h->cub_cap;
+    CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys2, h->idx, h->idx2, n, 0, h->key_bits,
+                                       h->compute));
+    switch (h->g.nr) {
+      case 1: launch_segsum<1>(h, c, f, h->keys2, h->idx2, n); break;
+      case 2: launch_segsum<2>(h, c, f, h->keys2, h->idx2, n); break;
+      default: launch_segsum<3>(h, c, f, h->keys2, h->idx2, n); break;
+    }
+    h->launches += 2 + (uint64_t)((h->key_bits + 7) / 8) * 2 + 1;  // keys, segsum, sort passes (approx.)
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(s.consumed, h->compute));
+
+  if (flag_to_host) {
+    CU(cudaMemcpyAsync(flag_host_or_dev, s.flag_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->compute));
+    h->d2h += sizeof(int) * (size_t)n;
+  }
+  const bool async = (h->flags & GRITAS_B200_FLAG_ASYNC) != 0;
+  if (!async || flag_to_host) return drain(h, bad_lev);
+  // async: the caller's arrays must be reusable on return -> wait for the copies, not the kernel
+  if (any_copy && !(h->flags & GRITAS_B200_FLAG_HOLD_INPUTS)) CU(cudaEventSynchronize(s.copied));
+  return 0;
+}
+
+int check_handle(gritas_b200_handle h) {
+  if (!h) return GRITAS_B200_ERR_ARG;
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, GRITAS_B200_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int gritas_b200_version(void) { return 100; }
+
+const char *gritas_b200_last_error(gritas_b200_handle h) { return h ? h->err : "null handle"; }
+
+int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs, int l2d, int l3d, int nr,
+                       const double *p1, const double *p2, const int32_t *kxkt_table, int kxmax, int ktmax, int mode,
+                       int device) {
+  if (!hp) return GRITAS_B200_ERR_ARG;
+  *hp = nullptr;
+  if (im < 1 || jm < 2 || km < 1 || nlevs < 1 || nlevs > km || l2d < 0 || l3d < 0 || !p1 || !p2 || !kxkt_table ||
+      kxmax < 1 || ktmax < 1)
+    return GRITAS_B200_ERR_ARG;
+  if (nr < 1) return GRITAS_B200_ERR_ARG;
+  if (nr > 3) return GRITAS_B200_ERR_NR;  // m_gritas_grids.f:395-396
+  const int m = mode & 0xff;
+  if (m != GRITAS_B200_MODE_FAST && m != GRITAS_B200_MODE_DETERMINISTIC) return GRITAS_B200_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return GRITAS_B200_ERR_CUDA;  // no CPU fallback
+  }
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    if (lr && *lr) device = atoi(lr) % ndev;
+    else if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= ndev) return GRITAS_B200_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return GRITAS_B200_ERR_CUDA;
+
+  const size_t nbox3 = (size_t)im * jm * km * l3d, nbox2 = (size_t)im * jm * l2d;
+  if (nbox3 + nbox2 >= (size_t)0xFFFFFFF0u) return GRITAS_B200_ERR_ARG;  // 32-bit record keys
+
+  gritas_b200_handle h = new (std::nothrow) gritas_b200_ctx();
+  if (!h) return GRITAS_B200_ERR_ARG;
+  h->device = device;
+  h->mode = m;
+  h->flags = mode & ~0xff;
+  GridDesc &g = h->g;
+  g.im = im; g.jm = jm; g.km = km; g.nlevs = nlevs; g.l2d = l2d; g.l3d = l3d; g.nr = nr;
+  g.rs = (nr == 1) ? 4 : 8;
+  g.kxmax = kxmax; g.ktmax = ktmax;
+  g.dlon = 360.0 / (double)im;        // m_gritas_grids.f:128
+  g.dlat = 180.0 / (double)(jm - 1);  // m_gritas_grids.f:129
+  g.nbox3 = (unsigned)nbox3; g.nbox2 = (unsigned)nbox2;
+  h->nrec = nbox3 + nbox2;
+  // GrITAS_Pint tables are contiguous (p1(k+1) is the same expression as p2(k)) and descending:
+  // then the branch-free search is exact.  Anything else takes the literal linear scan.
+  g.contiguous = 1;
+  for (int k = 0; k + 1 < nlevs; ++k)
+    if (!(p1[k + 1] == p2[k]) || !(p2[k] > p2[k + 1])) g.contiguous = 0;
+  if (!(p1[0] > p2[0])) g.contiguous = 0;
+  for (int k = 0; k < nlevs; ++k)
+    if (p1[k] != p1[k] || p2[k] != p2[k]) g.contiguous = 0;
+  g.p1_top = p1[0];
+  g.p2_in_smem = (sizeof(double) * (size_t)nlevs <= 40 * 1024) ? 1 : 0;
+  h->key_bits = 1;
+  while (h->key_bits < 32 && ((size_t)1 << h->key_bits) <= h->nrec) h->key_bits++;
+
+#define CUC(call)                                                                                       \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      fprintf(stderr, "gritas_b200_create: %s: %s\n", #call, cudaGetErrorString(e_));                   \
+      gritas_b200_destroy(h);                                                                           \
+      return GRITAS_B200_ERR_CUDA;                                                                      \
+    }                                                                                                   \
+  } while (0)
+  CUC(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+  for (int i = 0; i < NSLOT; ++i) {
+    CUC(cudaEventCreateWithFlags(&h->slot[i].consumed, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->slot[i].copied, cudaEventDisableTiming));
+  }
+  CUC(cudaMalloc(&h->d_table, sizeof(int) * (size_t)kxmax * ktmax));
+  CUC(cudaMalloc(&h->d_p1, sizeof(double) * nlevs));
+  CUC(cudaMalloc(&h->d_p2, sizeof(double) * nlevs));
+  CUC(cudaMalloc(&h->d_status, sizeof(Status)));
+  CUC(cudaMallocHost(&h->h_status, sizeof(Status)));
+  const size_t acc_bytes = sizeof(double) * (h->nrec > 0 ? h->nrec : 1) * g.rs;
+  CUC(cudaMalloc(&g.acc, acc_bytes));
+  CUC(cudaMemcpy(h->d_table, kxkt_table, sizeof(int) * (size_t)kxmax * ktmax, cudaMemcpyDefault));
+  CUC(cudaMemcpy(h->d_p1, p1, sizeof(double) * nlevs, cudaMemcpyDefault));
+  CUC(cudaMemcpy(h->d_p2, p2, sizeof(double) * nlevs, cudaMemcpyDefault));
+  CUC(cudaMemsetAsync(g.acc, 0, acc_bytes, h->compute));  // gritas.f:352-363
+  g.table = h->d_table; g.p1 = h->d_p1; g.p2 = h->d_p2;
+  Status st;
+  st.first_bad = BAD_NONE; st.bad_lev = 0.0; st.ticket = 0; st.pad = 0;
+  CUC(cudaMemcpyAsync(h->d_status, &st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
+  CUC(cudaStreamSynchronize(h->compute));
+#undef CUC
+  *hp = h;
+  return GRITAS_B200_OK;
+}
+
+void gritas_b200_destroy(gritas_b200_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->compute) cudaStreamSynchronize(h->compute);
+  if (h->copy) cudaStreamSynchronize(h->copy);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int i = 0; i < NSLOT; ++i) {
+    Slot &s = h->slot[i];
+    for (int c = 0; c < NCOL; ++c) {
+      if (s.dev[c]) cudaFree(s.dev[c]);
+      if (s.pin[c]) cudaFreeHost(s.pin[c]);
+    }
+    if (s.flag_out) cudaFree(s.flag_out);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+    if (s.copied) cudaEventDestroy(s.copied);
+  }
+  for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
+                  (void *)h->keys, (void *)h->idx, (void *)h->keys2, (void *)h->idx2, h->cub_tmp, (void *)h->out})
+    if (p) cudaFree(p);
+  if (h->h_status) cudaFreeHost(h->h_status);
+  if (h->compute && h->own_compute) cudaStreamDestroy(h->compute);
+  if (h->copy) cudaStreamDestroy(h->copy);
+  cudaGetLastError();
+  delete h;
+}
+
+static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
+                        const double *const dcol[3], const double *obs, const double *xvec, const double *omf_for_scale,
+                        const int32_t *kx, const int32_t *kt, const int32_t *flag_in, const int32_t *time,
+                        const FilterDesc &f, int32_t *flag_out, double *bad_lev) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (nobs < 0) return fail(h, GRITAS_B200_ERR_ARG, "nobs < 0");
+  h->call_seq += 1;
+  if (nobs == 0) return GRITAS_B200_OK;
+  if (!lat || !lon || !lev || !kx || !kt) return fail(h, GRITAS_B200_ERR_ARG, "null column");
+  for (int ir = 0; ir < h->g.nr; ++ir)
+    if (!dcol[ir]) return fail(h, GRITAS_B200_ERR_ARG, "null residual column %d", ir + 1);
+
+  Slot &s = h->slot[h->next_slot];
+  h->next_slot = (h->next_slot + 1) % NSLOT;
+  CU(cudaEventSynchronize(s.consumed));  // the kernel that last read this slot is done
+
+  ObsCols c = {};
+  c.n = nobs;
+  bool any = false;
+  const size_t nb8 = sizeof(double) * (size_t)nobs, nb4 = sizeof(int) * (size_t)nobs;
+  if ((rc = stage(h, s, C_LAT, lat, nb8, (const void **)&c.lat, &any))) return rc;
+  if ((rc = stage(h, s, C_LON, lon, nb8, (const void **)&c.lon, &any))) return rc;
+  if ((rc = stage(h, s, C_LEV, lev, nb8, (const void **)&c.lev, &any))) return rc;
+  for (int ir = 0; ir < h->g.nr; ++ir)
+    if ((rc = stage(h, s, C_D0 + ir, dcol[ir], nb8, (const void **)&c.d[ir], &any))) return rc;
+  if (f.scale_res == 1 && (rc = stage(h, s, C_XVEC, xvec, nb8, (const void **)&c.xvec, &any))) return rc;
+  if (f.scale_res >= 2 && (rc = stage(h, s, C_OBS, obs, nb8, (const void **)&c.obs, &any))) return rc;
+  if (f.scale_res == 3) {
+    // obs - omf needs omf even when it is not the accumulated column
+    if (omf_for_scale == dcol[0]) c.omf = c.d[0];
+    else if ((rc = stage(h, s, C_D2, omf_for_scale, nb8, (const void **)&c.omf, &any))) return rc;
+  }
+  if ((rc = stage(h, s, C_KX, kx, nb4, (const void **)&c.kx, &any))) return rc;
+  if ((rc = stage(h, s, C_KT, kt, nb4, (const void **)&c.kt, &any))) return rc;
+  if (flag_in && (rc = stage(h, s, C_FLAG, flag_in, nb4, (const void **)&c.flag, &any))) return rc;
+  if (f.use_time && (rc = stage(h, s, C_TIME, time, nb4, (const void **)&c.time, &any))) return rc;
+  return run_accum(h, c, f, s, any, flag_out, bad_lev);
+}
+
+int gritas_b200_accum(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
+                      const double *del, const int32_t *kx, const int32_t *kt, int32_t *ob_flag, double *bad_lev) {
+  if (!h) return GRITAS_B200_ERR_ARG;
+  if (nobs > 0 && !del) return fail(h, GRITAS_B200_ERR_ARG, "null del");
+  const double *d[3] = {del, h->g.nr > 1 ? del + (size_t)nobs : nullptr, h->g.nr > 2 ? del + 2 * (size_t)nobs : nullptr};
+  FilterDesc f = {};
+  return accum_common(h, nobs, lat, lon, lev, d, nullptr, nullptr, nullptr, kx, kt, ob_flag, nullptr, f, ob_flag, bad_lev);
+}
+
+int gritas_b200_accum_ods(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
+                          const int32_t *time, const int32_t *kt, const int32_t *kx, const int32_t *qcexcl,
+                          const double *omf, const double *oma, const double *obs, const double *xvec, int iopt,
+                          int scale_res, int ioptn, int t1, int t2, double lona, double lonb, int x_passive,
+                          int x_pre_bad, int32_t *ob_flag_out, double *bad_lev) {
+  if (!h) return GRITAS_B200_ERR_ARG;
+  const double *d[3] = {nullptr, nullptr, nullptr};
+  const int a = iopt < 0 ? -iopt : iopt;
+  int want_nr = 1;
+  if (a == 0 || a == GRITAS_B200_IOPT_OMF) d[0] = omf;                       // gritas.f:562-576
+  else if (a == 2 || a == GRITAS_B200_IOPT_OMA) d[0] = oma;                  // gritas.f:575-587
+  else if (a == GRITAS_B200_IOPT_OMF_OMA) { d[0] = omf; d[1] = oma; want_nr = 2; }
+  else return fail(h, GRITAS_B200_ERR_ARG, "iopt %d not supported by the fused entry", iopt);
+  if (want_nr != h->g.nr) return fail(h, GRITAS_B200_ERR_ARG, "iopt %d needs nr=%d, handle has nr=%d", iopt, want_nr, h->g.nr);
+  if (scale_res < 0 || scale_res > 3) return fail(h, GRITAS_B200_ERR_ARG, "scale_res out of range");
+  if (nobs > 0 && !qcexcl) return fail(h, GRITAS_B200_ERR_ARG, "null qcexcl");
+  if (nobs > 0 && scale_res == 1 && !xvec) return fail(h, GRITAS_B200_ERR_ARG, "scale_res=1 needs xvec");
+  if (nobs > 0 && scale_res >= 2 && !obs) return fail(h, GRITAS_B200_ERR_ARG, "scale_res=2,3 needs obs");
+  if (nobs > 0 && scale_res == 3 && !omf) return fail(h, GRITAS_B200_ERR_ARG, "scale_res=3 needs omf");
+  FilterDesc f = {};
+  // the filter only runs for odd iopt (gritas.f:710); otherwise ob_flag stays 0 (gritas.f:551)
+  const bool filtered = (a & 1) != 0;
+  f.ods = filtered ? 1 : 0;
+  f.ioptn = ioptn;
+  f.t1 = t1; f.t2 = t2;
+  f.use_time = (!filtered || t2 < t1) ? 0 : 1;                       // gritas.f:717-723
+  f.use_lon = (!filtered || (lona < -180.0 && lonb > 180.0)) ? 0 : 1;  // gritas.f:724-730
+  f.lona = lona; f.lonb = lonb;
+  f.x_passive = x_passive; f.x_pre_bad = x_pre_bad;
+  f.scale_res = scale_res;
+  if (nobs > 0 && f.use_time && !time) return fail(h, GRITAS_B200_ERR_ARG, "time window needs the time column");
+  return accum_common(h, nobs, lat, lon, lev, d, obs, xvec, omf, kx, kt, filtered ? qcexcl : nullptr, time, f,
+                      ob_flag_out, bad_lev);
+}
+
+int gritas_b200_sync(gritas_b200_handle h, double *bad_lev) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->copy));
+  return drain(h, bad_lev);
+}
+
+int gritas_b200_reset(gritas_b200_handle h) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
+  return 0;
+}
+
+// Finalize (raw=0) or export the raw sums (raw=1) into reference-layout planes.
+static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, double *const user[10], const double **dev_out) {
+  // order: bias_2d rtms_2d stdv_2d xcov_2d nobs_2d bias_3d rtms_3d stdv_3d xcov_3d nobs_3d
+  const GridDesc &g = h->g;
+  const int nr = g.nr;
+  if (!raw && nr > 2) return fail(h, GRITAS_B200_ERR_NR, "Accum: could not handle more then 2 residuals");  // :555
+  const size_t n2 = g.nbox2, n3 = g.nbox3;
+  const int xpl = raw ? 1 : nr;
+  const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
+  // nlevs<2: the reference returns before the 3-D loop (m_gritas_grids.f:607) -> 3-D sums stay raw
+  const bool raw3 = raw || g.nlevs < 2;
+  double *dst[10];
+  bool bounce[10];
+  size_t need = 0;
+  for (int a = 0; a < 10; ++a) {
+    bounce[a] = false;
+    dst[a] = nullptr;
+    const bool skip = (!user[a] && !dev_out) || sz[a] == 0 || (raw && (a == 2 || a == 7)) || (!raw && raw3 && a == 7);
+    if (skip) continue;
+    if (!dev_out && mem_kind(user[a]) == 2) dst[a] = user[a];
+    else { bounce[a] = true; need += sz[a]; }
+  }
+  if (need) {
+    int rc = grow_dev(h, (void **)&h->out, &h->out_cap, sizeof(double) * need);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int a = 0; a < 10; ++a)
+      if (bounce[a]) { dst[a] = h->out + off; off += sz[a]; }
+  }
+  const int ntr = ntresh < 0 ? 0 : ntresh;
+  if (n2) {
+    OutPlanes o = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
+    const int nb = grid_for(n2, 256, 8);
+    if (nr == 1) k_finalize2<1><<<nb, 256, 0, h->compute>>>(g, o, nrmlz, ntr, raw);
+    else if (nr == 2) k_finalize2<2><<<nb, 256, 0, h->compute>>>(g, o, nrmlz, ntr, raw);
+    else k_finalize2<3><<<nb, 256, 0, h->compute>>>(g, o, nrmlz, ntr, raw);
+    h->launches++;
+  }
+  if (n3) {
+    OutPlanes o = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && !raw) ? 1 : xpl};
+    dim3 blk(32, 32), grd((g.km + 31) / 32, (g.im + 31) / 32, 1);
+    size_t z = (size_t)g.jm * g.l3d;
+    grd.z = (unsigned)(z > 65535 ? 65535 : z);
+    const int r3 = raw3 ? 1 : 0;
+    if (nr == 1) k_finalize3<1><<<grd, blk, 0, h->compute>>>(g, o, nrmlz, ntr, r3);
+    else if (nr == 2) k_finalize3<2><<<grd, blk, 0, h->compute>>>(g, o, nrmlz, ntr, r3);
+    else k_finalize3<3><<<grd, blk, 0, h->compute>>>(g, o, nrmlz, ntr, r3);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  for (int a = 0; a < 10; ++a) {
+    if (dev_out) dev_out[a] = dst[a];
+    else if (bounce[a]) {
+      CU(cudaMemcpyAsync(user[a], dst[a], sizeof(double) * sz[a], cudaMemcpyDeviceToHost, h->compute));
+      h->d2h += sizeof(double) * sz[a];
+    }
+  }
+  CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+int gritas_b200_norm(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d, double *stdv_2d,
+                     double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *stdv_3d,
+                     double *xcov_3d, double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
+  return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
+}
+
+int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **bias_2d, const double **rtms_2d,
+                            const double **stdv_2d, const double **xcov_2d, const double **nobs_2d,
+                            const double **bias_3d, const double **rtms_3d, const double **stdv_3d,
+                            const double **xcov_3d, const double **nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  double *const u[10] = {};
+  const double *d[10] = {};
+  rc = finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, d);
+  if (rc) return rc;
+  const double **outp[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
+  for (int a = 0; a < 10; ++a)
+    if (outp[a]) *outp[a] = d[a];
+  return 0;
+}
+
+int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, double *xcov_2d, double *nobs_2d,
+                        double *bias_3d, double *rtms_3d, double *xcov_3d, double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  double *const u[10] = {bias_2d, rtms_2d, nullptr, xcov_2d, nobs_2d, bias_3d, rtms_3d, nullptr, xcov_3d, nobs_3d};
+  return finalize_to(h, 1, 0, 0, u, nullptr);
+}
+
+int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const double *rtms_2d, const double *xcov_2d,
+                        const double *nobs_2d, const double *bias_3d, const double *rtms_3d, const double *xcov_3d,
+                        const double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  const GridDesc &g = h->g;
+  const int nr = g.nr;
+  const size_t n2 = g.nbox2, n3 = g.nbox3;
+  const double *src[8] = {bias_2d, rtms_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, xcov_3d, nobs_3d};
+  const size_t sz[8] = {n2 * nr, n2 * nr, n2, n2, n3 * nr, n3 * nr, n3, n3};
+  const double *dev[8] = {};
+  size_t need = 0;
+  for (int a = 0; a < 8; ++a)
+    if (src[a] && sz[a] && mem_kind(src[a]) != 2) need += sz[a];
+  if (need) {
+    rc = grow_dev(h, (void **)&h->out, &h->out_cap, sizeof(double) * need);
+    if (rc) return rc;
+  }
+  size_t off = 0;
+  for (int a = 0; a < 8; ++a) {
+    if (!src[a] || !sz[a]) continue;
+    if (mem_kind(src[a]) == 2) { dev[a] = src[a]; continue; }
+    CU(cudaMemcpyAsync(h->out + off, src[a], sizeof(double) * sz[a], cudaMemcpyHostToDevice, h->compute));
+    h->h2d += sizeof(double) * sz[a];
+    dev[a] = h->out + off;
+    off += sz[a];
+  }
+  for (int is3d = 0; is3d < 2; ++is3d) {
+    const size_t nb = is3d ? n3 : n2;
+    if (!nb) continue;
+    const double *const *d = dev + 4 * is3d;
+    if (!d[0] && !d[1] && !d[2] && !d[3]) continue;
+    OutPlanes in = {(double *)d[0], (double *)d[1], nullptr, (double *)d[2], (double *)d[3], 1};
+    const int blocks = grid_for(nb, 256, 8);
+    if (nr == 1) k_add_raw<1><<<blocks, 256, 0, h->compute>>>(g, in, is3d);
+    else if (nr == 2) k_add_raw<2><<<blocks, 256, 0, h->compute>>>(g, in, is3d);
+    else k_add_raw<3><<<blocks, 256, 0, h->compute>>>(g, in, is3d);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------
+int gritas_b200_nccl_unique_id(void *id128) {
+  if (!id128) return GRITAS_B200_ERR_ARG;
+  if (!g_nccl.load()) return GRITAS_B200_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return GRITAS_B200_ERR_NCCL;
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int gritas_b200_comm_init(gritas_b200_handle h, int nranks, int rank, const void *id128) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(h, GRITAS_B200_ERR_ARG, "bad rank/nranks");
+  if (!g_nccl.load()) return fail(h, GRITAS_B200_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  int e = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  h->nranks = nranks;
+  h->rank = rank;
+  return 0;
+}
+
+int gritas_b200_allreduce(gritas_b200_handle h) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (h->nranks == 1 && !h->comm) return 0;
+  if (!h->comm) return fail(h, GRITAS_B200_ERR_NCCL, "comm_init not called");
+  CU(cudaStreamSynchronize(h->copy));
+  int e = g_nccl.AllReduce(h->g.acc, h->g.acc, h->nrec * h->g.rs, NCCL_FLOAT64, NCCL_SUM, h->comm, h->compute);
+  if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  return 0;
+}
+
+// ---- host-side table builders -------------------------------------------------------------------
+// GrITAS_Pint_ (m_gritas_grids.f:217-296).  Level k collects p1(k) >= lev > p2(k); the interfaces are
+// the log-pressure mid-points, the first interval opens at 2000 hPa and the last closes at 0.
+int gritas_b200_pint(int nlevs, const double *plevs, double *p1, double *p2) {
+  if (nlevs <= 0 || !plevs || !p1 || !p2) return 1;
+  if (nlevs == 1) {  // single-level case: a 0.1 hPa slab below the level (:249-256)
+    p1[0] = plevs[0];
+    p2[0] = plevs[0] - 0.1;
+    return 0;
+  }
+  for (int k = 1; k < nlevs; ++k)
+    if (!(plevs[k - 1] > plevs[k])) return 2;
+  if (plevs[nlevs - 1] == 0.0) return 3;
+  auto mid = [&](int a, int b) { return exp(0.5 * (log(plevs[a]) + log(plevs[b]))); };
+  for (int k = 0; k < nlevs; ++k) {
+    p1[k] = (k == 0) ? 2000.0 : mid(k - 1, k);
+    p2[k] = (k == nlevs - 1) ? 0.0 : mid(k + 1, k);
+  }
+  return 0;
+}
+
+// GrITAS_KxKt (gritas_kxkt.f:10-119): every rc row becomes one output grid; surface rows (kt < 0 or
+// kt in ktSurfAll, gritas_kxkt.f:133-164) number the 2-D grids, the others the 3-D grids; a (kx,kt)
+// named by several rows belongs to the last one.
+int gritas_b200_kxkt(int ktmax, int kxmax, int l2d_max, int l3d_max, int listsz, const int32_t *kt_list,
+                     const int32_t *kx_list, const int32_t *kt_surf, int n_surf, int32_t *kxkt_table,
+                     int32_t *list_2d, int32_t *list_3d, int *l2d_out, int *l3d_out) {
+  int n2 = 0, n3 = 0;
+  for (size_t e = 0; e < (size_t)kxmax * (size_t)ktmax; ++e) kxkt_table[e] = 0;
+  for (int row = 0; row < listsz; ++row) {
+    const int signed_kt = kt_list[row];
+    const int kt = signed_kt < 0 ? -signed_kt : signed_kt;
+    if (kt > ktmax) return 1;
+    if (kt < 1) return 2;
+    bool surface = signed_kt < 0;
+    for (int s = 0; s < n_surf && !surface; ++s) surface = (kt_surf[s] == signed_kt);
+    int value;
+    if (surface) {
+      if (++n2 > l2d_max) return 3;
+      if (list_2d) list_2d[n2 - 1] = row + 1;
+      value = -n2;
+    } else {
+      if (++n3 > l3d_max) return 4;
+      if (list_3d) list_3d[n3 - 1] = row + 1;
+      value = n3;
+    }
+    const int32_t *kxs = kx_list + (size_t)kxmax * (size_t)row;
+    for (int e = 0; e < kxmax && kxs[e] >= 0; ++e) {
+      if (kxs[e] > kxmax) return 5;
+      if (kxs[e] == 0) continue;  // kx = 0 would index out of bounds in the reference
+      kxkt_table[(size_t)(kxs[e] - 1) + (size_t)kxmax * (size_t)(kt - 1)] = value;
+    }
+  }
+  if (l2d_out) *l2d_out = n2;
+  if (l3d_out) *l3d_out = n3;
+  return 0;
+}
+
+// ---- utilities ------------------------------------------------------------------------------------
+void *gritas_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void gritas_b200_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+void *gritas_b200_stream(gritas_b200_handle h) { return h ? (void *)h->compute : nullptr; }
+
+int gritas_b200_set_stream(gritas_b200_handle h, void *stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->compute));
+  if (h->own_compute) CU(cudaStreamDestroy(h->compute));
+  h->compute = (cudaStream_t)stream;
+  h->own_compute = false;
+  return 0;
+}
+
+uint64_t gritas_b200_launch_count(gritas_b200_handle h) { return h ? h->launches : 0; }
+uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h) { return h ? h->h2d : 0; }
+uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h) { return h ? h->d2h : 0; }
+
+}  // extern "C"

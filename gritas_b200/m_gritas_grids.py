@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's `m_gritas_grids` interface for the gridding hot path.
+
+Same names, argument order, argument meaning and error behaviour as the Fortran module
+(reference src/Components/gritas/m_gritas_grids.f:85-101) and GrITAS_KxKt
+(src/Components/gritas/gritas_kxkt.f:10-12), sitting directly above the C ABI of
+include/gritas_b200.h -- it is what fortran/m_gritas_b200.F90 is, written in Python because
+this image has no Fortran compiler.  All arithmetic happens in libgritas_b200.so on the GPU.
+
+Differences a caller sees:
+  * the grids passed to GrITAS_Accum are NOT touched by it -- the accumulators stay in HBM and
+    the host arrays are filled by GrITAS_Norm (or get_raw) once, after the last file;
+  * gritas_perror (print + exit(7), gritas_etc.f:54-60) becomes the exception GritasPerror(code=7).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import cabi
+
+AMISS = 1.0e15        # m_gritas_grids.f:72
+LonMin = -180.0       # m_gritas_grids.f:33
+LatMin = -90.0        # m_gritas_grids.f:42
+
+
+class GritasPerror(RuntimeError):
+    """gritas_perror(msg): the reference prints msg and calls exit(7) (gritas_etc.f:54-60)."""
+
+    def __init__(self, msg, code=7, lev=None):
+        super().__init__(msg)
+        self.code = code
+        self.lev = lev
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def GrITAS_KxKt(KTMAX, KXMAX, L2D_MAX, L3D_MAX, listsz, kt_list, kx_list, ktSurfAll=(1, 2, 3)):
+    """gritas_kxkt.f:10-119.  kx_list: (KXMAX, listsz) F-order int32 with a negative terminator per
+    column, or a sequence of per-row kx sequences.  Returns (kxkt_table[KXMAX,KTMAX], list_2d, list_3d, l2d, l3d)."""
+    L = cabi.load()
+    if not isinstance(kx_list, np.ndarray):
+        rows = list(kx_list)
+        kx_arr = np.full((KXMAX, max(listsz, 1)), -1, dtype=np.int32, order="F")
+        for j, r in enumerate(rows[:listsz]):
+            kx_arr[: len(r), j] = np.asarray(r, dtype=np.int32)
+        kx_list = kx_arr
+    kx_list = np.asfortranarray(kx_list, dtype=np.int32)
+    kt_list = _i32(kt_list) if listsz else np.zeros(1, np.int32)
+    surf = _i32(ktSurfAll) if len(ktSurfAll) else np.zeros(1, np.int32)
+    table = np.zeros((KXMAX, KTMAX), dtype=np.int32, order="F")
+    l2 = np.zeros(max(L2D_MAX, 1), dtype=np.int32)
+    l3 = np.zeros(max(L3D_MAX, 1), dtype=np.int32)
+    a, b = C.c_int(0), C.c_int(0)
+    rc = L.gritas_b200_kxkt(KTMAX, KXMAX, L2D_MAX, L3D_MAX, listsz, kt_list.ctypes.data, kx_list.ctypes.data,
+                            surf.ctypes.data, len(ktSurfAll), table.ctypes.data, l2.ctypes.data, l3.ctypes.data,
+                            C.byref(a), C.byref(b))
+    if rc:
+        raise GritasPerror({1: "KxKt: invalid kt - too large", 2: "KxKt: invalid kt - negative",
+                            3: "KxKt: invalid l2d - too large", 4: "KxKt: invalid l3d - too large",
+                            5: "KxKt: invalid kx - too large"}[rc])
+    return table, l2[: a.value].copy(), l3[: b.value].copy(), a.value, b.value
+
+
+class Grids:
+    """The module state of m_gritas_grids (im, jm, km, nlevs, plevs, dLon, dLat; :24-72) plus the
+    device context that replaces the host accumulators."""
+
+    def __init__(self, im, jm, km, plevs, mode=cabi.MODE_FAST, device=-1):
+        """grids_init (m_gritas_grids.f:105-190).  plevs descending (gritas.f:1819 reverses them)."""
+        self.im, self.jm, self.km = int(im), int(jm), int(km)
+        self.plevs = _f64(plevs).copy()
+        self.nlevs = int(self.plevs.size)
+        self.dLon = 360.0 / self.im          # :128
+        self.dLat = 180.0 / (self.jm - 1)    # :129
+        self.mode = mode
+        self.device = device
+        self._h = None
+        self._sig = None
+
+    # ---- GrITAS_Pint_ (m_gritas_grids.f:217-296) -------------------------------------------
+    def GrITAS_Pint(self):
+        L = cabi.load()
+        n = self.nlevs
+        p1 = np.zeros(max(n, 1))
+        p2 = np.zeros(max(n, 1))
+        rc = L.gritas_b200_pint(n, self.plevs.ctypes.data if n else None, p1.ctypes.data, p2.ctypes.data)
+        if rc:
+            raise GritasPerror({1: "Pint: must have at least 1 vertical levels",
+                                2: "Pint: pressure levels do not decrease monotonically",
+                                3: "Pint: cannot handle 0 hPa"}[rc])
+        return p1[:n], p2[:n]
+
+    # ---- context management ---------------------------------------------------------------
+    def _ensure(self, nr, kxkt_table, p1, p2, l2d, l3d):
+        L = cabi.load()
+        table = np.asfortranarray(kxkt_table, dtype=np.int32)
+        p1, p2 = _f64(p1), _f64(p2)
+        sig = (nr, l2d, l3d, table.shape, hash(table.tobytes()), hash(p1.tobytes()), hash(p2.tobytes()))
+        if self._h is not None and sig == self._sig:
+            return
+        if self._h is not None:
+            raise ValueError("GrITAS_Accum called with tables/shapes that differ from the first call")
+        h = C.c_void_p()
+        rc = L.gritas_b200_create(C.byref(h), self.im, self.jm, self.km, self.nlevs, l2d, l3d, nr, p1.ctypes.data,
+                                  p2.ctypes.data, table.ctypes.data, table.shape[0], table.shape[1], self.mode,
+                                  self.device)
+        if rc == cabi.ERR_NR:
+            raise GritasPerror("Accum: could not handle more then 2 residuals")
+        if rc == cabi.ERR_CUDA:
+            raise RuntimeError("gritas_b200_create: no usable CUDA device (there is no CPU fallback)")
+        if rc:
+            raise ValueError(f"gritas_b200_create: rc={rc}")
+        self._h, self._sig = h, sig
+        self.nr, self.l2d, self.l3d = nr, l2d, l3d
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _err(self):
+        return cabi.load().gritas_b200_last_error(self._h).decode()
+
+    def _check(self, rc, bad=None):
+        if rc == cabi.OK:
+            return
+        if rc == cabi.ERR_LEVEL:
+            lev = bad.value if bad is not None else None
+            raise GritasPerror(f"Accum: obs level is {lev} hPa\nAccum: could not find level", 7, lev)
+        if rc == cabi.ERR_NR:
+            raise GritasPerror("Accum: could not handle more then 2 residuals")
+        raise RuntimeError(f"gritas_b200 rc={rc}: {self._err()}")
+
+    # ---- GrITAS_Accum_ (m_gritas_grids.f:307-478) ------------------------------------------
+    def GrITAS_Accum(self, lat, lon, lev, kx, kt, del_, nobs, nr, kxkt_table, p1, p2, ob_flag,
+                     l2d, bias_2d=None, rtms_2d=None, xcov_2d=None, nobs_2d=None,
+                     l3d=0, bias_3d=None, rtms_3d=None, xcov_3d=None, nobs_3d=None):
+        """Same argument list as the reference.  del_ is (nobs, nr) column-major.  ob_flag is inout
+        (int32) or None.  The grid arguments are accepted for signature parity and left untouched."""
+        self._ensure(nr, kxkt_table, p1, p2, l2d, l3d)
+        L = cabi.load()
+        bad = C.c_double(0.0)
+        if isinstance(del_, np.ndarray) and not del_.flags.f_contiguous:
+            del_ = np.asfortranarray(del_)
+        rc = L.gritas_b200_accum(self._h, int(nobs), cabi.ptr(lat, np.float64), cabi.ptr(lon, np.float64),
+                                 cabi.ptr(lev, np.float64), cabi.ptr(del_, np.float64), cabi.ptr(kx, np.int32),
+                                 cabi.ptr(kt, np.int32), cabi.ptr(ob_flag, np.int32), C.byref(bad))
+        self._check(rc, bad)
+
+    def accum_ods(self, ods, iopt=cabi.IOPT_OMF, scale_res=0, ioptn=None, t1=0, t2=-1, lona=-999.0, lonb=999.0,
+                  x_passive=7, x_pre_bad=1, kxkt_table=None, p1=None, p2=None, l2d=0, l3d=0, ob_flag_out=None):
+        """Fused gritas.f:562-587 (residual selection) + :710-739 (QC/time/lon filter) + GrITAS_Accum_
+        straight from the ODS columns (dict with lat lon lev time kt kx qcexcl omf oma [obs xvec])."""
+        nr = 2 if abs(iopt) == cabi.IOPT_OMF_OMA else 1
+        if self._h is None:
+            self._ensure(nr, kxkt_table, p1, p2, l2d, l3d)
+        L = cabi.load()
+        bad = C.c_double(0.0)
+        n = int(ods["lat"].shape[0])
+        g = lambda k, dt: cabi.ptr(ods.get(k), dt) if ods.get(k) is not None else None
+        rc = L.gritas_b200_accum_ods(self._h, n, g("lat", np.float64), g("lon", np.float64), g("lev", np.float64),
+                                     g("time", np.int32), g("kt", np.int32), g("kx", np.int32), g("qcexcl", np.int32),
+                                     g("omf", np.float64), g("oma", np.float64), g("obs", np.float64),
+                                     g("xvec", np.float64), iopt, scale_res, iopt if ioptn is None else ioptn,
+                                     t1, t2, lona, lonb, x_passive, x_pre_bad, cabi.ptr(ob_flag_out, np.int32),
+                                     C.byref(bad))
+        self._check(rc, bad)
+
+    def sync(self):
+        bad = C.c_double(0.0)
+        self._check(cabi.load().gritas_b200_sync(self._h, C.byref(bad)), bad)
+
+    def reset(self):
+        """grisas.f:285-296 zeroes the grids at every synoptic time."""
+        self._check(cabi.load().gritas_b200_reset(self._h))
+
+    # ---- GrITAS_Norm_ (m_gritas_grids.f:490-656) -------------------------------------------
+    def GrITAS_Norm(self, nr, nrmlz, l2d, bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d,
+                    l3d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d, ntresh=None):
+        if nr > 2:
+            raise GritasPerror("Accum: could not handle more then 2 residuals")  # :555 (sic)
+        if self._h is None:
+            raise RuntimeError("GrITAS_Norm before any GrITAS_Accum")
+        assert nr == self.nr and l2d == self.l2d and l3d == self.l3d
+        p = lambda a: cabi.ptr(a, np.float64)
+        rc = cabi.load().gritas_b200_norm(self._h, 1 if nrmlz else 0, -1 if ntresh is None else int(ntresh),
+                                          p(bias_2d), p(rtms_2d), p(stdv_2d), p(xcov_2d), p(nobs_2d),
+                                          p(bias_3d), p(rtms_3d), p(stdv_3d), p(xcov_3d), p(nobs_3d))
+        self._check(rc)
+
+    def get_raw(self, bias_2d, rtms_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, xcov_3d, nobs_3d):
+        p = lambda a: cabi.ptr(a, np.float64)
+        self._check(cabi.load().gritas_b200_get_raw(self._h, p(bias_2d), p(rtms_2d), p(xcov_2d), p(nobs_2d),
+                                                    p(bias_3d), p(rtms_3d), p(xcov_3d), p(nobs_3d)))
+
+    def add_raw(self, bias_2d, rtms_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, xcov_3d, nobs_3d):
+        p = lambda a: cabi.ptr(a, np.float64)
+        self._check(cabi.load().gritas_b200_add_raw(self._h, p(bias_2d), p(rtms_2d), p(xcov_2d), p(nobs_2d),
+                                                    p(bias_3d), p(rtms_3d), p(xcov_3d), p(nobs_3d)))
+
+    def alloc_grids(self, nr=None, pinned=False):
+        """Host arrays shaped like gritas.f:336-348, zero-initialised (gritas.f:352-363)."""
+        nr = self.nr if nr is None else nr
+        l2, l3 = max(self.l2d, 1), max(self.l3d, 1)
+        mk = (lambda *s: cabi.pinned_empty(s)) if pinned else (lambda *s: np.empty(s, dtype=np.float64, order="F"))
+        out = {}
+        for nm in ("bias", "rtms", "stdv", "xcov"):
+            out[nm + "_2d"] = mk(self.im, self.jm, l2, nr)
+            out[nm + "_3d"] = mk(self.im, self.jm, self.km, l3, nr)
+        out["nobs_2d"] = mk(self.im, self.jm, l2)
+        out["nobs_3d"] = mk(self.im, self.jm, self.km, l3)
+        for a in out.values():
+            a[...] = 0.0
+        return out
+
+    def norm_into(self, grids, nrmlz=True, ntresh=None):
+        g = grids
+        self.GrITAS_Norm(self.nr, nrmlz, self.l2d, g["bias_2d"] if self.l2d else None, g["rtms_2d"] if self.l2d else None,
+                         g["stdv_2d"] if self.l2d else None, g["xcov_2d"] if self.l2d else None,
+                         g["nobs_2d"] if self.l2d else None, self.l3d, g["bias_3d"] if self.l3d else None,
+                         g["rtms_3d"] if self.l3d else None, g["stdv_3d"] if self.l3d else None,
+                         g["xcov_3d"] if self.l3d else None, g["nobs_3d"] if self.l3d else None, ntresh)
+        return g
+
+    # ---- multi-GPU ------------------------------------------------------------------------
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(cabi.load().gritas_b200_comm_init(self._h, nranks, rank, buf))
+
+    def allreduce(self):
+        self._check(cabi.load().gritas_b200_allreduce(self._h))
+
+    # ---- introspection --------------------------------------------------------------------
+    def stream(self):
+        return cabi.load().gritas_b200_stream(self._h)
+
+    def counters(self):
+        L = cabi.load()
+        return dict(launches=L.gritas_b200_launch_count(self._h), h2d=L.gritas_b200_h2d_bytes(self._h),
+                    d2h=L.gritas_b200_d2h_bytes(self._h))
+
+    def close(self):
+        """GrITAS_Clean (gritas.f:2017-2026)."""
+        if self._h is not None:
+            cabi.load().gritas_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = cabi.load().gritas_b200_nccl_unique_id(buf)
+    if rc:
+        raise RuntimeError(f"gritas_b200_nccl_unique_id rc={rc}")
+    return buf.raw

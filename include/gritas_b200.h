@@ -1,0 +1,175 @@
+/*
+ * gritas_b200.h -- C ABI of the B200-native GrITAS gridding / accumulation / finalize path.
+ *
+ * This is the drop-in boundary.  The reference (GEOS-ESM/GrITAS) has no FFI; its seam is the
+ * pair of module generics GrITAS_Accum / GrITAS_Norm of m_gritas_grids
+ * (src/Components/gritas/m_gritas_grids.f:88-89), called from
+ * src/Applications/GrITAS_App/gritas.f:777-781 and 885-887 (and grisas.f:619-623, 639-642).
+ * A replacement m_gritas_grids keeps those Fortran signatures and forwards to the entry points
+ * below through ISO_C_BINDING (fortran/m_gritas_b200.F90).
+ *
+ * All arrays are caller-owned, contiguous, column-major and 1-based on the Fortran side.  Every
+ * `real` of the reference is 64-bit (FREAL8, src/Components/gritas/CMakeLists.txt:3-4), every
+ * `integer` 32-bit.  Input pointers may be pageable host, pinned host or device memory; the
+ * library detects which and stages accordingly.  No entry point ever exits the process or falls
+ * back to a CPU implementation: without a usable CUDA device gritas_b200_create fails with
+ * GRITAS_B200_ERR_CUDA.
+ */
+#ifndef GRITAS_B200_H
+#define GRITAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gritas_b200_ctx *gritas_b200_handle;
+
+/* accumulation mode (low byte of `mode`) */
+#define GRITAS_B200_MODE_FAST 0          /* warp-aggregated fp64 atomics (order not fixed, <=1e-6) */
+#define GRITAS_B200_MODE_DETERMINISTIC 1 /* stable sort by box key + in-order segment sums: bit-reproducible,
+                                            same summation order as the reference's sequential loop */
+/* flags OR-ed into `mode` */
+#define GRITAS_B200_FLAG_ASYNC 0x100     /* accum returns once inputs are consumed/staged; a level miss is
+                                            reported by the next accum/sync/norm instead */
+#define GRITAS_B200_FLAG_NO_AGGREGATE 0x200 /* fast mode: skip the __match_any_sync warp aggregation */
+#define GRITAS_B200_FLAG_HOLD_INPUTS 0x400  /* with ASYNC: the caller keeps pinned input arrays valid until the
+                                            next sync/norm, so accum does not even wait for the H2D copies */
+
+/* return codes */
+#define GRITAS_B200_OK 0
+#define GRITAS_B200_ERR_LEVEL 7   /* 'Accum: could not find level' -- the reference exits with 7
+                                     (m_gritas_grids.f:458-459 -> gritas_etc.f:54-60) */
+#define GRITAS_B200_ERR_NR 8      /* 'could not handle more then 2 residuals' (m_gritas_grids.f:395, 555) */
+#define GRITAS_B200_ERR_CUDA (-1) /* CUDA failure or no device; see gritas_b200_last_error */
+#define GRITAS_B200_ERR_ARG (-2)  /* bad argument */
+#define GRITAS_B200_ERR_NCCL (-3) /* NCCL not loadable / NCCL failure */
+
+/* Residual selection of the fused ODS entry (gritas.f:562-587).  |iopt| as in gritas.f:1408-1481. */
+#define GRITAS_B200_IOPT_OMF 1
+#define GRITAS_B200_IOPT_OMA 3
+#define GRITAS_B200_IOPT_OMF_OMA 101 /* nr=2: del(:,1)=omf, del(:,2)=oma -- the reference's two runs
+                                        (-omf, -oma; GrITAS_Proc/build-yaml.py.in:58) in one pass */
+
+/*
+ * Replaces: module state of m_gritas_grids (m_gritas_grids.f:24-72, init_ :105-190), the grid
+ * allocation + zeroing of gritas.f:336-363, and the table arguments of GrITAS_Accum_
+ * (m_gritas_grids.f:307-311).  dLon = 360/im, dLat = 180/(jm-1), LonMin = -180, LatMin = -90 are
+ * derived exactly as m_gritas_grids.f:128-129, 33, 42.
+ *   km          allocated vertical dimension of the 3-D grids (gritas.f:1885 sets km = nlevs)
+ *   p1,p2       level intervals from GrITAS_Pint (m_gritas_grids.f:217-296), nlevs entries
+ *   kxkt_table  (kxmax, ktmax) column-major: +l upper-air grid l, -l surface grid l, 0 unwanted
+ *               (gritas_kxkt.f:105)
+ *   nr          number of residual columns, 1..3 (3 = three-corner hat, xcov untouched)
+ *   device      CUDA device ordinal, or -1 for LOCAL_RANK (env) / current device
+ */
+int gritas_b200_create(gritas_b200_handle *h, int im, int jm, int km, int nlevs, int l2d, int l3d, int nr,
+                       const double *p1, const double *p2, const int32_t *kxkt_table, int kxmax, int ktmax,
+                       int mode, int device);
+
+/*
+ * Host-side table builders of the path (pure host code, no device needed), for callers that do not
+ * keep the Fortran originals:
+ *   gritas_b200_pint  = GrITAS_Pint_ (m_gritas_grids.f:217-296): plevs (descending, hPa) -> p1, p2.
+ *       returns 0, or 1 'must have at least 1 vertical levels', 2 'pressure levels do not decrease
+ *       monotonically', 3 'cannot handle 0 hPa' (the three gritas_perror cases).
+ *   gritas_b200_kxkt  = GrITAS_KxKt (gritas_kxkt.f:10-119): kt_list[listsz], kx_list (kxmax, listsz)
+ *       column-major with a negative terminator per column, kt_surf[n_surf] = m_odsmeta::ktSurfAll ->
+ *       kxkt_table (kxmax, ktmax), list_2d, list_3d, l2d, l3d.  returns 0, or 1 kt too large, 2 kt < 1,
+ *       3 l2d too large, 4 l3d too large, 5 kx too large.
+ */
+int gritas_b200_pint(int nlevs, const double *plevs, double *p1, double *p2);
+int gritas_b200_kxkt(int ktmax, int kxmax, int l2d_max, int l3d_max, int listsz, const int32_t *kt_list,
+                     const int32_t *kx_list, const int32_t *kt_surf, int n_surf, int32_t *kxkt_table,
+                     int32_t *list_2d, int32_t *list_3d, int *l2d, int *l3d);
+
+/* Replaces GrITAS_Clean's deallocation of the grids (gritas.f:2017-2026). */
+void gritas_b200_destroy(gritas_b200_handle h);
+
+/*
+ * Replaces GrITAS_Accum_ (m_gritas_grids.f:307-478), same argument meaning:
+ *   del      (nobs, nr) column-major, leading dimension nobs
+ *   ob_flag  inout, may be NULL (= all zero on input, nothing written back): nonzero on input
+ *            rejects the observation; set to 1 on output when (kx,kt) is not in the table
+ *   bad_lev  out, may be NULL: the offending level on GRITAS_B200_ERR_LEVEL (what the reference
+ *            prints in 'Accum: obs level is ... hPa')
+ * The grids live on the device and are only written to host arrays by _norm / _get_raw.
+ */
+int gritas_b200_accum(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
+                      const double *del, const int32_t *kx, const int32_t *kt, int32_t *ob_flag, double *bad_lev);
+
+/*
+ * Fused entry: residual selection (gritas.f:562-587, iopt above, scale_res 0..3), the QC / time /
+ * longitude filter (gritas.f:710-739) and GrITAS_Accum_ in one kernel, straight from the ODS
+ * columns.  time may be NULL when t2 < t1 (no time window); obs/xvec may be NULL when
+ * scale_res == 0; oma may be NULL for IOPT_OMF.  ioptn > 0 keeps passive data (gritas.f:713-715).
+ * x_passive / x_pre_bad are m_odsmeta constants (not in the reference tree), passed by the caller.
+ * ob_flag_out (may be NULL) receives the flags GrITAS_Accum_ would leave behind.
+ */
+int gritas_b200_accum_ods(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
+                          const int32_t *time, const int32_t *kt, const int32_t *kx, const int32_t *qcexcl,
+                          const double *omf, const double *oma, const double *obs, const double *xvec,
+                          int iopt, int scale_res, int ioptn, int t1, int t2, double lona, double lonb,
+                          int x_passive, int x_pre_bad, int32_t *ob_flag_out, double *bad_lev);
+
+/* Wait for all queued work; returns a pending GRITAS_B200_ERR_LEVEL (and its level) if any. */
+int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
+
+/* Zero the device grids (grisas.f:285-296 zeroes them every synoptic time). */
+int gritas_b200_reset(gritas_b200_handle h);
+
+/*
+ * Replaces GrITAS_Norm_ (m_gritas_grids.f:490-656): finalizes on the device and writes the
+ * caller's arrays: bias (mean), rtms (root mean square), stdv, xcov(...,1) = <xy>,
+ * xcov(...,nx) = covariance, nobs.  Shapes: *_2d (im,jm,l2d,nr), nobs_2d (im,jm,l2d),
+ * *_3d (im,jm,km,l3d,nr), nobs_3d (im,jm,km,l3d).  Any pointer may be NULL (not wanted).
+ * ntresh < 0 means "absent" (gritas.f:885-887 passes none).  In a multi-rank job call
+ * gritas_b200_allreduce first.  The device accumulators are left untouched (Norm can be repeated).
+ */
+int gritas_b200_norm(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d, double *stdv_2d,
+                     double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *stdv_3d,
+                     double *xcov_3d, double *nobs_3d);
+
+/* Same finalize, results left in device memory (for callers that post-process on the GPU and for
+ * timing the kernel without the D2H copy).  Pointers stay valid until the next norm/destroy. */
+int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **bias_2d,
+                            const double **rtms_2d, const double **stdv_2d, const double **xcov_2d,
+                            const double **nobs_2d, const double **bias_3d, const double **rtms_3d,
+                            const double **stdv_3d, const double **xcov_3d, const double **nobs_3d);
+
+/* The un-normalised sums in the reference's layout (what the host arrays hold between Accum and
+ * Norm: gritas.f:812-818, -nonorm gritas.f:1508-1509).  xcov_* receive slot 1 only. */
+int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, double *xcov_2d, double *nobs_2d,
+                        double *bias_3d, double *rtms_3d, double *xcov_3d, double *nobs_3d);
+
+/* Adds caller-held un-normalised sums into the device accumulators (resuming from -nonorm output,
+ * or honouring host grids that were not zero on the first Accum). */
+int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const double *rtms_2d, const double *xcov_2d,
+                        const double *nobs_2d, const double *bias_3d, const double *rtms_3d, const double *xcov_3d,
+                        const double *nobs_3d);
+
+/* Multi-GPU (one process per GPU): partial count / sum / sum-of-squares grids are summed over
+ * all ranks with one NCCL all-reduce before _norm.  The reference is single-process; this is new. */
+int gritas_b200_nccl_unique_id(void *id128);  /* rank 0 fills 128 bytes; broadcast them */
+int gritas_b200_comm_init(gritas_b200_handle h, int nranks, int rank, const void *id128);
+int gritas_b200_allreduce(gritas_b200_handle h);
+
+/* Pinned host memory for the caller's column arrays (direct DMA, no staging copy). */
+void *gritas_b200_host_alloc(size_t bytes);
+void gritas_b200_host_free(void *p);
+
+/* Introspection. */
+const char *gritas_b200_last_error(gritas_b200_handle h);
+void *gritas_b200_stream(gritas_b200_handle h);              /* cudaStream_t of the compute stream */
+int gritas_b200_set_stream(gritas_b200_handle h, void *stream); /* run on a caller-owned stream */
+uint64_t gritas_b200_launch_count(gritas_b200_handle h);     /* kernels launched so far */
+uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h);        /* bytes copied host->device so far */
+uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h);        /* bytes copied device->host so far */
+int gritas_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRITAS_B200_H */

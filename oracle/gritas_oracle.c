@@ -1,0 +1,448 @@
+/*
+ * gritas_oracle.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement of the GrITAS gridding hot path.
+ *
+ * This file is the checker ("oracle") for gritas_b200.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may build, load or call it.  The product
+ * (gritas_b200/, include/) never links against or falls back to anything in oracle/.
+ *
+ * PARITY UNPINNED: the reference (GEOS-ESM/GrITAS) ships no tests, golden vectors or sample
+ * data for this path and cannot be built here (no Fortran compiler; GMAO_Shared / ESMA_cmake
+ * are un-vendored externals).  The restatement below follows the reference source literally,
+ * one routine per reference routine, and is cross-checked against an independently written
+ * numpy twin (oracle/oracle_np.py) and the known-answer tests derived from the source
+ * (SURVEY.md section 4).  All citations are relative to /root/reference/.
+ *
+ * Conventions kept from the reference build:
+ *   - every `real` is 64-bit (FREAL8: src/Components/gritas/CMakeLists.txt:3-4), `integer` is
+ *     32-bit;
+ *   - arrays are column-major and 1-based (macros below);
+ *   - Fortran NINT rounds half away from zero (lround), not to even;
+ *   - compile with -ffp-contract=off so `rtms + del*del` is a multiply then an add.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_AMISS 1.0e15  /* m_gritas_grids.f:72 */
+#define ORC_LONMIN (-180.0) /* m_gritas_grids.f:33 */
+#define ORC_LATMIN (-90.0)  /* m_gritas_grids.f:42 */
+
+/* Fortran NINT for a 64-bit real into a default integer.  In range this is lround(); out of
+ * range (and NaN) is undefined in Fortran -- we pin it to saturation so the result is the same on
+ * every platform (NaN -> most negative, like the x86 "integer indefinite"). */
+static long orc_nint(double x) {
+  if (!(x == x)) return (long)INT32_MIN;
+  if (x >= 2147483647.0) return (long)INT32_MAX;
+  if (x <= -2147483648.0) return (long)INT32_MIN;
+  return lround(x);
+}
+
+/* m_gritas_grids.f:128-129 (init_): mesh sizes from the grid dimensions. */
+void orc_grid_init(int im, int jm, double *dlon, double *dlat) {
+  *dlon = 360.0 / (double)im;
+  *dlat = 180.0 / (double)(jm - 1);
+}
+
+/* m_gritas_grids.f:217-296 (GrITAS_Pint_).  Returns 0, or the gritas_perror case:
+ * 1 = nlevs<=0, 2 = not monotonically decreasing, 3 = last level is 0 hPa. */
+int orc_pint(int nlevs, const double *plevs, double *p1, double *p2) {
+  int k;
+  if (nlevs <= 0) return 1;                       /* :244-245 */
+  if (nlevs == 1) {                               /* :249-256 */
+    p1[0] = plevs[0];
+    p2[0] = plevs[0] - 0.1;
+    return 0;
+  }
+  for (k = 0; k < nlevs - 1; ++k)                 /* :261-264 */
+    if (plevs[k] <= plevs[k + 1]) return 2;
+  if (plevs[nlevs - 1] == 0.0) return 3;          /* :266-267 */
+  p1[0] = 2000.0;                                 /* :270 */
+  p2[0] = exp(0.5 * (log(plevs[1]) + log(plevs[0])));              /* :271 */
+  for (k = 1; k < nlevs - 1; ++k) {               /* :273-276 */
+    p1[k] = exp(0.5 * (log(plevs[k - 1]) + log(plevs[k])));
+    p2[k] = exp(0.5 * (log(plevs[k + 1]) + log(plevs[k])));
+  }
+  k = nlevs - 1;                                  /* :278-280 */
+  p1[k] = exp(0.5 * (log(plevs[k - 1]) + log(plevs[k])));
+  p2[k] = 0.0;
+  return 0;
+}
+
+/* gritas_kxkt.f:133-164 (is_surface): kt<0 or kt in ktSurfAll (m_odsmeta, not in tree: the
+ * list is passed in). */
+static int orc_is_surface(int kt, const int *kt_surf, int n_surf) {
+  int i;
+  if (kt < 0) return 1;
+  for (i = 0; i < n_surf; ++i)
+    if (kt_surf[i] == kt) return 1;
+  return 0;
+}
+
+/* gritas_kxkt.f:10-119 (GrITAS_KxKt).  kx_list is (kxmax, listsz) column-major, terminated by a
+ * negative entry per column.  kxkt_table is (kxmax, ktmax) column-major.
+ * Returns 0 or: 1 kt too large, 2 kt<1, 3 l2d too large, 4 l3d too large, 5 kx too large.
+ * A kx of 0 would index out of bounds in the reference; it is skipped here. */
+int orc_kxkt(int ktmax, int kxmax, int l2d_max, int l3d_max, int listsz, const int *kt_list,
+             const int *kx_list, const int *kt_surf, int n_surf, int *kxkt_table, int *list_2d,
+             int *list_3d, int *l2d_out, int *l3d_out) {
+  int i, j, kx, kt, l, l2d = 0, l3d = 0;
+  memset(kxkt_table, 0, sizeof(int) * (size_t)kxmax * (size_t)ktmax);   /* :73-77 */
+  for (j = 1; j <= listsz; ++j) {                                        /* :81 */
+    kt = abs(kt_list[j - 1]);
+    if (kt > ktmax) return 1;
+    if (kt < 1) return 2;
+    if (orc_is_surface(kt_list[j - 1], kt_surf, n_surf)) {               /* :87-92 */
+      l2d++;
+      if (l2d > l2d_max) return 3;
+      l = -l2d;
+      list_2d[l2d - 1] = j;
+    } else {                                                             /* :93-98 */
+      l3d++;
+      if (l3d > l3d_max) return 4;
+      l = l3d;
+      list_3d[l3d - 1] = j;
+    }
+    for (i = 1; i <= kxmax; ++i) {                                       /* :100-106 */
+      kx = kx_list[(size_t)(i - 1) + (size_t)kxmax * (size_t)(j - 1)];
+      if (kx < 0) break;
+      if (kx > kxmax) return 5;
+      if (kx == 0) continue;
+      kxkt_table[(size_t)(kx - 1) + (size_t)kxmax * (size_t)(kt - 1)] = l; /* last writer wins */
+    }
+  }
+  *l2d_out = l2d;
+  *l3d_out = l3d;
+  return 0;
+}
+
+/* Stable index merge sort on a double key (the role of m_MergeSorts::IndexSort, GMAO_mpeu --
+ * not in tree; gritas.f:500-508 only relies on "stable, ascending").  `is` holds 0-based
+ * indices into key. */
+static void orc_index_sort(int n, int *is, const double *key, int *tmp) {
+  int width, lo;
+  for (width = 1; width < n; width *= 2) {
+    for (lo = 0; lo < n; lo += 2 * width) {
+      int mid = lo + width < n ? lo + width : n;
+      int hi = lo + 2 * width < n ? lo + 2 * width : n;
+      int a = lo, b = mid, o = lo;
+      while (a < mid && b < hi) {
+        if (key[is[b]] < key[is[a]]) tmp[o++] = is[b++]; /* strict: ties keep left first */
+        else tmp[o++] = is[a++];
+      }
+      while (a < mid) tmp[o++] = is[a++];
+      while (b < hi) tmp[o++] = is[b++];
+    }
+    memcpy(is, tmp, sizeof(int) * (size_t)n);
+  }
+}
+
+/* gritas.f:499-508: IndexSet then 8 successive stable ascending sorts
+ * (qcexcl, lat, lon, lev, time, kt, ks, kx).  Output `is` is 0-based. */
+int orc_presort(int nobs, const int *qcexcl, const double *lat, const double *lon,
+                const double *lev, const int *time, const int *kt, const int *ks, const int *kx,
+                int *is) {
+  int i, p;
+  int *tmp = (int *)malloc(sizeof(int) * (size_t)(nobs > 0 ? nobs : 1));
+  double *key = (double *)malloc(sizeof(double) * (size_t)(nobs > 0 ? nobs : 1));
+  if (!tmp || !key) { free(tmp); free(key); return 1; }
+  for (i = 0; i < nobs; ++i) is[i] = i;                                  /* IndexSet */
+  for (p = 0; p < 8; ++p) {
+    const int *ik = NULL;
+    const double *dk = NULL;
+    switch (p) {
+      case 0: ik = qcexcl; break;
+      case 1: dk = lat; break;
+      case 2: dk = lon; break;
+      case 3: dk = lev; break;
+      case 4: ik = time; break;
+      case 5: ik = kt; break;
+      case 6: ik = ks; break;
+      default: ik = kx; break;
+    }
+    if (ik) { for (i = 0; i < nobs; ++i) key[i] = (double)ik[i]; dk = key; }
+    orc_index_sort(nobs, is, dk, tmp);
+  }
+  free(tmp);
+  free(key);
+  return 0;
+}
+
+/* gritas.f:510-523: column gathers through the sort index. */
+void orc_gather_f64(int nobs, const int *is, const double *src, double *dst) {
+  int i;
+  for (i = 0; i < nobs; ++i) dst[i] = src[is[i]];
+}
+void orc_gather_i32(int nobs, const int *is, const int *src, int *dst) {
+  int i;
+  for (i = 0; i < nobs; ++i) dst[i] = src[is[i]];
+}
+
+/* gritas.f:562-587: residual selection for iopt 0/1 (omf) and 2/3 (oma), with the optional
+ * scale_res division.  |iopt| is used.  del is (nobs, nr) column-major; only column 1 is set
+ * here (column 2 is set by the caller in the omf+oma one-pass mode, which is two reference
+ * runs fused).  Returns 1 for an iopt this restatement does not cover. */
+int orc_select_del(int nobs, int iopt, int scale_res, const double *omf, const double *oma,
+                   const double *obs, const double *xvec, double *del) {
+  int i, a = abs(iopt);
+  const double *src;
+  if (a == 0 || a == 1) src = omf;
+  else if (a == 2 || a == 3) src = oma;
+  else return 1;
+  for (i = 0; i < nobs; ++i) {
+    double d = src[i];
+    if (scale_res == 1) d = d / sqrt(xvec[i]);
+    if (scale_res == 2) d = d / obs[i];
+    if (scale_res == 3) d = d / (obs[i] - omf[i]);
+    del[i] = d;
+  }
+  return 0;
+}
+
+/* gritas.f:710-739: QC / time / longitude filter producing ob_flag (0 keep, 1 drop).  The
+ * caller only runs it when iopt is odd (always the case from the CLI). */
+void orc_filter(int nobs, const int *qcexcl, const int *time, const double *lon, int ioptn,
+                int t1, int t2, double lona, double lonb, int x_passive, int x_pre_bad,
+                int *ob_flag) {
+  int i;
+  for (i = 0; i < nobs; ++i) {
+    int iampassive = qcexcl[i] == x_passive || qcexcl[i] == x_pre_bad;
+    int iwantpassive = ioptn > 0 && iampassive;
+    int timeselect, lonselect;
+    if (t2 < t1) timeselect = 1;
+    else if (t1 <= time[i] && time[i] <= t2) timeselect = 1;
+    else timeselect = 0;
+    if (lona < -180.0 && lonb > 180.0) lonselect = 1;
+    else if (lona <= lon[i] && lon[i] <= lonb) lonselect = 1;
+    else lonselect = 0;
+    if (timeselect && lonselect && (qcexcl[i] == 0 || iwantpassive)) ob_flag[i] = 0;
+    else ob_flag[i] = 1;
+  }
+}
+
+/* Column-major 1-based offsets (m_gritas_grids.f:346-355). */
+#define IX2(i, j, l, ir) \
+  ((size_t)((i)-1) + (size_t)im * ((size_t)((j)-1) + (size_t)jm * ((size_t)((l)-1) + (size_t)l2d * (size_t)((ir)-1))))
+#define IX3(i, j, k, l, ir)                                                               \
+  ((size_t)((i)-1) +                                                                      \
+   (size_t)im * ((size_t)((j)-1) +                                                        \
+                 (size_t)jm * ((size_t)((k)-1) +                                          \
+                               (size_t)km * ((size_t)((l)-1) + (size_t)l3d * (size_t)((ir)-1)))))
+
+/* m_gritas_grids.f:307-478 (GrITAS_Accum_).  del is (nobs, nr) column-major; kxkt_table is
+ * (kxmax, ktmax) column-major.  xcov_* are addressed as (im,jm,l2d) / (im,jm,km,l3d), i.e. slot 1
+ * of the caller's 4-D/5-D array (gritas.f:780-781).
+ *
+ * Returns 0; 7 on "could not find level" (the reference prints the level and exits with 7,
+ * m_gritas_grids.f:458-459 -> gritas_etc.f:54-60): *bad_lev holds the level and *bad_n the
+ * 0-based observation, and accumulation stops there exactly as the reference's would;
+ * 8 for nr>3 (:395-396).
+ * A (kx,kt) outside the table is undefined behaviour in the reference (:409, no bounds check);
+ * here it is treated as "not in table". */
+int orc_accum(int im, int jm, int km, int nlevs, int nobs, int nr, const double *lat,
+              const double *lon, const double *lev, const int *kx, const int *kt,
+              const double *del, const int *kxkt_table, int kxmax, int ktmax, const double *p1,
+              const double *p2, int *ob_flag, int l2d, double *bias_2d, double *rtms_2d,
+              double *xcov_2d, double *nobs_2d, int l3d, double *bias_3d, double *rtms_3d,
+              double *xcov_3d, double *nobs_3d, double *bad_lev, int *bad_n) {
+  int n, i, j, k, kk, nx, l, ir, surface_var;
+  double dlon, dlat;
+  long ii, jj;
+  orc_grid_init(im, jm, &dlon, &dlat);
+  if (nr > 3) return 8;                                                  /* :395-396 */
+  nx = (nr == 3) ? 0 : (nr > 1 ? nr : 1);                                /* :397-401 */
+
+  for (n = 0; n < nobs; ++n) {                                           /* :405 */
+    if (ob_flag[n] != 0) continue;                                       /* :406-407 */
+    if (kx[n] < 1 || kx[n] > kxmax || kt[n] < 1 || kt[n] > ktmax) l = 0;
+    else l = kxkt_table[(size_t)(kx[n] - 1) + (size_t)kxmax * (size_t)(kt[n] - 1)]; /* :409 */
+    surface_var = l < 0;                                                 /* :410 */
+    l = abs(l);                                                          /* :411 */
+    if (l <= 0) {                                                        /* :413-416 */
+      ob_flag[n] = 1;
+      continue;
+    }
+    ii = 1 + orc_nint((lon[n] - ORC_LONMIN) / dlon);                     /* :420 */
+    if (ii == (long)im + 1) ii = 1;                                      /* :421 */
+    if (ii == 0) ii = im;                                                /* :422 */
+    jj = 1 + orc_nint((lat[n] - ORC_LATMIN) / dlat);                     /* :423 */
+    if (ii < 1) ii = 1;                                                  /* :425 */
+    if (ii > im) ii = im;
+    if (jj < 1) jj = 1;                                                  /* :426 */
+    if (jj > jm) jj = jm;
+    i = (int)ii;
+    j = (int)jj;
+
+    if (surface_var) {                                                   /* :432-441 */
+      for (ir = 1; ir <= nr; ++ir) {
+        double d = del[(size_t)n + (size_t)nobs * (size_t)(ir - 1)];
+        bias_2d[IX2(i, j, l, ir)] = bias_2d[IX2(i, j, l, ir)] + d;
+        rtms_2d[IX2(i, j, l, ir)] = rtms_2d[IX2(i, j, l, ir)] + d * d;
+      }
+      if (nx > 0)
+        xcov_2d[IX2(i, j, l, 1)] =
+            xcov_2d[IX2(i, j, l, 1)] + del[n] * del[(size_t)n + (size_t)nobs * (size_t)(nx - 1)];
+      nobs_2d[IX2(i, j, l, 1)] = nobs_2d[IX2(i, j, l, 1)] + 1.0;
+    } else {
+      k = 0;
+      for (kk = 1; kk <= nlevs; ++kk) {                                  /* :450-456 */
+        if (lev[n] <= p1[kk - 1] && lev[n] > p2[kk - 1]) {
+          k = kk;
+          break;
+        }
+      }
+      if (k == 0) {                                                      /* :458-459 */
+        if (bad_lev) *bad_lev = lev[n];
+        if (bad_n) *bad_n = n;
+        return 7;
+      }
+      for (ir = 1; ir <= nr; ++ir) {                                     /* :465-468 */
+        double d = del[(size_t)n + (size_t)nobs * (size_t)(ir - 1)];
+        bias_3d[IX3(i, j, k, l, ir)] = bias_3d[IX3(i, j, k, l, ir)] + d;
+        rtms_3d[IX3(i, j, k, l, ir)] = rtms_3d[IX3(i, j, k, l, ir)] + d * d;
+      }
+      if (nx > 0)                                                        /* :469 */
+        xcov_3d[IX3(i, j, k, l, 1)] =
+            xcov_3d[IX3(i, j, k, l, 1)] + del[n] * del[(size_t)n + (size_t)nobs * (size_t)(nx - 1)];
+      nobs_3d[IX3(i, j, k, l, 1)] = nobs_3d[IX3(i, j, k, l, 1)] + 1.0;   /* :470 */
+    }
+  }
+  return 0;
+}
+
+/* Box assignment only (the K1 half of Accum, m_gritas_grids.f:405-461), for index parity tests:
+ * key[n] = -1 rejected on entry, -2 not in table, -3 level miss, else the 0-based column-major
+ * offset into nobs_3d (upper air) or -(4 + offset into nobs_2d) (surface). */
+void orc_box_keys(int im, int jm, int km, int nlevs, int nobs, const double *lat,
+                  const double *lon, const double *lev, const int *kx, const int *kt,
+                  const int *kxkt_table, int kxmax, int ktmax, const double *p1, const double *p2,
+                  const int *ob_flag, int l2d, int l3d, int64_t *key) {
+  int n, kk, k, l, surface_var;
+  long ii, jj;
+  double dlon, dlat;
+  (void)l2d; (void)l3d;
+  orc_grid_init(im, jm, &dlon, &dlat);
+  for (n = 0; n < nobs; ++n) {
+    if (ob_flag[n] != 0) { key[n] = -1; continue; }
+    if (kx[n] < 1 || kx[n] > kxmax || kt[n] < 1 || kt[n] > ktmax) l = 0;
+    else l = kxkt_table[(size_t)(kx[n] - 1) + (size_t)kxmax * (size_t)(kt[n] - 1)];
+    surface_var = l < 0;
+    l = abs(l);
+    if (l <= 0) { key[n] = -2; continue; }
+    ii = 1 + orc_nint((lon[n] - ORC_LONMIN) / dlon);
+    if (ii == (long)im + 1) ii = 1;
+    if (ii == 0) ii = im;
+    jj = 1 + orc_nint((lat[n] - ORC_LATMIN) / dlat);
+    if (ii < 1) ii = 1;
+    if (ii > im) ii = im;
+    if (jj < 1) jj = 1;
+    if (jj > jm) jj = jm;
+    if (surface_var) {
+      key[n] = -(4 + (int64_t)((ii - 1) + (int64_t)im * ((jj - 1) + (int64_t)jm * (l - 1))));
+    } else {
+      k = 0;
+      for (kk = 1; kk <= nlevs; ++kk)
+        if (lev[n] <= p1[kk - 1] && lev[n] > p2[kk - 1]) { k = kk; break; }
+      if (k == 0) { key[n] = -3; continue; }
+      key[n] = (int64_t)(ii - 1) +
+               (int64_t)im * ((jj - 1) + (int64_t)jm * ((k - 1) + (int64_t)km * (l - 1)));
+    }
+  }
+}
+
+/* m_gritas_grids.f:490-656 (GrITAS_Norm_).  xcov_* here are the full (…, nr) arrays.
+ * `m` is an INTEGER in the reference (:548): m = n when nrmlz, else stays 1, so that
+ * m*tmp/(m-1) divides by zero under -nonorm exactly as the reference does.
+ * `tmp`/`xtmp` are locals that persist across boxes in the reference; in the 3-D n==1 branch
+ * (:642-644) with ntresh>1 they are read without having been set for this box, so the stale
+ * values of the last box that passed the threshold are used (uninitialised before the first
+ * such box: pinned to 0 here).  Returns 8 for nr>2 (:555). */
+int orc_norm(int im, int jm, int km, int nlevs, int nr, int nrmlz, int l2d, double *bias_2d,
+             double *rtms_2d, double *stdv_2d, double *xcov_2d, double *nobs_2d, int l3d,
+             double *bias_3d, double *rtms_3d, double *stdv_3d, double *xcov_3d, double *nobs_3d,
+             int ntresh) {
+  int i, j, k, l, m, nx, ir;
+  double tmp[2] = {0.0, 0.0}, xtmp = 0.0, n;
+  if (nr > 2) return 8;
+  nx = nr > 1 ? nr : 1;                                                  /* :556 */
+
+  m = 1;                                                                 /* :566 */
+  for (l = 1; l <= l2d; ++l)
+    for (j = 1; j <= jm; ++j)
+      for (i = 1; i <= im; ++i) {
+        n = nobs_2d[IX2(i, j, l, 1)];                                    /* :571 */
+        if (nrmlz) m = (int)n;                                           /* :572 */
+        if (n > 0.0 && n >= (double)ntresh) {                            /* :573-582 */
+          for (ir = 1; ir <= nr; ++ir) {
+            bias_2d[IX2(i, j, l, ir)] = bias_2d[IX2(i, j, l, ir)] / (double)m;
+            tmp[ir - 1] = rtms_2d[IX2(i, j, l, ir)] / (double)m;
+            rtms_2d[IX2(i, j, l, ir)] = sqrt(tmp[ir - 1]);
+            tmp[ir - 1] = fabs(tmp[ir - 1] - bias_2d[IX2(i, j, l, ir)] * bias_2d[IX2(i, j, l, ir)]);
+          }
+          xtmp = xcov_2d[IX2(i, j, l, 1)] / (double)m;
+          xcov_2d[IX2(i, j, l, 1)] = xtmp;
+          xtmp = xtmp - bias_2d[IX2(i, j, l, 1)] * bias_2d[IX2(i, j, l, nx)];
+        } else {                                                         /* :583-589 */
+          for (ir = 1; ir <= nr; ++ir) {
+            bias_2d[IX2(i, j, l, ir)] = ORC_AMISS;
+            rtms_2d[IX2(i, j, l, ir)] = ORC_AMISS;
+          }
+          xcov_2d[IX2(i, j, l, 1)] = ORC_AMISS;
+        }
+        if (n > 1.0 && n >= (double)ntresh) {                            /* :591-596 */
+          for (ir = 1; ir <= nr; ++ir)
+            stdv_2d[IX2(i, j, l, ir)] = sqrt((double)m * tmp[ir - 1] / (double)(m - 1));
+          xcov_2d[IX2(i, j, l, nx)] = (double)m * xtmp / (double)(m - 1);
+        } else {                                                         /* :597-601 */
+          for (ir = 1; ir <= nr; ++ir) stdv_2d[IX2(i, j, l, ir)] = ORC_AMISS;
+          xcov_2d[IX2(i, j, l, nx)] = ORC_AMISS;
+        }
+      }
+
+  if (nlevs < 2) return 0;                                               /* :607 */
+
+  m = 1;                                                                 /* :612 */
+  for (l = 1; l <= l3d; ++l)
+    for (k = 1; k <= nlevs; ++k)
+      for (j = 1; j <= jm; ++j)
+        for (i = 1; i <= im; ++i) {
+          n = nobs_3d[IX3(i, j, k, l, 1)];                               /* :618 */
+          if (nrmlz) m = (int)n;                                         /* :619 */
+          if (n > 0.0 && n >= (double)ntresh) {                          /* :620-629 */
+            for (ir = 1; ir <= nr; ++ir) {
+              bias_3d[IX3(i, j, k, l, ir)] = bias_3d[IX3(i, j, k, l, ir)] / (double)m;
+              tmp[ir - 1] = rtms_3d[IX3(i, j, k, l, ir)] / (double)m;
+              rtms_3d[IX3(i, j, k, l, ir)] = sqrt(tmp[ir - 1]);
+              tmp[ir - 1] =
+                  fabs(tmp[ir - 1] - bias_3d[IX3(i, j, k, l, ir)] * bias_3d[IX3(i, j, k, l, ir)]);
+            }
+            xtmp = xcov_3d[IX3(i, j, k, l, 1)] / (double)m;
+            xcov_3d[IX3(i, j, k, l, 1)] = xtmp;
+            xtmp = xtmp - bias_3d[IX3(i, j, k, l, 1)] * bias_3d[IX3(i, j, k, l, nx)];
+          } else {                                                       /* :630-636 */
+            for (ir = 1; ir <= nr; ++ir) {
+              bias_3d[IX3(i, j, k, l, ir)] = ORC_AMISS;
+              rtms_3d[IX3(i, j, k, l, ir)] = ORC_AMISS;
+            }
+            xcov_3d[IX3(i, j, k, l, 1)] = ORC_AMISS;
+          }
+          if (n > 1.0 && n >= (double)ntresh) {                          /* :638-640 */
+            for (ir = 1; ir <= nr; ++ir)
+              stdv_3d[IX3(i, j, k, l, ir)] = sqrt((double)m * tmp[ir - 1] / (double)(m - 1));
+            xcov_3d[IX3(i, j, k, l, nx)] = (double)m * xtmp / (double)(m - 1);
+          } else if (n == 1.0) {                                         /* :642-644 */
+            for (ir = 1; ir <= nr; ++ir) stdv_3d[IX3(i, j, k, l, ir)] = sqrt(tmp[ir - 1]);
+            xcov_3d[IX3(i, j, k, l, nx)] = xtmp;
+          } else {                                                       /* :646-647 */
+            for (ir = 1; ir <= nr; ++ir) stdv_3d[IX3(i, j, k, l, ir)] = ORC_AMISS;
+            xcov_3d[IX3(i, j, k, l, nx)] = ORC_AMISS;
+          }
+        }
+  return 0;
+}
+
+/* gritas.f:1002-1003: nobs / nredundant (ensemble files valid at the same time). */
+void orc_div_nredundant(size_t n, double *nobs_grid, int nredundant) {
+  size_t i;
+  for (i = 0; i < n; ++i) nobs_grid[i] = nobs_grid[i] / (double)nredundant;
+}

@@ -1,0 +1,215 @@
+"""ctypes front-end of the CPU oracle (oracle/gritas_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Never imported by the gritas_b200 package.
+PARITY UNPINNED (see gritas_oracle.c header): the reference ships no golden vectors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libgritas_oracle.so")
+
+AMISS = 1.0e15  # m_gritas_grids.f:72
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="F_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="F_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="F_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "gritas_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_pint.argtypes = [C.c_int, _f64p, _f64p, _f64p]
+        L.orc_pint.restype = C.c_int
+        L.orc_kxkt.argtypes = [C.c_int] * 5 + [_i32p, _i32p, _i32p, C.c_int, _i32p, _i32p, _i32p,
+                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_kxkt.restype = C.c_int
+        L.orc_presort.argtypes = [C.c_int, _i32p, _f64p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p, _i32p]
+        L.orc_presort.restype = C.c_int
+        L.orc_select_del.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p]
+        L.orc_select_del.restype = C.c_int
+        L.orc_filter.argtypes = [C.c_int, _i32p, _i32p, _f64p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_double, C.c_int, C.c_int, _i32p]
+        L.orc_filter.restype = None
+        L.orc_accum.argtypes = ([C.c_int] * 6 + [_f64p, _f64p, _f64p, _i32p, _i32p, _f64p, _i32p, C.c_int,
+                                                 C.c_int, _f64p, _f64p, _i32p,
+                                                 C.c_int, _f64p, _f64p, _f64p, _f64p,
+                                                 C.c_int, _f64p, _f64p, _f64p, _f64p,
+                                                 C.POINTER(C.c_double), C.POINTER(C.c_int)])
+        L.orc_accum.restype = C.c_int
+        L.orc_box_keys.argtypes = ([C.c_int] * 5 + [_f64p, _f64p, _f64p, _i32p, _i32p, _i32p, C.c_int, C.c_int,
+                                                    _f64p, _f64p, _i32p, C.c_int, C.c_int, _i64p])
+        L.orc_box_keys.restype = None
+        L.orc_norm.argtypes = ([C.c_int] * 6 + [C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p,
+                                                C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_int])
+        L.orc_norm.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def grid_init(im: int, jm: int):
+    """m_gritas_grids.f:128-129."""
+    return 360.0 / im, 180.0 / (jm - 1)
+
+
+def pint(plevs):
+    """GrITAS_Pint_ (m_gritas_grids.f:217-296) -> (p1, p2); raises on the gritas_perror cases."""
+    plevs = np.ascontiguousarray(plevs, dtype=np.float64)
+    n = plevs.size
+    p1 = np.zeros(max(n, 1))
+    p2 = np.zeros(max(n, 1))
+    rc = lib().orc_pint(n, plevs if n else np.zeros(1), p1, p2)
+    if rc:
+        raise ValueError({1: "Pint: must have at least 1 vertical levels",
+                          2: "Pint: pressure levels do not decrease monotonically",
+                          3: "Pint: cannot handle 0 hPa"}[rc])
+    return p1[:n], p2[:n]
+
+
+def kxkt(ktmax, kxmax, kt_list, kx_lists, kt_surf=(1, 2, 3), l2d_max=20, l3d_max=22):
+    """GrITAS_KxKt (gritas_kxkt.f:10-119).  kx_lists: one sequence of kx per list row.
+    Returns (table[kxmax,ktmax] F-order int32, list_2d, list_3d, l2d, l3d)."""
+    listsz = len(kt_list)
+    kxl = np.full((kxmax, max(listsz, 1)), -1, dtype=np.int32, order="F")
+    for j, ks in enumerate(kx_lists):
+        kxl[: len(ks), j] = np.asarray(ks, dtype=np.int32)
+    table = np.zeros((kxmax, ktmax), dtype=np.int32, order="F")
+    l2 = np.zeros(max(l2d_max, 1), dtype=np.int32)
+    l3 = np.zeros(max(l3d_max, 1), dtype=np.int32)
+    a, b = C.c_int(0), C.c_int(0)
+    ktl = np.asarray(kt_list, dtype=np.int32) if listsz else np.zeros(1, np.int32)
+    surf = np.asarray(kt_surf, dtype=np.int32) if len(kt_surf) else np.zeros(1, np.int32)
+    rc = lib().orc_kxkt(ktmax, kxmax, l2d_max, l3d_max, listsz, ktl, kxl, surf, len(kt_surf), table, l2, l3,
+                        C.byref(a), C.byref(b))
+    if rc:
+        raise ValueError({1: "KxKt: invalid kt - too large", 2: "KxKt: invalid kt - negative",
+                          3: "KxKt: invalid l2d - too large", 4: "KxKt: invalid l3d - too large",
+                          5: "KxKt: invalid kx - too large"}[rc])
+    return table, l2[: a.value].copy(), l3[: b.value].copy(), a.value, b.value
+
+
+def presort(qcexcl, lat, lon, lev, time, kt, ks, kx):
+    """gritas.f:499-508 -> 0-based permutation."""
+    n = len(lat)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib().orc_presort(n, *_c(np.int32, qcexcl), *_c(np.float64, lat, lon, lev),
+                           *_c(np.int32, time, kt, ks, kx), out)
+    if rc:
+        raise MemoryError
+    return out[:n]
+
+
+def _c(dt, *arrs):
+    out = []
+    for a in arrs:
+        a = np.ascontiguousarray(a, dtype=dt)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dt)
+        out.append(a)
+    return out
+
+
+def select_del(iopt, omf, oma, obs=None, xvec=None, scale_res=0):
+    """gritas.f:562-587, column 1."""
+    n = len(omf)
+    obs = np.zeros(n) if obs is None else obs
+    xvec = np.ones(n) if xvec is None else xvec
+    d = np.zeros(max(n, 1))
+    rc = lib().orc_select_del(n, iopt, scale_res, *_c(np.float64, omf, oma, obs, xvec), d)
+    if rc:
+        raise ValueError("iopt not covered by the oracle")
+    return d[:n]
+
+
+def filter_flags(qcexcl, time, lon, ioptn=1, t1=0, t2=-1, lona=-999.0, lonb=999.0, x_passive=7, x_pre_bad=1):
+    """gritas.f:710-739 -> ob_flag."""
+    n = len(qcexcl)
+    flag = np.zeros(max(n, 1), dtype=np.int32)
+    lib().orc_filter(n, *_c(np.int32, qcexcl, time), *_c(np.float64, lon), ioptn, t1, t2, lona, lonb,
+                     x_passive, x_pre_bad, flag)
+    return flag[:n]
+
+
+class LevelMiss(Exception):
+    """gritas_perror('Accum: could not find level') (m_gritas_grids.f:458-459)."""
+
+    def __init__(self, lev, n):
+        super().__init__(f"Accum: obs level is {lev} hPa; Accum: could not find level (obs {n})")
+        self.lev = lev
+        self.n = n
+
+
+class Grids:
+    """The reference's allocatable grids (gritas.f:336-363), zero-initialised, column-major."""
+
+    def __init__(self, im, jm, km, l2d, l3d, nr):
+        self.im, self.jm, self.km, self.l2d, self.l3d, self.nr = im, jm, km, l2d, l3d, nr
+        z = lambda *s: np.zeros(s, dtype=np.float64, order="F")
+        a2, a3 = max(l2d, 1), max(l3d, 1)
+        self.bias_2d, self.rtms_2d, self.stdv_2d, self.xcov_2d = (z(im, jm, a2, nr) for _ in range(4))
+        self.nobs_2d = z(im, jm, a2)
+        self.bias_3d, self.rtms_3d, self.stdv_3d, self.xcov_3d = (z(im, jm, km, a3, nr) for _ in range(4))
+        self.nobs_3d = z(im, jm, km, a3)
+
+    def names(self):
+        return ["bias_2d", "rtms_2d", "stdv_2d", "xcov_2d", "nobs_2d",
+                "bias_3d", "rtms_3d", "stdv_3d", "xcov_3d", "nobs_3d"]
+
+
+def accum(g: Grids, nlevs, lat, lon, lev, kx, kt, del_, kxkt_table, p1, p2, ob_flag):
+    """GrITAS_Accum_ (m_gritas_grids.f:307-478).  del_ is (nobs, nr) F-order; ob_flag int32 inout."""
+    nobs = len(lat)
+    del_ = np.asfortranarray(np.asarray(del_, dtype=np.float64).reshape(nobs, -1, order="F"))
+    nr = del_.shape[1]
+    assert nr == g.nr
+    assert ob_flag.dtype == np.int32
+    kxmax, ktmax = kxkt_table.shape
+    bad, badn = C.c_double(0.0), C.c_int(-1)
+    if nobs == 0:
+        return
+    rc = lib().orc_accum(g.im, g.jm, g.km, nlevs, nobs, nr, *_c(np.float64, lat, lon, lev),
+                         *_c(np.int32, kx, kt), del_, np.asfortranarray(kxkt_table, dtype=np.int32), kxmax, ktmax,
+                         *_c(np.float64, p1, p2), ob_flag,
+                         g.l2d, g.bias_2d, g.rtms_2d, g.xcov_2d, g.nobs_2d,
+                         g.l3d, g.bias_3d, g.rtms_3d, g.xcov_3d, g.nobs_3d, C.byref(bad), C.byref(badn))
+    if rc == 7:
+        raise LevelMiss(bad.value, badn.value)
+    if rc:
+        raise ValueError("Accum: could not handle more then 2 residuals")
+
+
+def box_keys(im, jm, km, nlevs, lat, lon, lev, kx, kt, kxkt_table, p1, p2, ob_flag, l2d, l3d):
+    nobs = len(lat)
+    key = np.zeros(max(nobs, 1), dtype=np.int64)
+    kxmax, ktmax = kxkt_table.shape
+    lib().orc_box_keys(im, jm, km, nlevs, nobs, *_c(np.float64, lat, lon, lev), *_c(np.int32, kx, kt),
+                       np.asfortranarray(kxkt_table, dtype=np.int32), kxmax, ktmax, *_c(np.float64, p1, p2),
+                       *_c(np.int32, ob_flag), l2d, l3d, key)
+    return key[:nobs]
+
+
+def norm(g: Grids, nlevs, nrmlz=True, ntresh=0):
+    """GrITAS_Norm_ (m_gritas_grids.f:490-656), in place."""
+    rc = lib().orc_norm(g.im, g.jm, g.km, nlevs, g.nr, int(bool(nrmlz)),
+                        g.l2d, g.bias_2d, g.rtms_2d, g.stdv_2d, g.xcov_2d, g.nobs_2d,
+                        g.l3d, g.bias_3d, g.rtms_3d, g.stdv_3d, g.xcov_3d, g.nobs_3d, ntresh)
+    if rc:
+        raise ValueError("Norm: could not handle more then 2 residuals")

@@ -1,0 +1,404 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): counts and box assignment bit-exact; mean/stdv/rms within 1e-12
+relative in the deterministic path (we require BIT-EXACT there: same summation order as the
+sequential reference loop) and within 1e-6 in the atomic path.
+"""
+import numpy as np
+import pytest
+
+from gritas_b200 import cabi, synth
+from gritas_b200.m_gritas_grids import Grids, GritasPerror
+from oracle import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_FAST = 1e-6   # north_star tolerance of the atomic path
+TOL_DET = 1e-12   # north_star tolerance of the deterministic path (tests demand bit-exact anyway)
+
+
+def small(name, scale, nfiles):
+    cfg = synth.get_config(name, scale)
+    files = [synth.make_file(cfg, i) for i in range(nfiles)]
+    return cfg, files
+
+
+def flags_of(cfg, cols, ioptn=1):
+    return oracle.filter_flags(cols["qcexcl"], cols["time"], cols["lon"], ioptn=ioptn)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("nr", [1, 2])
+def test_conventional_two_files(mode, nr):
+    cfg, files = small("cfg1", 0.05, 2)
+    fin = [flags_of(cfg, c) for c in files]
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, rflags = H.oracle_run(cfg, files, nr, fin)
+    out, gflags = H.gpu_run(cfg, files, nr, mode, fin)
+    for a, b in zip(gflags, rflags):
+        assert np.array_equal(a, b)                      # ob_flag write-back (m_gritas_grids.f:413-416)
+    H.compare(out, ref, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+def test_surface_and_upper_air_mix(mode):
+    """kt 1,2,3 are surface (2-D grids, lev ignored: m_gritas_grids.f:432-441); same (kx,kt) in two
+    rows -> last wins (gritas_kxkt.f:105)."""
+    cfg = synth.get_config("cfg1", 0.03)
+    cfg.kt_list = [44, 4, 5, 1, 2, 3, 44]
+    cfg.kx_lists = [[120, 130], [220], [220], [181, 187], [181], [180], [130]]
+    files = []
+    for i in range(2):
+        c = synth.make_file(synth.get_config("cfg1", 0.03), i)
+        rng = np.random.default_rng(100 + i)
+        row = rng.integers(0, 7, len(c["lat"]))
+        c["kt"] = np.asarray(cfg.kt_list, np.int32)[row]
+        c["kx"] = np.asarray([120, 220, 220, 181, 181, 180, 130], np.int32)[row]
+        surf = np.isin(c["kt"], [1, 2, 3])
+        c["lev"] = np.where(surf, rng.choice([0.0, -5.0, 5000.0, np.nan], len(surf)), c["lev"])  # ignored
+        files.append(c)
+    table, l2d, l3d, *_ = H.setup(cfg)
+    assert (l2d, l3d) == (3, 4)
+    for nr in (1, 2):
+        ref, rf = H.oracle_run(cfg, files, nr)
+        out, gf = H.gpu_run(cfg, files, nr, mode)
+        assert all(np.array_equal(a, b) for a, b in zip(gf, rf))
+        H.compare(out, ref, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+def _one_obs_box(cfg, lat, lon, lev, kx=120, kt=44):
+    """Which (i,j,k) box (1-based) a single observation lands in, via the count grid."""
+    cols = dict(lat=np.array([lat]), lon=np.array([lon]), lev=np.array([lev]), kx=np.array([kx], np.int32),
+                kt=np.array([kt], np.int32), omf=np.array([1.0]), oma=np.array([1.0]), xm=np.array([0.0]))
+    out, fl = H.gpu_run(cfg, [cols], 1, cabi.MODE_FAST, norm=False)
+    idx = np.argwhere(out["nobs_3d"] == 1.0)
+    assert idx.shape[0] == 1
+    return tuple(int(v) + 1 for v in idx[0][:3])
+
+
+def test_kat_box_assignment():
+    """Known-answer tests derived from the reference source."""
+    cfg = synth.get_config("cfg1", 0.001)
+    im, jm = cfg.im, cfg.jm
+    p1, p2 = oracle.pint(cfg.plevs)
+    dlon = 360.0 / im
+    assert _one_obs_box(cfg, 0.0, 180.0, 500.0)[0] == 1                       # i = im+1 -> 1 (m_gritas_grids.f:421)
+    assert _one_obs_box(cfg, 0.0, -180.0 - dlon / 2 - 1e-9, 500.0)[0] == im   # i = 0 -> im (:422)
+    assert _one_obs_box(cfg, 0.0, 270.0, 500.0)[0] == im                      # clamped, not wrapped (:425)
+    assert _one_obs_box(cfg, 0.0, -180.0 + dlon / 2, 500.0)[0] == 2           # nint(0.5) = 1, half away from zero
+    assert _one_obs_box(cfg, 0.0, -180.0 + 1.5 * dlon, 500.0)[0] == 3         # nint(1.5) = 2 (banker's would too)
+    assert _one_obs_box(cfg, 0.0, -180.0 + 2.5 * dlon, 500.0)[0] == 4         # nint(2.5) = 3 (banker's gives 2)
+    assert _one_obs_box(cfg, 90.0, 0.0, 500.0)[1] == jm
+    assert _one_obs_box(cfg, -90.0, 0.0, 500.0)[1] == 1
+    assert _one_obs_box(cfg, 95.0, 0.0, 500.0)[1] == jm                       # clamp (:426)
+    assert _one_obs_box(cfg, -1000.0, 0.0, 500.0)[1] == 1
+    k = 5
+    assert _one_obs_box(cfg, 0.0, 0.0, p2[k - 1])[2] == k + 1                 # lev == p2(k) -> level k+1 (.gt. p2)
+    assert _one_obs_box(cfg, 0.0, 0.0, p1[k - 1])[2] == k                     # lev == p1(k) -> level k (.le. p1)
+    assert _one_obs_box(cfg, 0.0, 0.0, 2000.0)[2] == 1
+    assert _one_obs_box(cfg, 0.0, 0.0, 1e-300)[2] == cfg.nlevs
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("badlev", [2000.5, 0.0, -3.0, float("nan")])
+def test_level_miss_is_fatal(mode, badlev):
+    """m_gritas_grids.f:458-459: print the level, gritas_perror -> exit(7).  Only for accepted 3-D obs."""
+    cfg, files = small("cfg1", 0.002, 1)
+    c = files[0]
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    fl = np.zeros(len(c["lat"]), np.int32)
+    good = np.nonzero((c["kt"] != 7))[0]
+    pos = int(good[len(good) // 2])
+    c["lev"][pos] = badlev
+    # an earlier bad level on a rejected / not-in-table observation must NOT be fatal
+    rej = int(np.nonzero(c["kt"] == 7)[0][0])
+    c["lev"][rej] = -1.0
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    with pytest.raises(GritasPerror) as ei:
+        G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 1), len(fl), 1, table, p1, p2, fl,
+                       l2d, l3d=l3d)
+    assert ei.value.code == 7
+    assert (np.isnan(badlev) and np.isnan(ei.value.lev)) or ei.value.lev == badlev
+    g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 1)
+    with pytest.raises(oracle.LevelMiss) as eo:
+        oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 1), table, p1, p2,
+                     np.zeros(len(fl), np.int32))
+    assert eo.value.n == pos
+    # the context stays usable after the error is reported
+    c["lev"][pos] = 500.0
+    G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 1), len(fl), 1, table, p1, p2, None,
+                   l2d, l3d=l3d)
+    G.close()
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 31, 33, 257, 1023])
+def test_empty_and_ragged(mode, n):
+    cfg = synth.get_config("cfg1", 1.0)
+    cfg.nobs_per_file = max(n, 1)
+    c = synth.make_file(cfg, 7)
+    c = {k: v[:n].copy() for k, v in c.items()}
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, rf = H.oracle_run(cfg, [c], 2)
+    out, gf = H.gpu_run(cfg, [c], 2, mode)
+    assert np.array_equal(gf[0], rf[0])
+    H.compare(out, ref, l2d, l3d, 2, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+def test_unaligned_columns(mode):
+    """Column sections that start on an odd element (8-byte but not 16-byte aligned; 4-byte ints)."""
+    cfg, files = small("cfg1", 0.01, 1)
+    c = {k: v[1:].copy() for k, v in files[0].items()}
+    n = len(c["lat"])
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    back = {k: np.concatenate([v[:1], v]) for k, v in c.items()}
+    view = {k: v[1:] for k, v in back.items()}                    # views with a one-element offset
+    dfull = np.zeros(2 * n + 1)
+    dfull[1:n + 1] = c["omf"]
+    dfull[n + 1:] = c["oma"]
+    dview = dfull[1:]
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    flfull = np.zeros(n + 1, np.int32)
+    G.GrITAS_Accum(view["lat"], view["lon"], view["lev"], view["kx"], view["kt"], dview, n, 2, table, p1, p2,
+                   flfull[1:], l2d, l3d=l3d)
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.close()
+    ref, rf = H.oracle_run(cfg, [c], 2)
+    assert np.array_equal(flfull[1:], rf[0])
+    H.compare(out, ref, l2d, l3d, 2, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+def test_device_resident_inputs(mode):
+    cfg, files = small("cfg1", 0.02, 2)
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 2)
+    out, _ = H.gpu_run(cfg, files, 2, mode, want_flags=False, device_inputs=True)
+    H.compare(out, ref, l2d, l3d, 2, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+def test_single_level():
+    """nlevs = 1: only plevs(1)-0.1 < lev <= plevs(1) is accepted (m_gritas_grids.f:249-256); Norm
+    leaves the 3-D sums raw (returns before the 3-D loop, :607)."""
+    cfg = synth.get_config("cfg1", 0.002)
+    cfg.plevs = np.array([500.0])
+    c = synth.make_file(synth.get_config("cfg1", 0.002), 0)
+    c["lev"] = np.full(len(c["lat"]), 499.95)
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, rf = H.oracle_run(cfg, [c], 1)
+    out, gf = H.gpu_run(cfg, [c], 1, cabi.MODE_DETERMINISTIC)
+    assert np.array_equal(gf[0], rf[0])
+    for nm in ("bias_3d", "rtms_3d", "nobs_3d"):
+        assert np.array_equal(out[nm], getattr(ref, nm))
+    assert np.array_equal(out["xcov_3d"][..., 0], ref.xcov_3d[..., 0])
+    assert np.all(out["stdv_3d"] == 0.0)                          # untouched
+    c["lev"][3] = oracle.pint(cfg.plevs)[1][0]                    # == p2: rejected (.gt.)
+    c["kt"][3], c["kx"][3] = 44, 120
+    with pytest.raises(GritasPerror):
+        H.gpu_run(cfg, [c], 1, cabi.MODE_FAST)
+
+
+@pytest.mark.parametrize("nrmlz,ntresh", [(True, None), (True, 0), (True, 1), (False, None)])
+def test_norm_variants(nrmlz, ntresh):
+    """-nonorm (m stays 1 -> division by m-1 = 0, m_gritas_grids.f:572, 593) and ntresh <= 1."""
+    cfg, files = small("cfg1", 0.2, 1)      # dense enough for boxes with n = 0, 1, 2, ...
+    cfg2 = synth.get_config("cfg1", 0.2)
+    cfg2.im, cfg2.jm = 24, 13
+    cfg.im, cfg.jm = 24, 13
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 2, nrmlz=nrmlz, ntresh=ntresh or 0)
+    out, _ = H.gpu_run(cfg, files, 2, cabi.MODE_DETERMINISTIC, nrmlz=nrmlz, ntresh=ntresh)
+    with np.errstate(invalid="ignore"):
+        H.compare(out, ref, l2d, l3d, 2, exact=True, tol=0.0)
+
+
+def test_norm_ntresh_large():
+    """ntresh > 1 (grisas -ntresh): boxes below the threshold are missing.  The reference's 3-D n==1
+    branch then reads stale temporaries of an earlier box (m_gritas_grids.f:642-644) -- those boxes
+    are excluded from the comparison (documented divergence)."""
+    cfg, files = small("cfg1", 0.2, 1)
+    cfg.im, cfg.jm = 24, 13
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 1, ntresh=4)
+    out, _ = H.gpu_run(cfg, files, 1, cabi.MODE_DETERMINISTIC, ntresh=4)
+    n = ref.nobs_3d
+    assert np.array_equal(out["nobs_3d"], n)
+    for nm in ("bias_3d", "rtms_3d"):
+        assert np.array_equal(out[nm], getattr(ref, nm))
+    keep = (n != 1.0)[..., None]
+    for nm in ("stdv_3d", "xcov_3d"):
+        assert np.array_equal(np.where(keep, out[nm], 0.0), np.where(keep, getattr(ref, nm), 0.0))
+    assert np.all(out["bias_3d"][(n < 4)[..., None] & np.ones_like(out["bias_3d"], bool)] == oracle.AMISS)
+
+
+def test_n_equals_one_quirk():
+    """Box with n = 1: 2-D stdv = AMISS, 3-D stdv = 0 (m_gritas_grids.f:597-600 vs 642-644)."""
+    cfg = synth.get_config("cfg1", 0.001)
+    cfg.kt_list, cfg.kx_lists = [44, 1], [[120], [181]]
+    cols = dict(lat=np.array([10.0, 10.0]), lon=np.array([20.0, 20.0]), lev=np.array([500.0, 500.0]),
+                kx=np.array([120, 181], np.int32), kt=np.array([44, 1], np.int32), omf=np.array([2.0, 3.0]),
+                oma=np.array([1.0, 1.0]), xm=np.zeros(2))
+    out, _ = H.gpu_run(cfg, [cols], 1, cabi.MODE_DETERMINISTIC)
+    i3 = np.argwhere(out["nobs_3d"] == 1.0)[0]
+    i2 = np.argwhere(out["nobs_2d"] == 1.0)[0]
+    assert out["stdv_3d"][tuple(i3) + (0,)] == 0.0
+    assert out["stdv_2d"][tuple(i2) + (0,)] == oracle.AMISS
+    assert out["bias_3d"][tuple(i3) + (0,)] == 2.0 and out["bias_2d"][tuple(i2) + (0,)] == 3.0
+    assert np.count_nonzero(out["bias_3d"] != oracle.AMISS) == 1       # every empty box is AMISS
+
+
+def test_three_residuals_raw():
+    """nr = 3 (three-corner hat): Accum leaves xcov untouched (nx = 0, m_gritas_grids.f:397-401); Norm
+    refuses nr > 2 (:555)."""
+    cfg, files = small("cfg1", 0.01, 1)
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 3, norm=False)
+    out, _ = H.gpu_run(cfg, files, 3, cabi.MODE_DETERMINISTIC, norm=False)
+    for nm in ("bias_3d", "rtms_3d", "nobs_3d"):
+        assert np.array_equal(out[nm], getattr(ref, nm))
+    assert np.all(out["xcov_3d"][..., 0] == 0.0) and np.all(ref.xcov_3d == 0.0)
+    with pytest.raises(GritasPerror):
+        H.gpu_run(cfg, files, 3, cabi.MODE_DETERMINISTIC, norm=True)
+
+
+def test_raw_round_trip_and_reset():
+    """get_raw / add_raw (the -nonorm combine workflow, gritas.f:1508-1509) and reset (grisas.f:285-296)."""
+    cfg, files = small("cfg1", 0.02, 2)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 2)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_DETERMINISTIC)
+    c = files[0]
+    G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 2), len(c["lat"]), 2, table, p1, p2,
+                   None, l2d, l3d=l3d)
+    raw = G.alloc_grids()
+    G.get_raw(None, None, None, None, raw["bias_3d"], raw["rtms_3d"], raw["xcov_3d"], raw["nobs_3d"])
+    G.reset()
+    zero = G.alloc_grids()
+    G.get_raw(None, None, None, None, zero["bias_3d"], zero["rtms_3d"], zero["xcov_3d"], zero["nobs_3d"])
+    assert not zero["nobs_3d"].any() and not zero["bias_3d"].any()
+    G.add_raw(None, None, None, None, raw["bias_3d"], raw["rtms_3d"], raw["xcov_3d"], raw["nobs_3d"])
+    c = files[1]
+    G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 2), len(c["lat"]), 2, table, p1, p2,
+                   None, l2d, l3d=l3d)
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.close()
+    H.compare(out, ref, l2d, l3d, 2, exact=True, tol=0.0)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("iopt,ioptn", [(1, 1), (1, -1), (3, 3), (3, -3), (101, 101), (101, -101)])
+def test_fused_ods_entry(mode, iopt, ioptn):
+    """gritas.f:562-587 + 710-739 + GrITAS_Accum_ fused; passive data kept iff ioptn > 0."""
+    cfg, files = small("cfg1", 0.03, 2)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    nr = 2 if iopt == 101 else 1
+    g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, nr)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    for c in files:
+        n = len(c["lat"])
+        fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=ioptn, t1=-90, t2=120, lona=-100.0, lonb=140.0,
+                                 x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
+        d = np.zeros((n, nr), order="F")
+        d[:, 0] = oracle.select_del(1 if iopt == 101 else iopt, c["omf"], c["oma"])
+        if nr == 2:
+            d[:, 1] = oracle.select_del(3, c["omf"], c["oma"])
+        oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], d, table, p1, p2, fl)
+        gfl = np.full(n, -9, np.int32)
+        G.accum_ods(c, iopt=iopt, ioptn=ioptn, t1=-90, t2=120, lona=-100.0, lonb=140.0, x_passive=synth.X_PASSIVE,
+                    x_pre_bad=synth.X_PRE_BAD, kxkt_table=table, p1=p1, p2=p2, l2d=l2d, l3d=l3d, ob_flag_out=gfl)
+        assert np.array_equal(gfl, fl)
+    oracle.norm(g, cfg.nlevs, True, 0)
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.close()
+    H.compare(out, g, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("scale_res", [1, 2, 3])
+def test_fused_ods_scaling(scale_res):
+    """gritas.f:564-572: del/sqrt(xvec), del/obs, del/(obs-omf)."""
+    cfg, files = small("cfg1", 0.02, 1)
+    c = files[0]
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    for iopt in (1, 3):
+        g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 1)
+        fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=iopt, x_passive=synth.X_PASSIVE,
+                                 x_pre_bad=synth.X_PRE_BAD)
+        d = oracle.select_del(iopt, c["omf"], c["oma"], c["obs"], c["xvec"], scale_res)
+        oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], d, table, p1, p2, fl)
+        oracle.norm(g, cfg.nlevs, True, 0)
+        G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_DETERMINISTIC)
+        G.accum_ods(c, iopt=iopt, scale_res=scale_res, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD,
+                    kxkt_table=table, p1=p1, p2=p2, l2d=l2d, l3d=l3d)
+        out = G.alloc_grids()
+        G.norm_into(out)
+        G.close()
+        H.compare(out, g, l2d, l3d, 1, exact=True, tol=0.0)
+
+
+@pytest.mark.parametrize("name,scale", [("cfg3_amsua", 0.002), ("cfg3_iasi", 0.004), ("cfg4", 0.03), ("cfg5", 0.05)])
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+def test_other_configs_small(name, scale, mode):
+    """BASELINE.json configs 3-5 at sizes the oracle finishes in seconds (grid shrunk for radiances:
+    the oracle's host grids at 0.25 deg x 616 channels would need 20 GB)."""
+    cfg = synth.get_config(name, scale)
+    if cfg.kind == "radiance":
+        cfg.im, cfg.jm = 144, 73
+    if name == "cfg4":
+        cfg.im, cfg.jm = 36, 19
+    files = [synth.make_file(cfg, i) for i in range(2)]
+    table, l2d, l3d, *_ = H.setup(cfg)
+    nr = cfg.nr
+    ref, rf = H.oracle_run(cfg, files, nr)
+    out, gf = H.gpu_run(cfg, files, nr, mode)
+    assert all(np.array_equal(a, b) for a, b in zip(gf, rf))
+    H.compare(out, ref, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+
+
+def test_deterministic_is_reproducible_on_clustered_data():
+    """config 5: two runs of the deterministic path must be bit-identical; the atomic path need not be."""
+    cfg, files = small("cfg5", 0.25, 2)
+    a, _ = H.gpu_run(cfg, files, 1, cabi.MODE_DETERMINISTIC, want_flags=False)
+    b, _ = H.gpu_run(cfg, files, 1, cabi.MODE_DETERMINISTIC, want_flags=False)
+    for nm in H.NAMES:
+        assert np.array_equal(a[nm], b[nm], equal_nan=True)
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 1)
+    H.compare(a, ref, l2d, l3d, 1, exact=True, tol=0.0)
+    f, _ = H.gpu_run(cfg, files, 1, cabi.MODE_FAST, want_flags=False)
+    H.compare(f, ref, l2d, l3d, 1, exact=False, tol=TOL_FAST)
+
+
+def test_full_size_file_properties():
+    """One full-size cfg2 file (1.21 M obs, omf+oma): size-independent properties + full oracle check."""
+    cfg = synth.get_config("cfg2")
+    c = synth.make_file(cfg, 3)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=101, x_passive=synth.X_PASSIVE,
+                             x_pre_bad=synth.X_PRE_BAD)
+    results = {}
+    for mode in (cabi.MODE_FAST, cabi.MODE_DETERMINISTIC):
+        G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+        gfl = np.zeros(len(fl), np.int32)
+        G.accum_ods(c, iopt=101, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD, kxkt_table=table, p1=p1, p2=p2,
+                    l2d=l2d, l3d=l3d, ob_flag_out=gfl)
+        raw = G.alloc_grids()
+        G.get_raw(None, None, None, None, raw["bias_3d"], raw["rtms_3d"], raw["xcov_3d"], raw["nobs_3d"])
+        G.close()
+        accepted = gfl == 0
+        assert raw["nobs_3d"].sum() == accepted.sum()                            # checksum of counts
+        assert np.isclose(raw["bias_3d"][..., 0].sum(), c["omf"][accepted].sum(), rtol=1e-9, atol=1e-6)
+        assert np.isclose(raw["rtms_3d"][..., 1].sum(), (c["oma"][accepted] ** 2).sum(), rtol=1e-12)
+        results[mode] = raw
+    assert np.array_equal(results[0]["nobs_3d"], results[1]["nobs_3d"])
+    g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 2)
+    d = np.zeros((len(fl), 2), order="F")
+    d[:, 0], d[:, 1] = c["omf"], c["oma"]
+    oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], d, table, p1, p2, fl)
+    for nm in ("bias_3d", "rtms_3d", "nobs_3d"):
+        assert np.array_equal(results[1][nm], getattr(g, nm))
+    assert np.array_equal(results[1]["xcov_3d"][..., 0], g.xcov_3d[..., 0])
