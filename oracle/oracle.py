@@ -177,6 +177,8 @@ class Grids:
 def accum(g: Grids, nlevs, lat, lon, lev, kx, kt, del_, kxkt_table, p1, p2, ob_flag):
     """GrITAS_Accum_ (m_gritas_grids.f:307-478).  del_ is (nobs, nr) F-order; ob_flag int32 inout."""
     nobs = len(lat)
+    if nobs == 0:
+        return
     del_ = np.asfortranarray(np.asarray(del_, dtype=np.float64).reshape(nobs, -1, order="F"))
     nr = del_.shape[1]
     assert nr == g.nr

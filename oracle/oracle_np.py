@@ -7,6 +7,8 @@ Citations are relative to /root/reference/src/Components/gritas/ unless noted.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 AMISS = 1.0e15  # m_gritas_grids.f:72
@@ -35,12 +37,16 @@ def pint(plevs):
         raise ValueError("Pint: pressure levels do not decrease monotonically")
     if p[-1] == 0.0:
         raise ValueError("Pint: cannot handle 0 hPa")
-    lg = np.log(p)
+    # scalar libm (math.log / math.exp), as gfortran would call; numpy's SIMD log/exp loops may differ
+    # from glibc by an ulp, which would move a level boundary
+    lg = [math.log(float(v)) for v in p]
     p1 = np.empty(n)
     p2 = np.empty(n)
     p1[0] = 2000.0
-    p1[1:] = np.exp(0.5 * (lg[:-1] + lg[1:]))   # exp(0.5*(log(p(k-1))+log(p(k))))
-    p2[:-1] = np.exp(0.5 * (lg[1:] + lg[:-1]))  # exp(0.5*(log(p(k+1))+log(p(k))))
+    for k in range(1, n):
+        p1[k] = math.exp(0.5 * (lg[k - 1] + lg[k]))   # exp(0.5*(log(p(k-1))+log(p(k))))
+    for k in range(n - 1):
+        p2[k] = math.exp(0.5 * (lg[k + 1] + lg[k]))   # exp(0.5*(log(p(k+1))+log(p(k))))
     p2[-1] = 0.0
     return p1, p2
 

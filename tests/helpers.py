@@ -118,3 +118,41 @@ def compare(out, ref: "oracle.Grids", l2d, l3d, nr, exact: bool, tol: float, raw
             else:
                 e = rel_err(a, b, np.broadcast_to(scale, b.shape))
                 assert e <= tol, f"{nm}_{tag}: rel err {e:.3e} > {tol:.1e}"
+
+
+# ---- golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py) ---------------------
+import glob
+import os
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GCOLS = ("lat", "lon", "lev", "time", "kt", "kx", "ks", "qcexcl", "omf", "oma")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = synth.Config(name, int(z["im"]), int(z["jm"]), z["plevs"], [int(v) for v in z["kt_list"]], [], int(z["nfiles"]),
+                       0, int(z["nr"]), kxmax=int(z["kxmax"]), ktmax=int(z["ktmax"]))
+    pos = 0
+    for ln in z["kx_len"]:
+        cfg.kx_lists.append([int(v) for v in z["kx_flat"][pos:pos + int(ln)]])
+        pos += int(ln)
+    files = [{k: z[f"f{i}_{k}"] for k in GCOLS} for i in range(cfg.nfiles)]
+    flags = [z[f"f{i}_flag"] for i in range(cfg.nfiles)]
+
+    def dense(prefix, nm, shape, fill):
+        a = np.full(int(np.prod(shape)), fill, dtype=np.float64)
+        a[z[f"{prefix}_{nm}_idx"]] = z[f"{prefix}_{nm}_val"]
+        return a.reshape(shape, order="F")
+    l2, l3, nr = max(int(z["l2d"]), 1), max(int(z["l3d"]), 1), cfg.nr
+    s2, s3 = (cfg.im, cfg.jm, l2), (cfg.im, cfg.jm, cfg.km, l3)
+    shapes = {"bias_2d": s2 + (nr,), "rtms_2d": s2 + (nr,), "stdv_2d": s2 + (nr,), "xcov_2d": s2 + (nr,), "nobs_2d": s2,
+              "bias_3d": s3 + (nr,), "rtms_3d": s3 + (nr,), "stdv_3d": s3 + (nr,), "xcov_3d": s3 + (nr,), "nobs_3d": s3}
+    norm = {nm: dense("norm", nm, sh, 0.0 if nm.startswith("nobs") else oracle.AMISS) for nm, sh in shapes.items()}
+    raw = {nm: dense("raw", nm, sh, 0.0) for nm, sh in shapes.items() if not nm.startswith("stdv")}
+    return cfg, files, flags, norm, raw, int(z["l2d"]), int(z["l3d"]), z["p1"], z["p2"]
+
+
+def filter_in(c, ioptn=1):
+    return oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=ioptn, x_passive=synth.X_PASSIVE,
+                               x_pre_bad=synth.X_PRE_BAD)
