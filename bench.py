@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-staging", action="store_true", help="fast mode without the tiled accumulate")
     return ap.parse_args()
 
 
@@ -75,6 +76,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.stop_ev = threading.Event()
+        self.ready = threading.Event()
+        self.active = False            # only samples taken while the timed region runs are kept
         self.sm, self.reasons, self.max = [], set(), None
 
     def run(self):
@@ -88,18 +91,22 @@ class ClockSampler(threading.Thread):
             if not names:
                 names = {getattr(nv, n): n[len("nvmlClocksThrottleReason"):] for n in dir(nv)
                          if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int)}
+            self.ready.set()
             while not self.stop_ev.is_set():
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if bit and (r & bit) and nm not in ("None", "All"):
-                        self.reasons.add(nm)
-                time.sleep(0.02)
+                if self.active:
+                    self.sm.append(clk)
+                    for bit, nm in names.items():
+                        if bit and (r & bit) and nm not in ("None", "All", "GpuIdle", "ApplicationsClocksSetting"):
+                            self.reasons.add(nm)
+                time.sleep(0.005)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
+            self.ready.set()
 
     def result(self):
         self.stop_ev.set()
@@ -230,6 +237,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     table, l2d, l3d = synth.kxkt_table(cfg)
     mode = (cabi.MODE_FAST if args.mode == "fast" else cabi.MODE_DETERMINISTIC) | cabi.FLAG_ASYNC | cabi.FLAG_HOLD_INPUTS
+    if args.no_staging:
+        mode |= cabi.FLAG_NO_STAGING
     G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode, device=local)
     p1, p2 = G.GrITAS_Pint()
     G._ensure(2, table, p1, p2, l2d, l3d)
@@ -274,6 +283,9 @@ def run_b200(args):
                 raise RuntimeError(f"accum_ods rc={rc}: {G._err()}")
         if marks is not None:
             marks[1].record(stream)
+        G.flush()
+        if marks is not None:
+            marks[2].record(stream)
         if world > 1:
             G.allreduce()
         if host_out is None:
@@ -285,27 +297,30 @@ def run_b200(args):
 
     # ---- device-resident arm ---------------------------------------------------------------
     dev_calls = calls_of(dev_files)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.ready.wait(timeout=20)
     for _ in range(max(3, args.warmup)):
         step(dev_calls)
     c0 = G.counters()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = ev(), ev()
-    marks = [(ev(), ev()) for _ in range(args.steps)]
+    marks = [(ev(), ev(), ev()) for _ in range(args.steps)]
+    sampler.active = True
     e0.record(stream)
     for s in range(args.steps):
         step(dev_calls, marks=marks[s])
     e1.record(stream)
     barrier()
-    clocks = sampler.result()
+    sampler.active = False
     c1 = G.counters()
     ms = e0.elapsed_time(e1) / args.steps
-    accum_ms = float(np.mean([a.elapsed_time(b) for a, b in marks]))
-    t = torch.tensor([ms, accum_ms], dtype=torch.float64, device="cuda")
+    accum_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
+    flush_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
+    t = torch.tensor([ms, accum_ms, flush_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, accum_ms = float(t[0]), float(t[1])
+    ms, accum_ms, flush_ms = float(t[0]), float(t[1]), float(t[2])
     launches_per_step = (c1["launches"] - c0["launches"]) // args.steps
     value = nobs_rank * world / (ms * 1e-3)
 
@@ -318,12 +333,14 @@ def run_b200(args):
         step(pin_calls, host_out)
         b0 = G.counters()
         barrier()
+        sampler.active = True
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             step(pin_calls, host_out)
         G.sync()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
+        sampler.active = False
         b1 = G.counters()
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -334,6 +351,7 @@ def run_b200(args):
                "d2h_bytes_per_step": (b1["d2h"] - b0["d2h"]) // args.e2e_steps,
                "note": "per rank bytes; pinned host columns -> C ABI -> pinned host mean/rms/stdv/xcov/nobs grids"}
         del pin_files
+    clocks = sampler.result()
 
     # ---- roofline of the dominant kernel (fused filter + box index + accumulate) -----------------
     try:
@@ -359,7 +377,7 @@ def run_b200(args):
             "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
                        "per_rank": "each rank bins its own month; one NCCL all-reduce of the partial grids, then finalize",
                        "l2": "inputs (7.8 GB/step) and accumulators (1.7 GB) both exceed the 126 MB L2; no flush needed"},
-            "accumulate_ms_per_step": accum_ms, "gpu_launches": int(launches_per_step * args.steps),
+            "accumulate_ms_per_step": accum_ms, "tile_flush_ms_per_step": flush_ms, "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
@@ -91,6 +92,13 @@ struct gritas_b200_ctx {
   void *cub_tmp = nullptr;
   size_t cub_cap = 0;
   int key_bits = 32;
+  // tiled fast path: staging lists + flush bookkeeping
+  StageDesc sg = {};
+  bool staging = false;
+  size_t stage_slots = 0;      // ntiles * cap
+  size_t staged_upper = 0;     // upper bound of entries appended since the last flush
+  size_t tile_smem = 0;
+  int tile_ctas = 0;
   // finalize scratch (reference-layout planes on the device)
   double *out = nullptr;
   size_t out_cap = 0;
@@ -217,10 +225,31 @@ int grid_for(size_t work, int threads, int per_sm) {
 
 template <int NR>
 void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
-  if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
-    k_accum_fast<NR, false><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
-  else
-    k_accum_fast<NR, true><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+  const bool agg = !(h->flags & GRITAS_B200_FLAG_NO_AGGREGATE);
+#define GB_LAUNCH(A, S) \
+  k_accum_fast<NR, A, S><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq, h->sg)
+  if (h->staging) { if (agg) GB_LAUNCH(true, true); else GB_LAUNCH(false, true); }
+  else { if (agg) GB_LAUNCH(true, false); else GB_LAUNCH(false, false); }
+#undef GB_LAUNCH
+}
+
+// K2t over every tile with staged entries; afterwards the lists are empty.
+template <int NR>
+void launch_tiles(gritas_b200_handle h) {
+  k_tile_accum<NR><<<h->tile_ctas, 1024, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec);
+}
+
+int flush_stage(gritas_b200_handle h) {
+  if (!h->staging || h->staged_upper == 0) return 0;
+  switch (h->g.nr) {
+    case 1: launch_tiles<1>(h); break;
+    case 2: launch_tiles<2>(h); break;
+    default: launch_tiles<3>(h); break;
+  }
+  CU(cudaGetLastError());
+  h->launches += 1;
+  h->staged_upper = 0;
+  return 0;
 }
 
 template <int NR>
@@ -256,6 +285,15 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
   }
   const size_t smem = h->g.p2_in_smem ? sizeof(double) * (size_t)h->g.nlevs : 0;
   if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
+    if (h->staging) {
+      // keep the expected list fill at or below ~half the capacity; what still overflows (skewed
+      // data) is accumulated directly by K1
+      if (h->staged_upper + (size_t)n > h->stage_slots / 2) {
+        int rc = flush_stage(h);
+        if (rc) return rc;
+      }
+      h->staged_upper += (size_t)n;
+    }
     const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
     const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
     switch (h->g.nr) {
@@ -407,6 +445,48 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   st.first_bad = BAD_NONE; st.bad_lev = 0.0; st.ticket = 0; st.pad = 0;
   CUC(cudaMemcpyAsync(h->d_status, &st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
   CUC(cudaStreamSynchronize(h->compute));
+
+  // ---- tiled fast path --------------------------------------------------
+  // Worth it when the whole grid is revisited many times (conventional data scattered over a grid far
+  // larger than L2); not for grids of many GB that a file only touches in places (radiances).
+  {
+    const char *e_on = getenv("GRITAS_B200_STAGE"), *e_shift = getenv("GRITAS_B200_TILE_SHIFT"),
+               *e_slots = getenv("GRITAS_B200_STAGE_SLOTS"), *e_max = getenv("GRITAS_B200_STAGE_MAX_GRID_MB");
+    const size_t max_grid = (e_max ? (size_t)atoll(e_max) : (size_t)8192) << 20;
+    bool want = m == GRITAS_B200_MODE_FAST && !(h->flags & GRITAS_B200_FLAG_NO_STAGING) && acc_bytes <= max_grid &&
+                h->nrec >= 4096;
+    if (e_on && atoi(e_on) == 0) want = false;
+    if (want) {
+      int shift = (nr == 1) ? 13 : (nr == 2 ? 12 : 11);
+      if (e_shift) shift = atoi(e_shift);
+      const int nv = (nr == 1) ? 2 : (nr == 2 ? 5 : 6);
+      const size_t T = (size_t)1 << shift;
+      const size_t smem = (size_t)nv * T * 8 + T * 4;
+      size_t free_b = 0, total_b = 0;
+      CUC(cudaMemGetInfo(&free_b, &total_b));
+      const size_t entry = 4 + 8 * (size_t)nr;
+      size_t slots = e_slots ? (size_t)atoll(e_slots) : std::min((size_t)320 << 20, std::max((size_t)8 << 20, 16 * h->nrec));
+      slots = std::min(slots, free_b / 4 / entry);
+      const size_t ntiles = (h->nrec + T - 1) / T;
+      size_t cap = (slots / ntiles) & ~(size_t)31;
+      if (cap >= 256 && smem <= 227 * 1024 && shift >= 8 && shift <= 16) {
+        h->sg.tile_shift = shift;
+        h->sg.ntiles = (unsigned)ntiles;
+        h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffff);
+        h->stage_slots = ntiles * (size_t)h->sg.cap;
+        h->tile_smem = smem;
+        h->tile_ctas = (int)std::min(ntiles, (size_t)1 << 20);
+        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * ntiles));
+        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * ntiles));
+        CUC(cudaMalloc(&h->sg.skey, sizeof(unsigned) * h->stage_slots));
+        for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sg.sd[ir], sizeof(double) * h->stage_slots));
+        if (nr == 1) CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->staging = true;
+      }
+    }
+  }
 #undef CUC
   *hp = h;
   return GRITAS_B200_OK;
@@ -428,6 +508,8 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (s.consumed) cudaEventDestroy(s.consumed);
     if (s.copied) cudaEventDestroy(s.copied);
   }
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2]})
+    if (p) cudaFree(p);
   for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
                   (void *)h->keys, (void *)h->idx, (void *)h->keys2, (void *)h->idx2, h->cub_tmp, (void *)h->out})
     if (p) cudaFree(p);
@@ -526,13 +608,24 @@ int gritas_b200_sync(gritas_b200_handle h, double *bad_lev) {
   int rc = check_handle(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->copy));
+  if ((rc = flush_stage(h))) return rc;
   return drain(h, bad_lev);
+}
+
+int gritas_b200_flush(gritas_b200_handle h) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  return flush_stage(h);
 }
 
 int gritas_b200_reset(gritas_b200_handle h) {
   int rc = check_handle(h);
   if (rc) return rc;
   CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
+  if (h->staging) {
+    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * h->sg.ntiles, h->compute));
+    h->staged_upper = 0;
+  }
   return 0;
 }
 
@@ -707,6 +800,7 @@ int gritas_b200_allreduce(gritas_b200_handle h) {
   if (h->nranks == 1 && !h->comm) return 0;
   if (!h->comm) return fail(h, GRITAS_B200_ERR_NCCL, "comm_init not called");
   CU(cudaStreamSynchronize(h->copy));
+  if ((rc = flush_stage(h))) return rc;
   int e = g_nccl.AllReduce(h->g.acc, h->g.acc, h->nrec * h->g.rs, NCCL_FLOAT64, NCCL_SUM, h->comm, h->compute);
   if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
   return 0;

@@ -64,6 +64,18 @@ struct FilterDesc {
   int scale_res;  // gritas.f:564-572
 };
 
+// Staging area of the tiled fast path.  The record grid is cut into tiles of
+// 2^tile_shift consecutive records; K1 appends every accepted observation as a compact
+// (record key, residuals) entry to the list of its tile; K2t later accumulates one tile at a time in
+// shared memory.  Lists have a fixed capacity; entries that do not fit are accumulated directly.
+struct StageDesc {
+  unsigned *fill;      // [ntiles] entries appended since the last flush (may exceed cap: clamp)
+  unsigned *skey;      // [ntiles * cap]
+  double *sd[3];       // [ntiles * cap] per residual column
+  unsigned cap, ntiles;
+  int tile_shift;
+};
+
 // ---------------------------------------------------------------------------------------------
 // Fortran NINT (round half away from zero), exact: x - trunc(x) is exact in fp64.  Out-of-range
 // and NaN saturate (undefined in Fortran; pinned identically in oracle/gritas_oracle.c).
@@ -270,9 +282,10 @@ __device__ __forceinline__ void load_p2(const GridDesc &g, double *s_p2) {
 // K1+K2a fused: stream the columns, classify, accumulate with fp64 RED into the record grid.
 // AGG: lanes of a warp that hit the same box (__match_any_sync) are summed in registers first and
 // only the lowest lane issues the atomics.
-template <int NR, bool AGG>
+template <int NR, bool AGG, bool STAGE>
 __global__ void __launch_bounds__(ACC_THREADS)
-k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq) {
+k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
+             const StageDesc sg) {
   extern __shared__ double s_p2[];
   load_p2(g, s_p2);
   const double *p2s = g.p2_in_smem ? s_p2 : g.p2;
@@ -302,8 +315,21 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
       if (NR == 2) sxy = __dmul_rn(sx[0], sx[1]);
       double cnt = 1.0;
       bool issue = key != KEY_NONE;
-      if (AGG) {
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (STAGE && issue) {
+        // append to the tile's list; the scattered 4/8-byte stores are merged into full sectors by L2
+        // (the list tails of all tiles stay resident), so HBM sees each staged byte once
+        const unsigned tile = key >> sg.tile_shift;
+        const unsigned pos = atomicAdd(sg.fill + tile, 1u);
+        if (pos < sg.cap) {
+          const size_t at = (size_t)tile * sg.cap + pos;
+          sg.skey[at] = key;
+#pragma unroll
+          for (int ir = 0; ir < NR; ++ir) sg.sd[ir][at] = sx[ir];
+          issue = false;
+        }
+      }
+      if (AGG && (!STAGE || __any_sync(0xffffffffu, issue))) {
+        const unsigned peers = __match_any_sync(0xffffffffu, issue ? key : KEY_NONE);  // staged lanes stay out
         const bool multi = issue && (peers & (peers - 1));
         if (__any_sync(0xffffffffu, multi)) {
           const int leader = __ffs(peers) - 1;
@@ -397,6 +423,98 @@ k_segment_sum(const GridDesc g, const ObsCols c, const FilterDesc f, const unsig
 #pragma unroll
   for (int ir = 0; ir < NR; ++ir) { rec[1 + 2 * ir] = sx[ir]; rec[2 + 2 * ir] = sq[ir]; }
   if (NR == 2) rec[5] = sxy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2t: tiled accumulate.  One CTA per tile: the tile's count / sum / sum-of-squares planes live in
+// shared memory (privatised histogram), the staged entries stream in coalesced, lanes of a warp that
+// hit the same box are combined first (__match_any_sync), the tile is then added to the HBM records
+// with plain coalesced read-modify-writes (the tile is owned by this CTA: no global atomics).
+template <int NR>
+struct TilePlanes { static constexpr int NV = (NR == 1) ? 2 : (NR == 2 ? 5 : 6); };
+
+template <int NR>
+__global__ void __launch_bounds__(1024, 1)
+k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec) {
+  constexpr int NV = TilePlanes<NR>::NV;
+  extern __shared__ double s_val[];                       // NV planes of T doubles, then T counts
+  const unsigned T = 1u << sg.tile_shift;
+  unsigned *s_cnt = reinterpret_cast<unsigned *>(s_val + (size_t)NV * T);
+  const int rs_shift = (g.rs == 4) ? 2 : 3;
+  for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
+    const unsigned n = min(sg.fill[tile], sg.cap);
+    if (n == 0) continue;                                 // uniform across the CTA
+    for (unsigned e = threadIdx.x; e < NV * T; e += blockDim.x) s_val[e] = 0.0;
+    for (unsigned e = threadIdx.x; e < T; e += blockDim.x) s_cnt[e] = 0u;
+    __syncthreads();
+    const size_t base = (size_t)tile * sg.cap;
+    const unsigned nw = (n + 31u) & ~31u;                 // whole warps iterate together
+    for (unsigned r = threadIdx.x; r < nw; r += blockDim.x) {
+      const bool live = r < n;
+      unsigned b = 0xFFFFFFFFu;
+      double d[NR];
+#pragma unroll
+      for (int ir = 0; ir < NR; ++ir) d[ir] = 0.0;
+      if (live) {
+        b = __ldcs(sg.skey + base + r) & (T - 1u);
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) d[ir] = __ldcs(sg.sd[ir] + base + r);
+      }
+      double v[NV];
+      if (NR == 1) { v[0] = d[0]; v[1] = __dmul_rn(d[0], d[0]); }
+      if (NR == 2) {
+        v[0] = d[0]; v[1] = __dmul_rn(d[0], d[0]); v[2] = d[NR - 1]; v[3] = __dmul_rn(d[NR - 1], d[NR - 1]);
+        v[4] = __dmul_rn(d[0], d[NR - 1]);
+      }
+      if (NR == 3) {
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) { v[2 * ir] = d[ir]; v[2 * ir + 1] = __dmul_rn(d[ir], d[ir]); }
+      }
+      unsigned cnt = 1u;
+      bool issue = live;
+      // warp aggregation: only pays (and only runs) when lanes collide, i.e. clustered data
+      const unsigned peers = __match_any_sync(0xffffffffu, b);
+      const bool multi = live && (peers & (peers - 1u));
+      if (__any_sync(0xffffffffu, multi)) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        const int npeer = live ? __popc(peers) : 1;
+        const int maxc = __reduce_max_sync(0xffffffffu, npeer);
+        unsigned others = peers & ~(1u << leader);
+        for (int it = 1; it < maxc; ++it) {
+          const int src = others ? (__ffs(others) - 1) : lane;
+          others &= others - 1u;
+          const bool take = (lane == leader) && (it < npeer);
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const double a = __shfl_sync(0xffffffffu, v[q], src);
+            if (take) v[q] = __dadd_rn(v[q], a);
+          }
+        }
+        cnt = (unsigned)npeer;
+        issue = live && (lane == leader);
+      }
+      if (issue) {
+        atomicAdd(s_cnt + b, cnt);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) atomicAdd(s_val + (size_t)q * T + b, v[q]);
+      }
+    }
+    __syncthreads();
+    // add the tile to the HBM records: element e of the tile's span is (box e >> rs_shift, slot e & (rs-1))
+    const size_t first = (size_t)tile << sg.tile_shift;
+    const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
+    double *span = g.acc + first * (size_t)g.rs;
+    for (unsigned e = threadIdx.x; e < (nb << rs_shift); e += blockDim.x) {
+      const unsigned bx = e >> rs_shift, slot = e & ((1u << rs_shift) - 1u);
+      const unsigned cn = s_cnt[bx];
+      if (cn == 0u || slot > (unsigned)NV) continue;
+      const double add = (slot == 0u) ? (double)cn : s_val[(size_t)(slot - 1u) * T + bx];
+      span[e] = __dadd_rn(span[e], add);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sg.fill[tile] = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

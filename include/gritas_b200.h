@@ -35,6 +35,8 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
 #define GRITAS_B200_FLAG_ASYNC 0x100     /* accum returns once inputs are consumed/staged; a level miss is
                                             reported by the next accum/sync/norm instead */
 #define GRITAS_B200_FLAG_NO_AGGREGATE 0x200 /* fast mode: skip the __match_any_sync warp aggregation */
+#define GRITAS_B200_FLAG_NO_STAGING 0x800   /* fast mode: never use the tiled (staged) accumulate; every
+                                            observation goes to the HBM records with fp64 RED */
 #define GRITAS_B200_FLAG_HOLD_INPUTS 0x400  /* with ASYNC: the caller keeps pinned input arrays valid until the
                                             next sync/norm, so accum does not even wait for the H2D copies */
 
@@ -116,6 +118,10 @@ int gritas_b200_accum_ods(gritas_b200_handle h, int nobs, const double *lat, con
 
 /* Wait for all queued work; returns a pending GRITAS_B200_ERR_LEVEL (and its level) if any. */
 int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
+
+/* Tiled fast path only: accumulate every staged observation into the HBM records now (asynchronous;
+ * sync / norm / get_raw / allreduce do it implicitly).  A no-op in the other modes. */
+int gritas_b200_flush(gritas_b200_handle h);
 
 /* Zero the device grids (grisas.f:285-296 zeroes them every synoptic time). */
 int gritas_b200_reset(gritas_b200_handle h);

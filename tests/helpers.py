@@ -8,6 +8,14 @@ from gritas_b200 import cabi, synth
 from gritas_b200.m_gritas_grids import Grids
 from oracle import oracle
 
+# fast (tiled/staged accumulate), fast with the direct fp64-RED accumulate, deterministic
+MODES = [cabi.MODE_FAST, cabi.MODE_FAST | cabi.FLAG_NO_STAGING, cabi.MODE_DETERMINISTIC]
+
+
+def is_det(mode):
+    return (mode & 0xff) == cabi.MODE_DETERMINISTIC
+
+
 NAMES = ["bias_2d", "rtms_2d", "stdv_2d", "xcov_2d", "nobs_2d", "bias_3d", "rtms_3d", "stdv_3d", "xcov_3d", "nobs_3d"]
 
 

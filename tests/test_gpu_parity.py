@@ -18,8 +18,12 @@ TOL_FAST = 1e-6   # north_star tolerance of the atomic path
 TOL_DET = 1e-12   # north_star tolerance of the deterministic path (tests demand bit-exact anyway)
 
 
-def small(name, scale, nfiles):
+def small(name, scale, nfiles, res=(72, 46)):
+    """A BASELINE.json config at reduced size: fewer obs per file and the reference's coarsest grid
+    (-res a = 72 x 46, gritas.f:1569) so that the oracle's host grids stay small."""
     cfg = synth.get_config(name, scale)
+    if res:
+        cfg.im, cfg.jm = res
     files = [synth.make_file(cfg, i) for i in range(nfiles)]
     return cfg, files
 
@@ -28,7 +32,7 @@ def flags_of(cfg, cols, ioptn=1):
     return oracle.filter_flags(cols["qcexcl"], cols["time"], cols["lon"], ioptn=ioptn)
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 @pytest.mark.parametrize("nr", [1, 2])
 def test_conventional_two_files(mode, nr):
     cfg, files = small("cfg1", 0.05, 2)
@@ -38,14 +42,15 @@ def test_conventional_two_files(mode, nr):
     out, gflags = H.gpu_run(cfg, files, nr, mode, fin)
     for a, b in zip(gflags, rflags):
         assert np.array_equal(a, b)                      # ob_flag write-back (m_gritas_grids.f:413-416)
-    H.compare(out, ref, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+    H.compare(out, ref, l2d, l3d, nr, exact=H.is_det(mode), tol=TOL_FAST)
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 def test_surface_and_upper_air_mix(mode):
     """kt 1,2,3 are surface (2-D grids, lev ignored: m_gritas_grids.f:432-441); same (kx,kt) in two
     rows -> last wins (gritas_kxkt.f:105)."""
     cfg = synth.get_config("cfg1", 0.03)
+    cfg.im, cfg.jm = 144, 91
     cfg.kt_list = [44, 4, 5, 1, 2, 3, 44]
     cfg.kx_lists = [[120, 130], [220], [220], [181, 187], [181], [180], [130]]
     files = []
@@ -64,7 +69,7 @@ def test_surface_and_upper_air_mix(mode):
         ref, rf = H.oracle_run(cfg, files, nr)
         out, gf = H.gpu_run(cfg, files, nr, mode)
         assert all(np.array_equal(a, b) for a, b in zip(gf, rf))
-        H.compare(out, ref, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+        H.compare(out, ref, l2d, l3d, nr, exact=H.is_det(mode), tol=TOL_FAST)
 
 
 def _one_obs_box(cfg, lat, lon, lev, kx=120, kt=44):
@@ -100,7 +105,7 @@ def test_kat_box_assignment():
     assert _one_obs_box(cfg, 0.0, 0.0, 1e-300)[2] == cfg.nlevs
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 @pytest.mark.parametrize("badlev", [2000.5, 0.0, -3.0, float("nan")])
 def test_level_miss_is_fatal(mode, badlev):
     """m_gritas_grids.f:458-459: print the level, gritas_perror -> exit(7).  Only for accepted 3-D obs."""
@@ -132,10 +137,11 @@ def test_level_miss_is_fatal(mode, badlev):
     G.close()
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 31, 33, 257, 1023])
 def test_empty_and_ragged(mode, n):
     cfg = synth.get_config("cfg1", 1.0)
+    cfg.im, cfg.jm = 72, 46
     cfg.nobs_per_file = max(n, 1)
     c = synth.make_file(cfg, 7)
     c = {k: v[:n].copy() for k, v in c.items()}
@@ -143,10 +149,10 @@ def test_empty_and_ragged(mode, n):
     ref, rf = H.oracle_run(cfg, [c], 2)
     out, gf = H.gpu_run(cfg, [c], 2, mode)
     assert np.array_equal(gf[0], rf[0])
-    H.compare(out, ref, l2d, l3d, 2, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+    H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 def test_unaligned_columns(mode):
     """Column sections that start on an odd element (8-byte but not 16-byte aligned; 4-byte ints)."""
     cfg, files = small("cfg1", 0.01, 1)
@@ -168,16 +174,16 @@ def test_unaligned_columns(mode):
     G.close()
     ref, rf = H.oracle_run(cfg, [c], 2)
     assert np.array_equal(flfull[1:], rf[0])
-    H.compare(out, ref, l2d, l3d, 2, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+    H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 def test_device_resident_inputs(mode):
     cfg, files = small("cfg1", 0.02, 2)
     table, l2d, l3d, *_ = H.setup(cfg)
     ref, _ = H.oracle_run(cfg, files, 2)
     out, _ = H.gpu_run(cfg, files, 2, mode, want_flags=False, device_inputs=True)
-    H.compare(out, ref, l2d, l3d, 2, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+    H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
 
 
 def test_single_level():
@@ -289,7 +295,7 @@ def test_raw_round_trip_and_reset():
     H.compare(out, ref, l2d, l3d, 2, exact=True, tol=0.0)
 
 
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 @pytest.mark.parametrize("iopt,ioptn", [(1, 1), (1, -1), (3, 3), (3, -3), (101, 101), (101, -101)])
 def test_fused_ods_entry(mode, iopt, ioptn):
     """gritas.f:562-587 + 710-739 + GrITAS_Accum_ fused; passive data kept iff ioptn > 0."""
@@ -315,7 +321,7 @@ def test_fused_ods_entry(mode, iopt, ioptn):
     out = G.alloc_grids()
     G.norm_into(out)
     G.close()
-    H.compare(out, g, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+    H.compare(out, g, l2d, l3d, nr, exact=H.is_det(mode), tol=TOL_FAST)
 
 
 @pytest.mark.parametrize("scale_res", [1, 2, 3])
@@ -341,7 +347,7 @@ def test_fused_ods_scaling(scale_res):
 
 
 @pytest.mark.parametrize("name,scale", [("cfg3_amsua", 0.002), ("cfg3_iasi", 0.004), ("cfg4", 0.03), ("cfg5", 0.05)])
-@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("mode", H.MODES)
 def test_other_configs_small(name, scale, mode):
     """BASELINE.json configs 3-5 at sizes the oracle finishes in seconds (grid shrunk for radiances:
     the oracle's host grids at 0.25 deg x 616 channels would need 20 GB)."""
@@ -356,7 +362,7 @@ def test_other_configs_small(name, scale, mode):
     ref, rf = H.oracle_run(cfg, files, nr)
     out, gf = H.gpu_run(cfg, files, nr, mode)
     assert all(np.array_equal(a, b) for a, b in zip(gf, rf))
-    H.compare(out, ref, l2d, l3d, nr, exact=(mode == cabi.MODE_DETERMINISTIC), tol=TOL_FAST)
+    H.compare(out, ref, l2d, l3d, nr, exact=H.is_det(mode), tol=TOL_FAST)
 
 
 def test_deterministic_is_reproducible_on_clustered_data():
@@ -402,3 +408,28 @@ def test_full_size_file_properties():
     for nm in ("bias_3d", "rtms_3d", "nobs_3d"):
         assert np.array_equal(results[1][nm], getattr(g, nm))
     assert np.array_equal(results[1]["xcov_3d"][..., 0], g.xcov_3d[..., 0])
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg5"])
+def test_staging_overflow_falls_back_to_direct_accumulate(name, monkeypatch):
+    """Tile lists with a tiny capacity: most entries overflow and take the direct fp64-RED path inside
+    K1 while the rest goes through the tiled accumulate -- the sum of both must still be right."""
+    monkeypatch.setenv("GRITAS_B200_STAGE_SLOTS", str(64 * 1024))
+    monkeypatch.setenv("GRITAS_B200_TILE_SHIFT", "10")
+    cfg, files = small(name, 0.1, 3, res=(24, 13))
+    table, l2d, l3d, *_ = H.setup(cfg)
+    for nr in (1, 2):
+        ref, rf = H.oracle_run(cfg, files, nr)
+        out, gf = H.gpu_run(cfg, files, nr, cabi.MODE_FAST)
+        assert all(np.array_equal(a, b) for a, b in zip(gf, rf))
+        H.compare(out, ref, l2d, l3d, nr, exact=False, tol=TOL_FAST)
+
+
+def test_staged_flush_between_files(monkeypatch):
+    """Capacity reached after every file -> the lists are flushed between Accum calls."""
+    monkeypatch.setenv("GRITAS_B200_STAGE_SLOTS", str(256 * 1024))
+    cfg, files = small("cfg2", 0.1, 4)
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 2)
+    out, _ = H.gpu_run(cfg, files, 2, cabi.MODE_FAST, want_flags=False)
+    H.compare(out, ref, l2d, l3d, 2, exact=False, tol=TOL_FAST)
