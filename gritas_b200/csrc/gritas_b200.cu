@@ -97,8 +97,11 @@ struct gritas_b200_ctx {
   bool staging = false;
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
-  size_t tile_smem = 0;
+  size_t tile_smem = 0, p1_smem = 0, p2_smem = 0;
   int tile_ctas = 0;
+  unsigned *fill1_buf = nullptr;  // 2 x PB_MAXB ping-pong bucket counters
+  int fill1_parity = 0;
+  size_t scratch_cap = 0;         // entries allocated for the level-1 scratch (nbuckets * cap1)
   // finalize scratch (reference-layout planes on the device)
   double *out = nullptr;
   size_t out_cap = 0;
@@ -225,18 +228,26 @@ int grid_for(size_t work, int threads, int per_sm) {
 
 template <int NR>
 void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
-  const bool agg = !(h->flags & GRITAS_B200_FLAG_NO_AGGREGATE);
-#define GB_LAUNCH(A, S) \
-  k_accum_fast<NR, A, S><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq, h->sg)
-  if (h->staging) { if (agg) GB_LAUNCH(true, true); else GB_LAUNCH(false, true); }
-  else { if (agg) GB_LAUNCH(true, false); else GB_LAUNCH(false, false); }
-#undef GB_LAUNCH
+  if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
+    k_accum_fast<NR, false><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+  else
+    k_accum_fast<NR, true><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+}
+
+// Tiled fast path, partition kernels of one slice of observations (K1p then K1q).
+template <int NR>
+void launch_partition(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int chunks_per_bucket) {
+  const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
+  const int g1 = std::min(nbatch, 148 * 3 * 4);
+  k_part_obs<NR><<<g1, P1_THREADS, h->p1_smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq, h->sg);
+  k_part_tiles<NR><<<(int)h->sg.nbuckets * chunks_per_bucket, P2_THREADS, h->p2_smem, h->compute>>>(h->g, h->sg,
+                                                                                                     chunks_per_bucket);
 }
 
 // K2t over every tile with staged entries; afterwards the lists are empty.
 template <int NR>
 void launch_tiles(gritas_b200_handle h) {
-  k_tile_accum<NR><<<h->tile_ctas, 1024, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec);
+  k_tile_accum<NR><<<h->tile_ctas, TILE_THREADS, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec);
 }
 
 int flush_stage(gritas_b200_handle h) {
@@ -284,16 +295,57 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     CU(cudaStreamWaitEvent(h->compute, s.copied, 0));
   }
   const size_t smem = h->g.p2_in_smem ? sizeof(double) * (size_t)h->g.nlevs : 0;
-  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
-    if (h->staging) {
-      // keep the expected list fill at or below ~half the capacity; what still overflows (skewed
-      // data) is accumulated directly by K1
-      if (h->staged_upper + (size_t)n > h->stage_slots / 2) {
+  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging) {
+    // tiled path: partition this call's observations into the per-tile lists (slices bound the scratch)
+    const int SLICE = 4 << 20;
+    for (int s0 = 0; s0 < n; s0 += SLICE) {
+      ObsCols cs = c;
+      cs.n = std::min(SLICE, n - s0);
+      cs.lat += s0; cs.lon += s0; cs.lev += s0; cs.kx += s0; cs.kt += s0;
+      for (int ir = 0; ir < h->g.nr; ++ir) cs.d[ir] += s0;
+      if (cs.obs) cs.obs += s0;
+      if (cs.xvec) cs.xvec += s0;
+      if (cs.omf) cs.omf += s0;
+      if (cs.flag) cs.flag += s0;
+      if (cs.time) cs.time += s0;
+      if (cs.flag_out) cs.flag_out += s0;
+      if (s0) h->call_seq += 1;  // the level-miss record is per launch
+      const size_t nb = h->sg.nbuckets;
+      const size_t nbatch = ((size_t)cs.n + P1_BATCH - 1) / P1_BATCH;
+      const size_t cap1 = (3 * (size_t)cs.n / nb + 8 * nbatch + 64 + 7) & ~(size_t)7;
+      if (h->scratch_cap < nb * cap1) {
+        CU(cudaStreamSynchronize(h->compute));
+        for (void *p : {(void *)h->sg.key1, (void *)h->sg.d1[0], (void *)h->sg.d1[1], (void *)h->sg.d1[2]})
+          if (p) CU(cudaFree(p));
+        h->sg.key1 = nullptr;
+        h->sg.d1[0] = h->sg.d1[1] = h->sg.d1[2] = nullptr;
+        h->scratch_cap = 0;
+        const size_t want = nb * cap1 + nb * cap1 / 4;
+        CU(cudaMalloc(&h->sg.key1, sizeof(unsigned) * want));
+        for (int ir = 0; ir < h->g.nr; ++ir) CU(cudaMalloc(&h->sg.d1[ir], sizeof(double) * want));
+        h->scratch_cap = want;
+      }
+      h->sg.cap1 = (unsigned)((h->scratch_cap / nb) & ~(size_t)7);
+      // keep the expected tile-list fill at or below ~half the capacity; what still overflows (skewed data)
+      // is accumulated directly by the partition kernels
+      const size_t add = (size_t)cs.n + (size_t)cs.n / 4;  // entries + padding sentinels
+      if (h->staged_upper + add > h->stage_slots / 2) {
         int rc = flush_stage(h);
         if (rc) return rc;
       }
-      h->staged_upper += (size_t)n;
+      h->staged_upper += add;
+      h->sg.fill1 = h->fill1_buf + (size_t)h->fill1_parity * PB_MAXB;
+      h->sg.fill1_next = h->fill1_buf + (size_t)(h->fill1_parity ^ 1) * PB_MAXB;
+      h->fill1_parity ^= 1;
+      const int cpb = (int)((h->sg.cap1 + P2_BATCH - 1) / P2_BATCH);
+      switch (h->g.nr) {
+        case 1: launch_partition<1>(h, cs, f, cpb); break;
+        case 2: launch_partition<2>(h, cs, f, cpb); break;
+        default: launch_partition<3>(h, cs, f, cpb); break;
+      }
+      h->launches += 2;
     }
+  } else if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
     const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
     const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
     switch (h->g.nr) {
@@ -457,7 +509,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
                 h->nrec >= 4096;
     if (e_on && atoi(e_on) == 0) want = false;
     if (want) {
-      int shift = (nr == 1) ? 13 : (nr == 2 ? 12 : 11);
+      int shift = (nr == 1) ? 12 : 11;
       if (e_shift) shift = atoi(e_shift);
       const int nv = (nr == 1) ? 2 : (nr == 2 ? 5 : 6);
       const size_t T = (size_t)1 << shift;
@@ -465,24 +517,51 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
       size_t free_b = 0, total_b = 0;
       CUC(cudaMemGetInfo(&free_b, &total_b));
       const size_t entry = 4 + 8 * (size_t)nr;
-      size_t slots = e_slots ? (size_t)atoll(e_slots) : std::min((size_t)320 << 20, std::max((size_t)8 << 20, 16 * h->nrec));
+      size_t slots = e_slots ? (size_t)atoll(e_slots) : std::min((size_t)384 << 20, std::max((size_t)8 << 20, 20 * h->nrec));
       slots = std::min(slots, free_b / 4 / entry);
       const size_t ntiles = (h->nrec + T - 1) / T;
+      size_t tpb = 1;                                     // tiles per level-1 bucket
+      while ((ntiles + tpb - 1) / tpb > PB_MAXB) tpb <<= 1;
+      int tsh = 0;
+      while (((size_t)1 << tsh) < tpb) ++tsh;
+      const size_t nbuckets = (ntiles + tpb - 1) / tpb;
       size_t cap = (slots / ntiles) & ~(size_t)31;
-      if (cap >= 256 && smem <= 227 * 1024 && shift >= 8 && shift <= 16) {
+      if (cap >= 256 && smem <= 227 * 1024 && shift >= 8 && shift <= 16 && tpb <= PB_MAXB) {
         h->sg.tile_shift = shift;
+        h->sg.bucket_shift = shift + tsh;
         h->sg.ntiles = (unsigned)ntiles;
-        h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffff);
+        h->sg.nbuckets = (unsigned)nbuckets;
+        h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffe0);
         h->stage_slots = ntiles * (size_t)h->sg.cap;
         h->tile_smem = smem;
         h->tile_ctas = (int)std::min(ntiles, (size_t)1 << 20);
-        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * ntiles));
-        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * ntiles));
+        const size_t nfill = nbuckets * tpb;              // padded: every (bucket, local tile) has a counter
+        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * nfill));
+        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * nfill));
+        CUC(cudaMalloc(&h->fill1_buf, sizeof(unsigned) * 2 * PB_MAXB));
+        CUC(cudaMemset(h->fill1_buf, 0, sizeof(unsigned) * 2 * PB_MAXB));
         CUC(cudaMalloc(&h->sg.skey, sizeof(unsigned) * h->stage_slots));
         for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sg.sd[ir], sizeof(double) * h->stage_slots));
-        if (nr == 1) CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t p2b = g.p2_in_smem ? sizeof(double) * (size_t)nlevs : 0;
+        if (nr == 1) {
+          h->p1_smem = ((part_smem_bytes<1, P1_SCAP>() + 15) & ~(size_t)15) + p2b;
+          h->p2_smem = part_smem_bytes<1, P2_SCAP>();
+          CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+        } else if (nr == 2) {
+          h->p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + p2b;
+          h->p2_smem = part_smem_bytes<2, P2_SCAP>();
+          CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+        } else {
+          h->p1_smem = ((part_smem_bytes<3, P1_SCAP>() + 15) & ~(size_t)15) + p2b;
+          h->p2_smem = part_smem_bytes<3, P2_SCAP>();
+          CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+        }
         h->staging = true;
       }
     }
@@ -508,7 +587,8 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (s.consumed) cudaEventDestroy(s.consumed);
     if (s.copied) cudaEventDestroy(s.copied);
   }
-  for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2]})
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2],
+                  (void *)h->fill1_buf, (void *)h->sg.key1, (void *)h->sg.d1[0], (void *)h->sg.d1[1], (void *)h->sg.d1[2]})
     if (p) cudaFree(p);
   for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
                   (void *)h->keys, (void *)h->idx, (void *)h->keys2, (void *)h->idx2, h->cub_tmp, (void *)h->out})
@@ -623,7 +703,9 @@ int gritas_b200_reset(gritas_b200_handle h) {
   if (rc) return rc;
   CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   if (h->staging) {
-    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * h->sg.ntiles, h->compute));
+    const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
+    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * nfill, h->compute));
+    CU(cudaMemsetAsync(h->fill1_buf, 0, sizeof(unsigned) * 2 * PB_MAXB, h->compute));
     h->staged_upper = 0;
   }
   return 0;

@@ -69,11 +69,19 @@ struct FilterDesc {
 // (record key, residuals) entry to the list of its tile; K2t later accumulates one tile at a time in
 // shared memory.  Lists have a fixed capacity; entries that do not fit are accumulated directly.
 struct StageDesc {
-  unsigned *fill;      // [ntiles] entries appended since the last flush (may exceed cap: clamp)
+  // level 2: one list of compact entries per tile of 2^tile_shift records
+  unsigned *fill;      // [ntiles (padded)] entries appended since the last flush (may exceed cap: clamp)
   unsigned *skey;      // [ntiles * cap]
   double *sd[3];       // [ntiles * cap] per residual column
   unsigned cap, ntiles;
   int tile_shift;
+  // level 1: per-bucket scratch of the current Accum call (a bucket = 2^(bucket_shift-tile_shift) tiles);
+  // small enough to stay in L2 between the two partition kernels
+  unsigned *fill1, *fill1_next;  // [PB_MAXB] ping-pong: the kernel of call n zeroes the counters of call n+1
+  unsigned *key1;
+  double *d1[3];
+  unsigned cap1, nbuckets;
+  int bucket_shift;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -282,10 +290,9 @@ __device__ __forceinline__ void load_p2(const GridDesc &g, double *s_p2) {
 // K1+K2a fused: stream the columns, classify, accumulate with fp64 RED into the record grid.
 // AGG: lanes of a warp that hit the same box (__match_any_sync) are summed in registers first and
 // only the lowest lane issues the atomics.
-template <int NR, bool AGG, bool STAGE>
+template <int NR, bool AGG>
 __global__ void __launch_bounds__(ACC_THREADS)
-k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
-             const StageDesc sg) {
+k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq) {
   extern __shared__ double s_p2[];
   load_p2(g, s_p2);
   const double *p2s = g.p2_in_smem ? s_p2 : g.p2;
@@ -315,21 +322,8 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
       if (NR == 2) sxy = __dmul_rn(sx[0], sx[1]);
       double cnt = 1.0;
       bool issue = key != KEY_NONE;
-      if (STAGE && issue) {
-        // append to the tile's list; the scattered 4/8-byte stores are merged into full sectors by L2
-        // (the list tails of all tiles stay resident), so HBM sees each staged byte once
-        const unsigned tile = key >> sg.tile_shift;
-        const unsigned pos = atomicAdd(sg.fill + tile, 1u);
-        if (pos < sg.cap) {
-          const size_t at = (size_t)tile * sg.cap + pos;
-          sg.skey[at] = key;
-#pragma unroll
-          for (int ir = 0; ir < NR; ++ir) sg.sd[ir][at] = sx[ir];
-          issue = false;
-        }
-      }
-      if (AGG && (!STAGE || __any_sync(0xffffffffu, issue))) {
-        const unsigned peers = __match_any_sync(0xffffffffu, issue ? key : KEY_NONE);  // staged lanes stay out
+      if (AGG) {
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
         const bool multi = issue && (peers & (peers - 1));
         if (__any_sync(0xffffffffu, multi)) {
           const int leader = __ffs(peers) - 1;
@@ -426,15 +420,281 @@ k_segment_sum(const GridDesc g, const ObsCols c, const FilterDesc f, const unsig
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2t: tiled accumulate.  One CTA per tile: the tile's count / sum / sum-of-squares planes live in
-// shared memory (privatised histogram), the staged entries stream in coalesced, lanes of a warp that
-// hit the same box are combined first (__match_any_sync), the tile is then added to the HBM records
-// with plain coalesced read-modify-writes (the tile is owned by this CTA: no global atomics).
-template <int NR>
-struct TilePlanes { static constexpr int NV = (NR == 1) ? 2 : (NR == 2 ? 5 : 6); };
+// Tiled fast path, part 1: two-level partition of the accepted observations into per-tile lists.
+//
+// Scattered 4/8-byte stores run at ~40 G/s on B200 (profiles/r1_microbench_tickets_scatter.txt): far
+// below what this path needs.  Both partition kernels therefore group a batch of entries by
+// destination in shared memory and write every destination's entries as one run whose start and
+// length are multiples of 8 entries (32 B of keys, 64 B of residuals): only full, aligned sectors
+// reach L2.  Runs are padded with KEY_NONE sentinels; readers skip them.
+//   K1p  k_part_obs    columns -> classify (filter, table, box index) -> per-BUCKET scratch lists
+//   K1q  k_part_tiles  bucket scratch (still in L2) -> per-TILE lists in HBM
+constexpr int PB_MAXB = 128;                      // destinations per grouping step
+constexpr unsigned PB_OVERFLOW = 0xFFFFFFFFu;
+// K1p: 256 threads x 8 observations, 3 CTAs per SM so that load / group / write-out phases of
+// different CTAs overlap.  K1q: 1024 threads x 4 entries (entries only, few registers), 2 CTAs per SM.
+constexpr int P1_THREADS = 256, P1_ITEMS = 8, P1_BATCH = P1_THREADS * P1_ITEMS, P1_SCAP = P1_BATCH + 8 * PB_MAXB;
+constexpr int P2_THREADS = 1024, P2_ITEMS = 4, P2_BATCH = P2_THREADS * P2_ITEMS, P2_SCAP = P2_BATCH + 8 * PB_MAXB;
 
 template <int NR>
-__global__ void __launch_bounds__(1024, 1)
+struct PartView {
+  double *d[NR];        // [SCAP] grouped residuals
+  unsigned *key;        // [SCAP] grouped keys
+  unsigned *cnt;        // [PB_MAXB] entries per destination in this batch
+  unsigned *off;        // [PB_MAXB] start of the destination's (padded) group in the staging arrays
+  unsigned *run;        // [PB_MAXB] start of the run inside the destination's global list, or PB_OVERFLOW
+  unsigned *total;      // padded entries in this batch
+  unsigned char *grp;   // [SCAP/8] destination of each group of 8 staged entries
+};
+
+template <int NR, int SCAP>
+__host__ __device__ constexpr size_t part_smem_bytes() {
+  return sizeof(double) * NR * SCAP + sizeof(unsigned) * (SCAP + 3 * PB_MAXB + 4) + SCAP / 8;
+}
+
+template <int NR, int SCAP>
+__device__ __forceinline__ PartView<NR> part_view(unsigned char *smem) {
+  PartView<NR> v;
+  double *dp = reinterpret_cast<double *>(smem);
+#pragma unroll
+  for (int ir = 0; ir < NR; ++ir) v.d[ir] = dp + (size_t)ir * SCAP;
+  unsigned *up = reinterpret_cast<unsigned *>(dp + (size_t)NR * SCAP);
+  v.key = up; up += SCAP;
+  v.cnt = up; up += PB_MAXB;
+  v.off = up; up += PB_MAXB;
+  v.run = up; up += PB_MAXB;
+  v.total = up; up += 4;
+  v.grp = reinterpret_cast<unsigned char *>(up);
+  return v;
+}
+
+// After the counting pass: lay the destinations out back to back (each padded to a multiple of 8),
+// reserve the same number of entries at the tail of every destination's global list, write the
+// pad sentinels and the group->destination map.  Called by all threads of the CTA.
+template <int NR>
+__device__ __forceinline__ void part_layout(const PartView<NR> &v, int nb, unsigned *__restrict__ g_fill,
+                                            unsigned *__restrict__ g_key, unsigned cap, unsigned list_first) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 32) {
+    unsigned p[4], local = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = lane * 4 + q;
+      const unsigned c = b < nb ? v.cnt[b] : 0u;
+      p[q] = (c + 7u) & ~7u;
+      local += p[q];
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    unsigned at = incl - local;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v.off[lane * 4 + q] = at;
+      at += p[q];
+    }
+    if (lane == 31) *v.total = incl;
+  }
+  __syncthreads();
+  if (tid < nb) {
+    const unsigned c = v.cnt[tid], padded = (c + 7u) & ~7u, off = v.off[tid];
+    unsigned run = 0;
+    if (c) {
+      const unsigned gpos = atomicAdd(g_fill + list_first + tid, padded);
+      if (gpos + padded <= cap) {
+        run = gpos;
+      } else {
+        // does not fit: these entries are accumulated directly by the caller.  Exactly one reservation
+        // straddles the capacity; it closes the unwritten gap with sentinels so readers never see garbage.
+        run = PB_OVERFLOW;
+        unsigned *lk = g_key + (size_t)(list_first + tid) * cap;
+        for (unsigned e = gpos; e < cap; ++e) lk[e] = KEY_NONE;
+      }
+      for (unsigned e = c; e < padded; ++e) {
+        v.key[off + e] = KEY_NONE;
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) v.d[ir][off + e] = 0.0;
+      }
+      for (unsigned gq = off >> 3; gq < ((off + padded) >> 3); ++gq) v.grp[gq] = (unsigned char)tid;
+    }
+    v.run[tid] = run;
+  }
+  __syncthreads();
+}
+
+// Staged groups -> runs at the tails of the global lists: consecutive threads write consecutive
+// entries, every group of 8 is one aligned 32 B (keys) / 64 B (residuals) sector.
+template <int NR>
+__device__ __forceinline__ void part_writeout(const PartView<NR> &v, unsigned cap, unsigned list_first,
+                                              unsigned *__restrict__ g_key, double *const (&g_d)[3]) {
+  const unsigned total = *v.total;
+  for (unsigned s = threadIdx.x * 2u; s < total; s += blockDim.x * 2u) {  // 2 entries per thread: 8 B + 16 B stores
+    const unsigned b = v.grp[s >> 3], run = v.run[b];
+    if (run == PB_OVERFLOW) continue;
+    const size_t gi = (size_t)(list_first + b) * cap + run + (s - v.off[b]);
+    *reinterpret_cast<uint2 *>(g_key + gi) = *reinterpret_cast<const uint2 *>(v.key + s);
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir)
+      *reinterpret_cast<double2 *>(g_d[ir] + gi) = *reinterpret_cast<const double2 *>(v.d[ir] + s);
+  }
+}
+
+// Direct accumulate of one entry (overflow of a list): the same fp64 RED the direct path uses.
+template <int NR>
+__device__ __forceinline__ void red_entry(const GridDesc &g, unsigned key, const double (&d)[NR]) {
+  double sq[NR];
+#pragma unroll
+  for (int ir = 0; ir < NR; ++ir) sq[ir] = __dmul_rn(d[ir], d[ir]);
+  const double sxy = (NR == 2) ? __dmul_rn(d[0], d[NR - 1]) : 0.0;
+  red_record<NR>(g.acc + (size_t)key * (size_t)g.rs, 1.0, d, sq, sxy);
+}
+
+// K1p: a batch of P1_BATCH observations per CTA iteration.
+template <int NR>
+__global__ void __launch_bounds__(P1_THREADS, 2)
+k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
+           const StageDesc sg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PartView<NR> v = part_view<NR, P1_SCAP>(smem_raw);
+  double *s_p2 = reinterpret_cast<double *>(smem_raw + ((part_smem_bytes<NR, P1_SCAP>() + 15) & ~(size_t)15));
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid < PB_MAXB) sg.fill1_next[tid] = 0u;  // counters of the NEXT call
+  load_p2(g, s_p2);
+  const double *p2s = g.p2_in_smem ? s_p2 : g.p2;
+  const int nb = (int)sg.nbuckets;
+  const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    if (tid < PB_MAXB) v.cnt[tid] = 0u;
+    __syncthreads();
+    unsigned rkey[P1_ITEMS], rrank[P1_ITEMS];
+    double rd[NR][P1_ITEMS];
+#pragma unroll
+    for (int h = 0; h < P1_ITEMS / 4; ++h) {
+      const int base = batch * P1_BATCH + (h * P1_THREADS + tid) * 4;
+      Obs4<NR> o;
+      int fa[4];
+      if (base < c.n) load_obs4<NR>(c, f, base, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = h * 4 + j;
+        unsigned key = KEY_NONE;
+        fa[j] = 0;
+        if (base + j < c.n)
+          key = classify(g, f, p2s, o.lat[j], o.lon[j], o.lev[j], o.kx[j], o.kt[j], o.fl[j], o.tm[j], base + j, st,
+                         call_seq, fa[j]);
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) {
+          double d = o.d[ir][j];
+          if (f.scale_res && key != KEY_NONE) d = scale_residual(f, c, d, base + j);
+          rd[ir][q] = d;
+        }
+        rkey[q] = key;
+        rrank[q] = (key != KEY_NONE) ? atomicAdd(v.cnt + (key >> sg.bucket_shift), 1u) : 0u;
+      }
+      if (c.flag_out && base < c.n) {
+        if (c.aligned && base + 3 < c.n) {
+          *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (base + j < c.n) c.flag_out[base + j] = fa[j];
+        }
+      }
+    }
+    __syncthreads();
+    part_layout<NR>(v, nb, sg.fill1, sg.key1, sg.cap1, 0u);
+#pragma unroll
+    for (int q = 0; q < P1_ITEMS; ++q) {
+      if (rkey[q] == KEY_NONE) continue;
+      const unsigned b = rkey[q] >> sg.bucket_shift;
+      double d[NR];
+#pragma unroll
+      for (int ir = 0; ir < NR; ++ir) d[ir] = rd[ir][q];
+      if (v.run[b] == PB_OVERFLOW) {
+        red_entry<NR>(g, rkey[q], d);
+      } else {
+        const unsigned s = v.off[b] + rrank[q];
+        v.key[s] = rkey[q];
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) v.d[ir][s] = d[ir];
+      }
+    }
+    __syncthreads();
+    part_writeout<NR>(v, sg.cap1, 0u, sg.key1, sg.d1);
+    __syncthreads();
+  }
+  finish_status(st, call_seq, c.lev);
+}
+
+// K1q: CTA (bucket, chunk) regroups P2_BATCH scratch entries of one bucket by tile.
+template <int NR>
+__global__ void __launch_bounds__(P2_THREADS, 1)
+k_part_tiles(const GridDesc g, const StageDesc sg, int chunks_per_bucket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PartView<NR> v = part_view<NR, P2_SCAP>(smem_raw);
+  const int tid = threadIdx.x;
+  const unsigned b = blockIdx.x / (unsigned)chunks_per_bucket, chunk = blockIdx.x % (unsigned)chunks_per_bucket;
+  const unsigned n = min(sg.fill1[b], sg.cap1);
+  const unsigned start = chunk * (unsigned)P2_BATCH;
+  if (start >= n) return;
+  const int tsh = sg.bucket_shift - sg.tile_shift;
+  const int nt = 1 << tsh;                        // tiles per bucket (<= PB_MAXB)
+  if (tid < PB_MAXB) v.cnt[tid] = 0u;
+  __syncthreads();
+  const size_t src = (size_t)b * sg.cap1 + start;
+  unsigned rkey[P2_ITEMS], rrank[P2_ITEMS];
+  double rd[NR][P2_ITEMS];
+#pragma unroll
+  for (int q = 0; q < P2_ITEMS; ++q) {
+    const unsigned e = (unsigned)(q * P2_THREADS + tid);
+    rkey[q] = (start + e < n) ? sg.key1[src + e] : KEY_NONE;
+  }
+#pragma unroll
+  for (int q = 0; q < P2_ITEMS; ++q) {
+    const unsigned e = (unsigned)(q * P2_THREADS + tid);
+    const bool live = rkey[q] != KEY_NONE;
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) rd[ir][q] = live ? sg.d1[ir][src + e] : 0.0;
+    rrank[q] = live ? atomicAdd(v.cnt + ((rkey[q] >> sg.tile_shift) & (unsigned)(nt - 1)), 1u) : 0u;
+  }
+  __syncthreads();
+  part_layout<NR>(v, nt, sg.fill, sg.skey, sg.cap, b << tsh);
+#pragma unroll
+  for (int q = 0; q < P2_ITEMS; ++q) {
+    if (rkey[q] == KEY_NONE) continue;
+    const unsigned t = (rkey[q] >> sg.tile_shift) & (unsigned)(nt - 1);
+    double d[NR];
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) d[ir] = rd[ir][q];
+    if (v.run[t] == PB_OVERFLOW) {
+      red_entry<NR>(g, rkey[q], d);
+    } else {
+      const unsigned s = v.off[t] + rrank[q];
+      v.key[s] = rkey[q];
+#pragma unroll
+      for (int ir = 0; ir < NR; ++ir) v.d[ir][s] = d[ir];
+    }
+  }
+  __syncthreads();
+  part_writeout<NR>(v, sg.cap, b << tsh, sg.skey, sg.sd);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled fast path, part 2 (K2t): one CTA per tile.  The tile's count / sum / sum-of-squares planes
+// live in shared memory (privatised histogram); the tile's list streams in coalesced; lanes of a warp
+// that hit the same box are combined first (__match_any_sync) and only then touch shared memory;
+// the tile is finally added to the HBM records with plain coalesced read-modify-writes (the tile is
+// owned by this CTA: no global atomics).
+template <int NR>
+struct TilePlanes { static constexpr int NV = (NR == 1) ? 2 : (NR == 2 ? 5 : 6); };
+constexpr int TILE_THREADS = 512;
+constexpr int TILE_ILP = 2;
+
+template <int NR>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
 k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec) {
   constexpr int NV = TilePlanes<NR>::NV;
   extern __shared__ double s_val[];                       // NV planes of T doubles, then T counts
@@ -448,69 +708,98 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec) {
     for (unsigned e = threadIdx.x; e < T; e += blockDim.x) s_cnt[e] = 0u;
     __syncthreads();
     const size_t base = (size_t)tile * sg.cap;
-    const unsigned nw = (n + 31u) & ~31u;                 // whole warps iterate together
-    for (unsigned r = threadIdx.x; r < nw; r += blockDim.x) {
-      const bool live = r < n;
-      unsigned b = 0xFFFFFFFFu;
-      double d[NR];
+    const unsigned stride = blockDim.x * TILE_ILP;
+    const unsigned nround = (n + stride - 1) / stride * stride;   // whole warps iterate together
+    for (unsigned r0 = threadIdx.x; r0 < nround; r0 += stride) {
+      unsigned bx[TILE_ILP];
+      double d[TILE_ILP][NR];
 #pragma unroll
-      for (int ir = 0; ir < NR; ++ir) d[ir] = 0.0;
-      if (live) {
-        b = __ldcs(sg.skey + base + r) & (T - 1u);
+      for (int u = 0; u < TILE_ILP; ++u) {                // all loads of the round first
+        const unsigned r = r0 + u * blockDim.x;
+        const unsigned key = (r < n) ? __ldcs(sg.skey + base + r) : KEY_NONE;
+        bx[u] = (key == KEY_NONE) ? 0xFFFFFFFFu : (key & (T - 1u));
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) d[ir] = __ldcs(sg.sd[ir] + base + r);
+        for (int ir = 0; ir < NR; ++ir) d[u][ir] = (r < n) ? __ldcs(sg.sd[ir] + base + r) : 0.0;
       }
-      double v[NV];
-      if (NR == 1) { v[0] = d[0]; v[1] = __dmul_rn(d[0], d[0]); }
-      if (NR == 2) {
-        v[0] = d[0]; v[1] = __dmul_rn(d[0], d[0]); v[2] = d[NR - 1]; v[3] = __dmul_rn(d[NR - 1], d[NR - 1]);
-        v[4] = __dmul_rn(d[0], d[NR - 1]);
-      }
-      if (NR == 3) {
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) { v[2 * ir] = d[ir]; v[2 * ir + 1] = __dmul_rn(d[ir], d[ir]); }
-      }
-      unsigned cnt = 1u;
-      bool issue = live;
-      // warp aggregation: only pays (and only runs) when lanes collide, i.e. clustered data
-      const unsigned peers = __match_any_sync(0xffffffffu, b);
-      const bool multi = live && (peers & (peers - 1u));
-      if (__any_sync(0xffffffffu, multi)) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(peers) - 1;
-        const int npeer = live ? __popc(peers) : 1;
-        const int maxc = __reduce_max_sync(0xffffffffu, npeer);
-        unsigned others = peers & ~(1u << leader);
-        for (int it = 1; it < maxc; ++it) {
-          const int src = others ? (__ffs(others) - 1) : lane;
-          others &= others - 1u;
-          const bool take = (lane == leader) && (it < npeer);
-#pragma unroll
-          for (int q = 0; q < NV; ++q) {
-            const double a = __shfl_sync(0xffffffffu, v[q], src);
-            if (take) v[q] = __dadd_rn(v[q], a);
-          }
+      for (int u = 0; u < TILE_ILP; ++u) {
+        const unsigned b = bx[u];
+        const bool live = b != 0xFFFFFFFFu;
+        double v[NV];
+        if (NR == 1) { v[0] = d[u][0]; v[1] = __dmul_rn(d[u][0], d[u][0]); }
+        if (NR == 2) {
+          v[0] = d[u][0]; v[1] = __dmul_rn(d[u][0], d[u][0]);
+          v[2] = d[u][NR - 1]; v[3] = __dmul_rn(d[u][NR - 1], d[u][NR - 1]);
+          v[4] = __dmul_rn(d[u][0], d[u][NR - 1]);
         }
-        cnt = (unsigned)npeer;
-        issue = live && (lane == leader);
-      }
-      if (issue) {
-        atomicAdd(s_cnt + b, cnt);
+        if (NR == 3) {
 #pragma unroll
-        for (int q = 0; q < NV; ++q) atomicAdd(s_val + (size_t)q * T + b, v[q]);
+          for (int ir = 0; ir < NR; ++ir) { v[2 * ir] = d[u][ir]; v[2 * ir + 1] = __dmul_rn(d[u][ir], d[u][ir]); }
+        }
+        unsigned cnt = 1u;
+        bool issue = live;
+        // warp aggregation: only pays (and only runs) when lanes collide, i.e. clustered data
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const bool multi = live && (peers & (peers - 1u));
+        if (__any_sync(0xffffffffu, multi)) {
+          const int lane = threadIdx.x & 31;
+          const int leader = __ffs(peers) - 1;
+          const int npeer = live ? __popc(peers) : 1;
+          const int maxc = __reduce_max_sync(0xffffffffu, npeer);
+          unsigned others = peers & ~(1u << leader);
+          for (int it = 1; it < maxc; ++it) {
+            const int src = others ? (__ffs(others) - 1) : lane;
+            others &= others - 1u;
+            const bool take = (lane == leader) && (it < npeer);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              const double a = __shfl_sync(0xffffffffu, v[q], src);
+              if (take) v[q] = __dadd_rn(v[q], a);
+            }
+          }
+          cnt = (unsigned)npeer;
+          issue = live && (lane == leader);
+        }
+        if (issue) {
+          atomicAdd(s_cnt + b, cnt);
+#pragma unroll
+          for (int q = 0; q < NV; ++q) atomicAdd(s_val + (size_t)q * T + b, v[q]);
+        }
       }
     }
     __syncthreads();
-    // add the tile to the HBM records: element e of the tile's span is (box e >> rs_shift, slot e & (rs-1))
+    // add the tile to the HBM records: element e of the tile's span is (box e >> rs_shift, slot e & (rs-1));
+    // each thread handles pairs of doubles (16 B), four pairs in flight
     const size_t first = (size_t)tile << sg.tile_shift;
     const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
-    double *span = g.acc + first * (size_t)g.rs;
-    for (unsigned e = threadIdx.x; e < (nb << rs_shift); e += blockDim.x) {
-      const unsigned bx = e >> rs_shift, slot = e & ((1u << rs_shift) - 1u);
-      const unsigned cn = s_cnt[bx];
-      if (cn == 0u || slot > (unsigned)NV) continue;
-      const double add = (slot == 0u) ? (double)cn : s_val[(size_t)(slot - 1u) * T + bx];
-      span[e] = __dadd_rn(span[e], add);
+    double2 *span = reinterpret_cast<double2 *>(g.acc + first * (size_t)g.rs);
+    const unsigned npair = (nb << rs_shift) >> 1;
+    for (unsigned e0 = threadIdx.x; e0 < npair; e0 += blockDim.x * 4u) {
+      double2 cur[4], add[4];
+      bool any[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned e = e0 + u * blockDim.x;
+        any[u] = false;
+        if (e < npair) {
+          const unsigned el = e << 1, bxi = el >> rs_shift, slot = el & ((1u << rs_shift) - 1u);
+          const unsigned cn = s_cnt[bxi];
+          if (cn != 0u && slot <= (unsigned)NV) {
+            any[u] = true;
+            add[u].x = (slot == 0u) ? (double)cn : s_val[(size_t)(slot - 1u) * T + bxi];
+            add[u].y = (slot + 1u <= (unsigned)NV) ? s_val[(size_t)slot * T + bxi] : 0.0;
+            cur[u] = span[e];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (any[u]) {
+          cur[u].x = __dadd_rn(cur[u].x, add[u].x);
+          cur[u].y = __dadd_rn(cur[u].y, add[u].y);
+          span[e0 + u * blockDim.x] = cur[u];
+        }
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) sg.fill[tile] = 0u;

@@ -66,6 +66,31 @@ __global__ void k_stream(const double2 *a, const double2 *b, const double2 *c, c
   if (s == 1.2345) out[0] = s;
 }
 
+// E: ticket atomics (atomicAdd with return) on `nc` counters, optionally followed by dependent scattered stores
+template <int ILP, bool STORE>
+__global__ void k_ticket(unsigned *cnt, unsigned nc, unsigned cap, unsigned *okey, double *od0, double *od1, uint32_t nvisit,
+                         uint32_t seed) {
+  for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * ILP; i0 < nvisit; i0 += gridDim.x * blockDim.x * ILP) {
+    unsigned t[ILP], pos[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) t[k] = (unsigned)(((uint64_t)hash32((i0 + k) * 2654435761u + seed) * nc) >> 32);
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) pos[k] = atomicAdd(cnt + t[k], 1u);
+    if (STORE) {
+#pragma unroll
+      for (int k = 0; k < ILP; ++k) {
+        const size_t at = (size_t)t[k] * cap + (pos[k] % cap);
+        okey[at] = i0 + k; od0[at] = 1.0 * k; od1[at] = 2.0 * k;
+      }
+    } else {
+      unsigned s = 0;
+#pragma unroll
+      for (int k = 0; k < ILP; ++k) s += pos[k];
+      if (s == 0xdeadbeef) okey[0] = s;
+    }
+  }
+}
+
 template <typename F>
 float timeit(F f, int reps) {
   cudaEvent_t a, b;
@@ -85,7 +110,7 @@ int main() {
   double *acc; CK(cudaMalloc(&acc, maxbytes)); CK(cudaMemset(acc, 0, maxbytes));
   const uint32_t nvisit = 16u << 20;
   printf("A: fp64 RED, 64 B records, %u visits\n", nvisit);
-  for (size_t mb : {8, 16, 32, 64, 96, 128, 256, 512, 1024, 1728}) {
+  for (size_t mb : {32, 1728}) {
     uint32_t nrec = (uint32_t)((mb << 20) / 64);
     for (int nred : {1, 3, 6}) {
       float ms = 0;
@@ -100,6 +125,32 @@ int main() {
       printf("  region %5zu MB  nred %d : %8.3f ms  %7.2f G visits/s  %7.2f G red/s\n", mb, nred, ms, nvisit / ms / 1e6,
              (double)nvisit * nred / ms / 1e6);
     }
+  }
+  {
+    const uint32_t nv = 32u << 20;
+    const size_t slots = (size_t)256 << 20;
+    unsigned *cnt, *okey; double *od0, *od1;
+    CK(cudaMalloc(&cnt, 4u << 20)); CK(cudaMalloc(&okey, slots * 4)); CK(cudaMalloc(&od0, slots * 8)); CK(cudaMalloc(&od1, slots * 8));
+    printf("E: ticket atomics with return, %u visits (1.21M-visit launches emulate one file)\n", nv);
+    for (unsigned nc : {256u, 1024u, 6618u, 13236u, 52944u, 423552u}) {
+      unsigned cap = (unsigned)(slots / nc);
+      for (int store = 0; store < 2; ++store) {
+        for (int ilp : {1, 4}) {
+          CK(cudaMemset(cnt, 0, 4u << 20));
+          uint32_t seed = 3;
+          auto f = [&]() {
+            seed += 11;
+            if (store) { if (ilp == 1) k_ticket<1, true><<<148 * 8, 256>>>(cnt, nc, cap, okey, od0, od1, nv, seed);
+                         else k_ticket<4, true><<<148 * 8, 256>>>(cnt, nc, cap, okey, od0, od1, nv, seed); }
+            else { if (ilp == 1) k_ticket<1, false><<<148 * 8, 256>>>(cnt, nc, cap, okey, od0, od1, nv, seed);
+                   else k_ticket<4, false><<<148 * 8, 256>>>(cnt, nc, cap, okey, od0, od1, nv, seed); }
+          };
+          float ms = timeit(f, 3);
+          printf("  counters %7u store %d ilp %d : %8.3f ms  %7.2f G tickets/s\n", nc, store, ilp, ms, nv / ms / 1e6);
+        }
+      }
+    }
+    cudaFree(cnt); cudaFree(okey); cudaFree(od0); cudaFree(od1);
   }
   uint32_t *o32; CK(cudaMalloc(&o32, 1024));
   double *o64; CK(cudaMalloc(&o64, 1024));
