@@ -273,15 +273,20 @@ def run_b200(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    host_enqueue = []
+
     def step(cols, host_out=None, marks=None):
         G.reset()
         if marks is not None:
             marks[0].record(stream)
+        th = time.perf_counter()
         for a in cols:
             rc = L.gritas_b200_accum_ods(*a)
             if rc:
                 raise RuntimeError(f"accum_ods rc={rc}: {G._err()}")
+        host_enqueue.append(time.perf_counter() - th)
         if marks is not None:
+            G.barrier()                # the library stream waits for the worker streams (no host sync)
             marks[1].record(stream)
         G.flush()
         if marks is not None:
@@ -314,6 +319,7 @@ def run_b200(args):
     barrier()
     sampler.active = False
     c1 = G.counters()
+    host_ms = 1e3 * float(np.mean(host_enqueue[-args.steps:]))
     ms = e0.elapsed_time(e1) / args.steps
     accum_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
     flush_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
@@ -377,7 +383,8 @@ def run_b200(args):
             "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
                        "per_rank": "each rank bins its own month; one NCCL all-reduce of the partial grids, then finalize",
                        "l2": "inputs (7.8 GB/step) and accumulators (1.7 GB) both exceed the 126 MB L2; no flush needed"},
-            "accumulate_ms_per_step": accum_ms, "tile_flush_ms_per_step": flush_ms, "gpu_launches": int(launches_per_step * args.steps),
+            "accumulate_ms_per_step": accum_ms, "tile_flush_ms_per_step": flush_ms,
+            "host_enqueue_ms_per_step": host_ms, "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

@@ -36,7 +36,7 @@ IOPT_OMF_OMA = 101
 # every symbol include/gritas_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "gritas_b200_create", "gritas_b200_destroy", "gritas_b200_pint", "gritas_b200_kxkt", "gritas_b200_accum",
-    "gritas_b200_accum_ods", "gritas_b200_flush", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
+    "gritas_b200_accum_ods", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
     "gritas_b200_get_raw", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
     "gritas_b200_allreduce", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
     "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
@@ -70,6 +70,7 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_sync.argtypes = [_P, C.POINTER(_D)]
     L.gritas_b200_reset.argtypes = [_P]
     L.gritas_b200_flush.argtypes = [_P]
+    L.gritas_b200_barrier.argtypes = [_P]
     L.gritas_b200_norm.argtypes = [_P, _I, _I] + [_P] * 10
     L.gritas_b200_norm_device.argtypes = [_P, _I, _I] + [C.POINTER(_P)] * 10
     L.gritas_b200_get_raw.argtypes = [_P] + [_P] * 8

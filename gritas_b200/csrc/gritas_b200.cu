@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
@@ -26,6 +27,7 @@ using namespace gb200;
 namespace {
 
 constexpr int NSLOT = 2;   // staging slots (double buffering)
+constexpr int NWK = 3;     // worker streams of the tiled path: partition kernels of consecutive calls overlap
 constexpr int NCOL = 12;   // staged columns per slot
 enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME };
 
@@ -68,6 +70,7 @@ struct Slot {
   size_t flag_out_cap = 0;
   cudaEvent_t consumed = nullptr;  // kernel that read this slot has finished
   cudaEvent_t copied = nullptr;    // H2D copies into this slot have finished
+  bool in_use = false;             // staging buffers of this slot are referenced by a queued kernel
 };
 
 }  // namespace
@@ -79,6 +82,7 @@ struct gritas_b200_ctx {
   size_t nrec = 0;
   int *d_table = nullptr;
   double *d_p1 = nullptr, *d_p2 = nullptr;
+  unsigned short *d_lut = nullptr;
   Status *d_status = nullptr;
   Status *h_status = nullptr;  // pinned
   cudaStream_t compute = nullptr, copy = nullptr;
@@ -99,9 +103,16 @@ struct gritas_b200_ctx {
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
   size_t tile_smem = 0, p1_smem = 0, p2_smem = 0;
   int tile_ctas = 0;
-  unsigned *fill1_buf = nullptr;  // 2 x PB_MAXB ping-pong bucket counters
-  int fill1_parity = 0;
-  size_t scratch_cap = 0;         // entries allocated for the level-1 scratch (nbuckets * cap1)
+  size_t scratch_cap = 0;         // slots allocated for the level-1 scratch (nbuckets * nbatch_cap * c1)
+  // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
+  // the GPU; consecutive calls run on different streams (own level-1 scratch, own level-miss record) and
+  // overlap.  Everything that reads or resets the accumulators runs on `compute` after join_workers().
+  cudaStream_t wk[NWK] = {};
+  cudaEvent_t wk_done[NWK] = {};
+  bool wk_pending[NWK] = {};
+  StageDesc sgw[NWK] = {};
+  int next_wk = 0;
+  cudaEvent_t main_ev = nullptr;  // last accumulator-wide operation queued on `compute`
   // finalize scratch (reference-layout planes on the device)
   double *out = nullptr;
   size_t out_cap = 0;
@@ -133,7 +144,11 @@ int fail(gritas_b200_handle h, int rc, const char *fmt, ...) {
   } while (0)
 
 // Where does a caller pointer live?  0 pageable host, 1 pinned host, 2 device / managed.
-int mem_kind(const void *p) {
+// cudaPointerGetAttributes costs about a microsecond and an Accum call passes nine columns, so the
+// answers are kept in a small direct-mapped cache (drivers reuse their column buffers).  Device and
+// host addresses never alias under UVA; a pageable/pinned mix-up after a free + realloc at the same
+// address only changes how the copy is staged, never its result.
+int mem_kind_query(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
@@ -142,6 +157,23 @@ int mem_kind(const void *p) {
   if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 2;
   if (a.type == cudaMemoryTypeHost) return 1;
   return 0;
+}
+
+struct KindCache {
+  static constexpr int N = 4096;
+  const void *ptr[N] = {};
+  signed char kind[N] = {};
+};
+thread_local KindCache g_kinds;
+
+int mem_kind(const void *p) {
+  if (!p) return 0;
+  const size_t slot = (((uintptr_t)p >> 4) * 0x9E3779B97F4A7C15ull >> 40) % KindCache::N;
+  if (g_kinds.ptr[slot] == p) return g_kinds.kind[slot];
+  const int k = mem_kind_query(p);
+  g_kinds.ptr[slot] = p;
+  g_kinds.kind[slot] = (signed char)k;
+  return k;
 }
 
 int grow_dev(gritas_b200_handle h, void **p, size_t *cap, size_t bytes) {
@@ -173,6 +205,10 @@ int stage(gritas_b200_handle h, Slot &s, int c, const void *src, size_t bytes, c
   if (!src || bytes == 0) { *out = src ? src : nullptr; return 0; }
   const int kind = mem_kind(src);
   if (kind == 2) { *out = src; return 0; }
+  if (s.in_use) {  // first overwrite of this slot in this call: the kernel that last read it must be done
+    CU(cudaEventSynchronize(s.consumed));
+    s.in_use = false;
+  }
   int rc = grow_dev(h, &s.dev[c], &s.dev_cap[c], bytes);
   if (rc) return rc;
   const void *from = src;
@@ -192,23 +228,42 @@ int stage(gritas_b200_handle h, Slot &s, int c, const void *src, size_t bytes, c
 bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
 int clear_status(gritas_b200_handle h) {
-  Status st;
-  st.first_bad = BAD_NONE;
-  st.bad_lev = 0.0;
-  st.ticket = 0;
-  st.pad = 0;
-  CU(cudaMemcpyAsync(h->d_status, &st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
+  Status st[NWK + 1];
+  for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.ticket = 0; q.pad = 0; }
+  CU(cudaMemcpyAsync(h->d_status, st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
   CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+// `compute` waits for every partition kernel queued on the worker streams (no host synchronisation).
+int join_workers(gritas_b200_handle h) {
+  for (int w = 0; w < NWK; ++w)
+    if (h->wk_pending[w]) {
+      CU(cudaStreamWaitEvent(h->compute, h->wk_done[w], 0));
+      h->wk_pending[w] = false;
+    }
+  return 0;
+}
+
+// Marks an accumulator-wide operation on `compute` (reset, flush, add_raw): later partition kernels on the
+// worker streams must not start before it.
+int mark_main(gritas_b200_handle h) {
+  if (h->main_ev) CU(cudaEventRecord(h->main_ev, h->compute));
   return 0;
 }
 
 // Waits for the compute stream and converts a recorded level miss into the return code.
 int drain(gritas_b200_handle h, double *bad_lev) {
-  CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status), cudaMemcpyDeviceToHost, h->compute));
+  int jr = join_workers(h);
+  if (jr) return jr;
+  CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status) * (NWK + 1), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaStreamSynchronize(h->compute));
-  if (h->h_status->first_bad != BAD_NONE) {
-    const double lev = h->h_status->bad_lev;
-    const unsigned long long fb = h->h_status->first_bad;
+  int best = 0;  // earliest (call, observation) over the streams
+  for (int q = 1; q <= NWK; ++q)
+    if (h->h_status[q].first_bad < h->h_status[best].first_bad) best = q;
+  if (h->h_status[best].first_bad != BAD_NONE) {
+    const double lev = h->h_status[best].bad_lev;
+    const unsigned long long fb = h->h_status[best].first_bad;
     if (bad_lev) *bad_lev = lev;
     int rc = clear_status(h);
     if (rc) return rc;
@@ -234,14 +289,20 @@ void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, in
     k_accum_fast<NR, true><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
 }
 
-// Tiled fast path, partition kernels of one slice of observations (K1p then K1q).
+// Tiled fast path, partition kernels of one slice of observations (K1p then K1q) on worker stream w.
 template <int NR>
-void launch_partition(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int chunks_per_bucket) {
+void launch_partition(gritas_b200_handle h, int w, const ObsCols &c, const FilterDesc &f) {
+  const StageDesc &sg = h->sgw[w];
   const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
   const int g1 = std::min(nbatch, 148 * 3 * 4);
-  k_part_obs<NR><<<g1, P1_THREADS, h->p1_smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq, h->sg);
-  k_part_tiles<NR><<<(int)h->sg.nbuckets * chunks_per_bucket, P2_THREADS, h->p2_smem, h->compute>>>(h->g, h->sg,
-                                                                                                     chunks_per_bucket);
+  k_part_obs<NR><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, h->d_status + 1 + w, h->call_seq, sg);
+  // K1q items: each bucket's runs in `parts` ranges of roughly 3800 entries (if everything were accepted)
+  const size_t per_bucket = (size_t)nbatch * P1_BATCH / sg.nbuckets;
+  const int parts = (int)std::max((size_t)1, (per_bucket + 3799) / 3800);
+  const int g2 = std::min((int)sg.nbuckets * parts, 148 * 2);
+  static const bool skip_q = getenv("GRITAS_B200_DEBUG_SKIP_K1Q") != nullptr;  // timing experiments only
+  if (skip_q) return;
+  k_part_tiles<NR><<<g2, P2_THREADS, h->p2_smem, h->wk[w]>>>(h->g, sg, parts);
 }
 
 // K2t over every tile with staged entries; afterwards the lists are empty.
@@ -252,6 +313,8 @@ void launch_tiles(gritas_b200_handle h) {
 
 int flush_stage(gritas_b200_handle h) {
   if (!h->staging || h->staged_upper == 0) return 0;
+  int jr = join_workers(h);
+  if (jr) return jr;
   switch (h->g.nr) {
     case 1: launch_tiles<1>(h); break;
     case 2: launch_tiles<2>(h); break;
@@ -260,7 +323,7 @@ int flush_stage(gritas_b200_handle h) {
   CU(cudaGetLastError());
   h->launches += 1;
   h->staged_upper = 0;
-  return 0;
+  return mark_main(h);
 }
 
 template <int NR>
@@ -290,14 +353,21 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
               aligned16(c.flag) && aligned16(c.time) && aligned16(c.flag_out);
   for (int ir = 0; ir < h->g.nr; ++ir) c.aligned = c.aligned && aligned16(c.d[ir]);
 
+  const bool tiled = (h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging;
+  const int w = h->next_wk;
+  cudaStream_t run = tiled ? h->wk[w] : h->compute;
+  if (tiled) {
+    h->next_wk = (h->next_wk + 1) % NWK;
+    CU(cudaStreamWaitEvent(run, h->main_ev, 0));   // not before the last reset / flush
+  }
   if (any_copy) {
     CU(cudaEventRecord(s.copied, h->copy));
-    CU(cudaStreamWaitEvent(h->compute, s.copied, 0));
+    CU(cudaStreamWaitEvent(run, s.copied, 0));
   }
-  const size_t smem = h->g.p2_in_smem ? sizeof(double) * (size_t)h->g.nlevs : 0;
+  const size_t smem = levtab_smem_bytes(h->g);
   if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging) {
     // tiled path: partition this call's observations into the per-tile lists (slices bound the scratch)
-    const int SLICE = 4 << 20;
+    const int SLICE = (int)h->sg.nbatch_cap * P1_BATCH;
     for (int s0 = 0; s0 < n; s0 += SLICE) {
       ObsCols cs = c;
       cs.n = std::min(SLICE, n - s0);
@@ -310,38 +380,20 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
       if (cs.time) cs.time += s0;
       if (cs.flag_out) cs.flag_out += s0;
       if (s0) h->call_seq += 1;  // the level-miss record is per launch
-      const size_t nb = h->sg.nbuckets;
-      const size_t nbatch = ((size_t)cs.n + P1_BATCH - 1) / P1_BATCH;
-      const size_t cap1 = (3 * (size_t)cs.n / nb + 8 * nbatch + 64 + 7) & ~(size_t)7;
-      if (h->scratch_cap < nb * cap1) {
-        CU(cudaStreamSynchronize(h->compute));
-        for (void *p : {(void *)h->sg.key1, (void *)h->sg.d1[0], (void *)h->sg.d1[1], (void *)h->sg.d1[2]})
-          if (p) CU(cudaFree(p));
-        h->sg.key1 = nullptr;
-        h->sg.d1[0] = h->sg.d1[1] = h->sg.d1[2] = nullptr;
-        h->scratch_cap = 0;
-        const size_t want = nb * cap1 + nb * cap1 / 4;
-        CU(cudaMalloc(&h->sg.key1, sizeof(unsigned) * want));
-        for (int ir = 0; ir < h->g.nr; ++ir) CU(cudaMalloc(&h->sg.d1[ir], sizeof(double) * want));
-        h->scratch_cap = want;
-      }
-      h->sg.cap1 = (unsigned)((h->scratch_cap / nb) & ~(size_t)7);
+      h->sgw[w].nbatch = (unsigned)(((size_t)cs.n + P1_BATCH - 1) / P1_BATCH);
       // keep the expected tile-list fill at or below ~half the capacity; what still overflows (skewed data)
       // is accumulated directly by the partition kernels
       const size_t add = (size_t)cs.n + (size_t)cs.n / 4;  // entries + padding sentinels
       if (h->staged_upper + add > h->stage_slots / 2) {
         int rc = flush_stage(h);
         if (rc) return rc;
+        CU(cudaStreamWaitEvent(run, h->main_ev, 0));
       }
       h->staged_upper += add;
-      h->sg.fill1 = h->fill1_buf + (size_t)h->fill1_parity * PB_MAXB;
-      h->sg.fill1_next = h->fill1_buf + (size_t)(h->fill1_parity ^ 1) * PB_MAXB;
-      h->fill1_parity ^= 1;
-      const int cpb = (int)((h->sg.cap1 + P2_BATCH - 1) / P2_BATCH);
       switch (h->g.nr) {
-        case 1: launch_partition<1>(h, cs, f, cpb); break;
-        case 2: launch_partition<2>(h, cs, f, cpb); break;
-        default: launch_partition<3>(h, cs, f, cpb); break;
+        case 1: launch_partition<1>(h, w, cs, f); break;
+        case 2: launch_partition<2>(h, w, cs, f); break;
+        default: launch_partition<3>(h, w, cs, f); break;
       }
       h->launches += 2;
     }
@@ -384,11 +436,18 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     h->launches += 2 + (uint64_t)((h->key_bits + 7) / 8) * 2 + 1;  // keys, segsum, sort passes (approx.)
   }
   CU(cudaGetLastError());
-  CU(cudaEventRecord(s.consumed, h->compute));
+  if (any_copy || flag_to_host) {
+    CU(cudaEventRecord(s.consumed, run));
+    s.in_use = true;
+  }
 
   if (flag_to_host) {
-    CU(cudaMemcpyAsync(flag_host_or_dev, s.flag_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaMemcpyAsync(flag_host_or_dev, s.flag_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, run));
     h->d2h += sizeof(int) * (size_t)n;
+  }
+  if (tiled) {
+    CU(cudaEventRecord(h->wk_done[w], run));
+    h->wk_pending[w] = true;
   }
   const bool async = (h->flags & GRITAS_B200_FLAG_ASYNC) != 0;
   if (!async || flag_to_host) return drain(h, bad_lev);
@@ -462,7 +521,19 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   for (int k = 0; k < nlevs; ++k)
     if (p1[k] != p1[k] || p2[k] != p2[k]) g.contiguous = 0;
   g.p1_top = p1[0];
-  g.p2_in_smem = (sizeof(double) * (size_t)nlevs <= 40 * 1024) ? 1 : 0;
+  g.rdlon = 1.0 / g.dlon;
+  g.rdlat = 1.0 / g.dlat;
+  // Level LUT for the branch-free lookup: cells of 2^-m octave on the high word of lev, chosen so that
+  // no cell holds more than LUT_STEPS interfaces (kernels.cuh find_level).
+  std::vector<unsigned short> lut;
+  g.lut_ncell = 0;
+  g.lut_shift = 0;
+  g.lut_cell0 = 0;
+  if (g.contiguous) {
+    lut.resize(16384);
+    g.lut_ncell = build_level_lut(nlevs, p1, p2, lut.data(), (int)lut.size(), &g.lut_shift, &g.lut_cell0);
+  }
+  g.p2_in_smem = (sizeof(double) * (size_t)nlevs + 2 * (size_t)g.lut_ncell + 8 <= 40 * 1024) ? 1 : 0;
   h->key_bits = 1;
   while (h->key_bits < 32 && ((size_t)1 << h->key_bits) <= h->nrec) h->key_bits++;
 
@@ -484,19 +555,25 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   CUC(cudaMalloc(&h->d_table, sizeof(int) * (size_t)kxmax * ktmax));
   CUC(cudaMalloc(&h->d_p1, sizeof(double) * nlevs));
   CUC(cudaMalloc(&h->d_p2, sizeof(double) * nlevs));
-  CUC(cudaMalloc(&h->d_status, sizeof(Status)));
-  CUC(cudaMallocHost(&h->h_status, sizeof(Status)));
+  CUC(cudaMalloc(&h->d_status, sizeof(Status) * (NWK + 1)));   // [0] compute stream, [1 + w] worker w
+  CUC(cudaMallocHost(&h->h_status, sizeof(Status) * (NWK + 1)));
   const size_t acc_bytes = sizeof(double) * (h->nrec > 0 ? h->nrec : 1) * g.rs;
   CUC(cudaMalloc(&g.acc, acc_bytes));
   CUC(cudaMemcpy(h->d_table, kxkt_table, sizeof(int) * (size_t)kxmax * ktmax, cudaMemcpyDefault));
   CUC(cudaMemcpy(h->d_p1, p1, sizeof(double) * nlevs, cudaMemcpyDefault));
   CUC(cudaMemcpy(h->d_p2, p2, sizeof(double) * nlevs, cudaMemcpyDefault));
+  if (g.lut_ncell > 0) {
+    CUC(cudaMalloc(&h->d_lut, sizeof(unsigned short) * (size_t)g.lut_ncell));
+    CUC(cudaMemcpy(h->d_lut, lut.data(), sizeof(unsigned short) * (size_t)g.lut_ncell, cudaMemcpyHostToDevice));
+  }
+  g.lut = h->d_lut;
   CUC(cudaMemsetAsync(g.acc, 0, acc_bytes, h->compute));  // gritas.f:352-363
   g.table = h->d_table; g.p1 = h->d_p1; g.p2 = h->d_p2;
-  Status st;
-  st.first_bad = BAD_NONE; st.bad_lev = 0.0; st.ticket = 0; st.pad = 0;
-  CUC(cudaMemcpyAsync(h->d_status, &st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
+  Status st[NWK + 1];
+  for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.ticket = 0; q.pad = 0; }
+  CUC(cudaMemcpyAsync(h->d_status, st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
   CUC(cudaStreamSynchronize(h->compute));
+  CUC(cudaEventCreateWithFlags(&h->main_ev, cudaEventDisableTiming));
 
   // ---- tiled fast path --------------------------------------------------
   // Worth it when the whole grid is revisited many times (conventional data scattered over a grid far
@@ -538,29 +615,51 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         const size_t nfill = nbuckets * tpb;              // padded: every (bucket, local tile) has a counter
         CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * nfill));
         CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * nfill));
-        CUC(cudaMalloc(&h->fill1_buf, sizeof(unsigned) * 2 * PB_MAXB));
-        CUC(cudaMemset(h->fill1_buf, 0, sizeof(unsigned) * 2 * PB_MAXB));
+        // level-1 scratch: one run of c1 slots per (bucket, K1p batch); c1 = power of two >= 1.5x the mean run
+        // (fuller runs are accumulated directly); few dead slots keep K1q's scan short
+        unsigned c1 = 16, c1_shift = 4;
+        while (c1 < 512 && (size_t)c1 * nbuckets * 2 < (size_t)3 * P1_BATCH) { c1 <<= 1; ++c1_shift; }
+        h->sg.c1 = c1;
+        h->sg.c1_shift = c1_shift;
+        h->sg.nbatch_cap = 1024;                          // 2 Mi observations per slice
+        h->scratch_cap = nbuckets * (size_t)h->sg.nbatch_cap * c1;
+        for (int w = 0; w < NWK; ++w) {                   // one scratch, stream and event per worker
+          h->sgw[w] = h->sg;
+          CUC(cudaMalloc(&h->sgw[w].cnt1, sizeof(unsigned) * nbuckets * h->sg.nbatch_cap));
+          CUC(cudaMalloc(&h->sgw[w].key1, sizeof(unsigned) * h->scratch_cap));
+          for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sgw[w].d1[ir], sizeof(double) * h->scratch_cap));
+          CUC(cudaStreamCreateWithFlags(&h->wk[w], cudaStreamNonBlocking));
+          CUC(cudaEventCreateWithFlags(&h->wk_done[w], cudaEventDisableTiming));
+        }
         CUC(cudaMalloc(&h->sg.skey, sizeof(unsigned) * h->stage_slots));
         for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sg.sd[ir], sizeof(double) * h->stage_slots));
-        const size_t p2b = g.p2_in_smem ? sizeof(double) * (size_t)nlevs : 0;
+        const size_t p2b = levtab_smem_bytes(g);
         if (nr == 1) {
-          h->p1_smem = ((part_smem_bytes<1, P1_SCAP>() + 15) & ~(size_t)15) + p2b;
-          h->p2_smem = part_smem_bytes<1, P2_SCAP>();
+          h->p1_smem = ((part_smem_bytes<1, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
+          h->p2_smem = ((part_smem_bytes<1, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
           CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUC(cudaFuncSetAttribute(k_part_obs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         } else if (nr == 2) {
-          h->p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + p2b;
-          h->p2_smem = part_smem_bytes<2, P2_SCAP>();
+          h->p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
+          h->p2_smem = ((part_smem_bytes<2, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
           CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUC(cudaFuncSetAttribute(k_part_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         } else {
-          h->p1_smem = ((part_smem_bytes<3, P1_SCAP>() + 15) & ~(size_t)15) + p2b;
-          h->p2_smem = part_smem_bytes<3, P2_SCAP>();
+          h->p1_smem = ((part_smem_bytes<3, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
+          h->p2_smem = ((part_smem_bytes<3, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
           CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUC(cudaFuncSetAttribute(k_part_obs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+        }
+        for (int w = 0; w < NWK; ++w) {                   // tile-list fields are shared by all workers
+          StageDesc &q = h->sgw[w];
+          q.fill = h->sg.fill; q.skey = h->sg.skey;
+          for (int ir = 0; ir < 3; ++ir) q.sd[ir] = h->sg.sd[ir];
+          q.cap = h->sg.cap; q.ntiles = h->sg.ntiles; q.tile_shift = h->sg.tile_shift;
+          q.c1 = h->sg.c1; q.c1_shift = h->sg.c1_shift; q.nbatch_cap = h->sg.nbatch_cap;
+          q.nbuckets = h->sg.nbuckets; q.bucket_shift = h->sg.bucket_shift;
         }
         h->staging = true;
       }
@@ -587,9 +686,17 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (s.consumed) cudaEventDestroy(s.consumed);
     if (s.copied) cudaEventDestroy(s.copied);
   }
-  for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2],
-                  (void *)h->fill1_buf, (void *)h->sg.key1, (void *)h->sg.d1[0], (void *)h->sg.d1[1], (void *)h->sg.d1[2]})
+  for (int w = 0; w < NWK; ++w) {
+    if (h->wk[w]) { cudaStreamSynchronize(h->wk[w]); cudaStreamDestroy(h->wk[w]); }
+    if (h->wk_done[w]) cudaEventDestroy(h->wk_done[w]);
+    for (void *p : {(void *)h->sgw[w].cnt1, (void *)h->sgw[w].key1, (void *)h->sgw[w].d1[0], (void *)h->sgw[w].d1[1],
+                    (void *)h->sgw[w].d1[2]})
+      if (p) cudaFree(p);
+  }
+  if (h->main_ev) cudaEventDestroy(h->main_ev);
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2]})
     if (p) cudaFree(p);
+  if (h->d_lut) cudaFree(h->d_lut);
   for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
                   (void *)h->keys, (void *)h->idx, (void *)h->keys2, (void *)h->idx2, h->cub_tmp, (void *)h->out})
     if (p) cudaFree(p);
@@ -615,7 +722,6 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
 
   Slot &s = h->slot[h->next_slot];
   h->next_slot = (h->next_slot + 1) % NSLOT;
-  CU(cudaEventSynchronize(s.consumed));  // the kernel that last read this slot is done
 
   ObsCols c = {};
   c.n = nobs;
@@ -701,14 +807,20 @@ int gritas_b200_flush(gritas_b200_handle h) {
 int gritas_b200_reset(gritas_b200_handle h) {
   int rc = check_handle(h);
   if (rc) return rc;
+  if ((rc = join_workers(h))) return rc;
   CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   if (h->staging) {
     const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
     CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * nfill, h->compute));
-    CU(cudaMemsetAsync(h->fill1_buf, 0, sizeof(unsigned) * 2 * PB_MAXB, h->compute));
     h->staged_upper = 0;
   }
-  return 0;
+  return mark_main(h);
+}
+
+int gritas_b200_barrier(gritas_b200_handle h) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  return join_workers(h);
 }
 
 // Finalize (raw=0) or export the raw sums (raw=1) into reference-layout planes.
@@ -813,6 +925,8 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
                         const double *nobs_3d) {
   int rc = check_handle(h);
   if (rc) return rc;
+  if ((rc = flush_stage(h))) return rc;
+  if ((rc = join_workers(h))) return rc;
   const GridDesc &g = h->g;
   const int nr = g.nr;
   const size_t n2 = g.nbox2, n3 = g.nbox3;
@@ -849,7 +963,7 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
   }
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->compute));
-  return 0;
+  return mark_main(h);
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------------------

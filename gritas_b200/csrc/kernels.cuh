@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace gb200 {
 
@@ -38,6 +39,12 @@ struct GridDesc {
   int contiguous;  // p1(k+1)==p2(k), strictly descending: branch-free lower bound is exact
   int p2_in_smem;
   double dlon, dlat, p1_top;
+  double rdlon, rdlat;   // 1/dlon, 1/dlat: fast path of the box index (exactness guarded, see grid_index)
+  // level LUT (branch-free level lookup): cell = (high word of lev >> lut_shift) - lut_cell0 over
+  // [0, lut_ncell); lut[cell] = number of interfaces at or above the cell's upper edge; at most
+  // LUT_STEPS interfaces fall inside any cell.  lut_ncell == 0: binary search instead.
+  int lut_shift, lut_cell0, lut_ncell;
+  const unsigned short *lut;
   unsigned nbox3, nbox2;
   const int *table;
   const double *p1, *p2;
@@ -75,12 +82,13 @@ struct StageDesc {
   double *sd[3];       // [ntiles * cap] per residual column
   unsigned cap, ntiles;
   int tile_shift;
-  // level 1: per-bucket scratch of the current Accum call (a bucket = 2^(bucket_shift-tile_shift) tiles);
-  // small enough to stay in L2 between the two partition kernels
-  unsigned *fill1, *fill1_next;  // [PB_MAXB] ping-pong: the kernel of call n zeroes the counters of call n+1
-  unsigned *key1;
+  // level 1: scratch of the current Accum call, one fixed run of c1 slots per (bucket, K1p batch): no
+  // global tickets (same-address atomics serialise at ~60 ns each on B200).  A bucket is
+  // 2^(bucket_shift-tile_shift) tiles.  The scratch is small enough to stay in L2 between K1p and K1q.
+  unsigned *cnt1;      // [nbuckets * nbatch_cap] live entries of each run (<= c1)
+  unsigned *key1;      // [nbuckets * nbatch_cap * c1]
   double *d1[3];
-  unsigned cap1, nbuckets;
+  unsigned c1, c1_shift, nbatch_cap, nbatch, nbuckets;
   int bucket_shift;
 };
 
@@ -99,6 +107,27 @@ __device__ __forceinline__ long long nint_sat(double x) {
   return r;
 }
 
+// 1 + NINT((x - xmin)/d) needs the correctly rounded quotient only when it lies within rounding
+// distance of a half-integer.  q~ = (x - xmin) * (1/d) differs from fl((x - xmin)/d) by at most 3 ulp
+// (< 1e-9 for |q| < 2^20); unless q~ is within 1e-6 of a half-integer both round to the same integer.
+// Everything else (ties, huge values, NaN) takes the IEEE division: results are bit-identical to
+// m_gritas_grids.f:420, 423 in all cases.
+// Returned values are clipped to +-2^30: anything that far out is clamped to the grid edge by the
+// caller exactly as the unclipped value would be (m_gritas_grids.f:425-426).
+__device__ __noinline__ int grid_index_exact(double num, double d) {   // rare: one copy, out of line
+  const long long r = nint_sat(__ddiv_rn(num, d));
+  return (int)min(1073741824ll, max(-1073741824ll, r));
+}
+
+__device__ __forceinline__ int grid_index(double x, double xmin, double d, double rinv) {
+  const double num = __dsub_rn(x, xmin);
+  const double qa = __dmul_rn(num, rinv);
+  const int k = __double2int_rn(qa);
+  const double diff = __dsub_rn(qa, (double)k);
+  if (fabs(diff) < 0.499999 && fabs(qa) < 1048576.0) return k;
+  return grid_index_exact(num, d);
+}
+
 // gritas.f:710-739.  Returns the ob_flag the reference would hand to GrITAS_Accum_.
 __device__ __forceinline__ int qc_filter(const FilterDesc &f, int qcexcl, int time, double lon) {
   const bool passive = (qcexcl == f.x_passive) | (qcexcl == f.x_pre_bad);
@@ -109,17 +138,64 @@ __device__ __forceinline__ int qc_filter(const FilterDesc &f, int qcexcl, int ti
 }
 
 // m_gritas_grids.f:450-456.  0-based level, or -1 ("could not find level").
-__device__ __forceinline__ int find_level(const GridDesc &g, const double *__restrict__ p2s, double lev) {
+constexpr int LUT_STEPS = 2;
+
+// Host: builds the level LUT for a contiguous table (p1, p2 from GrITAS_Pint): cells of 2^-m octave on
+// the high word of lev, with the smallest m in [3, 10] for which no cell holds more than LUT_STEPS
+// interfaces.  Returns the number of cells (0: no LUT, use the binary search).
+inline int build_level_lut(int nlevs, const double *p1, const double *p2, unsigned short *out, int out_cap, int *shift_out,
+                           int *cell0_out) {
+  if (nlevs < 2 || nlevs > 60000 || !(p2[nlevs - 2] > 0.0)) return 0;
+  const int len = nlevs - 1;
+  auto hiword = [](double x) { unsigned long long u; memcpy(&u, &x, 8); return (unsigned)(u >> 32); };
+  auto fromhi = [](unsigned hw) { unsigned long long u = (unsigned long long)hw << 32; double x; memcpy(&x, &u, 8); return x; };
+  const double vlo = p2[len - 1], vhi = p1[0] > p2[0] ? p1[0] : p2[0];
+  for (int mbits = 3; mbits <= 10; ++mbits) {
+    const int shift = 20 - mbits;
+    const unsigned c0 = hiword(vlo) >> shift, c1 = hiword(vhi) >> shift;
+    if (c1 < c0 || (int)(c1 - c0 + 1) > out_cap) continue;
+    const int ncell = (int)(c1 - c0 + 1);
+    int kk = 0;  // interfaces are descending: walk the cells from the top
+    bool ok = true;
+    for (int cell = ncell - 1; cell >= 0 && ok; --cell) {
+      const double ub = fromhi((c0 + (unsigned)cell + 1u) << shift), lb = fromhi((c0 + (unsigned)cell) << shift);
+      while (kk < len && p2[kk] >= ub) ++kk;        // kk = number of interfaces >= ub
+      out[cell] = (unsigned short)kk;
+      int inside = 0;
+      for (int q = kk; q < len && p2[q] >= lb; ++q) ++inside;
+      if (inside > LUT_STEPS) ok = false;
+    }
+    if (ok) {
+      *shift_out = shift;
+      *cell0_out = (int)c0;
+      return ncell;
+    }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ int find_level(const GridDesc &g, const double *__restrict__ p2s,
+                                          const unsigned short *__restrict__ luts, double lev) {
   const int nl = g.nlevs;
   if (g.contiguous) {
     // level = #{kk < nl-1 : lev <= p2(kk)}; p2 strictly descending so the predicate holds on a prefix.
-    int pos = 0;
     const int len = nl - 1;
-    int step = 1;
-    while ((step << 1) <= len) step <<= 1;
-    for (; step > 0; step >>= 1) {
-      const int np = pos + step;
-      if (np <= len && lev <= p2s[np - 1]) pos = np;
+    int pos = 0;
+    if (g.lut_ncell > 0) {
+      // branch-free: table on the exponent + leading mantissa bits of lev, then LUT_STEPS exact compares
+      const unsigned hi = (unsigned)__double2hiint(lev);
+      int cell = (int)(hi >> g.lut_shift) - g.lut_cell0;   // negative lev / NaN / inf land beyond the table
+      cell = min(max(cell, 0), g.lut_ncell - 1);
+      pos = (int)luts[cell];
+#pragma unroll
+      for (int s = 0; s < LUT_STEPS; ++s) pos += (pos < len && lev <= p2s[pos]) ? 1 : 0;
+    } else {
+      int step = 1;
+      while ((step << 1) <= len) step <<= 1;
+      for (; step > 0; step >>= 1) {
+        const int np = pos + step;
+        if (np <= len && lev <= p2s[np - 1]) pos = np;
+      }
     }
     const double top = (pos == 0) ? g.p1_top : p2s[pos - 1];
     return (lev <= top && lev > p2s[pos]) ? pos : -1;
@@ -130,24 +206,25 @@ __device__ __forceinline__ int find_level(const GridDesc &g, const double *__res
 }
 
 // m_gritas_grids.f:409-426 + level search.  outcome: 0 accumulate, 1 not in table, 2 level miss.
-__device__ __forceinline__ unsigned box_key(const GridDesc &g, const double *__restrict__ p2s, double lat,
-                                            double lon, double lev, int kx, int kt, int &outcome) {
+__device__ __forceinline__ unsigned box_key(const GridDesc &g, const double *__restrict__ p2s,
+                                            const unsigned short *__restrict__ luts, double lat, double lon,
+                                            double lev, int kx, int kt, int &outcome) {
   int l = 0;
   if (kx >= 1 && kx <= g.kxmax && kt >= 1 && kt <= g.ktmax)
     l = __ldg(g.table + (size_t)(kx - 1) + (size_t)g.kxmax * (size_t)(kt - 1));
   const bool surface = l < 0;
   l = abs(l);
   if (l <= 0) { outcome = 1; return KEY_NONE; }
-  long long ii = 1 + nint_sat(__ddiv_rn(__dsub_rn(lon, -180.0), g.dlon));
-  if (ii == (long long)g.im + 1) ii = 1;
+  int ii = 1 + grid_index(lon, -180.0, g.dlon, g.rdlon);
+  if (ii == g.im + 1) ii = 1;
   if (ii == 0) ii = g.im;
-  long long jj = 1 + nint_sat(__ddiv_rn(__dsub_rn(lat, -90.0), g.dlat));
-  ii = min((long long)g.im, max(1ll, ii));
-  jj = min((long long)g.jm, max(1ll, jj));
+  int jj = 1 + grid_index(lat, -90.0, g.dlat, g.rdlat);
+  ii = min(g.im, max(1, ii));
+  jj = min(g.jm, max(1, jj));
   const unsigned i = (unsigned)(ii - 1), j = (unsigned)(jj - 1);
   outcome = 0;
   if (surface) return g.nbox3 + i + (unsigned)g.im * (j + (unsigned)g.jm * (unsigned)(l - 1));
-  const int k = find_level(g, p2s, lev);
+  const int k = find_level(g, p2s, luts, lev);
   if (k < 0) { outcome = 2; return KEY_NONE; }
   return (unsigned)k + (unsigned)g.km * (i + (unsigned)g.im * (j + (unsigned)g.jm * (unsigned)(l - 1)));
 }
@@ -180,6 +257,33 @@ __device__ __forceinline__ void finish_status(Status *st, unsigned call_seq, con
   }
 }
 
+// One instruction (UBLKPF.L2) asks L2 to fetch a whole column slice: the CTA's loads then find their
+// lines in L2 instead of paying HBM latency one dependent phase at a time.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+  const unsigned long long a = (unsigned long long)p;
+  const unsigned long long a16 = (a + 15ull) & ~15ull;           // 16-byte aligned start, 16-byte multiple size
+  const unsigned skip = (unsigned)(a16 - a);
+  if (bytes <= skip + 16u) return;
+  const unsigned sz = (bytes - skip) & ~15u;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(sz) : "memory");
+}
+
+// All columns K1p reads for observations [first, first + count).
+__device__ __forceinline__ void prefetch_batch(const ObsCols &c, const FilterDesc &f, int nr, int first, int count) {
+  const int t = threadIdx.x;
+  const unsigned b8 = (unsigned)count * 8u, b4 = (unsigned)count * 4u;
+  if (t == 0) prefetch_l2_bulk(c.lat + first, b8);
+  if (t == 32) prefetch_l2_bulk(c.lon + first, b8);
+  if (t == 64) prefetch_l2_bulk(c.lev + first, b8);
+  if (t == 96) prefetch_l2_bulk(c.kx + first, b4);
+  if (t == 128) prefetch_l2_bulk(c.kt + first, b4);
+  if (t == 160 && c.flag) prefetch_l2_bulk(c.flag + first, b4);
+  if (t == 192 && f.use_time) prefetch_l2_bulk(c.time + first, b4);
+  if (t == 224) {
+    for (int ir = 0; ir < nr; ++ir) prefetch_l2_bulk(c.d[ir] + first, b8);
+  }
+}
+
 // streaming 128-bit loads that do not pollute L1
 __device__ __forceinline__ double2 ldg_stream2(const double *p) {
   double2 r;
@@ -200,8 +304,27 @@ struct Obs4 {
   int kx[4], kt[4], fl[4], tm[4];
 };
 
+// Coordinates, kx/kt, flag and time of 4 consecutive observations (36-40 B per observation).
 template <int NR>
-__device__ __forceinline__ void load_obs4(const ObsCols &c, const FilterDesc &f, int base, Obs4<NR> &o) {
+__device__ __forceinline__ void load_geo4_slow(const ObsCols &c, const FilterDesc &f, int base, Obs4<NR> &o) {
+  const int n = c.n;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = base + j;
+    const bool in = i < n;
+    const int ii = in ? i : 0;
+    o.lat[j] = in ? __ldg(c.lat + ii) : 0.0;
+    o.lon[j] = in ? __ldg(c.lon + ii) : 0.0;
+    o.lev[j] = in ? __ldg(c.lev + ii) : 0.0;
+    o.kx[j] = in ? __ldg(c.kx + ii) : 0;
+    o.kt[j] = in ? __ldg(c.kt + ii) : 0;
+    o.fl[j] = (in && c.flag) ? __ldg(c.flag + ii) : 0;
+    o.tm[j] = (in && f.use_time) ? __ldg(c.time + ii) : 0;
+  }
+}
+
+template <int NR>
+__device__ __forceinline__ void load_geo4(const ObsCols &c, const FilterDesc &f, int base, Obs4<NR> &o) {
   const int n = c.n;
   if (c.aligned && base + 3 < n) {
     double2 a, b;
@@ -211,11 +334,6 @@ __device__ __forceinline__ void load_obs4(const ObsCols &c, const FilterDesc &f,
     o.lon[0] = a.x; o.lon[1] = a.y; o.lon[2] = b.x; o.lon[3] = b.y;
     a = ldg_stream2(c.lev + base); b = ldg_stream2(c.lev + base + 2);
     o.lev[0] = a.x; o.lev[1] = a.y; o.lev[2] = b.x; o.lev[3] = b.y;
-#pragma unroll
-    for (int ir = 0; ir < NR; ++ir) {
-      a = ldg_stream2(c.d[ir] + base); b = ldg_stream2(c.d[ir] + base + 2);
-      o.d[ir][0] = a.x; o.d[ir][1] = a.y; o.d[ir][2] = b.x; o.d[ir][3] = b.y;
-    }
     int4 v = ldg_stream4(c.kx + base);
     o.kx[0] = v.x; o.kx[1] = v.y; o.kx[2] = v.z; o.kx[3] = v.w;
     v = ldg_stream4(c.kt + base);
@@ -233,28 +351,49 @@ __device__ __forceinline__ void load_obs4(const ObsCols &c, const FilterDesc &f,
       o.tm[0] = o.tm[1] = o.tm[2] = o.tm[3] = 0;
     }
   } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j;
-      const bool in = i < n;
-      const int ii = in ? i : 0;
-      o.lat[j] = in ? __ldg(c.lat + ii) : 0.0;
-      o.lon[j] = in ? __ldg(c.lon + ii) : 0.0;
-      o.lev[j] = in ? __ldg(c.lev + ii) : 0.0;
-#pragma unroll
-      for (int ir = 0; ir < NR; ++ir) o.d[ir][j] = in ? __ldg(c.d[ir] + ii) : 0.0;
-      o.kx[j] = in ? __ldg(c.kx + ii) : 0;
-      o.kt[j] = in ? __ldg(c.kt + ii) : 0;
-      o.fl[j] = (in && c.flag) ? __ldg(c.flag + ii) : 0;
-      o.tm[j] = (in && f.use_time) ? __ldg(c.time + ii) : 0;
-    }
+    load_geo4_slow<NR>(c, f, base, o);   // ragged tail / unaligned caller arrays
   }
+}
+
+// Residual columns of 4 consecutive observations (8 B per observation and column).
+template <int NR>
+__device__ __forceinline__ void load_del4_slow(const ObsCols &c, int base, double (&d)[NR][4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = base + j;
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) d[ir][j] = (i < c.n) ? __ldg(c.d[ir] + i) : 0.0;
+  }
+}
+
+template <int NR>
+__device__ __forceinline__ void load_del4(const ObsCols &c, int base, double (&d)[NR][4]) {
+  if (c.aligned && base + 3 < c.n) {
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) {
+      const double2 a = ldg_stream2(c.d[ir] + base), b = ldg_stream2(c.d[ir] + base + 2);
+      d[ir][0] = a.x; d[ir][1] = a.y; d[ir][2] = b.x; d[ir][3] = b.y;
+    }
+  } else {
+    load_del4_slow<NR>(c, base, d);
+  }
+}
+
+template <int NR>
+__device__ __forceinline__ void load_obs4(const ObsCols &c, const FilterDesc &f, int base, Obs4<NR> &o) {
+  load_geo4<NR>(c, f, base, o);
+  load_del4<NR>(c, base, o.d);
 }
 
 // Per-observation front half shared by the fast kernel and the key kernel: filter, table lookup,
 // box index.  Returns the record key (KEY_NONE if nothing is to be accumulated) and the ob_flag
 // the reference would leave behind.
-__device__ __forceinline__ unsigned classify(const GridDesc &g, const FilterDesc &f, const double *p2s,
+struct LevTab {   // level tables as the kernels see them (shared memory when they fit)
+  const double *p2;
+  const unsigned short *lut;
+};
+
+__device__ __forceinline__ unsigned classify(const GridDesc &g, const FilterDesc &f, const LevTab p2s,
                                              double lat, double lon, double lev, int kx, int kt, int flag_in,
                                              int tm, int n, Status *st, unsigned call_seq, int &flag_after) {
   int fl = flag_in;
@@ -262,10 +401,55 @@ __device__ __forceinline__ unsigned classify(const GridDesc &g, const FilterDesc
   flag_after = fl;
   if (fl != 0) return KEY_NONE;  // m_gritas_grids.f:406-407
   int outcome;
-  const unsigned key = box_key(g, p2s, lat, lon, lev, kx, kt, outcome);
+  const unsigned key = box_key(g, p2s.p2, p2s.lut, lat, lon, lev, kx, kt, outcome);
   if (outcome == 1) flag_after = 1;  // m_gritas_grids.f:413-416
   if (outcome == 2) report_miss(st, call_seq, n);
   return key;
+}
+
+// classify() for 4 consecutive observations, written step by step over the four so that the
+// independent chains (table lookup, two box indices, level lookup) of different observations overlap;
+// there is no control flow apart from the rare exact-division and level-miss paths.  Same results as
+// classify(): key (KEY_NONE if nothing is to be accumulated) and the ob_flag left behind.
+template <int NR>
+__device__ __forceinline__ void classify4(const GridDesc &g, const FilterDesc &f, const LevTab t, const Obs4<NR> &o,
+                                          int base, int n, Status *st, unsigned call_seq, unsigned (&key)[4],
+                                          int (&flag_after)[4]) {
+  int fl[4], l[4], ii[4], jj[4], k[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) fl[j] = f.ods ? qc_filter(f, o.fl[j], o.tm[j], o.lon[j]) : o.fl[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool inr = (unsigned)(o.kx[j] - 1) < (unsigned)g.kxmax && (unsigned)(o.kt[j] - 1) < (unsigned)g.ktmax;
+    const size_t idx = inr ? (size_t)(o.kx[j] - 1) + (size_t)g.kxmax * (size_t)(o.kt[j] - 1) : 0;
+    const int v = __ldg(g.table + idx);
+    l[j] = inr ? v : 0;                            // out-of-range kx/kt: "not in table" (m_gritas_grids.f:409)
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ii[j] = 1 + grid_index(o.lon[j], -180.0, g.dlon, g.rdlon);   // :420
+#pragma unroll
+  for (int j = 0; j < 4; ++j) jj[j] = 1 + grid_index(o.lat[j], -90.0, g.dlat, g.rdlat);    // :423
+#pragma unroll
+  for (int j = 0; j < 4; ++j) k[j] = find_level(g, t.p2, t.lut, o.lev[j]);                 // :450-456
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool live = (base + j < n) && fl[j] == 0;                                         // :406-407
+    const bool surface = l[j] < 0;                                                           // :410
+    const int la = abs(l[j]);
+    const bool intab = la > 0;                                                               // :413
+    int i2 = ii[j];
+    i2 = (i2 == g.im + 1) ? 1 : i2;                                                          // :421
+    i2 = (i2 == 0) ? g.im : i2;                                                              // :422
+    i2 = min(g.im, max(1, i2));                                                              // :425
+    const int j2 = min(g.jm, max(1, jj[j]));                                                 // :426
+    const unsigned cell = (unsigned)(i2 - 1) + (unsigned)g.im * ((unsigned)(j2 - 1) + (unsigned)g.jm * (unsigned)(la - 1));
+    const unsigned key2 = g.nbox3 + cell;
+    const unsigned key3 = (unsigned)k[j] + (unsigned)g.km * cell;
+    const bool ok = live && intab && (surface || k[j] >= 0);
+    key[j] = ok ? (surface ? key2 : key3) : KEY_NONE;
+    flag_after[j] = (base + j < n) ? ((live && !intab) ? 1 : fl[j]) : 0;                     // :413-416
+    if (live && intab && !surface && k[j] < 0) report_miss(st, call_seq, base + j);          // :458-459
+  }
 }
 
 template <int NR>
@@ -280,10 +464,25 @@ __device__ __forceinline__ void red_record(double *__restrict__ rec, double cnt,
   if (NR == 2) atomicAdd(rec + 5, sxy);
 }
 
-__device__ __forceinline__ void load_p2(const GridDesc &g, double *s_p2) {
-  if (g.p2_in_smem)
+// Level tables into shared memory (p2 doubles, then the LUT); includes the barrier.
+__host__ __device__ inline size_t levtab_smem_bytes(const GridDesc &g) {
+  if (!g.p2_in_smem) return 0;
+  return sizeof(double) * (size_t)g.nlevs + sizeof(unsigned short) * (size_t)((g.lut_ncell + 3) & ~3);
+}
+
+__device__ __forceinline__ LevTab load_p2(const GridDesc &g, double *s_p2) {
+  LevTab t;
+  t.p2 = g.p2;
+  t.lut = g.lut;
+  if (g.p2_in_smem) {
+    unsigned short *s_lut = reinterpret_cast<unsigned short *>(s_p2 + g.nlevs);
     for (int k = threadIdx.x; k < g.nlevs; k += blockDim.x) s_p2[k] = g.p2[k];
+    for (int k = threadIdx.x; k < g.lut_ncell; k += blockDim.x) s_lut[k] = g.lut[k];
+    t.p2 = s_p2;
+    t.lut = s_lut;
+  }
   __syncthreads();
+  return t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -294,23 +493,22 @@ template <int NR, bool AGG>
 __global__ void __launch_bounds__(ACC_THREADS)
 k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq) {
   extern __shared__ double s_p2[];
-  load_p2(g, s_p2);
-  const double *p2s = g.p2_in_smem ? s_p2 : g.p2;
+  const LevTab p2s = load_p2(g, s_p2);
   const int nvec = (c.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
   const int nvec_w = (nvec + 31) & ~31;  // whole warps iterate together (match/shfl need all lanes)
   const int lane = threadIdx.x & 31;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec_w; v += gridDim.x * blockDim.x) {
     const int base = v * OBS_PER_THREAD;
     Obs4<NR> o;
-    if (v < nvec) load_obs4<NR>(c, f, base, o);
-    int fa[4];
+    int fa[4] = {0, 0, 0, 0};
+    unsigned k4[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
+    if (v < nvec) {
+      load_obs4<NR>(c, f, base, o);
+      classify4<NR>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      unsigned key = KEY_NONE;
-      fa[j] = 0;
-      if (v < nvec && base + j < c.n)
-        key = classify(g, f, p2s, o.lat[j], o.lon[j], o.lev[j], o.kx[j], o.kt[j], o.fl[j], o.tm[j], base + j, st,
-                       call_seq, fa[j]);
+      const unsigned key = k4[j];
       double sx[NR], sq[NR], sxy = 0.0;
 #pragma unroll
       for (int ir = 0; ir < NR; ++ir) {
@@ -370,8 +568,7 @@ __global__ void __launch_bounds__(ACC_THREADS)
 k_box_keys(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
            unsigned *__restrict__ keys, unsigned *__restrict__ idx, unsigned nrec) {
   extern __shared__ double s_p2[];
-  load_p2(g, s_p2);
-  const double *p2s = g.p2_in_smem ? s_p2 : g.p2;
+  const LevTab p2s = load_p2(g, s_p2);
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < c.n; n += gridDim.x * blockDim.x) {
     const int fl = c.flag ? __ldg(c.flag + n) : 0;
     const int tm = f.use_time ? __ldg(c.time + n) : 0;
@@ -432,15 +629,16 @@ k_segment_sum(const GridDesc g, const ObsCols c, const FilterDesc f, const unsig
 constexpr int PB_MAXB = 128;                      // destinations per grouping step
 constexpr unsigned PB_OVERFLOW = 0xFFFFFFFFu;
 // K1p: 256 threads x 8 observations, 3 CTAs per SM so that load / group / write-out phases of
-// different CTAs overlap.  K1q: 1024 threads x 4 entries (entries only, few registers), 2 CTAs per SM.
+// different CTAs overlap.  K1q: 512 threads, two passes over a 4096-entry chunk (count, then regroup), 2 CTAs per SM.
 constexpr int P1_THREADS = 256, P1_ITEMS = 8, P1_BATCH = P1_THREADS * P1_ITEMS, P1_SCAP = P1_BATCH + 8 * PB_MAXB;
-constexpr int P2_THREADS = 1024, P2_ITEMS = 4, P2_BATCH = P2_THREADS * P2_ITEMS, P2_SCAP = P2_BATCH + 8 * PB_MAXB;
+constexpr int P2_THREADS = 512, P2_BATCH = 4096, P2_SCAP = P2_BATCH + 8 * PB_MAXB;
 
 template <int NR>
 struct PartView {
   double *d[NR];        // [SCAP] grouped residuals
   unsigned *key;        // [SCAP] grouped keys
   unsigned *cnt;        // [PB_MAXB] entries per destination in this batch
+  unsigned *cnt2;       // [PB_MAXB] second ticket counter (two-pass grouping)
   unsigned *off;        // [PB_MAXB] start of the destination's (padded) group in the staging arrays
   unsigned *run;        // [PB_MAXB] start of the run inside the destination's global list, or PB_OVERFLOW
   unsigned *total;      // padded entries in this batch
@@ -449,7 +647,7 @@ struct PartView {
 
 template <int NR, int SCAP>
 __host__ __device__ constexpr size_t part_smem_bytes() {
-  return sizeof(double) * NR * SCAP + sizeof(unsigned) * (SCAP + 3 * PB_MAXB + 4) + SCAP / 8;
+  return sizeof(double) * NR * SCAP + sizeof(unsigned) * (SCAP + 4 * PB_MAXB + 4) + SCAP / 8;
 }
 
 template <int NR, int SCAP>
@@ -461,6 +659,7 @@ __device__ __forceinline__ PartView<NR> part_view(unsigned char *smem) {
   unsigned *up = reinterpret_cast<unsigned *>(dp + (size_t)NR * SCAP);
   v.key = up; up += SCAP;
   v.cnt = up; up += PB_MAXB;
+  v.cnt2 = up; up += PB_MAXB;
   v.off = up; up += PB_MAXB;
   v.run = up; up += PB_MAXB;
   v.total = up; up += 4;
@@ -469,18 +668,23 @@ __device__ __forceinline__ PartView<NR> part_view(unsigned char *smem) {
 }
 
 // After the counting pass: lay the destinations out back to back (each padded to a multiple of 8),
-// reserve the same number of entries at the tail of every destination's global list, write the
-// pad sentinels and the group->destination map.  Called by all threads of the CTA.
-template <int NR>
-__device__ __forceinline__ void part_layout(const PartView<NR> &v, int nb, unsigned *__restrict__ g_fill,
-                                            unsigned *__restrict__ g_key, unsigned cap, unsigned list_first) {
+// decide where each destination's run goes in global memory, write the pad sentinels and the
+// group->destination map.  Called by all threads of the CTA.
+//   TICKET: the run is reserved at the tail of the destination's list with one global atomicAdd
+//           (K1q -> tile lists); a run that does not fit is marked PB_OVERFLOW.
+//   else  : every destination has a fixed run of `limit` slots starting at `fixed_run` (K1p -> bucket
+//           scratch); entries beyond `limit` are left to the caller (cnt is clipped).
+template <int NR, bool TICKET>
+__device__ __forceinline__ void part_layout(const PartView<NR> &v, int nb, unsigned limit, unsigned fixed_run,
+                                            unsigned *__restrict__ g_fill, unsigned *__restrict__ g_key, unsigned cap,
+                                            unsigned list_first) {
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 32) {
     unsigned p[4], local = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int b = lane * 4 + q;
-      const unsigned c = b < nb ? v.cnt[b] : 0u;
+      const unsigned c = b < nb ? min(v.cnt[b], limit) : 0u;
       p[q] = (c + 7u) & ~7u;
       local += p[q];
     }
@@ -500,18 +704,20 @@ __device__ __forceinline__ void part_layout(const PartView<NR> &v, int nb, unsig
   }
   __syncthreads();
   if (tid < nb) {
-    const unsigned c = v.cnt[tid], padded = (c + 7u) & ~7u, off = v.off[tid];
-    unsigned run = 0;
+    const unsigned c = min(v.cnt[tid], limit), padded = (c + 7u) & ~7u, off = v.off[tid];
+    unsigned run = fixed_run;
     if (c) {
-      const unsigned gpos = atomicAdd(g_fill + list_first + tid, padded);
-      if (gpos + padded <= cap) {
-        run = gpos;
-      } else {
-        // does not fit: these entries are accumulated directly by the caller.  Exactly one reservation
-        // straddles the capacity; it closes the unwritten gap with sentinels so readers never see garbage.
-        run = PB_OVERFLOW;
-        unsigned *lk = g_key + (size_t)(list_first + tid) * cap;
-        for (unsigned e = gpos; e < cap; ++e) lk[e] = KEY_NONE;
+      if (TICKET) {
+        const unsigned gpos = atomicAdd(g_fill + list_first + tid, padded);
+        if (gpos + padded <= cap) {
+          run = gpos;
+        } else {
+          // does not fit: these entries are accumulated directly by the caller.  Exactly one reservation
+          // straddles the capacity; it closes the unwritten gap with sentinels so readers never see garbage.
+          run = PB_OVERFLOW;
+          unsigned *lk = g_key + (size_t)(list_first + tid) * cap;
+          for (unsigned e = gpos; e < cap; ++e) lk[e] = KEY_NONE;
+        }
       }
       for (unsigned e = c; e < padded; ++e) {
         v.key[off + e] = KEY_NONE;
@@ -552,134 +758,230 @@ __device__ __forceinline__ void red_entry(const GridDesc &g, unsigned key, const
   red_record<NR>(g.acc + (size_t)key * (size_t)g.rs, 1.0, d, sq, sxy);
 }
 
-// K1p: a batch of P1_BATCH observations per CTA iteration.
+#ifdef GB_PHASE_TIMING
+__device__ unsigned long long *g_phase_buf = nullptr;   // [gridDim.x][8] globaltimer stamps (probe builds only)
+__device__ __forceinline__ void phase_stamp(int slot) {
+  if (threadIdx.x == 0 && g_phase_buf) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_phase_buf[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
+#define GB_STAMP(i) phase_stamp(i)
+#else
+#define GB_STAMP(i)
+#endif
+
+// K1p: a batch of P1_BATCH observations per CTA iteration, in two passes so that only the keys stay
+// in registers across the barriers: (A) coordinates -> classify -> count per bucket, (B) residual
+// columns -> ticket -> grouped staging.  Each column is still read from HBM exactly once.
 template <int NR>
-__global__ void __launch_bounds__(P1_THREADS, 2)
+__global__ void __launch_bounds__(P1_THREADS, 3)
 k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
            const StageDesc sg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PartView<NR> v = part_view<NR, P1_SCAP>(smem_raw);
-  double *s_p2 = reinterpret_cast<double *>(smem_raw + ((part_smem_bytes<NR, P1_SCAP>() + 15) & ~(size_t)15));
+  unsigned char *sp = smem_raw + ((part_smem_bytes<NR, P1_SCAP>() + 15) & ~(size_t)15);
+  uint4 *s_akey = reinterpret_cast<uint4 *>(sp);           // [P1_BATCH / 4] keys of the batch in arrival order
+  double *s_p2 = reinterpret_cast<double *>(sp + sizeof(unsigned) * P1_BATCH);
   const int tid = threadIdx.x;
-  if (blockIdx.x == 0 && tid < PB_MAXB) sg.fill1_next[tid] = 0u;  // counters of the NEXT call
-  load_p2(g, s_p2);
-  const double *p2s = g.p2_in_smem ? s_p2 : g.p2;
+  GB_STAMP(0);
+  const LevTab p2s = load_p2(g, s_p2);
+  GB_STAMP(1);
   const int nb = (int)sg.nbuckets;
   const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
+  if ((int)blockIdx.x < nbatch)
+    prefetch_batch(c, f, NR, blockIdx.x * P1_BATCH, min(P1_BATCH, c.n - (int)blockIdx.x * P1_BATCH));
   for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-    if (tid < PB_MAXB) v.cnt[tid] = 0u;
+    const int nxt = batch + (int)gridDim.x;
+    if (nxt < nbatch) prefetch_batch(c, f, NR, nxt * P1_BATCH, min(P1_BATCH, c.n - nxt * P1_BATCH));
+    if (tid < PB_MAXB) { v.cnt[tid] = 0u; v.cnt2[tid] = 0u; }
     __syncthreads();
-    unsigned rkey[P1_ITEMS], rrank[P1_ITEMS];
-    double rd[NR][P1_ITEMS];
-#pragma unroll
+    // ---- pass A: coordinates -> keys (kept in shared memory) + per-bucket counts ----
+#pragma unroll 1
     for (int h = 0; h < P1_ITEMS / 4; ++h) {
       const int base = batch * P1_BATCH + (h * P1_THREADS + tid) * 4;
-      Obs4<NR> o;
-      int fa[4];
-      if (base < c.n) load_obs4<NR>(c, f, base, o);
+      unsigned k4[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
+      if (base < c.n) {
+        Obs4<NR> o;
+        int fa[4];
+#ifdef GB_PROBE_NOLOAD
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o.lat[j] = -89.0 + 1e-4 * ((base + j) % 1700000); o.lon[j] = -179.0 + 2e-4 * ((base + j) % 1700000);
+          o.lev[j] = 11.0 + 1e-3 * ((base + j) % 1000000); o.kx[j] = 101 + ((base + j) & 15); o.kt[j] = 44; o.fl[j] = 0; o.tm[j] = 0;
+        }
+#else
+        load_geo4<NR>(c, f, base, o);
+#endif
+#ifdef GB_PROBE_NOCLASSIFY
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k4[j] = (unsigned)(__double2loint(o.lat[j]) ^ __double2loint(o.lon[j]) ^ o.kx[j]) % g.nbox3;
+        fa[0] = fa[1] = fa[2] = fa[3] = 0;
+#else
+        classify4<NR>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
+#endif
+        if (c.flag_out) {
+          if (c.aligned && base + 3 < c.n) {
+            *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (base + j < c.n) c.flag_out[base + j] = fa[j];
+          }
+        }
+      }
+      s_akey[h * P1_THREADS + tid] = make_uint4(k4[0], k4[1], k4[2], k4[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k4[j] != KEY_NONE) atomicAdd(v.cnt + (k4[j] >> sg.bucket_shift), 1u);
+    }
+    __syncthreads();
+    GB_STAMP(2);
+    // the run of (bucket b, this batch) starts at slot batch * c1 of bucket b's scratch row
+    part_layout<NR, false>(v, nb, sg.c1, (unsigned)batch << sg.c1_shift, nullptr, nullptr, 0u, 0u);
+    if (tid < nb) sg.cnt1[(size_t)tid * sg.nbatch_cap + batch] = min(v.cnt[tid], sg.c1);
+    GB_STAMP(3);
+    // ---- pass B: residual columns -> ticket -> grouped staging ----
+#pragma unroll 1
+    for (int h = 0; h < P1_ITEMS / 4; ++h) {
+      const int base = batch * P1_BATCH + (h * P1_THREADS + tid) * 4;
+      const uint4 kq = s_akey[h * P1_THREADS + tid];
+      const unsigned k4[4] = {kq.x, kq.y, kq.z, kq.w};
+      if ((kq.x & kq.y & kq.z & kq.w) == KEY_NONE) continue;
+      double dd[NR][4];
+      load_del4<NR>(c, base, dd);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = h * 4 + j;
-        unsigned key = KEY_NONE;
-        fa[j] = 0;
-        if (base + j < c.n)
-          key = classify(g, f, p2s, o.lat[j], o.lon[j], o.lev[j], o.kx[j], o.kt[j], o.fl[j], o.tm[j], base + j, st,
-                         call_seq, fa[j]);
+        const unsigned key = k4[j];
+        if (key == KEY_NONE) continue;
+        double d[NR];
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) {
-          double d = o.d[ir][j];
-          if (f.scale_res && key != KEY_NONE) d = scale_residual(f, c, d, base + j);
-          rd[ir][q] = d;
-        }
-        rkey[q] = key;
-        rrank[q] = (key != KEY_NONE) ? atomicAdd(v.cnt + (key >> sg.bucket_shift), 1u) : 0u;
-      }
-      if (c.flag_out && base < c.n) {
-        if (c.aligned && base + 3 < c.n) {
-          *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
+        for (int ir = 0; ir < NR; ++ir) d[ir] = f.scale_res ? scale_residual(f, c, dd[ir][j], base + j) : dd[ir][j];
+        const unsigned b = key >> sg.bucket_shift;
+        const unsigned rank = atomicAdd(v.cnt2 + b, 1u);
+        if (rank >= sg.c1) {
+          red_entry<NR>(g, key, d);     // the run of this (bucket, batch) is full: accumulate directly
         } else {
+          const unsigned sidx = v.off[b] + rank;
+          v.key[sidx] = key;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (base + j < c.n) c.flag_out[base + j] = fa[j];
+          for (int ir = 0; ir < NR; ++ir) v.d[ir][sidx] = d[ir];
         }
       }
     }
     __syncthreads();
-    part_layout<NR>(v, nb, sg.fill1, sg.key1, sg.cap1, 0u);
-#pragma unroll
-    for (int q = 0; q < P1_ITEMS; ++q) {
-      if (rkey[q] == KEY_NONE) continue;
-      const unsigned b = rkey[q] >> sg.bucket_shift;
-      double d[NR];
-#pragma unroll
-      for (int ir = 0; ir < NR; ++ir) d[ir] = rd[ir][q];
-      if (v.run[b] == PB_OVERFLOW) {
-        red_entry<NR>(g, rkey[q], d);
-      } else {
-        const unsigned s = v.off[b] + rrank[q];
-        v.key[s] = rkey[q];
-#pragma unroll
-        for (int ir = 0; ir < NR; ++ir) v.d[ir][s] = d[ir];
-      }
-    }
+    GB_STAMP(4);
+    part_writeout<NR>(v, sg.nbatch_cap << sg.c1_shift, 0u, sg.key1, sg.d1);
     __syncthreads();
-    part_writeout<NR>(v, sg.cap1, 0u, sg.key1, sg.d1);
-    __syncthreads();
+    GB_STAMP(5);
   }
   finish_status(st, call_seq, c.lev);
+  GB_STAMP(6);
 }
 
-// K1q: CTA (bucket, chunk) regroups P2_BATCH scratch entries of one bucket by tile.
+// K1q: regroups the bucket scratch by tile.  Work item = (bucket, one of `parts` equal ranges of K1p
+// batches); a persistent grid walks the items.  Inside an item the runs are packed greedily into
+// rounds of at most P2_BATCH live entries; every round is two passes over its runs (they sit in L2):
+// count per tile, lay out + reserve list space, then reload and scatter with a second ticket counter
+// -- nothing is kept in registers across the barriers.
+constexpr int P2_MAXRUNS = P2_THREADS;  // runs (K1p batches) per round: one count per thread
+
 template <int NR>
-__global__ void __launch_bounds__(P2_THREADS, 1)
-k_part_tiles(const GridDesc g, const StageDesc sg, int chunks_per_bucket) {
+__global__ void __launch_bounds__(P2_THREADS, 2)
+k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PartView<NR> v = part_view<NR, P2_SCAP>(smem_raw);
-  const int tid = threadIdx.x;
-  const unsigned b = blockIdx.x / (unsigned)chunks_per_bucket, chunk = blockIdx.x % (unsigned)chunks_per_bucket;
-  const unsigned n = min(sg.fill1[b], sg.cap1);
-  const unsigned start = chunk * (unsigned)P2_BATCH;
-  if (start >= n) return;
+  unsigned *s_rcnt = reinterpret_cast<unsigned *>(smem_raw + ((part_smem_bytes<NR, P2_SCAP>() + 15) & ~(size_t)15));
+  unsigned *s_scan = s_rcnt + P2_MAXRUNS;       // [32] warp totals, then [1] runs taken, [1] spare
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tsh = sg.bucket_shift - sg.tile_shift;
   const int nt = 1 << tsh;                        // tiles per bucket (<= PB_MAXB)
-  if (tid < PB_MAXB) v.cnt[tid] = 0u;
-  __syncthreads();
-  const size_t src = (size_t)b * sg.cap1 + start;
-  unsigned rkey[P2_ITEMS], rrank[P2_ITEMS];
-  double rd[NR][P2_ITEMS];
+  const unsigned tmask = (unsigned)(nt - 1);
+  const unsigned nitems = sg.nbuckets * (unsigned)parts;
+  const unsigned per = (sg.nbatch + (unsigned)parts - 1u) / (unsigned)parts;
+  for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const unsigned b = item % sg.nbuckets, part = item / sg.nbuckets;
+    unsigned lo = part * per;
+    const unsigned hi = min(sg.nbatch, lo + per);
+    const size_t row = (size_t)b * sg.nbatch_cap;
+    while (lo < hi) {
+      // ---- how many runs fit in this round: inclusive scan of the run counts, cut at P2_BATCH ----
+      const unsigned nrun_max = min((unsigned)P2_MAXRUNS, hi - lo);
+      const unsigned mine = ((unsigned)tid < nrun_max) ? sg.cnt1[row + lo + tid] : 0u;
+      unsigned incl = mine;
 #pragma unroll
-  for (int q = 0; q < P2_ITEMS; ++q) {
-    const unsigned e = (unsigned)(q * P2_THREADS + tid);
-    rkey[q] = (start + e < n) ? sg.key1[src + e] : KEY_NONE;
-  }
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_scan[wid] = incl;
+      if (tid < PB_MAXB) { v.cnt[tid] = 0u; v.cnt2[tid] = 0u; }
+      __syncthreads();
+      if (wid == 0) {
+        unsigned w = (lane < P2_THREADS / 32) ? s_scan[lane] : 0u, wi = w;
 #pragma unroll
-  for (int q = 0; q < P2_ITEMS; ++q) {
-    const unsigned e = (unsigned)(q * P2_THREADS + tid);
-    const bool live = rkey[q] != KEY_NONE;
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+          if (lane >= o) wi += t;
+        }
+        s_scan[lane] = wi - w;                    // exclusive warp offsets
+      }
+      __syncthreads();
+      incl += s_scan[wid];
+      s_rcnt[tid] = mine;
+      // runs taken = number of leading runs whose inclusive sum stays within the batch (at least one)
+      const bool fits = ((unsigned)tid < nrun_max) && (incl <= (unsigned)P2_BATCH || tid == 0);
+      const unsigned nrun = (unsigned)__syncthreads_count(fits);  // fits is a prefix property: count = cut
+      const unsigned nslot = nrun << sg.c1_shift;
+      const size_t src = (row + lo) << sg.c1_shift;
+      // ---- pass 1: count per tile (4 slots per thread and iteration, loads issued together) ----
+      for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
+        unsigned key[4];
 #pragma unroll
-    for (int ir = 0; ir < NR; ++ir) rd[ir][q] = live ? sg.d1[ir][src + e] : 0.0;
-    rrank[q] = live ? atomicAdd(v.cnt + ((rkey[q] >> sg.tile_shift) & (unsigned)(nt - 1)), 1u) : 0u;
-  }
-  __syncthreads();
-  part_layout<NR>(v, nt, sg.fill, sg.skey, sg.cap, b << tsh);
+        for (int u = 0; u < 4; ++u) {
+          const unsigned sidx = s0 + u * P2_THREADS;
+          const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
+          key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
+        }
 #pragma unroll
-  for (int q = 0; q < P2_ITEMS; ++q) {
-    if (rkey[q] == KEY_NONE) continue;
-    const unsigned t = (rkey[q] >> sg.tile_shift) & (unsigned)(nt - 1);
-    double d[NR];
+        for (int u = 0; u < 4; ++u)
+          if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
+      }
+      __syncthreads();
+      part_layout<NR, true>(v, nt, 0xFFFFFFFFu, 0u, sg.fill, sg.skey, sg.cap, b << tsh);
+      // ---- pass 2: reload, ticket, scatter ----
+      for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
+        unsigned key[4];
+        double d[4][NR];
 #pragma unroll
-    for (int ir = 0; ir < NR; ++ir) d[ir] = rd[ir][q];
-    if (v.run[t] == PB_OVERFLOW) {
-      red_entry<NR>(g, rkey[q], d);
-    } else {
-      const unsigned s = v.off[t] + rrank[q];
-      v.key[s] = rkey[q];
+        for (int u = 0; u < 4; ++u) {
+          const unsigned sidx = s0 + u * P2_THREADS;
+          const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
+          key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
 #pragma unroll
-      for (int ir = 0; ir < NR; ++ir) v.d[ir][s] = d[ir];
+          for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + src + sidx) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (key[u] == KEY_NONE) continue;
+          const unsigned t = (key[u] >> sg.tile_shift) & tmask;
+          if (v.run[t] == PB_OVERFLOW) {
+            red_entry<NR>(g, key[u], d[u]);
+          } else {
+            const unsigned at = v.off[t] + atomicAdd(v.cnt2 + t, 1u);
+            v.key[at] = key[u];
+#pragma unroll
+            for (int ir = 0; ir < NR; ++ir) v.d[ir][at] = d[u][ir];
+          }
+        }
+      }
+      __syncthreads();
+      part_writeout<NR>(v, sg.cap, b << tsh, sg.skey, sg.sd);
+      __syncthreads();
+      lo += nrun;
     }
   }
-  __syncthreads();
-  part_writeout<NR>(v, sg.cap, b << tsh, sg.skey, sg.sd);
 }
 
 // ---------------------------------------------------------------------------------------------

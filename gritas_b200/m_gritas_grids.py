@@ -176,6 +176,9 @@ class Grids:
         bad = C.c_double(0.0)
         self._check(cabi.load().gritas_b200_sync(self._h, C.byref(bad)), bad)
 
+    def barrier(self):
+        self._check(cabi.load().gritas_b200_barrier(self._h))
+
     def flush(self):
         self._check(cabi.load().gritas_b200_flush(self._h))
 

@@ -123,6 +123,10 @@ int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
  * sync / norm / get_raw / allreduce do it implicitly).  A no-op in the other modes. */
 int gritas_b200_flush(gritas_b200_handle h);
 
+/* The compute stream (gritas_b200_stream) waits for all accumulate work queued so far; no host
+ * synchronisation.  The tiled fast path runs consecutive Accum calls on internal worker streams. */
+int gritas_b200_barrier(gritas_b200_handle h);
+
 /* Zero the device grids (grisas.f:285-296 zeroes them every synoptic time). */
 int gritas_b200_reset(gritas_b200_handle h);
 
