@@ -281,12 +281,23 @@ int grid_for(size_t work, int threads, int per_sm) {
   return (int)b;
 }
 
+inline int filter_mode(const FilterDesc &f) { return !f.ods ? 0 : ((f.use_time || f.use_lon) ? 2 : 1); }
+
+template <int NR, int FMODE>
+void launch_fast_m(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
+  if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
+    k_accum_fast<NR, false, FMODE><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+  else
+    k_accum_fast<NR, true, FMODE><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+}
+
 template <int NR>
 void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
-  if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
-    k_accum_fast<NR, false><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
-  else
-    k_accum_fast<NR, true><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+  switch (filter_mode(f)) {
+    case 0: launch_fast_m<NR, 0>(h, c, f, nblk, smem); break;
+    case 1: launch_fast_m<NR, 1>(h, c, f, nblk, smem); break;
+    default: launch_fast_m<NR, 2>(h, c, f, nblk, smem); break;
+  }
 }
 
 // Tiled fast path, partition kernels of one slice of observations (K1p then K1q) on worker stream w.
@@ -295,7 +306,12 @@ void launch_partition(gritas_b200_handle h, int w, const ObsCols &c, const Filte
   const StageDesc &sg = h->sgw[w];
   const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
   const int g1 = std::min(nbatch, 148 * 3 * 4);
-  k_part_obs<NR><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, h->d_status + 1 + w, h->call_seq, sg);
+  Status *st = h->d_status + 1 + w;
+  switch (filter_mode(f)) {
+    case 0: k_part_obs<NR, 0><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, sg); break;
+    case 1: k_part_obs<NR, 1><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, sg); break;
+    default: k_part_obs<NR, 2><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, sg); break;
+  }
   // K1q items: each bucket's runs in `parts` ranges of roughly 3800 entries (if everything were accepted)
   const size_t per_bucket = (size_t)nbatch * P1_BATCH / sg.nbuckets;
   const int parts = (int)std::max((size_t)1, (per_bucket + 3799) / 3800);
@@ -638,19 +654,25 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
           h->p1_smem = ((part_smem_bytes<1, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
           h->p2_smem = ((part_smem_bytes<1, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
           CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         } else if (nr == 2) {
           h->p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
           h->p2_smem = ((part_smem_bytes<2, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
           CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         } else {
           h->p1_smem = ((part_smem_bytes<3, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
           h->p2_smem = ((part_smem_bytes<3, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
           CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
+          CUC(cudaFuncSetAttribute(k_part_obs<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         }
         for (int w = 0; w < NWK; ++w) {                   // tile-list fields are shared by all workers
@@ -867,9 +889,17 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     size_t z = (size_t)g.jm * g.l3d;
     grd.z = (unsigned)(z > 65535 ? 65535 : z);
     const int r3 = raw3 ? 1 : 0;
-    if (nr == 1) k_finalize3<1><<<grd, blk, 0, h->compute>>>(g, o, nrmlz, ntr, r3);
-    else if (nr == 2) k_finalize3<2><<<grd, blk, 0, h->compute>>>(g, o, nrmlz, ntr, r3);
-    else k_finalize3<3><<<grd, blk, 0, h->compute>>>(g, o, nrmlz, ntr, r3);
+    const size_t fsm = sizeof(double) * (size_t)(4 * nr + 1) * 32 * 33;
+    if (nr == 1) {
+      CU(cudaFuncSetAttribute(k_finalize3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      k_finalize3<1><<<grd, blk, fsm, h->compute>>>(g, o, nrmlz, ntr, r3);
+    } else if (nr == 2) {
+      CU(cudaFuncSetAttribute(k_finalize3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      k_finalize3<2><<<grd, blk, fsm, h->compute>>>(g, o, nrmlz, ntr, r3);
+    } else {
+      CU(cudaFuncSetAttribute(k_finalize3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      k_finalize3<3><<<grd, blk, fsm, h->compute>>>(g, o, nrmlz, ntr, r3);
+    }
     h->launches++;
   }
   CU(cudaGetLastError());

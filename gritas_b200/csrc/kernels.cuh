@@ -26,7 +26,7 @@ constexpr double AMISS = 1.0e15;  // m_gritas_grids.f:72
 constexpr int ACC_THREADS = 256;
 constexpr int OBS_PER_THREAD = 4;
 
-struct Status {
+struct alignas(16) Status {
   unsigned long long first_bad;  // (call_seq << 32) | obs index of the first level miss, or BAD_NONE
   double bad_lev;
   unsigned ticket;
@@ -238,23 +238,38 @@ __device__ __forceinline__ double scale_residual(const FilterDesc &f, const ObsC
   return d;
 }
 
-__device__ __forceinline__ void report_miss(Status *st, unsigned call_seq, int n) {
-  atomicMin(&st->first_bad, ((unsigned long long)call_seq << 32) | (unsigned)n);
+// Level miss (m_gritas_grids.f:458-459): keep the EARLIEST (call, observation) together with its level.
+// The pair {first_bad, bad_lev} is the first 16 bytes of Status and is replaced with one 128-bit CAS, so
+// the level always belongs to the recorded observation -- no per-CTA fence / last-block pass needed.
+__device__ __noinline__ void report_miss(Status *st, unsigned call_seq, int n, double lev) {
+  const unsigned long long mine = ((unsigned long long)call_seq << 32) | (unsigned)n;
+  unsigned long long cur_id = *reinterpret_cast<volatile unsigned long long *>(&st->first_bad);
+  unsigned long long cur_lev = *reinterpret_cast<volatile unsigned long long *>(&st->bad_lev);
+  const unsigned long long my_lev = (unsigned long long)__double_as_longlong(lev);
+  while (mine < cur_id) {
+    unsigned long long got_id, got_lev;
+    asm volatile(
+        "{\n\t.reg .b128 cmp, val, old;\n\t"
+        "mov.b128 cmp, {%2, %3};\n\t"
+        "mov.b128 val, {%4, %5};\n\t"
+        "atom.global.cas.b128 old, [%6], cmp, val;\n\t"
+        "mov.b128 {%0, %1}, old;\n\t}"
+        : "=l"(got_id), "=l"(got_lev)
+        : "l"(cur_id), "l"(cur_lev), "l"(mine), "l"(my_lev), "l"(st)
+        : "memory");
+    if (got_id == cur_id && got_lev == cur_lev) break;
+    cur_id = got_id;
+    cur_lev = got_lev;
+  }
 }
 
-// Last block to finish captures the offending level (what the reference prints before exit(7)).
-__device__ __forceinline__ void finish_status(Status *st, unsigned call_seq, const double *lev) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned t = atomicAdd(&st->ticket, 1u);
-    if (t == gridDim.x - 1) {
-      st->ticket = 0;
-      const unsigned long long fb = atomicAdd(&st->first_bad, 0ull);
-      if (fb != BAD_NONE && (unsigned)(fb >> 32) == call_seq) st->bad_lev = lev[(unsigned)fb];
-      __threadfence();
-    }
-  }
+// 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion wait.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // One instruction (UBLKPF.L2) asks L2 to fetch a whole column slice: the CTA's loads then find their
@@ -403,52 +418,92 @@ __device__ __forceinline__ unsigned classify(const GridDesc &g, const FilterDesc
   int outcome;
   const unsigned key = box_key(g, p2s.p2, p2s.lut, lat, lon, lev, kx, kt, outcome);
   if (outcome == 1) flag_after = 1;  // m_gritas_grids.f:413-416
-  if (outcome == 2) report_miss(st, call_seq, n);
+  if (outcome == 2) report_miss(st, call_seq, n, lev);
   return key;
 }
 
 // classify() for 4 consecutive observations, written step by step over the four so that the
-// independent chains (table lookup, two box indices, level lookup) of different observations overlap;
-// there is no control flow apart from the rare exact-division and level-miss paths.  Same results as
-// classify(): key (KEY_NONE if nothing is to be accumulated) and the ob_flag left behind.
-template <int NR>
+// independent chains (table lookup, two box indices, level lookup) of different observations overlap.
+// The only control flow is one rarely taken branch for the exact-division cases and one for level
+// misses.  FMODE: 0 = flags as given (GrITAS_Accum entry), 1 = QC filter without time / longitude
+// window (the usual ODS case), 2 = full filter of gritas.f:710-739.  Same results as classify().
+template <int NR, int FMODE>
 __device__ __forceinline__ void classify4(const GridDesc &g, const FilterDesc &f, const LevTab t, const Obs4<NR> &o,
                                           int base, int n, Status *st, unsigned call_seq, unsigned (&key)[4],
                                           int (&flag_after)[4]) {
   int fl[4], l[4], ii[4], jj[4], k[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) fl[j] = f.ods ? qc_filter(f, o.fl[j], o.tm[j], o.lon[j]) : o.fl[j];
+  for (int j = 0; j < 4; ++j) {
+    if (FMODE == 0) {
+      fl[j] = o.fl[j];
+    } else if (FMODE == 1) {
+      const bool passive = (o.fl[j] == f.x_passive) | (o.fl[j] == f.x_pre_bad);
+      fl[j] = ((o.fl[j] == 0) | ((f.ioptn > 0) & passive)) ? 0 : 1;
+    } else {
+      fl[j] = qc_filter(f, o.fl[j], o.tm[j], o.lon[j]);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const bool inr = (unsigned)(o.kx[j] - 1) < (unsigned)g.kxmax && (unsigned)(o.kt[j] - 1) < (unsigned)g.ktmax;
-    const size_t idx = inr ? (size_t)(o.kx[j] - 1) + (size_t)g.kxmax * (size_t)(o.kt[j] - 1) : 0;
+    const unsigned kx1 = (unsigned)(o.kx[j] - 1), kt1 = (unsigned)(o.kt[j] - 1);
+    const bool inr = kx1 < (unsigned)g.kxmax && kt1 < (unsigned)g.ktmax;
+    const unsigned idx = inr ? kx1 + (unsigned)g.kxmax * kt1 : 0u;
     const int v = __ldg(g.table + idx);
     l[j] = inr ? v : 0;                            // out-of-range kx/kt: "not in table" (m_gritas_grids.f:409)
   }
+  // box indices: reciprocal multiply for all eight coordinates, exactness checked once (see grid_index)
+  double num[8];
+  unsigned inexact = 0u;   // bit q: coordinate q needs the IEEE division
 #pragma unroll
-  for (int j = 0; j < 4; ++j) ii[j] = 1 + grid_index(o.lon[j], -180.0, g.dlon, g.rdlon);   // :420
+  for (int j = 0; j < 4; ++j) {
+    num[j] = __dsub_rn(o.lon[j], -180.0);
+    num[4 + j] = __dsub_rn(o.lat[j], -90.0);
+  }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) jj[j] = 1 + grid_index(o.lat[j], -90.0, g.dlat, g.rdlat);    // :423
+  for (int q = 0; q < 8; ++q) {
+    const double qa = __dmul_rn(num[q], q < 4 ? g.rdlon : g.rdlat);
+    const int kq = __double2int_rn(qa);
+    const double diff = __dsub_rn(qa, (double)kq);
+    inexact |= (fabs(diff) < 0.499999 && fabs(qa) < 1048576.0) ? 0u : (1u << q);
+    if (q < 4) ii[q] = kq; else jj[q - 4] = kq;
+  }
+  if (inexact) {   // ties, huge values, NaN: the IEEE division decides (rare)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (inexact & (1u << q)) {
+        const int kq = grid_index_exact(num[q], q < 4 ? g.dlon : g.dlat);
+        if (q < 4) ii[q] = kq; else jj[q - 4] = kq;
+      }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) k[j] = find_level(g, t.p2, t.lut, o.lev[j]);                 // :450-456
+  bool any_miss = false;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const bool live = (base + j < n) && fl[j] == 0;                                         // :406-407
     const bool surface = l[j] < 0;                                                           // :410
     const int la = abs(l[j]);
     const bool intab = la > 0;                                                               // :413
-    int i2 = ii[j];
+    int i2 = ii[j] + 1;                                                                      // :420
     i2 = (i2 == g.im + 1) ? 1 : i2;                                                          // :421
     i2 = (i2 == 0) ? g.im : i2;                                                              // :422
     i2 = min(g.im, max(1, i2));                                                              // :425
-    const int j2 = min(g.jm, max(1, jj[j]));                                                 // :426
+    const int j2 = min(g.jm, max(1, jj[j] + 1));                                             // :423, 426
     const unsigned cell = (unsigned)(i2 - 1) + (unsigned)g.im * ((unsigned)(j2 - 1) + (unsigned)g.jm * (unsigned)(la - 1));
     const unsigned key2 = g.nbox3 + cell;
     const unsigned key3 = (unsigned)k[j] + (unsigned)g.km * cell;
     const bool ok = live && intab && (surface || k[j] >= 0);
     key[j] = ok ? (surface ? key2 : key3) : KEY_NONE;
     flag_after[j] = (base + j < n) ? ((live && !intab) ? 1 : fl[j]) : 0;                     // :413-416
-    if (live && intab && !surface && k[j] < 0) report_miss(st, call_seq, base + j);          // :458-459
+    any_miss |= live && intab && !surface && k[j] < 0;
+  }
+  if (any_miss) {                                                                            // :458-459
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool live = (base + j < n) && fl[j] == 0;
+      if (live && l[j] > 0 && k[j] < 0) report_miss(st, call_seq, base + j, o.lev[j]);
+    }
   }
 }
 
@@ -489,7 +544,7 @@ __device__ __forceinline__ LevTab load_p2(const GridDesc &g, double *s_p2) {
 // K1+K2a fused: stream the columns, classify, accumulate with fp64 RED into the record grid.
 // AGG: lanes of a warp that hit the same box (__match_any_sync) are summed in registers first and
 // only the lowest lane issues the atomics.
-template <int NR, bool AGG>
+template <int NR, bool AGG, int FMODE>
 __global__ void __launch_bounds__(ACC_THREADS)
 k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq) {
   extern __shared__ double s_p2[];
@@ -504,7 +559,7 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
     unsigned k4[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
     if (v < nvec) {
       load_obs4<NR>(c, f, base, o);
-      classify4<NR>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
+      classify4<NR, FMODE>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -559,7 +614,6 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
       }
     }
   }
-  finish_status(st, call_seq, c.lev);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,7 +633,6 @@ k_box_keys(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
     idx[n] = (unsigned)n;
     if (c.flag_out) c.flag_out[n] = fa;
   }
-  finish_status(st, call_seq, c.lev);
 }
 
 // K2b: one thread per run of equal keys in the stably sorted list.  The run is added to the
@@ -645,9 +698,18 @@ struct PartView {
   unsigned char *grp;   // [SCAP/8] destination of each group of 8 staged entries
 };
 
+// Bytes of the grouped-entry staging (residual planes + keys).  K1p also parks the batch's lat / lon / lev
+// there while it classifies (3 * P1_BATCH doubles), so the region is at least that large.
+template <int NR, int SCAP>
+__host__ __device__ constexpr size_t part_stage_bytes() {
+  return (sizeof(double) * NR * SCAP + sizeof(unsigned) * SCAP) > (sizeof(double) * 3 * P1_BATCH)
+             ? (sizeof(double) * NR * SCAP + sizeof(unsigned) * SCAP)
+             : (sizeof(double) * 3 * P1_BATCH);
+}
+
 template <int NR, int SCAP>
 __host__ __device__ constexpr size_t part_smem_bytes() {
-  return sizeof(double) * NR * SCAP + sizeof(unsigned) * (SCAP + 4 * PB_MAXB + 4) + SCAP / 8;
+  return part_stage_bytes<NR, SCAP>() + sizeof(unsigned) * (4 * PB_MAXB + 4) + SCAP / 8;
 }
 
 template <int NR, int SCAP>
@@ -657,7 +719,8 @@ __device__ __forceinline__ PartView<NR> part_view(unsigned char *smem) {
 #pragma unroll
   for (int ir = 0; ir < NR; ++ir) v.d[ir] = dp + (size_t)ir * SCAP;
   unsigned *up = reinterpret_cast<unsigned *>(dp + (size_t)NR * SCAP);
-  v.key = up; up += SCAP;
+  v.key = up;
+  up = reinterpret_cast<unsigned *>(smem + part_stage_bytes<NR, SCAP>());
   v.cnt = up; up += PB_MAXB;
   v.cnt2 = up; up += PB_MAXB;
   v.off = up; up += PB_MAXB;
@@ -775,7 +838,7 @@ __device__ __forceinline__ void phase_stamp(int slot) {
 // K1p: a batch of P1_BATCH observations per CTA iteration, in two passes so that only the keys stay
 // in registers across the barriers: (A) coordinates -> classify -> count per bucket, (B) residual
 // columns -> ticket -> grouped staging.  Each column is still read from HBM exactly once.
-template <int NR>
+template <int NR, int FMODE>
 __global__ void __launch_bounds__(P1_THREADS, 3)
 k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
            const StageDesc sg) {
@@ -805,22 +868,8 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
       if (base < c.n) {
         Obs4<NR> o;
         int fa[4];
-#ifdef GB_PROBE_NOLOAD
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o.lat[j] = -89.0 + 1e-4 * ((base + j) % 1700000); o.lon[j] = -179.0 + 2e-4 * ((base + j) % 1700000);
-          o.lev[j] = 11.0 + 1e-3 * ((base + j) % 1000000); o.kx[j] = 101 + ((base + j) & 15); o.kt[j] = 44; o.fl[j] = 0; o.tm[j] = 0;
-        }
-#else
         load_geo4<NR>(c, f, base, o);
-#endif
-#ifdef GB_PROBE_NOCLASSIFY
-#pragma unroll
-        for (int j = 0; j < 4; ++j) k4[j] = (unsigned)(__double2loint(o.lat[j]) ^ __double2loint(o.lon[j]) ^ o.kx[j]) % g.nbox3;
-        fa[0] = fa[1] = fa[2] = fa[3] = 0;
-#else
-        classify4<NR>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
-#endif
+        classify4<NR, FMODE>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
         if (c.flag_out) {
           if (c.aligned && base + 3 < c.n) {
             *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
@@ -876,7 +925,6 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
     __syncthreads();
     GB_STAMP(5);
   }
-  finish_status(st, call_seq, c.lev);
   GB_STAMP(6);
 }
 
@@ -1167,30 +1215,31 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
 }
 
 // 3-D: tile of 32 levels x 32 longitudes for one (j,l).  Records are read level-fastest (the HBM
-// layout), statistics computed in registers, transposed through shared memory one plane at a
-// time, written longitude-fastest (the reference's layout).
+// layout), statistics computed in registers, all output planes transposed through shared memory in
+// one go (two barriers per tile), written longitude-fastest (the reference's layout).
 template <int NR>
 __global__ void __launch_bounds__(1024)
 k_finalize3(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw) {
-  __shared__ double tile[32][33];
+  constexpr int NP = 4 * NR + 1;
+  extern __shared__ double s_tile[];               // [NP][32][33]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int k0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
   const size_t plane = (size_t)g.im * g.jm * g.km * g.l3d;  // one ir slab
   for (int jl = blockIdx.z; jl < g.jm * g.l3d; jl += gridDim.z) {
     const int j = jl % g.jm, l = jl / g.jm;
-    double v[4 * NR + 1];
+    double v[NP];
 #pragma unroll
-    for (int p = 0; p < 4 * NR + 1; ++p) v[p] = 0.0;
+    for (int p = 0; p < NP; ++p) v[p] = 0.0;
     {
       const int k = k0 + tx, i = i0 + ty;
       if (k < g.nlevs && i < g.im) {  // levels nlevs..km-1 are never touched by the reference: zeros
         const double *rec =
             g.acc + ((size_t)k + (size_t)g.km * ((size_t)i + (size_t)g.im * ((size_t)j + (size_t)g.jm * l))) * g.rs;
         double r[8];
-        const double2 a = *reinterpret_cast<const double2 *>(rec), b = *reinterpret_cast<const double2 *>(rec + 2);
+        const double2 a = __ldcs(reinterpret_cast<const double2 *>(rec)), b = __ldcs(reinterpret_cast<const double2 *>(rec + 2));
         r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
         if (NR > 1) {
-          const double2 c2 = *reinterpret_cast<const double2 *>(rec + 4), d2 = *reinterpret_cast<const double2 *>(rec + 6);
+          const double2 c2 = __ldcs(reinterpret_cast<const double2 *>(rec + 4)), d2 = __ldcs(reinterpret_cast<const double2 *>(rec + 6));
           r[4] = c2.x; r[5] = c2.y; r[6] = d2.x; r[7] = d2.y;
         }
         double bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs;
@@ -1202,25 +1251,22 @@ k_finalize3(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw) {
         v[4 * NR] = nobs;
       }
     }
-    const int ko = k0 + ty, io = i0 + tx;
-    const bool inb = ko < g.km && io < g.im;
-    const size_t o = (size_t)io + (size_t)g.im * ((size_t)j + (size_t)g.jm * ((size_t)ko + (size_t)g.km * l));
 #pragma unroll
-    for (int p = 0; p < 4 * NR + 1; ++p) {
-      double *dst = nullptr;
-      const int grp = p / NR, ir = p % NR;
-      if (p == 4 * NR) dst = out.nobs;
-      else if (grp == 0) dst = out.bias;
-      else if (grp == 1) dst = out.rtms;
-      else if (grp == 2) dst = out.stdv;
-      else dst = out.xcov;
-      if (dst == nullptr) continue;  // uniform across the block
-      if (grp == 3 && ir >= out.xcov_planes) continue;
-      tile[ty][tx] = v[p];
-      __syncthreads();
-      if (inb) dst[o + (p == 4 * NR ? 0 : plane * ir)] = tile[tx][ty];
-      __syncthreads();
+    for (int p = 0; p < NP; ++p) s_tile[(p * 32 + ty) * 33 + tx] = v[p];
+    __syncthreads();
+    const int ko = k0 + ty, io = i0 + tx;
+    if (ko < g.km && io < g.im) {
+      const size_t o = (size_t)io + (size_t)g.im * ((size_t)j + (size_t)g.jm * ((size_t)ko + (size_t)g.km * l));
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int grp = p / NR, ir = p % NR;
+        double *dst = (p == 4 * NR) ? out.nobs : (grp == 0 ? out.bias : (grp == 1 ? out.rtms : (grp == 2 ? out.stdv : out.xcov)));
+        if (dst == nullptr) continue;
+        if (grp == 3 && p != 4 * NR && ir >= out.xcov_planes) continue;
+        __stcs(dst + o + (p == 4 * NR ? 0 : plane * ir), s_tile[(p * 32 + tx) * 33 + ty]);
+      }
     }
+    __syncthreads();
   }
 }
 

@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
   CK(cudaMalloc(&sg.cnt1, (size_t)sg.nbuckets * sg.nbatch_cap * 4)); CK(cudaMalloc(&sg.key1, sc * 4)); CK(cudaMalloc(&sg.d1[0], sc * 8)); CK(cudaMalloc(&sg.d1[1], sc * 8));
   const size_t p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + 4 * P1_BATCH + levtab_smem_bytes(g);
   const size_t p2_smem = ((part_smem_bytes<2, P2_SCAP>() + 15) & ~(size_t)15) + 4 * (P2_MAXRUNS + 40);
-  CK(cudaFuncSetAttribute(k_part_obs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem));
+  CK(cudaFuncSetAttribute(k_part_obs<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem));
   CK(cudaFuncSetAttribute(k_part_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
   const int nbatch = sg.nbatch;
   unsigned long long *buf; CK(cudaMalloc(&buf, (size_t)nbatch * 64)); CK(cudaMemset(buf, 0, (size_t)nbatch * 64));
@@ -74,7 +74,7 @@ int main(int argc, char **argv) {
   for (int r = 0; r < reps + 3; ++r) {
     CK(cudaMemsetAsync(sg.fill, 0, sg.nbuckets * tpb * 4));
     cudaEventRecord(e0);
-    k_part_obs<2><<<nbatch, P1_THREADS, p1_smem>>>(g, c, f, st, 1u, sg);
+    k_part_obs<2, 1><<<nbatch, P1_THREADS, p1_smem>>>(g, c, f, st, 1u, sg);
     cudaEventRecord(e1);
     k_part_tiles<2><<<g2, P2_THREADS, p2_smem>>>(g, sg, parts);
     cudaEventRecord(e2);
