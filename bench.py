@@ -264,6 +264,7 @@ def run_b200(args):
                         -999.0, 999.0, synth.X_PASSIVE, synth.X_PRE_BAD, None, None))
         return out
     dptr = [C_void() for _ in range(10)]
+    host_enqueue = []
 
     def barrier():
         torch.cuda.synchronize()
@@ -273,7 +274,7 @@ def run_b200(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    host_enqueue = []
+    outs10 = (ctypes.c_void_p * 10)()
 
     def step(cols, host_out=None, marks=None):
         G.reset()
@@ -288,20 +289,49 @@ def run_b200(args):
         if marks is not None:
             G.barrier()                # the library stream waits for the worker streams (no host sync)
             marks[1].record(stream)
-        G.flush()
-        if marks is not None:
-            marks[2].record(stream)
-        if world > 1:
-            G.allreduce()
-        if host_out is None:
-            rc = L.gritas_b200_norm_device(G.handle, 1, -1, *[None] * 5, *dptr[5:])
-            if rc:
-                raise RuntimeError(f"norm_device rc={rc}")
+        if world == 1:
+            G.flush()
+            if marks is not None:
+                marks[2].record(stream)
+            if host_out is None:
+                rc = L.gritas_b200_norm_device(G.handle, 1, -1, *[None] * 5, *dptr[5:])
+                if rc:
+                    raise RuntimeError(f"norm_device rc={rc}")
+            else:
+                G.norm_into(host_out)
         else:
-            G.norm_into(host_out)
+            # one collective: tile flush + ncclReduce to rank 0 + finalize, pipelined chunk by chunk
+            if marks is not None:
+                marks[2].record(stream)
+            if host_out is None:
+                rc = L.gritas_b200_norm_reduce_device(G.handle, 0, 1, -1, ctypes.cast(outs10, ctypes.POINTER(ctypes.c_void_p)))
+                if rc:
+                    raise RuntimeError(f"norm_reduce_device rc={rc}: {G._err()}")
+            else:
+                G.norm_reduce_into(host_out, root=0)
 
     # ---- device-resident arm ---------------------------------------------------------------
     dev_calls = calls_of(dev_files)
+    check = None
+    if world > 1:
+        # sanity of the multi-rank path: the reduced count grid on rank 0 must hold every rank's accepted obs
+        G.reset()
+        for a in dev_calls:
+            L.gritas_b200_accum_ods(*a)
+        raw = G.alloc_grids()
+        G.get_raw(None, None, None, None, None, None, None, raw["nobs_3d"])
+        mine = torch.tensor([float(raw["nobs_3d"].sum())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(mine)
+        chk = G.alloc_grids()
+        G.reset()
+        for a in dev_calls:
+            L.gritas_b200_accum_ods(*a)
+        G.norm_reduce_into(chk, root=0)
+        if rank == 0:
+            check = bool(chk["nobs_3d"].sum() == float(mine[0]))
+            if not check:
+                raise SystemExit(f"multi-rank check failed: reduced count {chk['nobs_3d'].sum()} != {float(mine[0])}")
+        del raw, chk
     sampler = ClockSampler(local)
     sampler.start()
     sampler.ready.wait(timeout=20)
@@ -384,10 +414,10 @@ def run_b200(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
-                       "per_rank": "each rank bins its own month; one NCCL all-reduce of the partial grids, then finalize",
+                       "per_rank": "each rank bins its own month; tile flush + ncclReduce to rank 0 + finalize pipelined in 8 chunks (rank 0 writes the grids, as the reference has one writer)",
                        "l2": "inputs (7.8 GB/step) and accumulators (1.7 GB) both exceed the 126 MB L2; no flush needed"},
             "accumulate_ms_per_step": accum_ms, "tile_flush_ms_per_step": flush_ms,
-            "host_enqueue_ms_per_step": host_ms, "gpu_launches": int(launches_per_step * args.steps),
+            "host_enqueue_ms_per_step": host_ms, "multi_rank_count_check": check, "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

@@ -38,7 +38,7 @@ SYMBOLS = [
     "gritas_b200_create", "gritas_b200_destroy", "gritas_b200_pint", "gritas_b200_kxkt", "gritas_b200_accum",
     "gritas_b200_accum_ods", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
     "gritas_b200_get_raw", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
-    "gritas_b200_allreduce", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
+    "gritas_b200_allreduce", "gritas_b200_norm_reduce", "gritas_b200_norm_reduce_device", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
     "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
     "gritas_b200_d2h_bytes", "gritas_b200_version",
 ]
@@ -78,6 +78,8 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_nccl_unique_id.argtypes = [_P]
     L.gritas_b200_comm_init.argtypes = [_P, _I, _I, _P]
     L.gritas_b200_allreduce.argtypes = [_P]
+    L.gritas_b200_norm_reduce.argtypes = [_P, _I, _I, _I] + [_P] * 10
+    L.gritas_b200_norm_reduce_device.argtypes = [_P, _I, _I, _I, C.POINTER(_P)]
     L.gritas_b200_host_alloc.argtypes = [C.c_size_t]
     L.gritas_b200_host_alloc.restype = _P
     L.gritas_b200_host_free.argtypes = [_P]

@@ -39,6 +39,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool load() {
@@ -52,9 +53,10 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(so, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(so, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(so, "ncclAllReduce");
+    Reduce = (decltype(Reduce))dlsym(so, "ncclReduce");
     CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    return GetUniqueId && CommInitRank && AllReduce && Reduce && CommDestroy;
   }
 };
 NcclApi g_nccl;
@@ -113,6 +115,11 @@ struct gritas_b200_ctx {
   StageDesc sgw[NWK] = {};
   int next_wk = 0;
   cudaEvent_t main_ev = nullptr;  // last accumulator-wide operation queued on `compute`
+  // reduce + finalize pipeline (multi-GPU): chunk c is tile-accumulated on `compute`, reduced to the root on
+  // `comm_stream`, finalized on `fin_stream` while later chunks are still being accumulated / reduced
+  static constexpr int NCHUNK = 8;
+  cudaStream_t comm_stream = nullptr, fin_stream = nullptr;
+  cudaEvent_t ev_acc[NCHUNK] = {}, ev_red[NCHUNK] = {}, ev_fin = nullptr;
   // finalize scratch (reference-layout planes on the device)
   double *out = nullptr;
   size_t out_cap = 0;
@@ -323,19 +330,24 @@ void launch_partition(gritas_b200_handle h, int w, const ObsCols &c, const Filte
 
 // K2t over every tile with staged entries; afterwards the lists are empty.
 template <int NR>
-void launch_tiles(gritas_b200_handle h) {
-  k_tile_accum<NR><<<h->tile_ctas, TILE_THREADS, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec);
+void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1) {
+  if (t1 <= t0) return;
+  k_tile_accum<NR><<<(int)(t1 - t0), TILE_THREADS, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, t0, t1);
+}
+
+void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1) {
+  switch (h->g.nr) {
+    case 1: launch_tiles<1>(h, t0, t1); break;
+    case 2: launch_tiles<2>(h, t0, t1); break;
+    default: launch_tiles<3>(h, t0, t1); break;
+  }
 }
 
 int flush_stage(gritas_b200_handle h) {
   if (!h->staging || h->staged_upper == 0) return 0;
   int jr = join_workers(h);
   if (jr) return jr;
-  switch (h->g.nr) {
-    case 1: launch_tiles<1>(h); break;
-    case 2: launch_tiles<2>(h); break;
-    default: launch_tiles<3>(h); break;
-  }
+  launch_tiles_nr(h, 0u, h->sg.ntiles);
   CU(cudaGetLastError());
   h->launches += 1;
   h->staged_upper = 0;
@@ -716,6 +728,13 @@ void gritas_b200_destroy(gritas_b200_handle h) {
       if (p) cudaFree(p);
   }
   if (h->main_ev) cudaEventDestroy(h->main_ev);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->fin_stream) cudaStreamDestroy(h->fin_stream);
+  for (int c = 0; c < gritas_b200_ctx::NCHUNK; ++c) {
+    if (h->ev_acc[c]) cudaEventDestroy(h->ev_acc[c]);
+    if (h->ev_red[c]) cudaEventDestroy(h->ev_red[c]);
+  }
+  if (h->ev_fin) cudaEventDestroy(h->ev_fin);
   for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2]})
     if (p) cudaFree(p);
   if (h->d_lut) cudaFree(h->d_lut);
@@ -845,8 +864,49 @@ int gritas_b200_barrier(gritas_b200_handle h) {
   return join_workers(h);
 }
 
+// K3 launches for 3-D rows [jl0, jl1) (jl = j + jm*l) and, if with2d, the surface boxes, on stream `sm`.
+static int launch_finalize(gritas_b200_handle h, cudaStream_t sm, double *const dst[10], int raw, bool raw3, int xpl, int nrmlz,
+                           int ntr, int jl0, int jl1, bool with2d) {
+  const GridDesc &g = h->g;
+  const int nr = g.nr;
+  const size_t n2 = g.nbox2;
+  if (n2 && with2d) {
+    OutPlanes o = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
+    const int nb = grid_for(n2, 256, 8);
+    if (nr == 1) k_finalize2<1><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw);
+    else if (nr == 2) k_finalize2<2><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw);
+    else k_finalize2<3><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw);
+    h->launches++;
+  }
+  if (g.nbox3 && jl1 > jl0) {
+    OutPlanes o = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && !raw) ? 1 : xpl};
+    dim3 blk(32, 32), grd((g.km + 31) / 32, (g.im + 31) / 32, 1);
+    const int z = jl1 - jl0;
+    grd.z = (unsigned)(z > 65535 ? 65535 : z);
+    const int r3 = raw3 ? 1 : 0;
+    const size_t fsm = sizeof(double) * (size_t)(4 * nr + 1) * 32 * 33;
+    if (nr == 1) {
+      CU(cudaFuncSetAttribute(k_finalize3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      k_finalize3<1><<<grd, blk, fsm, sm>>>(g, o, nrmlz, ntr, r3, jl0, jl1);
+    } else if (nr == 2) {
+      CU(cudaFuncSetAttribute(k_finalize3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      k_finalize3<2><<<grd, blk, fsm, sm>>>(g, o, nrmlz, ntr, r3, jl0, jl1);
+    } else {
+      CU(cudaFuncSetAttribute(k_finalize3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      k_finalize3<3><<<grd, blk, fsm, sm>>>(g, o, nrmlz, ntr, r3, jl0, jl1);
+    }
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // Finalize (raw=0) or export the raw sums (raw=1) into reference-layout planes.
-static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, double *const user[10], const double **dev_out) {
+// reduce_root < 0: the accumulators are final (flushed, all-reduced if wanted) -- finalize them.
+// reduce_root >= 0 (multi-rank): tile flush, ncclReduce to the root and finalize are pipelined chunk by
+// chunk; only the root finalizes and writes outputs.
+static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, double *const user[10], const double **dev_out,
+                       int reduce_root = -1) {
   // order: bias_2d rtms_2d stdv_2d xcov_2d nobs_2d bias_3d rtms_3d stdv_3d xcov_3d nobs_3d
   const GridDesc &g = h->g;
   const int nr = g.nr;
@@ -856,13 +916,15 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
   // nlevs<2: the reference returns before the 3-D loop (m_gritas_grids.f:607) -> 3-D sums stay raw
   const bool raw3 = raw || g.nlevs < 2;
+  const bool piped = reduce_root >= 0 && h->comm != nullptr && h->nranks > 1;
+  const bool writer = !piped || h->rank == reduce_root;
   double *dst[10];
   bool bounce[10];
   size_t need = 0;
   for (int a = 0; a < 10; ++a) {
     bounce[a] = false;
     dst[a] = nullptr;
-    const bool skip = (!user[a] && !dev_out) || sz[a] == 0 || (raw && (a == 2 || a == 7)) || (!raw && raw3 && a == 7);
+    const bool skip = !writer || (!user[a] && !dev_out) || sz[a] == 0 || (raw && (a == 2 || a == 7)) || (!raw && raw3 && a == 7);
     if (skip) continue;
     if (!dev_out && mem_kind(user[a]) == 2) dst[a] = user[a];
     else { bounce[a] = true; need += sz[a]; }
@@ -875,34 +937,59 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
       if (bounce[a]) { dst[a] = h->out + off; off += sz[a]; }
   }
   const int ntr = ntresh < 0 ? 0 : ntresh;
-  if (n2) {
-    OutPlanes o = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
-    const int nb = grid_for(n2, 256, 8);
-    if (nr == 1) k_finalize2<1><<<nb, 256, 0, h->compute>>>(g, o, nrmlz, ntr, raw);
-    else if (nr == 2) k_finalize2<2><<<nb, 256, 0, h->compute>>>(g, o, nrmlz, ntr, raw);
-    else k_finalize2<3><<<nb, 256, 0, h->compute>>>(g, o, nrmlz, ntr, raw);
-    h->launches++;
-  }
-  if (n3) {
-    OutPlanes o = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && !raw) ? 1 : xpl};
-    dim3 blk(32, 32), grd((g.km + 31) / 32, (g.im + 31) / 32, 1);
-    size_t z = (size_t)g.jm * g.l3d;
-    grd.z = (unsigned)(z > 65535 ? 65535 : z);
-    const int r3 = raw3 ? 1 : 0;
-    const size_t fsm = sizeof(double) * (size_t)(4 * nr + 1) * 32 * 33;
-    if (nr == 1) {
-      CU(cudaFuncSetAttribute(k_finalize3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-      k_finalize3<1><<<grd, blk, fsm, h->compute>>>(g, o, nrmlz, ntr, r3);
-    } else if (nr == 2) {
-      CU(cudaFuncSetAttribute(k_finalize3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-      k_finalize3<2><<<grd, blk, fsm, h->compute>>>(g, o, nrmlz, ntr, r3);
-    } else {
-      CU(cudaFuncSetAttribute(k_finalize3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-      k_finalize3<3><<<grd, blk, fsm, h->compute>>>(g, o, nrmlz, ntr, r3);
+  const int nrows = n3 ? g.jm * g.l3d : 0;
+  if (!piped) {
+    int rc = launch_finalize(h, h->compute, dst, raw, raw3, xpl, nrmlz, ntr, 0, nrows, true);
+    if (rc) return rc;
+  } else {
+    int rc = join_workers(h);
+    if (rc) return rc;
+    if (!h->comm_stream) {
+      CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&h->fin_stream, cudaStreamNonBlocking));
+      for (int c = 0; c < gritas_b200_ctx::NCHUNK; ++c) {
+        CU(cudaEventCreateWithFlags(&h->ev_acc[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_red[c], cudaEventDisableTiming));
+      }
+      CU(cudaEventCreateWithFlags(&h->ev_fin, cudaEventDisableTiming));
     }
-    h->launches++;
+    const int NC = gritas_b200_ctx::NCHUNK;
+    const bool staged = h->staging && h->staged_upper > 0;
+    const size_t T = h->staging ? ((size_t)1 << h->sg.tile_shift) : 1;
+    const size_t row_recs = (size_t)g.im * g.km;
+    unsigned tprev = 0;
+    size_t rprev = 0;
+    for (int c = 0; c < NC; ++c) {
+      const int r0 = (int)((long long)nrows * c / NC), r1 = (int)((long long)nrows * (c + 1) / NC);
+      const bool last = c == NC - 1;
+      const size_t rec_end = last ? h->nrec : (size_t)r1 * row_recs;   // the last chunk also carries the 2-D boxes
+      if (staged) {
+        const unsigned t1 = last ? h->sg.ntiles : (unsigned)std::min((size_t)h->sg.ntiles, (rec_end + T - 1) / T);
+        launch_tiles_nr(h, tprev, t1);    // includes a tile straddling into the next chunk: complete before its reduce
+        tprev = t1;
+        h->launches++;
+      }
+      CU(cudaEventRecord(h->ev_acc[c], h->compute));
+      CU(cudaStreamWaitEvent(h->comm_stream, h->ev_acc[c], 0));
+      if (rec_end > rprev) {
+        double *seg = g.acc + rprev * g.rs;
+        int e = g_nccl.Reduce(seg, seg, (rec_end - rprev) * g.rs, NCCL_FLOAT64, NCCL_SUM, reduce_root, h->comm, h->comm_stream);
+        if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+      }
+      rprev = rec_end;
+      CU(cudaEventRecord(h->ev_red[c], h->comm_stream));
+      if (writer) {
+        CU(cudaStreamWaitEvent(h->fin_stream, h->ev_red[c], 0));
+        rc = launch_finalize(h, h->fin_stream, dst, raw, raw3, xpl, nrmlz, ntr, r0, r1, last);
+        if (rc) return rc;
+      }
+    }
+    CU(cudaGetLastError());
+    h->staged_upper = 0;
+    CU(cudaEventRecord(h->ev_fin, writer ? h->fin_stream : h->comm_stream));
+    CU(cudaStreamWaitEvent(h->compute, h->ev_fin, 0));
+    if ((rc = mark_main(h))) return rc;
   }
-  CU(cudaGetLastError());
   for (int a = 0; a < 10; ++a) {
     if (dev_out) dev_out[a] = dst[a];
     else if (bounce[a]) {
@@ -910,6 +997,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
       h->d2h += sizeof(double) * sz[a];
     }
   }
+  if (piped) return drain(h, nullptr);
   CU(cudaStreamSynchronize(h->compute));
   return 0;
 }
@@ -939,6 +1027,36 @@ int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const d
   for (int a = 0; a < 10; ++a)
     if (outp[a]) *outp[a] = d[a];
   return 0;
+}
+
+// Multi-rank Norm: tile flush, reduction of the partial accumulators to `root` and finalize, pipelined in
+// chunks; only the root's output arrays are written.  Collective over the communicator.
+int gritas_b200_norm_reduce(gritas_b200_handle h, int root, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d,
+                            double *stdv_2d, double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d,
+                            double *stdv_3d, double *xcov_3d, double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (root < 0 || root >= h->nranks) return fail(h, GRITAS_B200_ERR_ARG, "bad root");
+  CU(cudaStreamSynchronize(h->copy));
+  double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
+  if (h->nranks == 1 || !h->comm) {
+    if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+    return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
+  }
+  return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr, root);
+}
+
+int gritas_b200_norm_reduce_device(gritas_b200_handle h, int root, int nrmlz, int ntresh, const double **outs10) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (root < 0 || root >= h->nranks || !outs10) return fail(h, GRITAS_B200_ERR_ARG, "bad root / outs");
+  CU(cudaStreamSynchronize(h->copy));
+  double *const u[10] = {};
+  if (h->nranks == 1 || !h->comm) {
+    if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+    return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10);
+  }
+  return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10, root);
 }
 
 int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, double *xcov_2d, double *nobs_2d,

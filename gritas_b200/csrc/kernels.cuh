@@ -1045,13 +1045,13 @@ constexpr int TILE_ILP = 2;
 
 template <int NR>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
-k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec) {
+k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0, unsigned tile1) {
   constexpr int NV = TilePlanes<NR>::NV;
   extern __shared__ double s_val[];                       // NV planes of T doubles, then T counts
   const unsigned T = 1u << sg.tile_shift;
   unsigned *s_cnt = reinterpret_cast<unsigned *>(s_val + (size_t)NV * T);
   const int rs_shift = (g.rs == 4) ? 2 : 3;
-  for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
+  for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
     if (n == 0) continue;                                 // uniform across the CTA
     for (unsigned e = threadIdx.x; e < NV * T; e += blockDim.x) s_val[e] = 0.0;
@@ -1219,13 +1219,13 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
 // one go (two barriers per tile), written longitude-fastest (the reference's layout).
 template <int NR>
 __global__ void __launch_bounds__(1024)
-k_finalize3(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw) {
+k_finalize3(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw, int jl0, int jl1) {
   constexpr int NP = 4 * NR + 1;
   extern __shared__ double s_tile[];               // [NP][32][33]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int k0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
   const size_t plane = (size_t)g.im * g.jm * g.km * g.l3d;  // one ir slab
-  for (int jl = blockIdx.z; jl < g.jm * g.l3d; jl += gridDim.z) {
+  for (int jl = jl0 + blockIdx.z; jl < jl1; jl += gridDim.z) {
     const int j = jl % g.jm, l = jl / g.jm;
     double v[NP];
 #pragma unroll

@@ -239,6 +239,17 @@ class Grids:
         buf = C.create_string_buffer(unique_id, 128)
         self._check(cabi.load().gritas_b200_comm_init(self._h, nranks, rank, buf))
 
+    def norm_reduce_into(self, grids, root=0, nrmlz=True, ntresh=None):
+        """Collective GrITAS_Norm of a multi-rank run: only the root's arrays are written."""
+        g = grids
+        p = lambda k, on: cabi.ptr(g[k], np.float64) if on else None
+        rc = cabi.load().gritas_b200_norm_reduce(
+            self._h, root, 1 if nrmlz else 0, -1 if ntresh is None else int(ntresh),
+            p("bias_2d", self.l2d), p("rtms_2d", self.l2d), p("stdv_2d", self.l2d), p("xcov_2d", self.l2d), p("nobs_2d", self.l2d),
+            p("bias_3d", self.l3d), p("rtms_3d", self.l3d), p("stdv_3d", self.l3d), p("xcov_3d", self.l3d), p("nobs_3d", self.l3d))
+        self._check(rc)
+        return g
+
     def allreduce(self):
         self._check(cabi.load().gritas_b200_allreduce(self._h))
 

@@ -165,6 +165,15 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
 int gritas_b200_nccl_unique_id(void *id128);  /* rank 0 fills 128 bytes; broadcast them */
 int gritas_b200_comm_init(gritas_b200_handle h, int nranks, int rank, const void *id128);
 int gritas_b200_allreduce(gritas_b200_handle h);
+/* Multi-rank GrITAS_Norm in one collective call: the tile flush, an ncclReduce of the partial accumulators
+ * to `root` and the finalize kernel are pipelined chunk by chunk (the reduction of chunk c overlaps the
+ * accumulation of chunk c+1 and the finalize of chunk c-1).  Only the root's arrays are written (the
+ * reference has one writer).  Same array meaning as gritas_b200_norm / _norm_device (outs10: the ten
+ * pointers in the order bias_2d rtms_2d stdv_2d xcov_2d nobs_2d bias_3d rtms_3d stdv_3d xcov_3d nobs_3d). */
+int gritas_b200_norm_reduce(gritas_b200_handle h, int root, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d,
+                            double *stdv_2d, double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d,
+                            double *stdv_3d, double *xcov_3d, double *nobs_3d);
+int gritas_b200_norm_reduce_device(gritas_b200_handle h, int root, int nrmlz, int ntresh, const double **outs10);
 
 /* Pinned host memory for the caller's column arrays (direct DMA, no staging copy). */
 void *gritas_b200_host_alloc(size_t bytes);
