@@ -27,7 +27,8 @@ using namespace gb200;
 namespace {
 
 constexpr int NSLOT = 2;   // staging slots (double buffering)
-constexpr int NWK = 3;     // worker streams of the tiled path: partition kernels of consecutive calls overlap
+constexpr int NWK = 8;     // max worker streams of the tiled path (GRITAS_B200_WORKERS, default 3): partition
+                           // kernels of consecutive calls overlap
 constexpr int NCOL = 12;   // staged columns per slot
 enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME };
 
@@ -114,6 +115,8 @@ struct gritas_b200_ctx {
   bool wk_pending[NWK] = {};
   StageDesc sgw[NWK] = {};
   int next_wk = 0;
+  int nwk = 3;
+  bool p2_small = false;          // K1q round size 2048 (256 threads) instead of 4096 (512 threads)
   cudaEvent_t main_ev = nullptr;  // last accumulator-wide operation queued on `compute`
   // reduce + finalize pipeline (multi-GPU): chunk c is tile-accumulated on `compute`, reduced to the root on
   // `comm_stream`, finalized on `fin_stream` while later chunks are still being accumulated / reduced
@@ -321,18 +324,21 @@ void launch_partition(gritas_b200_handle h, int w, const ObsCols &c, const Filte
   }
   // K1q items: each bucket's runs in `parts` ranges of roughly 3800 entries (if everything were accepted)
   const size_t per_bucket = (size_t)nbatch * P1_BATCH / sg.nbuckets;
-  const int parts = (int)std::max((size_t)1, (per_bucket + 3799) / 3800);
-  const int g2 = std::min((int)sg.nbuckets * parts, 148 * 2);
+  const size_t per_part = h->p2_small ? 1900 : 3800;
+  const int parts = (int)std::max((size_t)1, (per_bucket + per_part - 1) / per_part);
+  const int g2 = std::min((int)sg.nbuckets * parts, 148 * (h->p2_small ? 4 : 2));
   static const bool skip_q = getenv("GRITAS_B200_DEBUG_SKIP_K1Q") != nullptr;  // timing experiments only
   if (skip_q) return;
-  k_part_tiles<NR><<<g2, P2_THREADS, h->p2_smem, h->wk[w]>>>(h->g, sg, parts);
+  if (h->p2_small) k_part_tiles<NR, 2048, 256><<<g2, 256, h->p2_smem, h->wk[w]>>>(h->g, sg, parts);
+  else k_part_tiles<NR, 4096, 512><<<g2, 512, h->p2_smem, h->wk[w]>>>(h->g, sg, parts);
 }
 
 // K2t over every tile with staged entries; afterwards the lists are empty.
 template <int NR>
 void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1) {
   if (t1 <= t0) return;
-  k_tile_accum<NR><<<(int)(t1 - t0), TILE_THREADS, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, t0, t1);
+  const int thr = h->tile_smem > 110 * 1024 ? 1024 : TILE_THREADS;   // one CTA per SM: give it all the warps
+  k_tile_accum<NR><<<(int)(t1 - t0), thr, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, t0, t1);
 }
 
 void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1) {
@@ -385,7 +391,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
   const int w = h->next_wk;
   cudaStream_t run = tiled ? h->wk[w] : h->compute;
   if (tiled) {
-    h->next_wk = (h->next_wk + 1) % NWK;
+    h->next_wk = (h->next_wk + 1) % h->nwk;
     CU(cudaStreamWaitEvent(run, h->main_ev, 0));   // not before the last reset / flush
   }
   if (any_copy) {
@@ -625,8 +631,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
       size_t slots = e_slots ? (size_t)atoll(e_slots) : std::min((size_t)384 << 20, std::max((size_t)8 << 20, 20 * h->nrec));
       slots = std::min(slots, free_b / 4 / entry);
       const size_t ntiles = (h->nrec + T - 1) / T;
-      size_t tpb = 1;                                     // tiles per level-1 bucket
-      while ((ntiles + tpb - 1) / tpb > PB_MAXB) tpb <<= 1;
+      size_t tpb = 1;                                     // tiles per level-1 bucket: 57..112 buckets when possible
+      while ((ntiles + tpb - 1) / tpb > 112) tpb <<= 1;
       int tsh = 0;
       while (((size_t)1 << tsh) < tpb) ++tsh;
       const size_t nbuckets = (ntiles + tpb - 1) / tpb;
@@ -643,15 +649,19 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         const size_t nfill = nbuckets * tpb;              // padded: every (bucket, local tile) has a counter
         CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * nfill));
         CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * nfill));
-        // level-1 scratch: one run of c1 slots per (bucket, K1p batch); c1 = power of two >= 1.5x the mean run
-        // (fuller runs are accumulated directly); few dead slots keep K1q's scan short
+        // level-1 scratch: one run of c1 slots per (bucket, K1p batch), mirrored by a shared-memory bin in K1p;
+        // c1 = power of two >= 1.5x the mean run when every observation is accepted (fuller bins overflow
+        // into the direct accumulate), bounded by the shared memory the bins may take
         unsigned c1 = 16, c1_shift = 4;
         while (c1 < 512 && (size_t)c1 * nbuckets * 2 < (size_t)3 * P1_BATCH) { c1 <<= 1; ++c1_shift; }
+        while (c1 > 16 && (size_t)c1 * nbuckets * (8 * nr + 4) > (size_t)100 * 1024) { c1 >>= 1; --c1_shift; }
         h->sg.c1 = c1;
         h->sg.c1_shift = c1_shift;
         h->sg.nbatch_cap = 1024;                          // 2 Mi observations per slice
         h->scratch_cap = nbuckets * (size_t)h->sg.nbatch_cap * c1;
-        for (int w = 0; w < NWK; ++w) {                   // one scratch, stream and event per worker
+        if (const char *e_p = getenv("GRITAS_B200_P2_SMALL")) h->p2_small = atoi(e_p) != 0;
+        if (const char *e_w = getenv("GRITAS_B200_WORKERS")) h->nwk = std::max(1, std::min(NWK, atoi(e_w)));
+        for (int w = 0; w < h->nwk; ++w) {                // one scratch, stream and event per worker
           h->sgw[w] = h->sg;
           CUC(cudaMalloc(&h->sgw[w].cnt1, sizeof(unsigned) * nbuckets * h->sg.nbatch_cap));
           CUC(cudaMalloc(&h->sgw[w].key1, sizeof(unsigned) * h->scratch_cap));
@@ -663,31 +673,34 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sg.sd[ir], sizeof(double) * h->stage_slots));
         const size_t p2b = levtab_smem_bytes(g);
         if (nr == 1) {
-          h->p1_smem = ((part_smem_bytes<1, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
-          h->p2_smem = ((part_smem_bytes<1, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
+          h->p1_smem = p1_smem_bytes<1>((unsigned)(nbuckets << c1_shift)) + p2b;
+          h->p2_smem = h->p2_small ? p2_smem_bytes<1, 2048, 256>() : p2_smem_bytes<1, 4096, 512>();
           CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUC(cudaFuncSetAttribute(k_part_obs<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_obs<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_obs<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+          if (h->p2_small) CUC(cudaFuncSetAttribute(k_part_tiles<1, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+          else CUC(cudaFuncSetAttribute(k_part_tiles<1, 4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         } else if (nr == 2) {
-          h->p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
-          h->p2_smem = ((part_smem_bytes<2, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
+          h->p1_smem = p1_smem_bytes<2>((unsigned)(nbuckets << c1_shift)) + p2b;
+          h->p2_smem = h->p2_small ? p2_smem_bytes<2, 2048, 256>() : p2_smem_bytes<2, 4096, 512>();
           CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUC(cudaFuncSetAttribute(k_part_obs<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_obs<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_obs<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+          if (h->p2_small) CUC(cudaFuncSetAttribute(k_part_tiles<2, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+          else CUC(cudaFuncSetAttribute(k_part_tiles<2, 4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         } else {
-          h->p1_smem = ((part_smem_bytes<3, P1_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * P1_BATCH + p2b;
-          h->p2_smem = ((part_smem_bytes<3, P2_SCAP>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_MAXRUNS + 40);
+          h->p1_smem = p1_smem_bytes<3>((unsigned)(nbuckets << c1_shift)) + p2b;
+          h->p2_smem = h->p2_small ? p2_smem_bytes<3, 2048, 256>() : p2_smem_bytes<3, 4096, 512>();
           CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CUC(cudaFuncSetAttribute(k_part_obs<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_obs<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
           CUC(cudaFuncSetAttribute(k_part_obs<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+          if (h->p2_small) CUC(cudaFuncSetAttribute(k_part_tiles<3, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
+          else CUC(cudaFuncSetAttribute(k_part_tiles<3, 4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
         }
-        for (int w = 0; w < NWK; ++w) {                   // tile-list fields are shared by all workers
+        for (int w = 0; w < h->nwk; ++w) {                // tile-list fields are shared by all workers
           StageDesc &q = h->sgw[w];
           q.fill = h->sg.fill; q.skey = h->sg.skey;
           for (int ir = 0; ir < 3; ++ir) q.sd[ir] = h->sg.sd[ir];

@@ -299,18 +299,41 @@ __device__ __forceinline__ void prefetch_batch(const ObsCols &c, const FilterDes
   }
 }
 
-// streaming 128-bit loads that do not pollute L1
+// L2 residency policy: the observation columns are read exactly once (evict first), the level-1 scratch is
+// written by K1p and read back by K1q a few microseconds later (evict last) -- otherwise the 63 MB of columns
+// per file push the 20 MB scratch out of L2 and it makes a round trip through HBM.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// streaming 128-bit loads that do not pollute L1 and leave L2 first
 __device__ __forceinline__ double2 ldg_stream2(const double *p) {
   double2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
 __device__ __forceinline__ int4 ldg_stream4(const int *p) {
   int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+               : "l"(p), "l"(l2_policy_evict_first()));
   return r;
+}
+// scratch stores that should stay in L2 until K1q has read them
+__device__ __forceinline__ void stg_keep2(unsigned *p, uint2 v) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(l2_policy_evict_last()) : "memory");
+}
+__device__ __forceinline__ void stg_keep2(double *p, double2 v) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(l2_policy_evict_last()) : "memory");
 }
 
 template <int NR>
@@ -684,7 +707,8 @@ constexpr unsigned PB_OVERFLOW = 0xFFFFFFFFu;
 // K1p: 256 threads x 8 observations, 3 CTAs per SM so that load / group / write-out phases of
 // different CTAs overlap.  K1q: 512 threads, two passes over a 4096-entry chunk (count, then regroup), 2 CTAs per SM.
 constexpr int P1_THREADS = 256, P1_ITEMS = 8, P1_BATCH = P1_THREADS * P1_ITEMS, P1_SCAP = P1_BATCH + 8 * PB_MAXB;
-constexpr int P2_THREADS = 512, P2_BATCH = 4096, P2_SCAP = P2_BATCH + 8 * PB_MAXB;
+// K1q comes in two sizes: rounds of 4096 entries (512 threads, 2 CTAs/SM) or 2048 entries (256 threads, 4 CTAs/SM)
+constexpr int P2_PAD = 8 * PB_MAXB;
 
 template <int NR>
 struct PartView {
@@ -698,13 +722,10 @@ struct PartView {
   unsigned char *grp;   // [SCAP/8] destination of each group of 8 staged entries
 };
 
-// Bytes of the grouped-entry staging (residual planes + keys).  K1p also parks the batch's lat / lon / lev
-// there while it classifies (3 * P1_BATCH doubles), so the region is at least that large.
+// Bytes of the grouped-entry staging (residual planes + keys).
 template <int NR, int SCAP>
 __host__ __device__ constexpr size_t part_stage_bytes() {
-  return (sizeof(double) * NR * SCAP + sizeof(unsigned) * SCAP) > (sizeof(double) * 3 * P1_BATCH)
-             ? (sizeof(double) * NR * SCAP + sizeof(unsigned) * SCAP)
-             : (sizeof(double) * 3 * P1_BATCH);
+  return sizeof(double) * NR * SCAP + sizeof(unsigned) * SCAP;
 }
 
 template <int NR, int SCAP>
@@ -804,10 +825,10 @@ __device__ __forceinline__ void part_writeout(const PartView<NR> &v, unsigned ca
     const unsigned b = v.grp[s >> 3], run = v.run[b];
     if (run == PB_OVERFLOW) continue;
     const size_t gi = (size_t)(list_first + b) * cap + run + (s - v.off[b]);
-    *reinterpret_cast<uint2 *>(g_key + gi) = *reinterpret_cast<const uint2 *>(v.key + s);
+    __stcs(reinterpret_cast<uint2 *>(g_key + gi), *reinterpret_cast<const uint2 *>(v.key + s));
 #pragma unroll
     for (int ir = 0; ir < NR; ++ir)
-      *reinterpret_cast<double2 *>(g_d[ir] + gi) = *reinterpret_cast<const double2 *>(v.d[ir] + s);
+      __stcs(reinterpret_cast<double2 *>(g_d[ir] + gi), *reinterpret_cast<const double2 *>(v.d[ir] + s));
   }
 }
 
@@ -835,18 +856,28 @@ __device__ __forceinline__ void phase_stamp(int slot) {
 #define GB_STAMP(i)
 #endif
 
-// K1p: a batch of P1_BATCH observations per CTA iteration, in two passes so that only the keys stay
-// in registers across the barriers: (A) coordinates -> classify -> count per bucket, (B) residual
-// columns -> ticket -> grouped staging.  Each column is still read from HBM exactly once.
+// K1p: a batch of P1_BATCH observations per CTA iteration, ONE pass.  Every level-1 bucket owns a bin of c1
+// slots in shared memory -- the image of its run in the global scratch.  A thread classifies 4 observations,
+// takes a ticket in the bucket's bin for each accepted one, loads the residuals and drops the entry into
+// the bin (entries beyond c1 are accumulated directly).  After one barrier the live part of every bin,
+// rounded up to 8 entries, is copied to the global run with full aligned sectors.
+template <int NR>
+__host__ __device__ constexpr size_t p1_smem_bytes(unsigned nslot) {
+  return ((size_t)nslot * (8 * NR + 4) + 15) / 16 * 16 + sizeof(unsigned) * PB_MAXB;
+}
+
 template <int NR, int FMODE>
 __global__ void __launch_bounds__(P1_THREADS, 3)
 k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
            const StageDesc sg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const PartView<NR> v = part_view<NR, P1_SCAP>(smem_raw);
-  unsigned char *sp = smem_raw + ((part_smem_bytes<NR, P1_SCAP>() + 15) & ~(size_t)15);
-  uint4 *s_akey = reinterpret_cast<uint4 *>(sp);           // [P1_BATCH / 4] keys of the batch in arrival order
-  double *s_p2 = reinterpret_cast<double *>(sp + sizeof(unsigned) * P1_BATCH);
+  const unsigned nslot = sg.nbuckets << sg.c1_shift;
+  double *s_d[NR];
+#pragma unroll
+  for (int ir = 0; ir < NR; ++ir) s_d[ir] = reinterpret_cast<double *>(smem_raw) + (size_t)ir * nslot;
+  unsigned *s_key = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(smem_raw) + (size_t)NR * nslot);
+  unsigned *s_cnt = reinterpret_cast<unsigned *>(smem_raw + ((size_t)nslot * (8 * NR + 4) + 15) / 16 * 16);
+  double *s_p2 = reinterpret_cast<double *>(smem_raw + p1_smem_bytes<NR>(nslot));
   const int tid = threadIdx.x;
   GB_STAMP(0);
   const LevTab p2s = load_p2(g, s_p2);
@@ -858,14 +889,14 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
   for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
     const int nxt = batch + (int)gridDim.x;
     if (nxt < nbatch) prefetch_batch(c, f, NR, nxt * P1_BATCH, min(P1_BATCH, c.n - nxt * P1_BATCH));
-    if (tid < PB_MAXB) { v.cnt[tid] = 0u; v.cnt2[tid] = 0u; }
+    if (tid < PB_MAXB) s_cnt[tid] = 0u;
     __syncthreads();
-    // ---- pass A: coordinates -> keys (kept in shared memory) + per-bucket counts ----
 #pragma unroll 1
     for (int h = 0; h < P1_ITEMS / 4; ++h) {
       const int base = batch * P1_BATCH + (h * P1_THREADS + tid) * 4;
-      unsigned k4[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
-      if (base < c.n) {
+      if (base >= c.n) continue;
+      unsigned k4[4];
+      {
         Obs4<NR> o;
         int fa[4];
         load_geo4<NR>(c, f, base, o);
@@ -880,24 +911,7 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
           }
         }
       }
-      s_akey[h * P1_THREADS + tid] = make_uint4(k4[0], k4[1], k4[2], k4[3]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (k4[j] != KEY_NONE) atomicAdd(v.cnt + (k4[j] >> sg.bucket_shift), 1u);
-    }
-    __syncthreads();
-    GB_STAMP(2);
-    // the run of (bucket b, this batch) starts at slot batch * c1 of bucket b's scratch row
-    part_layout<NR, false>(v, nb, sg.c1, (unsigned)batch << sg.c1_shift, nullptr, nullptr, 0u, 0u);
-    if (tid < nb) sg.cnt1[(size_t)tid * sg.nbatch_cap + batch] = min(v.cnt[tid], sg.c1);
-    GB_STAMP(3);
-    // ---- pass B: residual columns -> ticket -> grouped staging ----
-#pragma unroll 1
-    for (int h = 0; h < P1_ITEMS / 4; ++h) {
-      const int base = batch * P1_BATCH + (h * P1_THREADS + tid) * 4;
-      const uint4 kq = s_akey[h * P1_THREADS + tid];
-      const unsigned k4[4] = {kq.x, kq.y, kq.z, kq.w};
-      if ((kq.x & kq.y & kq.z & kq.w) == KEY_NONE) continue;
+      if ((k4[0] & k4[1] & k4[2] & k4[3]) == KEY_NONE) continue;
       double dd[NR][4];
       load_del4<NR>(c, base, dd);
 #pragma unroll
@@ -908,20 +922,29 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) d[ir] = f.scale_res ? scale_residual(f, c, dd[ir][j], base + j) : dd[ir][j];
         const unsigned b = key >> sg.bucket_shift;
-        const unsigned rank = atomicAdd(v.cnt2 + b, 1u);
+        const unsigned rank = atomicAdd(s_cnt + b, 1u);
         if (rank >= sg.c1) {
-          red_entry<NR>(g, key, d);     // the run of this (bucket, batch) is full: accumulate directly
+          red_entry<NR>(g, key, d);     // the bin of this bucket is full: accumulate directly
         } else {
-          const unsigned sidx = v.off[b] + rank;
-          v.key[sidx] = key;
+          const unsigned slot = (b << sg.c1_shift) + rank;
+          s_key[slot] = key;
 #pragma unroll
-          for (int ir = 0; ir < NR; ++ir) v.d[ir][sidx] = d[ir];
+          for (int ir = 0; ir < NR; ++ir) s_d[ir][slot] = d[ir];
         }
       }
     }
     __syncthreads();
-    GB_STAMP(4);
-    part_writeout<NR>(v, sg.nbatch_cap << sg.c1_shift, 0u, sg.key1, sg.d1);
+    GB_STAMP(2);
+    if (tid < nb) sg.cnt1[(size_t)tid * sg.nbatch_cap + batch] = min(s_cnt[tid], sg.c1);
+    // bins -> runs: bucket b's run of this batch starts at slot (b * nbatch_cap + batch) * c1 of the scratch
+    for (unsigned s2 = (unsigned)tid * 2u; s2 < nslot; s2 += P1_THREADS * 2u) {
+      const unsigned b = s2 >> sg.c1_shift, i = s2 & (sg.c1 - 1u);
+      if (i >= ((min(s_cnt[b], sg.c1) + 7u) & ~7u)) continue;   // slots past the count hold stale data: never read
+      const size_t gi = (((size_t)b * sg.nbatch_cap + (size_t)batch) << sg.c1_shift) + i;
+      stg_keep2(sg.key1 + gi, *reinterpret_cast<const uint2 *>(s_key + s2));
+#pragma unroll
+      for (int ir = 0; ir < NR; ++ir) stg_keep2(sg.d1[ir] + gi, *reinterpret_cast<const double2 *>(s_d[ir] + s2));
+    }
     __syncthreads();
     GB_STAMP(5);
   }
@@ -933,11 +956,16 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
 // rounds of at most P2_BATCH live entries; every round is two passes over its runs (they sit in L2):
 // count per tile, lay out + reserve list space, then reload and scatter with a second ticket counter
 // -- nothing is kept in registers across the barriers.
-constexpr int P2_MAXRUNS = P2_THREADS;  // runs (K1p batches) per round: one count per thread
+template <int NR, int P2_BATCH, int P2_THREADS>
+__host__ __device__ constexpr size_t p2_smem_bytes() {
+  return ((part_smem_bytes<NR, P2_BATCH + P2_PAD>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_THREADS + 40);
+}
 
-template <int NR>
-__global__ void __launch_bounds__(P2_THREADS, 2)
+template <int NR, int P2_BATCH, int P2_THREADS>
+__global__ void __launch_bounds__(P2_THREADS, 2048 / P2_THREADS / 2)
 k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
+  constexpr int P2_SCAP = P2_BATCH + P2_PAD;
+  constexpr int P2_MAXRUNS = P2_THREADS;  // runs (K1p batches) per round: one count per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PartView<NR> v = part_view<NR, P2_SCAP>(smem_raw);
   unsigned *s_rcnt = reinterpret_cast<unsigned *>(smem_raw + ((part_smem_bytes<NR, P2_SCAP>() + 15) & ~(size_t)15));
@@ -983,45 +1011,84 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
       const unsigned nrun = (unsigned)__syncthreads_count(fits);  // fits is a prefix property: count = cut
       const unsigned nslot = nrun << sg.c1_shift;
       const size_t src = (row + lo) << sg.c1_shift;
-      // ---- pass 1: count per tile (4 slots per thread and iteration, loads issued together) ----
-      for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
-        unsigned key[4];
+      // ---- pass 1: count per tile.  One warp per run (c1 <= 32: lane = slot), two runs in flight ----
+      if (sg.c1 <= 32u) {
+        const unsigned rpw = 32u / sg.c1;                   // runs per warp instruction
+        const unsigned sub = (unsigned)lane >> sg.c1_shift, i = (unsigned)lane & (sg.c1 - 1u);
+        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 2u) {
+          unsigned key[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const unsigned sidx = s0 + u * P2_THREADS;
-          const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
-          key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
+          for (int u = 0; u < 2; ++u) {
+            const unsigned r = r0 + (unsigned)u * (P2_THREADS / 32) * rpw + sub;
+            const bool live = r < nrun && i < s_rcnt[r];
+            key[u] = live ? __ldcg(sg.key1 + src + ((size_t)r << sg.c1_shift) + i) : KEY_NONE;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
         }
+      } else {
+        for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
+          unsigned key[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
+          for (int u = 0; u < 4; ++u) {
+            const unsigned sidx = s0 + u * P2_THREADS;
+            const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
+            key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
+        }
       }
       __syncthreads();
       part_layout<NR, true>(v, nt, 0xFFFFFFFFu, 0u, sg.fill, sg.skey, sg.cap, b << tsh);
       // ---- pass 2: reload, ticket, scatter ----
-      for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
-        unsigned key[4];
-        double d[4][NR];
+      auto place = [&](unsigned key, const double (&d)[NR]) {
+        const unsigned t = (key >> sg.tile_shift) & tmask;
+        if (v.run[t] == PB_OVERFLOW) {
+          red_entry<NR>(g, key, d);
+        } else {
+          const unsigned at = v.off[t] + atomicAdd(v.cnt2 + t, 1u);
+          v.key[at] = key;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const unsigned sidx = s0 + u * P2_THREADS;
-          const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
-          key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
-#pragma unroll
-          for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + src + sidx) : 0.0;
+          for (int ir = 0; ir < NR; ++ir) v.d[ir][at] = d[ir];
         }
+      };
+      if (sg.c1 <= 32u) {
+        const unsigned rpw = 32u / sg.c1;
+        const unsigned sub = (unsigned)lane >> sg.c1_shift, i = (unsigned)lane & (sg.c1 - 1u);
+        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 2u) {
+          unsigned key[2];
+          double d[2][NR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (key[u] == KEY_NONE) continue;
-          const unsigned t = (key[u] >> sg.tile_shift) & tmask;
-          if (v.run[t] == PB_OVERFLOW) {
-            red_entry<NR>(g, key[u], d[u]);
-          } else {
-            const unsigned at = v.off[t] + atomicAdd(v.cnt2 + t, 1u);
-            v.key[at] = key[u];
+          for (int u = 0; u < 2; ++u) {
+            const unsigned r = r0 + (unsigned)u * (P2_THREADS / 32) * rpw + sub;
+            const bool live = r < nrun && i < s_rcnt[r];
+            const size_t at = src + ((size_t)r << sg.c1_shift) + i;
+            key[u] = live ? __ldcg(sg.key1 + at) : KEY_NONE;
 #pragma unroll
-            for (int ir = 0; ir < NR; ++ir) v.d[ir][at] = d[u][ir];
+            for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + at) : 0.0;
           }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (key[u] != KEY_NONE) place(key[u], d[u]);
+        }
+      } else {
+        for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
+          unsigned key[4];
+          double d[4][NR];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned sidx = s0 + u * P2_THREADS;
+            const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
+            key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
+#pragma unroll
+            for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + src + sidx) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (key[u] != KEY_NONE) place(key[u], d[u]);
         }
       }
       __syncthreads();

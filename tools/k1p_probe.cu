@@ -53,17 +53,17 @@ int main(int argc, char **argv) {
   Status hs; hs.first_bad = BAD_NONE; hs.bad_lev = 0; hs.ticket = 0; hs.pad = 0; CK(cudaMemcpy(st, &hs, sizeof(hs), cudaMemcpyHostToDevice));
   StageDesc sg = {};
   sg.tile_shift = 11; const size_t T = 2048; const size_t ntiles = (nrec + T - 1) / T;
-  size_t tpb = 1; while ((ntiles + tpb - 1) / tpb > PB_MAXB) tpb <<= 1; int tsh = 0; while (((size_t)1 << tsh) < tpb) ++tsh;
+  size_t tpb = 1; while ((ntiles + tpb - 1) / tpb > 112) tpb <<= 1; int tsh = 0; while (((size_t)1 << tsh) < tpb) ++tsh;
   sg.bucket_shift = 11 + tsh; sg.ntiles = (unsigned)ntiles; sg.nbuckets = (unsigned)((ntiles + tpb - 1) / tpb);
   sg.cap = 24000; sg.c1 = 32; sg.c1_shift = 5; sg.nbatch_cap = 1024; sg.nbatch = (n + P1_BATCH - 1) / P1_BATCH;
   CK(cudaMalloc(&sg.fill, sg.nbuckets * tpb * 4)); CK(cudaMemset(sg.fill, 0, sg.nbuckets * tpb * 4));
   CK(cudaMalloc(&sg.skey, ntiles * sg.cap * 4)); CK(cudaMalloc(&sg.sd[0], ntiles * sg.cap * 8)); CK(cudaMalloc(&sg.sd[1], ntiles * sg.cap * 8));
   const size_t sc = (size_t)sg.nbuckets * sg.nbatch_cap * sg.c1;
   CK(cudaMalloc(&sg.cnt1, (size_t)sg.nbuckets * sg.nbatch_cap * 4)); CK(cudaMalloc(&sg.key1, sc * 4)); CK(cudaMalloc(&sg.d1[0], sc * 8)); CK(cudaMalloc(&sg.d1[1], sc * 8));
-  const size_t p1_smem = ((part_smem_bytes<2, P1_SCAP>() + 15) & ~(size_t)15) + 4 * P1_BATCH + levtab_smem_bytes(g);
-  const size_t p2_smem = ((part_smem_bytes<2, P2_SCAP>() + 15) & ~(size_t)15) + 4 * (P2_MAXRUNS + 40);
+  const size_t p1_smem = p1_smem_bytes<2>(sg.nbuckets << sg.c1_shift) + levtab_smem_bytes(g);
+  const size_t p2_smem = p2_smem_bytes<2, 4096, 512>();
   CK(cudaFuncSetAttribute(k_part_obs<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem));
-  CK(cudaFuncSetAttribute(k_part_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
+  CK(cudaFuncSetAttribute((k_part_tiles<2, 4096, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
   const int nbatch = sg.nbatch;
   unsigned long long *buf; CK(cudaMalloc(&buf, (size_t)nbatch * 64)); CK(cudaMemset(buf, 0, (size_t)nbatch * 64));
   CK(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
@@ -76,7 +76,7 @@ int main(int argc, char **argv) {
     cudaEventRecord(e0);
     k_part_obs<2, 1><<<nbatch, P1_THREADS, p1_smem>>>(g, c, f, st, 1u, sg);
     cudaEventRecord(e1);
-    k_part_tiles<2><<<g2, P2_THREADS, p2_smem>>>(g, sg, parts);
+    k_part_tiles<2, 4096, 512><<<g2, 512, p2_smem>>>(g, sg, parts);
     cudaEventRecord(e2);
     CK(cudaDeviceSynchronize());
     float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
@@ -94,7 +94,7 @@ int main(int argc, char **argv) {
     const double s = (double)(hb[b * 8] - t0); start_avg += s; start_max = std::max(start_max, s);
   }
   printf("kernel span %.2f us; CTA start offset avg %.2f max %.2f us\n", (tend - t0) * 1e-3, start_avg / nbatch * 1e-3, start_max * 1e-3);
-  const char *nm[7] = {"", "load_p2", "passA(load+classify+count)", "layout", "passB(load d+scatter)", "writeout", "finish_status"};
+  const char *nm[7] = {"", "load_p2", "classify+ticket+bin", "-", "-", "writeout(2->5)", "end"};
   for (int k = 1; k < 7; ++k) printf("  %-28s %8.2f us avg per CTA\n", nm[k], ph[k] / nbatch * 1e-3);
   // histogram of CTA lifetimes
   std::vector<double> life(nbatch); for (int b = 0; b < nbatch; ++b) life[b] = (hb[b * 8 + 6] - hb[b * 8]) * 1e-3;
