@@ -45,6 +45,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DRIVER = os.path.join(HERE, "bin", "gritas_b200_driver")
+
+
+def build_driver(force: bool = False) -> str:
+    """C++ stand-in for the Fortran caller (csrc/gritas_driver.cpp + m_gritas_grids.hpp), linked against the .so."""
+    src = [os.path.join(CSRC, "gritas_driver.cpp"), os.path.join(CSRC, "m_gritas_grids.hpp")]
+    if not force and os.path.exists(DRIVER) and all(os.path.getmtime(DRIVER) >= os.path.getmtime(s) for s in src + [LIB]):
+        return DRIVER
+    os.makedirs(os.path.dirname(DRIVER), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", DRIVER, src[0], "-L" + LIBDIR, "-lgritas_b200",
+                           "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../lib"])
+    return DRIVER
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_driver(force=True))

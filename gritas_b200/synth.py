@@ -183,3 +183,31 @@ def make_file(cfg: Config, file_index: int = 0) -> dict:
     xm = rng.normal(0.0, 0.2, n)
     return dict(lat=lat, lon=lon, lev=lev, time=time, kt=kt, kx=kx, ks=ks, qcexcl=qcexcl,
                 obs=obs, omf=omf, oma=oma, xvec=xvec, xm=xm)
+
+
+def write_flat(path, cols) -> None:
+    """One synoptic time as the flat column file read by csrc/gritas_driver.cpp (no NetCDF in this image)."""
+    n = len(cols["lat"])
+    with open(path, "wb") as f:
+        np.asarray([n], np.int32).tofile(f)
+        for k in ("lat", "lon", "lev"):
+            np.ascontiguousarray(cols[k], np.float64).tofile(f)
+        for k in ("time", "kt", "kx", "ks", "qcexcl"):
+            np.ascontiguousarray(cols[k], np.int32).tofile(f)
+        for k in ("obs", "omf", "oma", "xvec"):
+            np.ascontiguousarray(cols[k], np.float64).tofile(f)
+
+
+def write_setup(path, cfg: Config) -> None:
+    """Grid / level / kt-kx list description for csrc/gritas_driver.cpp."""
+    listsz = len(cfg.kt_list)
+    kxl = np.full((cfg.kxmax, listsz), -1, dtype=np.int32, order="F")
+    for j, ks in enumerate(cfg.kx_lists):
+        kxl[: len(ks), j] = np.asarray(ks, np.int32)
+    with open(path, "wb") as f:
+        np.asarray([cfg.im, cfg.jm, cfg.nlevs, cfg.kxmax, cfg.ktmax, listsz], np.int32).tofile(f)
+        np.ascontiguousarray(cfg.plevs, np.float64).tofile(f)
+        np.asarray(cfg.kt_list, np.int32).tofile(f)
+        kxl.ravel(order="F").tofile(f)
+        np.asarray([len(cfg.kt_surf)], np.int32).tofile(f)
+        np.asarray(cfg.kt_surf, np.int32).tofile(f)

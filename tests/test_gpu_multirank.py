@@ -1,0 +1,62 @@
+"""Two ranks on two GPUs: files sharded f mod 2, partial accumulators reduced to rank 0 inside the pipelined
+multi-rank Norm, result compared with the single-process oracle.  Skipped on boxes with one GPU."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, nfiles, uid_q, out_q, mode):
+    import torch
+
+    from gritas_b200 import shard, synth
+    from gritas_b200.m_gritas_grids import Grids, nccl_unique_id
+    torch.cuda.set_device(rank)
+    cfg = synth.get_config("cfg2", 0.02)
+    cfg.im, cfg.jm = 72, 46
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode, device=rank)
+    G._ensure(2, table, p1, p2, l2d, l3d)
+    if rank == 0:
+        uid = nccl_unique_id()
+        for _ in range(world - 1):
+            uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    G.comm_init(world, rank, uid)
+    for fi in shard.files_for_rank(nfiles, rank, world):
+        c = synth.make_file(cfg, fi)
+        G.accum_ods(c, iopt=101, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
+    out = G.alloc_grids()
+    G.norm_reduce_into(out, root=0)
+    if rank == 0:
+        out_q.put({k: v.copy() for k, v in out.items()})
+    G.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_two_rank_norm_reduce_matches_oracle(mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from gritas_b200 import synth
+    world, nfiles = 2, 5
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, nfiles, uid_q, out_q, mode)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = out_q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    cfg = synth.get_config("cfg2", 0.02)
+    cfg.im, cfg.jm = 72, 46
+    files = [synth.make_file(cfg, i) for i in range(nfiles)]
+    table, l2d, l3d, *_ = H.setup(cfg)
+    ref, _ = H.oracle_run(cfg, files, 2, [H.filter_in(c, 101) for c in files])
+    H.compare(got, ref, l2d, l3d, 2, exact=False, tol=1e-12)      # sums re-associated across ranks: not bit-exact
