@@ -33,7 +33,9 @@ METRIC = "observations_binned_per_sec"
 UNIT = "obs/s"
 COLS_F64 = ("lat", "lon", "lev", "omf", "oma")
 COLS_I32 = ("kt", "kx", "qcexcl")
-B_OBS = 36 + 8 * 2  # algorithmic bytes per observation at nr=2 (SURVEY.md 8d / BASELINE.md 3)
+def b_obs(nr):
+    """algorithmic bytes per observation (SURVEY.md 8d / BASELINE.md 3): 44 B at nr=1, 52 B at nr=2"""
+    return 36 + 8 * nr
 
 
 def parse():
@@ -64,7 +66,8 @@ def gen_files(cfg, first, count, workers=8):
 
 
 def workload_name(cfg, nfiles):
-    return (f"{cfg.name}: {nfiles} files x {cfg.nobs_per_file} obs, omf+oma (nr=2), {cfg.im}x{cfg.jm}x{cfg.km}, "
+    what = "omf+oma (nr=2)" if cfg.nr == 2 else "omf (nr=1)"
+    return (f"{cfg.name}: {nfiles} files x {cfg.nobs_per_file} obs, {what}, {cfg.im}x{cfg.jm}x{cfg.km}, "
             f"{len(cfg.kt_list)} (kt,kx) grids")
 
 
@@ -128,7 +131,7 @@ def cpu_reference_step(cfg, files, table, l2d, l3d, p1, p2, nthreads, grids):
         for a in (g.bias_3d, g.rtms_3d, g.xcov_3d, g.nobs_3d, g.bias_2d, g.rtms_2d, g.xcov_2d, g.nobs_2d):
             a[...] = 0.0
         for c in files[t::nthreads]:
-            fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=101, x_passive=synth.X_PASSIVE,
+            fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=1, x_passive=synth.X_PASSIVE,
                                      x_pre_bad=synth.X_PRE_BAD)
             oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], c["del"], table, p1, p2, fl)
     if nthreads == 1:
@@ -147,12 +150,14 @@ def cpu_reference_step(cfg, files, table, l2d, l3d, p1, p2, nthreads, grids):
     oracle.norm(grids[0], cfg.nlevs, True, 0)
 
 
-def prepare_cpu_files(files):
+def prepare_cpu_files(files, nr=2):
     out = []
     for c in files:
         n = len(c["lat"])
-        d = np.zeros((n, 2), order="F")
-        d[:, 0], d[:, 1] = c["omf"], c["oma"]      # gritas.f:562-587 (omf, oma)
+        d = np.zeros((n, nr), order="F")
+        d[:, 0] = c["omf"]                          # gritas.f:562-587 (omf [, oma])
+        if nr == 2:
+            d[:, 1] = c["oma"]
         cc = dict(c)
         cc["del"] = d
         cc["time"] = np.zeros(n, np.int32)
@@ -165,8 +170,8 @@ def time_cpu(cfg, files, nthreads, steps, warmup):
     from oracle import oracle
     table, l2d, l3d = synth.kxkt_table(cfg)
     p1, p2 = oracle.pint(cfg.plevs)
-    grids = [oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 2) for _ in range(nthreads)]
-    cf = prepare_cpu_files(files)
+    grids = [oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, cfg.nr) for _ in range(nthreads)]
+    cf = prepare_cpu_files(files, cfg.nr)
     nobs = sum(len(c["lat"]) for c in cf)
     for _ in range(warmup):
         cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids)
@@ -191,7 +196,7 @@ def run_reference(args):
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 16 << 30
-    per_thread = 8 * cfg.im * cfg.jm * cfg.km * len(cfg.kt_list) * 9 + (1 << 28)
+    per_thread = 8 * cfg.im * cfg.jm * cfg.km * len(cfg.kt_list) * (4 * cfg.nr + 1) + (1 << 28)
     nthreads = int(max(1, min(cores, 16, (avail // 2) // per_thread)))
     # bounded sample: about 4 s of CPU work per step (0.33 s per 1.21 M-obs file and thread here)
     nfiles = args.files or int(min(cfg.nfiles, max(nthreads, (4.0 / 0.35) * nthreads * (1.21e6 / cfg.nobs_per_file))))
@@ -241,7 +246,9 @@ def run_b200(args):
         mode |= cabi.FLAG_NO_STAGING
     G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode, device=local)
     p1, p2 = G.GrITAS_Pint()
-    G._ensure(2, table, p1, p2, l2d, l3d)
+    NR = cfg.nr
+    IOPT = cabi.IOPT_OMF_OMA if NR == 2 else cabi.IOPT_OMF
+    G._ensure(NR, table, p1, p2, l2d, l3d)
     if world > 1:
         ids = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -251,6 +258,12 @@ def run_b200(args):
 
     dev_files = [{k: torch.from_numpy(v).cuda() for k, v in c.items()} for c in files]
     torch.cuda.synchronize()
+    # host copies: pinned for the end-to-end arm; the pageable originals are only kept for the CPU baseline sample
+    pin_files = None
+    if not args.no_e2e:
+        pin_files = [{k: torch.from_numpy(v).pin_memory() for k, v in c.items()} for c in files]
+    keep = 32 if (rank == 0 and world == 1 and not args.no_cpu_baseline) else 0
+    files = files[:keep]
     import ctypes
 
     def calls_of(cols):
@@ -260,7 +273,7 @@ def run_b200(args):
         for c in cols:
             p = lambda k: cabi.ptr(c[k])
             out.append((G.handle, int(c["lat"].shape[0]), p("lat"), p("lon"), p("lev"), None, p("kt"), p("kx"),
-                        p("qcexcl"), p("omf"), p("oma"), None, None, cabi.IOPT_OMF_OMA, 0, cabi.IOPT_OMF_OMA, 0, -1,
+                        p("qcexcl"), p("omf"), p("oma") if NR == 2 else None, None, None, IOPT, 0, IOPT, 0, -1,
                         -999.0, 999.0, synth.X_PASSIVE, synth.X_PRE_BAD, None, None))
         return out
     dptr = [C_void() for _ in range(10)]
@@ -363,7 +376,6 @@ def run_b200(args):
     # ---- end-to-end arm: pinned host columns in, finalized grids out to pinned host arrays ----
     e2e = None
     if not args.no_e2e:
-        pin_files = [{k: torch.from_numpy(v).pin_memory() for k, v in c.items()} for c in files]
         host_out = G.alloc_grids(pinned=True)
         pin_calls = calls_of(pin_files)
         step(pin_calls, host_out)
@@ -396,16 +408,17 @@ def run_b200(args):
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     nbox = cfg.im * cfg.jm * cfg.km * l3d + cfg.im * cfg.jm * l2d
-    grid_bytes = 8 * (1 + 2 * 2) * nbox                      # written once per pass
+    B_OBS = b_obs(NR)
+    grid_bytes = 8 * (1 + 2 * NR) * nbox                     # written once per pass
     alg_bytes_per_launch = (nobs_rank * B_OBS + grid_bytes) / nfiles
     path_ms = accum_ms + flush_ms
     launch_ms = path_ms / nfiles
     achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    staged = args.mode == "fast" and not args.no_staging
+    staged = bool(L.gritas_b200_tiled(G.handle))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None,
                 "kernel": ("k_part_obs + k_part_tiles per file, k_tile_accum per flush" if staged else
-                           ("k_accum_fast<2>" if args.mode == "fast" else "k_box_keys + radix sort + k_segment_sum")),
+                           ("k_accum_fast" if args.mode == "fast" else "k_box_keys + radix sort + k_segment_sum")),
                 "peak_source": peak_src, "avg_launch_ms": launch_ms, "alg_bytes_per_launch": alg_bytes_per_launch,
                 "note": f"one launch = the accumulate work of one file: {B_OBS} B/obs x obs per file + (8*(1+2*nr)*boxes)/files; "
                         f"duration = (accumulate region + tile flush, CUDA events on the library stream) / {nfiles} files"}
@@ -415,7 +428,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
                        "per_rank": "each rank bins its own month; tile flush + ncclReduce to rank 0 + finalize pipelined in 8 chunks (rank 0 writes the grids, as the reference has one writer)",
-                       "l2": "inputs (7.8 GB/step) and accumulators (1.7 GB) both exceed the 126 MB L2; no flush needed"},
+                       "l2": f"inputs ({nobs_rank * b_obs(NR) / 1e9:.1f} GB/step) exceed the 126 MB L2; no flush needed"},
             "accumulate_ms_per_step": accum_ms, "tile_flush_ms_per_step": flush_ms,
             "host_enqueue_ms_per_step": host_ms, "multi_rank_count_check": check, "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roofline}
@@ -424,7 +437,7 @@ def run_b200(args):
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): single thread, like gritas.x ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ns = min(nfiles, 32)
+        ns = len(files)
         v, dt, nobs = time_cpu(cfg, files[:ns], 1, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{ns} of {nfiles} files ({nobs} obs): QC filter + GrITAS_Accum per file, "

@@ -102,6 +102,7 @@ struct gritas_b200_ctx {
   // tiled fast path: staging lists + flush bookkeeping
   StageDesc sg = {};
   bool staging = false;
+  bool acc_fresh = true;       // records untouched since create / reset (apart from direct RED, see StageDesc::dirty)
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
   size_t tile_smem = 0, p1_smem = 0, p2_smem = 0;
@@ -338,7 +339,7 @@ template <int NR>
 void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1) {
   if (t1 <= t0) return;
   const int thr = h->tile_smem > 110 * 1024 ? 1024 : TILE_THREADS;   // one CTA per SM: give it all the warps
-  k_tile_accum<NR><<<(int)(t1 - t0), thr, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, t0, t1);
+  k_tile_accum<NR><<<(int)(t1 - t0), thr, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, t0, t1, h->acc_fresh ? 1 : 0);
 }
 
 void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1) {
@@ -357,6 +358,7 @@ int flush_stage(gritas_b200_handle h) {
   CU(cudaGetLastError());
   h->launches += 1;
   h->staged_upper = 0;
+  h->acc_fresh = false;
   return mark_main(h);
 }
 
@@ -432,6 +434,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
       h->launches += 2;
     }
   } else if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
+    h->acc_fresh = false;
     const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
     const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
     switch (h->g.nr) {
@@ -441,6 +444,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     }
     h->launches += 1;
   } else {
+    h->acc_fresh = false;
     // K1 keys -> stable LSD radix sort of (key, obs index) -> in-order segment sums
     if (h->sort_cap < (size_t)n) {
       for (unsigned **p : {&h->keys, &h->idx, &h->keys2, &h->idx2}) {
@@ -647,8 +651,9 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         h->tile_smem = smem;
         h->tile_ctas = (int)std::min(ntiles, (size_t)1 << 20);
         const size_t nfill = nbuckets * tpb;              // padded: every (bucket, local tile) has a counter
-        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * nfill));
-        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * nfill));
+        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * (nfill + 4)));   // + the dirty word
+        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * (nfill + 4)));
+        h->sg.dirty = h->sg.fill + nfill;
         // level-1 scratch: one run of c1 slots per (bucket, K1p batch), mirrored by a shared-memory bin in K1p;
         // c1 = power of two >= 1.5x the mean run when every observation is accepted (fuller bins overflow
         // into the direct accumulate), bounded by the shared memory the bins may take
@@ -657,7 +662,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         while (c1 > 16 && (size_t)c1 * nbuckets * (8 * nr + 4) > (size_t)100 * 1024) { c1 >>= 1; --c1_shift; }
         h->sg.c1 = c1;
         h->sg.c1_shift = c1_shift;
-        h->sg.nbatch_cap = 1024;                          // 2 Mi observations per slice
+        h->sg.nbatch_cap = 2048;                          // 2 Mi observations per slice
         h->scratch_cap = nbuckets * (size_t)h->sg.nbatch_cap * c1;
         if (const char *e_p = getenv("GRITAS_B200_P2_SMALL")) h->p2_small = atoi(e_p) != 0;
         if (const char *e_w = getenv("GRITAS_B200_WORKERS")) h->nwk = std::max(1, std::min(NWK, atoi(e_w)));
@@ -702,7 +707,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         }
         for (int w = 0; w < h->nwk; ++w) {                // tile-list fields are shared by all workers
           StageDesc &q = h->sgw[w];
-          q.fill = h->sg.fill; q.skey = h->sg.skey;
+          q.fill = h->sg.fill; q.skey = h->sg.skey; q.dirty = h->sg.dirty;
           for (int ir = 0; ir < 3; ++ir) q.sd[ir] = h->sg.sd[ir];
           q.cap = h->sg.cap; q.ntiles = h->sg.ntiles; q.tile_shift = h->sg.tile_shift;
           q.c1 = h->sg.c1; q.c1_shift = h->sg.c1_shift; q.nbatch_cap = h->sg.nbatch_cap;
@@ -862,10 +867,11 @@ int gritas_b200_reset(gritas_b200_handle h) {
   int rc = check_handle(h);
   if (rc) return rc;
   if ((rc = join_workers(h))) return rc;
+  h->acc_fresh = true;
   CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   if (h->staging) {
     const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
-    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * nfill, h->compute));
+    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * (nfill + 4), h->compute));   // counters and the dirty word
     h->staged_upper = 0;
   }
   return mark_main(h);
@@ -999,6 +1005,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     }
     CU(cudaGetLastError());
     h->staged_upper = 0;
+    h->acc_fresh = false;
     CU(cudaEventRecord(h->ev_fin, writer ? h->fin_stream : h->comm_stream));
     CU(cudaStreamWaitEvent(h->compute, h->ev_fin, 0));
     if ((rc = mark_main(h))) return rc;
@@ -1088,6 +1095,7 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
   if (rc) return rc;
   if ((rc = flush_stage(h))) return rc;
   if ((rc = join_workers(h))) return rc;
+  h->acc_fresh = false;
   const GridDesc &g = h->g;
   const int nr = g.nr;
   const size_t n2 = g.nbox2, n3 = g.nbox3;
@@ -1158,6 +1166,7 @@ int gritas_b200_allreduce(gritas_b200_handle h) {
   if (!h->comm) return fail(h, GRITAS_B200_ERR_NCCL, "comm_init not called");
   CU(cudaStreamSynchronize(h->copy));
   if ((rc = flush_stage(h))) return rc;
+  h->acc_fresh = false;
   int e = g_nccl.AllReduce(h->g.acc, h->g.acc, h->nrec * h->g.rs, NCCL_FLOAT64, NCCL_SUM, h->comm, h->compute);
   if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
   return 0;
@@ -1247,6 +1256,7 @@ int gritas_b200_set_stream(gritas_b200_handle h, void *stream) {
   return 0;
 }
 
+int gritas_b200_tiled(gritas_b200_handle h) { return (h && h->staging) ? 1 : 0; }
 uint64_t gritas_b200_launch_count(gritas_b200_handle h) { return h ? h->launches : 0; }
 uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h) { return h ? h->h2d : 0; }
 uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h) { return h ? h->d2h : 0; }

@@ -82,6 +82,7 @@ struct StageDesc {
   double *sd[3];       // [ntiles * cap] per residual column
   unsigned cap, ntiles;
   int tile_shift;
+  unsigned *dirty;     // set when an entry was accumulated directly (list overflow): the records are no longer all zero
   // level 1: scratch of the current Accum call, one fixed run of c1 slots per (bucket, K1p batch): no
   // global tickets (same-address atomics serialise at ~60 ns each on B200).  A bucket is
   // 2^(bucket_shift-tile_shift) tiles.  The scratch is small enough to stay in L2 between K1p and K1q.
@@ -288,13 +289,13 @@ __device__ __forceinline__ void prefetch_batch(const ObsCols &c, const FilterDes
   const int t = threadIdx.x;
   const unsigned b8 = (unsigned)count * 8u, b4 = (unsigned)count * 4u;
   if (t == 0) prefetch_l2_bulk(c.lat + first, b8);
-  if (t == 32) prefetch_l2_bulk(c.lon + first, b8);
-  if (t == 64) prefetch_l2_bulk(c.lev + first, b8);
-  if (t == 96) prefetch_l2_bulk(c.kx + first, b4);
-  if (t == 128) prefetch_l2_bulk(c.kt + first, b4);
-  if (t == 160 && c.flag) prefetch_l2_bulk(c.flag + first, b4);
-  if (t == 192 && f.use_time) prefetch_l2_bulk(c.time + first, b4);
-  if (t == 224) {
+  if (t == 16) prefetch_l2_bulk(c.lon + first, b8);
+  if (t == 32) prefetch_l2_bulk(c.lev + first, b8);
+  if (t == 48) prefetch_l2_bulk(c.kx + first, b4);
+  if (t == 64) prefetch_l2_bulk(c.kt + first, b4);
+  if (t == 80 && c.flag) prefetch_l2_bulk(c.flag + first, b4);
+  if (t == 96 && f.use_time) prefetch_l2_bulk(c.time + first, b4);
+  if (t == 112) {
     for (int ir = 0; ir < nr; ++ir) prefetch_l2_bulk(c.d[ir] + first, b8);
   }
 }
@@ -925,6 +926,7 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
         const unsigned rank = atomicAdd(s_cnt + b, 1u);
         if (rank >= sg.c1) {
           red_entry<NR>(g, key, d);     // the bin of this bucket is full: accumulate directly
+          *sg.dirty = 1u;
         } else {
           const unsigned slot = (b << sg.c1_shift) + rank;
           s_key[slot] = key;
@@ -1048,6 +1050,7 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
         const unsigned t = (key >> sg.tile_shift) & tmask;
         if (v.run[t] == PB_OVERFLOW) {
           red_entry<NR>(g, key, d);
+          *sg.dirty = 1u;
         } else {
           const unsigned at = v.off[t] + atomicAdd(v.cnt2 + t, 1u);
           v.key[at] = key;
@@ -1112,12 +1115,14 @@ constexpr int TILE_ILP = 2;
 
 template <int NR>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
-k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0, unsigned tile1) {
+k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0, unsigned tile1, int fresh) {
   constexpr int NV = TilePlanes<NR>::NV;
   extern __shared__ double s_val[];                       // NV planes of T doubles, then T counts
   const unsigned T = 1u << sg.tile_shift;
   unsigned *s_cnt = reinterpret_cast<unsigned *>(s_val + (size_t)NV * T);
   const int rs_shift = (g.rs == 4) ? 2 : 3;
+  // first flush after a reset and nothing was accumulated directly: the records are zero, store instead of RMW
+  const bool overwrite = fresh && (*reinterpret_cast<volatile unsigned *>(sg.dirty) == 0u);
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
     if (n == 0) continue;                                 // uniform across the CTA
@@ -1205,7 +1210,7 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0
             any[u] = true;
             add[u].x = (slot == 0u) ? (double)cn : s_val[(size_t)(slot - 1u) * T + bxi];
             add[u].y = (slot + 1u <= (unsigned)NV) ? s_val[(size_t)slot * T + bxi] : 0.0;
-            cur[u] = span[e];
+            cur[u] = overwrite ? make_double2(0.0, 0.0) : span[e];
           }
         }
       }

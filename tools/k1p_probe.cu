@@ -55,8 +55,8 @@ int main(int argc, char **argv) {
   sg.tile_shift = 11; const size_t T = 2048; const size_t ntiles = (nrec + T - 1) / T;
   size_t tpb = 1; while ((ntiles + tpb - 1) / tpb > 112) tpb <<= 1; int tsh = 0; while (((size_t)1 << tsh) < tpb) ++tsh;
   sg.bucket_shift = 11 + tsh; sg.ntiles = (unsigned)ntiles; sg.nbuckets = (unsigned)((ntiles + tpb - 1) / tpb);
-  sg.cap = 24000; sg.c1 = 32; sg.c1_shift = 5; sg.nbatch_cap = 1024; sg.nbatch = (n + P1_BATCH - 1) / P1_BATCH;
-  CK(cudaMalloc(&sg.fill, sg.nbuckets * tpb * 4)); CK(cudaMemset(sg.fill, 0, sg.nbuckets * tpb * 4));
+  sg.cap = 24000; sg.c1 = 32; sg.c1_shift = 5; sg.nbatch_cap = 2048; sg.nbatch = (n + P1_BATCH - 1) / P1_BATCH;
+  CK(cudaMalloc(&sg.fill, sg.nbuckets * tpb * 4 + 16)); CK(cudaMemset(sg.fill, 0, sg.nbuckets * tpb * 4 + 16)); sg.dirty = sg.fill + sg.nbuckets * tpb;
   CK(cudaMalloc(&sg.skey, ntiles * sg.cap * 4)); CK(cudaMalloc(&sg.sd[0], ntiles * sg.cap * 8)); CK(cudaMalloc(&sg.sd[1], ntiles * sg.cap * 8));
   const size_t sc = (size_t)sg.nbuckets * sg.nbatch_cap * sg.c1;
   CK(cudaMalloc(&sg.cnt1, (size_t)sg.nbuckets * sg.nbatch_cap * 4)); CK(cudaMalloc(&sg.key1, sc * 4)); CK(cudaMalloc(&sg.d1[0], sc * 8)); CK(cudaMalloc(&sg.d1[1], sc * 8));
