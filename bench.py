@@ -414,7 +414,7 @@ def run_b200(args):
     path_ms = accum_ms + flush_ms
     launch_ms = path_ms / nfiles
     achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    staged = bool(L.gritas_b200_tiled(G.handle))
+    staged = L.gritas_b200_tiled(G.handle) == 1
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None,
                 "kernel": ("k_part_obs + k_part_tiles per file, k_tile_accum per flush" if staged else

@@ -21,6 +21,7 @@ FLAG_ASYNC = 0x100
 FLAG_NO_AGGREGATE = 0x200
 FLAG_HOLD_INPUTS = 0x400
 FLAG_NO_STAGING = 0x800
+FLAG_FORCE_TILED = 0x1000
 
 OK = 0
 ERR_LEVEL = 7

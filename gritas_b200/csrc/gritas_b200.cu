@@ -101,7 +101,8 @@ struct gritas_b200_ctx {
   int key_bits = 32;
   // tiled fast path: staging lists + flush bookkeeping
   StageDesc sg = {};
-  bool staging = false;
+  bool staging = false;        // tiled path available (buffers allocated)
+  int tiled_choice = -1;       // -1 undecided (probe the first large call), 0 direct, 1 tiled
   bool acc_fresh = true;       // records untouched since create / reset (apart from direct RED, see StageDesc::dirty)
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
@@ -240,7 +241,7 @@ bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
 
 int clear_status(gritas_b200_handle h) {
   Status st[NWK + 1];
-  for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.ticket = 0; q.pad = 0; }
+  for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.near_pairs = 0; q.pairs = 0; }
   CU(cudaMemcpyAsync(h->d_status, st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
   CU(cudaStreamSynchronize(h->compute));
   return 0;
@@ -295,19 +296,21 @@ int grid_for(size_t work, int threads, int per_sm) {
 inline int filter_mode(const FilterDesc &f) { return !f.ods ? 0 : ((f.use_time || f.use_lon) ? 2 : 1); }
 
 template <int NR, int FMODE>
-void launch_fast_m(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
-  if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
+void launch_fast_m(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem, bool probe) {
+  if (probe)
+    k_accum_fast<NR, true, FMODE, true><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
+  else if (h->flags & GRITAS_B200_FLAG_NO_AGGREGATE)
     k_accum_fast<NR, false, FMODE><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
   else
     k_accum_fast<NR, true, FMODE><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq);
 }
 
 template <int NR>
-void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem) {
+void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, int nblk, size_t smem, bool probe) {
   switch (filter_mode(f)) {
-    case 0: launch_fast_m<NR, 0>(h, c, f, nblk, smem); break;
-    case 1: launch_fast_m<NR, 1>(h, c, f, nblk, smem); break;
-    default: launch_fast_m<NR, 2>(h, c, f, nblk, smem); break;
+    case 0: launch_fast_m<NR, 0>(h, c, f, nblk, smem, probe); break;
+    case 1: launch_fast_m<NR, 1>(h, c, f, nblk, smem, probe); break;
+    default: launch_fast_m<NR, 2>(h, c, f, nblk, smem, probe); break;
   }
 }
 
@@ -389,7 +392,11 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
               aligned16(c.flag) && aligned16(c.time) && aligned16(c.flag_out);
   for (int ir = 0; ir < h->g.nr; ++ir) c.aligned = c.aligned && aligned16(c.d[ir]);
 
-  const bool tiled = (h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging;
+  // Fast mode picks between the tiled and the direct accumulate by looking at the data: the first call with at
+  // least 64 Ki observations runs the direct kernel with a locality probe (both paths add into the same records).
+  bool probe = false;
+  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice < 0) probe = n >= 65536;
+  const bool tiled = (h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice == 1;
   const int w = h->next_wk;
   cudaStream_t run = tiled ? h->wk[w] : h->compute;
   if (tiled) {
@@ -401,7 +408,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     CU(cudaStreamWaitEvent(run, s.copied, 0));
   }
   const size_t smem = levtab_smem_bytes(h->g);
-  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging) {
+  if (tiled) {
     // tiled path: partition this call's observations into the per-tile lists (slices bound the scratch)
     const int SLICE = (int)h->sg.nbatch_cap * P1_BATCH;
     for (int s0 = 0; s0 < n; s0 += SLICE) {
@@ -438,11 +445,17 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
     const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
     switch (h->g.nr) {
-      case 1: launch_fast<1>(h, c, f, nblk, smem); break;
-      case 2: launch_fast<2>(h, c, f, nblk, smem); break;
-      default: launch_fast<3>(h, c, f, nblk, smem); break;
+      case 1: launch_fast<1>(h, c, f, nblk, smem, probe); break;
+      case 2: launch_fast<2>(h, c, f, nblk, smem, probe); break;
+      default: launch_fast<3>(h, c, f, nblk, smem, probe); break;
     }
     h->launches += 1;
+    if (probe) {
+      CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status), cudaMemcpyDeviceToHost, h->compute));
+      CU(cudaStreamSynchronize(h->compute));
+      const unsigned pairs = h->h_status[0].pairs, nearp = h->h_status[0].near_pairs;
+      h->tiled_choice = (pairs > 0 && (double)nearp < 0.5 * (double)pairs) ? 1 : 0;
+    }
   } else {
     h->acc_fresh = false;
     // K1 keys -> stable LSD radix sort of (key, obs index) -> in-order segment sums
@@ -608,7 +621,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   CUC(cudaMemsetAsync(g.acc, 0, acc_bytes, h->compute));  // gritas.f:352-363
   g.table = h->d_table; g.p1 = h->d_p1; g.p2 = h->d_p2;
   Status st[NWK + 1];
-  for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.ticket = 0; q.pad = 0; }
+  for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.near_pairs = 0; q.pairs = 0; }
   CUC(cudaMemcpyAsync(h->d_status, st, sizeof(st), cudaMemcpyHostToDevice, h->compute));
   CUC(cudaStreamSynchronize(h->compute));
   CUC(cudaEventCreateWithFlags(&h->main_ev, cudaEventDisableTiming));
@@ -714,6 +727,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
           q.nbuckets = h->sg.nbuckets; q.bucket_shift = h->sg.bucket_shift;
         }
         h->staging = true;
+        if (h->flags & GRITAS_B200_FLAG_FORCE_TILED) h->tiled_choice = 1;
+        if (e_on && atoi(e_on) == 1) h->tiled_choice = 1;
       }
     }
   }
@@ -1256,7 +1271,7 @@ int gritas_b200_set_stream(gritas_b200_handle h, void *stream) {
   return 0;
 }
 
-int gritas_b200_tiled(gritas_b200_handle h) { return (h && h->staging) ? 1 : 0; }
+int gritas_b200_tiled(gritas_b200_handle h) { return (h && h->staging) ? h->tiled_choice : 0; }
 uint64_t gritas_b200_launch_count(gritas_b200_handle h) { return h ? h->launches : 0; }
 uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h) { return h ? h->h2d : 0; }
 uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h) { return h ? h->d2h : 0; }

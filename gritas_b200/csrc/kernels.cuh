@@ -29,8 +29,8 @@ constexpr int OBS_PER_THREAD = 4;
 struct alignas(16) Status {
   unsigned long long first_bad;  // (call_seq << 32) | obs index of the first level miss, or BAD_NONE
   double bad_lev;
-  unsigned ticket;
-  unsigned pad;
+  unsigned near_pairs;  // locality probe of the direct kernel: consecutive accepted observations whose records
+  unsigned pairs;       // lie within 64 of each other / all consecutive accepted pairs
 };
 
 struct GridDesc {
@@ -568,7 +568,7 @@ __device__ __forceinline__ LevTab load_p2(const GridDesc &g, double *s_p2) {
 // K1+K2a fused: stream the columns, classify, accumulate with fp64 RED into the record grid.
 // AGG: lanes of a warp that hit the same box (__match_any_sync) are summed in registers first and
 // only the lowest lane issues the atomics.
-template <int NR, bool AGG, int FMODE>
+template <int NR, bool AGG, int FMODE, bool PROBE = false>
 __global__ void __launch_bounds__(ACC_THREADS)
 k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq) {
   extern __shared__ double s_p2[];
@@ -584,6 +584,21 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
     if (v < nvec) {
       load_obs4<NR>(c, f, base, o);
       classify4<NR, FMODE>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
+    }
+    if (PROBE) {
+      // How local is this data?  Soundings / radiance footprints put consecutive observations into neighbouring
+      // records (the direct RED path coalesces); scattered data does not (the tiled path wins).
+      unsigned nearc = 0, pairc = 0;
+#pragma unroll
+      for (int j = 1; j < 4; ++j) {
+        const bool both = k4[j] != KEY_NONE && k4[j - 1] != KEY_NONE;
+        const unsigned dist = k4[j] > k4[j - 1] ? k4[j] - k4[j - 1] : k4[j - 1] - k4[j];
+        pairc += both ? 1u : 0u;
+        nearc += (both && dist < 64u) ? 1u : 0u;
+      }
+      nearc = __reduce_add_sync(0xffffffffu, nearc);
+      pairc = __reduce_add_sync(0xffffffffu, pairc);
+      if (lane == 0 && pairc) { atomicAdd(&st->near_pairs, nearc); atomicAdd(&st->pairs, pairc); }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

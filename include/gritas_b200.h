@@ -37,6 +37,8 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
 #define GRITAS_B200_FLAG_NO_AGGREGATE 0x200 /* fast mode: skip the __match_any_sync warp aggregation */
 #define GRITAS_B200_FLAG_NO_STAGING 0x800   /* fast mode: never use the tiled (staged) accumulate; every
                                             observation goes to the HBM records with fp64 RED */
+#define GRITAS_B200_FLAG_FORCE_TILED 0x1000 /* fast mode: use the tiled accumulate from the first call on instead of
+                                            deciding from the locality of the first large call */
 #define GRITAS_B200_FLAG_HOLD_INPUTS 0x400  /* with ASYNC: the caller keeps pinned input arrays valid until the
                                             next sync/norm, so accum does not even wait for the H2D copies */
 
@@ -183,7 +185,7 @@ void gritas_b200_host_free(void *p);
 const char *gritas_b200_last_error(gritas_b200_handle h);
 void *gritas_b200_stream(gritas_b200_handle h);              /* cudaStream_t of the compute stream */
 int gritas_b200_set_stream(gritas_b200_handle h, void *stream); /* run on a caller-owned stream */
-int gritas_b200_tiled(gritas_b200_handle h);                 /* 1: fast mode uses the tiled accumulate */
+int gritas_b200_tiled(gritas_b200_handle h);                 /* fast mode: 1 tiled accumulate, 0 direct, -1 undecided */
 uint64_t gritas_b200_launch_count(gritas_b200_handle h);     /* kernels launched so far */
 uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h);        /* bytes copied host->device so far */
 uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h);        /* bytes copied device->host so far */

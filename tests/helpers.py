@@ -9,7 +9,7 @@ from gritas_b200.m_gritas_grids import Grids
 from oracle import oracle
 
 # fast (tiled/staged accumulate), fast with the direct fp64-RED accumulate, deterministic
-MODES = [cabi.MODE_FAST, cabi.MODE_FAST | cabi.FLAG_NO_STAGING, cabi.MODE_DETERMINISTIC]
+MODES = [cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, cabi.MODE_FAST | cabi.FLAG_NO_STAGING, cabi.MODE_DETERMINISTIC]
 
 
 def is_det(mode):

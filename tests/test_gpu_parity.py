@@ -420,7 +420,7 @@ def test_staging_overflow_falls_back_to_direct_accumulate(name, monkeypatch):
     table, l2d, l3d, *_ = H.setup(cfg)
     for nr in (1, 2):
         ref, rf = H.oracle_run(cfg, files, nr)
-        out, gf = H.gpu_run(cfg, files, nr, cabi.MODE_FAST)
+        out, gf = H.gpu_run(cfg, files, nr, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED)
         assert all(np.array_equal(a, b) for a, b in zip(gf, rf))
         H.compare(out, ref, l2d, l3d, nr, exact=False, tol=TOL_FAST)
 
@@ -431,5 +431,28 @@ def test_staged_flush_between_files(monkeypatch):
     cfg, files = small("cfg2", 0.1, 4)
     table, l2d, l3d, *_ = H.setup(cfg)
     ref, _ = H.oracle_run(cfg, files, 2)
-    out, _ = H.gpu_run(cfg, files, 2, cabi.MODE_FAST, want_flags=False)
+    out, _ = H.gpu_run(cfg, files, 2, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, want_flags=False)
     H.compare(out, ref, l2d, l3d, 2, exact=False, tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("name,expect", [("cfg2", 1), ("cfg3_amsua", 0)])
+def test_fast_mode_picks_the_path_from_the_data(name, expect):
+    """Plain fast mode: the first call with >= 64 Ki observations runs the direct kernel with a locality probe;
+    scattered conventional data then switches to the tiled accumulate, radiance footprints (consecutive channels
+    -> consecutive records) stay on the direct path.  Results must not depend on the choice."""
+    cfg = synth.get_config(name, 0.1 if name == "cfg2" else 0.006)
+    cfg.im, cfg.jm = 72, 46
+    files = [synth.make_file(cfg, i) for i in range(3)]
+    assert len(files[0]["lat"]) >= 65536
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    nr = cfg.nr
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_FAST)
+    for c in files:
+        G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, nr), len(c["lat"]), nr, table, p1, p2,
+                       None, l2d, l3d=l3d)
+    assert cabi.load().gritas_b200_tiled(G.handle) == expect
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.close()
+    ref, _ = H.oracle_run(cfg, files, nr)
+    H.compare(out, ref, l2d, l3d, nr, exact=False, tol=TOL_FAST)
