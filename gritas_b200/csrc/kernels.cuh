@@ -999,6 +999,7 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
     const unsigned hi = min(sg.nbatch, lo + per);
     const size_t row = (size_t)b * sg.nbatch_cap;
     while (lo < hi) {
+      GB_STAMP(0);
       // ---- how many runs fit in this round: inclusive scan of the run counts, cut at P2_BATCH ----
       const unsigned nrun_max = min((unsigned)P2_MAXRUNS, hi - lo);
       const unsigned mine = ((unsigned)tid < nrun_max) ? sg.cnt1[row + lo + tid] : 0u;
@@ -1028,20 +1029,21 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
       const unsigned nrun = (unsigned)__syncthreads_count(fits);  // fits is a prefix property: count = cut
       const unsigned nslot = nrun << sg.c1_shift;
       const size_t src = (row + lo) << sg.c1_shift;
+      GB_STAMP(1);
       // ---- pass 1: count per tile.  One warp per run (c1 <= 32: lane = slot), two runs in flight ----
       if (sg.c1 <= 32u) {
         const unsigned rpw = 32u / sg.c1;                   // runs per warp instruction
         const unsigned sub = (unsigned)lane >> sg.c1_shift, i = (unsigned)lane & (sg.c1 - 1u);
-        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 2u) {
-          unsigned key[2];
+        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 8u) {
+          unsigned key[8];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < 8; ++u) {                     // eight runs in flight per warp
             const unsigned r = r0 + (unsigned)u * (P2_THREADS / 32) * rpw + sub;
             const bool live = r < nrun && i < s_rcnt[r];
             key[u] = live ? __ldcg(sg.key1 + src + ((size_t)r << sg.c1_shift) + i) : KEY_NONE;
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < 8; ++u)
             if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
         }
       } else {
@@ -1059,7 +1061,9 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
         }
       }
       __syncthreads();
+      GB_STAMP(2);
       part_layout<NR, true>(v, nt, 0xFFFFFFFFu, 0u, sg.fill, sg.skey, sg.cap, b << tsh);
+      GB_STAMP(3);
       // ---- pass 2: reload, ticket, scatter ----
       auto place = [&](unsigned key, const double (&d)[NR]) {
         const unsigned t = (key >> sg.tile_shift) & tmask;
@@ -1076,11 +1080,11 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
       if (sg.c1 <= 32u) {
         const unsigned rpw = 32u / sg.c1;
         const unsigned sub = (unsigned)lane >> sg.c1_shift, i = (unsigned)lane & (sg.c1 - 1u);
-        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 2u) {
-          unsigned key[2];
-          double d[2][NR];
+        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 4u) {
+          unsigned key[4];
+          double d[4][NR];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < 4; ++u) {                     // four runs in flight per warp
             const unsigned r = r0 + (unsigned)u * (P2_THREADS / 32) * rpw + sub;
             const bool live = r < nrun && i < s_rcnt[r];
             const size_t at = src + ((size_t)r << sg.c1_shift) + i;
@@ -1089,7 +1093,7 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
             for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + at) : 0.0;
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < 4; ++u)
             if (key[u] != KEY_NONE) place(key[u], d[u]);
         }
       } else {
@@ -1110,8 +1114,10 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
         }
       }
       __syncthreads();
+      GB_STAMP(4);
       part_writeout<NR>(v, sg.cap, b << tsh, sg.skey, sg.sd);
       __syncthreads();
+      GB_STAMP(5);
       lo += nrun;
     }
   }
@@ -1250,6 +1256,20 @@ struct OutPlanes {
   int xcov_planes;                           // how many ir slabs of xcov exist (1 for the raw getters)
 };
 
+// Correctly rounded x / d when several numerators share one divisor (the count m, or m-1): with r = RN(1/d),
+// q = RN(x r) is a faithful quotient and one residual correction with two FMAs, q' = RN(q + RN(x - q d) r),
+// is the correctly rounded quotient (Markstein's theorem; x - q d is exact in an FMA).  Non-finite or
+// vanishing intermediate results fall back to the IEEE division.  Bit-identical to __ddiv_rn.
+__device__ __forceinline__ double div_shared(double x, double d, double r) {
+  const double q = __dmul_rn(x, r);
+  const double rem = __fma_rn(-q, d, x);
+  const double q2 = __fma_rn(rem, r, q);
+  // guard: huge / tiny magnitudes (overflow, underflow into subnormals) are not covered by the theorem
+  const double aq = fabs(q);
+  if (!(aq < 1.0e300) || (aq < 1.0e-290 && x != 0.0)) return __ddiv_rn(x, d);
+  return q2;
+}
+
 // m_gritas_grids.f:566-605 (2-D) and 612-654 (3-D) for one box.  raw: pass the sums through.
 template <int NR>
 __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, bool is3d, int nrmlz, int ntresh,
@@ -1269,16 +1289,22 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
   const double dm = (double)m, dm1 = (double)(m - 1);
   const bool some = (n > 0.0) && (n >= (double)ntresh);
   const bool many = (n > 1.0) && (n >= (double)ntresh);
+  // m >= 1 whenever `some` holds with nrmlz; m = 1, m-1 = 0 under -nonorm: the reciprocal path needs a finite,
+  // non-zero divisor, anything else takes the plain division (inf / NaN results exactly as the reference)
+  const bool fast_m = some && dm >= 1.0, fast_m1 = many && dm1 >= 1.0;
+  const double rm = fast_m ? __drcp_rn(dm) : 0.0, rm1 = fast_m1 ? __drcp_rn(dm1) : 0.0;
+  auto div_m = [&](double x) { return fast_m ? div_shared(x, dm, rm) : __ddiv_rn(x, dm); };
+  auto div_m1 = [&](double x) { return fast_m1 ? div_shared(x, dm1, rm1) : __ddiv_rn(x, dm1); };
   double tmp[NR], xtmp = 0.0;
   if (some) {
 #pragma unroll
     for (int ir = 0; ir < NR; ++ir) {
-      bias[ir] = __ddiv_rn(rec[1 + 2 * ir], dm);
-      const double t = __ddiv_rn(rec[2 + 2 * ir], dm);
+      bias[ir] = div_m(rec[1 + 2 * ir]);
+      const double t = div_m(rec[2 + 2 * ir]);
       rtms[ir] = __dsqrt_rn(t);
       tmp[ir] = fabs(__dsub_rn(t, __dmul_rn(bias[ir], bias[ir])));
     }
-    xtmp = __ddiv_rn(xraw, dm);
+    xtmp = div_m(xraw);
     xcov[0] = xtmp;
     xtmp = __dsub_rn(xtmp, __dmul_rn(bias[0], bias[nx - 1]));
   } else {
@@ -1288,8 +1314,8 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
   }
   if (many) {
 #pragma unroll
-    for (int ir = 0; ir < NR; ++ir) stdv[ir] = __dsqrt_rn(__ddiv_rn(__dmul_rn(dm, tmp[ir]), dm1));
-    xcov[nx - 1] = __ddiv_rn(__dmul_rn(dm, xtmp), dm1);
+    for (int ir = 0; ir < NR; ++ir) stdv[ir] = __dsqrt_rn(div_m1(__dmul_rn(dm, tmp[ir])));
+    xcov[nx - 1] = div_m1(__dmul_rn(dm, xtmp));
   } else if (is3d && n == 1.0) {  // m_gritas_grids.f:642-644 (the 2-D branch has no such case)
 #pragma unroll
     for (int ir = 0; ir < NR; ++ir) stdv[ir] = __dsqrt_rn(tmp[ir]);

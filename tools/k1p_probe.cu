@@ -50,7 +50,7 @@ int main(int argc, char **argv) {
   c.n = n; c.aligned = 1;
   FilterDesc f = {}; f.ods = 1; f.ioptn = 1; f.x_passive = 7; f.x_pre_bad = 1;
   Status *st; CK(cudaMalloc(&st, sizeof(Status)));
-  Status hs; hs.first_bad = BAD_NONE; hs.bad_lev = 0; hs.ticket = 0; hs.pad = 0; CK(cudaMemcpy(st, &hs, sizeof(hs), cudaMemcpyHostToDevice));
+  Status hs; hs.first_bad = BAD_NONE; hs.bad_lev = 0; hs.near_pairs = 0; hs.pairs = 0; CK(cudaMemcpy(st, &hs, sizeof(hs), cudaMemcpyHostToDevice));
   StageDesc sg = {};
   sg.tile_shift = 11; const size_t T = 2048; const size_t ntiles = (nrec + T - 1) / T;
   size_t tpb = 1; while ((ntiles + tpb - 1) / tpb > 112) tpb <<= 1; int tsh = 0; while (((size_t)1 << tsh) < tpb) ++tsh;
@@ -100,5 +100,19 @@ int main(int argc, char **argv) {
   std::vector<double> life(nbatch); for (int b = 0; b < nbatch; ++b) life[b] = (hb[b * 8 + 6] - hb[b * 8]) * 1e-3;
   std::sort(life.begin(), life.end());
   printf("CTA lifetime us: min %.2f p50 %.2f p90 %.2f max %.2f\n", life[0], life[nbatch / 2], life[nbatch * 9 / 10], life[nbatch - 1]);
+  // ---- K1q phases (stamps of the last round of each CTA) ----
+  CK(cudaMemset(buf, 0, (size_t)nbatch * 64));
+  CK(cudaMemsetAsync(sg.fill, 0, sg.nbuckets * tpb * 4));
+  k_part_obs<2, 1><<<nbatch, P1_THREADS, p1_smem>>>(g, c, f, st, 1u, sg);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(buf, 0, (size_t)nbatch * 64));
+  k_part_tiles<2, 4096, 512><<<g2, 512, p2_smem>>>(g, sg, parts);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(hb.data(), buf, (size_t)g2 * 64, cudaMemcpyDeviceToHost));
+  double q[6] = {0}; int cnt = 0;
+  for (int b = 0; b < g2; ++b) { if (!hb[b * 8 + 5]) continue; ++cnt; for (int k = 1; k < 6; ++k) q[k] += (double)(hb[b * 8 + k] - hb[b * 8 + k - 1]); }
+  const char *qn[6] = {"", "scan run counts", "pass1 count", "layout+tickets", "pass2 scatter", "writeout"};
+  printf("K1q: %d CTAs of %d, parts %d\n", cnt, g2, parts);
+  for (int k = 1; k < 6; ++k) printf("  %-20s %8.2f us avg (last round of a CTA)\n", qn[k], q[k] / std::max(cnt, 1) * 1e-3);
   return 0;
 }
