@@ -37,12 +37,21 @@ IOPT_OMF_OMA = 101
 # every symbol include/gritas_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "gritas_b200_create", "gritas_b200_destroy", "gritas_b200_pint", "gritas_b200_kxkt", "gritas_b200_accum",
-    "gritas_b200_accum_ods", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
+    "gritas_b200_accum_ods", "gritas_b200_accum_odsx", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
     "gritas_b200_get_raw", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
     "gritas_b200_allreduce", "gritas_b200_norm_reduce", "gritas_b200_norm_reduce_device", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
     "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_tiled", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
     "gritas_b200_d2h_bytes", "gritas_b200_version",
 ]
+
+OPT_TCH = 1
+OPT_SELF = 2
+
+
+class OdsCols(C.Structure):
+    """struct gritas_b200_ods of include/gritas_b200.h"""
+    _fields_ = [(k, C.c_void_p) for k in ("lat", "lon", "lev", "obs", "omf", "oma", "xvec", "xm", "time", "kt", "kx", "qcexcl")]
+
 
 _lib = None
 _P = C.c_void_p
@@ -68,6 +77,7 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_kxkt.argtypes = [_I] * 5 + [_P, _P, _P, _I, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]
     L.gritas_b200_accum.argtypes = [_P, _I] + [_P] * 7 + [C.POINTER(_D)]
     L.gritas_b200_accum_ods.argtypes = [_P, _I] + [_P] * 11 + [_I] * 5 + [_D, _D, _I, _I, _P, C.POINTER(_D)]
+    L.gritas_b200_accum_odsx.argtypes = [_P, _I, _P] + [_I] * 6 + [_D, _D, _I, _I, _P, C.POINTER(_D)]
     L.gritas_b200_sync.argtypes = [_P, C.POINTER(_D)]
     L.gritas_b200_reset.argtypes = [_P]
     L.gritas_b200_flush.argtypes = [_P]

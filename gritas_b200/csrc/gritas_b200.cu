@@ -29,8 +29,8 @@ namespace {
 constexpr int NSLOT = 2;   // staging slots (double buffering)
 constexpr int NWK = 8;     // max worker streams of the tiled path (GRITAS_B200_WORKERS, default 3): partition
                            // kernels of consecutive calls overlap
-constexpr int NCOL = 12;   // staged columns per slot
-enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME };
+constexpr int NCOL = 18;   // staged columns per slot
+enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME, C_B0, C_B1, C_B2, C_C0, C_C1, C_C2 };
 
 // --- NCCL through dlopen: the library has no link-time dependency on it ------------------------
 typedef struct ncclComm *ncclComm_t;
@@ -781,10 +781,17 @@ void gritas_b200_destroy(gritas_b200_handle h) {
   delete h;
 }
 
+// Residual columns as expressions of ODS columns (gritas.f:588-704): del(:,ir) = sa*a[ir] [+/- b[ir]] [+ c[ir]].
+struct ResidualSpec {
+  const double *b[3] = {nullptr, nullptr, nullptr}, *c[3] = {nullptr, nullptr, nullptr};
+  signed char sa[3] = {1, 1, 1}, sb[3] = {0, 0, 0};
+  int expr = 0, post = 0;
+};
+
 static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
                         const double *const dcol[3], const double *obs, const double *xvec, const double *omf_for_scale,
                         const int32_t *kx, const int32_t *kt, const int32_t *flag_in, const int32_t *time,
-                        const FilterDesc &f, int32_t *flag_out, double *bad_lev) {
+                        FilterDesc f, int32_t *flag_out, double *bad_lev, const ResidualSpec *rs = nullptr) {
   int rc = check_handle(h);
   if (rc) return rc;
   if (nobs < 0) return fail(h, GRITAS_B200_ERR_ARG, "nobs < 0");
@@ -801,22 +808,39 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   c.n = nobs;
   bool any = false;
   const size_t nb8 = sizeof(double) * (size_t)nobs, nb4 = sizeof(int) * (size_t)nobs;
-  if ((rc = stage(h, s, C_LAT, lat, nb8, (const void **)&c.lat, &any))) return rc;
-  if ((rc = stage(h, s, C_LON, lon, nb8, (const void **)&c.lon, &any))) return rc;
-  if ((rc = stage(h, s, C_LEV, lev, nb8, (const void **)&c.lev, &any))) return rc;
+  // a source column may appear in several roles: stage it once per call
+  const void *seen_src[NCOL] = {}, *seen_dev[NCOL] = {};
+  int nseen = 0;
+  auto stage1 = [&](int col, const void *src, size_t bytes, const void **out) -> int {
+    for (int q = 0; q < nseen; ++q)
+      if (seen_src[q] == src) { *out = seen_dev[q]; return 0; }
+    const int r = stage(h, s, col, src, bytes, out, &any);
+    if (!r && nseen < NCOL) { seen_src[nseen] = src; seen_dev[nseen] = *out; ++nseen; }
+    return r;
+  };
+  if ((rc = stage1(C_LAT, lat, nb8, (const void **)&c.lat))) return rc;
+  if ((rc = stage1(C_LON, lon, nb8, (const void **)&c.lon))) return rc;
+  if ((rc = stage1(C_LEV, lev, nb8, (const void **)&c.lev))) return rc;
   for (int ir = 0; ir < h->g.nr; ++ir)
-    if ((rc = stage(h, s, C_D0 + ir, dcol[ir], nb8, (const void **)&c.d[ir], &any))) return rc;
-  if (f.scale_res == 1 && (rc = stage(h, s, C_XVEC, xvec, nb8, (const void **)&c.xvec, &any))) return rc;
-  if (f.scale_res >= 2 && (rc = stage(h, s, C_OBS, obs, nb8, (const void **)&c.obs, &any))) return rc;
-  if (f.scale_res == 3) {
-    // obs - omf needs omf even when it is not the accumulated column
-    if (omf_for_scale == dcol[0]) c.omf = c.d[0];
-    else if ((rc = stage(h, s, C_D2, omf_for_scale, nb8, (const void **)&c.omf, &any))) return rc;
+    if ((rc = stage1(C_D0 + ir, dcol[ir], nb8, (const void **)&c.d[ir]))) return rc;
+  for (int ir = 0; ir < 3; ++ir) { c.sa[ir] = 1; c.sb[ir] = 0; }
+  if (rs && rs->expr) {
+    f.expr = 1;
+    f.post = rs->post;
+    for (int ir = 0; ir < h->g.nr; ++ir) {
+      c.sa[ir] = rs->sa[ir];
+      c.sb[ir] = rs->sb[ir];
+      if (rs->b[ir] && (rc = stage1(C_B0 + ir, rs->b[ir], nb8, (const void **)&c.db[ir]))) return rc;
+      if (rs->c[ir] && (rc = stage1(C_C0 + ir, rs->c[ir], nb8, (const void **)&c.dc[ir]))) return rc;
+    }
   }
-  if ((rc = stage(h, s, C_KX, kx, nb4, (const void **)&c.kx, &any))) return rc;
-  if ((rc = stage(h, s, C_KT, kt, nb4, (const void **)&c.kt, &any))) return rc;
-  if (flag_in && (rc = stage(h, s, C_FLAG, flag_in, nb4, (const void **)&c.flag, &any))) return rc;
-  if (f.use_time && (rc = stage(h, s, C_TIME, time, nb4, (const void **)&c.time, &any))) return rc;
+  if ((f.scale_res == 1 || f.post) && (rc = stage1(C_XVEC, xvec, nb8, (const void **)&c.xvec))) return rc;
+  if (f.scale_res >= 2 && (rc = stage1(C_OBS, obs, nb8, (const void **)&c.obs))) return rc;
+  if (f.scale_res == 3 && (rc = stage1(C_D2, omf_for_scale, nb8, (const void **)&c.omf))) return rc;   // obs - omf
+  if ((rc = stage1(C_KX, kx, nb4, (const void **)&c.kx))) return rc;
+  if ((rc = stage1(C_KT, kt, nb4, (const void **)&c.kt))) return rc;
+  if (flag_in && (rc = stage1(C_FLAG, flag_in, nb4, (const void **)&c.flag))) return rc;
+  if (f.use_time && (rc = stage1(C_TIME, time, nb4, (const void **)&c.time))) return rc;
   return run_accum(h, c, f, s, any, flag_out, bad_lev);
 }
 
@@ -862,6 +886,78 @@ int gritas_b200_accum_ods(gritas_b200_handle h, int nobs, const double *lat, con
   if (nobs > 0 && f.use_time && !time) return fail(h, GRITAS_B200_ERR_ARG, "time window needs the time column");
   return accum_common(h, nobs, lat, lon, lev, d, obs, xvec, omf, kx, kt, filtered ? qcexcl : nullptr, time, f,
                       ob_flag_out, bad_lev);
+}
+
+// Fused entry for every residual option of gritas.f:562-704 that needs one ODS structure only
+// (no -meanres second file): |iopt| 0..25, 28..33 and GRITAS_B200_IOPT_OMF_OMA.
+int gritas_b200_accum_odsx(gritas_b200_handle h, int nobs, const gritas_b200_ods *o, int iopt, int options, int scale_res,
+                           int ioptn, int t1, int t2, double lona, double lonb, int x_passive, int x_pre_bad,
+                           int32_t *ob_flag_out, double *bad_lev) {
+  if (!h || !o) return GRITAS_B200_ERR_ARG;
+  const int a = iopt < 0 ? -iopt : iopt;
+  const bool tch = (options & GRITAS_B200_OPT_TCH) != 0, self = (options & GRITAS_B200_OPT_SELF) != 0;
+  const double *A[3] = {nullptr, nullptr, nullptr};
+  ResidualSpec rs;
+  int nr = 1;
+  auto col = [&](int ir, const double *pa, int sa, const double *pb = nullptr, int sb = 0, const double *pc = nullptr) {
+    A[ir] = pa; rs.sa[ir] = (signed char)sa; rs.b[ir] = pb; rs.sb[ir] = (signed char)sb; rs.c[ir] = pc;
+    if (sa < 0 || pb || pc) rs.expr = 1;
+  };
+  const double *omf = o->omf, *oma = o->oma, *obs = o->obs, *xvec = o->xvec, *xm = o->xm;
+  switch (a) {
+    case 0: case 1: col(0, omf, 1); break;                                              // gritas.f:562-574
+    case 2: case 3: col(0, oma, 1); break;                                              // :575-587
+    case 4: case 5: col(0, obs, 1); break;                                              // :588-589
+    case 6: case 7: col(0, xvec, 1); break;                                             // :590-591 prescribed sigo
+    case 8: case 9: col(0, xm, 1); break;                                               // :592-593 observation bias
+    case 10: case 11:                                                                   // :594-611 <AmF,OmF>
+      if (tch) { col(0, oma, 1, omf, -1); col(1, omf, -1); col(2, oma, -1); nr = 3; }
+      else { col(0, omf, 1, oma, -1); col(1, omf, 1); nr = 2; }
+      break;
+    case 12: case 13:                                                                   // :612-624 <AmF,OmA>
+      if (tch) { col(0, oma, -1); col(1, omf, 1, oma, -1); col(2, omf, 1); nr = 3; }
+      else { col(0, omf, 1, oma, -1); col(1, oma, 1); nr = 2; }
+      break;
+    case 14: case 15:                                                                   // :625-640 <OmA,OmF>
+      if (tch && self) { col(0, obs, 1); col(1, obs, 1, omf, -1); col(2, obs, 1, oma, -1); nr = 3; }
+      else if (tch) { col(0, omf, 1); col(1, oma, 1); col(2, oma, 1, omf, -1); nr = 3; }
+      else { col(0, oma, 1); col(1, omf, 1); nr = 2; }
+      break;
+    case 16: case 17: col(0, omf, 1); col(1, xvec, 1); nr = 2; if (a == 17) { rs.post = 2; rs.expr = 1; } break;   // :641-644, :738
+    case 18: case 19: col(0, oma, 1); col(1, xvec, 1); nr = 2; if (a == 19) { rs.post = 2; rs.expr = 1; } break;   // :645-648, :738
+    case 20: case 21: col(0, obs, 1, xm, 1); break;                                     // :649-650 original observation
+    case 22: case 23: col(0, xvec, 1); break;                                           // :651-652 observation impacts
+    case 24: case 25: col(0, obs, 1, omf, -1); break;                                   // :653-664 (no -meanres)
+    case 28: case 29: col(0, obs, 1, omf, -1, xm); break;                               // :678-679 h(xf)
+    case 30: case 31: col(0, obs, 1, oma, -1); break;                                   // :680-691 (no -meanres)
+    case 32: case 33: col(0, omf, 1, oma, -1); col(1, oma, 1); nr = 2; rs.post = 1; rs.expr = 1; break;   // :692-701
+    case GRITAS_B200_IOPT_OMF_OMA: col(0, omf, 1); col(1, oma, 1); nr = 2; break;
+    default: return fail(h, GRITAS_B200_ERR_ARG, "iopt %d: not valid / needs -meanres (gritas.f:702-703)", iopt);
+  }
+  if (nr != h->g.nr) return fail(h, GRITAS_B200_ERR_ARG, "iopt %d needs nr=%d, handle has nr=%d", iopt, nr, h->g.nr);
+  if (scale_res < 0 || scale_res > 3) return fail(h, GRITAS_B200_ERR_ARG, "scale_res out of range");
+  if (a > 3) scale_res = 0;                                   // the reference scales only the omf / oma options
+  if (nobs > 0) {
+    for (int ir = 0; ir < nr; ++ir)
+      if (!A[ir] || (rs.sb[ir] && !rs.b[ir])) return fail(h, GRITAS_B200_ERR_ARG, "iopt %d: a column it needs is null", iopt);
+    if (!o->qcexcl) return fail(h, GRITAS_B200_ERR_ARG, "null qcexcl");
+    if ((scale_res == 1 || rs.post) && !xvec) return fail(h, GRITAS_B200_ERR_ARG, "xvec needed");
+    if (scale_res >= 2 && !obs) return fail(h, GRITAS_B200_ERR_ARG, "scale_res=2,3 needs obs");
+    if (scale_res == 3 && !omf) return fail(h, GRITAS_B200_ERR_ARG, "scale_res=3 needs omf");
+  }
+  FilterDesc f = {};
+  const bool filtered = (a & 1) != 0;                         // gritas.f:710: the filter runs for odd iopt only
+  f.ods = filtered ? 1 : 0;
+  f.ioptn = ioptn;
+  f.t1 = t1; f.t2 = t2;
+  f.use_time = (!filtered || t2 < t1) ? 0 : 1;
+  f.use_lon = (!filtered || (lona < -180.0 && lonb > 180.0)) ? 0 : 1;
+  f.lona = lona; f.lonb = lonb;
+  f.x_passive = x_passive; f.x_pre_bad = x_pre_bad;
+  f.scale_res = scale_res;
+  if (nobs > 0 && f.use_time && !o->time) return fail(h, GRITAS_B200_ERR_ARG, "time window needs the time column");
+  return accum_common(h, nobs, o->lat, o->lon, o->lev, A, obs, xvec, omf, o->kx, o->kt, filtered ? o->qcexcl : nullptr,
+                      o->time, f, ob_flag_out, bad_lev, &rs);
 }
 
 int gritas_b200_sync(gritas_b200_handle h, double *bad_lev) {

@@ -53,8 +53,11 @@ struct GridDesc {
 
 struct ObsCols {
   const double *lat, *lon, *lev;
-  const double *d[3];        // residual source columns (del(:,ir), or omf / oma)
-  const double *obs, *xvec, *omf;  // only for scale_res
+  const double *d[3];        // residual source columns (del(:,ir), or omf / oma / obs / xvec / xm)
+  const double *obs, *xvec, *omf;  // only for scale_res and the expression post-operations
+  // general residual expressions of gritas.f:588-704 (FilterDesc::expr): del(:,ir) = sa*d[ir] [+/- db[ir]] [+ dc[ir]]
+  const double *db[3], *dc[3];
+  signed char sa[3], sb[3];
   const int *kx, *kt;
   const int *flag;           // ob_flag (plain entry) or qcexcl (ODS entry); may be null (all 0)
   const int *time;           // may be null
@@ -69,6 +72,8 @@ struct FilterDesc {
   double lona, lonb;
   int x_passive, x_pre_bad;
   int scale_res;  // gritas.f:564-572
+  int expr;       // residual columns are expressions (ObsCols::db/dc/sa/sb) instead of plain columns
+  int post;       // 1: every column / xvec where xvec > 0 else AMISS (gritas.f:692-701); 2: column 1 / xvec (:738)
 };
 
 // Staging area of the tiled fast path.  The record grid is cut into tiles of
@@ -237,6 +242,25 @@ __device__ __forceinline__ double scale_residual(const FilterDesc &f, const ObsC
   if (f.scale_res == 2) return __ddiv_rn(d, __ldg(c.obs + n));
   if (f.scale_res == 3) return __ddiv_rn(d, __dsub_rn(__ldg(c.obs + n), __ldg(c.omf + n)));
   return d;
+}
+
+// Residual column ir of observation n from its primary source value d: the expressions of gritas.f:588-704
+// evaluated left to right exactly as written there, then the optional scaling.
+__device__ __forceinline__ double residual_value(const FilterDesc &f, const ObsCols &c, int ir, double d, int n) {
+  if (f.expr) {
+    if (c.sa[ir] < 0) d = -d;
+    if (c.db[ir]) {
+      const double b = __ldg(c.db[ir] + n);
+      d = c.sb[ir] > 0 ? __dadd_rn(d, b) : __dsub_rn(d, b);
+    }
+    if (c.dc[ir]) d = __dadd_rn(d, __ldg(c.dc[ir] + n));
+    if (f.post == 1) {
+      const double x = __ldg(c.xvec + n);
+      d = x > 0.0 ? __ddiv_rn(d, x) : AMISS;
+    }
+    if (f.post == 2 && ir == 0) d = __ddiv_rn(d, __ldg(c.xvec + n));
+  }
+  return f.scale_res ? scale_residual(f, c, d, n) : d;
 }
 
 // Level miss (m_gritas_grids.f:458-459): keep the EARLIEST (call, observation) together with its level.
@@ -607,7 +631,7 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
 #pragma unroll
       for (int ir = 0; ir < NR; ++ir) {
         double d = o.d[ir][j];
-        if (f.scale_res && key != KEY_NONE) d = scale_residual(f, c, d, base + j);
+        if ((f.scale_res | f.expr) && key != KEY_NONE) d = residual_value(f, c, ir, d, base + j);
         sx[ir] = d;
         sq[ir] = __dmul_rn(d, d);
       }
@@ -695,7 +719,7 @@ k_segment_sum(const GridDesc g, const ObsCols c, const FilterDesc f, const unsig
     double d[NR];
 #pragma unroll
     for (int ir = 0; ir < NR; ++ir) {
-      d[ir] = scale_residual(f, c, __ldg(c.d[ir] + i), i);
+      d[ir] = residual_value(f, c, ir, __ldg(c.d[ir] + i), i);
       sx[ir] = __dadd_rn(sx[ir], d[ir]);
       sq[ir] = __dadd_rn(sq[ir], __dmul_rn(d[ir], d[ir]));
     }
@@ -936,7 +960,7 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
         if (key == KEY_NONE) continue;
         double d[NR];
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) d[ir] = f.scale_res ? scale_residual(f, c, dd[ir][j], base + j) : dd[ir][j];
+        for (int ir = 0; ir < NR; ++ir) d[ir] = (f.scale_res | f.expr) ? residual_value(f, c, ir, dd[ir][j], base + j) : dd[ir][j];
         const unsigned b = key >> sg.bucket_shift;
         const unsigned rank = atomicAdd(s_cnt + b, 1u);
         if (rank >= sg.c1) {

@@ -172,6 +172,26 @@ class Grids:
                                      C.byref(bad))
         self._check(rc, bad)
 
+    NR_OF_IOPT = {10: 2, 11: 2, 12: 2, 13: 2, 14: 2, 15: 2, 16: 2, 17: 2, 18: 2, 19: 2, 32: 2, 33: 2, cabi.IOPT_OMF_OMA: 2}
+
+    def accum_odsx(self, ods, iopt, options=0, scale_res=0, ioptn=None, t1=0, t2=-1, lona=-999.0, lonb=999.0, x_passive=7,
+                   x_pre_bad=1, kxkt_table=None, p1=None, p2=None, l2d=0, l3d=0, ob_flag_out=None):
+        """All single-ODS residual options of gritas.f:562-704 fused with the QC filter and GrITAS_Accum_."""
+        a = abs(iopt)
+        nr = 3 if (options & cabi.OPT_TCH and 10 <= a <= 15) else self.NR_OF_IOPT.get(a, 1)
+        if self._h is None:
+            self._ensure(nr, kxkt_table, p1, p2, l2d, l3d)
+        cols = cabi.OdsCols()
+        dt = {"time": np.int32, "kt": np.int32, "kx": np.int32, "qcexcl": np.int32}
+        for k, _ in cabi.OdsCols._fields_:
+            v = ods.get(k)
+            setattr(cols, k, cabi.ptr(v, dt.get(k, np.float64)) if v is not None else None)
+        bad = C.c_double(0.0)
+        rc = cabi.load().gritas_b200_accum_odsx(self._h, int(ods["lat"].shape[0]), C.byref(cols), iopt, options, scale_res,
+                                                iopt if ioptn is None else ioptn, t1, t2, lona, lonb, x_passive, x_pre_bad,
+                                                cabi.ptr(ob_flag_out, np.int32), C.byref(bad))
+        self._check(rc, bad)
+
     def sync(self):
         bad = C.c_double(0.0)
         self._check(cabi.load().gritas_b200_sync(self._h, C.byref(bad)), bad)

@@ -118,6 +118,26 @@ int gritas_b200_accum_ods(gritas_b200_handle h, int nobs, const double *lat, con
                           int iopt, int scale_res, int ioptn, int t1, int t2, double lona, double lonb,
                           int x_passive, int x_pre_bad, int32_t *ob_flag_out, double *bad_lev);
 
+/*
+ * Fused entry for all residual options of gritas.f:562-704 that work on one ODS structure: |iopt| as in the
+ * reference (0/1 omf, 2/3 oma, 4/5 obs, 6/7 sigo, 8/9 obias, 10/11 hbh, 12/13 hah, 14/15 esigo, 16-19 job/joa,
+ * 20/21 obs+xm, 22/23 imp, 24/25 obs-omf, 28/29 obs-omf+xm, 30/31 obs-oma, 32/33 (omf-oma)/xvec, oma/xvec) or
+ * GRITAS_B200_IOPT_OMF_OMA.  The expressions are evaluated on the device exactly as written in the reference
+ * (left to right, fp64).  options: GRITAS_B200_OPT_TCH (-tch, three residual columns for 10..15),
+ * GRITAS_B200_OPT_SELF.  The -meanres variants (24..27, 30/31 with a second ODS) are not covered: build del on the
+ * host and call gritas_b200_accum.  Columns an option does not use may be NULL.  The handle's nr must match.
+ */
+typedef struct gritas_b200_ods {
+  const double *lat, *lon, *lev;
+  const double *obs, *omf, *oma, *xvec, *xm;
+  const int32_t *time, *kt, *kx, *qcexcl;
+} gritas_b200_ods;
+#define GRITAS_B200_OPT_TCH 1
+#define GRITAS_B200_OPT_SELF 2
+int gritas_b200_accum_odsx(gritas_b200_handle h, int nobs, const gritas_b200_ods *ods, int iopt, int options, int scale_res,
+                           int ioptn, int t1, int t2, double lona, double lonb, int x_passive, int x_pre_bad,
+                           int32_t *ob_flag_out, double *bad_lev);
+
 /* Wait for all queued work; returns a pending GRITAS_B200_ERR_LEVEL (and its level) if any. */
 int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
 

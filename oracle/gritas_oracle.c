@@ -199,6 +199,57 @@ int orc_select_del(int nobs, int iopt, int scale_res, const double *omf, const d
   return 0;
 }
 
+/* gritas.f:562-704, every residual option that works on one ODS structure (no -meanres second file):
+ * fills del (nobs, nr) column-major and returns nr (1..3), or 0 for an option this restatement does not
+ * cover (26/27, invalid).  Includes the division of gritas.f:738 (iopt 17/19: del(:,1)/del(:,2)), which the
+ * reference performs right after the QC filter.  `amiss` is m_gritas_grids' AMISS. */
+int orc_select_del_all(int nobs, int iopt, int tch, int self, int scale_res, const double *omf, const double *oma,
+                       const double *obs, const double *xvec, const double *xm, double *del) {
+  int i, a = abs(iopt), nr = 1;
+  double *d1 = del, *d2 = del + (size_t)nobs, *d3 = del + 2 * (size_t)nobs;
+  if (a == 0 || a == 1 || a == 2 || a == 3) {                         /* :562-587 */
+    if (orc_select_del(nobs, iopt, scale_res, omf, oma, obs, xvec, del)) return 0;
+    return 1;
+  }
+  for (i = 0; i < nobs; ++i) {
+    switch (a) {
+      case 4: case 5: d1[i] = obs[i]; break;                          /* :588-589 */
+      case 6: case 7: d1[i] = xvec[i]; break;                         /* :590-591 */
+      case 8: case 9: d1[i] = xm[i]; break;                           /* :592-593 */
+      case 10: case 11:                                               /* :594-611 */
+        if (tch) { d1[i] = oma[i] - omf[i]; d2[i] = -omf[i]; d3[i] = -oma[i]; nr = 3; }
+        else { d1[i] = omf[i] - oma[i]; d2[i] = omf[i]; nr = 2; }
+        break;
+      case 12: case 13:                                               /* :612-624 */
+        if (tch) { d1[i] = -oma[i]; d2[i] = omf[i] - oma[i]; d3[i] = omf[i]; nr = 3; }
+        else { d1[i] = omf[i] - oma[i]; d2[i] = oma[i]; nr = 2; }
+        break;
+      case 14: case 15:                                               /* :625-640 */
+        if (tch && self) { d1[i] = obs[i]; d2[i] = obs[i] - omf[i]; d3[i] = obs[i] - oma[i]; nr = 3; }
+        else if (tch) { d1[i] = omf[i]; d2[i] = oma[i]; d3[i] = oma[i] - omf[i]; nr = 3; }
+        else { d1[i] = oma[i]; d2[i] = omf[i]; nr = 2; }
+        break;
+      case 16: case 17: d1[i] = omf[i]; d2[i] = xvec[i]; nr = 2; break; /* :641-644 */
+      case 18: case 19: d1[i] = oma[i]; d2[i] = xvec[i]; nr = 2; break; /* :645-648 */
+      case 20: case 21: d1[i] = obs[i] + xm[i]; break;                /* :649-650 */
+      case 22: case 23: d1[i] = xvec[i]; break;                       /* :651-652 */
+      case 24: case 25: d1[i] = obs[i] - omf[i]; break;               /* :663 (not -meanres) */
+      case 28: case 29: d1[i] = obs[i] - omf[i] + xm[i]; break;       /* :678-679 */
+      case 30: case 31: d1[i] = obs[i] - oma[i]; break;               /* :690 (not -meanres) */
+      case 32: case 33:                                               /* :692-701 */
+        d1[i] = omf[i] - oma[i];
+        d2[i] = oma[i];
+        if (xvec[i] > 0.0) { d1[i] = d1[i] / xvec[i]; d2[i] = d2[i] / xvec[i]; }
+        else { d1[i] = ORC_AMISS; d2[i] = ORC_AMISS; }
+        nr = 2;
+        break;
+      default: return 0;
+    }
+    if (a == 17 || a == 19) d1[i] = d1[i] / d2[i];                    /* :738, inside the odd-iopt filter block */
+  }
+  return nr;
+}
+
 /* gritas.f:710-739: QC / time / longitude filter producing ob_flag (0 keep, 1 drop).  The
  * caller only runs it when iopt is odd (always the case from the CLI). */
 void orc_filter(int nobs, const int *qcexcl, const int *time, const double *lon, int ioptn,

@@ -46,6 +46,8 @@ def lib():
         L.orc_presort.restype = C.c_int
         L.orc_select_del.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p]
         L.orc_select_del.restype = C.c_int
+        L.orc_select_del_all.argtypes = [C.c_int] * 5 + [_f64p] * 6
+        L.orc_select_del_all.restype = C.c_int
         L.orc_filter.argtypes = [C.c_int, _i32p, _i32p, _f64p, C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_double, C.c_int, C.c_int, _i32p]
         L.orc_filter.restype = None
@@ -137,6 +139,17 @@ def select_del(iopt, omf, oma, obs=None, xvec=None, scale_res=0):
     if rc:
         raise ValueError("iopt not covered by the oracle")
     return d[:n]
+
+
+def select_del_all(iopt, omf, oma, obs, xvec, xm, tch=False, self_=False, scale_res=0):
+    """gritas.f:562-704 (+ :738) for every single-ODS residual option -> del (nobs, nr) F-order."""
+    n = len(omf)
+    d = np.zeros((max(n, 1), 3), order="F")
+    nr = lib().orc_select_del_all(n, iopt, int(tch), int(self_), scale_res, *_c(np.float64, omf, oma, obs, xvec, xm),
+                                  d.reshape(-1, order="F"))
+    if nr == 0:
+        raise ValueError("iopt not covered by the oracle")
+    return np.asfortranarray(d[:n, :nr])
 
 
 def filter_flags(qcexcl, time, lon, ioptn=1, t1=0, t2=-1, lona=-999.0, lonb=999.0, x_passive=7, x_pre_bad=1):

@@ -172,3 +172,22 @@ def norm(grids, nlevs, nr, nrmlz=True, ntresh=0):
                 out["xcov_" + tag][..., nx - 1] = np.where(many, xfull, np.where(one, xp, AMISS))
             out["stdv_" + tag] = stdv
     return out
+
+
+def select_del_all(iopt, omf, oma, obs, xvec, xm, tch=False, self_=False):
+    """GrITAS_App/gritas.f:588-704 (+ :738), numpy twin for the single-ODS residual options >= 4."""
+    a = abs(iopt)
+    omf, oma, obs, xvec, xm = (np.asarray(v, dtype=np.float64) for v in (omf, oma, obs, xvec, xm))
+    with np.errstate(all="ignore"):
+        cols = {
+            4: [obs], 6: [xvec], 8: [xm],
+            10: [oma - omf, -omf, -oma] if tch else [omf - oma, omf],
+            12: [-oma, omf - oma, omf] if tch else [omf - oma, oma],
+            14: ([obs, obs - omf, obs - oma] if self_ else [omf, oma, oma - omf]) if tch else [oma, omf],
+            16: [omf, xvec], 18: [oma, xvec], 20: [obs + xm], 22: [xvec], 24: [obs - omf], 28: [obs - omf + xm],
+            30: [obs - oma],
+            32: [np.where(xvec > 0.0, (omf - oma) / xvec, AMISS), np.where(xvec > 0.0, oma / xvec, AMISS)],
+        }[a - (a & 1)]
+        if a in (17, 19):
+            cols = [cols[0] / cols[1], cols[1]]
+    return np.asfortranarray(np.stack(cols, axis=1))

@@ -456,3 +456,52 @@ def test_fast_mode_picks_the_path_from_the_data(name, expect):
     G.close()
     ref, _ = H.oracle_run(cfg, files, nr)
     H.compare(out, ref, l2d, l3d, nr, exact=False, tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, cabi.MODE_DETERMINISTIC])
+@pytest.mark.parametrize("iopt,options", [(5, 0), (7, 0), (9, 0), (11, 0), (11, cabi.OPT_TCH), (13, 0), (13, cabi.OPT_TCH),
+                                          (15, 0), (15, cabi.OPT_TCH), (15, cabi.OPT_TCH | cabi.OPT_SELF), (-17, 0), (19, 0),
+                                          (21, 0), (23, 0), (-25, 0), (29, 0), (31, 0), (33, 0), (16, 0), (32, 0)])
+def test_fused_entry_all_residual_options(mode, iopt, options):
+    """gritas_b200_accum_odsx: the residual expressions of gritas.f:588-704 evaluated on the device must be
+    bit-identical to the oracle's host-side del (deterministic mode) for every single-ODS option."""
+    cfg, files = small("cfg1", 0.02, 2)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    tch, self_ = bool(options & cabi.OPT_TCH), bool(options & cabi.OPT_SELF)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    g = None
+    for c in files:
+        c = dict(c)
+        c["xvec"] = np.where(np.arange(len(c["lat"])) % 97 == 0, -1.0, c["xvec"])     # non-positive sigo now and then
+        d = oracle.select_del_all(iopt, c["omf"], c["oma"], c["obs"], c["xvec"], c["xm"], tch=tch, self_=self_)
+        nr = d.shape[1]
+        if g is None:
+            g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, nr)
+        n = len(c["lat"])
+        if abs(iopt) & 1:          # the QC filter only runs for odd options (gritas.f:710)
+            fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=iopt, x_passive=synth.X_PASSIVE,
+                                     x_pre_bad=synth.X_PRE_BAD)
+        else:
+            fl = np.zeros(n, np.int32)
+        oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], d, table, p1, p2, fl)
+        gfl = np.full(n, -9, np.int32)
+        G.accum_odsx(c, iopt, options=options, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD, kxkt_table=table,
+                     p1=p1, p2=p2, l2d=l2d, l3d=l3d, ob_flag_out=gfl)
+        assert np.array_equal(gfl, fl)
+    out = G.alloc_grids()
+    raw = nr == 3
+    if raw:
+        G.get_raw(None, None, None, None, out["bias_3d"], out["rtms_3d"], out["xcov_3d"], out["nobs_3d"])
+    else:
+        oracle.norm(g, cfg.nlevs, True, 0)
+        G.norm_into(out)
+    G.close()
+    with np.errstate(invalid="ignore"):
+        if raw and H.is_det(mode):
+            for nm in ("bias_3d", "rtms_3d", "nobs_3d"):
+                assert np.array_equal(out[nm], getattr(g, nm))
+        elif raw:
+            assert np.array_equal(out["nobs_3d"], g.nobs_3d)
+            assert np.allclose(out["bias_3d"], g.bias_3d, rtol=1e-9, atol=1e-9)
+        else:
+            H.compare(out, g, l2d, l3d, nr, exact=H.is_det(mode), tol=TOL_FAST)

@@ -154,3 +154,19 @@ def test_level_miss_stops_the_oracle_at_the_first_offender():
                      np.zeros(len(c["lat"]), np.int32))
     assert e.value.n == ok[10] and e.value.lev == 3000.0
     assert g.nobs_3d.sum() == 10
+
+
+@pytest.mark.parametrize("iopt", [4, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 23, 25, 28, 29, 31, 32, 33])
+def test_residual_options_c_equals_numpy(iopt):
+    """gritas.f:588-704: the C restatement of every single-ODS residual option against the numpy twin."""
+    rng = np.random.default_rng(iopt)
+    n = 500
+    omf, oma, xm = rng.normal(0, 2, n), rng.normal(0, 1, n), rng.normal(0, 0.3, n)
+    obs = rng.normal(250, 30, n)
+    xvec = rng.uniform(-0.5, 2.0, n)          # some non-positive sigo values exercise the `where` of option 32/33
+    for tch, self_ in ((False, False), (True, False), (True, True)):
+        a = oracle.select_del_all(iopt, omf, oma, obs, xvec, xm, tch=tch, self_=self_)
+        b = oracle_np.select_del_all(iopt, omf, oma, obs, xvec, xm, tch=tch, self_=self_)
+        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+    with pytest.raises(ValueError):
+        oracle.select_del_all(26, omf, oma, obs, xvec, xm)
