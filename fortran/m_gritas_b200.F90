@@ -32,9 +32,10 @@
       private
 
       public :: B200_Accum_, B200_Norm_, B200_GetRaw, B200_Reset, B200_Clean
+      public :: B200_MinMax_, B200_SetMask
       public :: B200_SetMode
 
-      integer(c_int), parameter :: MODE_FAST = 0, MODE_DETERMINISTIC = 1
+      integer(c_int), parameter :: MODE_FAST = 0, MODE_DETERMINISTIC = 1, FLAG_MINMAX = 8192
       integer(c_int), parameter :: ERR_LEVEL = 7
 
       type(c_ptr), save      :: handle = c_null_ptr
@@ -82,6 +83,18 @@
             type(c_ptr),    value             :: h
             real(c_double), intent(inout)     :: bias_2d(*), rtms_2d(*), xcov_2d(*), nobs_2d(*)
             real(c_double), intent(inout)     :: bias_3d(*), rtms_3d(*), xcov_3d(*), nobs_3d(*)
+         end function
+         integer(c_int) function gritas_b200_get_minmax ( h, minv_2d, maxv_2d, nobs_2d,         &
+                                  minv_3d, maxv_3d, nobs_3d ) bind(C, name='gritas_b200_get_minmax')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            real(c_double), intent(inout)     :: minv_2d(*), maxv_2d(*), nobs_2d(*)
+            real(c_double), intent(inout)     :: minv_3d(*), maxv_3d(*), nobs_3d(*)
+         end function
+         integer(c_int) function gritas_b200_set_mask ( h, maskfld ) bind(C, name='gritas_b200_set_mask')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            real(c_double), intent(in)        :: maskfld(*)
          end function
          integer(c_int) function gritas_b200_reset ( h ) bind(C, name='gritas_b200_reset')
             import :: c_ptr, c_int
@@ -163,6 +176,54 @@
                               bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d )
       if ( rc /= 0 ) call gritas_perror ('Norm: B200 finalize failed')
       end subroutine B200_Norm_
+
+!     Same argument list as GrITAS_MinMax_ (m_gritas_grids.f:1019-1023).  Unlike Accum/Norm there is no
+!     separate finalize call in the driver (gritas.f:884 skips Norm with -minmax), so the min / max / count
+!     grids are downloaded after every call; drivers that process many files may call the C entry
+!     gritas_b200_get_minmax once after the file loop instead.
+      subroutine B200_MinMax_ ( lat, lon, lev, kx, kt, del, nobs, nr,                           &
+                                kxkt_table, p1, p2, ob_flag,                                    &
+                                l2d, minv_2d, maxv_2d, nobs_2d,                                 &
+                                l3d, minv_3d, maxv_3d, nobs_3d )
+      use m_gritas_grids, only : im, jm, km, nlevs
+      use m_odsmeta,      only : KTMAX, KXMAX
+      integer, intent(in)    :: nobs, nr
+      real,    intent(in)    :: lat(nobs), lon(nobs), lev(nobs), del(nobs,nr)
+      integer, intent(in)    :: kx(nobs), kt(nobs)
+      integer, intent(in)    :: kxkt_table(KXMAX,KTMAX)
+      real,    intent(in)    :: p1(nlevs), p2(nlevs)
+      integer, intent(in)    :: l2d, l3d
+      integer, intent(inout) :: ob_flag(nobs)
+      real,    intent(inout) :: minv_2d(im,jm,l2d,nr), maxv_2d(im,jm,l2d,nr), nobs_2d(im,jm,l2d)
+      real,    intent(inout) :: minv_3d(im,jm,km,l3d,nr), maxv_3d(im,jm,km,l3d,nr), nobs_3d(im,jm,km,l3d)
+      integer(c_int) :: rc
+      real(c_double) :: bad_lev
+      if ( nr > 1 ) call gritas_perror ('MinMax: could not handle more then 1 field')      ! :1071-1072
+      if ( .not. c_associated(handle) ) then
+         rc = gritas_b200_create ( handle, im, jm, km, nlevs, l2d, l3d, nr, p1, p2,             &
+                                   kxkt_table, KXMAX, KTMAX, mode + FLAG_MINMAX, -1_c_int )
+         if ( rc /= 0 ) call gritas_perror ('MinMax: cannot create the B200 context')
+      end if
+      rc = gritas_b200_accum ( handle, nobs, lat, lon, lev, del, kx, kt, ob_flag, bad_lev )
+      if ( rc == ERR_LEVEL ) then                                        ! m_gritas_grids.f:1132-1135
+         print *, 'Accum: obs level is ', bad_lev, ' hPa'
+         call gritas_perror ('Accum: could not find level')
+      else if ( rc /= 0 ) then
+         call gritas_perror ('MinMax: B200 accumulate failed')
+      end if
+      rc = gritas_b200_get_minmax ( handle, minv_2d, maxv_2d, nobs_2d, minv_3d, maxv_3d, nobs_3d )
+      if ( rc /= 0 ) call gritas_perror ('MinMax: B200 download failed')
+      end subroutine B200_MinMax_
+
+!     gritas_maskout (m_gritas_masks.F90:137-186): hand the (im,jm) fraction field of ini_masks_ to the library
+!     once; every later Accum flags the observations whose box holds less than 0.99 (replaces gritas.f:745).
+      subroutine B200_SetMask ( maskfld )
+      real, intent(in) :: maskfld(*)
+      integer(c_int) :: rc
+      if ( .not. c_associated(handle) ) call gritas_perror ('SetMask: call after the first Accum')
+      rc = gritas_b200_set_mask ( handle, maskfld )
+      if ( rc /= 0 ) call gritas_perror ('SetMask: B200 upload failed')
+      end subroutine B200_SetMask
 
 !     Un-normalised sums into the host grids (what they would hold between Accum and Norm).
       subroutine B200_GetRaw ( bias_2d, rtms_2d, xcov_2d, nobs_2d,                              &

@@ -22,6 +22,7 @@ FLAG_NO_AGGREGATE = 0x200
 FLAG_HOLD_INPUTS = 0x400
 FLAG_NO_STAGING = 0x800
 FLAG_FORCE_TILED = 0x1000
+FLAG_MINMAX = 0x2000
 
 OK = 0
 ERR_LEVEL = 7
@@ -38,7 +39,7 @@ IOPT_OMF_OMA = 101
 SYMBOLS = [
     "gritas_b200_create", "gritas_b200_destroy", "gritas_b200_pint", "gritas_b200_kxkt", "gritas_b200_accum",
     "gritas_b200_accum_ods", "gritas_b200_accum_odsx", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
-    "gritas_b200_get_raw", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
+    "gritas_b200_get_raw", "gritas_b200_get_minmax", "gritas_b200_set_mask", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
     "gritas_b200_allreduce", "gritas_b200_norm_reduce", "gritas_b200_norm_reduce_device", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
     "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_tiled", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
     "gritas_b200_d2h_bytes", "gritas_b200_version",
@@ -86,6 +87,8 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_norm_device.argtypes = [_P, _I, _I] + [C.POINTER(_P)] * 10
     L.gritas_b200_get_raw.argtypes = [_P] + [_P] * 8
     L.gritas_b200_add_raw.argtypes = [_P] + [_P] * 8
+    L.gritas_b200_get_minmax.argtypes = [_P] + [_P] * 6
+    L.gritas_b200_set_mask.argtypes = [_P, _P]
     L.gritas_b200_nccl_unique_id.argtypes = [_P]
     L.gritas_b200_comm_init.argtypes = [_P, _I, _I, _P]
     L.gritas_b200_allreduce.argtypes = [_P]

@@ -103,6 +103,8 @@ struct gritas_b200_ctx {
   StageDesc sg = {};
   bool staging = false;        // tiled path available (buffers allocated)
   int tiled_choice = -1;       // -1 undecided (probe the first large call), 0 direct, 1 tiled
+  bool minmax = false;         // GrITAS_MinMax handle: records {n, min key, max key, pad}
+  double *d_mask = nullptr;    // gritas_maskout fraction field (im x jm), optional
   bool acc_fresh = true;       // records untouched since create / reset (apart from direct RED, see StageDesc::dirty)
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
@@ -395,7 +397,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
   // Fast mode picks between the tiled and the direct accumulate by looking at the data: the first call with at
   // least 64 Ki observations runs the direct kernel with a locality probe (both paths add into the same records).
   bool probe = false;
-  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice < 0) probe = n >= 65536;
+  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice < 0 && !h->minmax) probe = n >= 65536;
   const bool tiled = (h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice == 1;
   const int w = h->next_wk;
   cudaStream_t run = tiled ? h->wk[w] : h->compute;
@@ -408,7 +410,16 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     CU(cudaStreamWaitEvent(run, s.copied, 0));
   }
   const size_t smem = levtab_smem_bytes(h->g);
-  if (tiled) {
+  if (h->minmax) {
+    const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
+    const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
+    switch (filter_mode(f)) {
+      case 0: k_minmax<0><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq); break;
+      case 1: k_minmax<1><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq); break;
+      default: k_minmax<2><<<nblk, ACC_THREADS, smem, h->compute>>>(h->g, c, f, h->d_status, h->call_seq); break;
+    }
+    h->launches += 1;
+  } else if (tiled) {
     // tiled path: partition this call's observations into the per-tile lists (slices bound the scratch)
     const int SLICE = (int)h->sg.nbatch_cap * P1_BATCH;
     for (int s0 = 0; s0 < n; s0 += SLICE) {
@@ -532,6 +543,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
     return GRITAS_B200_ERR_ARG;
   if (nr < 1) return GRITAS_B200_ERR_ARG;
   if (nr > 3) return GRITAS_B200_ERR_NR;  // m_gritas_grids.f:395-396
+  if ((mode & GRITAS_B200_FLAG_MINMAX) && nr > 1) return GRITAS_B200_ERR_NR;  // 'MinMax: could not handle more then 1 field' (:1072)
   const int m = mode & 0xff;
   if (m != GRITAS_B200_MODE_FAST && m != GRITAS_B200_MODE_DETERMINISTIC) return GRITAS_B200_ERR_ARG;
   int ndev = 0;
@@ -555,6 +567,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   h->device = device;
   h->mode = m;
   h->flags = mode & ~0xff;
+  h->minmax = (mode & GRITAS_B200_FLAG_MINMAX) != 0;
   GridDesc &g = h->g;
   g.im = im; g.jm = jm; g.km = km; g.nlevs = nlevs; g.l2d = l2d; g.l3d = l3d; g.nr = nr;
   g.rs = (nr == 1) ? 4 : 8;
@@ -618,7 +631,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
     CUC(cudaMemcpy(h->d_lut, lut.data(), sizeof(unsigned short) * (size_t)g.lut_ncell, cudaMemcpyHostToDevice));
   }
   g.lut = h->d_lut;
-  CUC(cudaMemsetAsync(g.acc, 0, acc_bytes, h->compute));  // gritas.f:352-363
+  if (h->minmax) k_minmax_init<<<grid_for(h->nrec, 256, 8), 256, 0, h->compute>>>(g.acc, h->nrec);  // gritas.f:364-366
+  else CUC(cudaMemsetAsync(g.acc, 0, acc_bytes, h->compute));  // gritas.f:352-363
   g.table = h->d_table; g.p1 = h->d_p1; g.p2 = h->d_p2;
   Status st[NWK + 1];
   for (Status &q : st) { q.first_bad = BAD_NONE; q.bad_lev = 0.0; q.near_pairs = 0; q.pairs = 0; }
@@ -633,7 +647,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
     const char *e_on = getenv("GRITAS_B200_STAGE"), *e_shift = getenv("GRITAS_B200_TILE_SHIFT"),
                *e_slots = getenv("GRITAS_B200_STAGE_SLOTS"), *e_max = getenv("GRITAS_B200_STAGE_MAX_GRID_MB");
     const size_t max_grid = (e_max ? (size_t)atoll(e_max) : (size_t)8192) << 20;
-    bool want = m == GRITAS_B200_MODE_FAST && !(h->flags & GRITAS_B200_FLAG_NO_STAGING) && acc_bytes <= max_grid &&
+    bool want = m == GRITAS_B200_MODE_FAST && !h->minmax && !(h->flags & GRITAS_B200_FLAG_NO_STAGING) && acc_bytes <= max_grid &&
                 h->nrec >= 4096;
     if (e_on && atoi(e_on) == 0) want = false;
     if (want) {
@@ -771,6 +785,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
   for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2]})
     if (p) cudaFree(p);
   if (h->d_lut) cudaFree(h->d_lut);
+  if (h->d_mask) cudaFree(h->d_mask);
   for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
                   (void *)h->keys, (void *)h->idx, (void *)h->keys2, (void *)h->idx2, h->cub_tmp, (void *)h->out})
     if (p) cudaFree(p);
@@ -979,7 +994,8 @@ int gritas_b200_reset(gritas_b200_handle h) {
   if (rc) return rc;
   if ((rc = join_workers(h))) return rc;
   h->acc_fresh = true;
-  CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
+  if (h->minmax) k_minmax_init<<<grid_for(h->nrec, 256, 8), 256, 0, h->compute>>>(h->g.acc, h->nrec);
+  else CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   if (h->staging) {
     const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
     CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * (nfill + 4), h->compute));   // counters and the dirty word
@@ -1013,7 +1029,7 @@ static int launch_finalize(gritas_b200_handle h, cudaStream_t sm, double *const 
     dim3 blk(32, 32), grd((g.km + 31) / 32, (g.im + 31) / 32, 1);
     const int z = jl1 - jl0;
     grd.z = (unsigned)(z > 65535 ? 65535 : z);
-    const int r3 = raw3 ? 1 : 0;
+    const int r3 = raw == 2 ? 2 : (raw3 ? 1 : 0);
     const size_t fsm = sizeof(double) * (size_t)(4 * nr + 1) * 32 * 33;
     if (nr == 1) {
       CU(cudaFuncSetAttribute(k_finalize3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
@@ -1042,6 +1058,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   const int nr = g.nr;
   if (!raw && nr > 2) return fail(h, GRITAS_B200_ERR_NR, "Accum: could not handle more then 2 residuals");  // :555
   const size_t n2 = g.nbox2, n3 = g.nbox3;
+  if (!raw && h->minmax) return fail(h, GRITAS_B200_ERR_ARG, "Norm on a MinMax handle: use gritas_b200_get_minmax (gritas.f:884 skips Norm)");
   const int xpl = raw ? 1 : nr;
   const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
   // nlevs<2: the reference returns before the 3-D loop (m_gritas_grids.f:607) -> 3-D sums stay raw
@@ -1054,7 +1071,8 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   for (int a = 0; a < 10; ++a) {
     bounce[a] = false;
     dst[a] = nullptr;
-    const bool skip = !writer || (!user[a] && !dev_out) || sz[a] == 0 || (raw && (a == 2 || a == 7)) || (!raw && raw3 && a == 7);
+    const bool skip = !writer || (!user[a] && !dev_out) || sz[a] == 0 || (raw == 1 && (a == 2 || a == 7)) ||
+                      (raw == 2 && (a == 1 || a == 3 || a == 6 || a == 8)) || (!raw && raw3 && a == 7);
     if (skip) continue;
     if (!dev_out && mem_kind(user[a]) == 2) dst[a] = user[a];
     else { bounce[a] = true; need += sz[a]; }
@@ -1199,6 +1217,37 @@ int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, 
   return finalize_to(h, 1, 0, 0, u, nullptr);
 }
 
+// GrITAS_MinMax results (m_gritas_grids.f:1019-1167): minv (AMISS where nothing fell), maxv (-AMISS where
+// nothing fell; gritas.f:997-1000 turns those into AMISS afterwards) and the counts, reference layout.
+int gritas_b200_get_minmax(gritas_b200_handle h, double *minv_2d, double *maxv_2d, double *nobs_2d, double *minv_3d,
+                           double *maxv_3d, double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->minmax) return fail(h, GRITAS_B200_ERR_ARG, "not a MinMax handle (GRITAS_B200_FLAG_MINMAX)");
+  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  double *const u[10] = {minv_2d, nullptr, maxv_2d, nullptr, nobs_2d, minv_3d, nullptr, maxv_3d, nullptr, nobs_3d};
+  return finalize_to(h, 2, 0, 0, u, nullptr);
+}
+
+// gritas_maskout fused into the classify step: observations whose box has maskfld(i,j) < 0.99 are flagged
+// (m_gritas_masks.F90:164-183).  maskfld: (im, jm) column-major on the handle's grid; NULL removes the mask.
+int gritas_b200_set_mask(gritas_b200_handle h, const double *maskfld) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->compute));
+  if ((rc = join_workers(h))) return rc;
+  CU(cudaStreamSynchronize(h->compute));
+  if (!maskfld) {
+    h->g.mask = nullptr;
+    return 0;
+  }
+  const size_t bytes = sizeof(double) * (size_t)h->g.im * h->g.jm;
+  if (!h->d_mask) CU(cudaMalloc(&h->d_mask, bytes));
+  CU(cudaMemcpy(h->d_mask, maskfld, bytes, cudaMemcpyDefault));
+  h->g.mask = h->d_mask;
+  return 0;
+}
+
 int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const double *rtms_2d, const double *xcov_2d,
                         const double *nobs_2d, const double *bias_3d, const double *rtms_3d, const double *xcov_3d,
                         const double *nobs_3d) {
@@ -1275,6 +1324,7 @@ int gritas_b200_allreduce(gritas_b200_handle h) {
   if (rc) return rc;
   if (h->nranks == 1 && !h->comm) return 0;
   if (!h->comm) return fail(h, GRITAS_B200_ERR_NCCL, "comm_init not called");
+  if (h->minmax) return fail(h, GRITAS_B200_ERR_ARG, "MinMax handles are not summed across ranks");
   CU(cudaStreamSynchronize(h->copy));
   if ((rc = flush_stage(h))) return rc;
   h->acc_fresh = false;

@@ -48,6 +48,7 @@ struct GridDesc {
   unsigned nbox3, nbox2;
   const int *table;
   const double *p1, *p2;
+  const double *mask;    // optional (im, jm) fraction field of gritas_maskout (m_gritas_masks.F90:137-186), or null
   double *acc;
 };
 
@@ -461,6 +462,14 @@ __device__ __forceinline__ unsigned classify(const GridDesc &g, const FilterDesc
                                              int tm, int n, Status *st, unsigned call_seq, int &flag_after) {
   int fl = flag_in;
   if (f.ods) fl = qc_filter(f, flag_in, tm, lon);
+  if (g.mask && fl == 0) {  // gritas_maskout (gritas.f:745): same box formula, fraction < 0.99 -> flagged
+    int ii = 1 + grid_index(lon, -180.0, g.dlon, g.rdlon);
+    if (ii == g.im + 1) ii = 1;
+    if (ii == 0) ii = g.im;
+    ii = min(g.im, max(1, ii));
+    const int jj = min(g.jm, max(1, 1 + grid_index(lat, -90.0, g.dlat, g.rdlat)));
+    if (__ldg(g.mask + (size_t)(ii - 1) + (size_t)g.im * (size_t)(jj - 1)) < 0.99) fl = 1;
+  }
   flag_after = fl;
   if (fl != 0) return KEY_NONE;  // m_gritas_grids.f:406-407
   int outcome;
@@ -529,15 +538,17 @@ __device__ __forceinline__ void classify4(const GridDesc &g, const FilterDesc &f
   bool any_miss = false;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const bool live = (base + j < n) && fl[j] == 0;                                         // :406-407
-    const bool surface = l[j] < 0;                                                           // :410
-    const int la = abs(l[j]);
-    const bool intab = la > 0;                                                               // :413
     int i2 = ii[j] + 1;                                                                      // :420
     i2 = (i2 == g.im + 1) ? 1 : i2;                                                          // :421
     i2 = (i2 == 0) ? g.im : i2;                                                              // :422
     i2 = min(g.im, max(1, i2));                                                              // :425
     const int j2 = min(g.jm, max(1, jj[j] + 1));                                             // :423, 426
+    if (g.mask && fl[j] == 0 && base + j < n)   // gritas_maskout (gritas.f:745, m_gritas_masks.F90:164-183)
+      fl[j] = (__ldg(g.mask + (size_t)(i2 - 1) + (size_t)g.im * (size_t)(j2 - 1)) < 0.99) ? 1 : 0;
+    const bool live = (base + j < n) && fl[j] == 0;                                         // :406-407
+    const bool surface = l[j] < 0;                                                           // :410
+    const int la = abs(l[j]);
+    const bool intab = la > 0;                                                               // :413
     const unsigned cell = (unsigned)(i2 - 1) + (unsigned)g.im * ((unsigned)(j2 - 1) + (unsigned)g.jm * (unsigned)(la - 1));
     const unsigned key2 = g.nbox3 + cell;
     const unsigned key3 = (unsigned)k[j] + (unsigned)g.km * cell;
@@ -668,6 +679,67 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
       if (issue) red_record<NR>(g.acc + (size_t)key * (size_t)g.rs, cnt, sx, sq, sxy);
     }
     if (c.flag_out && v < nvec) {
+      if (c.aligned && base + 3 < c.n) {
+        *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (base + j < c.n) c.flag_out[base + j] = fa[j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GrITAS_MinMax_ (m_gritas_grids.f:1019-1167): same filter / box index, keeps the smallest and largest
+// residual of every box and the count.  Records are {n, min, max, pad}; min / max are held as order-preserving
+// int64 keys so that they can be updated with native 64-bit atomicMin / atomicMax (order-free: exact and
+// reproducible in every mode).  NaN residuals count but never win a comparison, as in the reference.
+__device__ __forceinline__ long long f64_order_key(double x) {
+  const long long b = __double_as_longlong(x);
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffll);
+}
+__device__ __forceinline__ double f64_from_order_key(long long k) {
+  return __longlong_as_double(k >= 0 ? k : (k ^ 0x7fffffffffffffffll));
+}
+
+__global__ void __launch_bounds__(256)
+k_minmax_init(double *__restrict__ acc, size_t nrec) {
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += (size_t)gridDim.x * blockDim.x) {
+    double *rec = acc + r * 4;
+    rec[0] = 0.0;
+    reinterpret_cast<long long *>(rec)[1] = f64_order_key(AMISS);    // gritas.f:364-366: min starts at AMISS,
+    reinterpret_cast<long long *>(rec)[2] = f64_order_key(-AMISS);   // max at -AMISS
+    rec[3] = 0.0;
+  }
+}
+
+template <int FMODE>
+__global__ void __launch_bounds__(ACC_THREADS)
+k_minmax(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq) {
+  extern __shared__ double s_p2[];
+  const LevTab p2s = load_p2(g, s_p2);
+  const int nvec = (c.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const int base = v * OBS_PER_THREAD;
+    Obs4<1> o;
+    int fa[4];
+    unsigned k4[4];
+    load_obs4<1>(c, f, base, o);
+    classify4<1, FMODE>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (k4[j] == KEY_NONE) continue;
+      double d = o.d[0][j];
+      if (f.scale_res | f.expr) d = residual_value(f, c, 0, d, base + j);
+      double *rec = g.acc + (size_t)k4[j] * 4;
+      atomicAdd(rec, 1.0);                                                // :1113, 1148
+      if (d == d) {
+        atomicMin(reinterpret_cast<long long *>(rec) + 1, f64_order_key(d));   // :1109, 1144
+        atomicMax(reinterpret_cast<long long *>(rec) + 2, f64_order_key(d));   // :1110, 1145
+      }
+    }
+    if (c.flag_out) {
       if (c.aligned && base + 3 < c.n) {
         *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
       } else {
@@ -1297,10 +1369,17 @@ __device__ __forceinline__ double div_shared(double x, double d, double r) {
 // m_gritas_grids.f:566-605 (2-D) and 612-654 (3-D) for one box.  raw: pass the sums through.
 template <int NR>
 __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, bool is3d, int nrmlz, int ntresh,
-                                             bool raw, double (&bias)[NR], double (&rtms)[NR], double (&stdv)[NR],
+                                             int raw, double (&bias)[NR], double (&rtms)[NR], double (&stdv)[NR],
                                              double (&xcov)[NR], double &nobs) {
   const double n = rec[0];
   nobs = n;
+  if (raw == 2) {   // MinMax records: bias <- min, stdv <- max (the arrays gritas.f:770-775 passes to GrITAS_MinMax)
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) { bias[ir] = 0.0; rtms[ir] = 0.0; stdv[ir] = 0.0; xcov[ir] = 0.0; }
+    bias[0] = f64_from_order_key(__double_as_longlong(rec[1]));
+    stdv[0] = f64_from_order_key(__double_as_longlong(rec[2]));
+    return;
+  }
   const double xraw = (NR == 1) ? rec[2] : (NR == 2 ? rec[5] : 0.0);  // nr=3: xcov untouched (:397-401)
   if (raw) {
 #pragma unroll
@@ -1380,7 +1459,7 @@ k_finalize3(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw, int
           r[4] = c2.x; r[5] = c2.y; r[6] = d2.x; r[7] = d2.y;
         }
         double bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs;
-        finalize_box<NR>(r, true, nrmlz, ntresh, raw != 0, bias, rtms, stdv, xcov, nobs);
+        finalize_box<NR>(r, true, nrmlz, ntresh, raw, bias, rtms, stdv, xcov, nobs);
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) {
           v[ir] = bias[ir]; v[NR + ir] = rtms[ir]; v[2 * NR + ir] = stdv[ir]; v[3 * NR + ir] = xcov[ir];
@@ -1418,7 +1497,7 @@ k_finalize2(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw) {
 #pragma unroll
     for (int q = 0; q < (NR > 1 ? 8 : 4); ++q) r[q] = rec[q];
     double bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs;
-    finalize_box<NR>(r, false, nrmlz, ntresh, raw != 0, bias, rtms, stdv, xcov, nobs);
+    finalize_box<NR>(r, false, nrmlz, ntresh, raw, bias, rtms, stdv, xcov, nobs);
 #pragma unroll
     for (int ir = 0; ir < NR; ++ir) {
       if (out.bias) out.bias[b + nb * ir] = bias[ir];

@@ -230,6 +230,28 @@ class Grids:
         self._check(cabi.load().gritas_b200_add_raw(self._h, p(bias_2d), p(rtms_2d), p(xcov_2d), p(nobs_2d),
                                                     p(bias_3d), p(rtms_3d), p(xcov_3d), p(nobs_3d)))
 
+    # ---- GrITAS_MinMax_ (m_gritas_grids.f:1019-1167) ---------------------------------------
+    def GrITAS_MinMax(self, lat, lon, lev, kx, kt, del_, nobs, nr, kxkt_table, p1, p2, ob_flag, l2d, minv_2d=None,
+                      maxv_2d=None, nobs_2d=None, l3d=0, minv_3d=None, maxv_3d=None, nobs_3d=None):
+        """Same argument list as the reference; the handle must have been made with FLAG_MINMAX."""
+        if nr > 1:
+            raise GritasPerror("MinMax: could not handle more then 1 field")
+        if not (self.mode & cabi.FLAG_MINMAX):
+            raise ValueError("Grids(..., mode=... | cabi.FLAG_MINMAX) needed for GrITAS_MinMax")
+        self.GrITAS_Accum(lat, lon, lev, kx, kt, del_, nobs, nr, kxkt_table, p1, p2, ob_flag, l2d, l3d=l3d)
+
+    def get_minmax(self, minv_2d, maxv_2d, nobs_2d, minv_3d, maxv_3d, nobs_3d):
+        p = lambda a: cabi.ptr(a, np.float64)
+        self._check(cabi.load().gritas_b200_get_minmax(self._h, p(minv_2d), p(maxv_2d), p(nobs_2d), p(minv_3d), p(maxv_3d),
+                                                       p(nobs_3d)))
+
+    def set_mask(self, maskfld):
+        """gritas_maskout (m_gritas_masks.F90:137-186) fused into the accumulate kernels; (im, jm) fraction field."""
+        if maskfld is not None:
+            maskfld = np.asfortranarray(maskfld, dtype=np.float64)
+            assert maskfld.shape == (self.im, self.jm)
+        self._check(cabi.load().gritas_b200_set_mask(self._h, cabi.ptr(maskfld, np.float64)))
+
     def alloc_grids(self, nr=None, pinned=False):
         """Host arrays shaped like gritas.f:336-348, zero-initialised (gritas.f:352-363)."""
         nr = self.nr if nr is None else nr

@@ -39,6 +39,8 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
                                             observation goes to the HBM records with fp64 RED */
 #define GRITAS_B200_FLAG_FORCE_TILED 0x1000 /* fast mode: use the tiled accumulate from the first call on instead of
                                             deciding from the locality of the first large call */
+#define GRITAS_B200_FLAG_MINMAX 0x2000      /* the handle implements GrITAS_MinMax_ (m_gritas_grids.f:1019-1167, -minmax):
+                                            accum keeps min / max / count per box instead of sums; nr must be 1 */
 #define GRITAS_B200_FLAG_HOLD_INPUTS 0x400  /* with ASYNC: the caller keeps pinned input arrays valid until the
                                             next sync/norm, so accum does not even wait for the H2D copies */
 
@@ -175,6 +177,17 @@ int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const d
  * Norm: gritas.f:812-818, -nonorm gritas.f:1508-1509).  xcov_* receive slot 1 only. */
 int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, double *xcov_2d, double *nobs_2d,
                         double *bias_3d, double *rtms_3d, double *xcov_3d, double *nobs_3d);
+
+/* Replaces GrITAS_MinMax_ (m_gritas_grids.f:1019-1167) together with gritas_b200_accum on a handle created with
+ * GRITAS_B200_FLAG_MINMAX: minv (AMISS where empty), maxv (-AMISS where empty, gritas.f:997-1000 flips those)
+ * and the counts, reference layout (im,jm,l2d) / (im,jm,km,l3d). */
+int gritas_b200_get_minmax(gritas_b200_handle h, double *minv_2d, double *maxv_2d, double *nobs_2d, double *minv_3d,
+                           double *maxv_3d, double *nobs_3d);
+
+/* Replaces gritas_maskout (m_gritas_masks.F90:137-186, called at gritas.f:745): with a mask set, every accum
+ * entry flags the observations whose box has maskfld(i,j) < 0.99 before accumulating (ob_flag = 1 on return).
+ * maskfld is (im, jm) column-major on the handle's grid (ini_masks_ bins it to the target grid); NULL clears. */
+int gritas_b200_set_mask(gritas_b200_handle h, const double *maskfld);
 
 /* Adds caller-held un-normalised sums into the device accumulators (resuming from -nonorm output,
  * or honouring host grids that were not zero on the first Accum). */

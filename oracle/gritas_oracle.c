@@ -497,3 +497,77 @@ void orc_div_nredundant(size_t n, double *nobs_grid, int nredundant) {
   size_t i;
   for (i = 0; i < n; ++i) nobs_grid[i] = nobs_grid[i] / (double)nredundant;
 }
+
+/* m_gritas_grids.f:1019-1167 (GrITAS_MinMax_): nr must be 1 ("could not handle more then 1 field", :1072).
+ * minv / maxv are inout (the driver starts them at AMISS / -AMISS, gritas.f:364-366).  Same return codes and
+ * level-miss behaviour as orc_accum (the message at :1133-1134 is the Accum one). */
+int orc_minmax(int im, int jm, int km, int nlevs, int nobs, int nr, const double *lat, const double *lon,
+               const double *lev, const int *kx, const int *kt, const double *del, const int *kxkt_table, int kxmax,
+               int ktmax, const double *p1, const double *p2, int *ob_flag, int l2d, double *minv_2d, double *maxv_2d,
+               double *nobs_2d, int l3d, double *minv_3d, double *maxv_3d, double *nobs_3d, double *bad_lev, int *bad_n) {
+  int n, i, j, k, kk, l, surface_var;
+  double dlon, dlat;
+  long ii, jj;
+  if (nr > 1) return 8;                                                  /* :1071-1072 */
+  orc_grid_init(im, jm, &dlon, &dlat);
+  for (n = 0; n < nobs; ++n) {                                           /* :1077 */
+    if (ob_flag[n] != 0) continue;                                       /* :1078-1079 */
+    if (kx[n] < 1 || kx[n] > kxmax || kt[n] < 1 || kt[n] > ktmax) l = 0;
+    else l = kxkt_table[(size_t)(kx[n] - 1) + (size_t)kxmax * (size_t)(kt[n] - 1)]; /* :1081 */
+    surface_var = l < 0;
+    l = abs(l);
+    if (l <= 0) { ob_flag[n] = 1; continue; }                            /* :1085-1088 */
+    ii = 1 + orc_nint((lon[n] - ORC_LONMIN) / dlon);                     /* :1092-1098 */
+    if (ii == (long)im + 1) ii = 1;
+    if (ii == 0) ii = im;
+    jj = 1 + orc_nint((lat[n] - ORC_LATMIN) / dlat);
+    if (ii < 1) ii = 1;
+    if (ii > im) ii = im;
+    if (jj < 1) jj = 1;
+    if (jj > jm) jj = jm;
+    i = (int)ii;
+    j = (int)jj;
+    if (surface_var) {                                                   /* :1104-1113 */
+      if (del[n] < minv_2d[IX2(i, j, l, 1)]) minv_2d[IX2(i, j, l, 1)] = del[n];
+      if (del[n] > maxv_2d[IX2(i, j, l, 1)]) maxv_2d[IX2(i, j, l, 1)] = del[n];
+      nobs_2d[IX2(i, j, l, 1)] = nobs_2d[IX2(i, j, l, 1)] + 1.0;
+    } else {
+      k = 0;
+      for (kk = 1; kk <= nlevs; ++kk)                                    /* :1123-1130 */
+        if (lev[n] <= p1[kk - 1] && lev[n] > p2[kk - 1]) { k = kk; break; }
+      if (k == 0) {                                                      /* :1132-1135 */
+        if (bad_lev) *bad_lev = lev[n];
+        if (bad_n) *bad_n = n;
+        return 7;
+      }
+      if (del[n] < minv_3d[IX3(i, j, k, l, 1)]) minv_3d[IX3(i, j, k, l, 1)] = del[n];   /* :1143-1148 */
+      if (del[n] > maxv_3d[IX3(i, j, k, l, 1)]) maxv_3d[IX3(i, j, k, l, 1)] = del[n];
+      nobs_3d[IX3(i, j, k, l, 1)] = nobs_3d[IX3(i, j, k, l, 1)] + 1.0;
+    }
+  }
+  return 0;
+}
+
+/* m_gritas_masks.F90:137-186 (maskout_): flags the observations whose box of the (im, jm) fraction field holds
+ * less than 0.99.  Returns the number of observations excluded (the value the reference prints). */
+int orc_maskout(int im, int jm, int nobs, const double *lat, const double *lon, const double *maskfld, int *qcx) {
+  int n, nexcl = 0;
+  double dlon, dlat;
+  long ii, jj;
+  orc_grid_init(im, jm, &dlon, &dlat);                                   /* :151-152 */
+  for (n = 0; n < nobs; ++n) {
+    ii = 1 + orc_nint((lon[n] - ORC_LONMIN) / dlon);                     /* :168-174 */
+    if (ii == (long)im + 1) ii = 1;
+    if (ii == 0) ii = im;
+    jj = 1 + orc_nint((lat[n] - ORC_LATMIN) / dlat);
+    if (ii < 1) ii = 1;
+    if (ii > im) ii = im;
+    if (jj < 1) jj = 1;
+    if (jj > jm) jj = jm;
+    if (maskfld[(size_t)(ii - 1) + (size_t)im * (size_t)(jj - 1)] < 0.99 && qcx[n] == 0) {   /* :178-181 */
+      nexcl++;
+      qcx[n] = 1;
+    }
+  }
+  return nexcl;
+}

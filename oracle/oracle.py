@@ -60,6 +60,12 @@ def lib():
         L.orc_box_keys.argtypes = ([C.c_int] * 5 + [_f64p, _f64p, _f64p, _i32p, _i32p, _i32p, C.c_int, C.c_int,
                                                     _f64p, _f64p, _i32p, C.c_int, C.c_int, _i64p])
         L.orc_box_keys.restype = None
+        L.orc_minmax.argtypes = ([C.c_int] * 6 + [_f64p, _f64p, _f64p, _i32p, _i32p, _f64p, _i32p, C.c_int, C.c_int, _f64p, _f64p,
+                                                  _i32p, C.c_int, _f64p, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p,
+                                                  C.POINTER(C.c_double), C.POINTER(C.c_int)])
+        L.orc_minmax.restype = C.c_int
+        L.orc_maskout.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _f64p, _i32p]
+        L.orc_maskout.restype = C.c_int
         L.orc_norm.argtypes = ([C.c_int] * 6 + [C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p,
                                                 C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_int])
         L.orc_norm.restype = C.c_int
@@ -228,3 +234,35 @@ def norm(g: Grids, nlevs, nrmlz=True, ntresh=0):
                         g.l3d, g.bias_3d, g.rtms_3d, g.stdv_3d, g.xcov_3d, g.nobs_3d, ntresh)
     if rc:
         raise ValueError("Norm: could not handle more then 2 residuals")
+
+
+def minmax(g: Grids, nlevs, lat, lon, lev, kx, kt, del_, kxkt_table, p1, p2, ob_flag):
+    """GrITAS_MinMax_ (m_gritas_grids.f:1019-1167): min in g.bias_*, max in g.stdv_*, counts in g.nobs_* -- the arrays
+    gritas.f:770-775 passes; start them at AMISS / -AMISS (gritas.f:364-366) with minmax_init."""
+    nobs = len(lat)
+    if nobs == 0:
+        return
+    d = np.asfortranarray(np.asarray(del_, dtype=np.float64).reshape(nobs, -1, order="F"))
+    kxmax, ktmax = kxkt_table.shape
+    bad, badn = C.c_double(0.0), C.c_int(-1)
+    rc = lib().orc_minmax(g.im, g.jm, g.km, nlevs, nobs, d.shape[1], *_c(np.float64, lat, lon, lev), *_c(np.int32, kx, kt),
+                          d, np.asfortranarray(kxkt_table, dtype=np.int32), kxmax, ktmax, *_c(np.float64, p1, p2), ob_flag,
+                          g.l2d, g.bias_2d, g.stdv_2d, g.nobs_2d, g.l3d, g.bias_3d, g.stdv_3d, g.nobs_3d,
+                          C.byref(bad), C.byref(badn))
+    if rc == 7:
+        raise LevelMiss(bad.value, badn.value)
+    if rc:
+        raise ValueError("MinMax: could not handle more then 1 field")
+
+
+def minmax_init(g: Grids):
+    """gritas.f:364-366."""
+    for a in (g.bias_2d, g.bias_3d):
+        a[...] = AMISS
+    for a in (g.stdv_2d, g.stdv_3d):
+        a[...] = -AMISS
+
+
+def maskout(im, jm, lat, lon, maskfld, qcx):
+    """m_gritas_masks.F90:137-186; qcx int32 inout, returns the number of observations excluded."""
+    return lib().orc_maskout(im, jm, len(lat), *_c(np.float64, lat, lon), np.asfortranarray(maskfld, dtype=np.float64), qcx)

@@ -505,3 +505,73 @@ def test_fused_entry_all_residual_options(mode, iopt, options):
             assert np.allclose(out["bias_3d"], g.bias_3d, rtol=1e-9, atol=1e-9)
         else:
             H.compare(out, g, l2d, l3d, nr, exact=H.is_det(mode), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("mode", [cabi.MODE_FAST, cabi.MODE_DETERMINISTIC])
+def test_minmax_matches_oracle_exactly(mode):
+    """GrITAS_MinMax_ (m_gritas_grids.f:1019-1167, -minmax): min / max / count per box, surface and upper air;
+    min and max are order-free, so every mode must be bit-exact.  NaN residuals count but never win."""
+    cfg = synth.get_config("cfg1", 0.05)
+    cfg.im, cfg.jm = 72, 46
+    cfg.kt_list = [44, 4, 1, 2]
+    cfg.kx_lists = [[120, 130], [220], [181], [181, 187]]
+    files = []
+    for i in range(2):
+        c = synth.make_file(synth.get_config("cfg1", 0.05), i)
+        rng = np.random.default_rng(300 + i)
+        pairs = [(44, 120), (44, 130), (4, 220), (1, 181), (2, 181), (2, 187), (7, 120)]
+        pick = rng.integers(0, len(pairs), len(c["lat"]))
+        c["kt"] = np.asarray([p[0] for p in pairs], np.int32)[pick]
+        c["kx"] = np.asarray([p[1] for p in pairs], np.int32)[pick]
+        c["omf"][::53] = np.nan
+        c["omf"][1::211] = 0.0
+        c["omf"][2::211] = -0.0
+        files.append(c)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 1)
+    oracle.minmax_init(g)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode | cabi.FLAG_MINMAX)
+    for c in files:
+        fl = H.filter_in(c)
+        gfl = fl.copy()
+        oracle.minmax(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], c["omf"], table, p1, p2, fl)
+        G.GrITAS_MinMax(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], np.asfortranarray(c["omf"].reshape(-1, 1)),
+                        len(fl), 1, table, p1, p2, gfl, l2d, l3d=l3d)
+        assert np.array_equal(gfl, fl)
+    out = G.alloc_grids()
+    G.get_minmax(out["bias_2d"], out["stdv_2d"], out["nobs_2d"], out["bias_3d"], out["stdv_3d"], out["nobs_3d"])
+    with pytest.raises(RuntimeError):
+        G.norm_into(G.alloc_grids())           # the driver never calls Norm with -minmax (gritas.f:884)
+    G.close()
+    for nm in ("bias_2d", "stdv_2d", "nobs_2d", "bias_3d", "stdv_3d", "nobs_3d"):
+        assert np.array_equal(out[nm], getattr(g, nm)), nm
+    assert (out["bias_3d"] == oracle.AMISS).any() and (out["stdv_3d"] == -oracle.AMISS).any()
+    with pytest.raises(Exception):
+        Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.FLAG_MINMAX)._ensure(2, table, p1, p2, l2d, l3d)
+
+
+@pytest.mark.parametrize("mode", H.MODES)
+def test_mask_gather_matches_maskout(mode):
+    """gritas_maskout (m_gritas_masks.F90:137-186) fused into the accumulate kernels."""
+    cfg, files = small("cfg2", 0.05, 2)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    rng = np.random.default_rng(5)
+    maskfld = np.asfortranarray(rng.choice([0.0, 0.5, 0.98999, 0.99, 1.0], size=(cfg.im, cfg.jm)))
+    g = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 2)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    G._ensure(2, table, p1, p2, l2d, l3d)
+    G.set_mask(maskfld)
+    for c in files:
+        fl = H.filter_in(c, 101)
+        nex = oracle.maskout(cfg.im, cfg.jm, c["lat"], c["lon"], maskfld, fl)       # gritas.f:745
+        assert 0 < nex < len(fl)
+        oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 2), table, p1, p2, fl)
+        gfl = np.full(len(fl), -9, np.int32)
+        G.accum_ods(c, iopt=101, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD, ob_flag_out=gfl)
+        assert np.array_equal(gfl, fl)
+    oracle.norm(g, cfg.nlevs, True, 0)
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.set_mask(None)
+    G.close()
+    H.compare(out, g, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
