@@ -41,7 +41,7 @@ SYMBOLS = [
     "gritas_b200_accum_ods", "gritas_b200_accum_odsx", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_device",
     "gritas_b200_get_raw", "gritas_b200_get_minmax", "gritas_b200_set_mask", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
     "gritas_b200_allreduce", "gritas_b200_norm_reduce", "gritas_b200_norm_reduce_device", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
-    "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_tiled", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
+    "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_tiled", "gritas_b200_fused_norm", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
     "gritas_b200_d2h_bytes", "gritas_b200_version",
 ]
 
@@ -103,10 +103,12 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_stream.argtypes = [_P]
     L.gritas_b200_stream.restype = _P
     L.gritas_b200_set_stream.argtypes = [_P, _P]
-    for nm in ("gritas_b200_tiled", "gritas_b200_launch_count", "gritas_b200_h2d_bytes", "gritas_b200_d2h_bytes"):
+    for nm in ("gritas_b200_tiled", "gritas_b200_fused_norm", "gritas_b200_launch_count", "gritas_b200_h2d_bytes", "gritas_b200_d2h_bytes"):
         getattr(L, nm).argtypes = [_P]
         getattr(L, nm).restype = C.c_uint64
     L.gritas_b200_tiled.argtypes = [_P]
+    L.gritas_b200_fused_norm.argtypes = [_P]
+    L.gritas_b200_fused_norm.restype = C.c_int
     L.gritas_b200_version.argtypes = []
     _lib = L
     return L

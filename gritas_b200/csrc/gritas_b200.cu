@@ -109,6 +109,8 @@ struct gritas_b200_ctx {
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
   size_t tile_smem = 0, p1_smem = 0, p2_smem = 0;
+  size_t tf_smem = 0;            // K2f (fused tile accumulate + finalize); 0: not available
+  int tf_ctas = 148;
   int tile_ctas = 0;
   size_t scratch_cap = 0;         // slots allocated for the level-1 scratch (nbuckets * nbatch_cap * c1)
   // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
@@ -365,6 +367,29 @@ int flush_stage(gritas_b200_handle h) {
   h->staged_upper = 0;
   h->acc_fresh = false;
   return mark_main(h);
+}
+
+// K2f: Norm / get_raw straight from the tile lists (+ the records if anything was flushed into them).
+template <int NR>
+void launch_tile_final(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
+                       int raw2, int raw3) {
+  k_tile_final<NR><<<h->tf_ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, ntr,
+                                                                          raw2, raw3, h->acc_fresh ? 1 : 0);
+}
+
+bool fused_norm_ok(gritas_b200_handle h) {
+  return h->staging && h->tf_smem != 0 && h->staged_upper > 0 && !h->minmax;
+}
+
+// Host side of every reader of the accumulators: copies done, lists flushed unless the reader consumes them itself
+// (K2f), level misses reported.
+int settle(gritas_b200_handle h, bool keep_lists, double *bad_lev) {
+  CU(cudaStreamSynchronize(h->copy));
+  if (!keep_lists) {
+    int rc = flush_stage(h);
+    if (rc) return rc;
+  }
+  return drain(h, bad_lev);
 }
 
 template <int NR>
@@ -741,6 +766,19 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
           q.nbuckets = h->sg.nbuckets; q.bucket_shift = h->sg.bucket_shift;
         }
         h->staging = true;
+        {  // K2f (fused tile accumulate + finalize): one CTA per SM with the sum planes and a sort chunk in shared memory
+          const size_t tf = nr == 1 ? TileFinal<1>::smem_bytes(T) : (nr == 2 ? TileFinal<2>::smem_bytes(T) : TileFinal<3>::smem_bytes(T));
+          const char *e_f = getenv("GRITAS_B200_FUSED_NORM");
+          if (tf <= (size_t)227 * 1024 && shift <= 15 && !(e_f && atoi(e_f) == 0)) {
+            if (nr == 1) CUC(cudaFuncSetAttribute(k_tile_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
+            else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_final<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
+            else CUC(cudaFuncSetAttribute(k_tile_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
+            h->tf_smem = tf;
+            int nsm = 148;
+            CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+            h->tf_ctas = (int)std::min((size_t)nsm, ntiles);
+          }
+        }
         if (h->flags & GRITAS_B200_FLAG_FORCE_TILED) h->tiled_choice = 1;
         if (e_on && atoi(e_on) == 1) h->tiled_choice = 1;
       }
@@ -993,9 +1031,16 @@ int gritas_b200_reset(gritas_b200_handle h) {
   int rc = check_handle(h);
   if (rc) return rc;
   if ((rc = join_workers(h))) return rc;
+  if (h->minmax) {
+    k_minmax_init<<<grid_for(h->nrec, 256, 8), 256, 0, h->compute>>>(h->g.acc, h->nrec);
+  } else if (h->staging && h->acc_fresh) {
+    // nothing was flushed into the records since they were last zeroed: only a list overflow can have touched them
+    k_zero_if_dirty<<<148 * 8, 256, 0, h->compute>>>(h->g.acc, h->nrec * (size_t)h->g.rs, h->sg.dirty);
+    h->launches++;
+  } else {
+    CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
+  }
   h->acc_fresh = true;
-  if (h->minmax) k_minmax_init<<<grid_for(h->nrec, 256, 8), 256, 0, h->compute>>>(h->g.acc, h->nrec);
-  else CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   if (h->staging) {
     const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
     CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * (nfill + 4), h->compute));   // counters and the dirty word
@@ -1086,7 +1131,20 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   }
   const int ntr = ntresh < 0 ? 0 : ntresh;
   const int nrows = n3 ? g.jm * g.l3d : 0;
-  if (!piped) {
+  if (!piped && raw != 2 && fused_norm_ok(h)) {
+    int rc = join_workers(h);
+    if (rc) return rc;
+    const OutPlanes o2 = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
+    const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && !raw) ? 1 : xpl};
+    switch (nr) {
+      case 1: launch_tile_final<1>(h, h->compute, o2, o3, nrmlz, ntr, raw, raw3 ? 1 : 0); break;
+      case 2: launch_tile_final<2>(h, h->compute, o2, o3, nrmlz, ntr, raw, raw3 ? 1 : 0); break;
+      default: launch_tile_final<3>(h, h->compute, o2, o3, nrmlz, ntr, raw, raw3 ? 1 : 0); break;
+    }
+    CU(cudaGetLastError());
+    h->launches++;
+    if ((rc = mark_main(h))) return rc;     // later partition kernels append to the lists this kernel reads
+  } else if (!piped) {
     int rc = launch_finalize(h, h->compute, dst, raw, raw3, xpl, nrmlz, ntr, 0, nrows, true);
     if (rc) return rc;
   } else {
@@ -1156,7 +1214,7 @@ int gritas_b200_norm(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2
                      double *xcov_3d, double *nobs_3d) {
   int rc = check_handle(h);
   if (rc) return rc;
-  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
   double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
   return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
 }
@@ -1167,7 +1225,7 @@ int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const d
                             const double **xcov_3d, const double **nobs_3d) {
   int rc = check_handle(h);
   if (rc) return rc;
-  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
   double *const u[10] = {};
   const double *d[10] = {};
   rc = finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, d);
@@ -1189,7 +1247,7 @@ int gritas_b200_norm_reduce(gritas_b200_handle h, int root, int nrmlz, int ntres
   CU(cudaStreamSynchronize(h->copy));
   double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
   if (h->nranks == 1 || !h->comm) {
-    if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+    if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
     return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
   }
   return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr, root);
@@ -1202,7 +1260,7 @@ int gritas_b200_norm_reduce_device(gritas_b200_handle h, int root, int nrmlz, in
   CU(cudaStreamSynchronize(h->copy));
   double *const u[10] = {};
   if (h->nranks == 1 || !h->comm) {
-    if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+    if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
     return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10);
   }
   return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10, root);
@@ -1212,7 +1270,7 @@ int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, 
                         double *bias_3d, double *rtms_3d, double *xcov_3d, double *nobs_3d) {
   int rc = check_handle(h);
   if (rc) return rc;
-  if ((rc = gritas_b200_sync(h, nullptr))) return rc;
+  if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
   double *const u[10] = {bias_2d, rtms_2d, nullptr, xcov_2d, nobs_2d, bias_3d, rtms_3d, nullptr, xcov_3d, nobs_3d};
   return finalize_to(h, 1, 0, 0, u, nullptr);
 }
@@ -1418,6 +1476,7 @@ int gritas_b200_set_stream(gritas_b200_handle h, void *stream) {
 }
 
 int gritas_b200_tiled(gritas_b200_handle h) { return (h && h->staging) ? h->tiled_choice : 0; }
+int gritas_b200_fused_norm(gritas_b200_handle h) { return (h && fused_norm_ok(h)) ? 1 : 0; }
 uint64_t gritas_b200_launch_count(gritas_b200_handle h) { return h ? h->launches : 0; }
 uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h) { return h ? h->h2d : 0; }
 uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h) { return h ? h->d2h : 0; }

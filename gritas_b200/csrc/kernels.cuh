@@ -1536,4 +1536,240 @@ k_add_raw(const GridDesc g, OutPlanes in, int is3d) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2f: tile accumulate FUSED with finalize -- what GrITAS_Norm runs when the month is still parked in the
+// tile lists (one process, no reduction across ranks).  One CTA per tile, nothing is written but the output
+// planes: the records (1.7 GB at cfg2) are neither written by a flush nor read back by K3, and the lists
+// stay as they are (Norm does not change the accumulation state).
+//
+// No floating-point atomics: shared memory has no native fp64 add (k_tile_accum spends its time in CAS
+// loops).  Instead every chunk of the list is counting-sorted by box inside the CTA -- one native int32
+// shared-memory atomic per entry gives the entry its rank within the box, a scan of the per-box counts gives
+// the box's start, the residuals are dropped into shared memory at start + rank -- and the thread that owns
+// a box then adds the box's run with plain DADDs into the tile's sum planes.  The planes double as the
+// transposition buffer: the finalize step walks the tile level by level (the records are level-fastest, the
+// reference's arrays longitude-fastest) and writes each plane in runs of ~tile/km consecutive doubles.
+template <int NR>
+struct TileFinal {
+  static constexpr int THREADS = 1024;
+  static constexpr int EPT = (NR == 3) ? 4 : 6;           // entries per thread and chunk
+  static constexpr int CH = EPT * THREADS;                // chunk of the list sorted at a time
+  static constexpr int NV = TilePlanes<NR>::NV;
+  __host__ __device__ static constexpr size_t smem_bytes(size_t T) {
+    return sizeof(double) * ((size_t)NV * T + (size_t)NR * CH) + sizeof(unsigned) * (2 * T + 4 + 32);
+  }
+};
+
+template <int NR>
+__global__ void __launch_bounds__(TileFinal<NR>::THREADS, 1)
+k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh,
+             int raw2, int raw3, int fresh) {
+  using TF = TileFinal<NR>;
+  constexpr int NV = TF::NV, EPT = TF::EPT, CH = TF::CH, NTH = TF::THREADS;
+  extern __shared__ __align__(16) double s_dyn[];
+  const unsigned T = 1u << sg.tile_shift;
+  double *s_val = s_dyn;                                   // [NV][T] sums of the tile
+  double *s_stage = s_val + (size_t)NV * T;                // [NR][CH] residuals of the chunk, sorted by box
+  unsigned *s_tot = reinterpret_cast<unsigned *>(s_stage + (size_t)NR * CH);   // [T] entries per box so far
+  unsigned *s_cnt = s_tot + T;                             // [T+1] chunk: count per box, then exclusive start
+  unsigned *s_warp = s_cnt + T + 4;                        // [32]
+  const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
+  // records untouched since the reset (no flush, no direct accumulate): they are zero, do not read them
+  const bool addrec = !fresh || (*reinterpret_cast<volatile unsigned *>(sg.dirty) != 0u);
+  const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
+  for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
+    const unsigned n = min(sg.fill[tile], sg.cap);
+    const size_t base = (size_t)tile * sg.cap;
+    {  // the list of the tile this SM will probably get next: ask L2 for it now
+      const unsigned nt = tile + gridDim.x;
+      if (nt < sg.ntiles && tid < 32u * (1 + NR)) {
+        const unsigned nn = min(sg.fill[nt], sg.cap);
+        const size_t nbase = (size_t)nt * sg.cap;
+        const unsigned col = wid;                           // 0: keys, 1..NR: residual columns
+        const unsigned esz = col ? 8u : 4u;
+        const unsigned per = ((nn + 31u) / 32u + 3u) & ~3u;  // entries per lane, 16-byte multiples
+        const unsigned e0 = lane * per;
+        if (e0 < nn) {
+          const unsigned cntp = min(per, nn - e0);
+          const char *p = reinterpret_cast<const char *>(sg.skey + nbase + e0);
+#pragma unroll
+          for (int ir = 0; ir < NR; ++ir)                     // no dynamic index into the kernel parameters
+            if (col == (unsigned)ir + 1u) p = reinterpret_cast<const char *>(sg.sd[ir] + nbase + e0);
+          prefetch_l2_bulk(p, cntp * esz);
+        }
+      }
+    }
+    for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = 0.0;
+    for (unsigned e = tid; e < T; e += NTH) s_tot[e] = 0u;
+    for (unsigned c0 = 0; c0 < n; c0 += CH) {
+      for (unsigned e = tid; e <= T; e += NTH) s_cnt[e] = 0u;
+      __syncthreads();
+      // ---- rank of every entry within its box ----
+      unsigned pk[EPT];
+      double d[EPT][NR];
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const unsigned e = c0 + (unsigned)u * NTH + tid;
+        const unsigned key = (e < n) ? __ldcs(sg.skey + base + e) : KEY_NONE;
+        pk[u] = (key == KEY_NONE) ? KEY_NONE : (key & (T - 1u));
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) d[u][ir] = (e < n) ? __ldcs(sg.sd[ir] + base + e) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < EPT; ++u)
+        if (pk[u] != KEY_NONE) pk[u] |= atomicAdd(s_cnt + pk[u], 1u) << 16;
+      __syncthreads();
+      // ---- exclusive scan of the counts (in place); s_cnt[T] = entries of the chunk ----
+      {
+        unsigned sum = 0u;
+        for (unsigned q = 0; q < PT; ++q) {
+          const unsigned i = tid * PT + q;
+          if (i < T) sum += s_cnt[i];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31u) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0u) {
+          const unsigned w = s_warp[lane];
+          unsigned wi = w;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (unsigned)o) wi += t;
+          }
+          s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        unsigned excl = incl - sum + s_warp[wid];
+        for (unsigned q = 0; q < PT; ++q) {
+          const unsigned i = tid * PT + q;
+          if (i < T) {
+            const unsigned c = s_cnt[i];
+            s_cnt[i] = excl;
+            excl += c;
+          }
+        }
+        if (tid == NTH - 1u) s_cnt[T] = excl;
+      }
+      __syncthreads();
+      // ---- residuals to start(box) + rank ----
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        if (pk[u] == KEY_NONE) continue;
+        const unsigned pos = s_cnt[pk[u] & 0xFFFFu] + (pk[u] >> 16);
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + pos] = d[u][ir];
+      }
+      __syncthreads();
+      // ---- the owner of a box adds its run ----
+      for (unsigned b = tid; b < T; b += NTH) {
+        const unsigned s = s_cnt[b], e = s_cnt[b + 1u];
+        if (e == s) continue;
+        double a[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) a[q] = 0.0;
+        for (unsigned p = s; p < e; ++p) {
+          double x[NR];
+#pragma unroll
+          for (int ir = 0; ir < NR; ++ir) x[ir] = s_stage[(size_t)ir * CH + p];
+          if (NR == 2) {
+            a[0] = __dadd_rn(a[0], x[0]); a[1] = __dadd_rn(a[1], __dmul_rn(x[0], x[0]));
+            a[2] = __dadd_rn(a[2], x[NR - 1]); a[3] = __dadd_rn(a[3], __dmul_rn(x[NR - 1], x[NR - 1]));
+            a[4] = __dadd_rn(a[4], __dmul_rn(x[0], x[NR - 1]));
+          } else {
+#pragma unroll
+            for (int ir = 0; ir < NR; ++ir) {
+              a[2 * ir] = __dadd_rn(a[2 * ir], x[ir]);
+              a[2 * ir + 1] = __dadd_rn(a[2 * ir + 1], __dmul_rn(x[ir], x[ir]));
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) s_val[(size_t)q * T + b] = __dadd_rn(s_val[(size_t)q * T + b], a[q]);
+        s_tot[b] += e - s;
+      }
+      // the next chunk zeroes s_cnt: every owner must be done with it
+      __syncthreads();
+    }
+    __syncthreads();
+    // ---- finalize (m_gritas_grids.f:566-654) straight from the planes ----
+    const size_t first = (size_t)tile << sg.tile_shift;
+    const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
+    auto box = [&](unsigned b, bool is3d, bool zero, int raw, const OutPlanes &out, size_t o, size_t plane) {
+      double r[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[q] = 0.0;
+      if (!zero) {
+        r[0] = (double)s_tot[b];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) r[1 + q] = s_val[(size_t)q * T + b];
+        if (addrec) {
+          const double *rec = g.acc + (first + b) * (size_t)g.rs;
+          const double2 a0 = *reinterpret_cast<const double2 *>(rec), a1 = *reinterpret_cast<const double2 *>(rec + 2);
+          r[0] = __dadd_rn(a0.x, r[0]); r[1] = __dadd_rn(a0.y, r[1]); r[2] = __dadd_rn(a1.x, r[2]);
+          if (NR > 1) {
+            const double2 a2 = *reinterpret_cast<const double2 *>(rec + 4), a3 = *reinterpret_cast<const double2 *>(rec + 6);
+            r[3] = __dadd_rn(a1.y, r[3]); r[4] = __dadd_rn(a2.x, r[4]); r[5] = __dadd_rn(a2.y, r[5]);
+            if (NR > 2) r[6] = __dadd_rn(a3.x, r[6]);
+          }
+        }
+      }
+      double bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs = 0.0;
+      if (zero) {
+#pragma unroll
+        for (int ir = 0; ir < NR; ++ir) { bias[ir] = 0.0; rtms[ir] = 0.0; stdv[ir] = 0.0; xcov[ir] = 0.0; }
+      } else {
+        finalize_box<NR>(r, is3d, nrmlz, ntresh, raw, bias, rtms, stdv, xcov, nobs);
+      }
+#pragma unroll
+      for (int ir = 0; ir < NR; ++ir) {
+        if (out.bias) __stcs(out.bias + o + plane * ir, bias[ir]);
+        if (out.rtms) __stcs(out.rtms + o + plane * ir, rtms[ir]);
+        if (out.stdv) __stcs(out.stdv + o + plane * ir, stdv[ir]);
+        if (out.xcov && ir < out.xcov_planes) __stcs(out.xcov + o + plane * ir, xcov[ir]);
+      }
+      if (out.nobs) __stcs(out.nobs + o, nobs);
+    };
+    const size_t end3 = min(first + nb, plane3);
+    if (first < end3) {
+      // the tile's span of level-fastest records covers columns c0..c1 (column = i + im*(j + jm*l)); walk it level
+      // by level so that consecutive threads write consecutive longitudes
+      const unsigned km = (unsigned)g.km;
+      const size_t c0 = first / km, c1 = (end3 - 1) / km;
+      const unsigned ncol = (unsigned)(c1 - c0 + 1);
+      const unsigned head = (unsigned)(first - c0 * km), span = (unsigned)(end3 - first);
+      for (unsigned q = tid; q < ncol * km; q += NTH) {
+        const unsigned k = q / ncol, ci = q - k * ncol;
+        const unsigned rel = ci * km + k;
+        if (rel < head || rel - head >= span) continue;
+        const unsigned col = (unsigned)c0 + ci;               // < nbox3 / km: 32 bits
+        const unsigned i = col % (unsigned)g.im, jl = col / (unsigned)g.im;
+        const size_t j = jl % (unsigned)g.jm, l = jl / (unsigned)g.jm;
+        const size_t o = (size_t)i + (size_t)g.im * (j + (size_t)g.jm * ((size_t)k + (size_t)km * l));
+        box(rel - head, true, (int)k >= g.nlevs, raw3, o3, o, plane3);   // levels nlevs..km-1: never touched, zeros
+      }
+    }
+    for (size_t rec = max(first, plane3) + tid; rec < first + nb; rec += NTH)
+      box((unsigned)(rec - first), false, false, raw2, o2, rec - plane3, plane2);
+    __syncthreads();
+  }
+}
+
+// Reset when the records were never written since the last reset (everything parked in the tile lists or consumed
+// by K2f): only a list overflow (direct accumulate, sg.dirty) can have touched them.
+__global__ void __launch_bounds__(256)
+k_zero_if_dirty(double *__restrict__ acc, size_t ndouble, const unsigned *__restrict__ dirty) {
+  if (*dirty == 0u) return;
+  double2 *a2 = reinterpret_cast<double2 *>(acc);
+  const size_t n2 = ndouble >> 1;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x)
+    a2[e] = make_double2(0.0, 0.0);
+}
+
 }  // namespace gb200

@@ -219,6 +219,7 @@ const char *gritas_b200_last_error(gritas_b200_handle h);
 void *gritas_b200_stream(gritas_b200_handle h);              /* cudaStream_t of the compute stream */
 int gritas_b200_set_stream(gritas_b200_handle h, void *stream); /* run on a caller-owned stream */
 int gritas_b200_tiled(gritas_b200_handle h);                 /* fast mode: 1 tiled accumulate, 0 direct, -1 undecided */
+int gritas_b200_fused_norm(gritas_b200_handle h);            /* 1: the next Norm / get_raw consumes the tile lists itself (K2f: tile accumulate fused with finalize) */
 uint64_t gritas_b200_launch_count(gritas_b200_handle h);     /* kernels launched so far */
 uint64_t gritas_b200_h2d_bytes(gritas_b200_handle h);        /* bytes copied host->device so far */
 uint64_t gritas_b200_d2h_bytes(gritas_b200_handle h);        /* bytes copied device->host so far */

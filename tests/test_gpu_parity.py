@@ -575,3 +575,61 @@ def test_mask_gather_matches_maskout(mode):
     G.set_mask(None)
     G.close()
     H.compare(out, g, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("nr", [1, 2])
+def test_fused_norm_consumes_the_tile_lists_without_changing_the_state(nr, monkeypatch):
+    """Tiled path, one rank: GrITAS_Norm runs K2f (tile accumulate fused with finalize) on the parked lists.  It must
+    (a) agree with the oracle, (b) be repeatable -- Norm does not change the accumulation state, (c) let the
+    accumulation continue afterwards, (d) agree with the unfused path (flush into the records, then K3), including when
+    part of the data was already flushed into the records, and (e) honour a reset."""
+    cfg, files = small("cfg2", 0.05, 4)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    mode = cabi.MODE_FAST | cabi.FLAG_FORCE_TILED
+    L = cabi.load()
+
+    def accum(G, fs):
+        for c in fs:
+            G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, nr), len(c["lat"]), nr, table, p1, p2,
+                           None, l2d, l3d=l3d)
+
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    accum(G, files[:2])
+    assert L.gritas_b200_fused_norm(G.handle) == 1
+    a, b = G.alloc_grids(), G.alloc_grids()
+    G.norm_into(a)
+    assert L.gritas_b200_fused_norm(G.handle) == 1            # the lists are still there
+    G.norm_into(b)
+    ref2, _ = H.oracle_run(cfg, files[:2], nr)
+    H.compare(a, ref2, l2d, l3d, nr, exact=False, tol=TOL_FAST)
+    for nm in H.NAMES:
+        if nm.startswith("nobs"):
+            assert np.array_equal(a[nm], b[nm]), nm
+        else:                                                  # the order of the additions inside a box is not fixed
+            assert np.allclose(a[nm], b[nm], rtol=1e-9, atol=1e-9, equal_nan=True), nm
+    G.flush()                                                  # half of the month now sits in the records
+    assert L.gritas_b200_fused_norm(G.handle) == 0
+    accum(G, files[2:])
+    assert L.gritas_b200_fused_norm(G.handle) == 1
+    c4 = G.alloc_grids()
+    G.norm_into(c4)                                            # K2f adds the records to the tile sums
+    ref4, _ = H.oracle_run(cfg, files, nr)
+    H.compare(c4, ref4, l2d, l3d, nr, exact=False, tol=TOL_FAST)
+    raw = G.alloc_grids()
+    G.get_raw(raw["bias_2d"] if l2d else None, raw["rtms_2d"] if l2d else None, raw["xcov_2d"] if l2d else None,
+              raw["nobs_2d"] if l2d else None, raw["bias_3d"] if l3d else None, raw["rtms_3d"] if l3d else None,
+              raw["xcov_3d"] if l3d else None, raw["nobs_3d"] if l3d else None)
+    refraw, _ = H.oracle_run(cfg, files, nr, norm=False)
+    H.compare(raw, refraw, l2d, l3d, nr, exact=False, tol=TOL_FAST, raw=True)
+    G.reset()
+    accum(G, files[:1])
+    r1 = G.alloc_grids()
+    G.norm_into(r1)
+    ref1, _ = H.oracle_run(cfg, files[:1], nr)
+    H.compare(r1, ref1, l2d, l3d, nr, exact=False, tol=TOL_FAST)
+    G.close()
+    # unfused path on the same data
+    monkeypatch.setenv("GRITAS_B200_FUSED_NORM", "0")
+    out, _ = H.gpu_run(cfg, files, nr, mode, want_flags=False)
+    assert np.array_equal(out["nobs_3d"], c4["nobs_3d"])
+    H.compare(out, ref4, l2d, l3d, nr, exact=False, tol=TOL_FAST)
