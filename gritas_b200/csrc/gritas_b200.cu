@@ -703,8 +703,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         h->tile_smem = smem;
         h->tile_ctas = (int)std::min(ntiles, (size_t)1 << 20);
         const size_t nfill = nbuckets * tpb;              // padded: every (bucket, local tile) has a counter
-        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * (nfill + 4)));   // + the dirty word
-        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * (nfill + 4)));
+        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * 2 * nfill));   // + the per-tile dirty words
+        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * 2 * nfill));
         h->sg.dirty = h->sg.fill + nfill;
         // level-1 scratch: one run of c1 slots per (bucket, K1p batch), mirrored by a shared-memory bin in K1p;
         // c1 = power of two >= 1.5x the mean run when every observation is accepted (fuller bins overflow
@@ -1035,7 +1035,7 @@ int gritas_b200_reset(gritas_b200_handle h) {
     k_minmax_init<<<grid_for(h->nrec, 256, 8), 256, 0, h->compute>>>(h->g.acc, h->nrec);
   } else if (h->staging && h->acc_fresh) {
     // nothing was flushed into the records since they were last zeroed: only a list overflow can have touched them
-    k_zero_if_dirty<<<148 * 8, 256, 0, h->compute>>>(h->g.acc, h->nrec * (size_t)h->g.rs, h->sg.dirty);
+    k_zero_dirty_tiles<<<148 * 8, 256, 0, h->compute>>>(h->g.acc, h->nrec * (size_t)h->g.rs, h->g.rs, h->sg);
     h->launches++;
   } else {
     CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
@@ -1043,7 +1043,7 @@ int gritas_b200_reset(gritas_b200_handle h) {
   h->acc_fresh = true;
   if (h->staging) {
     const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
-    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * (nfill + 4), h->compute));   // counters and the dirty word
+    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * 2 * nfill, h->compute));   // counters and the dirty words
     h->staged_upper = 0;
   }
   return mark_main(h);

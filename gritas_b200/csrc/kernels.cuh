@@ -88,7 +88,8 @@ struct StageDesc {
   double *sd[3];       // [ntiles * cap] per residual column
   unsigned cap, ntiles;
   int tile_shift;
-  unsigned *dirty;     // set when an entry was accumulated directly (list overflow): the records are no longer all zero
+  unsigned *dirty;     // [ntiles (padded)] set when an entry of the tile was accumulated directly (bin / list overflow):
+                       // the tile's records are no longer all zero
   // level 1: scratch of the current Accum call, one fixed run of c1 slots per (bucket, K1p batch): no
   // global tickets (same-address atomics serialise at ~60 ns each on B200).  A bucket is
   // 2^(bucket_shift-tile_shift) tiles.  The scratch is small enough to stay in L2 between K1p and K1q.
@@ -1037,7 +1038,7 @@ k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
         const unsigned rank = atomicAdd(s_cnt + b, 1u);
         if (rank >= sg.c1) {
           red_entry<NR>(g, key, d);     // the bin of this bucket is full: accumulate directly
-          *sg.dirty = 1u;
+          sg.dirty[key >> sg.tile_shift] = 1u;
         } else {
           const unsigned slot = (b << sg.c1_shift) + rank;
           s_key[slot] = key;
@@ -1165,7 +1166,7 @@ k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
         const unsigned t = (key >> sg.tile_shift) & tmask;
         if (v.run[t] == PB_OVERFLOW) {
           red_entry<NR>(g, key, d);
-          *sg.dirty = 1u;
+          sg.dirty[key >> sg.tile_shift] = 1u;
         } else {
           const unsigned at = v.off[t] + atomicAdd(v.cnt2 + t, 1u);
           v.key[at] = key;
@@ -1239,10 +1240,10 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0
   unsigned *s_cnt = reinterpret_cast<unsigned *>(s_val + (size_t)NV * T);
   const int rs_shift = (g.rs == 4) ? 2 : 3;
   // first flush after a reset and nothing was accumulated directly: the records are zero, store instead of RMW
-  const bool overwrite = fresh && (*reinterpret_cast<volatile unsigned *>(sg.dirty) == 0u);
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
     if (n == 0) continue;                                 // uniform across the CTA
+    const bool overwrite = fresh && sg.dirty[tile] == 0u;
     for (unsigned e = threadIdx.x; e < NV * T; e += blockDim.x) s_val[e] = 0.0;
     for (unsigned e = threadIdx.x; e < T; e += blockDim.x) s_cnt[e] = 0u;
     __syncthreads();
@@ -1323,9 +1324,10 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0
         if (e < npair) {
           const unsigned el = e << 1, bxi = el >> rs_shift, slot = el & ((1u << rs_shift) - 1u);
           const unsigned cn = s_cnt[bxi];
-          if (cn != 0u && slot <= (unsigned)NV) {
+          // overwrite: the pad slots are stored too (zeros), so that only whole 32-byte sectors reach L2
+          if (cn != 0u && (overwrite || slot <= (unsigned)NV)) {
             any[u] = true;
-            add[u].x = (slot == 0u) ? (double)cn : s_val[(size_t)(slot - 1u) * T + bxi];
+            add[u].x = (slot == 0u) ? (double)cn : (slot <= (unsigned)NV ? s_val[(size_t)(slot - 1u) * T + bxi] : 0.0);
             add[u].y = (slot + 1u <= (unsigned)NV) ? s_val[(size_t)slot * T + bxi] : 0.0;
             cur[u] = overwrite ? make_double2(0.0, 0.0) : span[e];
           }
@@ -1415,19 +1417,16 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
     for (int ir = 0; ir < NR; ++ir) { bias[ir] = AMISS; rtms[ir] = AMISS; tmp[ir] = 0.0; }
     xcov[0] = AMISS;
   }
-  if (many) {
+  // many: sqrt(m*tmp/(m-1)); a single observation in a 3-D box: sqrt(tmp) (m_gritas_grids.f:642-644, the 2-D branch
+  // has no such case); otherwise AMISS.  One square root per column serves both cases (a warp usually holds both).
+  const bool one = !many && is3d && n == 1.0;
 #pragma unroll
-    for (int ir = 0; ir < NR; ++ir) stdv[ir] = __dsqrt_rn(div_m1(__dmul_rn(dm, tmp[ir])));
-    xcov[nx - 1] = div_m1(__dmul_rn(dm, xtmp));
-  } else if (is3d && n == 1.0) {  // m_gritas_grids.f:642-644 (the 2-D branch has no such case)
-#pragma unroll
-    for (int ir = 0; ir < NR; ++ir) stdv[ir] = __dsqrt_rn(tmp[ir]);
-    xcov[nx - 1] = xtmp;
-  } else {
-#pragma unroll
-    for (int ir = 0; ir < NR; ++ir) stdv[ir] = AMISS;
-    xcov[nx - 1] = AMISS;
+  for (int ir = 0; ir < NR; ++ir) {
+    const double arg = many ? div_m1(__dmul_rn(dm, tmp[ir])) : tmp[ir];
+    const double sq = __dsqrt_rn(arg);
+    stdv[ir] = (many || one) ? sq : AMISS;
   }
+  xcov[nx - 1] = many ? div_m1(__dmul_rn(dm, xtmp)) : (one ? xtmp : AMISS);
 }
 
 // 3-D: tile of 32 levels x 32 longitudes for one (j,l).  Records are read level-fastest (the HBM
@@ -1575,12 +1574,13 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   unsigned *s_warp = s_cnt + T + 4;                        // [32]
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
-  // records untouched since the reset (no flush, no direct accumulate): they are zero, do not read them
-  const bool addrec = !fresh || (*reinterpret_cast<volatile unsigned *>(sg.dirty) != 0u);
+  const unsigned PB = (T >= 2u * NTH) ? 2u : 1u;           // boxes per owner stretch
   const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
   for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
     const size_t base = (size_t)tile * sg.cap;
+    // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
+    const bool addrec = !fresh || sg.dirty[tile] != 0u;
     {  // the list of the tile this SM will probably get next: ask L2 for it now
       const unsigned nt = tile + gridDim.x;
       if (nt < sg.ntiles && tid < 32u * (1 + NR)) {
@@ -1667,32 +1667,52 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
         for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + pos] = d[u][ir];
       }
       __syncthreads();
-      // ---- the owner of a box adds its run ----
-      for (unsigned b = tid; b < T; b += NTH) {
-        const unsigned s = s_cnt[b], e = s_cnt[b + 1u];
-        if (e == s) continue;
+      // ---- the owner of a box adds its run.  A thread owns PB consecutive boxes, i.e. one contiguous stretch of the
+      // sorted chunk: one loop over the stretch (run lengths vary; the sum over PB boxes varies less) ----
+      for (unsigned b0 = tid * PB; b0 < T; b0 += NTH * PB) {
+        unsigned p = s_cnt[b0];
+        const unsigned pend = s_cnt[b0 + PB];
+        if (p == pend) continue;
+        unsigned b = b0, bend = s_cnt[b0 + 1u];
         double a[NV];
 #pragma unroll
         for (int q = 0; q < NV; ++q) a[q] = 0.0;
-        for (unsigned p = s; p < e; ++p) {
+        unsigned cn = 0u;
+        auto put = [&]() {
+          if (cn) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              s_val[(size_t)q * T + b] = __dadd_rn(s_val[(size_t)q * T + b], a[q]);
+              a[q] = 0.0;
+            }
+            s_tot[b] += cn;
+            cn = 0u;
+          }
+        };
+        for (; p < pend; ++p) {
+          while (p >= bend) {                               // next box of the stretch (empty boxes are skipped)
+            put();
+            ++b;
+            bend = s_cnt[b + 1u];
+          }
           double x[NR];
 #pragma unroll
           for (int ir = 0; ir < NR; ++ir) x[ir] = s_stage[(size_t)ir * CH + p];
+          // fused multiply-adds: the squares are not rounded separately (fast mode is order-free anyway)
           if (NR == 2) {
-            a[0] = __dadd_rn(a[0], x[0]); a[1] = __dadd_rn(a[1], __dmul_rn(x[0], x[0]));
-            a[2] = __dadd_rn(a[2], x[NR - 1]); a[3] = __dadd_rn(a[3], __dmul_rn(x[NR - 1], x[NR - 1]));
-            a[4] = __dadd_rn(a[4], __dmul_rn(x[0], x[NR - 1]));
+            a[0] = __dadd_rn(a[0], x[0]); a[1] = __fma_rn(x[0], x[0], a[1]);
+            a[2] = __dadd_rn(a[2], x[NR - 1]); a[3] = __fma_rn(x[NR - 1], x[NR - 1], a[3]);
+            a[4] = __fma_rn(x[0], x[NR - 1], a[4]);
           } else {
 #pragma unroll
             for (int ir = 0; ir < NR; ++ir) {
               a[2 * ir] = __dadd_rn(a[2 * ir], x[ir]);
-              a[2 * ir + 1] = __dadd_rn(a[2 * ir + 1], __dmul_rn(x[ir], x[ir]));
+              a[2 * ir + 1] = __fma_rn(x[ir], x[ir], a[2 * ir + 1]);
             }
           }
+          ++cn;
         }
-#pragma unroll
-        for (int q = 0; q < NV; ++q) s_val[(size_t)q * T + b] = __dadd_rn(s_val[(size_t)q * T + b], a[q]);
-        s_tot[b] += e - s;
+        put();
       }
       // the next chunk zeroes s_cnt: every owner must be done with it
       __syncthreads();
@@ -1761,15 +1781,17 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   }
 }
 
-// Reset when the records were never written since the last reset (everything parked in the tile lists or consumed
-// by K2f): only a list overflow (direct accumulate, sg.dirty) can have touched them.
+// Reset when nothing was flushed into the records since the last reset (everything parked in the tile lists or
+// consumed by K2f): only tiles that took a direct accumulate (bin / list overflow, sg.dirty) hold anything.
 __global__ void __launch_bounds__(256)
-k_zero_if_dirty(double *__restrict__ acc, size_t ndouble, const unsigned *__restrict__ dirty) {
-  if (*dirty == 0u) return;
-  double2 *a2 = reinterpret_cast<double2 *>(acc);
-  const size_t n2 = ndouble >> 1;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x)
-    a2[e] = make_double2(0.0, 0.0);
+k_zero_dirty_tiles(double *__restrict__ acc, size_t ndouble, int rs, const StageDesc sg) {
+  for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
+    if (sg.dirty[tile] == 0u) continue;
+    const size_t first = ((size_t)tile << sg.tile_shift) * (size_t)rs;
+    const size_t n = min(((size_t)1 << sg.tile_shift) * (size_t)rs, ndouble - first);
+    double2 *a2 = reinterpret_cast<double2 *>(acc + first);
+    for (size_t e = threadIdx.x; e < (n >> 1); e += blockDim.x) a2[e] = make_double2(0.0, 0.0);
+  }
 }
 
 }  // namespace gb200
