@@ -108,21 +108,18 @@ struct gritas_b200_ctx {
   bool acc_fresh = true;       // records untouched since create / reset (apart from direct RED, see StageDesc::dirty)
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
-  size_t tile_smem = 0, p1_smem = 0, p2_smem = 0;
+  size_t tile_smem = 0;
   size_t tf_smem = 0;            // K2f (fused tile accumulate + finalize); 0: not available
   int tf_ctas = 148;
   int tile_ctas = 0;
-  size_t scratch_cap = 0;         // slots allocated for the level-1 scratch (nbuckets * nbatch_cap * c1)
   // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
   // the GPU; consecutive calls run on different streams (own level-1 scratch, own level-miss record) and
   // overlap.  Everything that reads or resets the accumulators runs on `compute` after join_workers().
   cudaStream_t wk[NWK] = {};
   cudaEvent_t wk_done[NWK] = {};
   bool wk_pending[NWK] = {};
-  StageDesc sgw[NWK] = {};
   int next_wk = 0;
   int nwk = 3;
-  bool p2_small = false;          // K1q round size 2048 (256 threads) instead of 4096 (512 threads)
   cudaEvent_t main_ev = nullptr;  // last accumulator-wide operation queued on `compute`
   // reduce + finalize pipeline (multi-GPU): chunk c is tile-accumulated on `compute`, reduced to the root on
   // `comm_stream`, finalized on `fin_stream` while later chunks are still being accumulated / reduced
@@ -318,27 +315,18 @@ void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, in
   }
 }
 
-// Tiled fast path, partition kernels of one slice of observations (K1p then K1q) on worker stream w.
+// Tiled fast path, K1 of one Accum call on worker stream w: every accepted observation -> one entry in its tile's list.
 template <int NR>
-void launch_partition(gritas_b200_handle h, int w, const ObsCols &c, const FilterDesc &f) {
-  const StageDesc &sg = h->sgw[w];
-  const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
-  const int g1 = std::min(nbatch, 148 * 3 * 4);
+void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDesc &f) {
+  const int nvec = (c.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
+  const int g1 = grid_for((size_t)nvec, K1_THREADS, 8);
+  const size_t smem = levtab_smem_bytes(h->g);
   Status *st = h->d_status + 1 + w;
   switch (filter_mode(f)) {
-    case 0: k_part_obs<NR, 0><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, sg); break;
-    case 1: k_part_obs<NR, 1><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, sg); break;
-    default: k_part_obs<NR, 2><<<g1, P1_THREADS, h->p1_smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, sg); break;
+    case 0: k_list_obs<NR, 0><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg); break;
+    case 1: k_list_obs<NR, 1><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg); break;
+    default: k_list_obs<NR, 2><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg); break;
   }
-  // K1q items: each bucket's runs in `parts` ranges of roughly 3800 entries (if everything were accepted)
-  const size_t per_bucket = (size_t)nbatch * P1_BATCH / sg.nbuckets;
-  const size_t per_part = h->p2_small ? 1900 : 3800;
-  const int parts = (int)std::max((size_t)1, (per_bucket + per_part - 1) / per_part);
-  const int g2 = std::min((int)sg.nbuckets * parts, 148 * (h->p2_small ? 4 : 2));
-  static const bool skip_q = getenv("GRITAS_B200_DEBUG_SKIP_K1Q") != nullptr;  // timing experiments only
-  if (skip_q) return;
-  if (h->p2_small) k_part_tiles<NR, 2048, 256><<<g2, 256, h->p2_smem, h->wk[w]>>>(h->g, sg, parts);
-  else k_part_tiles<NR, 4096, 512><<<g2, 512, h->p2_smem, h->wk[w]>>>(h->g, sg, parts);
 }
 
 // K2t over every tile with staged entries; afterwards the lists are empty.
@@ -445,37 +433,20 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     }
     h->launches += 1;
   } else if (tiled) {
-    // tiled path: partition this call's observations into the per-tile lists (slices bound the scratch)
-    const int SLICE = (int)h->sg.nbatch_cap * P1_BATCH;
-    for (int s0 = 0; s0 < n; s0 += SLICE) {
-      ObsCols cs = c;
-      cs.n = std::min(SLICE, n - s0);
-      cs.lat += s0; cs.lon += s0; cs.lev += s0; cs.kx += s0; cs.kt += s0;
-      for (int ir = 0; ir < h->g.nr; ++ir) cs.d[ir] += s0;
-      if (cs.obs) cs.obs += s0;
-      if (cs.xvec) cs.xvec += s0;
-      if (cs.omf) cs.omf += s0;
-      if (cs.flag) cs.flag += s0;
-      if (cs.time) cs.time += s0;
-      if (cs.flag_out) cs.flag_out += s0;
-      if (s0) h->call_seq += 1;  // the level-miss record is per launch
-      h->sgw[w].nbatch = (unsigned)(((size_t)cs.n + P1_BATCH - 1) / P1_BATCH);
-      // keep the expected tile-list fill at or below ~half the capacity; what still overflows (skewed data)
-      // is accumulated directly by the partition kernels
-      const size_t add = (size_t)cs.n + (size_t)cs.n / 4;  // entries + padding sentinels
-      if (h->staged_upper + add > h->stage_slots / 2) {
-        int rc = flush_stage(h);
-        if (rc) return rc;
-        CU(cudaStreamWaitEvent(run, h->main_ev, 0));
-      }
-      h->staged_upper += add;
-      switch (h->g.nr) {
-        case 1: launch_partition<1>(h, w, cs, f); break;
-        case 2: launch_partition<2>(h, w, cs, f); break;
-        default: launch_partition<3>(h, w, cs, f); break;
-      }
-      h->launches += 2;
+    // tiled path: append this call's accepted observations to the per-tile lists.  Keep the expected fill at or
+    // below ~half the capacity; what still overflows (skewed data) is accumulated directly by K1
+    if (h->staged_upper + (size_t)n > h->stage_slots / 2) {
+      int rc = flush_stage(h);
+      if (rc) return rc;
+      CU(cudaStreamWaitEvent(run, h->main_ev, 0));
     }
+    h->staged_upper += (size_t)n;
+    switch (h->g.nr) {
+      case 1: launch_lists<1>(h, w, c, f); break;
+      case 2: launch_lists<2>(h, w, c, f); break;
+      default: launch_lists<3>(h, w, c, f); break;
+    }
+    h->launches += 1;
   } else if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
     h->acc_fresh = false;
     const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
@@ -683,88 +654,30 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
       const size_t smem = (size_t)nv * T * 8 + T * 4;
       size_t free_b = 0, total_b = 0;
       CUC(cudaMemGetInfo(&free_b, &total_b));
-      const size_t entry = 4 + 8 * (size_t)nr;
+      const size_t entry = (nr == 1) ? ListEntry<1>::BYTES : ListEntry<2>::BYTES;
       size_t slots = e_slots ? (size_t)atoll(e_slots) : std::min((size_t)384 << 20, std::max((size_t)8 << 20, 20 * h->nrec));
       slots = std::min(slots, free_b / 4 / entry);
       const size_t ntiles = (h->nrec + T - 1) / T;
-      size_t tpb = 1;                                     // tiles per level-1 bucket: 57..112 buckets when possible
-      while ((ntiles + tpb - 1) / tpb > 112) tpb <<= 1;
-      int tsh = 0;
-      while (((size_t)1 << tsh) < tpb) ++tsh;
-      const size_t nbuckets = (ntiles + tpb - 1) / tpb;
       size_t cap = (slots / ntiles) & ~(size_t)31;
-      if (cap >= 256 && smem <= 227 * 1024 && shift >= 8 && shift <= 16 && tpb <= PB_MAXB) {
+      if (cap >= 256 && smem <= 227 * 1024 && shift >= 8 && shift <= 16) {
         h->sg.tile_shift = shift;
-        h->sg.bucket_shift = shift + tsh;
         h->sg.ntiles = (unsigned)ntiles;
-        h->sg.nbuckets = (unsigned)nbuckets;
         h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffe0);
         h->stage_slots = ntiles * (size_t)h->sg.cap;
         h->tile_smem = smem;
         h->tile_ctas = (int)std::min(ntiles, (size_t)1 << 20);
-        const size_t nfill = nbuckets * tpb;              // padded: every (bucket, local tile) has a counter
-        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * 2 * nfill));   // + the per-tile dirty words
-        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * 2 * nfill));
-        h->sg.dirty = h->sg.fill + nfill;
-        // level-1 scratch: one run of c1 slots per (bucket, K1p batch), mirrored by a shared-memory bin in K1p;
-        // c1 = power of two >= 1.5x the mean run when every observation is accepted (fuller bins overflow
-        // into the direct accumulate), bounded by the shared memory the bins may take
-        unsigned c1 = 16, c1_shift = 4;
-        while (c1 < 512 && (size_t)c1 * nbuckets * 2 < (size_t)3 * P1_BATCH) { c1 <<= 1; ++c1_shift; }
-        while (c1 > 16 && (size_t)c1 * nbuckets * (8 * nr + 4) > (size_t)100 * 1024) { c1 >>= 1; --c1_shift; }
-        h->sg.c1 = c1;
-        h->sg.c1_shift = c1_shift;
-        h->sg.nbatch_cap = 2048;                          // 2 Mi observations per slice
-        h->scratch_cap = nbuckets * (size_t)h->sg.nbatch_cap * c1;
-        if (const char *e_p = getenv("GRITAS_B200_P2_SMALL")) h->p2_small = atoi(e_p) != 0;
+        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * 2 * ntiles));   // tickets + the per-tile dirty words
+        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * 2 * ntiles));
+        h->sg.dirty = h->sg.fill + ntiles;
+        CUC(cudaMalloc(&h->sg.lists, entry * h->stage_slots));
         if (const char *e_w = getenv("GRITAS_B200_WORKERS")) h->nwk = std::max(1, std::min(NWK, atoi(e_w)));
-        for (int w = 0; w < h->nwk; ++w) {                // one scratch, stream and event per worker
-          h->sgw[w] = h->sg;
-          CUC(cudaMalloc(&h->sgw[w].cnt1, sizeof(unsigned) * nbuckets * h->sg.nbatch_cap));
-          CUC(cudaMalloc(&h->sgw[w].key1, sizeof(unsigned) * h->scratch_cap));
-          for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sgw[w].d1[ir], sizeof(double) * h->scratch_cap));
+        for (int w = 0; w < h->nwk; ++w) {                // one stream, event and level-miss record per worker
           CUC(cudaStreamCreateWithFlags(&h->wk[w], cudaStreamNonBlocking));
           CUC(cudaEventCreateWithFlags(&h->wk_done[w], cudaEventDisableTiming));
         }
-        CUC(cudaMalloc(&h->sg.skey, sizeof(unsigned) * h->stage_slots));
-        for (int ir = 0; ir < nr; ++ir) CUC(cudaMalloc(&h->sg.sd[ir], sizeof(double) * h->stage_slots));
-        const size_t p2b = levtab_smem_bytes(g);
-        if (nr == 1) {
-          h->p1_smem = p1_smem_bytes<1>((unsigned)(nbuckets << c1_shift)) + p2b;
-          h->p2_smem = h->p2_small ? p2_smem_bytes<1, 2048, 256>() : p2_smem_bytes<1, 4096, 512>();
-          CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          if (h->p2_small) CUC(cudaFuncSetAttribute(k_part_tiles<1, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
-          else CUC(cudaFuncSetAttribute(k_part_tiles<1, 4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
-        } else if (nr == 2) {
-          h->p1_smem = p1_smem_bytes<2>((unsigned)(nbuckets << c1_shift)) + p2b;
-          h->p2_smem = h->p2_small ? p2_smem_bytes<2, 2048, 256>() : p2_smem_bytes<2, 4096, 512>();
-          CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          if (h->p2_small) CUC(cudaFuncSetAttribute(k_part_tiles<2, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
-          else CUC(cudaFuncSetAttribute(k_part_tiles<2, 4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
-        } else {
-          h->p1_smem = p1_smem_bytes<3>((unsigned)(nbuckets << c1_shift)) + p2b;
-          h->p2_smem = h->p2_small ? p2_smem_bytes<3, 2048, 256>() : p2_smem_bytes<3, 4096, 512>();
-          CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          CUC(cudaFuncSetAttribute(k_part_obs<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p1_smem));
-          if (h->p2_small) CUC(cudaFuncSetAttribute(k_part_tiles<3, 2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
-          else CUC(cudaFuncSetAttribute(k_part_tiles<3, 4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->p2_smem));
-        }
-        for (int w = 0; w < h->nwk; ++w) {                // tile-list fields are shared by all workers
-          StageDesc &q = h->sgw[w];
-          q.fill = h->sg.fill; q.skey = h->sg.skey; q.dirty = h->sg.dirty;
-          for (int ir = 0; ir < 3; ++ir) q.sd[ir] = h->sg.sd[ir];
-          q.cap = h->sg.cap; q.ntiles = h->sg.ntiles; q.tile_shift = h->sg.tile_shift;
-          q.c1 = h->sg.c1; q.c1_shift = h->sg.c1_shift; q.nbatch_cap = h->sg.nbatch_cap;
-          q.nbuckets = h->sg.nbuckets; q.bucket_shift = h->sg.bucket_shift;
-        }
+        if (nr == 1) CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->staging = true;
         {  // K2f (fused tile accumulate + finalize): one CTA per SM with the sum planes and a sort chunk in shared memory
           const size_t tf = nr == 1 ? TileFinal<1>::smem_bytes(T) : (nr == 2 ? TileFinal<2>::smem_bytes(T) : TileFinal<3>::smem_bytes(T));
@@ -808,9 +721,6 @@ void gritas_b200_destroy(gritas_b200_handle h) {
   for (int w = 0; w < NWK; ++w) {
     if (h->wk[w]) { cudaStreamSynchronize(h->wk[w]); cudaStreamDestroy(h->wk[w]); }
     if (h->wk_done[w]) cudaEventDestroy(h->wk_done[w]);
-    for (void *p : {(void *)h->sgw[w].cnt1, (void *)h->sgw[w].key1, (void *)h->sgw[w].d1[0], (void *)h->sgw[w].d1[1],
-                    (void *)h->sgw[w].d1[2]})
-      if (p) cudaFree(p);
   }
   if (h->main_ev) cudaEventDestroy(h->main_ev);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -820,7 +730,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (h->ev_red[c]) cudaEventDestroy(h->ev_red[c]);
   }
   if (h->ev_fin) cudaEventDestroy(h->ev_fin);
-  for (void *p : {(void *)h->sg.fill, (void *)h->sg.skey, (void *)h->sg.sd[0], (void *)h->sg.sd[1], (void *)h->sg.sd[2]})
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists})
     if (p) cudaFree(p);
   if (h->d_lut) cudaFree(h->d_lut);
   if (h->d_mask) cudaFree(h->d_mask);
@@ -1042,8 +952,7 @@ int gritas_b200_reset(gritas_b200_handle h) {
   }
   h->acc_fresh = true;
   if (h->staging) {
-    const size_t nfill = (size_t)h->sg.nbuckets << (h->sg.bucket_shift - h->sg.tile_shift);
-    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * 2 * nfill, h->compute));   // counters and the dirty words
+    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * 2 * h->sg.ntiles, h->compute));   // tickets and the dirty words
     h->staged_upper = 0;
   }
   return mark_main(h);

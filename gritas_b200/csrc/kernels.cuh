@@ -78,26 +78,16 @@ struct FilterDesc {
 };
 
 // Staging area of the tiled fast path.  The record grid is cut into tiles of
-// 2^tile_shift consecutive records; K1 appends every accepted observation as a compact
-// (record key, residuals) entry to the list of its tile; K2t later accumulates one tile at a time in
-// shared memory.  Lists have a fixed capacity; entries that do not fit are accumulated directly.
+// 2^tile_shift consecutive records; K1 appends every accepted observation as one (record key, residuals)
+// entry to the list of its tile; K2t / K2f later accumulate one tile at a time in shared memory.  Lists
+// have a fixed capacity; entries that do not fit are accumulated directly.
 struct StageDesc {
-  // level 2: one list of compact entries per tile of 2^tile_shift records
-  unsigned *fill;      // [ntiles (padded)] entries appended since the last flush (may exceed cap: clamp)
-  unsigned *skey;      // [ntiles * cap]
-  double *sd[3];       // [ntiles * cap] per residual column
+  unsigned *fill;        // [ntiles] tickets handed out since the last flush (may exceed cap: clamp)
+  unsigned char *lists;  // [ntiles * cap] entries of ListEntry<nr>::BYTES bytes
   unsigned cap, ntiles;
   int tile_shift;
-  unsigned *dirty;     // [ntiles (padded)] set when an entry of the tile was accumulated directly (bin / list overflow):
-                       // the tile's records are no longer all zero
-  // level 1: scratch of the current Accum call, one fixed run of c1 slots per (bucket, K1p batch): no
-  // global tickets (same-address atomics serialise at ~60 ns each on B200).  A bucket is
-  // 2^(bucket_shift-tile_shift) tiles.  The scratch is small enough to stay in L2 between K1p and K1q.
-  unsigned *cnt1;      // [nbuckets * nbatch_cap] live entries of each run (<= c1)
-  unsigned *key1;      // [nbuckets * nbatch_cap * c1]
-  double *d1[3];
-  unsigned c1, c1_shift, nbatch_cap, nbatch, nbuckets;
-  int bucket_shift;
+  unsigned *dirty;       // [ntiles] set when an entry of the tile was accumulated directly (list overflow): the tile's
+                         // records are no longer all zero
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -290,16 +280,7 @@ __device__ __noinline__ void report_miss(Status *st, unsigned call_seq, int n, d
   }
 }
 
-// 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion wait.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-// One instruction (UBLKPF.L2) asks L2 to fetch a whole column slice: the CTA's loads then find their
+// One instruction (UBLKPF.L2) asks L2 to fetch a contiguous slice: the CTA's later loads then find their
 // lines in L2 instead of paying HBM latency one dependent phase at a time.
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
   const unsigned long long a = (unsigned long long)p;
@@ -310,33 +291,11 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(sz) : "memory");
 }
 
-// All columns K1p reads for observations [first, first + count).
-__device__ __forceinline__ void prefetch_batch(const ObsCols &c, const FilterDesc &f, int nr, int first, int count) {
-  const int t = threadIdx.x;
-  const unsigned b8 = (unsigned)count * 8u, b4 = (unsigned)count * 4u;
-  if (t == 0) prefetch_l2_bulk(c.lat + first, b8);
-  if (t == 16) prefetch_l2_bulk(c.lon + first, b8);
-  if (t == 32) prefetch_l2_bulk(c.lev + first, b8);
-  if (t == 48) prefetch_l2_bulk(c.kx + first, b4);
-  if (t == 64) prefetch_l2_bulk(c.kt + first, b4);
-  if (t == 80 && c.flag) prefetch_l2_bulk(c.flag + first, b4);
-  if (t == 96 && f.use_time) prefetch_l2_bulk(c.time + first, b4);
-  if (t == 112) {
-    for (int ir = 0; ir < nr; ++ir) prefetch_l2_bulk(c.d[ir] + first, b8);
-  }
-}
-
-// L2 residency policy: the observation columns are read exactly once (evict first), the level-1 scratch is
-// written by K1p and read back by K1q a few microseconds later (evict last) -- otherwise the 63 MB of columns
-// per file push the 20 MB scratch out of L2 and it makes a round trip through HBM.
+// L2 residency policy: the observation columns are read exactly once (evict first), so that they do not push the
+// open tails of the tile lists out of L2.
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
   unsigned long long p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 
@@ -355,14 +314,6 @@ __device__ __forceinline__ int4 ldg_stream4(const int *p) {
                : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
-// scratch stores that should stay in L2 until K1q has read them
-__device__ __forceinline__ void stg_keep2(unsigned *p, uint2 v) {
-  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(l2_policy_evict_last()) : "memory");
-}
-__device__ __forceinline__ void stg_keep2(double *p, double2 v) {
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(l2_policy_evict_last()) : "memory");
-}
-
 template <int NR>
 struct Obs4 {
   double lat[4], lon[4], lev[4], d[NR][4];
@@ -806,146 +757,50 @@ k_segment_sum(const GridDesc g, const ObsCols c, const FilterDesc f, const unsig
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tiled fast path, part 1: two-level partition of the accepted observations into per-tile lists.
+// Tiled fast path, part 1 (K1): every accepted observation becomes ONE entry in the list of its tile.
 //
-// Scattered 4/8-byte stores run at ~40 G/s on B200 (profiles/r1_microbench_tickets_scatter.txt): far
-// below what this path needs.  Both partition kernels therefore group a batch of entries by
-// destination in shared memory and write every destination's entries as one run whose start and
-// length are multiples of 8 entries (32 B of keys, 64 B of residuals): only full, aligned sectors
-// reach L2.  Runs are padded with KEY_NONE sentinels; readers skip them.
-//   K1p  k_part_obs    columns -> classify (filter, table, box index) -> per-BUCKET scratch lists
-//   K1q  k_part_tiles  bucket scratch (still in L2) -> per-TILE lists in HBM
-constexpr int PB_MAXB = 128;                      // destinations per grouping step
-constexpr unsigned PB_OVERFLOW = 0xFFFFFFFFu;
-// K1p: 256 threads x 8 observations, 3 CTAs per SM so that load / group / write-out phases of
-// different CTAs overlap.  K1q: 512 threads, two passes over a 4096-entry chunk (count, then regroup), 2 CTAs per SM.
-constexpr int P1_THREADS = 256, P1_ITEMS = 8, P1_BATCH = P1_THREADS * P1_ITEMS, P1_SCAP = P1_BATCH + 8 * PB_MAXB;
-// K1q comes in two sizes: rounds of 4096 entries (512 threads, 2 CTAs/SM) or 2048 entries (256 threads, 4 CTAs/SM)
-constexpr int P2_PAD = 8 * PB_MAXB;
-
+// An entry is one aligned 32-byte sector {key u32, -, d1 f64, d2 f64 [, d3]} (16 bytes {key, -, d1} at nr = 1) and
+// is written with a single 256-bit store at the position a ticket (atomicAdd on the tile's fill counter) hands out.
+// Measured on B200 (profiles/r1_microbench_one_level.txt): scattered stores run at ~40 G requests/s whether they
+// carry 4 or 32 bytes, tickets on 13 K counters at ~65 G/s, and both behind the 52 B/obs column stream give
+// 47 G obs/s -- faster than grouping the entries in shared memory first (two partition kernels per file, an
+// L2-resident scratch and ~13 % padding, 31 G obs/s), because that path was bound by instruction issue, not by
+// memory.  Lanes of a warp that hit the same tile share one ticket (__match_any_sync): clustered data
+// (radiosonde sites, swaths) would otherwise serialise on the tile's counter.
 template <int NR>
-struct PartView {
-  double *d[NR];        // [SCAP] grouped residuals
-  unsigned *key;        // [SCAP] grouped keys
-  unsigned *cnt;        // [PB_MAXB] entries per destination in this batch
-  unsigned *cnt2;       // [PB_MAXB] second ticket counter (two-pass grouping)
-  unsigned *off;        // [PB_MAXB] start of the destination's (padded) group in the staging arrays
-  unsigned *run;        // [PB_MAXB] start of the run inside the destination's global list, or PB_OVERFLOW
-  unsigned *total;      // padded entries in this batch
-  unsigned char *grp;   // [SCAP/8] destination of each group of 8 staged entries
+struct ListEntry {
+  static constexpr int BYTES = (NR == 1) ? 16 : 32;
 };
 
-// Bytes of the grouped-entry staging (residual planes + keys).
-template <int NR, int SCAP>
-__host__ __device__ constexpr size_t part_stage_bytes() {
-  return sizeof(double) * NR * SCAP + sizeof(unsigned) * SCAP;
-}
-
-template <int NR, int SCAP>
-__host__ __device__ constexpr size_t part_smem_bytes() {
-  return part_stage_bytes<NR, SCAP>() + sizeof(unsigned) * (4 * PB_MAXB + 4) + SCAP / 8;
-}
-
-template <int NR, int SCAP>
-__device__ __forceinline__ PartView<NR> part_view(unsigned char *smem) {
-  PartView<NR> v;
-  double *dp = reinterpret_cast<double *>(smem);
-#pragma unroll
-  for (int ir = 0; ir < NR; ++ir) v.d[ir] = dp + (size_t)ir * SCAP;
-  unsigned *up = reinterpret_cast<unsigned *>(dp + (size_t)NR * SCAP);
-  v.key = up;
-  up = reinterpret_cast<unsigned *>(smem + part_stage_bytes<NR, SCAP>());
-  v.cnt = up; up += PB_MAXB;
-  v.cnt2 = up; up += PB_MAXB;
-  v.off = up; up += PB_MAXB;
-  v.run = up; up += PB_MAXB;
-  v.total = up; up += 4;
-  v.grp = reinterpret_cast<unsigned char *>(up);
-  return v;
-}
-
-// After the counting pass: lay the destinations out back to back (each padded to a multiple of 8),
-// decide where each destination's run goes in global memory, write the pad sentinels and the
-// group->destination map.  Called by all threads of the CTA.
-//   TICKET: the run is reserved at the tail of the destination's list with one global atomicAdd
-//           (K1q -> tile lists); a run that does not fit is marked PB_OVERFLOW.
-//   else  : every destination has a fixed run of `limit` slots starting at `fixed_run` (K1p -> bucket
-//           scratch); entries beyond `limit` are left to the caller (cnt is clipped).
-template <int NR, bool TICKET>
-__device__ __forceinline__ void part_layout(const PartView<NR> &v, int nb, unsigned limit, unsigned fixed_run,
-                                            unsigned *__restrict__ g_fill, unsigned *__restrict__ g_key, unsigned cap,
-                                            unsigned list_first) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (tid < 32) {
-    unsigned p[4], local = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int b = lane * 4 + q;
-      const unsigned c = b < nb ? min(v.cnt[b], limit) : 0u;
-      p[q] = (c + 7u) & ~7u;
-      local += p[q];
-    }
-    unsigned incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    unsigned at = incl - local;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      v.off[lane * 4 + q] = at;
-      at += p[q];
-    }
-    if (lane == 31) *v.total = incl;
-  }
-  __syncthreads();
-  if (tid < nb) {
-    const unsigned c = min(v.cnt[tid], limit), padded = (c + 7u) & ~7u, off = v.off[tid];
-    unsigned run = fixed_run;
-    if (c) {
-      if (TICKET) {
-        const unsigned gpos = atomicAdd(g_fill + list_first + tid, padded);
-        if (gpos + padded <= cap) {
-          run = gpos;
-        } else {
-          // does not fit: these entries are accumulated directly by the caller.  Exactly one reservation
-          // straddles the capacity; it closes the unwritten gap with sentinels so readers never see garbage.
-          run = PB_OVERFLOW;
-          unsigned *lk = g_key + (size_t)(list_first + tid) * cap;
-          for (unsigned e = gpos; e < cap; ++e) lk[e] = KEY_NONE;
-        }
-      }
-      for (unsigned e = c; e < padded; ++e) {
-        v.key[off + e] = KEY_NONE;
-#pragma unroll
-        for (int ir = 0; ir < NR; ++ir) v.d[ir][off + e] = 0.0;
-      }
-      for (unsigned gq = off >> 3; gq < ((off + padded) >> 3); ++gq) v.grp[gq] = (unsigned char)tid;
-    }
-    v.run[tid] = run;
-  }
-  __syncthreads();
-}
-
-// Staged groups -> runs at the tails of the global lists: consecutive threads write consecutive
-// entries, every group of 8 is one aligned 32 B (keys) / 64 B (residuals) sector.
 template <int NR>
-__device__ __forceinline__ void part_writeout(const PartView<NR> &v, unsigned cap, unsigned list_first,
-                                              unsigned *__restrict__ g_key, double *const (&g_d)[3]) {
-  const unsigned total = *v.total;
-  for (unsigned s = threadIdx.x * 2u; s < total; s += blockDim.x * 2u) {  // 2 entries per thread: 8 B + 16 B stores
-    const unsigned b = v.grp[s >> 3], run = v.run[b];
-    if (run == PB_OVERFLOW) continue;
-    const size_t gi = (size_t)(list_first + b) * cap + run + (s - v.off[b]);
-    __stcs(reinterpret_cast<uint2 *>(g_key + gi), *reinterpret_cast<const uint2 *>(v.key + s));
-#pragma unroll
-    for (int ir = 0; ir < NR; ++ir)
-      __stcs(reinterpret_cast<double2 *>(g_d[ir] + gi), *reinterpret_cast<const double2 *>(v.d[ir] + s));
+__device__ __forceinline__ void entry_store(unsigned char *lists, size_t idx, unsigned key, const double (&d)[NR]) {
+  unsigned char *p = lists + idx * (size_t)ListEntry<NR>::BYTES;
+  const double k = __longlong_as_double((long long)key);
+  if (NR == 1) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(k), "d"(d[0]) : "memory");
+  } else {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(k), "d"(d[0]), "d"(d[1]), "d"(d[NR - 1]) : "memory");
   }
 }
 
-// Direct accumulate of one entry (overflow of a list): the same fp64 RED the direct path uses.
+// Streaming (read-once) load of entry idx; returns the key.
+template <int NR>
+__device__ __forceinline__ unsigned entry_load(const unsigned char *lists, size_t idx, double (&d)[NR]) {
+  const unsigned char *p = lists + idx * (size_t)ListEntry<NR>::BYTES;
+  double k, a, b, c;
+  if (NR == 1) {
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(k), "=d"(a) : "l"(p));
+    d[0] = a;
+  } else {
+    asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(k), "=d"(a), "=d"(b), "=d"(c) : "l"(p));
+    d[0] = a;
+    d[1] = b;
+    if (NR == 3) d[NR - 1] = c;
+  }
+  return (unsigned)__double_as_longlong(k);
+}
+
+// Direct accumulate of one entry (a full list): the same fp64 RED the direct path uses.
 template <int NR>
 __device__ __forceinline__ void red_entry(const GridDesc &g, unsigned key, const double (&d)[NR]) {
   double sq[NR];
@@ -955,267 +810,66 @@ __device__ __forceinline__ void red_entry(const GridDesc &g, unsigned key, const
   red_record<NR>(g.acc + (size_t)key * (size_t)g.rs, 1.0, d, sq, sxy);
 }
 
-#ifdef GB_PHASE_TIMING
-__device__ unsigned long long *g_phase_buf = nullptr;   // [gridDim.x][8] globaltimer stamps (probe builds only)
-__device__ __forceinline__ void phase_stamp(int slot) {
-  if (threadIdx.x == 0 && g_phase_buf) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    g_phase_buf[(size_t)blockIdx.x * 8 + slot] = t;
-  }
-}
-#define GB_STAMP(i) phase_stamp(i)
-#else
-#define GB_STAMP(i)
-#endif
-
-// K1p: a batch of P1_BATCH observations per CTA iteration, ONE pass.  Every level-1 bucket owns a bin of c1
-// slots in shared memory -- the image of its run in the global scratch.  A thread classifies 4 observations,
-// takes a ticket in the bucket's bin for each accepted one, loads the residuals and drops the entry into
-// the bin (entries beyond c1 are accumulated directly).  After one barrier the live part of every bin,
-// rounded up to 8 entries, is copied to the global run with full aligned sectors.
-template <int NR>
-__host__ __device__ constexpr size_t p1_smem_bytes(unsigned nslot) {
-  return ((size_t)nslot * (8 * NR + 4) + 15) / 16 * 16 + sizeof(unsigned) * PB_MAXB;
-}
+constexpr int K1_THREADS = 256;
 
 template <int NR, int FMODE>
-__global__ void __launch_bounds__(P1_THREADS, 3)
-k_part_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
+__global__ void __launch_bounds__(K1_THREADS, 4)
+k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
            const StageDesc sg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const unsigned nslot = sg.nbuckets << sg.c1_shift;
-  double *s_d[NR];
-#pragma unroll
-  for (int ir = 0; ir < NR; ++ir) s_d[ir] = reinterpret_cast<double *>(smem_raw) + (size_t)ir * nslot;
-  unsigned *s_key = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(smem_raw) + (size_t)NR * nslot);
-  unsigned *s_cnt = reinterpret_cast<unsigned *>(smem_raw + ((size_t)nslot * (8 * NR + 4) + 15) / 16 * 16);
-  double *s_p2 = reinterpret_cast<double *>(smem_raw + p1_smem_bytes<NR>(nslot));
-  const int tid = threadIdx.x;
-  GB_STAMP(0);
-  const LevTab p2s = load_p2(g, s_p2);
-  GB_STAMP(1);
-  const int nb = (int)sg.nbuckets;
-  const int nbatch = (c.n + P1_BATCH - 1) / P1_BATCH;
-  if ((int)blockIdx.x < nbatch)
-    prefetch_batch(c, f, NR, blockIdx.x * P1_BATCH, min(P1_BATCH, c.n - (int)blockIdx.x * P1_BATCH));
-  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-    const int nxt = batch + (int)gridDim.x;
-    if (nxt < nbatch) prefetch_batch(c, f, NR, nxt * P1_BATCH, min(P1_BATCH, c.n - nxt * P1_BATCH));
-    if (tid < PB_MAXB) s_cnt[tid] = 0u;
-    __syncthreads();
-#pragma unroll 1
-    for (int h = 0; h < P1_ITEMS / 4; ++h) {
-      const int base = batch * P1_BATCH + (h * P1_THREADS + tid) * 4;
-      if (base >= c.n) continue;
-      unsigned k4[4];
-      {
-        Obs4<NR> o;
-        int fa[4];
-        load_geo4<NR>(c, f, base, o);
-        classify4<NR, FMODE>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
-        if (c.flag_out) {
-          if (c.aligned && base + 3 < c.n) {
-            *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (base + j < c.n) c.flag_out[base + j] = fa[j];
-          }
-        }
-      }
-      if ((k4[0] & k4[1] & k4[2] & k4[3]) == KEY_NONE) continue;
-      double dd[NR][4];
-      load_del4<NR>(c, base, dd);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned key = k4[j];
-        if (key == KEY_NONE) continue;
-        double d[NR];
-#pragma unroll
-        for (int ir = 0; ir < NR; ++ir) d[ir] = (f.scale_res | f.expr) ? residual_value(f, c, ir, dd[ir][j], base + j) : dd[ir][j];
-        const unsigned b = key >> sg.bucket_shift;
-        const unsigned rank = atomicAdd(s_cnt + b, 1u);
-        if (rank >= sg.c1) {
-          red_entry<NR>(g, key, d);     // the bin of this bucket is full: accumulate directly
-          sg.dirty[key >> sg.tile_shift] = 1u;
+  const LevTab p2s = load_p2(g, reinterpret_cast<double *>(smem_raw));
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  const int nvec = (c.n + 3) >> 2;
+  // whole warps iterate together (the ticket aggregation is warp-wide)
+  const int nround = (nvec + K1_THREADS - 1) / K1_THREADS * K1_THREADS;
+  for (int vec = blockIdx.x * K1_THREADS + threadIdx.x; vec < nround; vec += gridDim.x * K1_THREADS) {
+    const int base = vec * 4;
+    unsigned k4[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
+    if (base < c.n) {
+      Obs4<NR> o;
+      int fa[4];
+      load_geo4<NR>(c, f, base, o);
+      classify4<NR, FMODE>(g, f, p2s, o, base, c.n, st, call_seq, k4, fa);
+      if (c.flag_out) {
+        if (c.aligned && base + 3 < c.n) {
+          *reinterpret_cast<int4 *>(c.flag_out + base) = make_int4(fa[0], fa[1], fa[2], fa[3]);
         } else {
-          const unsigned slot = (b << sg.c1_shift) + rank;
-          s_key[slot] = key;
 #pragma unroll
-          for (int ir = 0; ir < NR; ++ir) s_d[ir][slot] = d[ir];
+          for (int j = 0; j < 4; ++j)
+            if (base + j < c.n) c.flag_out[base + j] = fa[j];
         }
       }
     }
-    __syncthreads();
-    GB_STAMP(2);
-    if (tid < nb) sg.cnt1[(size_t)tid * sg.nbatch_cap + batch] = min(s_cnt[tid], sg.c1);
-    // bins -> runs: bucket b's run of this batch starts at slot (b * nbatch_cap + batch) * c1 of the scratch
-    for (unsigned s2 = (unsigned)tid * 2u; s2 < nslot; s2 += P1_THREADS * 2u) {
-      const unsigned b = s2 >> sg.c1_shift, i = s2 & (sg.c1 - 1u);
-      if (i >= ((min(s_cnt[b], sg.c1) + 7u) & ~7u)) continue;   // slots past the count hold stale data: never read
-      const size_t gi = (((size_t)b * sg.nbatch_cap + (size_t)batch) << sg.c1_shift) + i;
-      stg_keep2(sg.key1 + gi, *reinterpret_cast<const uint2 *>(s_key + s2));
+    const bool any = (k4[0] & k4[1] & k4[2] & k4[3]) != KEY_NONE;
+    if (!__any_sync(0xffffffffu, any)) continue;
+    double dd[NR][4];
+    if (any) load_del4<NR>(c, base, dd);
+    // tickets first (four independent atomics in flight), then the stores
+    unsigned pos[4];
 #pragma unroll
-      for (int ir = 0; ir < NR; ++ir) stg_keep2(sg.d1[ir] + gi, *reinterpret_cast<const double2 *>(s_d[ir] + s2));
+    for (int j = 0; j < 4; ++j) {
+      const unsigned tile = (k4[j] == KEY_NONE) ? 0xFFFFFFFFu : (k4[j] >> sg.tile_shift);
+      const unsigned peers = __match_any_sync(0xffffffffu, tile);
+      const int leader = __ffs(peers) - 1;
+      unsigned p0 = 0u;
+      if ((int)lane == leader && tile != 0xFFFFFFFFu) p0 = atomicAdd(sg.fill + tile, (unsigned)__popc(peers));
+      pos[j] = __shfl_sync(0xffffffffu, p0, leader) + (unsigned)__popc(peers & lt);
     }
-    __syncthreads();
-    GB_STAMP(5);
-  }
-  GB_STAMP(6);
-}
-
-// K1q: regroups the bucket scratch by tile.  Work item = (bucket, one of `parts` equal ranges of K1p
-// batches); a persistent grid walks the items.  Inside an item the runs are packed greedily into
-// rounds of at most P2_BATCH live entries; every round is two passes over its runs (they sit in L2):
-// count per tile, lay out + reserve list space, then reload and scatter with a second ticket counter
-// -- nothing is kept in registers across the barriers.
-template <int NR, int P2_BATCH, int P2_THREADS>
-__host__ __device__ constexpr size_t p2_smem_bytes() {
-  return ((part_smem_bytes<NR, P2_BATCH + P2_PAD>() + 15) & ~(size_t)15) + sizeof(unsigned) * (P2_THREADS + 40);
-}
-
-template <int NR, int P2_BATCH, int P2_THREADS>
-__global__ void __launch_bounds__(P2_THREADS, 2048 / P2_THREADS / 2)
-k_part_tiles(const GridDesc g, const StageDesc sg, int parts) {
-  constexpr int P2_SCAP = P2_BATCH + P2_PAD;
-  constexpr int P2_MAXRUNS = P2_THREADS;  // runs (K1p batches) per round: one count per thread
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const PartView<NR> v = part_view<NR, P2_SCAP>(smem_raw);
-  unsigned *s_rcnt = reinterpret_cast<unsigned *>(smem_raw + ((part_smem_bytes<NR, P2_SCAP>() + 15) & ~(size_t)15));
-  unsigned *s_scan = s_rcnt + P2_MAXRUNS;       // [32] warp totals, then [1] runs taken, [1] spare
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int tsh = sg.bucket_shift - sg.tile_shift;
-  const int nt = 1 << tsh;                        // tiles per bucket (<= PB_MAXB)
-  const unsigned tmask = (unsigned)(nt - 1);
-  const unsigned nitems = sg.nbuckets * (unsigned)parts;
-  const unsigned per = (sg.nbatch + (unsigned)parts - 1u) / (unsigned)parts;
-  for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const unsigned b = item % sg.nbuckets, part = item / sg.nbuckets;
-    unsigned lo = part * per;
-    const unsigned hi = min(sg.nbatch, lo + per);
-    const size_t row = (size_t)b * sg.nbatch_cap;
-    while (lo < hi) {
-      GB_STAMP(0);
-      // ---- how many runs fit in this round: inclusive scan of the run counts, cut at P2_BATCH ----
-      const unsigned nrun_max = min((unsigned)P2_MAXRUNS, hi - lo);
-      const unsigned mine = ((unsigned)tid < nrun_max) ? sg.cnt1[row + lo + tid] : 0u;
-      unsigned incl = mine;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (lane == 31) s_scan[wid] = incl;
-      if (tid < PB_MAXB) { v.cnt[tid] = 0u; v.cnt2[tid] = 0u; }
-      __syncthreads();
-      if (wid == 0) {
-        unsigned w = (lane < P2_THREADS / 32) ? s_scan[lane] : 0u, wi = w;
+    for (int j = 0; j < 4; ++j) {
+      const unsigned key = k4[j];
+      if (key == KEY_NONE) continue;
+      double d[NR];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
-          if (lane >= o) wi += t;
-        }
-        s_scan[lane] = wi - w;                    // exclusive warp offsets
-      }
-      __syncthreads();
-      incl += s_scan[wid];
-      s_rcnt[tid] = mine;
-      // runs taken = number of leading runs whose inclusive sum stays within the batch (at least one)
-      const bool fits = ((unsigned)tid < nrun_max) && (incl <= (unsigned)P2_BATCH || tid == 0);
-      const unsigned nrun = (unsigned)__syncthreads_count(fits);  // fits is a prefix property: count = cut
-      const unsigned nslot = nrun << sg.c1_shift;
-      const size_t src = (row + lo) << sg.c1_shift;
-      GB_STAMP(1);
-      // ---- pass 1: count per tile.  One warp per run (c1 <= 32: lane = slot), two runs in flight ----
-      if (sg.c1 <= 32u) {
-        const unsigned rpw = 32u / sg.c1;                   // runs per warp instruction
-        const unsigned sub = (unsigned)lane >> sg.c1_shift, i = (unsigned)lane & (sg.c1 - 1u);
-        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 8u) {
-          unsigned key[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {                     // eight runs in flight per warp
-            const unsigned r = r0 + (unsigned)u * (P2_THREADS / 32) * rpw + sub;
-            const bool live = r < nrun && i < s_rcnt[r];
-            key[u] = live ? __ldcg(sg.key1 + src + ((size_t)r << sg.c1_shift) + i) : KEY_NONE;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
-        }
+      for (int ir = 0; ir < NR; ++ir) d[ir] = (f.scale_res | f.expr) ? residual_value(f, c, ir, dd[ir][j], base + j) : dd[ir][j];
+      const unsigned tile = key >> sg.tile_shift;
+      if (pos[j] < sg.cap) {
+        entry_store<NR>(sg.lists, (size_t)tile * sg.cap + pos[j], key, d);
       } else {
-        for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
-          unsigned key[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const unsigned sidx = s0 + u * P2_THREADS;
-            const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
-            key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (key[u] != KEY_NONE) atomicAdd(v.cnt + ((key[u] >> sg.tile_shift) & tmask), 1u);
-        }
+        red_entry<NR>(g, key, d);       // the list is full: accumulate directly
+        sg.dirty[tile] = 1u;
       }
-      __syncthreads();
-      GB_STAMP(2);
-      part_layout<NR, true>(v, nt, 0xFFFFFFFFu, 0u, sg.fill, sg.skey, sg.cap, b << tsh);
-      GB_STAMP(3);
-      // ---- pass 2: reload, ticket, scatter ----
-      auto place = [&](unsigned key, const double (&d)[NR]) {
-        const unsigned t = (key >> sg.tile_shift) & tmask;
-        if (v.run[t] == PB_OVERFLOW) {
-          red_entry<NR>(g, key, d);
-          sg.dirty[key >> sg.tile_shift] = 1u;
-        } else {
-          const unsigned at = v.off[t] + atomicAdd(v.cnt2 + t, 1u);
-          v.key[at] = key;
-#pragma unroll
-          for (int ir = 0; ir < NR; ++ir) v.d[ir][at] = d[ir];
-        }
-      };
-      if (sg.c1 <= 32u) {
-        const unsigned rpw = 32u / sg.c1;
-        const unsigned sub = (unsigned)lane >> sg.c1_shift, i = (unsigned)lane & (sg.c1 - 1u);
-        for (unsigned r0 = (unsigned)wid * rpw; r0 < nrun; r0 += (P2_THREADS / 32) * rpw * 4u) {
-          unsigned key[4];
-          double d[4][NR];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {                     // four runs in flight per warp
-            const unsigned r = r0 + (unsigned)u * (P2_THREADS / 32) * rpw + sub;
-            const bool live = r < nrun && i < s_rcnt[r];
-            const size_t at = src + ((size_t)r << sg.c1_shift) + i;
-            key[u] = live ? __ldcg(sg.key1 + at) : KEY_NONE;
-#pragma unroll
-            for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + at) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (key[u] != KEY_NONE) place(key[u], d[u]);
-        }
-      } else {
-        for (unsigned s0 = tid; s0 < nslot; s0 += 4 * P2_THREADS) {
-          unsigned key[4];
-          double d[4][NR];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const unsigned sidx = s0 + u * P2_THREADS;
-            const bool live = sidx < nslot && (sidx & (sg.c1 - 1u)) < s_rcnt[sidx >> sg.c1_shift];
-            key[u] = live ? __ldcg(sg.key1 + src + sidx) : KEY_NONE;
-#pragma unroll
-            for (int ir = 0; ir < NR; ++ir) d[u][ir] = live ? __ldcg(sg.d1[ir] + src + sidx) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (key[u] != KEY_NONE) place(key[u], d[u]);
-        }
-      }
-      __syncthreads();
-      GB_STAMP(4);
-      part_writeout<NR>(v, sg.cap, b << tsh, sg.skey, sg.sd);
-      __syncthreads();
-      GB_STAMP(5);
-      lo += nrun;
     }
   }
 }
@@ -1256,10 +910,10 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0
 #pragma unroll
       for (int u = 0; u < TILE_ILP; ++u) {                // all loads of the round first
         const unsigned r = r0 + u * blockDim.x;
-        const unsigned key = (r < n) ? __ldcs(sg.skey + base + r) : KEY_NONE;
-        bx[u] = (key == KEY_NONE) ? 0xFFFFFFFFu : (key & (T - 1u));
+        bx[u] = 0xFFFFFFFFu;
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) d[u][ir] = (r < n) ? __ldcs(sg.sd[ir] + base + r) : 0.0;
+        for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
+        if (r < n) bx[u] = entry_load<NR>(sg.lists, base + r, d[u]) & (T - 1u);
       }
 #pragma unroll
       for (int u = 0; u < TILE_ILP; ++u) {
@@ -1581,23 +1235,15 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
     const size_t base = (size_t)tile * sg.cap;
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
     const bool addrec = !fresh || sg.dirty[tile] != 0u;
-    {  // the list of the tile this SM will probably get next: ask L2 for it now
+    {  // the list of the tile this SM gets next: ask L2 for it now
       const unsigned nt = tile + gridDim.x;
-      if (nt < sg.ntiles && tid < 32u * (1 + NR)) {
+      if (nt < sg.ntiles && tid < 32u) {
         const unsigned nn = min(sg.fill[nt], sg.cap);
-        const size_t nbase = (size_t)nt * sg.cap;
-        const unsigned col = wid;                           // 0: keys, 1..NR: residual columns
-        const unsigned esz = col ? 8u : 4u;
-        const unsigned per = ((nn + 31u) / 32u + 3u) & ~3u;  // entries per lane, 16-byte multiples
+        const unsigned per = (nn + 31u) / 32u;               // entries per lane (16- or 32-byte entries: aligned)
         const unsigned e0 = lane * per;
-        if (e0 < nn) {
-          const unsigned cntp = min(per, nn - e0);
-          const char *p = reinterpret_cast<const char *>(sg.skey + nbase + e0);
-#pragma unroll
-          for (int ir = 0; ir < NR; ++ir)                     // no dynamic index into the kernel parameters
-            if (col == (unsigned)ir + 1u) p = reinterpret_cast<const char *>(sg.sd[ir] + nbase + e0);
-          prefetch_l2_bulk(p, cntp * esz);
-        }
+        if (e0 < nn)
+          prefetch_l2_bulk(sg.lists + ((size_t)nt * sg.cap + e0) * (size_t)ListEntry<NR>::BYTES,
+                           min(per, nn - e0) * (unsigned)ListEntry<NR>::BYTES);
       }
     }
     for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = 0.0;
@@ -1611,10 +1257,10 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
 #pragma unroll
       for (int u = 0; u < EPT; ++u) {
         const unsigned e = c0 + (unsigned)u * NTH + tid;
-        const unsigned key = (e < n) ? __ldcs(sg.skey + base + e) : KEY_NONE;
-        pk[u] = (key == KEY_NONE) ? KEY_NONE : (key & (T - 1u));
+        pk[u] = KEY_NONE;
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) d[u][ir] = (e < n) ? __ldcs(sg.sd[ir] + base + e) : 0.0;
+        for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
+        if (e < n) pk[u] = entry_load<NR>(sg.lists, base + e, d[u]) & (T - 1u);
       }
 #pragma unroll
       for (int u = 0; u < EPT; ++u)
