@@ -11,7 +11,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("GRITAS_B200_LIBDIR") or os.path.join(HERE, "lib")   # override: experiments with alternative builds
 LIB = os.path.join(LIBDIR, "libgritas_b200.so")
 SOURCES = ["gritas_b200.cu"]
 HEADERS = ["kernels.cuh", os.path.join("..", "..", "include", "gritas_b200.h")]
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [nvcc_path()] + NVCC_FLAGS + os.environ.get("GRITAS_B200_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

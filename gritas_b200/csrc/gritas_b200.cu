@@ -319,7 +319,8 @@ void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, in
 template <int NR>
 void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDesc &f) {
   const int nvec = (c.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
-  const int g1 = grid_for((size_t)nvec, K1_THREADS, 8);
+  static const int per_sm = getenv("GRITAS_B200_K1_CTAS_PER_SM") ? std::max(1, atoi(getenv("GRITAS_B200_K1_CTAS_PER_SM"))) : 8;
+  const int g1 = grid_for((size_t)nvec, K1_THREADS, per_sm);
   const size_t smem = levtab_smem_bytes(h->g);
   Status *st = h->d_status + 1 + w;
   switch (filter_mode(f)) {
@@ -647,7 +648,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
                 h->nrec >= 4096;
     if (e_on && atoi(e_on) == 0) want = false;
     if (want) {
-      int shift = (nr == 1) ? 12 : 11;
+      int shift = (nr == 1) ? 11 : 10;     // tile = 2048 / 1024 records: K2f keeps 3 / 2 CTAs per SM (sum planes + sort chunk)
       if (e_shift) shift = atoi(e_shift);
       const int nv = (nr == 1) ? 2 : (nr == 2 ? 5 : 6);
       const size_t T = (size_t)1 << shift;
@@ -687,9 +688,12 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
             else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_final<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
             else CUC(cudaFuncSetAttribute(k_tile_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
             h->tf_smem = tf;
-            int nsm = 148;
+            int nsm = 148, per_sm = 1;
             CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
-            h->tf_ctas = (int)std::min((size_t)nsm, ntiles);
+            if (nr == 1) CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<1>, TileFinal<1>::THREADS, tf));
+            else if (nr == 2) CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<2>, TileFinal<2>::THREADS, tf));
+            else CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<3>, TileFinal<3>::THREADS, tf));
+            h->tf_ctas = (int)std::min((size_t)nsm * (size_t)std::max(per_sm, 1), ntiles);   // persistent: all CTAs resident
           }
         }
         if (h->flags & GRITAS_B200_FLAG_FORCE_TILED) h->tiled_choice = 1;

@@ -83,7 +83,7 @@ struct FilterDesc {
 // have a fixed capacity; entries that do not fit are accumulated directly.
 struct StageDesc {
   unsigned *fill;        // [ntiles] tickets handed out since the last flush (may exceed cap: clamp)
-  unsigned char *lists;  // [ntiles * cap] entries of ListEntry<nr>::BYTES bytes
+  unsigned char *lists;  // [cap / LIST_G][ntiles][LIST_G] entries of ListEntry<nr>::BYTES bytes, see list_slot()
   unsigned cap, ntiles;
   int tile_shift;
   unsigned *dirty;       // [ntiles] set when an entry of the tile was accumulated directly (list overflow): the tile's
@@ -278,17 +278,6 @@ __device__ __noinline__ void report_miss(Status *st, unsigned call_seq, int n, d
     cur_id = got_id;
     cur_lev = got_lev;
   }
-}
-
-// One instruction (UBLKPF.L2) asks L2 to fetch a contiguous slice: the CTA's later loads then find their
-// lines in L2 instead of paying HBM latency one dependent phase at a time.
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
-  const unsigned long long a = (unsigned long long)p;
-  const unsigned long long a16 = (a + 15ull) & ~15ull;           // 16-byte aligned start, 16-byte multiple size
-  const unsigned skip = (unsigned)(a16 - a);
-  if (bytes <= skip + 16u) return;
-  const unsigned sz = (bytes - skip) & ~15u;
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a16), "r"(sz) : "memory");
 }
 
 // L2 residency policy: the observation columns are read exactly once (evict first), so that they do not push the
@@ -772,6 +761,16 @@ struct ListEntry {
   static constexpr int BYTES = (NR == 1) ? 16 : 32;
 };
 
+// Where entry `pos` of tile `tile` lives.  The lists are interleaved in granules of LIST_G entries (256 bytes at
+// nr = 2): granule c of every tile sits next to granule c of its neighbours, so the open tails of all lists form one
+// contiguous frontier that moves through memory as the month is read.  With list-major storage every tail is a
+// separate DRAM row and the entry stores run at the random-sector rate (~40 G/s); interleaved they reach the
+// ticket rate (~60 G/s), and a tile's list still reads back at full bandwidth (profiles/r1_microbench_one_level.txt).
+constexpr unsigned LIST_G = 8;
+__device__ __forceinline__ size_t list_slot(const StageDesc &sg, unsigned tile, unsigned pos) {
+  return ((size_t)(pos / LIST_G) * sg.ntiles + tile) * LIST_G + (pos % LIST_G);
+}
+
 template <int NR>
 __device__ __forceinline__ void entry_store(unsigned char *lists, size_t idx, unsigned key, const double (&d)[NR]) {
   unsigned char *p = lists + idx * (size_t)ListEntry<NR>::BYTES;
@@ -811,9 +810,12 @@ __device__ __forceinline__ void red_entry(const GridDesc &g, unsigned key, const
 }
 
 constexpr int K1_THREADS = 256;
+#ifndef GB_K1_MINB
+#define GB_K1_MINB 4
+#endif
 
 template <int NR, int FMODE>
-__global__ void __launch_bounds__(K1_THREADS, 4)
+__global__ void __launch_bounds__(K1_THREADS, GB_K1_MINB)
 k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
            const StageDesc sg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -865,7 +867,7 @@ k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
       for (int ir = 0; ir < NR; ++ir) d[ir] = (f.scale_res | f.expr) ? residual_value(f, c, ir, dd[ir][j], base + j) : dd[ir][j];
       const unsigned tile = key >> sg.tile_shift;
       if (pos[j] < sg.cap) {
-        entry_store<NR>(sg.lists, (size_t)tile * sg.cap + pos[j], key, d);
+        entry_store<NR>(sg.lists, list_slot(sg, tile, pos[j]), key, d);
       } else {
         red_entry<NR>(g, key, d);       // the list is full: accumulate directly
         sg.dirty[tile] = 1u;
@@ -901,7 +903,6 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0
     for (unsigned e = threadIdx.x; e < NV * T; e += blockDim.x) s_val[e] = 0.0;
     for (unsigned e = threadIdx.x; e < T; e += blockDim.x) s_cnt[e] = 0u;
     __syncthreads();
-    const size_t base = (size_t)tile * sg.cap;
     const unsigned stride = blockDim.x * TILE_ILP;
     const unsigned nround = (n + stride - 1) / stride * stride;   // whole warps iterate together
     for (unsigned r0 = threadIdx.x; r0 < nround; r0 += stride) {
@@ -913,7 +914,7 @@ k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0
         bx[u] = 0xFFFFFFFFu;
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
-        if (r < n) bx[u] = entry_load<NR>(sg.lists, base + r, d[u]) & (T - 1u);
+        if (r < n) bx[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, r), d[u]) & (T - 1u);
       }
 #pragma unroll
       for (int u = 0; u < TILE_ILP; ++u) {
@@ -1204,7 +1205,7 @@ k_add_raw(const GridDesc g, OutPlanes in, int is3d) {
 // reference's arrays longitude-fastest) and writes each plane in runs of ~tile/km consecutive doubles.
 template <int NR>
 struct TileFinal {
-  static constexpr int THREADS = 1024;
+  static constexpr int THREADS = 512;                     // 2 or 3 CTAs per SM: their barrier-separated phases overlap
   static constexpr int EPT = (NR == 3) ? 4 : 6;           // entries per thread and chunk
   static constexpr int CH = EPT * THREADS;                // chunk of the list sorted at a time
   static constexpr int NV = TilePlanes<NR>::NV;
@@ -1214,7 +1215,7 @@ struct TileFinal {
 };
 
 template <int NR>
-__global__ void __launch_bounds__(TileFinal<NR>::THREADS, 1)
+__global__ void __launch_bounds__(TileFinal<NR>::THREADS, 2)
 k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh,
              int raw2, int raw3, int fresh) {
   using TF = TileFinal<NR>;
@@ -1232,20 +1233,8 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
   for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
-    const size_t base = (size_t)tile * sg.cap;
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
     const bool addrec = !fresh || sg.dirty[tile] != 0u;
-    {  // the list of the tile this SM gets next: ask L2 for it now
-      const unsigned nt = tile + gridDim.x;
-      if (nt < sg.ntiles && tid < 32u) {
-        const unsigned nn = min(sg.fill[nt], sg.cap);
-        const unsigned per = (nn + 31u) / 32u;               // entries per lane (16- or 32-byte entries: aligned)
-        const unsigned e0 = lane * per;
-        if (e0 < nn)
-          prefetch_l2_bulk(sg.lists + ((size_t)nt * sg.cap + e0) * (size_t)ListEntry<NR>::BYTES,
-                           min(per, nn - e0) * (unsigned)ListEntry<NR>::BYTES);
-      }
-    }
     for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = 0.0;
     for (unsigned e = tid; e < T; e += NTH) s_tot[e] = 0u;
     for (unsigned c0 = 0; c0 < n; c0 += CH) {
@@ -1260,7 +1249,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
         pk[u] = KEY_NONE;
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
-        if (e < n) pk[u] = entry_load<NR>(sg.lists, base + e, d[u]) & (T - 1u);
+        if (e < n) pk[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, e), d[u]) & (T - 1u);
       }
 #pragma unroll
       for (int u = 0; u < EPT; ++u)
