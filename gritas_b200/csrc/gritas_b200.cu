@@ -319,7 +319,8 @@ void launch_fast(gritas_b200_handle h, const ObsCols &c, const FilterDesc &f, in
 template <int NR>
 void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDesc &f) {
   const int nvec = (c.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
-  static const int per_sm = getenv("GRITAS_B200_K1_CTAS_PER_SM") ? std::max(1, atoi(getenv("GRITAS_B200_K1_CTAS_PER_SM"))) : 8;
+  // one resident wave (4 CTAs per SM, launch bounds of k_list_obs), grid-stride over the file
+  static const int per_sm = getenv("GRITAS_B200_K1_CTAS_PER_SM") ? std::max(1, atoi(getenv("GRITAS_B200_K1_CTAS_PER_SM"))) : 4;
   const int g1 = grid_for((size_t)nvec, K1_THREADS, per_sm);
   const size_t smem = levtab_smem_bytes(h->g);
   Status *st = h->d_status + 1 + w;
@@ -648,7 +649,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
                 h->nrec >= 4096;
     if (e_on && atoi(e_on) == 0) want = false;
     if (want) {
-      int shift = (nr == 1) ? 11 : 10;     // tile = 2048 / 1024 records: K2f keeps 3 / 2 CTAs per SM (sum planes + sort chunk)
+      int shift = (nr == 1) ? 11 : 10;     // tile = 2048 / 1024 records (measured best of 256..2048 at cfg2): K2f keeps 2 CTAs per SM
       if (e_shift) shift = atoi(e_shift);
       const int nv = (nr == 1) ? 2 : (nr == 2 ? 5 : 6);
       const size_t T = (size_t)1 << shift;

@@ -1017,9 +1017,10 @@ __device__ __forceinline__ double div_shared(double x, double d, double r) {
   const double q = __dmul_rn(x, r);
   const double rem = __fma_rn(-q, d, x);
   const double q2 = __fma_rn(rem, r, q);
-  // guard: huge / tiny magnitudes (overflow, underflow into subnormals) are not covered by the theorem
-  const double aq = fabs(q);
-  if (!(aq < 1.0e300) || (aq < 1.0e-290 && x != 0.0)) return __ddiv_rn(x, d);
+  // guard: huge / tiny magnitudes (overflow, underflow into subnormals), zero, inf and NaN are not covered by the
+  // theorem (or not worth covering): one test on the exponent field, 2^-960 <= |q| < 2^960 takes the fast result
+  const unsigned ex = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;
+  if (ex - 63u >= 1920u) return __ddiv_rn(x, d);
   return q2;
 }
 
@@ -1229,14 +1230,15 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   unsigned *s_warp = s_cnt + T + 4;                        // [32]
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
-  const unsigned PB = (T >= 2u * NTH) ? 2u : 1u;           // boxes per owner stretch
   const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
   for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
     const bool addrec = !fresh || sg.dirty[tile] != 0u;
-    for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = 0.0;
-    for (unsigned e = tid; e < T; e += NTH) s_tot[e] = 0u;
+    if (n == 0u) {                                          // empty list: nothing will store the planes
+      for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = 0.0;
+      for (unsigned e = tid; e < T; e += NTH) s_tot[e] = 0u;
+    }
     for (unsigned c0 = 0; c0 < n; c0 += CH) {
       for (unsigned e = tid; e <= T; e += NTH) s_cnt[e] = 0u;
       __syncthreads();
@@ -1302,34 +1304,16 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
         for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + pos] = d[u][ir];
       }
       __syncthreads();
-      // ---- the owner of a box adds its run.  A thread owns PB consecutive boxes, i.e. one contiguous stretch of the
-      // sorted chunk: one loop over the stretch (run lengths vary; the sum over PB boxes varies less) ----
-      for (unsigned b0 = tid * PB; b0 < T; b0 += NTH * PB) {
-        unsigned p = s_cnt[b0];
-        const unsigned pend = s_cnt[b0 + PB];
-        if (p == pend) continue;
-        unsigned b = b0, bend = s_cnt[b0 + 1u];
+      // ---- the owner of a box adds its run.  The first chunk STORES the sums (zeros for empty boxes: the planes are
+      // never cleared), later chunks add to them; with 512-record tiles most lists are a single chunk ----
+      const bool first_chunk = c0 == 0u;
+      for (unsigned b = tid; b < T; b += NTH) {
+        const unsigned s0 = s_cnt[b], e0 = s_cnt[b + 1u];
+        if (!first_chunk && e0 == s0) continue;
         double a[NV];
 #pragma unroll
         for (int q = 0; q < NV; ++q) a[q] = 0.0;
-        unsigned cn = 0u;
-        auto put = [&]() {
-          if (cn) {
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              s_val[(size_t)q * T + b] = __dadd_rn(s_val[(size_t)q * T + b], a[q]);
-              a[q] = 0.0;
-            }
-            s_tot[b] += cn;
-            cn = 0u;
-          }
-        };
-        for (; p < pend; ++p) {
-          while (p >= bend) {                               // next box of the stretch (empty boxes are skipped)
-            put();
-            ++b;
-            bend = s_cnt[b + 1u];
-          }
+        for (unsigned p = s0; p < e0; ++p) {
           double x[NR];
 #pragma unroll
           for (int ir = 0; ir < NR; ++ir) x[ir] = s_stage[(size_t)ir * CH + p];
@@ -1345,9 +1329,16 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
               a[2 * ir + 1] = __fma_rn(x[ir], x[ir], a[2 * ir + 1]);
             }
           }
-          ++cn;
         }
-        put();
+        if (first_chunk) {
+#pragma unroll
+          for (int q = 0; q < NV; ++q) s_val[(size_t)q * T + b] = a[q];
+          s_tot[b] = e0 - s0;
+        } else {
+#pragma unroll
+          for (int q = 0; q < NV; ++q) s_val[(size_t)q * T + b] = __dadd_rn(s_val[(size_t)q * T + b], a[q]);
+          s_tot[b] += e0 - s0;
+        }
       }
       // the next chunk zeroes s_cnt: every owner must be done with it
       __syncthreads();

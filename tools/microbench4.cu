@@ -1,0 +1,90 @@
+// microbench4.cu -- which part bounds K1 (column stream + ticket + interleaved entry store)?  One launch over a month.
+//   G0 stream only, G1 stream + ticket, G2 stream + store at a pseudo-ticket (no atomic), G3 all three
+// Not part of the product.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <stdlib.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x;
+}
+struct alignas(32) Entry { double a, b, c, d; };
+__device__ __forceinline__ void st256(Entry *p, unsigned key, double d1, double d2) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(__longlong_as_double((long long)key)), "d"(0.0), "d"(d1), "d"(d2) : "memory");
+}
+__device__ __forceinline__ double2 ld2(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+k_g(const double2 *a, const double2 *b, const double2 *c, const double2 *d, const double2 *e, const int4 *x, const int4 *y,
+    const int4 *z, size_t n4, unsigned *cnt, unsigned nc, Entry *lists, uint32_t seed, double *out) {
+  double sink = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    double2 p0 = ld2(a + 2 * i), p1 = ld2(a + 2 * i + 1), q0 = ld2(b + 2 * i), q1 = ld2(b + 2 * i + 1), r0 = ld2(c + 2 * i), r1 = ld2(c + 2 * i + 1);
+    int4 u = x[i], v = y[i], w = z[i];
+    const double geo[4] = {p0.x + q0.x + r0.x, p0.y + q0.y + r0.y, p1.x + q1.x + r1.x, p1.y + q1.y + r1.y};
+    const int ii[4] = {u.x + v.x + w.x, u.y + v.y + w.y, u.z + v.z + w.z, u.w + v.w + w.w};
+    unsigned t[4], pos[4];
+    bool acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t h = hash32((uint32_t)(4 * i + k) * 2654435761u + seed + (uint32_t)ii[k] + (uint32_t)__double2int_rn(geo[k]));
+      acc[k] = (h & 0xffu) < 207u;   // 81 %
+      t[k] = (unsigned)(((uint64_t)hash32(h) * nc) >> 32);
+    }
+    double2 d0 = ld2(d + 2 * i), d1 = ld2(d + 2 * i + 1), e0 = ld2(e + 2 * i), e1 = ld2(e + 2 * i + 1);
+    const double dd1[4] = {d0.x, d0.y, d1.x, d1.y}, dd2[4] = {e0.x, e0.y, e1.x, e1.y};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (MODE == 1 || MODE == 3) pos[k] = acc[k] ? atomicAdd(cnt + t[k], 1u) : 0u;
+      else pos[k] = (unsigned)((4 * i + k) * 0.81 / nc);      // what the ticket would roughly be
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!acc[k]) continue;
+      if (MODE >= 2) {
+        const size_t at = ((size_t)(pos[k] / 8) * nc + t[k]) * 8 + pos[k] % 8;
+        st256(lists + at, t[k], dd1[k], dd2[k]);
+      } else {
+        sink += dd1[k] + dd2[k] + pos[k];
+      }
+    }
+  }
+  if (sink == 1.2345) out[0] = sink;
+}
+int main() {
+  const unsigned nc = 26472;
+  const size_t n = 148u << 20;  // obs of one month
+  const size_t slots = (size_t)nc * 16384;
+  unsigned *cnt; Entry *lists; double *out;
+  CK(cudaMalloc(&cnt, 4u << 20)); CK(cudaMalloc(&lists, slots * sizeof(Entry))); CK(cudaMalloc(&out, 64));
+  double *cols[5]; int *ic[3];
+  for (auto &c : cols) { CK(cudaMalloc(&c, n * 8)); CK(cudaMemset(c, 0, n * 8)); }
+  for (auto &c : ic) { CK(cudaMalloc(&c, n * 4)); CK(cudaMemset(c, 0, n * 4)); }
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  const char *nm[4] = {"G0 stream only", "G1 stream + ticket", "G2 stream + store (pseudo-ticket)", "G3 stream + ticket + store"};
+  for (int mode = 0; mode < 4; ++mode)
+    for (int bps : {4, 8}) {
+      float best = 1e9f;
+      for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaMemset(cnt, 0, 4u << 20));
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(a);
+#define ARGS (double2 *)cols[0], (double2 *)cols[1], (double2 *)cols[2], (double2 *)cols[3], (double2 *)cols[4], (int4 *)ic[0], (int4 *)ic[1], (int4 *)ic[2], n / 4, cnt, nc, lists, 5u + rep, out
+        if (mode == 0) k_g<0><<<148 * bps, 256>>>(ARGS);
+        if (mode == 1) k_g<1><<<148 * bps, 256>>>(ARGS);
+        if (mode == 2) k_g<2><<<148 * bps, 256>>>(ARGS);
+        if (mode == 3) k_g<3><<<148 * bps, 256>>>(ARGS);
+        cudaEventRecord(b);
+        CK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        best = ms < best ? ms : best;
+      }
+      printf("  %-36s %d blk/SM : %7.3f ms  %6.2f G obs/s\n", nm[mode], bps, best, n / best / 1e6);
+    }
+  return 0;
+}
