@@ -108,10 +108,9 @@ struct gritas_b200_ctx {
   bool acc_fresh = true;       // records untouched since create / reset (apart from direct RED, see StageDesc::dirty)
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
-  size_t tile_smem = 0;
-  size_t tf_smem = 0;            // K2f (fused tile accumulate + finalize); 0: not available
+  size_t tf_smem = 0;            // shared memory of the tile kernel (K2f / K2t)
   int tf_ctas = 148;
-  int tile_ctas = 0;
+  bool fused_norm = true;        // Norm consumes the tile lists itself (K2f) instead of flush (K2t) + K3
   // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
   // the GPU; consecutive calls run on different streams (own level-1 scratch, own level-miss record) and
   // overlap.  Everything that reads or resets the accumulators runs on `compute` after join_workers().
@@ -331,12 +330,14 @@ void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDes
   }
 }
 
-// K2t over every tile with staged entries; afterwards the lists are empty.
+// K2t over tiles [t0, t1): the lists are added to the records and emptied.
 template <int NR>
 void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1) {
   if (t1 <= t0) return;
-  const int thr = h->tile_smem > 110 * 1024 ? 1024 : TILE_THREADS;   // one CTA per SM: give it all the warps
-  k_tile_accum<NR><<<(int)(t1 - t0), thr, h->tile_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, t0, t1, h->acc_fresh ? 1 : 0);
+  const OutPlanes none = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
+  k_tile_final<NR, true><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0, 0, 0,
+                                                                                   h->acc_fresh ? 1 : 0, t0, t1);
 }
 
 void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1) {
@@ -363,12 +364,13 @@ int flush_stage(gritas_b200_handle h) {
 template <int NR>
 void launch_tile_final(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
                        int raw2, int raw3) {
-  k_tile_final<NR><<<h->tf_ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, ntr,
-                                                                          raw2, raw3, h->acc_fresh ? 1 : 0);
+  k_tile_final<NR, false><<<h->tf_ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz,
+                                                                                 ntr, raw2, raw3, h->acc_fresh ? 1 : 0, 0u,
+                                                                                 h->sg.ntiles);
 }
 
 bool fused_norm_ok(gritas_b200_handle h) {
-  return h->staging && h->tf_smem != 0 && h->staged_upper > 0 && !h->minmax;
+  return h->staging && h->fused_norm && h->staged_upper > 0 && !h->minmax;
 }
 
 // Host side of every reader of the accumulators: copies done, lists flushed unless the reader consumes them itself
@@ -651,9 +653,9 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
     if (want) {
       int shift = (nr == 1) ? 11 : 10;     // tile = 2048 / 1024 records (measured best of 256..2048 at cfg2): K2f keeps 2 CTAs per SM
       if (e_shift) shift = atoi(e_shift);
-      const int nv = (nr == 1) ? 2 : (nr == 2 ? 5 : 6);
       const size_t T = (size_t)1 << shift;
-      const size_t smem = (size_t)nv * T * 8 + T * 4;
+      // the tile kernel (K2f / K2t) keeps the tile's sum planes and one sort chunk of its list in shared memory
+      const size_t smem = nr == 1 ? TileFinal<1>::smem_bytes(T) : (nr == 2 ? TileFinal<2>::smem_bytes(T) : TileFinal<3>::smem_bytes(T));
       size_t free_b = 0, total_b = 0;
       CUC(cudaMemGetInfo(&free_b, &total_b));
       const size_t entry = (nr == 1) ? ListEntry<1>::BYTES : ListEntry<2>::BYTES;
@@ -661,13 +663,11 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
       slots = std::min(slots, free_b / 4 / entry);
       const size_t ntiles = (h->nrec + T - 1) / T;
       size_t cap = (slots / ntiles) & ~(size_t)31;
-      if (cap >= 256 && smem <= 227 * 1024 && shift >= 8 && shift <= 16) {
+      if (cap >= 256 && smem <= (size_t)227 * 1024 && shift >= 8 && shift <= 15) {
         h->sg.tile_shift = shift;
         h->sg.ntiles = (unsigned)ntiles;
         h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffe0);
         h->stage_slots = ntiles * (size_t)h->sg.cap;
-        h->tile_smem = smem;
-        h->tile_ctas = (int)std::min(ntiles, (size_t)1 << 20);
         CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * 2 * ntiles));   // tickets + the per-tile dirty words
         CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * 2 * ntiles));
         h->sg.dirty = h->sg.fill + ntiles;
@@ -677,26 +677,24 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
           CUC(cudaStreamCreateWithFlags(&h->wk[w], cudaStreamNonBlocking));
           CUC(cudaEventCreateWithFlags(&h->wk_done[w], cudaEventDisableTiming));
         }
-        if (nr == 1) CUC(cudaFuncSetAttribute(k_tile_accum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_accum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CUC(cudaFuncSetAttribute(k_tile_accum<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nsm = 148, per_sm = 1;
+        CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+#define TF_SETUP(NR_)                                                                                                        \
+  do {                                                                                                                        \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<NR_, false>, TileFinal<NR_>::THREADS, smem));    \
+  } while (0)
+        if (nr == 1) TF_SETUP(1);
+        else if (nr == 2) TF_SETUP(2);
+        else TF_SETUP(3);
+#undef TF_SETUP
+        h->tf_smem = smem;
+        h->tf_ctas = (int)std::min((size_t)nsm * (size_t)std::max(per_sm, 1), ntiles);   // persistent: all CTAs resident
+        // GRITAS_B200_FUSED_NORM=0: Norm flushes the lists into the records (K2t) and finalizes them with K3
+        const char *e_f = getenv("GRITAS_B200_FUSED_NORM");
+        h->fused_norm = !(e_f && atoi(e_f) == 0);
         h->staging = true;
-        {  // K2f (fused tile accumulate + finalize): one CTA per SM with the sum planes and a sort chunk in shared memory
-          const size_t tf = nr == 1 ? TileFinal<1>::smem_bytes(T) : (nr == 2 ? TileFinal<2>::smem_bytes(T) : TileFinal<3>::smem_bytes(T));
-          const char *e_f = getenv("GRITAS_B200_FUSED_NORM");
-          if (tf <= (size_t)227 * 1024 && shift <= 15 && !(e_f && atoi(e_f) == 0)) {
-            if (nr == 1) CUC(cudaFuncSetAttribute(k_tile_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
-            else if (nr == 2) CUC(cudaFuncSetAttribute(k_tile_final<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
-            else CUC(cudaFuncSetAttribute(k_tile_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf));
-            h->tf_smem = tf;
-            int nsm = 148, per_sm = 1;
-            CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
-            if (nr == 1) CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<1>, TileFinal<1>::THREADS, tf));
-            else if (nr == 2) CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<2>, TileFinal<2>::THREADS, tf));
-            else CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<3>, TileFinal<3>::THREADS, tf));
-            h->tf_ctas = (int)std::min((size_t)nsm * (size_t)std::max(per_sm, 1), ntiles);   // persistent: all CTAs resident
-          }
-        }
         if (h->flags & GRITAS_B200_FLAG_FORCE_TILED) h->tiled_choice = 1;
         if (e_on && atoi(e_on) == 1) h->tiled_choice = 1;
       }

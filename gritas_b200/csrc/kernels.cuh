@@ -876,131 +876,9 @@ k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Tiled fast path, part 2 (K2t): one CTA per tile.  The tile's count / sum / sum-of-squares planes
-// live in shared memory (privatised histogram); the tile's list streams in coalesced; lanes of a warp
-// that hit the same box are combined first (__match_any_sync) and only then touch shared memory;
-// the tile is finally added to the HBM records with plain coalesced read-modify-writes (the tile is
-// owned by this CTA: no global atomics).
+// Sum planes of a tile per number of residual columns: nr=1 {Sx, Sxx}, nr=2 {Sx1, Sxx1, Sx2, Sxx2, Sx1x2}, nr=3 three pairs.
 template <int NR>
 struct TilePlanes { static constexpr int NV = (NR == 1) ? 2 : (NR == 2 ? 5 : 6); };
-constexpr int TILE_THREADS = 512;
-constexpr int TILE_ILP = 2;
-
-template <int NR>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
-k_tile_accum(const GridDesc g, const StageDesc sg, unsigned nrec, unsigned tile0, unsigned tile1, int fresh) {
-  constexpr int NV = TilePlanes<NR>::NV;
-  extern __shared__ double s_val[];                       // NV planes of T doubles, then T counts
-  const unsigned T = 1u << sg.tile_shift;
-  unsigned *s_cnt = reinterpret_cast<unsigned *>(s_val + (size_t)NV * T);
-  const int rs_shift = (g.rs == 4) ? 2 : 3;
-  // first flush after a reset and nothing was accumulated directly: the records are zero, store instead of RMW
-  for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
-    const unsigned n = min(sg.fill[tile], sg.cap);
-    if (n == 0) continue;                                 // uniform across the CTA
-    const bool overwrite = fresh && sg.dirty[tile] == 0u;
-    for (unsigned e = threadIdx.x; e < NV * T; e += blockDim.x) s_val[e] = 0.0;
-    for (unsigned e = threadIdx.x; e < T; e += blockDim.x) s_cnt[e] = 0u;
-    __syncthreads();
-    const unsigned stride = blockDim.x * TILE_ILP;
-    const unsigned nround = (n + stride - 1) / stride * stride;   // whole warps iterate together
-    for (unsigned r0 = threadIdx.x; r0 < nround; r0 += stride) {
-      unsigned bx[TILE_ILP];
-      double d[TILE_ILP][NR];
-#pragma unroll
-      for (int u = 0; u < TILE_ILP; ++u) {                // all loads of the round first
-        const unsigned r = r0 + u * blockDim.x;
-        bx[u] = 0xFFFFFFFFu;
-#pragma unroll
-        for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
-        if (r < n) bx[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, r), d[u]) & (T - 1u);
-      }
-#pragma unroll
-      for (int u = 0; u < TILE_ILP; ++u) {
-        const unsigned b = bx[u];
-        const bool live = b != 0xFFFFFFFFu;
-        double v[NV];
-        if (NR == 1) { v[0] = d[u][0]; v[1] = __dmul_rn(d[u][0], d[u][0]); }
-        if (NR == 2) {
-          v[0] = d[u][0]; v[1] = __dmul_rn(d[u][0], d[u][0]);
-          v[2] = d[u][NR - 1]; v[3] = __dmul_rn(d[u][NR - 1], d[u][NR - 1]);
-          v[4] = __dmul_rn(d[u][0], d[u][NR - 1]);
-        }
-        if (NR == 3) {
-#pragma unroll
-          for (int ir = 0; ir < NR; ++ir) { v[2 * ir] = d[u][ir]; v[2 * ir + 1] = __dmul_rn(d[u][ir], d[u][ir]); }
-        }
-        unsigned cnt = 1u;
-        bool issue = live;
-        // warp aggregation: only pays (and only runs) when lanes collide, i.e. clustered data
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        const bool multi = live && (peers & (peers - 1u));
-        if (__any_sync(0xffffffffu, multi)) {
-          const int lane = threadIdx.x & 31;
-          const int leader = __ffs(peers) - 1;
-          const int npeer = live ? __popc(peers) : 1;
-          const int maxc = __reduce_max_sync(0xffffffffu, npeer);
-          unsigned others = peers & ~(1u << leader);
-          for (int it = 1; it < maxc; ++it) {
-            const int src = others ? (__ffs(others) - 1) : lane;
-            others &= others - 1u;
-            const bool take = (lane == leader) && (it < npeer);
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-              const double a = __shfl_sync(0xffffffffu, v[q], src);
-              if (take) v[q] = __dadd_rn(v[q], a);
-            }
-          }
-          cnt = (unsigned)npeer;
-          issue = live && (lane == leader);
-        }
-        if (issue) {
-          atomicAdd(s_cnt + b, cnt);
-#pragma unroll
-          for (int q = 0; q < NV; ++q) atomicAdd(s_val + (size_t)q * T + b, v[q]);
-        }
-      }
-    }
-    __syncthreads();
-    // add the tile to the HBM records: element e of the tile's span is (box e >> rs_shift, slot e & (rs-1));
-    // each thread handles pairs of doubles (16 B), four pairs in flight
-    const size_t first = (size_t)tile << sg.tile_shift;
-    const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
-    double2 *span = reinterpret_cast<double2 *>(g.acc + first * (size_t)g.rs);
-    const unsigned npair = (nb << rs_shift) >> 1;
-    for (unsigned e0 = threadIdx.x; e0 < npair; e0 += blockDim.x * 4u) {
-      double2 cur[4], add[4];
-      bool any[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const unsigned e = e0 + u * blockDim.x;
-        any[u] = false;
-        if (e < npair) {
-          const unsigned el = e << 1, bxi = el >> rs_shift, slot = el & ((1u << rs_shift) - 1u);
-          const unsigned cn = s_cnt[bxi];
-          // overwrite: the pad slots are stored too (zeros), so that only whole 32-byte sectors reach L2
-          if (cn != 0u && (overwrite || slot <= (unsigned)NV)) {
-            any[u] = true;
-            add[u].x = (slot == 0u) ? (double)cn : (slot <= (unsigned)NV ? s_val[(size_t)(slot - 1u) * T + bxi] : 0.0);
-            add[u].y = (slot + 1u <= (unsigned)NV) ? s_val[(size_t)slot * T + bxi] : 0.0;
-            cur[u] = overwrite ? make_double2(0.0, 0.0) : span[e];
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (any[u]) {
-          cur[u].x = __dadd_rn(cur[u].x, add[u].x);
-          cur[u].y = __dadd_rn(cur[u].y, add[u].y);
-          span[e0 + u * blockDim.x] = cur[u];
-        }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) sg.fill[tile] = 0u;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // K3 finalize.  Output planes per box, in this order: bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs.
@@ -1192,16 +1070,20 @@ k_add_raw(const GridDesc g, OutPlanes in, int is3d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2f: tile accumulate FUSED with finalize -- what GrITAS_Norm runs when the month is still parked in the
-// tile lists (one process, no reduction across ranks).  One CTA per tile, nothing is written but the output
-// planes: the records (1.7 GB at cfg2) are neither written by a flush nor read back by K3, and the lists
-// stay as they are (Norm does not change the accumulation state).
+// Tiled fast path, part 2: one CTA per tile accumulates the tile's list in shared memory, then either
+//   K2f (FLUSH = false): finalizes straight from shared memory -- what GrITAS_Norm runs when the month is still
+//        parked in the tile lists (one process, no reduction across ranks).  Nothing is written but the output
+//        planes: the records (1.7 GB at cfg2) are neither written by a flush nor read back by K3, and the lists stay
+//        as they are (Norm does not change the accumulation state);
+//   K2t (FLUSH = true): adds the tile to its HBM records with plain coalesced read-modify-writes (the tile is owned
+//        by this CTA: no global atomics; stores when the records are known to be zero) and empties the list --
+//        the flush when the lists fill up and before a reduction across ranks.
 //
-// No floating-point atomics: shared memory has no native fp64 add (k_tile_accum spends its time in CAS
-// loops).  Instead every chunk of the list is counting-sorted by box inside the CTA -- one native int32
-// shared-memory atomic per entry gives the entry its rank within the box, a scan of the per-box counts gives
-// the box's start, the residuals are dropped into shared memory at start + rank -- and the thread that owns
-// a box then adds the box's run with plain DADDs into the tile's sum planes.  The planes double as the
+// No floating-point atomics: shared memory has no native fp64 add (a CAS loop per add; an earlier version of this
+// kernel spent its time there).  Instead every chunk of the list is counting-sorted by box inside the CTA -- one
+// native int32 shared-memory atomic per entry gives the entry its rank within the box, a scan of the per-box counts
+// gives the box's start, the residuals are dropped into shared memory at start + rank -- and the thread that owns a
+// box then adds the box's run with plain DADD/DFMAs into the tile's sum planes.  The planes double as the
 // transposition buffer: the finalize step walks the tile level by level (the records are level-fastest, the
 // reference's arrays longitude-fastest) and writes each plane in runs of ~tile/km consecutive doubles.
 template <int NR>
@@ -1215,10 +1097,10 @@ struct TileFinal {
   }
 };
 
-template <int NR>
+template <int NR, bool FLUSH>
 __global__ void __launch_bounds__(TileFinal<NR>::THREADS, 2)
 k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh,
-             int raw2, int raw3, int fresh) {
+             int raw2, int raw3, int fresh, unsigned tile0, unsigned tile1) {
   using TF = TileFinal<NR>;
   constexpr int NV = TF::NV, EPT = TF::EPT, CH = TF::CH, NTH = TF::THREADS;
   extern __shared__ __align__(16) double s_dyn[];
@@ -1231,8 +1113,9 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
   const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
-  for (unsigned tile = blockIdx.x; tile < sg.ntiles; tile += gridDim.x) {
+  for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     const unsigned n = min(sg.fill[tile], sg.cap);
+    if (FLUSH && n == 0u) continue;                       // uniform across the CTA
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
     const bool addrec = !fresh || sg.dirty[tile] != 0u;
     if (n == 0u) {                                          // empty list: nothing will store the planes
@@ -1344,9 +1227,48 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       __syncthreads();
     }
     __syncthreads();
-    // ---- finalize (m_gritas_grids.f:566-654) straight from the planes ----
     const size_t first = (size_t)tile << sg.tile_shift;
     const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
+    if (FLUSH) {
+      // ---- add the tile to the HBM records: element e of the tile's span is (box e >> rs_shift, slot e & (rs-1));
+      // each thread handles pairs of doubles (16 B), four pairs in flight.  Untouched records are zero: store, and
+      // store the pad slots too, so that only whole 32-byte sectors reach L2 ----
+      const int rs_shift = (g.rs == 4) ? 2 : 3;
+      const bool overwrite = !addrec;
+      double2 *span = reinterpret_cast<double2 *>(g.acc + first * (size_t)g.rs);
+      const unsigned npair = (nb << rs_shift) >> 1;
+      for (unsigned e0 = tid; e0 < npair; e0 += NTH * 4u) {
+        double2 cur[4], add[4];
+        bool any[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned e = e0 + u * NTH;
+          any[u] = false;
+          if (e < npair) {
+            const unsigned el = e << 1, bxi = el >> rs_shift, slot = el & ((1u << rs_shift) - 1u);
+            const unsigned cn = s_tot[bxi];
+            if (cn != 0u && (overwrite || slot <= (unsigned)NV)) {
+              any[u] = true;
+              add[u].x = (slot == 0u) ? (double)cn : (slot <= (unsigned)NV ? s_val[(size_t)(slot - 1u) * T + bxi] : 0.0);
+              add[u].y = (slot + 1u <= (unsigned)NV) ? s_val[(size_t)slot * T + bxi] : 0.0;
+              cur[u] = overwrite ? make_double2(0.0, 0.0) : span[e];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (any[u]) {
+            cur[u].x = __dadd_rn(cur[u].x, add[u].x);
+            cur[u].y = __dadd_rn(cur[u].y, add[u].y);
+            span[e0 + u * NTH] = cur[u];
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0u) sg.fill[tile] = 0u;
+      continue;
+    }
+    // ---- finalize (m_gritas_grids.f:566-654) straight from the planes ----
     auto box = [&](unsigned b, bool is3d, bool zero, int raw, const OutPlanes &out, size_t o, size_t plane) {
       double r[8];
 #pragma unroll
