@@ -891,6 +891,8 @@ struct OutPlanes {
 // q = RN(x r) is a faithful quotient and one residual correction with two FMAs, q' = RN(q + RN(x - q d) r),
 // is the correctly rounded quotient (Markstein's theorem; x - q d is exact in an FMA).  Non-finite or
 // vanishing intermediate results fall back to the IEEE division.  Bit-identical to __ddiv_rn.
+__device__ __noinline__ double div_ieee(double x, double d) { return __ddiv_rn(x, d); }   // rare: one copy, never speculated
+
 __device__ __forceinline__ double div_shared(double x, double d, double r) {
   const double q = __dmul_rn(x, r);
   const double rem = __fma_rn(-q, d, x);
@@ -898,7 +900,7 @@ __device__ __forceinline__ double div_shared(double x, double d, double r) {
   // guard: huge / tiny magnitudes (overflow, underflow into subnormals), zero, inf and NaN are not covered by the
   // theorem (or not worth covering): one test on the exponent field, 2^-960 <= |q| < 2^960 takes the fast result
   const unsigned ex = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;
-  if (ex - 63u >= 1920u) return __ddiv_rn(x, d);
+  if (ex - 63u >= 1920u) return div_ieee(x, d);
   return q2;
 }
 
@@ -932,8 +934,8 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
   // non-zero divisor, anything else takes the plain division (inf / NaN results exactly as the reference)
   const bool fast_m = some && dm >= 1.0, fast_m1 = many && dm1 >= 1.0;
   const double rm = fast_m ? __drcp_rn(dm) : 0.0, rm1 = fast_m1 ? __drcp_rn(dm1) : 0.0;
-  auto div_m = [&](double x) { return fast_m ? div_shared(x, dm, rm) : __ddiv_rn(x, dm); };
-  auto div_m1 = [&](double x) { return fast_m1 ? div_shared(x, dm1, rm1) : __ddiv_rn(x, dm1); };
+  auto div_m = [&](double x) { return fast_m ? div_shared(x, dm, rm) : div_ieee(x, dm); };
+  auto div_m1 = [&](double x) { return fast_m1 ? div_shared(x, dm1, rm1) : div_ieee(x, dm1); };
   double tmp[NR], xtmp = 0.0;
   if (some) {
 #pragma unroll
