@@ -31,7 +31,7 @@
       implicit none
       private
 
-      public :: B200_Accum_, B200_Norm_, B200_GetRaw, B200_Reset, B200_Clean
+      public :: B200_Accum_, B200_Norm_, B200_3CH_Norm_, B200_GetRaw, B200_Reset, B200_Clean
       public :: B200_MinMax_, B200_SetMask
       public :: B200_SetMode
 
@@ -75,6 +75,16 @@
             integer(c_int), value             :: nrmlz, ntresh
             real(c_double), intent(inout)     :: bias_2d(*), rtms_2d(*), stdv_2d(*), xcov_2d(*), nobs_2d(*)
             real(c_double), intent(inout)     :: bias_3d(*), rtms_3d(*), stdv_3d(*), xcov_3d(*), nobs_3d(*)
+         end function
+         integer(c_int) function gritas_b200_norm_3ch ( h, nrmlz, ntresh,                       &
+                                  bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d,                   &
+                                  bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d )                  &
+                                  bind(C, name='gritas_b200_norm_3ch')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            integer(c_int), value             :: nrmlz, ntresh
+            real(c_double), intent(inout)     :: bias_2d(*), rtms_2d(*), var_2d(*), xcov_2d(*), nobs_2d(*)
+            real(c_double), intent(inout)     :: bias_3d(*), rtms_3d(*), var_3d(*), xcov_3d(*), nobs_3d(*)
          end function
          integer(c_int) function gritas_b200_get_raw ( h, bias_2d, rtms_2d, xcov_2d, nobs_2d,   &
                                   bias_3d, rtms_3d, xcov_3d, nobs_3d )                          &
@@ -176,6 +186,32 @@
                               bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d )
       if ( rc /= 0 ) call gritas_perror ('Norm: B200 finalize failed')
       end subroutine B200_Norm_
+
+!     Same argument list as GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1181; gritas.f:813-818, -tch).
+      subroutine B200_3CH_Norm_ ( nr, nrmlz,                                                    &
+                                  l2d, bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d,              &
+                                  l3d, bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d,              &
+                                  ntresh )
+      use m_gritas_grids, only : im, jm, km
+      integer, intent(in)           :: nr, l2d, l3d
+      logical, intent(in)           :: nrmlz
+      integer, OPTIONAL, intent(in) :: ntresh
+      real, intent(inout) :: bias_2d(im,jm,l2d,nr), rtms_2d(im,jm,l2d,nr), xcov_2d(im,jm,l2d,nr)
+      real, intent(inout) :: var_2d(im,jm,l2d,nr), nobs_2d(im,jm,l2d)
+      real, intent(inout) :: bias_3d(im,jm,km,l3d,nr), rtms_3d(im,jm,km,l3d,nr), xcov_3d(im,jm,km,l3d,nr)
+      real, intent(inout) :: var_3d(im,jm,km,l3d,nr), nobs_3d(im,jm,km,l3d)
+
+      integer(c_int) :: rc, inrm, intr
+
+      if ( nr > 3 ) call gritas_perror ('GrITAS_3CH_Norm_ could not handle more then 2 residuals')   ! :1240
+      inrm = 0
+      if ( nrmlz ) inrm = 1
+      intr = -1                                                         ! "absent"
+      if ( present(ntresh) ) intr = ntresh
+      rc = gritas_b200_norm_3ch ( handle, inrm, intr, bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d, &
+                                  bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d )
+      if ( rc /= 0 ) call gritas_perror ('3CH_Norm: B200 finalize failed')
+      end subroutine B200_3CH_Norm_
 
 !     Same argument list as GrITAS_MinMax_ (m_gritas_grids.f:1019-1023).  Unlike Accum/Norm there is no
 !     separate finalize call in the driver (gritas.f:884 skips Norm with -minmax), so the min / max / count

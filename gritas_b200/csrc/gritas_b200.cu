@@ -982,11 +982,11 @@ static int launch_finalize(gritas_b200_handle h, cudaStream_t sm, double *const 
     h->launches++;
   }
   if (g.nbox3 && jl1 > jl0) {
-    OutPlanes o = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && !raw) ? 1 : xpl};
+    OutPlanes o = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && (raw == 0 || raw == 3)) ? 1 : xpl};
     dim3 blk(32, 32), grd((g.km + 31) / 32, (g.im + 31) / 32, 1);
     const int z = jl1 - jl0;
     grd.z = (unsigned)(z > 65535 ? 65535 : z);
-    const int r3 = raw == 2 ? 2 : (raw3 ? 1 : 0);
+    const int r3 = raw == 2 ? 2 : (raw3 ? 1 : raw);
     const size_t fsm = sizeof(double) * (size_t)(4 * nr + 1) * 32 * 33;
     if (nr == 1) {
       CU(cudaFuncSetAttribute(k_finalize3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
@@ -1014,12 +1014,13 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   const GridDesc &g = h->g;
   const int nr = g.nr;
   if (!raw && nr > 2) return fail(h, GRITAS_B200_ERR_NR, "Accum: could not handle more then 2 residuals");  // :555
+  if (raw == 3 && nr != 3) return fail(h, GRITAS_B200_ERR_NR, "GrITAS_3CH_Norm_ could not handle more then 2 residuals");  // :1240
   const size_t n2 = g.nbox2, n3 = g.nbox3;
   if (!raw && h->minmax) return fail(h, GRITAS_B200_ERR_ARG, "Norm on a MinMax handle: use gritas_b200_get_minmax (gritas.f:884 skips Norm)");
-  const int xpl = raw ? 1 : nr;
+  const int xpl = (raw == 1 || raw == 2) ? 1 : nr;    // raw == 3: GrITAS_3CH_Norm_, three 3CH planes in xcov
   const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
   // nlevs<2: the reference returns before the 3-D loop (m_gritas_grids.f:607) -> 3-D sums stay raw
-  const bool raw3 = raw || g.nlevs < 2;
+  const bool raw3 = raw == 1 || raw == 2 || g.nlevs < 2;   // (also m_gritas_grids.f:1292 for the 3CH variant)
   const bool piped = reduce_root >= 0 && h->comm != nullptr && h->nranks > 1;
   const bool writer = !piped || h->rank == reduce_root;
   double *dst[10];
@@ -1029,7 +1030,8 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     bounce[a] = false;
     dst[a] = nullptr;
     const bool skip = !writer || (!user[a] && !dev_out) || sz[a] == 0 || (raw == 1 && (a == 2 || a == 7)) ||
-                      (raw == 2 && (a == 1 || a == 3 || a == 6 || a == 8)) || (!raw && raw3 && a == 7);
+                      (raw == 2 && (a == 1 || a == 3 || a == 6 || a == 8)) || (!raw && raw3 && a == 7) ||
+                      (raw == 3 && raw3 && (a == 7 || a == 8));
     if (skip) continue;
     if (!dev_out && mem_kind(user[a]) == 2) dst[a] = user[a];
     else { bounce[a] = true; need += sz[a]; }
@@ -1047,11 +1049,12 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     int rc = join_workers(h);
     if (rc) return rc;
     const OutPlanes o2 = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
-    const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && !raw) ? 1 : xpl};
+    const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && (raw == 0 || raw == 3)) ? 1 : xpl};
+    const int r3 = raw3 ? 1 : raw;
     switch (nr) {
-      case 1: launch_tile_final<1>(h, h->compute, o2, o3, nrmlz, ntr, raw, raw3 ? 1 : 0); break;
-      case 2: launch_tile_final<2>(h, h->compute, o2, o3, nrmlz, ntr, raw, raw3 ? 1 : 0); break;
-      default: launch_tile_final<3>(h, h->compute, o2, o3, nrmlz, ntr, raw, raw3 ? 1 : 0); break;
+      case 1: launch_tile_final<1>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
+      case 2: launch_tile_final<2>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
+      default: launch_tile_final<3>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
     }
     CU(cudaGetLastError());
     h->launches++;
@@ -1129,6 +1132,19 @@ int gritas_b200_norm(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2
   if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
   double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
   return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
+}
+
+// GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341; gritas.f:813-818, -tch): three residual series; var_* receive the variances
+// (no square root), xcov_* the three-cornered-hat estimates.
+int gritas_b200_norm_3ch(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d, double *var_2d,
+                         double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *var_3d,
+                         double *xcov_3d, double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (h->g.nr != 3) return fail(h, GRITAS_B200_ERR_NR, "GrITAS_3CH_Norm_ needs three residual series (nr = %d)", h->g.nr);
+  if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
+  double *const u[10] = {bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d};
+  return finalize_to(h, 3, nrmlz ? 1 : 0, ntresh, u, nullptr);
 }
 
 int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **bias_2d, const double **rtms_2d,

@@ -918,6 +918,37 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
     stdv[0] = f64_from_order_key(__double_as_longlong(rec[2]));
     return;
   }
+  if (NR == 3 && raw == 3) {   // GrITAS_3CH_Norm_ (m_gritas_grids.f:1247-1339): variances + three-cornered-hat estimates
+    const int m = nrmlz ? (int)n : 1;
+    const double dm = (double)m, dm1 = (double)(m - 1);
+    const bool some = (n > 0.0) && (n >= (double)ntresh);
+    const bool many = (n > 1.0) && (n >= (double)ntresh);
+    const bool one = !many && is3d && n == 1.0;                           // :1322 (the 2-D block has no such case)
+    double var[NR];
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) {
+      double tmp = 0.0;
+      if (some) {
+        bias[ir] = div_ieee(rec[1 + 2 * ir], dm);
+        const double t = div_ieee(rec[2 + 2 * ir], dm);
+        rtms[ir] = __dsqrt_rn(t);
+        tmp = fabs(__dsub_rn(t, __dmul_rn(bias[ir], bias[ir])));
+      } else {
+        bias[ir] = AMISS;
+        rtms[ir] = AMISS;
+      }
+      var[ir] = many ? div_ieee(__dmul_rn(dm, tmp), dm1) : (one ? tmp : AMISS);
+      stdv[ir] = var[ir];
+    }
+    // the whole-array expressions of :1287-1289 / :1337-1339 run over missing values too; slots 2 and 3 are combined
+    // in a different order in the 2-D and the 3-D block
+    const double v1 = var[0], v2 = var[1], v3 = var[NR - 1];
+    xcov[0] = __dmul_rn(0.5, __dsub_rn(__dadd_rn(v1, v2), v3));
+    const double a = __dmul_rn(0.5, __dsub_rn(__dadd_rn(v2, v3), v1)), b = __dmul_rn(0.5, __dsub_rn(__dadd_rn(v3, v1), v2));
+    xcov[1] = is3d ? b : a;
+    xcov[NR - 1] = is3d ? a : b;
+    return;
+  }
   const double xraw = (NR == 1) ? rec[2] : (NR == 2 ? rec[5] : 0.0);  // nr=3: xcov untouched (:397-401)
   if (raw) {
 #pragma unroll

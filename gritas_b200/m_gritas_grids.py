@@ -220,6 +220,20 @@ class Grids:
                                           p(bias_3d), p(rtms_3d), p(stdv_3d), p(xcov_3d), p(nobs_3d))
         self._check(rc)
 
+    # ---- GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341; gritas.f:813-818, -tch) -------------
+    def GrITAS_3CH_Norm(self, nr, nrmlz, l2d, bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d,
+                        l3d, bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d, ntresh=None):
+        if nr > 3:
+            raise GritasPerror("GrITAS_3CH_Norm_ could not handle more then 2 residuals")  # :1240 (sic)
+        if self._h is None:
+            raise RuntimeError("GrITAS_3CH_Norm before any GrITAS_Accum")
+        assert nr == self.nr and l2d == self.l2d and l3d == self.l3d
+        p = lambda a: cabi.ptr(a, np.float64)
+        rc = cabi.load().gritas_b200_norm_3ch(self._h, 1 if nrmlz else 0, -1 if ntresh is None else int(ntresh),
+                                              p(bias_2d), p(rtms_2d), p(var_2d), p(xcov_2d), p(nobs_2d),
+                                              p(bias_3d), p(rtms_3d), p(var_3d), p(xcov_3d), p(nobs_3d))
+        self._check(rc)
+
     def get_raw(self, bias_2d, rtms_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, xcov_3d, nobs_3d):
         p = lambda a: cabi.ptr(a, np.float64)
         self._check(cabi.load().gritas_b200_get_raw(self._h, p(bias_2d), p(rtms_2d), p(xcov_2d), p(nobs_2d),

@@ -166,6 +166,17 @@ int gritas_b200_norm(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2
                      double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *stdv_3d,
                      double *xcov_3d, double *nobs_3d);
 
+/*
+ * Replaces GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341; called by gritas.f:813-818 under -tch): the handle
+ * accumulates three residual series (nr = 3).  bias (mean) and rtms as above, var_* receive the variances (no
+ * square root, :1273 / :1320), xcov_*(...,1:3) the three-cornered-hat estimates -- combined exactly as the
+ * reference's whole-array expressions do (:1287-1289, :1337-1339; missing values take part, the 2-D and the 3-D block
+ * order slots 2 and 3 differently).  Returns GRITAS_B200_ERR_NR unless nr = 3.
+ */
+int gritas_b200_norm_3ch(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d, double *var_2d,
+                         double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *var_3d,
+                         double *xcov_3d, double *nobs_3d);
+
 /* Same finalize, results left in device memory (for callers that post-process on the GPU and for
  * timing the kernel without the D2H copy).  Pointers stay valid until the next norm/destroy. */
 int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **bias_2d,

@@ -492,6 +492,97 @@ int orc_norm(int im, int jm, int km, int nlevs, int nr, int nrmlz, int l2d, doub
   return 0;
 }
 
+/* GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341): the normalisation of a -tch (three-cornered hat) run, nr = 3 residual
+ * series.  Means and rms as in GrITAS_Norm_, but the third output is the VARIANCE (no square root, :1274, :1322) and
+ * xcov receives the 3CH estimates.  Kept literally: the whole-array 3CH expressions run over missing values too
+ * (0.5*(AMISS+AMISS-AMISS)), the 2-D and the 3-D blocks combine the variances in a DIFFERENT order for slots 2 and 3
+ * (:1287-1289 vs :1337-1339), a 3-D box with one observation keeps tmp (:1324-1325) while the 2-D one is missing, and
+ * with nlevs < 2 the routine returns before the 3-D block (:1292). */
+int orc_norm_3ch(int im, int jm, int km, int nlevs, int nr, int nrmlz, int l2d, double *bias_2d,
+                 double *rtms_2d, double *var_2d, double *xcov_2d, double *nobs_2d, int l3d,
+                 double *bias_3d, double *rtms_3d, double *var_3d, double *xcov_3d, double *nobs_3d,
+                 int ntresh) {
+  int i, j, k, l, m, ir;
+  double tmp[3] = {0.0, 0.0, 0.0}, n;
+  if (nr != 3) return 8;                      /* :1240 rejects nr > 3; the 3CH expressions need exactly three series */
+
+  m = 1;                                                                   /* :1247 */
+  for (l = 1; l <= l2d; ++l)
+    for (j = 1; j <= jm; ++j)
+      for (i = 1; i <= im; ++i) {
+        n = nobs_2d[IX2(i, j, l, 1)];                                      /* :1252 */
+        if (nrmlz) m = (int)n;                                             /* :1253 */
+        if (n > 0.0 && n >= (double)ntresh) {                              /* :1254-1260 */
+          for (ir = 1; ir <= nr; ++ir) {
+            bias_2d[IX2(i, j, l, ir)] = bias_2d[IX2(i, j, l, ir)] / (double)m;
+            tmp[ir - 1] = rtms_2d[IX2(i, j, l, ir)] / (double)m;
+            rtms_2d[IX2(i, j, l, ir)] = sqrt(tmp[ir - 1]);
+            tmp[ir - 1] = fabs(tmp[ir - 1] - bias_2d[IX2(i, j, l, ir)] * bias_2d[IX2(i, j, l, ir)]);
+          }
+        } else {                                                           /* :1261-1266 */
+          for (ir = 1; ir <= nr; ++ir) {
+            bias_2d[IX2(i, j, l, ir)] = ORC_AMISS;
+            rtms_2d[IX2(i, j, l, ir)] = ORC_AMISS;
+          }
+        }
+        if (n > 1.0 && n >= (double)ntresh) {                              /* :1269-1272 */
+          for (ir = 1; ir <= nr; ++ir) var_2d[IX2(i, j, l, ir)] = (double)m * tmp[ir - 1] / (double)(m - 1);
+        } else {                                                           /* :1273-1277 */
+          for (ir = 1; ir <= nr; ++ir) var_2d[IX2(i, j, l, ir)] = ORC_AMISS;
+        }
+      }
+  for (l = 1; l <= l2d; ++l)                                               /* :1287-1289 */
+    for (j = 1; j <= jm; ++j)
+      for (i = 1; i <= im; ++i) {
+        const double v1 = var_2d[IX2(i, j, l, 1)], v2 = var_2d[IX2(i, j, l, 2)], v3 = var_2d[IX2(i, j, l, 3)];
+        xcov_2d[IX2(i, j, l, 1)] = 0.5 * (v1 + v2 - v3);
+        xcov_2d[IX2(i, j, l, 2)] = 0.5 * (v2 + v3 - v1);
+        xcov_2d[IX2(i, j, l, 3)] = 0.5 * (v3 + v1 - v2);
+      }
+
+  if (nlevs < 2) return 0;                                                 /* :1292 */
+
+  m = 1;                                                                   /* :1297 */
+  for (l = 1; l <= l3d; ++l)
+    for (k = 1; k <= nlevs; ++k)
+      for (j = 1; j <= jm; ++j)
+        for (i = 1; i <= im; ++i) {
+          n = nobs_3d[IX3(i, j, k, l, 1)];                                 /* :1303 */
+          if (nrmlz) m = (int)n;                                           /* :1304 */
+          if (n > 0.0 && n >= (double)ntresh) {                            /* :1305-1311 */
+            for (ir = 1; ir <= nr; ++ir) {
+              bias_3d[IX3(i, j, k, l, ir)] = bias_3d[IX3(i, j, k, l, ir)] / (double)m;
+              tmp[ir - 1] = rtms_3d[IX3(i, j, k, l, ir)] / (double)m;
+              rtms_3d[IX3(i, j, k, l, ir)] = sqrt(tmp[ir - 1]);
+              tmp[ir - 1] =
+                  fabs(tmp[ir - 1] - bias_3d[IX3(i, j, k, l, ir)] * bias_3d[IX3(i, j, k, l, ir)]);
+            }
+          } else {                                                         /* :1312-1317 */
+            for (ir = 1; ir <= nr; ++ir) {
+              bias_3d[IX3(i, j, k, l, ir)] = ORC_AMISS;
+              rtms_3d[IX3(i, j, k, l, ir)] = ORC_AMISS;
+            }
+          }
+          if (n > 1.0 && n >= (double)ntresh) {                            /* :1319-1320 */
+            for (ir = 1; ir <= nr; ++ir) var_3d[IX3(i, j, k, l, ir)] = (double)m * tmp[ir - 1] / (double)(m - 1);
+          } else if (n == 1.0) {                                           /* :1322-1323: stale tmp if ntresh > 1 */
+            for (ir = 1; ir <= nr; ++ir) var_3d[IX3(i, j, k, l, ir)] = tmp[ir - 1];
+          } else {                                                         /* :1324-1325 */
+            for (ir = 1; ir <= nr; ++ir) var_3d[IX3(i, j, k, l, ir)] = ORC_AMISS;
+          }
+        }
+  for (l = 1; l <= l3d; ++l)                                               /* :1337-1339: ALL km levels */
+    for (k = 1; k <= km; ++k)
+      for (j = 1; j <= jm; ++j)
+        for (i = 1; i <= im; ++i) {
+          const double v1 = var_3d[IX3(i, j, k, l, 1)], v2 = var_3d[IX3(i, j, k, l, 2)], v3 = var_3d[IX3(i, j, k, l, 3)];
+          xcov_3d[IX3(i, j, k, l, 1)] = 0.5 * (v1 + v2 - v3);
+          xcov_3d[IX3(i, j, k, l, 2)] = 0.5 * (v3 + v1 - v2);
+          xcov_3d[IX3(i, j, k, l, 3)] = 0.5 * (v2 + v3 - v1);
+        }
+  return 0;
+}
+
 /* gritas.f:1002-1003: nobs / nredundant (ensemble files valid at the same time). */
 void orc_div_nredundant(size_t n, double *nobs_grid, int nredundant) {
   size_t i;

@@ -69,6 +69,8 @@ def lib():
         L.orc_norm.argtypes = ([C.c_int] * 6 + [C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p,
                                                 C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_int])
         L.orc_norm.restype = C.c_int
+        L.orc_norm_3ch.argtypes = L.orc_norm.argtypes
+        L.orc_norm_3ch.restype = C.c_int
         _lib = L
     return _lib
 
@@ -234,6 +236,15 @@ def norm(g: Grids, nlevs, nrmlz=True, ntresh=0):
                         g.l3d, g.bias_3d, g.rtms_3d, g.stdv_3d, g.xcov_3d, g.nobs_3d, ntresh)
     if rc:
         raise ValueError("Norm: could not handle more then 2 residuals")
+
+
+def norm_3ch(g: Grids, nlevs, nrmlz=True, ntresh=0):
+    """GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341), in place: g.stdv_* receive the variances, g.xcov_* the 3CH estimates."""
+    rc = lib().orc_norm_3ch(g.im, g.jm, g.km, nlevs, g.nr, int(bool(nrmlz)),
+                            g.l2d, g.bias_2d, g.rtms_2d, g.stdv_2d, g.xcov_2d, g.nobs_2d,
+                            g.l3d, g.bias_3d, g.rtms_3d, g.stdv_3d, g.xcov_3d, g.nobs_3d, ntresh)
+    if rc:
+        raise ValueError("GrITAS_3CH_Norm_ could not handle more then 2 residuals")
 
 
 def minmax(g: Grids, nlevs, lat, lon, lev, kx, kt, del_, kxkt_table, p1, p2, ob_flag):

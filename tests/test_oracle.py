@@ -170,3 +170,50 @@ def test_residual_options_c_equals_numpy(iopt):
         assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
     with pytest.raises(ValueError):
         oracle.select_del_all(26, omf, oma, obs, xvec, xm)
+
+
+def test_norm_3ch_known_answers():
+    """GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341) on hand-computed boxes: variances (no square root), the 3CH
+    estimates with the different slot order of the 2-D and the 3-D block, missing values taking part in the
+    whole-array expressions, the n = 1 asymmetry, untouched levels above nlevs, and the early return for nlevs < 2."""
+    im, jm, km, nlevs = 2, 1, 3, 2
+    g = oracle.Grids(im, jm, km, 1, 1, 3)
+    # series with exactly representable statistics: x = {1, 3}, y = {2, 6}, z = {0, 4}
+    xs = np.array([[1.0, 3.0], [2.0, 6.0], [0.0, 4.0]])
+    for arrs in ((g.nobs_2d, g.bias_2d, g.rtms_2d, (0, 0, 0)), (g.nobs_3d, g.bias_3d, g.rtms_3d, (0, 0, 0, 0))):
+        nobs, bias, rtms, ix = arrs
+        nobs[ix] = 2.0
+        for ir in range(3):
+            bias[ix + (ir,)] = xs[ir].sum()
+            rtms[ix + (ir,)] = (xs[ir] ** 2).sum()
+    # second box: a single observation (2-D: missing variance, 3-D: tmp = |x^2 - x^2| = 0)
+    for nobs, bias, rtms, ix in ((g.nobs_2d, g.bias_2d, g.rtms_2d, (1, 0, 0)), (g.nobs_3d, g.bias_3d, g.rtms_3d, (1, 0, 0, 0))):
+        nobs[ix] = 1.0
+        for ir in range(3):
+            bias[ix + (ir,)] = 2.0 + ir
+            rtms[ix + (ir,)] = (2.0 + ir) ** 2
+    g.bias_3d[0, 0, 2, 0, :] = 7.0          # level 3 > nlevs: never touched
+    oracle.norm_3ch(g, nlevs, True, 0)
+    v = np.array([2.0, 8.0, 8.0])           # sample variances n/(n-1) * (mean(x^2) - mean(x)^2)
+    assert np.array_equal(g.bias_2d[0, 0, 0], [2.0, 4.0, 2.0]) and np.array_equal(g.bias_3d[0, 0, 0, 0], [2.0, 4.0, 2.0])
+    assert np.allclose(g.rtms_2d[0, 0, 0], np.sqrt([5.0, 20.0, 8.0]), rtol=0, atol=0)
+    assert np.array_equal(g.stdv_2d[0, 0, 0], v) and np.array_equal(g.stdv_3d[0, 0, 0, 0], v)
+    e1, ea, eb = 0.5 * (v[0] + v[1] - v[2]), 0.5 * (v[1] + v[2] - v[0]), 0.5 * (v[2] + v[0] - v[1])
+    assert np.array_equal(g.xcov_2d[0, 0, 0], [e1, ea, eb])            # :1287-1289
+    assert np.array_equal(g.xcov_3d[0, 0, 0, 0], [e1, eb, ea])         # :1337-1339: slots 2 and 3 swapped
+    # n = 1
+    assert np.all(g.stdv_2d[1, 0, 0] == oracle.AMISS) and np.all(g.xcov_2d[1, 0, 0] == 0.5 * oracle.AMISS)
+    assert np.all(g.stdv_3d[1, 0, 0, 0] == 0.0) and np.all(g.xcov_3d[1, 0, 0, 0] == 0.0)
+    # empty box of level 2: everything missing, 3CH of three missing values
+    assert np.all(g.bias_3d[0, 0, 1, 0] == oracle.AMISS) and np.all(g.xcov_3d[0, 0, 1, 0] == 0.5 * oracle.AMISS)
+    # level 3 (> nlevs): untouched sums, variances stay 0, 3CH of zeros
+    assert np.all(g.bias_3d[0, 0, 2, 0] == 7.0) and np.all(g.stdv_3d[:, :, 2] == 0.0) and np.all(g.xcov_3d[:, :, 2] == 0.0)
+    # nlevs < 2: the 3-D block is never reached (:1292)
+    h = oracle.Grids(im, jm, km, 1, 1, 3)
+    h.nobs_3d[0, 0, 0, 0] = 2.0
+    h.bias_3d[0, 0, 0, 0, :] = 4.0
+    oracle.norm_3ch(h, 1, True, 0)
+    assert np.all(h.bias_3d[0, 0, 0, 0] == 4.0) and np.all(h.xcov_3d == 0.0) and np.all(h.stdv_3d == 0.0)
+    # nr != 3 is rejected
+    with pytest.raises(ValueError):
+        oracle.norm_3ch(oracle.Grids(im, jm, km, 1, 1, 2), nlevs, True, 0)
