@@ -587,6 +587,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   g.p1_top = p1[0];
   g.rdlon = 1.0 / g.dlon;
   g.rdlat = 1.0 / g.dlat;
+  g.rim = 1.0 / (double)im;
+  g.rjm = 1.0 / (double)jm;
   // Level LUT for the branch-free lookup: cells of 2^-m octave on the high word of lev, chosen so that
   // no cell holds more than LUT_STEPS interfaces (kernels.cuh find_level).
   std::vector<unsigned short> lut;

@@ -40,6 +40,7 @@ struct GridDesc {
   int p2_in_smem;
   double dlon, dlat, p1_top;
   double rdlon, rdlat;   // 1/dlon, 1/dlat: fast path of the box index (exactness guarded, see grid_index)
+  double rim, rjm;       // 1/im, 1/jm: column -> (i, j, l) in the tile kernel without integer divisions
   // level LUT (branch-free level lookup): cell = (high word of lev >> lut_shift) - lut_cell0 over
   // [0, lut_ncell); lut[cell] = number of interfaces at or above the cell's upper edge; at most
   // LUT_STEPS interfaces fall inside any cell.  lut_ncell == 0: binary search instead.
@@ -1161,17 +1162,18 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       // ---- rank of every entry within its box ----
       unsigned pk[EPT];
       double d[EPT][NR];
+      const unsigned live_u = min((unsigned)EPT, (n - c0 + NTH - 1u) / NTH);   // uniform: rows of the chunk that hold entries
 #pragma unroll
       for (int u = 0; u < EPT; ++u) {
         const unsigned e = c0 + (unsigned)u * NTH + tid;
         pk[u] = KEY_NONE;
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
-        if (e < n) pk[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, e), d[u]) & (T - 1u);
+        if ((unsigned)u < live_u && e < n) pk[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, e), d[u]) & (T - 1u);
       }
 #pragma unroll
       for (int u = 0; u < EPT; ++u)
-        if (pk[u] != KEY_NONE) pk[u] |= atomicAdd(s_cnt + pk[u], 1u) << 16;
+        if ((unsigned)u < live_u && pk[u] != KEY_NONE) pk[u] |= atomicAdd(s_cnt + pk[u], 1u) << 16;
       __syncthreads();
       // ---- exclusive scan of the counts (in place); s_cnt[T] = entries of the chunk ----
       {
@@ -1214,7 +1216,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       // ---- residuals to start(box) + rank ----
 #pragma unroll
       for (int u = 0; u < EPT; ++u) {
-        if (pk[u] == KEY_NONE) continue;
+        if ((unsigned)u >= live_u || pk[u] == KEY_NONE) continue;
         const unsigned pos = s_cnt[pk[u] & 0xFFFFu] + (pk[u] >> 16);
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + pos] = d[u][ir];
@@ -1345,14 +1347,31 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       const size_t c0 = first / km, c1 = (end3 - 1) / km;
       const unsigned ncol = (unsigned)(c1 - c0 + 1);
       const unsigned head = (unsigned)(first - c0 * km), span = (unsigned)(end3 - first);
-      for (unsigned q = tid; q < ncol * km; q += NTH) {
-        const unsigned k = q / ncol, ci = q - k * ncol;
+      // The span is enumerated without holes, so that a full tile is exactly T / NTH rounds: first the interior columns
+      // level by level (consecutive threads -> consecutive longitudes), then the valid levels of the partial first
+      // and last column.  Divisions by the column count, im and jm are multiplications: floor((x + 0.5) / d) =
+      // trunc((x + 0.5) * (1/d)) as long as the rounding error stays below 0.5/d -- q < 2^16 in fp32, col < 2^32 in
+      // fp64 (error < 2e-6 for any im)
+      const unsigned nin = ncol > 2u ? ncol - 2u : 0u;                         // interior columns
+      const unsigned nA = nin * km, nB = (ncol == 1u) ? span : km - head;     // interior cells, cells of the first column
+      const float rnin = 1.0f / (float)max(nin, 1u);
+      for (unsigned q = tid; q < span; q += NTH) {
+        unsigned k, ci;
+        if (q < nA) {
+          k = (unsigned)(((float)q + 0.5f) * rnin);
+          ci = 1u + (q - k * nin);
+        } else if (q < nA + nB) {
+          k = head + (q - nA);
+          ci = 0u;
+        } else {
+          k = q - nA - nB;
+          ci = ncol - 1u;
+        }
         const unsigned rel = ci * km + k;
-        if (rel < head || rel - head >= span) continue;
         const unsigned col = (unsigned)c0 + ci;               // < nbox3 / km: 32 bits
-        const unsigned i = col % (unsigned)g.im, jl = col / (unsigned)g.im;
-        const size_t j = jl % (unsigned)g.jm, l = jl / (unsigned)g.jm;
-        const size_t o = (size_t)i + (size_t)g.im * (j + (size_t)g.jm * ((size_t)k + (size_t)km * l));
+        const unsigned jl = (unsigned)(((double)col + 0.5) * g.rim), i = col - jl * (unsigned)g.im;
+        const unsigned l = (unsigned)(((double)jl + 0.5) * g.rjm), j = jl - l * (unsigned)g.jm;
+        const size_t o = (size_t)i + (size_t)g.im * ((size_t)j + (size_t)g.jm * ((size_t)k + (size_t)km * (size_t)l));
         box(rel - head, true, (int)k >= g.nlevs, raw3, o3, o, plane3);   // levels nlevs..km-1: never touched, zeros
       }
     }

@@ -675,3 +675,38 @@ def test_3ch_norm_matches_the_oracle(mode, nrmlz, ntresh, km_extra):
                 big = np.abs(b) > 1e14                      # AMISS and the 3CH combinations of AMISS
                 assert np.array_equal(a[big], b[big]), f"{nm}_{tag} missing pattern"
                 assert np.allclose(a[~big], b[~big], rtol=1e-6, atol=1e-9, equal_nan=True), f"{nm}_{tag}"
+
+
+@pytest.mark.parametrize("mode", H.MODES)
+def test_per_time_mode_reset_accum_norm_each_synoptic_time(mode):
+    """grisas.f:279-689: the grids are zeroed, accumulated and normalised (with ntresh) for every synoptic time
+    separately; only the means, the std-dev slot and the counts are written (grisas.f:663-675), so the other output
+    arrays are not requested.  One handle serves all times (gritas_b200_reset)."""
+    cfg, files = small("cfg1", 0.05, 3)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    for c in files:
+        ref, _ = H.oracle_run(cfg, [c], 1, ntresh=2)
+        if G.handle is not None:
+            G.reset()                                          # grisas.f:285-296
+        G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 1), len(c["lat"]), 1, table, p1, p2,
+                       None, l2d, l3d=l3d)
+        out = G.alloc_grids()
+        G.GrITAS_Norm(1, True, l2d, out["bias_2d"] if l2d else None, None, out["stdv_2d"] if l2d else None, None,
+                      out["nobs_2d"] if l2d else None, l3d, out["bias_3d"], None, out["stdv_3d"], None, out["nobs_3d"], ntresh=2)
+        single = ref.nobs_3d == 1.0                            # ntresh > 1, n = 1: stale temporaries in the reference
+        for tag, on in (("2d", l2d), ("3d", l3d)):
+            if not on:
+                continue
+            assert np.array_equal(out["nobs_" + tag], getattr(ref, "nobs_" + tag))
+            for nm in ("bias", "stdv"):
+                a, b = out[f"{nm}_{tag}"], getattr(ref, f"{nm}_{tag}")
+                if tag == "3d" and nm == "stdv":
+                    a, b = a[~single], b[~single]
+                assert np.array_equal(a == oracle.AMISS, b == oracle.AMISS)
+                if H.is_det(mode):
+                    assert np.array_equal(a, b)
+                else:
+                    assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
+            assert not out[f"rtms_{tag}"].any() and not out[f"xcov_{tag}"].any()      # not requested, not written
+    G.close()
