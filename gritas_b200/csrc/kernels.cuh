@@ -894,6 +894,14 @@ struct OutPlanes {
 // vanishing intermediate results fall back to the IEEE division.  Bit-identical to __ddiv_rn.
 __device__ __noinline__ double div_ieee(double x, double d) { return __ddiv_rn(x, d); }   // rare: one copy, never speculated
 
+// Square root for the statistics.  The library routine sends zero (and the other special operands) down an
+// out-of-line slow path; zeros are everywhere here (empty boxes, boxes with one observation), so every warp would pay
+// for it.  sqrt(+0) = +0 is answered directly, everything else is the correctly rounded library result.
+__device__ __forceinline__ double sqrt_stat(double x) {
+  const double s = __dsqrt_rn(x == 0.0 ? 1.0 : x);
+  return x == 0.0 ? x : s;
+}
+
 __device__ __forceinline__ double div_shared(double x, double d, double r) {
   const double q = __dmul_rn(x, r);
   const double rem = __fma_rn(-q, d, x);
@@ -932,7 +940,7 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
       if (some) {
         bias[ir] = div_ieee(rec[1 + 2 * ir], dm);
         const double t = div_ieee(rec[2 + 2 * ir], dm);
-        rtms[ir] = __dsqrt_rn(t);
+        rtms[ir] = sqrt_stat(t);
         tmp = fabs(__dsub_rn(t, __dmul_rn(bias[ir], bias[ir])));
       } else {
         bias[ir] = AMISS;
@@ -965,7 +973,8 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
   // m >= 1 whenever `some` holds with nrmlz; m = 1, m-1 = 0 under -nonorm: the reciprocal path needs a finite,
   // non-zero divisor, anything else takes the plain division (inf / NaN results exactly as the reference)
   const bool fast_m = some && dm >= 1.0, fast_m1 = many && dm1 >= 1.0;
-  const double rm = fast_m ? __drcp_rn(dm) : 0.0, rm1 = fast_m1 ? __drcp_rn(dm1) : 0.0;
+  // (the reciprocals are evaluated for every lane: keep zero divisors away from the library's slow path)
+  const double rm = __drcp_rn(fast_m ? dm : 1.0), rm1 = __drcp_rn(fast_m1 ? dm1 : 1.0);
   auto div_m = [&](double x) { return fast_m ? div_shared(x, dm, rm) : div_ieee(x, dm); };
   auto div_m1 = [&](double x) { return fast_m1 ? div_shared(x, dm1, rm1) : div_ieee(x, dm1); };
   double tmp[NR], xtmp = 0.0;
@@ -974,7 +983,7 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
     for (int ir = 0; ir < NR; ++ir) {
       bias[ir] = div_m(rec[1 + 2 * ir]);
       const double t = div_m(rec[2 + 2 * ir]);
-      rtms[ir] = __dsqrt_rn(t);
+      rtms[ir] = sqrt_stat(t);
       tmp[ir] = fabs(__dsub_rn(t, __dmul_rn(bias[ir], bias[ir])));
     }
     xtmp = div_m(xraw);
@@ -991,7 +1000,7 @@ __device__ __forceinline__ void finalize_box(const double *__restrict__ rec, boo
 #pragma unroll
   for (int ir = 0; ir < NR; ++ir) {
     const double arg = many ? div_m1(__dmul_rn(dm, tmp[ir])) : tmp[ir];
-    const double sq = __dsqrt_rn(arg);
+    const double sq = sqrt_stat(arg);
     stdv[ir] = (many || one) ? sq : AMISS;
   }
   xcov[nx - 1] = many ? div_m1(__dmul_rn(dm, xtmp)) : (one ? xtmp : AMISS);
