@@ -31,7 +31,7 @@
       implicit none
       private
 
-      public :: B200_Accum_, B200_Norm_, B200_3CH_Norm_, B200_GetRaw, B200_Reset, B200_Clean
+      public :: B200_Accum_, B200_Norm_, B200_3CH_Norm_, B200_GetRaw, B200_Reset, B200_Clean, B200_PreSort
       public :: B200_MinMax_, B200_SetMask
       public :: B200_SetMode
 
@@ -85,6 +85,16 @@
             integer(c_int), value             :: nrmlz, ntresh
             real(c_double), intent(inout)     :: bias_2d(*), rtms_2d(*), var_2d(*), xcov_2d(*), nobs_2d(*)
             real(c_double), intent(inout)     :: bias_3d(*), rtms_3d(*), var_3d(*), xcov_3d(*), nobs_3d(*)
+         end function
+         integer(c_int) function gritas_b200_presort ( h, nobs, qcexcl, lat, lon, lev, time,    &
+                                  kt, ks, kx, index_base, is )                                  &
+                                  bind(C, name='gritas_b200_presort')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            integer(c_int), value             :: nobs, index_base
+            integer(c_int), intent(in)        :: qcexcl(*), time(*), kt(*), ks(*), kx(*)
+            real(c_double), intent(in)        :: lat(*), lon(*), lev(*)
+            integer(c_int), intent(out)       :: is(*)
          end function
          integer(c_int) function gritas_b200_get_raw ( h, bias_2d, rtms_2d, xcov_2d, nobs_2d,   &
                                   bias_3d, rtms_3d, xcov_3d, nobs_3d )                          &
@@ -186,6 +196,20 @@
                               bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d )
       if ( rc /= 0 ) call gritas_perror ('Norm: B200 finalize failed')
       end subroutine B200_Norm_
+
+!     Replaces IndexSet + the eight IndexSort calls of gritas.f:500-508:
+!         call B200_PreSort ( nobs, is, ods%data%qcexcl, ods%data%lat, ods%data%lon, ods%data%lev,
+!                             ods%data%time, ods%data%kt, ods%data%ks, ods%data%kx )
+!     `is` comes back 1-based, ready for the gathers of gritas.f:510-523.  Works before the first B200_Accum_.
+      subroutine B200_PreSort ( nobs, is, qcexcl, lat, lon, lev, time, kt, ks, kx )
+      integer, intent(in)  :: nobs
+      integer, intent(out) :: is(nobs)
+      integer, intent(in)  :: qcexcl(nobs), time(nobs), kt(nobs), ks(nobs), kx(nobs)
+      real,    intent(in)  :: lat(nobs), lon(nobs), lev(nobs)
+      integer(c_int) :: rc
+      rc = gritas_b200_presort ( handle, nobs, qcexcl, lat, lon, lev, time, kt, ks, kx, 1, is )
+      if ( rc /= 0 ) call gritas_perror ('PreSort: B200 sort failed')
+      end subroutine B200_PreSort
 
 !     Same argument list as GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1181; gritas.f:813-818, -tch).
       subroutine B200_3CH_Norm_ ( nr, nrmlz,                                                    &

@@ -38,7 +38,7 @@ IOPT_OMF_OMA = 101
 # every symbol include/gritas_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "gritas_b200_create", "gritas_b200_destroy", "gritas_b200_pint", "gritas_b200_kxkt", "gritas_b200_accum",
-    "gritas_b200_accum_ods", "gritas_b200_accum_odsx", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_3ch", "gritas_b200_norm_device",
+    "gritas_b200_accum_ods", "gritas_b200_accum_odsx", "gritas_b200_flush", "gritas_b200_barrier", "gritas_b200_sync", "gritas_b200_reset", "gritas_b200_norm", "gritas_b200_norm_3ch", "gritas_b200_presort", "gritas_b200_norm_device",
     "gritas_b200_get_raw", "gritas_b200_get_minmax", "gritas_b200_set_mask", "gritas_b200_add_raw", "gritas_b200_nccl_unique_id", "gritas_b200_comm_init",
     "gritas_b200_allreduce", "gritas_b200_norm_reduce", "gritas_b200_norm_reduce_device", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
     "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_tiled", "gritas_b200_fused_norm", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
@@ -85,6 +85,7 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_barrier.argtypes = [_P]
     L.gritas_b200_norm.argtypes = [_P, _I, _I] + [_P] * 10
     L.gritas_b200_norm_3ch.argtypes = [_P, _I, _I] + [_P] * 10
+    L.gritas_b200_presort.argtypes = [_P, _I] + [_P] * 8 + [_I, _P]
     L.gritas_b200_norm_device.argtypes = [_P, _I, _I] + [C.POINTER(_P)] * 10
     L.gritas_b200_get_raw.argtypes = [_P] + [_P] * 8
     L.gritas_b200_add_raw.argtypes = [_P] + [_P] * 8

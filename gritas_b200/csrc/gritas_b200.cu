@@ -125,6 +125,9 @@ struct gritas_b200_ctx {
   static constexpr int NCHUNK = 8;
   cudaStream_t comm_stream = nullptr, fin_stream = nullptr;
   cudaEvent_t ev_acc[NCHUNK] = {}, ev_red[NCHUNK] = {}, ev_fin = nullptr;
+  // pre-sort scratch (gritas_b200_presort)
+  void *ps_cols = nullptr, *ps_key[2] = {}, *ps_idx[2] = {};
+  size_t ps_cols_cap = 0, ps_key_cap[2] = {}, ps_idx_cap[2] = {};
   // finalize scratch (reference-layout planes on the device)
   double *out = nullptr;
   size_t out_cap = 0;
@@ -737,6 +740,8 @@ void gritas_b200_destroy(gritas_b200_handle h) {
   if (h->ev_fin) cudaEventDestroy(h->ev_fin);
   for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists})
     if (p) cudaFree(p);
+  for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1]})
+    if (p) cudaFree(p);
   if (h->d_lut) cudaFree(h->d_lut);
   if (h->d_mask) cudaFree(h->d_mask);
   for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
@@ -1281,6 +1286,99 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->compute));
   return mark_main(h);
+}
+
+// ---- pre-sort (gritas.f:499-508) ------------------------------------------------------------------
+// IndexSet followed by eight stable ascending IndexSorts -- qcexcl, lat, lon, lev, time, kt, ks, kx, in this order, so
+// that the final order is (kx, ks, kt, time, lev, lon, lat, qcexcl, original position).  The reference spends seconds
+// per synoptic time here (index merge sorts on the host); on the device it is eight LSD radix-sort passes over
+// (order-preserving key, index) pairs.  `is` receives the permutation (index_base 0 or 1: Fortran's `is` is 1-based);
+// the column gathers of gritas.f:510-523 stay with the caller.  Columns and `is` may live on the host or the device.
+// The result is the unique stable order, hence identical to the host sort for any input without NaNs (the merge
+// compares with `<`: -0.0 and +0.0 are equal there and here; the place of NaNs is unspecified in both).
+int gritas_b200_presort(gritas_b200_handle h, int nobs, const int32_t *qcexcl, const double *lat, const double *lon,
+                        const double *lev, const int32_t *time, const int32_t *kt, const int32_t *ks, const int32_t *kx,
+                        int index_base, int32_t *is) {
+  // gritas.f sorts while reading a file, before the first GrITAS_Accum has created the handle: a NULL handle uses a
+  // process-wide scratch context (a stream and buffers on the current device)
+  static gritas_b200_handle scratch = nullptr;
+  if (!h) {
+    if (!scratch) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess) return GRITAS_B200_ERR_CUDA;
+      scratch = new gritas_b200_ctx();
+      scratch->device = dev;
+      if (cudaStreamCreateWithFlags(&scratch->compute, cudaStreamNonBlocking) != cudaSuccess) {
+        delete scratch;
+        scratch = nullptr;
+        return GRITAS_B200_ERR_CUDA;
+      }
+    }
+    h = scratch;
+  }
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (nobs < 0 || !is || !qcexcl || !lat || !lon || !lev || !time || !kt || !ks || !kx || (index_base != 0 && index_base != 1))
+    return fail(h, GRITAS_B200_ERR_ARG, "presort: bad arguments");
+  if (nobs == 0) return 0;
+  const size_t n = (size_t)nobs;
+  cudaStream_t sm = h->compute;
+  // staging of host columns: 3 fp64 + 5 int32 columns
+  const void *src[8] = {qcexcl, lat, lon, lev, time, kt, ks, kx};
+  const size_t esz[8] = {4, 8, 8, 8, 4, 4, 4, 4};
+  size_t need = 0;
+  for (int c = 0; c < 8; ++c)
+    if (mem_kind(src[c]) != 2) need += (esz[c] * n + 15) & ~(size_t)15;
+  if (need && (rc = grow_dev(h, &h->ps_cols, &h->ps_cols_cap, need))) return rc;
+  const void *dev[8];
+  size_t off = 0;
+  for (int c = 0; c < 8; ++c) {
+    if (mem_kind(src[c]) == 2) { dev[c] = src[c]; continue; }
+    void *d = (char *)h->ps_cols + off;
+    CU(cudaMemcpyAsync(d, src[c], esz[c] * n, cudaMemcpyHostToDevice, sm));
+    h->h2d += esz[c] * n;
+    dev[c] = d;
+    off += (esz[c] * n + 15) & ~(size_t)15;
+  }
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = grow_dev(h, &h->ps_key[b], &h->ps_key_cap[b], 8 * n))) return rc;
+    if ((rc = grow_dev(h, &h->ps_idx[b], &h->ps_idx_cap[b], 4 * n))) return rc;
+  }
+  size_t t32 = 0, t64 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t32, (unsigned *)nullptr, (unsigned *)nullptr, (int *)nullptr, (int *)nullptr, nobs, 0, 32, sm);
+  cub::DeviceRadixSort::SortPairs(nullptr, t64, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int *)nullptr,
+                                  (int *)nullptr, nobs, 0, 64, sm);
+  if ((rc = grow_dev(h, &h->cub_tmp, &h->cub_cap, std::max(t32, t64)))) return rc;
+  const int nblk = grid_for(n, 256, 8);
+  int cur = 0;
+  k_iota<<<nblk, 256, 0, sm>>>((int *)h->ps_idx[0], nobs);
+  for (int p = 0; p < 8; ++p) {
+    int *idx = (int *)h->ps_idx[cur], *idx2 = (int *)h->ps_idx[cur ^ 1];
+    size_t tmp = h->cub_cap;
+    if (esz[p] == 4) {
+      k_sortkey_i32<<<nblk, 256, 0, sm>>>((const int *)dev[p], idx, (unsigned *)h->ps_key[0], nobs);
+      CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, (unsigned *)h->ps_key[0], (unsigned *)h->ps_key[1], idx, idx2, nobs, 0, 32, sm));
+    } else {
+      k_sortkey_f64<<<nblk, 256, 0, sm>>>((const double *)dev[p], idx, (unsigned long long *)h->ps_key[0], nobs);
+      CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, (unsigned long long *)h->ps_key[0], (unsigned long long *)h->ps_key[1], idx,
+                                         idx2, nobs, 0, 64, sm));
+    }
+    cur ^= 1;
+    h->launches += 1 + (esz[p] == 4 ? 9 : 17);   // key kernel + radix passes (approx.)
+  }
+  int *fin = (int *)h->ps_idx[cur];
+  if (mem_kind(is) == 2) {
+    k_add_base<<<nblk, 256, 0, sm>>>(fin, is, index_base, nobs);
+  } else {
+    int *out = (int *)h->ps_idx[cur ^ 1];
+    k_add_base<<<nblk, 256, 0, sm>>>(fin, out, index_base, nobs);
+    CU(cudaMemcpyAsync(is, out, 4 * n, cudaMemcpyDeviceToHost, sm));
+    h->d2h += 4 * n;
+  }
+  h->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(sm));
+  return 0;
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------------------

@@ -1390,6 +1390,32 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pre-sort (gritas.f:499-508): IndexSet + eight successive stable ascending index sorts.  One LSD pass = gather the
+// pass's column through the current index into an order-preserving unsigned key, then a stable radix sort of
+// (key, index) pairs.
+__global__ void __launch_bounds__(256)
+k_iota(int *__restrict__ idx, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) idx[i] = i;
+}
+__global__ void __launch_bounds__(256)
+k_sortkey_i32(const int *__restrict__ col, const int *__restrict__ idx, unsigned *__restrict__ key, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    key[i] = (unsigned)col[idx[i]] ^ 0x80000000u;                       // signed order -> unsigned order
+}
+__global__ void __launch_bounds__(256)
+k_sortkey_f64(const double *__restrict__ col, const int *__restrict__ idx, unsigned long long *__restrict__ key, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // -0.0 and +0.0 compare equal in the reference's merge (strict <): canonicalise before taking the bit pattern
+    const double x = __dadd_rn(col[idx[i]], 0.0);
+    key[i] = (unsigned long long)f64_order_key(x) ^ 0x8000000000000000ull;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_add_base(const int *__restrict__ idx, int *__restrict__ out, int base, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = idx[i] + base;
+}
+
 // Reset when nothing was flushed into the records since the last reset (everything parked in the tile lists or
 // consumed by K2f): only tiles that took a direct accumulate (bin / list overflow, sg.dirty) hold anything.
 __global__ void __launch_bounds__(256)

@@ -220,6 +220,20 @@ class Grids:
                                           p(bias_3d), p(rtms_3d), p(stdv_3d), p(xcov_3d), p(nobs_3d))
         self._check(rc)
 
+    # ---- pre-sort (gritas.f:499-508) --------------------------------------------------------
+    def presort(self, qcexcl, lat, lon, lev, time, kt, ks, kx, index_base=0, out=None):
+        """IndexSet + the eight stable IndexSorts of gritas.f:499-508 on the device; returns the permutation `is`
+        (int32, 0- or 1-based).  Works before the first GrITAS_Accum (no handle yet)."""
+        n = int(lat.shape[0])
+        if out is None:
+            out = np.zeros(n, np.int32)
+        p = cabi.ptr
+        rc = cabi.load().gritas_b200_presort(self._h, n, p(qcexcl), p(lat), p(lon), p(lev), p(time), p(kt), p(ks), p(kx),
+                                             int(index_base), p(out))
+        if rc:
+            raise RuntimeError(f"gritas_b200_presort rc={rc}")
+        return out
+
     # ---- GrITAS_3CH_Norm_ (m_gritas_grids.f:1178-1341; gritas.f:813-818, -tch) -------------
     def GrITAS_3CH_Norm(self, nr, nrmlz, l2d, bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d,
                         l3d, bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d, ntresh=None):

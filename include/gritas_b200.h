@@ -206,6 +206,18 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
                         const double *nobs_2d, const double *bias_3d, const double *rtms_3d, const double *xcov_3d,
                         const double *nobs_3d);
 
+/*
+ * Replaces the eight IndexSort calls of gritas.f:499-508 (GMAO_mpeu m_MergeSorts, the reference's largest host cost
+ * per synoptic time): IndexSet + stable ascending sorts by qcexcl, lat, lon, lev, time, kt, ks, kx in this order, i.e.
+ * the final order (kx, ks, kt, time, lev, lon, lat, qcexcl, original position).  `is` (nobs int32, host or device)
+ * receives the permutation, 0- or 1-based (index_base; Fortran's `is` is 1-based); the column gathers of
+ * gritas.f:510-523 stay with the caller.  The stable order is unique: the result is identical to the host sort for
+ * NaN-free keys.  Needs a handle only for its device scratch and stream.
+ */
+int gritas_b200_presort(gritas_b200_handle h, int nobs, const int32_t *qcexcl, const double *lat, const double *lon,
+                        const double *lev, const int32_t *time, const int32_t *kt, const int32_t *ks, const int32_t *kx,
+                        int index_base, int32_t *is);
+
 /* Multi-GPU (one process per GPU): partial count / sum / sum-of-squares grids are summed over
  * all ranks with one NCCL all-reduce before _norm.  The reference is single-process; this is new. */
 int gritas_b200_nccl_unique_id(void *id128);  /* rank 0 fills 128 bytes; broadcast them */

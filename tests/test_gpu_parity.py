@@ -710,3 +710,38 @@ def test_per_time_mode_reset_accum_norm_each_synoptic_time(mode):
                     assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
             assert not out[f"rtms_{tag}"].any() and not out[f"xcov_{tag}"].any()      # not requested, not written
     G.close()
+
+
+@pytest.mark.parametrize("name,device_inputs", [("cfg1", False), ("cfg5", False), ("cfg3_amsua", True)])
+def test_presort_is_the_reference_permutation(name, device_inputs):
+    """gritas_b200_presort = IndexSet + the eight stable IndexSorts of gritas.f:499-508: the permutation must equal the
+    oracle's merge-sort restatement index for index (integer-exact), with duplicates (clustered sites: identical lat /
+    lon), signed zeros and negative keys in the columns, before any handle exists and through an existing handle."""
+    cfg = synth.get_config(name, 0.05 if name != "cfg3_amsua" else 0.004)
+    c = dict(synth.make_file(cfg, 3))
+    n = len(c["lat"])
+    lat, lon = c["lat"].copy(), c["lon"].copy()
+    lat[::17] = 0.0
+    lat[5::34] = -0.0                                   # equal to +0.0 in the reference's `<` merge
+    lon[::13] = -lon[::13]
+    time = c["time"].copy()
+    time[::7] = -time[::7]                              # negative int keys
+    cols = dict(qcexcl=c["qcexcl"], lat=lat, lon=lon, lev=c["lev"], time=time, kt=c["kt"], ks=c["ks"], kx=c["kx"])
+    ref = oracle.presort(**cols)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs)        # no handle yet: the library's scratch context
+    args = cols
+    keep = None
+    if device_inputs:
+        import torch
+        keep = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in cols.items()}
+        args = keep
+    got0 = G.presort(**args)
+    assert np.array_equal(got0, ref)
+    got1 = G.presort(**args, index_base=1)              # Fortran's `is`
+    assert np.array_equal(got1, ref + 1)
+    # sorted columns are in (kx, ks, kt, time, lev, lon, lat, qcexcl) order
+    k = np.stack([cols[nm][got0] for nm in ("kx", "ks", "kt", "time", "lev", "lon", "lat", "qcexcl")], axis=1).astype(np.float64)
+    d = np.diff(k, axis=0)
+    first = np.argmax(d != 0, axis=1)
+    assert np.all((d[np.arange(n - 1), first] > 0) | ~(d != 0).any(axis=1))
+    G.close()
