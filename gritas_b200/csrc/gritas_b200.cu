@@ -109,7 +109,7 @@ struct gritas_b200_ctx {
   size_t stage_slots = 0;      // ntiles * cap
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
   size_t tf_smem = 0;            // shared memory of the tile kernel (K2f / K2t)
-  int tf_ctas = 148;
+  int tf_ctas = 148, tf_per_sm = 1;
   bool fused_norm = true;        // Norm consumes the tile lists itself (K2f) instead of flush (K2t) + K3
   // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
   // the GPU; consecutive calls run on different streams (own level-1 scratch, own level-miss record) and
@@ -122,7 +122,7 @@ struct gritas_b200_ctx {
   cudaEvent_t main_ev = nullptr;  // last accumulator-wide operation queued on `compute`
   // reduce + finalize pipeline (multi-GPU): chunk c is tile-accumulated on `compute`, reduced to the root on
   // `comm_stream`, finalized on `fin_stream` while later chunks are still being accumulated / reduced
-  static constexpr int NCHUNK = 8;
+  static constexpr int NCHUNK = 16;   // capacity; the pipeline uses GRITAS_B200_PIPE_CHUNKS of them (default 8)
   cudaStream_t comm_stream = nullptr, fin_stream = nullptr;
   cudaEvent_t ev_acc[NCHUNK] = {}, ev_red[NCHUNK] = {}, ev_fin = nullptr;
   // pre-sort scratch (gritas_b200_presort)
@@ -335,19 +335,21 @@ void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDes
 
 // K2t over tiles [t0, t1): the lists are added to the records and emptied.
 template <int NR>
-void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1) {
+void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sms) {
   if (t1 <= t0) return;
   const OutPlanes none = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-  const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
+  // the grid is persistent (every CTA resident): when a collective runs next to it, leave SMs for its channels
+  const int avail = std::max(h->tf_per_sm, h->tf_ctas - free_sms * h->tf_per_sm);
+  const int ctas = (int)std::min((unsigned)avail, t1 - t0);
   k_tile_final<NR, true><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0, 0, 0,
                                                                                    h->acc_fresh ? 1 : 0, t0, t1);
 }
 
-void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1) {
+void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sms = 0) {
   switch (h->g.nr) {
-    case 1: launch_tiles<1>(h, t0, t1); break;
-    case 2: launch_tiles<2>(h, t0, t1); break;
-    default: launch_tiles<3>(h, t0, t1); break;
+    case 1: launch_tiles<1>(h, t0, t1, free_sms); break;
+    case 2: launch_tiles<2>(h, t0, t1, free_sms); break;
+    default: launch_tiles<3>(h, t0, t1, free_sms); break;
   }
 }
 
@@ -695,7 +697,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         else TF_SETUP(3);
 #undef TF_SETUP
         h->tf_smem = smem;
-        h->tf_ctas = (int)std::min((size_t)nsm * (size_t)std::max(per_sm, 1), ntiles);   // persistent: all CTAs resident
+        h->tf_per_sm = std::max(per_sm, 1);
+        h->tf_ctas = (int)std::min((size_t)nsm * (size_t)h->tf_per_sm, ntiles);   // persistent: all CTAs resident
         // GRITAS_B200_FUSED_NORM=0: Norm flushes the lists into the records (K2t) and finalizes them with K3
         const char *e_f = getenv("GRITAS_B200_FUSED_NORM");
         h->fused_norm = !(e_f && atoi(e_f) == 0);
@@ -1081,7 +1084,8 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
       }
       CU(cudaEventCreateWithFlags(&h->ev_fin, cudaEventDisableTiming));
     }
-    const int NC = gritas_b200_ctx::NCHUNK;
+    static const int NC = getenv("GRITAS_B200_PIPE_CHUNKS") ? std::min((int)gritas_b200_ctx::NCHUNK, std::max(1, atoi(getenv("GRITAS_B200_PIPE_CHUNKS")))) : 8;
+    static const int pipe_free_sms = getenv("GRITAS_B200_PIPE_FREE_SMS") ? std::max(0, atoi(getenv("GRITAS_B200_PIPE_FREE_SMS"))) : 0;
     const bool staged = h->staging && h->staged_upper > 0;
     const size_t T = h->staging ? ((size_t)1 << h->sg.tile_shift) : 1;
     const size_t row_recs = (size_t)g.im * g.km;
@@ -1093,7 +1097,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
       const size_t rec_end = last ? h->nrec : (size_t)r1 * row_recs;   // the last chunk also carries the 2-D boxes
       if (staged) {
         const unsigned t1 = last ? h->sg.ntiles : (unsigned)std::min((size_t)h->sg.ntiles, (rec_end + T - 1) / T);
-        launch_tiles_nr(h, tprev, t1);    // includes a tile straddling into the next chunk: complete before its reduce
+        launch_tiles_nr(h, tprev, t1, pipe_free_sms);   // includes a tile straddling into the next chunk: complete before its reduce
         tprev = t1;
         h->launches++;
       }
