@@ -424,14 +424,14 @@ def run_b200(args):
     grid_bytes = 8 * (1 + 2 * NR) * nbox                     # the sums, once per pass (SURVEY 8d B_grid)
     alg_bytes_per_launch = (nobs_rank * B_OBS + grid_bytes) / nfiles
     staged = L.gritas_b200_tiled(G.handle) == 1
-    # tiled path: the accumulate is only complete after the tile kernel, which at N=1 is fused with the finalize (K2f):
-    # the whole Norm region is charged to the path; direct / deterministic path: the accumulate region is the path
-    path_ms = accum_ms + (flush_ms if staged else 0.0)
+    # the algorithmic bytes hold the grid once (B_grid), so the duration holds the pass over the grid too: at N=1 the
+    # whole Norm region (tiled path: K2f, the tile accumulate fused with the finalize; direct / deterministic path: K3)
+    path_ms = accum_ms + flush_ms
     launch_ms = path_ms / nfiles
     achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
     traffic = None
     try:   # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic_cfg2.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic_cfg2.json")))
         if staged and cfg.name == "cfg2" and nfiles == cfg.nfiles and args.scale == 1.0:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
