@@ -1240,7 +1240,8 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
         double a[NV];
 #pragma unroll
         for (int q = 0; q < NV; ++q) a[q] = 0.0;
-        for (unsigned p = s0; p < e0; ++p) {
+#pragma unroll 1
+        for (unsigned p = s0; p < e0; ++p) {                    // runs are short (~3): no unrolled prologue / main loop / tail
           double x[NR];
 #pragma unroll
           for (int ir = 0; ir < NR; ++ir) x[ir] = s_stage[(size_t)ir * CH + p];
