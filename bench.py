@@ -439,7 +439,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": (("k_list_obs (K1) per file + k_tile_final<finalize> (K2f: tile accumulate fused with finalize) per Norm" if world == 1 else
-                            "k_list_obs (K1) per file + k_tile_final<flush> (K2t) per flush") if staged else
+                            "k_list_obs (K1) per file + k_tile_final<export> (K2x) per Norm") if staged else
                            ("k_accum_fast" if args.mode == "fast" else "k_box_keys + radix sort + k_segment_sum")),
                 "peak_source": peak_src, "avg_launch_ms": launch_ms, "alg_bytes_per_launch": alg_bytes_per_launch,
                 "note": f"one launch = the accumulate work of one file: {B_OBS} B/obs x obs per file + (8*(1+2*nr)*boxes)/files; "
@@ -450,7 +450,7 @@ def run_b200(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
-                       "per_rank": "each rank bins its own month; N=1: Norm = K2f on the parked tile lists; N>1: tile flush + ncclReduce to rank 0 + finalize pipelined in 8 chunks (rank 0 writes the grids, as the reference has one writer)",
+                       "per_rank": "each rank bins its own month; N=1: Norm = K2f on the parked tile lists; N>1: K2x (tile sums as compact planes) + ncclReduce to rank 0 + K3x (finalize) pipelined in 8 chunks (rank 0 writes the grids, as the reference has one writer)",
                        "l2": f"inputs ({nobs_rank * b_obs(NR) / 1e9:.1f} GB/step) exceed the 126 MB L2; no flush needed"},
             "accumulate_ms_per_step": accum_ms, "norm_ms_per_step" if world == 1 else "tile_flush_ms_per_step": flush_ms,
             "host_enqueue_ms_per_step": host_ms, "count_check": check, "accepted_obs_per_rank": expected_rank, "gpu_launches": int(launches_per_step * args.steps),

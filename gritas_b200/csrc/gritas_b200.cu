@@ -111,6 +111,8 @@ struct gritas_b200_ctx {
   size_t tf_smem = 0;            // shared memory of the tile kernel (K2f / K2t)
   int tf_ctas = 148, tf_per_sm = 1;
   bool fused_norm = true;        // Norm consumes the tile lists itself (K2f) instead of flush (K2t) + K3
+  double *red = nullptr;         // multi-rank Norm: compact {n, sums} planes per tile, the operand of ncclReduce
+  size_t red_cap = 0;
   // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
   // the GPU; consecutive calls run on different streams (own level-1 scratch, own level-miss record) and
   // overlap.  Everything that reads or resets the accumulators runs on `compute` after join_workers().
@@ -341,8 +343,8 @@ void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sms) 
   // the grid is persistent (every CTA resident): when a collective runs next to it, leave SMs for its channels
   const int avail = std::max(h->tf_per_sm, h->tf_ctas - free_sms * h->tf_per_sm);
   const int ctas = (int)std::min((unsigned)avail, t1 - t0);
-  k_tile_final<NR, true><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0, 0, 0,
-                                                                                   h->acc_fresh ? 1 : 0, t0, t1);
+  k_tile_final<NR, TILE_FLUSH><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0,
+                                                                                         0, 0, h->acc_fresh ? 1 : 0, t0, t1, nullptr);
 }
 
 void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sms = 0) {
@@ -369,9 +371,28 @@ int flush_stage(gritas_b200_handle h) {
 template <int NR>
 void launch_tile_final(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
                        int raw2, int raw3) {
-  k_tile_final<NR, false><<<h->tf_ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz,
-                                                                                 ntr, raw2, raw3, h->acc_fresh ? 1 : 0, 0u,
-                                                                                 h->sg.ntiles);
+  k_tile_final<NR, TILE_FINALIZE><<<h->tf_ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3,
+                                                                                         nrmlz, ntr, raw2, raw3, h->acc_fresh ? 1 : 0,
+                                                                                         0u, h->sg.ntiles, nullptr);
+}
+
+// Multi-rank Norm on the tiled path: K2x exports the sums of tiles [t0, t1) as compact planes (the reduction operand),
+// K3x finalizes them once they are reduced.
+template <int NR>
+void launch_tile_export(gritas_b200_handle h, cudaStream_t sm, unsigned t0, unsigned t1) {
+  if (t1 <= t0) return;
+  const OutPlanes none = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
+  k_tile_final<NR, TILE_EXPORT><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0, 0, 0,
+                                                                                   h->acc_fresh ? 1 : 0, t0, t1, h->red);
+}
+template <int NR>
+void launch_tile_import(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
+                        int raw2, int raw3, unsigned t0, unsigned t1) {
+  if (t1 <= t0) return;
+  const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
+  k_tile_final<NR, TILE_IMPORT><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, ntr,
+                                                                                   raw2, raw3, 1, t0, t1, h->red);
 }
 
 bool fused_norm_ok(gritas_b200_handle h) {
@@ -689,9 +710,11 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
 #define TF_SETUP(NR_)                                                                                                        \
   do {                                                                                                                        \
-    CUC(cudaFuncSetAttribute(k_tile_final<NR_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    CUC(cudaFuncSetAttribute(k_tile_final<NR_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<NR_, false>, TileFinal<NR_>::THREADS, smem));    \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_FINALIZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_EXPORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_IMPORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<NR_, TILE_FINALIZE>, TileFinal<NR_>::THREADS, smem)); \
   } while (0)
         if (nr == 1) TF_SETUP(1);
         else if (nr == 2) TF_SETUP(2);
@@ -742,7 +765,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (h->ev_red[c]) cudaEventDestroy(h->ev_red[c]);
   }
   if (h->ev_fin) cudaEventDestroy(h->ev_fin);
-  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists})
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red})
     if (p) cudaFree(p);
   for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1]})
     if (p) cudaFree(p);
@@ -1089,6 +1112,49 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     static const int pipe_free_sms = getenv("GRITAS_B200_PIPE_FREE_SMS") ? std::max(0, atoi(getenv("GRITAS_B200_PIPE_FREE_SMS"))) : 0;
     const bool staged = h->staging && h->staged_upper > 0;
     const size_t T = h->staging ? ((size_t)1 << h->sg.tile_shift) : 1;
+    static const bool compact_off = getenv("GRITAS_B200_COMPACT_REDUCE") && atoi(getenv("GRITAS_B200_COMPACT_REDUCE")) == 0;
+    if (staged && h->fused_norm && raw != 2 && !compact_off) {
+      // Tiled path: the month is parked in the tile lists.  Per chunk of tiles: K2x accumulates the lists and exports
+      // {n, sums} as compact planes (48 bytes per box at nr = 2 instead of a 64-byte record; records that already hold
+      // part of a tile are folded in), ncclReduce sums the planes to the root, K3x finalizes them there.  The records and
+      // the lists are not touched: like the one-rank Norm, this does not change the accumulation state.
+      const int nv1 = 1 + (nr == 1 ? 2 : (nr == 2 ? 5 : 6));
+      const size_t per_tile = (size_t)nv1 * T;
+      if ((rc = grow_dev(h, (void **)&h->red, &h->red_cap, sizeof(double) * per_tile * h->sg.ntiles))) return rc;
+      const OutPlanes o2 = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
+      const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && (raw == 0 || raw == 3)) ? 1 : xpl};
+      const int r3 = raw3 ? 1 : raw;
+      for (int c = 0; c < NC; ++c) {
+        const unsigned t0 = (unsigned)((unsigned long long)h->sg.ntiles * c / NC), t1 = (unsigned)((unsigned long long)h->sg.ntiles * (c + 1) / NC);
+        switch (nr) {
+          case 1: launch_tile_export<1>(h, h->compute, t0, t1); break;
+          case 2: launch_tile_export<2>(h, h->compute, t0, t1); break;
+          default: launch_tile_export<3>(h, h->compute, t0, t1); break;
+        }
+        h->launches++;
+        CU(cudaEventRecord(h->ev_acc[c], h->compute));
+        CU(cudaStreamWaitEvent(h->comm_stream, h->ev_acc[c], 0));
+        if (t1 > t0) {
+          double *seg = h->red + (size_t)t0 * per_tile;
+          int e = g_nccl.Reduce(seg, seg, (size_t)(t1 - t0) * per_tile, NCCL_FLOAT64, NCCL_SUM, reduce_root, h->comm, h->comm_stream);
+          if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+        }
+        CU(cudaEventRecord(h->ev_red[c], h->comm_stream));
+        if (writer) {
+          CU(cudaStreamWaitEvent(h->fin_stream, h->ev_red[c], 0));
+          switch (nr) {
+            case 1: launch_tile_import<1>(h, h->fin_stream, o2, o3, nrmlz, ntr, raw, r3, t0, t1); break;
+            case 2: launch_tile_import<2>(h, h->fin_stream, o2, o3, nrmlz, ntr, raw, r3, t0, t1); break;
+            default: launch_tile_import<3>(h, h->fin_stream, o2, o3, nrmlz, ntr, raw, r3, t0, t1); break;
+          }
+          h->launches++;
+        }
+      }
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(h->ev_fin, writer ? h->fin_stream : h->comm_stream));
+      CU(cudaStreamWaitEvent(h->compute, h->ev_fin, 0));
+      if ((rc = mark_main(h))) return rc;
+    } else {
     const size_t row_recs = (size_t)g.im * g.km;
     unsigned tprev = 0;
     size_t rprev = 0;
@@ -1123,6 +1189,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     CU(cudaEventRecord(h->ev_fin, writer ? h->fin_stream : h->comm_stream));
     CU(cudaStreamWaitEvent(h->compute, h->ev_fin, 0));
     if ((rc = mark_main(h))) return rc;
+    }
   }
   for (int a = 0; a < 10; ++a) {
     if (dev_out) dev_out[a] = dst[a];

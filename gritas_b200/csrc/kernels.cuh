@@ -1140,10 +1140,18 @@ struct TileFinal {
   }
 };
 
-template <int NR, bool FLUSH>
+// MODE: what happens to the tile's sums once its list is accumulated
+constexpr int TILE_FINALIZE = 0;   // K2f: statistics straight from shared memory (one rank)
+constexpr int TILE_FLUSH = 1;      // K2t: add to the HBM records, empty the list
+constexpr int TILE_EXPORT = 2;     // K2x: write {n, sums} (+ the tile's records, if any) as compact planes: the operand of the
+                                   //      reduction across ranks -- 8*(1+NV) bytes per box instead of a 64-byte record
+constexpr int TILE_IMPORT = 3;     // K3x: no list; the planes come from the reduced buffer, then the statistics as K2f
+
+template <int NR, int MODE>
 __global__ void __launch_bounds__(TileFinal<NR>::THREADS, 2)
 k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh,
-             int raw2, int raw3, int fresh, unsigned tile0, unsigned tile1) {
+             int raw2, int raw3, int fresh, unsigned tile0, unsigned tile1, double *__restrict__ red) {
+  constexpr bool FLUSH = MODE == TILE_FLUSH;
   using TF = TileFinal<NR>;
   constexpr int NV = TF::NV, EPT = TF::EPT, CH = TF::CH, NTH = TF::THREADS;
   extern __shared__ __align__(16) double s_dyn[];
@@ -1157,11 +1165,17 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
   const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
-    const unsigned n = min(sg.fill[tile], sg.cap);
+    const unsigned n = (MODE == TILE_IMPORT) ? 0u : min(sg.fill[tile], sg.cap);
     if (FLUSH && n == 0u) continue;                       // uniform across the CTA
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
-    const bool addrec = !fresh || sg.dirty[tile] != 0u;
-    if (n == 0u) {                                          // empty list: nothing will store the planes
+    const bool addrec = (MODE != TILE_IMPORT) && (!fresh || sg.dirty[tile] != 0u);
+    // compact planes of this tile in the reduction buffer: [1 + NV][T] doubles, the counts first
+    double *rplanes = (MODE == TILE_EXPORT || MODE == TILE_IMPORT) ? red + (size_t)tile * (size_t)(1 + NV) * T : nullptr;
+    double *s_nd = s_stage;                                 // TILE_IMPORT: [T] counts as doubles (the staging area is idle)
+    if (MODE == TILE_IMPORT) {
+      for (unsigned e = tid; e < T; e += NTH) s_nd[e] = __ldcs(rplanes + e);
+      for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = __ldcs(rplanes + T + e);
+    } else if (n == 0u) {                                   // empty list: nothing will store the planes
       for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = 0.0;
       for (unsigned e = tid; e < T; e += NTH) s_tot[e] = 0u;
     }
@@ -1274,6 +1288,17 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
     __syncthreads();
     const size_t first = (size_t)tile << sg.tile_shift;
     const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
+    if (MODE == TILE_EXPORT) {
+      // ---- the tile's {n, sums} as compact planes; records that already hold part of the tile are folded in ----
+      for (unsigned e = tid; e < (1u + NV) * T; e += NTH) {
+        const unsigned q = e >> sg.tile_shift, b = e & (T - 1u);      // plane (0: counts), box
+        double v = (q == 0u) ? (double)s_tot[b] : s_val[(size_t)(q - 1u) * T + b];
+        if (addrec && b < nb) v = __dadd_rn(g.acc[(first + b) * (size_t)g.rs + q], v);
+        __stcs(rplanes + e, v);
+      }
+      __syncthreads();
+      continue;
+    }
     if (FLUSH) {
       // ---- add the tile to the HBM records: element e of the tile's span is (box e >> rs_shift, slot e & (rs-1));
       // each thread handles pairs of doubles (16 B), four pairs in flight.  Untouched records are zero: store, and
@@ -1319,7 +1344,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
 #pragma unroll
       for (int q = 0; q < 8; ++q) r[q] = 0.0;
       if (!zero) {
-        r[0] = (double)s_tot[b];
+        r[0] = (MODE == TILE_IMPORT) ? s_nd[b] : (double)s_tot[b];
 #pragma unroll
         for (int q = 0; q < NV; ++q) r[1 + q] = s_val[(size_t)q * T + b];
         if (addrec) {
