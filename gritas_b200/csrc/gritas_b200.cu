@@ -27,8 +27,8 @@ using namespace gb200;
 namespace {
 
 constexpr int NSLOT = 2;   // staging slots (double buffering)
-constexpr int NWK = 8;     // max worker streams of the tiled path (GRITAS_B200_WORKERS, default 3): partition
-                           // kernels of consecutive calls overlap
+constexpr int NWK = 8;     // max worker streams of the tiled path (GRITAS_B200_WORKERS, default 3): the K1 launches
+                           // of consecutive calls overlap
 constexpr int NCOL = 18;   // staged columns per slot
 enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME, C_B0, C_B1, C_B2, C_C0, C_C1, C_C2 };
 
@@ -113,9 +113,9 @@ struct gritas_b200_ctx {
   bool fused_norm = true;        // Norm consumes the tile lists itself (K2f) instead of flush (K2t) + K3
   double *red = nullptr;         // multi-rank Norm: compact {n, sums} planes per tile, the operand of ncclReduce
   size_t red_cap = 0;
-  // Worker streams: the partition kernels of one Accum call are a short dependent chain that cannot fill
-  // the GPU; consecutive calls run on different streams (own level-1 scratch, own level-miss record) and
-  // overlap.  Everything that reads or resets the accumulators runs on `compute` after join_workers().
+  // Worker streams: the K1 launch of one Accum call (1.2 M observations, two waves of short CTAs) cannot fill
+  // the GPU; consecutive calls run on different streams (own level-miss record) and overlap.  Everything
+  // that reads or resets the accumulators runs on `compute` after join_workers().
   cudaStream_t wk[NWK] = {};
   cudaEvent_t wk_done[NWK] = {};
   bool wk_pending[NWK] = {};
@@ -252,7 +252,7 @@ int clear_status(gritas_b200_handle h) {
   return 0;
 }
 
-// `compute` waits for every partition kernel queued on the worker streams (no host synchronisation).
+// `compute` waits for every K1 launch queued on the worker streams (no host synchronisation).
 int join_workers(gritas_b200_handle h) {
   for (int w = 0; w < NWK; ++w)
     if (h->wk_pending[w]) {
@@ -262,7 +262,7 @@ int join_workers(gritas_b200_handle h) {
   return 0;
 }
 
-// Marks an accumulator-wide operation on `compute` (reset, flush, add_raw): later partition kernels on the
+// Marks an accumulator-wide operation on `compute` (reset, flush, add_raw): later K1 launches on the
 // worker streams must not start before it.
 int mark_main(gritas_b200_handle h) {
   if (h->main_ev) CU(cudaEventRecord(h->main_ev, h->compute));
@@ -1092,7 +1092,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     }
     CU(cudaGetLastError());
     h->launches++;
-    if ((rc = mark_main(h))) return rc;     // later partition kernels append to the lists this kernel reads
+    if ((rc = mark_main(h))) return rc;     // later K1 launches append to the lists this kernel reads
   } else if (!piped) {
     int rc = launch_finalize(h, h->compute, dst, raw, raw3, xpl, nrmlz, ntr, 0, nrows, true);
     if (rc) return rc;

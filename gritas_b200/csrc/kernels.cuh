@@ -1,9 +1,16 @@
 // kernels.cuh -- sm_100a device code of the GrITAS gridding hot path.
 //
-// K1  box index + QC filter      reference m_gritas_grids.f:405-461, gritas.f:562-587, 710-739
-// K2a fast accumulate            reference m_gritas_grids.f:432-441, 465-470 (warp-aggregated fp64 RED)
-// K2b deterministic accumulate   same lines; stable sort by box key, then in-order segment sums
-// K3  finalize                   reference m_gritas_grids.f:566-654
+// classify4        box index + QC filter, shared by every accumulate kernel
+//                                reference m_gritas_grids.f:405-461, gritas.f:562-587, 710-739
+// k_accum_fast     direct fast accumulate (warp-aggregated fp64 RED)      m_gritas_grids.f:432-441, 465-470
+// k_list_obs       K1 of the tiled fast path: one 32-byte entry per accepted observation in its tile's list
+// k_tile_final     K2f / K2t / K2x / K3x: a tile's list accumulated in shared memory (counting sort, no fp64
+//                  atomics), then finalized / flushed to the records / exported for or imported from the
+//                  reduction across ranks                                  same lines and m_gritas_grids.f:566-654
+// k_box_keys + CUB sort + k_segment_sum   deterministic accumulate: stable sort by box key, in-order segment sums
+// k_finalize3/2    K3: finalize from the records                           m_gritas_grids.f:566-654, 1178-1341 (3CH)
+// k_minmax         GrITAS_MinMax_                                          m_gritas_grids.f:1019-1167
+// k_sortkey_*      the pre-sort of gritas.f:499-508 (with CUB radix sort passes on the host side)
 //
 // HBM layout of the accumulators: one record of RS doubles per box,
 //   nr=1: {n, Sx, Sxx, pad}            RS=4 (32 B = one DRAM sector)
