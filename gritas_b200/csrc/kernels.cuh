@@ -1154,6 +1154,7 @@ constexpr int TILE_EXPORT = 2;     // K2x: write {n, sums} (+ the tile's records
                                    //      reduction across ranks -- 8*(1+NV) bytes per box instead of a 64-byte record
 constexpr int TILE_IMPORT = 3;     // K3x: no list; the planes come from the reduced buffer, then the statistics as K2f
 
+#pragma nv_diag_suppress 186   // TILE_IMPORT instantiates the list loop with n = 0: 'pointless comparison' is the point
 template <int NR, int MODE>
 __global__ void __launch_bounds__(TileFinal<NR>::THREADS, 2)
 k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh,
@@ -1448,6 +1449,8 @@ __global__ void __launch_bounds__(256)
 k_add_base(const int *__restrict__ idx, int *__restrict__ out, int base, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = idx[i] + base;
 }
+
+#pragma nv_diag_default 186
 
 // Reset when nothing was flushed into the records since the last reset (everything parked in the tile lists or
 // consumed by K2f): only tiles that took a direct accumulate (bin / list overflow, sg.dirty) hold anything.
