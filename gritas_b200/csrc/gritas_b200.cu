@@ -93,10 +93,19 @@ struct gritas_b200_ctx {
   Slot slot[NSLOT];
   int next_slot = 0;
   unsigned call_seq = 0;
-  // deterministic path scratch
-  unsigned *keys = nullptr, *idx = nullptr, *keys2 = nullptr, *idx2 = nullptr;
-  size_t sort_cap = 0;
-  void *cub_tmp = nullptr;
+  // deterministic path: keys + sort of call n+1 run on a sort stream while the in-order segment sums of call n (which
+  // must stay serial: they continue the running sums in the records) run on `compute`.  Two buffer sets alternate.
+  struct DetBuf {
+    unsigned *keys = nullptr, *idx = nullptr, *keys2 = nullptr, *idx2 = nullptr;
+    size_t cap = 0;
+    void *tmp = nullptr;
+    size_t tmp_cap = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t sorted = nullptr, consumed = nullptr;
+    bool busy = false;          // `consumed` has been recorded at least once
+  } det[2];
+  int next_det = 0;
+  void *cub_tmp = nullptr;      // pre-sort scratch
   size_t cub_cap = 0;
   int key_bits = 32;
   // tiled fast path: staging lists + flush bookkeeping
@@ -495,32 +504,48 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     }
   } else {
     h->acc_fresh = false;
-    // K1 keys -> stable LSD radix sort of (key, obs index) -> in-order segment sums
-    if (h->sort_cap < (size_t)n) {
-      for (unsigned **p : {&h->keys, &h->idx, &h->keys2, &h->idx2}) {
+    // keys -> stable LSD radix sort of (key, obs index) on a sort stream -> in-order segment sums on `compute`
+    gritas_b200_ctx::DetBuf &db = h->det[h->next_det];
+    h->next_det ^= 1;
+    if (!db.st) {
+      CU(cudaStreamCreateWithFlags(&db.st, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&db.sorted, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&db.consumed, cudaEventDisableTiming));
+    }
+    if (db.busy) CU(cudaStreamWaitEvent(db.st, db.consumed, 0));   // the segment sums that read this buffer set are done
+    if (db.cap < (size_t)n) {
+      if (db.busy) CU(cudaEventSynchronize(db.consumed));
+      for (unsigned **p : {&db.keys, &db.idx, &db.keys2, &db.idx2}) {
         if (*p) CU(cudaFree(*p));
         *p = nullptr;
       }
       size_t want = (size_t)n + (size_t)n / 8 + 1024;
-      CU(cudaMalloc(&h->keys, want * 4));
-      CU(cudaMalloc(&h->idx, want * 4));
-      CU(cudaMalloc(&h->keys2, want * 4));
-      CU(cudaMalloc(&h->idx2, want * 4));
-      h->sort_cap = want;
+      CU(cudaMalloc(&db.keys, want * 4));
+      CU(cudaMalloc(&db.idx, want * 4));
+      CU(cudaMalloc(&db.keys2, want * 4));
+      CU(cudaMalloc(&db.idx2, want * 4));
+      db.cap = want;
     }
     size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, h->keys, h->keys2, h->idx, h->idx2, n, 0, h->key_bits, h->compute);
-    if (grow_dev(h, &h->cub_tmp, &h->cub_cap, need)) return GRITAS_B200_ERR_CUDA;
-    k_box_keys<<<grid_for((size_t)n, ACC_THREADS, 8), ACC_THREADS, smem, h->compute>>>(
-        h->g, c, f, h->d_status, h->call_seq, h->keys, h->idx, (unsigned)h->nrec);
-    size_t tmp = h->cub_cap;
-    CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->keys, h->keys2, h->idx, h->idx2, n, 0, h->key_bits,
-                                       h->compute));
-    switch (h->g.nr) {
-      case 1: launch_segsum<1>(h, c, f, h->keys2, h->idx2, n); break;
-      case 2: launch_segsum<2>(h, c, f, h->keys2, h->idx2, n); break;
-      default: launch_segsum<3>(h, c, f, h->keys2, h->idx2, n); break;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, db.keys, db.keys2, db.idx, db.idx2, n, 0, h->key_bits, db.st);
+    if (db.tmp_cap < need) {
+      if (db.busy) CU(cudaEventSynchronize(db.consumed));
+      if (grow_dev(h, &db.tmp, &db.tmp_cap, need)) return GRITAS_B200_ERR_CUDA;
     }
+    if (any_copy) CU(cudaStreamWaitEvent(db.st, s.copied, 0));
+    k_box_keys<<<grid_for((size_t)n, ACC_THREADS, 8), ACC_THREADS, smem, db.st>>>(
+        h->g, c, f, h->d_status, h->call_seq, db.keys, db.idx, (unsigned)h->nrec);
+    size_t tmp = db.tmp_cap;
+    CU(cub::DeviceRadixSort::SortPairs(db.tmp, tmp, db.keys, db.keys2, db.idx, db.idx2, n, 0, h->key_bits, db.st));
+    CU(cudaEventRecord(db.sorted, db.st));
+    CU(cudaStreamWaitEvent(h->compute, db.sorted, 0));
+    switch (h->g.nr) {
+      case 1: launch_segsum<1>(h, c, f, db.keys2, db.idx2, n); break;
+      case 2: launch_segsum<2>(h, c, f, db.keys2, db.idx2, n); break;
+      default: launch_segsum<3>(h, c, f, db.keys2, db.idx2, n); break;
+    }
+    CU(cudaEventRecord(db.consumed, h->compute));
+    db.busy = true;
     h->launches += 2 + (uint64_t)((h->key_bits + 7) / 8) * 2 + 1;  // keys, segsum, sort passes (approx.)
   }
   CU(cudaGetLastError());
@@ -769,10 +794,17 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (p) cudaFree(p);
   for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1]})
     if (p) cudaFree(p);
+  for (auto &db : h->det) {
+    if (db.st) { cudaStreamSynchronize(db.st); cudaStreamDestroy(db.st); }
+    if (db.sorted) cudaEventDestroy(db.sorted);
+    if (db.consumed) cudaEventDestroy(db.consumed);
+    for (void *p : {(void *)db.keys, (void *)db.idx, (void *)db.keys2, (void *)db.idx2, db.tmp})
+      if (p) cudaFree(p);
+  }
   if (h->d_lut) cudaFree(h->d_lut);
   if (h->d_mask) cudaFree(h->d_mask);
   for (void *p : {(void *)h->d_table, (void *)h->d_p1, (void *)h->d_p2, (void *)h->d_status, (void *)h->g.acc,
-                  (void *)h->keys, (void *)h->idx, (void *)h->keys2, (void *)h->idx2, h->cub_tmp, (void *)h->out})
+                  h->cub_tmp, (void *)h->out})
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
   if (h->compute && h->own_compute) cudaStreamDestroy(h->compute);
@@ -1038,6 +1070,12 @@ static int launch_finalize(gritas_b200_handle h, cudaStream_t sm, double *const 
   return 0;
 }
 
+// GRITAS_B200_FORCE_PIPELINE=1 (tests): a single rank runs the multi-rank Norm pipeline, minus the collective.
+static bool force_pipeline() {
+  const char *e = getenv("GRITAS_B200_FORCE_PIPELINE");
+  return e && atoi(e) != 0;
+}
+
 // Finalize (raw=0) or export the raw sums (raw=1) into reference-layout planes.
 // reduce_root < 0: the accumulators are final (flushed, all-reduced if wanted) -- finalize them.
 // reduce_root >= 0 (multi-rank): tile flush, ncclReduce to the root and finalize are pipelined chunk by
@@ -1055,7 +1093,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
   // nlevs<2: the reference returns before the 3-D loop (m_gritas_grids.f:607) -> 3-D sums stay raw
   const bool raw3 = raw == 1 || raw == 2 || g.nlevs < 2;   // (also m_gritas_grids.f:1292 for the 3CH variant)
-  const bool piped = reduce_root >= 0 && h->comm != nullptr && h->nranks > 1;
+  const bool piped = reduce_root >= 0 && ((h->comm != nullptr && h->nranks > 1) || force_pipeline());
   const bool writer = !piped || h->rank == reduce_root;
   double *dst[10];
   bool bounce[10];
@@ -1134,7 +1172,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
         h->launches++;
         CU(cudaEventRecord(h->ev_acc[c], h->compute));
         CU(cudaStreamWaitEvent(h->comm_stream, h->ev_acc[c], 0));
-        if (t1 > t0) {
+        if (t1 > t0 && h->nranks > 1) {
           double *seg = h->red + (size_t)t0 * per_tile;
           int e = g_nccl.Reduce(seg, seg, (size_t)(t1 - t0) * per_tile, NCCL_FLOAT64, NCCL_SUM, reduce_root, h->comm, h->comm_stream);
           if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
@@ -1170,7 +1208,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
       }
       CU(cudaEventRecord(h->ev_acc[c], h->compute));
       CU(cudaStreamWaitEvent(h->comm_stream, h->ev_acc[c], 0));
-      if (rec_end > rprev) {
+      if (rec_end > rprev && h->nranks > 1) {
         double *seg = g.acc + rprev * g.rs;
         int e = g_nccl.Reduce(seg, seg, (rec_end - rprev) * g.rs, NCCL_FLOAT64, NCCL_SUM, reduce_root, h->comm, h->comm_stream);
         if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
@@ -1253,7 +1291,7 @@ int gritas_b200_norm_reduce(gritas_b200_handle h, int root, int nrmlz, int ntres
   if (root < 0 || root >= h->nranks) return fail(h, GRITAS_B200_ERR_ARG, "bad root");
   CU(cudaStreamSynchronize(h->copy));
   double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
-  if (h->nranks == 1 || !h->comm) {
+  if ((h->nranks == 1 || !h->comm) && !force_pipeline()) {
     if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
     return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
   }
@@ -1266,7 +1304,7 @@ int gritas_b200_norm_reduce_device(gritas_b200_handle h, int root, int nrmlz, in
   if (root < 0 || root >= h->nranks || !outs10) return fail(h, GRITAS_B200_ERR_ARG, "bad root / outs");
   CU(cudaStreamSynchronize(h->copy));
   double *const u[10] = {};
-  if (h->nranks == 1 || !h->comm) {
+  if ((h->nranks == 1 || !h->comm) && !force_pipeline()) {
     if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
     return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10);
   }
