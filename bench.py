@@ -431,7 +431,7 @@ def run_b200(args):
     achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
     traffic = None
     try:   # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic_cfg2.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic_cfg2.json")))
         if staged and cfg.name == "cfg2" and nfiles == cfg.nfiles and args.scale == 1.0:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
