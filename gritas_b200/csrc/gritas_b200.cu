@@ -1151,7 +1151,10 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     const bool staged = h->staging && h->staged_upper > 0;
     const size_t T = h->staging ? ((size_t)1 << h->sg.tile_shift) : 1;
     static const bool compact_off = getenv("GRITAS_B200_COMPACT_REDUCE") && atoi(getenv("GRITAS_B200_COMPACT_REDUCE")) == 0;
-    if (staged && h->fused_norm && raw != 2 && !compact_off) {
+    if (h->staging && h->fused_norm && raw != 2 && !compact_off) {
+      // (The choice must be the same on every rank -- it decides the size of the collective -- so it depends on the
+      // handle's configuration only, not on whether this rank has anything parked: a rank whose data went to the
+      // records, or that has none, exports those.)
       // Tiled path: the month is parked in the tile lists.  Per chunk of tiles: K2x accumulates the lists and exports
       // {n, sums} as compact planes (48 bytes per box at nr = 2 instead of a 64-byte record; records that already hold
       // part of a tile are folded in), ncclReduce sums the planes to the root, K3x finalizes them there.  The records and

@@ -747,18 +747,19 @@ def test_presort_is_the_reference_permutation(name, device_inputs):
     G.close()
 
 
-@pytest.mark.parametrize("case", ["plain", "overflow", "flushed", "direct"])
+@pytest.mark.parametrize("case", ["plain", "overflow", "flushed", "records_only", "direct"])
 def test_multi_rank_norm_pipeline_on_one_rank(case, monkeypatch):
     """The multi-rank Norm pipeline without the collective (GRITAS_B200_FORCE_PIPELINE=1): tiled path = K2x (tile sums
     exported as compact planes, records folded in where a tile has any) -> K3x (finalize from the planes); other paths =
     tile flush -> K3.  'overflow': tiny lists, most entries take the direct accumulate (dirty tiles); 'flushed': half of
-    the data already sits in the records; 'direct': no tile lists at all."""
+    the data already sits in the records; 'records_only': the lists exist but the data took the direct kernel (files
+    too small for the locality probe) -- the planes are exported from the records; 'direct': no tile lists at all."""
     monkeypatch.setenv("GRITAS_B200_FORCE_PIPELINE", "1")
     if case == "overflow":
         monkeypatch.setenv("GRITAS_B200_STAGE_SLOTS", str(64 * 1024))
     cfg, files = small("cfg2", 0.05, 4)
     table, l2d, l3d, p1, p2 = H.setup(cfg)
-    mode = cabi.MODE_FAST | (cabi.FLAG_NO_STAGING if case == "direct" else cabi.FLAG_FORCE_TILED)
+    mode = cabi.MODE_FAST | {"direct": cabi.FLAG_NO_STAGING, "records_only": 0}.get(case, cabi.FLAG_FORCE_TILED)
     G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
     for fi, c in enumerate(files):
         G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 2), len(c["lat"]), 2, table, p1, p2,
@@ -769,7 +770,7 @@ def test_multi_rank_norm_pipeline_on_one_rank(case, monkeypatch):
     G.norm_reduce_into(out, root=0)
     ref, _ = H.oracle_run(cfg, files, 2)
     H.compare(out, ref, l2d, l3d, 2, exact=False, tol=TOL_FAST)
-    if case != "direct":                                   # the tiled pipeline does not change the state: Norm still works
+    if case != "direct":                                   # the plane-based pipeline does not change the state: Norm still works
         again = G.alloc_grids()
         G.norm_into(again)
         H.compare(again, ref, l2d, l3d, 2, exact=False, tol=TOL_FAST)
