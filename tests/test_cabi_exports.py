@@ -60,6 +60,14 @@ def test_no_cpu_fallback_without_device(lib):
     t = np.zeros((4, 4), np.int32, order="F")
     rc = lib.gritas_b200_create(ctypes.byref(h), 8, 5, 2, 2, 0, 1, 1, p1.ctypes.data, p2.ctypes.data, t.ctypes.data, 4, 4, 0, -1)
     assert rc == cabi.ERR_CUDA and not h.value
+    # the pre-sort works without a handle, but not without a device: it must not sort on the host
+    n = 16
+    ic = np.arange(n, dtype=np.int32)
+    dc = np.linspace(-1.0, 1.0, n)
+    out = np.full(n, -7, np.int32)
+    rc = lib.gritas_b200_presort(None, n, ic.ctypes.data, dc.ctypes.data, dc.ctypes.data, dc.ctypes.data, ic.ctypes.data,
+                                 ic.ctypes.data, ic.ctypes.data, ic.ctypes.data, 0, out.ctypes.data)
+    assert rc == cabi.ERR_CUDA and np.all(out == -7)
 
 
 def test_product_never_imports_the_oracle():
