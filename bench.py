@@ -4,9 +4,10 @@
 A "step" is one pass of the hot path over one month of synthetic conventional ODS columns
 (BASELINE.json configs[1]: 124 six-hourly files x ~1.21 M obs, omf+oma in one pass, 1x1 deg x 26
 levels, 16 (kt,kx) grids): zero the accumulators, accumulate every file (QC filter + box index +
-count/sum/sum-of-squares, fused kernel), [all-reduce the partial grids over ranks], finalize
-mean / rms / stdv.  With N ranks every rank processes its own month (weak scaling) and the grids
-are summed with one NCCL all-reduce before the finalize.
+count/sum/sum-of-squares, fused kernel), finalize mean / rms / stdv.  With N ranks the SAME month is
+sharded f mod N (strong scaling, BASELINE.json configs[1]); every rank then finalizes 1/N of the rows,
+pulling the parked observations of those rows from all ranks over NVLink peer memory (sharded Norm).
+An extra weak-scaling leg (every rank its own month) is reported under "weak".
 
   value  : whole-job obs/s with the columns already resident in HBM (CUDA events on the library stream)
   e2e    : same step through the C ABI with pinned HOST columns (H2D inside) and the finalized
@@ -52,6 +53,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-staging", action="store_true", help="fast mode without the tiled accumulate")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling leg")
+    ap.add_argument("--norm", default="sharded", choices=["sharded", "reduce"],
+                    help="N > 1: sharded Norm over peer memory (default) or the NCCL reduce pipeline")
     return ap.parse_args()
 
 
@@ -63,6 +67,16 @@ def gen_files(cfg, first, count, workers=8):
         return {k: np.ascontiguousarray(c[k]) for k in COLS_F64 + COLS_I32}
     with ThreadPoolExecutor(max_workers=max(1, min(workers, os.cpu_count() or 1))) as ex:
         return list(ex.map(one, range(count)))
+
+
+def gen_files_idx(cfg, indices, workers=8):
+    from gritas_b200 import synth
+
+    def one(i):
+        c = synth.make_file(cfg, i)
+        return {k: np.ascontiguousarray(c[k]) for k in COLS_F64 + COLS_I32}
+    with ThreadPoolExecutor(max_workers=max(1, min(workers, os.cpu_count() or 1))) as ex:
+        return list(ex.map(one, indices))
 
 
 def workload_name(cfg, nfiles):
@@ -216,11 +230,18 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def stats3(xs):
+    xs = sorted(float(x) for x in xs)
+    return {"min": xs[0], "median": xs[len(xs) // 2], "max": xs[-1]}
+
+
 def run_b200(args):
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
-    from gritas_b200 import cabi, synth
+    from gritas_b200 import cabi, shard, synth
     from gritas_b200.m_gritas_grids import Grids, nccl_unique_id
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,12 +255,17 @@ def run_b200(args):
 
     cfg = synth.get_config(args.config, args.scale)
     nfiles = args.files or cfg.nfiles
-    files = gen_files(cfg, rank * cfg.nfiles, nfiles)        # before CUDA work: numpy threads only
-    nobs_rank = sum(len(c["lat"]) for c in files)
+    # BASELINE.json configs[1]: ONE month, its files sharded over the ranks f mod N (strong scaling)
+    mine = shard.files_for_rank(nfiles, rank, world)
+    files = gen_files_idx(cfg, mine)                          # before CUDA work: numpy threads only
     table0, _, _ = synth.kxkt_table(cfg)
-    # observations that must end up in the count grids: QC pass (passive kept, ioptn > 0) and (kx,kt) in the table
-    expected_rank = int(sum(np.count_nonzero(np.isin(c["qcexcl"], (0, synth.X_PASSIVE, synth.X_PRE_BAD)) &
-                                             (table0[c["kx"] - 1, c["kt"] - 1] != 0)) for c in files))
+
+    def accepted(fs):
+        # observations that must end up in the count grids: QC pass (passive kept, ioptn > 0) and (kx,kt) in the table
+        return int(sum(np.count_nonzero(np.isin(c["qcexcl"], (0, synth.X_PASSIVE, synth.X_PRE_BAD)) &
+                                        (table0[c["kx"] - 1, c["kt"] - 1] != 0)) for c in fs))
+    nobs_rank = sum(len(c["lat"]) for c in files)
+    expected_rank = accepted(files)
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -248,27 +274,45 @@ def run_b200(args):
     mode = (cabi.MODE_FAST if args.mode == "fast" else cabi.MODE_DETERMINISTIC) | cabi.FLAG_ASYNC | cabi.FLAG_HOLD_INPUTS
     if args.no_staging:
         mode |= cabi.FLAG_NO_STAGING
+    if world > 1 and args.mode == "fast" and not args.no_staging:
+        mode |= cabi.FLAG_FORCE_TILED        # the ranks must agree on the path; a short shard would not trigger the locality probe
     G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode, device=local)
     p1, p2 = G.GrITAS_Pint()
     NR = cfg.nr
     IOPT = cabi.IOPT_OMF_OMA if NR == 2 else cabi.IOPT_OMF
     G._ensure(NR, table, p1, p2, l2d, l3d)
+    norm_kind = "k2f"
     if world > 1:
         ids = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         G.comm_init(world, rank, ids[0])
+        blobs = [None] * world
+        dist.all_gather_object(blobs, G.peer_export())
+        ok = torch.ones(1, device="cuda")
+        try:
+            if args.norm == "reduce":
+                raise RuntimeError("--norm reduce")
+            G.peer_attach(world, rank, blobs)
+            norm_kind = "sharded-peer"
+        except RuntimeError as e:            # no CUDA IPC between the ranks: the NCCL pipeline still works
+            ok[0] = 0
+            if rank == 0 and args.norm != "reduce":
+                print(f"peer_attach failed ({e}); falling back to norm_reduce", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok[0]) == 0:
+            norm_kind = "nccl-reduce"
     L = cabi.load()
     stream = torch.cuda.ExternalStream(G.stream(), device=torch.device("cuda", local))
+    tot = torch.tensor([float(nobs_rank), float(expected_rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    nobs_total, expected_total = int(tot[0]), int(tot[1])
 
-    dev_files = [{k: torch.from_numpy(v).cuda() for k, v in c.items()} for c in files]
-    torch.cuda.synchronize()
-    # host copies: pinned for the end-to-end arm; the pageable originals are only kept for the CPU baseline sample
-    pin_files = None
-    if not args.no_e2e:
-        pin_files = [{k: torch.from_numpy(v).pin_memory() for k, v in c.items()} for c in files]
-    keep = 32 if (rank == 0 and world == 1 and not args.no_cpu_baseline) else 0
-    files = files[:keep]
-    import ctypes
+    def to_dev(fs):
+        return [{k: torch.from_numpy(v).cuda() for k, v in c.items()} for c in fs]
+
+    def to_pin(fs):
+        return [{k: torch.from_numpy(v).pin_memory() for k, v in c.items()} for c in fs]
 
     def calls_of(cols):
         # argument tuples of gritas_b200_accum_ods, built once: the timed loop is then what a compiled
@@ -281,6 +325,7 @@ def run_b200(args):
                         -999.0, 999.0, synth.X_PASSIVE, synth.X_PRE_BAD, None, None))
         return out
     dptr = [C_void() for _ in range(10)]
+    outs10 = (ctypes.c_void_p * 10)()
     host_enqueue = []
 
     def barrier():
@@ -291,7 +336,30 @@ def run_b200(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    outs10 = (ctypes.c_void_p * 10)()
+    def norm(host_out):
+        if world == 1:
+            # GrITAS_Norm: on the tiled path K2f accumulates the parked tile lists and finalizes in one kernel
+            if host_out is None:
+                rc = L.gritas_b200_norm_device(G.handle, 1, -1, *[None] * 5, *dptr[5:])
+                if rc:
+                    raise RuntimeError(f"norm_device rc={rc}: {G._err()}")
+            else:
+                G.norm_into(host_out)
+        elif norm_kind == "sharded-peer":
+            # every rank finalizes its slab of rows, pulling the parked entries of those rows from all ranks over NVLink
+            if host_out is None:
+                rc = L.gritas_b200_norm_sharded_device(G.handle, 1, -1, ctypes.cast(outs10, ctypes.POINTER(ctypes.c_void_p)))
+                if rc:
+                    raise RuntimeError(f"norm_sharded_device rc={rc}: {G._err()}")
+            else:
+                G.norm_sharded_into(host_out)
+        else:
+            if host_out is None:
+                rc = L.gritas_b200_norm_reduce_device(G.handle, 0, 1, -1, ctypes.cast(outs10, ctypes.POINTER(ctypes.c_void_p)))
+                if rc:
+                    raise RuntimeError(f"norm_reduce_device rc={rc}: {G._err()}")
+            else:
+                G.norm_reduce_into(host_out, root=0)
 
     def step(cols, host_out=None, marks=None):
         G.reset()
@@ -306,114 +374,154 @@ def run_b200(args):
         if marks is not None:
             G.barrier()                # the library stream waits for the worker streams (no host sync)
             marks[1].record(stream)
-        if world == 1:
-            # GrITAS_Norm: on the tiled path K2f accumulates the parked tile lists and finalizes in one kernel
-            if host_out is None:
-                rc = L.gritas_b200_norm_device(G.handle, 1, -1, *[None] * 5, *dptr[5:])
-                if rc:
-                    raise RuntimeError(f"norm_device rc={rc}")
-            else:
-                G.norm_into(host_out)
-            if marks is not None:
-                marks[2].record(stream)
-        else:
-            # one collective: tile flush + ncclReduce to rank 0 + finalize, pipelined chunk by chunk
-            if marks is not None:
-                marks[2].record(stream)
-            if host_out is None:
-                rc = L.gritas_b200_norm_reduce_device(G.handle, 0, 1, -1, ctypes.cast(outs10, ctypes.POINTER(ctypes.c_void_p)))
-                if rc:
-                    raise RuntimeError(f"norm_reduce_device rc={rc}: {G._err()}")
-            else:
-                G.norm_reduce_into(host_out, root=0)
+        norm(host_out)
+        if marks is not None:
+            marks[2].record(stream)
 
-    # ---- device-resident arm ---------------------------------------------------------------
-    dev_calls = calls_of(dev_files)
-    check = None
-    if world > 1:
-        # sanity of the multi-rank path: the reduced count grid on rank 0 must hold every rank's accepted obs
-        G.reset()
-        for a in dev_calls:
-            L.gritas_b200_accum_ods(*a)
-        raw = G.alloc_grids()
-        G.get_raw(None, None, None, None, None, None, None, raw["nobs_3d"])
-        mine = torch.tensor([float(raw["nobs_3d"].sum())], dtype=torch.float64, device="cuda")
-        dist.all_reduce(mine)
-        chk = G.alloc_grids()
-        G.reset()
-        for a in dev_calls:
-            L.gritas_b200_accum_ods(*a)
-        G.norm_reduce_into(chk, root=0)
-        if rank == 0:
-            check = bool(chk["nobs_3d"].sum() == float(mine[0]))
-            if not check:
-                raise SystemExit(f"multi-rank check failed: reduced count {chk['nobs_3d'].sum()} != {float(mine[0])}")
-        del raw, chk
-    sampler = ClockSampler(local)
-    sampler.start()
-    sampler.ready.wait(timeout=20)
-    for _ in range(max(3, args.warmup)):
-        step(dev_calls)
-    c0 = G.counters()
-    barrier()
-    e0, e1 = ev(), ev()
-    marks = [(ev(), ev(), ev()) for _ in range(args.steps)]
-    sampler.active = True
-    e0.record(stream)
-    for s in range(args.steps):
-        step(dev_calls, marks=marks[s])
-    e1.record(stream)
-    barrier()
-    sampler.active = False
-    c1 = G.counters()
-    if world == 1:
-        # every accepted observation of the month is in exactly one box (count grid vs the host-side filter)
-        raw = G.alloc_grids()
-        G.get_raw(None, None, None, None, None, None, None, raw["nobs_3d"])
-        check = bool(int(raw["nobs_3d"].sum()) == expected_rank)
-        if not check:
-            raise SystemExit(f"count check failed: {int(raw['nobs_3d'].sum())} binned, {expected_rank} expected")
-        del raw
-    host_ms = 1e3 * float(np.mean(host_enqueue[-args.steps:]))
-    ms = e0.elapsed_time(e1) / args.steps
-    accum_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
-    flush_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks]))
-    t = torch.tensor([ms, accum_ms, flush_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, accum_ms, flush_ms = float(t[0]), float(t[1]), float(t[2])
-    launches_per_step = (c1["launches"] - c0["launches"]) // args.steps
-    value = nobs_rank * world / (ms * 1e-3)
+    def slab_count(host):
+        """accepted observations in this rank's slab of the count grid (whole grid at N=1)"""
+        if world == 1 or norm_kind != "sharded-peer":
+            return float(host["nobs_3d"].sum()) if (world == 1 or rank == 0) else 0.0
+        a3, b3, _, _ = G.slab(rank, world)
+        tot3 = 0.0
+        for l in range(a3 // cfg.jm, (b3 - 1) // cfg.jm + 1 if b3 > a3 else 0):
+            ja, jb = max(a3, l * cfg.jm) - l * cfg.jm, min(b3, (l + 1) * cfg.jm) - l * cfg.jm
+            tot3 += float(host["nobs_3d"][:, ja:jb, :, l].sum())
+        return tot3
 
-    # ---- end-to-end arm: pinned host columns in, finalized grids out to pinned host arrays ----
-    e2e = None
-    if not args.no_e2e:
-        host_out = G.alloc_grids(pinned=True)
-        pin_calls = calls_of(pin_files)
-        step(pin_calls, host_out)
+    def timed_device(calls, steps, warmup):
+        for _ in range(warmup):
+            step(calls)
+        c0 = G.counters()
+        barrier()
+        e0, e1 = ev(), ev()
+        marks = [(ev(), ev(), ev()) for _ in range(steps)]
+        sampler.active = True
+        e0.record(stream)
+        for s in range(steps):
+            step(calls, marks=marks[s])
+        e1.record(stream)
+        barrier()
+        sampler.active = False
+        c1 = G.counters()
+        acc = [m[0].elapsed_time(m[1]) for m in marks]
+        nrm = [m[1].elapsed_time(m[2]) for m in marks]
+        t = torch.tensor([e0.elapsed_time(e1) / steps, float(np.mean(acc)), float(np.mean(nrm))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"ms": float(t[0]), "accum_ms": float(t[1]), "norm_ms": float(t[2]), "accum_spread": stats3(acc),
+                "norm_spread": stats3(nrm), "launches_per_step": (c1["launches"] - c0["launches"]) // steps}
+
+    def timed_e2e(calls, host_out, steps):
+        step(calls, host_out)
         b0 = G.counters()
         barrier()
         sampler.active = True
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            step(pin_calls, host_out)
+        for _ in range(steps):
+            step(calls, host_out)
         G.sync()
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
+        dt = (time.perf_counter() - t0) / steps
         sampler.active = False
         b1 = G.counters()
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        by = torch.tensor([float(b1["h2d"] - b0["h2d"]), float(b1["d2h"] - b0["d2h"])], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt[0])
-        e2e = {"value": nobs_rank * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "h2d_bytes_per_step": (b1["h2d"] - b0["h2d"]) // args.e2e_steps,
-               "d2h_bytes_per_step": (b1["d2h"] - b0["d2h"]) // args.e2e_steps,
-               "note": "per rank bytes; pinned host columns -> C ABI -> pinned host mean/rms/stdv/xcov/nobs grids"}
+            dist.all_reduce(by)
+        return float(tt[0]), int(by[0]) // steps, int(by[1]) // steps
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.ready.wait(timeout=20)
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    dev_files = to_dev(files)
+    torch.cuda.synchronize()
+    dev_calls = calls_of(dev_files)
+    dev = timed_device(dev_calls, args.steps, max(3, args.warmup))
+    ms, accum_ms, norm_ms = dev["ms"], dev["accum_ms"], dev["norm_ms"]
+    value = nobs_total / (ms * 1e-3)
+
+    # every accepted observation of the month is in exactly one box (count grid vs the host-side filter)
+    host_out = G.alloc_grids(pinned=True)
+    step(dev_calls, host_out)
+    cnt = torch.tensor([slab_count(host_out)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt)
+    check = bool(int(cnt[0]) == expected_total)
+    if not check:
+        raise SystemExit(f"count check failed: {int(cnt[0])} binned, {expected_total} expected")
+
+    # ---- end-to-end arm: pinned host columns in, finalized grids out to pinned host arrays ----
+    e2e = None
+    if not args.no_e2e:
+        pin_files = to_pin(files)
+        dt, h2d, d2h = timed_e2e(calls_of(pin_files), host_out, args.e2e_steps)
+        e2e = {"value": nobs_total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": "bytes summed over the ranks; pinned host columns -> gritas_b200_accum_ods -> Norm -> pinned host "
+                       "mean/rms/stdv/xcov/nobs grids" + ("" if world == 1 else " (every rank copies its slab of rows)")}
         del pin_files
+
+    # ---- the drop-in's end to end: what an untouched gritas.f gets through fortran/m_gritas_b200.F90 ----
+    # pageable columns, del built and ob_flag filtered on the host as gritas.f:562-587, 710-739 do, GrITAS_Accum
+    # (ob_flag inout, synchronous), GrITAS_Norm into pageable arrays
+    e2e_pageable = None
+    if not args.no_e2e and world == 1:
+        Gp = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_FAST, device=local)
+        Gp._ensure(NR, table, p1, p2, l2d, l3d)
+        pfiles = []
+        for c in files:
+            d = np.empty((len(c["lat"]), NR), order="F")
+            d[:, 0] = c["omf"]
+            if NR == 2:
+                d[:, 1] = c["oma"]
+            # gritas.f:710-739 as the untouched driver runs it on the host (no time / longitude window, ioptn > 0)
+            fl = np.where(np.isin(c["qcexcl"], (0, synth.X_PASSIVE, synth.X_PRE_BAD)), 0, 1).astype(np.int32)
+            pfiles.append((c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], d, fl))
+        pout = Gp.alloc_grids()
+
+        def pstep():
+            Gp.reset()
+            for lat, lon, lev, kx, kt, d, fl in pfiles:
+                fw = fl.copy()
+                Gp.GrITAS_Accum(lat, lon, lev, kx, kt, d, len(lat), NR, table, p1, p2, fw, l2d, l3d=l3d)
+            Gp.norm_into(pout)
+        pstep()
+        c0 = Gp.counters()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            pstep()
+        dtp = (time.perf_counter() - t0) / args.e2e_steps
+        c1 = Gp.counters()
+        ok = bool(int(pout["nobs_3d"].sum()) == expected_total)
+        e2e_pageable = {"value": nobs_total / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": args.e2e_steps,
+                        "h2d_bytes_per_step": (c1["h2d"] - c0["h2d"]) // args.e2e_steps,
+                        "d2h_bytes_per_step": (c1["d2h"] - c0["d2h"]) // args.e2e_steps, "count_check": ok,
+                        "note": "pageable numpy columns + host-built del and ob_flag -> gritas_b200_accum (ob_flag inout, "
+                                "synchronous) per file -> gritas_b200_norm into pageable arrays: the call sequence of "
+                                "fortran/m_gritas_b200.F90 under an untouched gritas.f"}
+        Gp.close()
+        del pfiles, pout
+
+    # ---- weak leg (extra): every rank bins a whole month of its own, one sharded Norm over all of them ----
+    weak = None
+    if world > 1 and not args.no_weak:
+        del dev_files, dev_calls
+        wfiles = gen_files_idx(cfg, [rank * cfg.nfiles + i for i in range(nfiles)])
+        wn = torch.tensor([float(sum(len(c["lat"]) for c in wfiles))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wn)
+        wdev = to_dev(wfiles)
+        del wfiles
+        w = timed_device(calls_of(wdev), max(3, args.steps // 2), 2)
+        weak = {"value": float(wn[0]) / (w["ms"] * 1e-3), "unit": UNIT, "ms_per_step": w["ms"], "accumulate_ms_per_step": w["accum_ms"],
+                "norm_ms_per_step": w["norm_ms"], "note": "weak scaling: every rank bins its own month (N months per step), one sharded Norm"}
+        del wdev
     clocks = sampler.result()
 
-    # ---- roofline of the accumulate path (partition kernels of every file + the tile accumulate) ---------
+    # ---- roofline of the path: K1 of every file + the Norm kernel that accumulates the parked tiles and finalizes ----
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -422,45 +530,61 @@ def run_b200(args):
     nbox = cfg.im * cfg.jm * cfg.km * l3d + cfg.im * cfg.jm * l2d
     B_OBS = b_obs(NR)
     grid_bytes = 8 * (1 + 2 * NR) * nbox                     # the sums, once per pass (SURVEY 8d B_grid)
-    alg_bytes_per_launch = (nobs_rank * B_OBS + grid_bytes) / nfiles
+    # per GPU and launch: this rank's observations + its share of the grid pass (each rank finalizes 1/N of the rows)
+    nf_rank = max(1, len(files))
+    alg_bytes_per_launch = (nobs_total / world * B_OBS + grid_bytes / world) / nf_rank
     staged = L.gritas_b200_tiled(G.handle) == 1
-    # the algorithmic bytes hold the grid once (B_grid), so the duration holds the pass over the grid too: at N=1 the
-    # whole Norm region (tiled path: K2f, the tile accumulate fused with the finalize; direct / deterministic path: K3)
-    path_ms = accum_ms + flush_ms
-    launch_ms = path_ms / nfiles
+    # the algorithmic bytes hold the grid once (B_grid), so the duration holds the pass over the grid too: the whole Norm
+    # region (tiled path: the tile kernel = accumulate of the parked lists fused with the finalize, at N > 1 including the
+    # pull over NVLink and the two barriers; direct / deterministic path: K3)
+    path_ms = accum_ms + norm_ms
+    launch_ms = path_ms / nf_rank
     achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
     traffic = None
-    try:   # DRAM bytes per launch from the committed `ncu --set full` capture of this workload (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic_cfg2.json")))
-        if staged and cfg.name == "cfg2" and nfiles == cfg.nfiles and args.scale == 1.0:
+    try:   # DRAM bytes per launch from this round's `ncu --set full` capture of this workload (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic_cfg2.json")))
+        if staged and world == 1 and cfg.name == "cfg2" and nfiles == cfg.nfiles and args.scale == 1.0:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
+    kern = ("k_list_obs (K1) per file + k_tile_final (tile accumulate fused with finalize"
+            + ("" if world == 1 else ", entries pulled from all ranks over NVLink peer memory") + ") per Norm") if staged else \
+           ("k_accum_fast" if args.mode == "fast" else "k_box_keys + radix sort + k_segment_sum")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
-                "kernel": (("k_list_obs (K1) per file + k_tile_final<finalize> (K2f: tile accumulate fused with finalize) per Norm" if world == 1 else
-                            "k_list_obs (K1) per file + k_tile_final<export> (K2x) per Norm") if staged else
-                           ("k_accum_fast" if args.mode == "fast" else "k_box_keys + radix sort + k_segment_sum")),
+                "traffic": traffic, "kernel": kern,
                 "peak_source": peak_src, "avg_launch_ms": launch_ms, "alg_bytes_per_launch": alg_bytes_per_launch,
-                "note": f"one launch = the accumulate work of one file: {B_OBS} B/obs x obs per file + (8*(1+2*nr)*boxes)/files; "
-                        f"duration = (accumulate region + {'Norm region (K2f: tile accumulate + finalize)' if world == 1 else 'tile flush'}, "
-                        f"CUDA events on the library stream) / {nfiles} files"}
+                "note": f"per GPU; one launch = the accumulate work of one file: {B_OBS} B/obs x obs per file + this rank's share of "
+                        f"(8*(1+2*nr)*boxes) / its files; duration = (accumulate region + the whole Norm region, CUDA events on "
+                        f"the library stream, max over ranks) / {nf_rank} files per rank"}
 
+    per_rank = {1: "N=1: Norm = K2f on the parked tile lists",
+                }.get(world, f"file f -> rank f mod {world}; Norm = {norm_kind}: " +
+                      ("every rank finalizes 1/N of the rows, its tile kernel pulls the parked entries of those rows from all "
+                       "ranks' lists over NVLink (CUDA IPC peer mappings); barriers = two one-element NCCL all-reduces"
+                       if norm_kind == "sharded-peer" else
+                       "K2x (tile sums as compact planes) + ncclReduce to rank 0 + K3x (finalize) pipelined in 8 chunks"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode,
-                       "per_rank": "each rank bins its own month; N=1: Norm = K2f on the parked tile lists; N>1: K2x (tile sums as compact planes) + ncclReduce to rank 0 + K3x (finalize) pipelined in 8 chunks (rank 0 writes the grids, as the reference has one writer)",
-                       "l2": f"inputs ({nobs_rank * b_obs(NR) / 1e9:.1f} GB/step) exceed the 126 MB L2; no flush needed"},
-            "accumulate_ms_per_step": accum_ms, "norm_ms_per_step" if world == 1 else "tile_flush_ms_per_step": flush_ms,
-            "host_enqueue_ms_per_step": host_ms, "count_check": check, "accepted_obs_per_rank": expected_rank, "gpu_launches": int(launches_per_step * args.steps),
-            "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roofline}
+            "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode, "sharding": per_rank,
+                       "l2": f"inputs ({nobs_rank * b_obs(NR) / 1e9:.2f} GB/step per rank) exceed the 126 MB L2; no flush needed"},
+            "accumulate_ms_per_step": accum_ms, "norm_ms_per_step": norm_ms,
+            "spread": {"accumulate_ms": dev["accum_spread"], "norm_ms": dev["norm_spread"], "note": "rank 0, per timed step"},
+            "host_enqueue_ms_per_step": 1e3 * float(np.mean(host_enqueue[-args.steps:])), "count_check": check,
+            "accepted_obs": expected_total, "gpu_launches": int(dev["launches_per_step"] * args.steps),
+            "gpu_launches_per_step": int(dev["launches_per_step"]), "clocks": clocks, "roofline": roofline}
+    if world == 1:
+        line["scaling_note"] = "N=1: one GPU bins the whole month; N>1 lines shard the same month (strong scaling)"
     if e2e:
         line["e2e"] = e2e
+    if e2e_pageable:
+        line["e2e_pageable"] = e2e_pageable
+    if weak:
+        line["weak"] = weak
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): single thread, like gritas.x ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ns = len(files)
+        ns = min(32, len(files))
         v, dt, nobs = time_cpu(cfg, files[:ns], 1, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{ns} of {nfiles} files ({nobs} obs): QC filter + GrITAS_Accum per file, "

@@ -43,7 +43,10 @@ SYMBOLS = [
     "gritas_b200_allreduce", "gritas_b200_norm_reduce", "gritas_b200_norm_reduce_device", "gritas_b200_host_alloc", "gritas_b200_host_free", "gritas_b200_last_error",
     "gritas_b200_stream", "gritas_b200_set_stream", "gritas_b200_tiled", "gritas_b200_fused_norm", "gritas_b200_launch_count", "gritas_b200_h2d_bytes",
     "gritas_b200_d2h_bytes", "gritas_b200_version",
+    "gritas_b200_peer_export", "gritas_b200_peer_attach", "gritas_b200_slab", "gritas_b200_norm_sharded",
+    "gritas_b200_norm_sharded_device", "gritas_b200_host_register", "gritas_b200_host_unregister", "gritas_b200_wait",
 ]
+PEER_BLOB_BYTES = 512
 
 OPT_TCH = 1
 OPT_SELF = 2
@@ -80,6 +83,7 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_accum_ods.argtypes = [_P, _I] + [_P] * 11 + [_I] * 5 + [_D, _D, _I, _I, _P, C.POINTER(_D)]
     L.gritas_b200_accum_odsx.argtypes = [_P, _I, _P] + [_I] * 6 + [_D, _D, _I, _I, _P, C.POINTER(_D)]
     L.gritas_b200_sync.argtypes = [_P, C.POINTER(_D)]
+    L.gritas_b200_wait.argtypes = [_P, C.POINTER(_D)]
     L.gritas_b200_reset.argtypes = [_P]
     L.gritas_b200_flush.argtypes = [_P]
     L.gritas_b200_barrier.argtypes = [_P]
@@ -96,6 +100,13 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_allreduce.argtypes = [_P]
     L.gritas_b200_norm_reduce.argtypes = [_P, _I, _I, _I] + [_P] * 10
     L.gritas_b200_norm_reduce_device.argtypes = [_P, _I, _I, _I, C.POINTER(_P)]
+    L.gritas_b200_peer_export.argtypes = [_P, _P]
+    L.gritas_b200_peer_attach.argtypes = [_P, _I, _I, _P]
+    L.gritas_b200_slab.argtypes = [_P, _I, _I] + [C.POINTER(_I)] * 4
+    L.gritas_b200_norm_sharded.argtypes = [_P, _I, _I] + [_P] * 10
+    L.gritas_b200_norm_sharded_device.argtypes = [_P, _I, _I, C.POINTER(_P)]
+    L.gritas_b200_host_register.argtypes = [_P, C.c_size_t]
+    L.gritas_b200_host_unregister.argtypes = [_P]
     L.gritas_b200_host_alloc.argtypes = [C.c_size_t]
     L.gritas_b200_host_alloc.restype = _P
     L.gritas_b200_host_free.argtypes = [_P]

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <vector>
@@ -145,6 +146,13 @@ struct gritas_b200_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  // sharded Norm over peer memory (gritas_b200_peer_attach): every rank's lists / fill words / records
+  int np = 1, prank = 0;
+  void *peer_lists[MAX_PEERS] = {}, *peer_fill[MAX_PEERS] = {}, *peer_acc[MAX_PEERS] = {};
+  bool peer_ipc[MAX_PEERS] = {};      // pointers of rank s came from cudaIpcOpenMemHandle (close them on destroy)
+  unsigned *fill_snap = nullptr;      // local snapshot of every rank's fill / dirty / records-touched words
+  size_t fill_snap_cap = 0;
+  double *bar_buf = nullptr;          // operand of the stream-ordered barrier (a one-element all-reduce)
   // counters
   uint64_t launches = 0, h2d = 0, d2h = 0;
   char err[512] = {0};
@@ -278,6 +286,15 @@ int mark_main(gritas_b200_handle h) {
   return 0;
 }
 
+// The records are about to receive sums (flush, direct accumulate, add_raw, reduction): they are no longer "all zero
+// apart from dirty tiles".  The device copy of that fact (the word after the dirty words) is what a peer's sharded Norm reads.
+int touch_records(gritas_b200_handle h) {
+  if (!h->acc_fresh) return 0;
+  h->acc_fresh = false;
+  if (h->staging) CU(cudaMemsetAsync(h->sg.fill + 2 * (size_t)h->sg.ntiles, 1, sizeof(unsigned), h->compute));
+  return 0;
+}
+
 // Waits for the compute stream and converts a recorded level miss into the return code.
 int drain(gritas_b200_handle h, double *bad_lev) {
   int jr = join_workers(h);
@@ -353,7 +370,7 @@ void launch_tiles(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sms) 
   const int avail = std::max(h->tf_per_sm, h->tf_ctas - free_sms * h->tf_per_sm);
   const int ctas = (int)std::min((unsigned)avail, t1 - t0);
   k_tile_final<NR, TILE_FLUSH><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, h->compute>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0,
-                                                                                         0, 0, h->acc_fresh ? 1 : 0, t0, t1, nullptr);
+                                                                                         0, 0, h->acc_fresh ? 1 : 0, t0, t1, nullptr, PeerSet{});
 }
 
 void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sms = 0) {
@@ -372,7 +389,7 @@ int flush_stage(gritas_b200_handle h) {
   CU(cudaGetLastError());
   h->launches += 1;
   h->staged_upper = 0;
-  h->acc_fresh = false;
+  if ((jr = touch_records(h))) return jr;
   return mark_main(h);
 }
 
@@ -382,7 +399,7 @@ void launch_tile_final(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &o
                        int raw2, int raw3) {
   k_tile_final<NR, TILE_FINALIZE><<<h->tf_ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3,
                                                                                          nrmlz, ntr, raw2, raw3, h->acc_fresh ? 1 : 0,
-                                                                                         0u, h->sg.ntiles, nullptr);
+                                                                                         0u, h->sg.ntiles, nullptr, PeerSet{});
 }
 
 // Multi-rank Norm on the tiled path: K2x exports the sums of tiles [t0, t1) as compact planes (the reduction operand),
@@ -393,7 +410,7 @@ void launch_tile_export(gritas_b200_handle h, cudaStream_t sm, unsigned t0, unsi
   const OutPlanes none = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
   k_tile_final<NR, TILE_EXPORT><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, none, none, 0, 0, 0, 0,
-                                                                                   h->acc_fresh ? 1 : 0, t0, t1, h->red);
+                                                                                   h->acc_fresh ? 1 : 0, t0, t1, h->red, PeerSet{});
 }
 template <int NR>
 void launch_tile_import(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
@@ -401,7 +418,7 @@ void launch_tile_import(gritas_b200_handle h, cudaStream_t sm, const OutPlanes &
   if (t1 <= t0) return;
   const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
   k_tile_final<NR, TILE_IMPORT><<<ctas, TileFinal<NR>::THREADS, h->tf_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, ntr,
-                                                                                   raw2, raw3, 1, t0, t1, h->red);
+                                                                                   raw2, raw3, 1, t0, t1, h->red, PeerSet{});
 }
 
 bool fused_norm_ok(gritas_b200_handle h) {
@@ -442,6 +459,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
       flag_to_host = true;
     }
   }
+  c.flag_rw = (c.flag && c.flag == c.flag_out) ? 1 : 0;   // device-resident inout ob_flag: read with coherent loads
   c.aligned = aligned16(c.lat) && aligned16(c.lon) && aligned16(c.lev) && aligned16(c.kx) && aligned16(c.kt) &&
               aligned16(c.flag) && aligned16(c.time) && aligned16(c.flag_out);
   for (int ir = 0; ir < h->g.nr; ++ir) c.aligned = c.aligned && aligned16(c.d[ir]);
@@ -487,7 +505,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     }
     h->launches += 1;
   } else if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST) {
-    h->acc_fresh = false;
+    if (int tr = touch_records(h)) return tr;
     const int nvec = (n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
     const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
     switch (h->g.nr) {
@@ -503,7 +521,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
       h->tiled_choice = (pairs > 0 && (double)nearp < 0.5 * (double)pairs) ? 1 : 0;
     }
   } else {
-    h->acc_fresh = false;
+    if (int tr = touch_records(h)) return tr;
     // keys -> stable LSD radix sort of (key, obs index) on a sort stream -> in-order segment sums on `compute`
     gritas_b200_ctx::DetBuf &db = h->det[h->next_det];
     h->next_det ^= 1;
@@ -722,8 +740,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         h->sg.ntiles = (unsigned)ntiles;
         h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffe0);
         h->stage_slots = ntiles * (size_t)h->sg.cap;
-        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * 2 * ntiles));   // tickets + the per-tile dirty words
-        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * 2 * ntiles));
+        CUC(cudaMalloc(&h->sg.fill, sizeof(unsigned) * (2 * ntiles + 4)));   // tickets, the per-tile dirty words, the records-touched word
+        CUC(cudaMemset(h->sg.fill, 0, sizeof(unsigned) * (2 * ntiles + 4)));
         h->sg.dirty = h->sg.fill + ntiles;
         CUC(cudaMalloc(&h->sg.lists, entry * h->stage_slots));
         if (const char *e_w = getenv("GRITAS_B200_WORKERS")) h->nwk = std::max(1, std::min(NWK, atoi(e_w)));
@@ -739,6 +757,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
     CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_EXPORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_IMPORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<NR_, TILE_FINALIZE>, TileFinal<NR_>::THREADS, smem)); \
   } while (0)
         if (nr == 1) TF_SETUP(1);
@@ -790,7 +809,11 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (h->ev_red[c]) cudaEventDestroy(h->ev_red[c]);
   }
   if (h->ev_fin) cudaEventDestroy(h->ev_fin);
-  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red})
+  for (int r = 0; r < MAX_PEERS; ++r)
+    if (h->peer_ipc[r])
+      for (void *p : {h->peer_lists[r], h->peer_fill[r], h->peer_acc[r]})
+        if (p) cudaIpcCloseMemHandle(p);
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red, (void *)h->fill_snap, (void *)h->bar_buf})
     if (p) cudaFree(p);
   for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1]})
     if (p) cudaFree(p);
@@ -1000,6 +1023,12 @@ int gritas_b200_sync(gritas_b200_handle h, double *bad_lev) {
   return drain(h, bad_lev);
 }
 
+int gritas_b200_wait(gritas_b200_handle h, double *bad_lev) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  return settle(h, true, bad_lev);
+}
+
 int gritas_b200_flush(gritas_b200_handle h) {
   int rc = check_handle(h);
   if (rc) return rc;
@@ -1021,7 +1050,7 @@ int gritas_b200_reset(gritas_b200_handle h) {
   }
   h->acc_fresh = true;
   if (h->staging) {
-    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * 2 * h->sg.ntiles, h->compute));   // tickets and the dirty words
+    CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * (2 * (size_t)h->sg.ntiles + 4), h->compute));   // tickets, dirty words, records-touched word
     h->staged_upper = 0;
   }
   return mark_main(h);
@@ -1035,16 +1064,16 @@ int gritas_b200_barrier(gritas_b200_handle h) {
 
 // K3 launches for 3-D rows [jl0, jl1) (jl = j + jm*l) and, if with2d, the surface boxes, on stream `sm`.
 static int launch_finalize(gritas_b200_handle h, cudaStream_t sm, double *const dst[10], int raw, bool raw3, int xpl, int nrmlz,
-                           int ntr, int jl0, int jl1, bool with2d) {
+                           int ntr, int jl0, int jl1, bool with2d, size_t b2_0 = 0, size_t b2_1 = 0) {
   const GridDesc &g = h->g;
   const int nr = g.nr;
   const size_t n2 = g.nbox2;
   if (n2 && with2d) {
     OutPlanes o = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
     const int nb = grid_for(n2, 256, 8);
-    if (nr == 1) k_finalize2<1><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw);
-    else if (nr == 2) k_finalize2<2><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw);
-    else k_finalize2<3><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw);
+    if (nr == 1) k_finalize2<1><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw, b2_0, b2_1 ? b2_1 : n2);
+    else if (nr == 2) k_finalize2<2><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw, b2_0, b2_1 ? b2_1 : n2);
+    else k_finalize2<3><<<nb, 256, 0, sm>>>(g, o, nrmlz, ntr, raw, b2_0, b2_1 ? b2_1 : n2);
     h->launches++;
   }
   if (g.nbox3 && jl1 > jl0) {
@@ -1226,7 +1255,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     }
     CU(cudaGetLastError());
     h->staged_upper = 0;
-    h->acc_fresh = false;
+    if ((rc = touch_records(h))) return rc;
     CU(cudaEventRecord(h->ev_fin, writer ? h->fin_stream : h->comm_stream));
     CU(cudaStreamWaitEvent(h->compute, h->ev_fin, 0));
     if ((rc = mark_main(h))) return rc;
@@ -1361,7 +1390,7 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
   if (rc) return rc;
   if ((rc = flush_stage(h))) return rc;
   if ((rc = join_workers(h))) return rc;
-  h->acc_fresh = false;
+  if ((rc = touch_records(h))) return rc;
   const GridDesc &g = h->g;
   const int nr = g.nr;
   const size_t n2 = g.nbox2, n3 = g.nbox3;
@@ -1526,9 +1555,316 @@ int gritas_b200_allreduce(gritas_b200_handle h) {
   if (h->minmax) return fail(h, GRITAS_B200_ERR_ARG, "MinMax handles are not summed across ranks");
   CU(cudaStreamSynchronize(h->copy));
   if ((rc = flush_stage(h))) return rc;
-  h->acc_fresh = false;
+  if ((rc = join_workers(h))) return rc;      // flush_stage returns early when nothing is parked: K1 launches may still be queued
+  if ((rc = touch_records(h))) return rc;
   int e = g_nccl.AllReduce(h->g.acc, h->g.acc, h->nrec * h->g.rs, NCCL_FLOAT64, NCCL_SUM, h->comm, h->compute);
   if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  return mark_main(h);                        // later K1 launches (direct RED on a full list) must not overlap the in-place reduction
+}
+
+// ---- sharded multi-rank Norm over peer memory --------------------------------------------------------
+// The month is sharded f mod nranks (gritas.f:389-393 is the file loop each rank runs on its share); every rank parks
+// its accepted observations in its own tile lists.  GrITAS_Norm (gritas.f:885-887) then needs the sums over all ranks.
+// Instead of reducing the sum grids (1.3 GB at cfg2 whatever the rank count) rank r takes 1/nranks of the rows and its
+// tile kernel pulls the parked entries of those tiles from every rank's lists through NVLink peer mappings
+// (3.9 GB / nranks per rank), finalizes them and writes its slab of the output arrays.  No collective on the data path;
+// the two stream-ordered barriers are one-element all-reduces.
+namespace {
+
+struct PeerBlob {
+  uint64_t magic;
+  int32_t pid, device, staging, nr, tile_shift, mode;
+  uint32_t ntiles, cap;
+  uint64_t nrec;
+  uint64_t raw_lists, raw_fill, raw_acc;
+  int32_t ipc_ok, pad;
+  cudaIpcMemHandle_t ipc_lists, ipc_fill, ipc_acc;
+  char host[64];
+};
+static_assert(sizeof(PeerBlob) <= GRITAS_B200_PEER_BLOB_BYTES, "PeerBlob must fit the ABI blob");
+constexpr uint64_t PEER_MAGIC = 0x6772697461733262ull;
+
+struct Slab {
+  size_t lo, hi;                    // records [lo, hi)
+  int jl3_0, jl3_1, jl2_0, jl2_1;   // rows jl = j + jm*l of the 3-D / 2-D grids
+};
+
+// Rows are never split: the slab of rank r starts at the row boundary at or below nrec * r / n.
+size_t slab_bound(const GridDesc &g, size_t nrec, int r, int n) {
+  if (r <= 0) return 0;
+  if (r >= n) return nrec;
+  const size_t x = nrec * (size_t)r / (size_t)n;
+  const size_t row3 = (size_t)g.im * g.km;
+  if (x <= (size_t)g.nbox3) return x / row3 * row3;
+  return (size_t)g.nbox3 + (x - g.nbox3) / g.im * g.im;
+}
+
+Slab slab_of(const GridDesc &g, size_t nrec, int r, int n) {
+  Slab s;
+  s.lo = slab_bound(g, nrec, r, n);
+  s.hi = slab_bound(g, nrec, r + 1, n);
+  const size_t row3 = (size_t)g.im * g.km, n3 = g.nbox3;
+  s.jl3_0 = (int)(std::min(s.lo, n3) / row3);
+  s.jl3_1 = (int)(std::min(s.hi, n3) / row3);
+  s.jl2_0 = (int)((std::max(s.lo, n3) - n3) / g.im);
+  s.jl2_1 = (int)((std::max(s.hi, n3) - n3) / g.im);
+  return s;
+}
+
+// Every rank has queued everything before this point of its compute stream (stream-ordered; no host wait).
+int stream_barrier(gritas_b200_handle h) {
+  if (!h->comm || h->nranks < 2) return 0;
+  if (!h->bar_buf) {
+    CU(cudaMalloc(&h->bar_buf, 64));
+    CU(cudaMemsetAsync(h->bar_buf, 0, 64, h->compute));
+  }
+  int e = g_nccl.AllReduce(h->bar_buf, h->bar_buf, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->compute);
+  if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclAllReduce (barrier): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  return 0;
+}
+
+// Device -> host (or in place) copy of this rank's slab of reference-layout array `a` (see finalize_to for the order).
+int copy_slab(gritas_b200_handle h, const Slab &sl, int a, int planes, double *user, const double *dev) {
+  const GridDesc &g = h->g;
+  const bool is3 = a >= 5;
+  if (a == 4 || a == 9) planes = 1;
+  if (is3) {
+    const size_t pitch = sizeof(double) * (size_t)g.im * g.jm;
+    for (int ir = 0; ir < planes; ++ir)
+      for (int l = sl.jl3_0 / g.jm; l <= (sl.jl3_1 - 1) / g.jm && sl.jl3_1 > sl.jl3_0; ++l) {
+        const int ja = std::max(sl.jl3_0, l * g.jm) - l * g.jm, jb = std::min(sl.jl3_1, (l + 1) * g.jm) - l * g.jm;
+        if (jb <= ja) continue;
+        const size_t off = (size_t)g.im * ((size_t)ja + (size_t)g.jm * ((size_t)g.km * ((size_t)l + (size_t)g.l3d * ir)));
+        const size_t width = sizeof(double) * (size_t)g.im * (size_t)(jb - ja);
+        CU(cudaMemcpy2DAsync(user + off, pitch, dev + off, pitch, width, (size_t)g.km, cudaMemcpyDeviceToHost, h->compute));
+        h->d2h += width * g.km;
+      }
+  } else {
+    for (int ir = 0; ir < planes; ++ir) {
+      if (sl.jl2_1 <= sl.jl2_0) continue;
+      const size_t off = (size_t)g.im * (size_t)sl.jl2_0 + (size_t)g.nbox2 * ir;
+      const size_t bytes = sizeof(double) * (size_t)g.im * (size_t)(sl.jl2_1 - sl.jl2_0);
+      CU(cudaMemcpyAsync(user + off, dev + off, bytes, cudaMemcpyDeviceToHost, h->compute));
+      h->d2h += bytes;
+    }
+  }
+  return 0;
+}
+
+int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const user[10], const double **dev_out) {
+  const GridDesc &g = h->g;
+  const int nr = g.nr;
+  if (nr > 2) return fail(h, GRITAS_B200_ERR_NR, "Accum: could not handle more then 2 residuals");  // :555
+  if (h->minmax) return fail(h, GRITAS_B200_ERR_ARG, "Norm on a MinMax handle");
+  const size_t n2 = g.nbox2, n3 = g.nbox3;
+  const int xpl = nr;
+  const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
+  const bool raw3 = g.nlevs < 2;   // m_gritas_grids.f:607: the 3-D sums stay raw
+  const Slab sl = slab_of(g, h->nrec, h->prank, h->np);
+  double *dst[10];
+  bool bounce[10];
+  size_t need = 0;
+  for (int a = 0; a < 10; ++a) {
+    bounce[a] = false;
+    dst[a] = nullptr;
+    if ((!user[a] && !dev_out) || sz[a] == 0 || (raw3 && a == 7)) continue;
+    if (!dev_out && mem_kind(user[a]) == 2) dst[a] = user[a];
+    else { bounce[a] = true; need += sz[a]; }
+  }
+  int rc;
+  if (need) {
+    if ((rc = grow_dev(h, (void **)&h->out, &h->out_cap, sizeof(double) * need))) return rc;
+    size_t off = 0;
+    for (int a = 0; a < 10; ++a)
+      if (bounce[a]) { dst[a] = h->out + off; off += sz[a]; }
+  }
+  const int ntr = ntresh < 0 ? 0 : ntresh;
+  if ((rc = join_workers(h))) return rc;
+  if ((rc = stream_barrier(h))) return rc;            // every rank's accumulate work is complete
+  PeerSet ps = {};
+  ps.n = h->np;
+  ps.own_lo = (unsigned)sl.lo;
+  ps.own_hi = (unsigned)sl.hi;
+  for (int s = 0; s < h->np; ++s) {
+    ps.lists[s] = (const unsigned char *)h->peer_lists[s];
+    ps.fill[s] = (const unsigned *)h->peer_fill[s];
+    ps.acc[s] = (const double *)h->peer_acc[s];
+  }
+  if (h->staging) {
+    const unsigned nwords = 2u * h->sg.ntiles + 4u;
+    if ((rc = grow_dev(h, (void **)&h->fill_snap, &h->fill_snap_cap, sizeof(unsigned) * (size_t)nwords * h->np))) return rc;
+    k_gather_words<<<148, 256, 0, h->compute>>>(h->fill_snap, ps, nwords);
+    for (int s = 0; s < h->np; ++s) ps.fill[s] = h->fill_snap + (size_t)s * nwords;
+    const OutPlanes o2 = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
+    const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], raw3 ? 1 : xpl};
+    const int r3 = raw3 ? 1 : 0;
+    const unsigned T = 1u << h->sg.tile_shift;
+    const unsigned t0 = (unsigned)(sl.lo >> h->sg.tile_shift), t1 = (unsigned)((sl.hi + T - 1) >> h->sg.tile_shift);
+    if (t1 > t0) {
+      const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
+#define PEER_LAUNCH(NR_)                                                                                                      \
+  k_tile_final<NR_, TILE_PEERS><<<ctas, TileFinal<NR_>::THREADS, h->tf_smem, h->compute>>>(g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, \
+                                                                                          ntr, 0, r3, 0, t0, t1, nullptr, ps)
+      if (nr == 1) PEER_LAUNCH(1);
+      else PEER_LAUNCH(2);
+#undef PEER_LAUNCH
+    }
+    h->launches += 2;
+    CU(cudaGetLastError());
+  } else {
+    // no lists on this path (deterministic mode, GRITAS_B200_FLAG_NO_STAGING): the records of this rank's rows are summed
+    // over the ranks in rank order, then finalized by K3.  One-shot: this rank's records then hold the total of its rows.
+    const size_t d0 = sl.lo * (size_t)g.rs, d1 = sl.hi * (size_t)g.rs;
+    if (d1 > d0) {
+      k_sum_peer_records<<<grid_for((d1 - d0), 256, 8), 256, 0, h->compute>>>(g.acc, ps, h->prank, d0, d1);
+      h->launches += 1;
+    }
+    if ((rc = touch_records(h))) return rc;
+    const size_t b0 = (std::max(sl.lo, n3) - n3), b1 = (std::max(sl.hi, n3) - n3);
+    if ((rc = launch_finalize(h, h->compute, dst, 0, raw3, xpl, nrmlz, ntr, sl.jl3_0, sl.jl3_1, b1 > b0, b0, b1))) return rc;
+  }
+  if ((rc = stream_barrier(h))) return rc;            // every rank has read what it needs from this rank
+  if ((rc = mark_main(h))) return rc;
+  for (int a = 0; a < 10; ++a) {
+    if (dev_out) dev_out[a] = dst[a];
+    else if (bounce[a] && (rc = copy_slab(h, sl, a, (a == 3 || a == 8) ? ((a == 8 && raw3) ? 1 : xpl) : nr, user[a], dst[a]))) return rc;
+  }
+  return drain(h, nullptr);
+}
+
+}  // namespace
+
+int gritas_b200_peer_export(gritas_b200_handle h, void *blob) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!blob) return fail(h, GRITAS_B200_ERR_ARG, "null blob");
+  PeerBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = PEER_MAGIC;
+  b.pid = (int32_t)getpid();
+  b.device = h->device;
+  b.staging = h->staging ? 1 : 0;
+  b.nr = h->g.nr;
+  b.tile_shift = h->staging ? h->sg.tile_shift : 0;
+  b.mode = h->mode;
+  b.ntiles = h->staging ? h->sg.ntiles : 0;
+  b.cap = h->staging ? h->sg.cap : 0;
+  b.nrec = h->nrec;
+  b.raw_lists = (uint64_t)(uintptr_t)h->sg.lists;
+  b.raw_fill = (uint64_t)(uintptr_t)h->sg.fill;
+  b.raw_acc = (uint64_t)(uintptr_t)h->g.acc;
+  gethostname(b.host, sizeof(b.host) - 1);
+  b.ipc_ok = 1;
+  if (cudaIpcGetMemHandle(&b.ipc_acc, h->g.acc) != cudaSuccess) b.ipc_ok = 0;
+  if (h->staging && (cudaIpcGetMemHandle(&b.ipc_lists, h->sg.lists) != cudaSuccess ||
+                     cudaIpcGetMemHandle(&b.ipc_fill, h->sg.fill) != cudaSuccess))
+    b.ipc_ok = 0;
+  cudaGetLastError();
+  memset(blob, 0, GRITAS_B200_PEER_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int gritas_b200_peer_attach(gritas_b200_handle h, int nranks, int rank, const void *blobs) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (nranks < 1 || nranks > MAX_PEERS || rank < 0 || rank >= nranks || !blobs)
+    return fail(h, GRITAS_B200_ERR_ARG, "peer_attach: 1 <= nranks <= %d, 0 <= rank < nranks", MAX_PEERS);
+  if (h->np > 1) return fail(h, GRITAS_B200_ERR_ARG, "peer_attach: already attached");
+  if (h->comm && h->nranks != nranks) return fail(h, GRITAS_B200_ERR_ARG, "peer_attach: nranks differs from comm_init");
+  PeerBlob b[MAX_PEERS];
+  for (int s = 0; s < nranks; ++s) {
+    memcpy(&b[s], (const char *)blobs + (size_t)s * GRITAS_B200_PEER_BLOB_BYTES, sizeof(PeerBlob));
+    if (b[s].magic != PEER_MAGIC) return fail(h, GRITAS_B200_ERR_ARG, "peer_attach: blob %d is not a peer_export blob", s);
+    // what decides the shape of the exchange must be the same everywhere (every rank sees every blob: all fail alike)
+    if (b[s].staging != b[0].staging || b[s].nr != b[0].nr || b[s].tile_shift != b[0].tile_shift || b[s].ntiles != b[0].ntiles ||
+        b[s].cap != b[0].cap || b[s].nrec != b[0].nrec || (b[s].mode & 0xff) != (b[0].mode & 0xff))
+      return fail(h, GRITAS_B200_ERR_ARG,
+                  "peer_attach: rank %d differs from rank 0 (tiled %d/%d, nr %d/%d, tile_shift %d/%d, ntiles %u/%u, cap %u/%u, "
+                  "nrec %llu/%llu): same grid, mode and GRITAS_B200_* settings on every rank (GRITAS_B200_STAGE_SLOTS pins cap)",
+                  s, b[s].staging, b[0].staging, b[s].nr, b[0].nr, b[s].tile_shift, b[0].tile_shift, b[s].ntiles, b[0].ntiles,
+                  b[s].cap, b[0].cap, (unsigned long long)b[s].nrec, (unsigned long long)b[0].nrec);
+  }
+  if ((uint64_t)(uintptr_t)h->g.acc != b[rank].raw_acc || b[rank].pid != (int32_t)getpid())
+    return fail(h, GRITAS_B200_ERR_ARG, "peer_attach: blob %d is not this handle's", rank);
+  for (int s = 0; s < nranks; ++s) {
+    if (s == rank || b[s].pid == (int32_t)getpid()) {
+      // same process (several handles driven by one host thread, or this rank itself): plain pointers
+      if (b[s].device != h->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(b[s].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(h, GRITAS_B200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", b[s].device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      h->peer_lists[s] = (void *)(uintptr_t)b[s].raw_lists;
+      h->peer_fill[s] = (void *)(uintptr_t)b[s].raw_fill;
+      h->peer_acc[s] = (void *)(uintptr_t)b[s].raw_acc;
+      continue;
+    }
+    if (strncmp(b[s].host, b[rank].host, sizeof(b[s].host)) != 0)
+      return fail(h, GRITAS_B200_ERR_ARG, "peer_attach: rank %d runs on host %s, this rank on %s (peer memory is one node)", s, b[s].host,
+                  b[rank].host);
+    if (!b[s].ipc_ok) return fail(h, GRITAS_B200_ERR_CUDA, "peer_attach: rank %d could not export CUDA IPC handles", s);
+    CU(cudaIpcOpenMemHandle(&h->peer_acc[s], b[s].ipc_acc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_ipc[s] = true;
+    if (b[s].staging) {
+      CU(cudaIpcOpenMemHandle(&h->peer_lists[s], b[s].ipc_lists, cudaIpcMemLazyEnablePeerAccess));
+      CU(cudaIpcOpenMemHandle(&h->peer_fill[s], b[s].ipc_fill, cudaIpcMemLazyEnablePeerAccess));
+    }
+  }
+  h->np = nranks;
+  h->prank = rank;
+  return 0;
+}
+
+int gritas_b200_slab(gritas_b200_handle h, int rank, int nranks, int *jl3_0, int *jl3_1, int *jl2_0, int *jl2_1) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return GRITAS_B200_ERR_ARG;
+  const Slab s = slab_of(h->g, h->nrec, rank, nranks);
+  if (jl3_0) *jl3_0 = s.jl3_0;
+  if (jl3_1) *jl3_1 = s.jl3_1;
+  if (jl2_0) *jl2_0 = s.jl2_0;
+  if (jl2_1) *jl2_1 = s.jl2_1;
+  return 0;
+}
+
+int gritas_b200_norm_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d, double *stdv_2d,
+                             double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *stdv_3d,
+                             double *xcov_3d, double *nobs_3d) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->copy));
+  double *const u[10] = {bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d};
+  if (h->np < 2) {
+    if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
+    return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, nullptr);
+  }
+  return finalize_sharded(h, nrmlz ? 1 : 0, ntresh, u, nullptr);
+}
+
+int gritas_b200_norm_sharded_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **outs10) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!outs10) return fail(h, GRITAS_B200_ERR_ARG, "null outs");
+  CU(cudaStreamSynchronize(h->copy));
+  double *const u[10] = {};
+  if (h->np < 2) {
+    if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
+    return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10);
+  }
+  return finalize_sharded(h, nrmlz ? 1 : 0, ntresh, u, outs10);
+}
+
+int gritas_b200_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return GRITAS_B200_ERR_ARG;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) { cudaGetLastError(); return GRITAS_B200_ERR_CUDA; }
+  return 0;
+}
+
+int gritas_b200_host_unregister(void *p) {
+  if (!p) return GRITAS_B200_ERR_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return GRITAS_B200_ERR_CUDA; }
   return 0;
 }
 

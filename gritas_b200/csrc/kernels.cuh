@@ -73,6 +73,7 @@ struct ObsCols {
   int *flag_out;             // may be null
   int n;
   int aligned;               // every non-null column pointer is 16-byte aligned
+  int flag_rw;               // flag and flag_out are the same array (GrITAS_Accum's inout ob_flag): no non-coherent loads
 };
 
 struct FilterDesc {
@@ -96,6 +97,18 @@ struct StageDesc {
   int tile_shift;
   unsigned *dirty;       // [ntiles] set when an entry of the tile was accumulated directly (list overflow): the tile's
                          // records are no longer all zero
+};
+
+// Sharded multi-rank Norm: rank r finalizes the records [own_lo, own_hi) and pulls the parked
+// entries of those tiles from every rank's lists over NVLink peer memory (CUDA IPC mappings of the peers' buffers) --
+// the exchange step of the path fused into the tile kernel instead of a collective on the sum grids.
+constexpr int MAX_PEERS = 8;
+struct PeerSet {
+  int n;                                  // ranks (sources); lists[self] is this rank's own buffer
+  unsigned own_lo, own_hi;                // records this rank finalizes
+  const unsigned char *lists[MAX_PEERS];  // every rank's tile lists (same ntiles / cap / tile_shift on all ranks)
+  const unsigned *fill[MAX_PEERS];        // local snapshot of every rank's [tickets | dirty words | records-touched word]
+  const double *acc[MAX_PEERS];           // every rank's records (read only where a rank accumulated directly)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -311,6 +324,17 @@ __device__ __forceinline__ int4 ldg_stream4(const int *p) {
                : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
+// same for a column the kernel also writes (ob_flag inout): ld.global.nc would be undefined there
+__device__ __forceinline__ int4 ldg_rw4(const int *p) {
+  int4 r;
+  asm volatile("ld.global.cs.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ int ld_rw(const int *p) {
+  int r;
+  asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
 template <int NR>
 struct Obs4 {
   double lat[4], lon[4], lev[4], d[NR][4];
@@ -331,7 +355,7 @@ __device__ __forceinline__ void load_geo4_slow(const ObsCols &c, const FilterDes
     o.lev[j] = in ? __ldg(c.lev + ii) : 0.0;
     o.kx[j] = in ? __ldg(c.kx + ii) : 0;
     o.kt[j] = in ? __ldg(c.kt + ii) : 0;
-    o.fl[j] = (in && c.flag) ? __ldg(c.flag + ii) : 0;
+    o.fl[j] = (in && c.flag) ? (c.flag_rw ? ld_rw(c.flag + ii) : __ldg(c.flag + ii)) : 0;
     o.tm[j] = (in && f.use_time) ? __ldg(c.time + ii) : 0;
   }
 }
@@ -352,7 +376,7 @@ __device__ __forceinline__ void load_geo4(const ObsCols &c, const FilterDesc &f,
     v = ldg_stream4(c.kt + base);
     o.kt[0] = v.x; o.kt[1] = v.y; o.kt[2] = v.z; o.kt[3] = v.w;
     if (c.flag) {
-      v = ldg_stream4(c.flag + base);
+      v = c.flag_rw ? ldg_rw4(c.flag + base) : ldg_stream4(c.flag + base);
       o.fl[0] = v.x; o.fl[1] = v.y; o.fl[2] = v.z; o.fl[3] = v.w;
     } else {
       o.fl[0] = o.fl[1] = o.fl[2] = o.fl[3] = 0;
@@ -708,7 +732,7 @@ k_box_keys(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
   extern __shared__ double s_p2[];
   const LevTab p2s = load_p2(g, s_p2);
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < c.n; n += gridDim.x * blockDim.x) {
-    const int fl = c.flag ? __ldg(c.flag + n) : 0;
+    const int fl = c.flag ? (c.flag_rw ? ld_rw(c.flag + n) : __ldg(c.flag + n)) : 0;
     const int tm = f.use_time ? __ldg(c.time + n) : 0;
     int fa;
     const unsigned key = classify(g, f, p2s, __ldg(c.lat + n), __ldg(c.lon + n), __ldg(c.lev + n), __ldg(c.kx + n),
@@ -1072,9 +1096,9 @@ k_finalize3(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw, int
 // 2-D: one thread per surface box, no transpose needed.
 template <int NR>
 __global__ void __launch_bounds__(256)
-k_finalize2(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw) {
+k_finalize2(const GridDesc g, OutPlanes out, int nrmlz, int ntresh, int raw, size_t b0, size_t b1) {
   const size_t nb = g.nbox2;
-  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+  for (size_t b = b0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += (size_t)gridDim.x * blockDim.x) {
     const double *rec = g.acc + ((size_t)g.nbox3 + b) * g.rs;
     double r[8];
 #pragma unroll
@@ -1153,13 +1177,18 @@ constexpr int TILE_FLUSH = 1;      // K2t: add to the HBM records, empty the lis
 constexpr int TILE_EXPORT = 2;     // K2x: write {n, sums} (+ the tile's records, if any) as compact planes: the operand of the
                                    //      reduction across ranks -- 8*(1+NV) bytes per box instead of a 64-byte record
 constexpr int TILE_IMPORT = 3;     // K3x: no list; the planes come from the reduced buffer, then the statistics as K2f
+constexpr int TILE_PEERS = 4;      // K2p: K2f of a sharded multi-rank Norm -- the tile's entries are pulled from the lists of
+                                   //      every rank (peer memory over NVLink), only the boxes this rank owns are finalized
 
 #pragma nv_diag_suppress 186   // TILE_IMPORT instantiates the list loop with n = 0: 'pointless comparison' is the point
 template <int NR, int MODE>
 __global__ void __launch_bounds__(TileFinal<NR>::THREADS, 2)
 k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh,
-             int raw2, int raw3, int fresh, unsigned tile0, unsigned tile1, double *__restrict__ red) {
+             int raw2, int raw3, int fresh, unsigned tile0, unsigned tile1, double *__restrict__ red, const PeerSet peers) {
   constexpr bool FLUSH = MODE == TILE_FLUSH;
+  constexpr bool PEER = MODE == TILE_PEERS;
+  __shared__ unsigned s_off[MAX_PEERS + 1];                // PEER: start of every rank's entries in the tile's virtual list
+  __shared__ unsigned s_recmask;                           // PEER: ranks whose records hold part of this tile
   using TF = TileFinal<NR>;
   constexpr int NV = TF::NV, EPT = TF::EPT, CH = TF::CH, NTH = TF::THREADS;
   extern __shared__ __align__(16) double s_dyn[];
@@ -1173,10 +1202,27 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
   const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
-    const unsigned n = (MODE == TILE_IMPORT) ? 0u : min(sg.fill[tile], sg.cap);
+    if (PEER) {
+      // the tile's list is the concatenation of every rank's list of this tile (a chunk of the counting sort may span
+      // ranks: eight short lists cost one pass over the boxes, not eight)
+      if (tid == 0u) {
+        unsigned tot = 0u, mask = 0u;
+        for (int s = 0; s < peers.n; ++s) {
+          const unsigned *f = peers.fill[s];
+          s_off[s] = tot;
+          tot += min(f[tile], sg.cap);
+          if (f[2u * sg.ntiles] != 0u || f[sg.ntiles + tile] != 0u) mask |= 1u << s;
+        }
+        s_off[peers.n] = tot;
+        s_recmask = mask;
+      }
+      __syncthreads();
+    }
+    const unsigned n = (MODE == TILE_IMPORT) ? 0u : (PEER ? s_off[peers.n] : min(sg.fill[tile], sg.cap));
     if (FLUSH && n == 0u) continue;                       // uniform across the CTA
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
-    const bool addrec = (MODE != TILE_IMPORT) && (!fresh || sg.dirty[tile] != 0u);
+    const unsigned recmask = PEER ? s_recmask : 0u;
+    const bool addrec = PEER ? (recmask != 0u) : ((MODE != TILE_IMPORT) && (!fresh || sg.dirty[tile] != 0u));
     // compact planes of this tile in the reduction buffer: [1 + NV][T] doubles, the counts first
     double *rplanes = (MODE == TILE_EXPORT || MODE == TILE_IMPORT) ? red + (size_t)tile * (size_t)(1 + NV) * T : nullptr;
     double *s_nd = s_stage;                                 // TILE_IMPORT: [T] counts as doubles (the staging area is idle)
@@ -1200,7 +1246,15 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
         pk[u] = KEY_NONE;
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) d[u][ir] = 0.0;
-        if ((unsigned)u < live_u && e < n) pk[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, e), d[u]) & (T - 1u);
+        if ((unsigned)u < live_u && e < n) {
+          if (PEER) {
+            int src = 0;
+            while (src + 1 < peers.n && e >= s_off[src + 1]) ++src;
+            pk[u] = entry_load<NR>(peers.lists[src], list_slot(sg, tile, e - s_off[src]), d[u]) & (T - 1u);
+          } else {
+            pk[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, e), d[u]) & (T - 1u);
+          }
+        }
       }
 #pragma unroll
       for (int u = 0; u < EPT; ++u)
@@ -1356,13 +1410,17 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
 #pragma unroll
         for (int q = 0; q < NV; ++q) r[1 + q] = s_val[(size_t)q * T + b];
         if (addrec) {
-          const double *rec = g.acc + (first + b) * (size_t)g.rs;
-          const double2 a0 = *reinterpret_cast<const double2 *>(rec), a1 = *reinterpret_cast<const double2 *>(rec + 2);
-          r[0] = __dadd_rn(a0.x, r[0]); r[1] = __dadd_rn(a0.y, r[1]); r[2] = __dadd_rn(a1.x, r[2]);
-          if (NR > 1) {
-            const double2 a2 = *reinterpret_cast<const double2 *>(rec + 4), a3 = *reinterpret_cast<const double2 *>(rec + 6);
-            r[3] = __dadd_rn(a1.y, r[3]); r[4] = __dadd_rn(a2.x, r[4]); r[5] = __dadd_rn(a2.y, r[5]);
-            if (NR > 2) r[6] = __dadd_rn(a3.x, r[6]);
+          // PEER: the records of every rank that accumulated part of this tile directly, in rank order
+          for (int src = 0; src < (PEER ? peers.n : 1); ++src) {
+            if (PEER && !(recmask & (1u << src))) continue;
+            const double *rec = (PEER ? peers.acc[src] : g.acc) + (first + b) * (size_t)g.rs;
+            const double2 a0 = *reinterpret_cast<const double2 *>(rec), a1 = *reinterpret_cast<const double2 *>(rec + 2);
+            r[0] = __dadd_rn(a0.x, r[0]); r[1] = __dadd_rn(a0.y, r[1]); r[2] = __dadd_rn(a1.x, r[2]);
+            if (NR > 1) {
+              const double2 a2 = *reinterpret_cast<const double2 *>(rec + 4), a3 = *reinterpret_cast<const double2 *>(rec + 6);
+              r[3] = __dadd_rn(a1.y, r[3]); r[4] = __dadd_rn(a2.x, r[4]); r[5] = __dadd_rn(a2.y, r[5]);
+              if (NR > 2) r[6] = __dadd_rn(a3.x, r[6]);
+            }
           }
         }
       }
@@ -1411,6 +1469,10 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
           ci = ncol - 1u;
         }
         const unsigned rel = ci * km + k;
+        if (PEER) {                                           // a tile straddling the slab boundary: the neighbour rank has the rest
+          const size_t recno = first + (rel - head);
+          if (recno < peers.own_lo || recno >= peers.own_hi) continue;
+        }
         const unsigned col = (unsigned)c0 + ci;               // < nbox3 / km: 32 bits
         const unsigned jl = (unsigned)(((double)col + 0.5) * g.rim), i = col - jl * (unsigned)g.im;
         const unsigned l = (unsigned)(((double)jl + 0.5) * g.rjm), j = jl - l * (unsigned)g.jm;
@@ -1418,8 +1480,10 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
         box(rel - head, true, (int)k >= g.nlevs, raw3, o3, o, plane3);   // levels nlevs..km-1: never touched, zeros
       }
     }
-    for (size_t rec = max(first, plane3) + tid; rec < first + nb; rec += NTH)
+    for (size_t rec = max(first, plane3) + tid; rec < first + nb; rec += NTH) {
+      if (PEER && (rec < peers.own_lo || rec >= peers.own_hi)) continue;
       box((unsigned)(rec - first), false, false, raw2, o2, rec - plane3, plane2);
+    }
     __syncthreads();
   }
 }
@@ -1462,6 +1526,26 @@ k_zero_dirty_tiles(double *__restrict__ acc, size_t ndouble, int rs, const Stage
     const size_t n = min(((size_t)1 << sg.tile_shift) * (size_t)rs, ndouble - first);
     double2 *a2 = reinterpret_cast<double2 *>(acc + first);
     for (size_t e = threadIdx.x; e < (n >> 1); e += blockDim.x) a2[e] = make_double2(0.0, 0.0);
+  }
+}
+
+// Sharded Norm: local snapshot of every rank's [tickets | dirty | records-touched] words (one launch instead of a
+// peer copy per rank; the tile kernel then reads them from local memory).
+__global__ void __launch_bounds__(256)
+k_gather_words(unsigned *__restrict__ dst, const PeerSet src, unsigned nwords) {
+  for (int s = 0; s < src.n; ++s)
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < nwords; e += gridDim.x * blockDim.x)
+      dst[(size_t)s * nwords + e] = src.fill[s][e];
+}
+
+// Sharded Norm on the direct / deterministic path (no lists): the records of rows this rank owns are summed over the
+// ranks in rank order (reproducible) into this rank's records; K3 then finalizes them.  One-shot, like the reduction it replaces.
+__global__ void __launch_bounds__(256)
+k_sum_peer_records(double *__restrict__ acc, const PeerSet peers, int self, size_t d0, size_t d1) {
+  for (size_t e = d0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < d1; e += (size_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int s = 0; s < peers.n; ++s) v = __dadd_rn(v, (s == self ? acc : peers.acc[s])[e]);
+    acc[e] = v;
   }
 }
 

@@ -196,6 +196,12 @@ class Grids:
         bad = C.c_double(0.0)
         self._check(cabi.load().gritas_b200_sync(self._h, C.byref(bad)), bad)
 
+    def sync_no_flush(self):
+        """Waits for every queued accumulate kernel without touching the tile lists (before a sharded Norm driven from
+        one process: the lists of all handles must be complete before any handle pulls from them)."""
+        bad = C.c_double(0.0)
+        self._check(cabi.load().gritas_b200_wait(self._h, C.byref(bad)), bad)
+
     def barrier(self):
         self._check(cabi.load().gritas_b200_barrier(self._h))
 
@@ -315,6 +321,37 @@ class Grids:
         p = lambda k, on: cabi.ptr(g[k], np.float64) if on else None
         rc = cabi.load().gritas_b200_norm_reduce(
             self._h, root, 1 if nrmlz else 0, -1 if ntresh is None else int(ntresh),
+            p("bias_2d", self.l2d), p("rtms_2d", self.l2d), p("stdv_2d", self.l2d), p("xcov_2d", self.l2d), p("nobs_2d", self.l2d),
+            p("bias_3d", self.l3d), p("rtms_3d", self.l3d), p("stdv_3d", self.l3d), p("xcov_3d", self.l3d), p("nobs_3d", self.l3d))
+        self._check(rc)
+        return g
+
+    # sharded Norm over peer memory (one node): every rank finalizes and writes its slab of rows
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(cabi.PEER_BLOB_BYTES)
+        self._check(cabi.load().gritas_b200_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, nranks, rank, blobs):
+        """blobs: the peer_export() bytes of every rank, in rank order (all-gathered by the caller)."""
+        raw = b"".join(blobs)
+        assert len(raw) == nranks * cabi.PEER_BLOB_BYTES
+        self._check(cabi.load().gritas_b200_peer_attach(self._h, nranks, rank, C.create_string_buffer(raw, len(raw))))
+
+    def slab(self, rank, nranks):
+        """Rows (jl = j + jm*l, 0-based, half-open) of the 3-D and the 2-D grids that `rank` finalizes and writes."""
+        v = [C.c_int(0) for _ in range(4)]
+        rc = cabi.load().gritas_b200_slab(self._h, rank, nranks, *[C.byref(x) for x in v])
+        if rc:
+            raise ValueError(f"gritas_b200_slab rc={rc}")
+        return tuple(x.value for x in v)
+
+    def norm_sharded_into(self, grids, nrmlz=True, ntresh=None):
+        """Collective GrITAS_Norm of a multi-rank run: this rank's slab of every array is written."""
+        g = grids
+        p = lambda k, on: cabi.ptr(g[k], np.float64) if on else None
+        rc = cabi.load().gritas_b200_norm_sharded(
+            self._h, 1 if nrmlz else 0, -1 if ntresh is None else int(ntresh),
             p("bias_2d", self.l2d), p("rtms_2d", self.l2d), p("stdv_2d", self.l2d), p("xcov_2d", self.l2d), p("nobs_2d", self.l2d),
             p("bias_3d", self.l3d), p("rtms_3d", self.l3d), p("stdv_3d", self.l3d), p("xcov_3d", self.l3d), p("nobs_3d", self.l3d))
         self._check(rc)

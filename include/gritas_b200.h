@@ -144,6 +144,10 @@ int gritas_b200_accum_odsx(gritas_b200_handle h, int nobs, const gritas_b200_ods
 /* Wait for all queued work; returns a pending GRITAS_B200_ERR_LEVEL (and its level) if any. */
 int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
 
+/* Same wait, but the tile lists of the tiled fast path stay parked (nothing is flushed into the records): what a host
+ * that drives several handles needs before a sharded Norm, and what an ASYNC caller uses to pick up a level miss. */
+int gritas_b200_wait(gritas_b200_handle h, double *bad_lev);
+
 /* Tiled fast path only: accumulate every staged observation into the HBM records now (asynchronous;
  * sync / norm / get_raw / allreduce do it implicitly).  A no-op in the other modes. */
 int gritas_b200_flush(gritas_b200_handle h);
@@ -233,6 +237,38 @@ int gritas_b200_norm_reduce(gritas_b200_handle h, int root, int nrmlz, int ntres
                             double *stdv_2d, double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d,
                             double *stdv_3d, double *xcov_3d, double *nobs_3d);
 int gritas_b200_norm_reduce_device(gritas_b200_handle h, int root, int nrmlz, int ntresh, const double **outs10);
+
+/*
+ * Sharded multi-rank GrITAS_Norm over peer memory (one node, up to 8 ranks; the reference is single-process, its
+ * file loop gritas.f:389-393 runs on each rank's share f mod nranks and gritas.f:885-887 becomes this call).
+ * Rank r finalizes 1/nranks of the rows (whole (j,l) rows, gritas_b200_slab) and its tile kernel pulls the parked
+ * observations of those rows from every rank's tile lists through NVLink peer mappings -- the exchange step of the
+ * path is fused into the accumulate + finalize kernel, no collective touches the sum grids.  Every rank writes only
+ * its slab of the output arrays (same shapes and meaning as gritas_b200_norm): pass arrays in a shared-memory segment
+ * (gritas_b200_host_register pins it) and the writer process sees the whole grids.
+ *   peer_export  fills a GRITAS_B200_PEER_BLOB_BYTES blob (CUDA IPC handles of the lists / records + the settings that
+ *                shape the exchange); gather the blobs of all ranks in rank order with whatever the host has
+ *                (MPI_Allgather in the Fortran driver, torch.distributed in bench.py)
+ *   peer_attach  maps the peers' buffers; fails on every rank alike if the ranks' settings differ
+ *   norm_sharded collective over the ranks (call it on every rank); with a communicator (gritas_b200_comm_init) the two
+ *                barriers it needs are stream-ordered one-element all-reduces, without one (several handles in one
+ *                process) the caller orders the calls: gritas_b200_sync on every handle first
+ * On the direct / deterministic path (no lists) the records of the slab are summed over the ranks in rank order
+ * (reproducible) and finalized; that variant is one-shot (reset afterwards), like gritas_b200_allreduce.
+ */
+#define GRITAS_B200_PEER_BLOB_BYTES 512
+int gritas_b200_peer_export(gritas_b200_handle h, void *blob);
+int gritas_b200_peer_attach(gritas_b200_handle h, int nranks, int rank, const void *blobs);
+int gritas_b200_slab(gritas_b200_handle h, int rank, int nranks, int *jl3_0, int *jl3_1, int *jl2_0, int *jl2_1);
+int gritas_b200_norm_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *bias_2d, double *rtms_2d, double *stdv_2d,
+                             double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *stdv_3d,
+                             double *xcov_3d, double *nobs_3d);
+int gritas_b200_norm_sharded_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **outs10);
+
+/* Page-locks / releases caller-owned host memory (Fortran allocatables, a shared-memory segment): copies to and from
+ * it are then direct DMA, no staging memcpy (replaces nothing in the reference; gritas.f:336-348 allocates the arrays). */
+int gritas_b200_host_register(void *p, size_t bytes);
+int gritas_b200_host_unregister(void *p);
 
 /* Pinned host memory for the caller's column arrays (direct DMA, no staging copy). */
 void *gritas_b200_host_alloc(size_t bytes);

@@ -71,3 +71,80 @@ def test_two_rank_norm_reduce_matches_oracle(mode):
     table, l2d, l3d, *_ = H.setup(cfg)
     ref, _ = H.oracle_run(cfg, files, 2, [H.filter_in(c, 101) for c in files])
     H.compare(got, ref, l2d, l3d, 2, exact=False, tol=1e-12)      # sums re-associated across ranks: not bit-exact
+
+
+def _worker_sharded(rank, world, nfiles, uid_q, blob_qs, out_q, mode):
+    import torch
+
+    from gritas_b200 import shard, synth
+    from gritas_b200.m_gritas_grids import Grids, nccl_unique_id
+    torch.cuda.set_device(rank)
+    cfg = synth.get_config("cfg2", 0.02)
+    cfg.im, cfg.jm = 72, 46
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode | 0x100, device=rank)     # ASYNC: nothing waits on the host
+    G._ensure(2, table, p1, p2, l2d, l3d)
+    if rank == 0:
+        uid = nccl_unique_id()
+        for _ in range(world - 1):
+            uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    G.comm_init(world, rank, uid)
+    blob = G.peer_export()
+    for q in blob_qs:
+        q.put((rank, blob))
+    got = dict(blob_qs[rank].get(timeout=120) for _ in range(world))
+    G.peer_attach(world, rank, [got[r] for r in range(world)])       # CUDA IPC mappings of the peer's lists / records
+    outs = []
+    for rep in range(2):                                              # twice: the barriers order the reset against the peer's reads
+        G.reset()
+        for fi in shard.files_for_rank(nfiles, rank, world):
+            c = synth.make_file(cfg, fi)
+            G.accum_ods(c, iopt=101, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
+        out = G.alloc_grids()
+        G.norm_sharded_into(out)
+        outs.append(out)
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True) or not (mode & 0x1000), k
+    out_q.put((rank, G.slab(rank, world), {k: v.copy() for k, v in outs[1].items()}))
+    G.close()
+
+
+@pytest.mark.parametrize("mode", [0x1000, 1])     # fast on the tiled path (entries pulled over NVLink), deterministic (records)
+def test_two_rank_sharded_norm_over_ipc_matches_oracle(mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from gritas_b200 import synth
+    world, nfiles = 2, 5
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    blob_qs = [ctx.Queue() for _ in range(world)]
+    procs = [ctx.Process(target=_worker_sharded, args=(r, world, nfiles, uid_q, blob_qs, out_q, mode)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = [out_q.get(timeout=200) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    cfg = synth.get_config("cfg2", 0.02)
+    cfg.im, cfg.jm = 72, 46
+    files = [synth.make_file(cfg, i) for i in range(nfiles)]
+    table, l2d, l3d, *_ = H.setup(cfg)
+    # stitch the slabs: rank r wrote rows [jl0, jl1) of every 3-D array (jl = j + jm*l)
+    merged = {k: np.full_like(v, -777.0) for k, v in parts[0][2].items()}
+    for rank, (a3, b3, a2, b2), out in parts:
+        for k, v in out.items():
+            if not k.endswith("3d"):
+                continue
+            for jl in range(a3, b3):
+                j, l = jl % cfg.jm, jl // cfg.jm
+                merged[k][:, j, :, l] = v[:, j, :, l]
+    for k in list(merged):
+        if k.endswith("2d"):
+            merged[k][...] = parts[0][2][k]
+    ref, _ = H.oracle_run(cfg, files, 2, [H.filter_in(c, 101) for c in files])
+    H.compare(merged, ref, 0, l3d, 2, exact=False, tol=1e-12 if mode == 1 else 1e-6)
