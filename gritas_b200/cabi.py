@@ -23,6 +23,7 @@ FLAG_HOLD_INPUTS = 0x400
 FLAG_NO_STAGING = 0x800
 FLAG_FORCE_TILED = 0x1000
 FLAG_MINMAX = 0x2000
+FLAG_NO_WRITEBACK = 0x4000
 
 OK = 0
 ERR_LEVEL = 7

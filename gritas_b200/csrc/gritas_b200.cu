@@ -18,6 +18,11 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -65,7 +70,70 @@ NcclApi g_nccl;
 constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
 constexpr int NCCL_SUM = 0;      // ncclSum
 
+// --- host copy pool: pageable caller arrays <-> pinned staging, chunk by chunk, on a few threads ---------------
+// An untouched gritas.f hands GrITAS_Accum pageable allocatables (ODS_Get allocates them per synoptic time, so a
+// cudaHostRegister cache would never hit) and expects GrITAS_Norm to fill pageable grids.  One thread's memcpy runs
+// at a fraction of PCIe; a handful of threads copying 1 MB chunks keep the DMA engine fed while it already moves
+// the chunks that are done.
+constexpr size_t COPY_CHUNK = (size_t)1 << 20;
+class CopyPool {
+ public:
+  struct Task { void *dst; const void *src; size_t n; std::atomic<int> *done; };
+  static CopyPool &get() {
+    static CopyPool *pool = new CopyPool();   // lives for the process: no destructor race at exit
+    return *pool;
+  }
+  void submit(void *dst, const void *src, size_t n, std::atomic<int> *done) {
+    if (th_.empty()) { memcpy(dst, src, n); done->store(1, std::memory_order_release); return; }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      q_.push_back(Task{dst, src, n, done});
+    }
+    cv_.notify_one();
+  }
+  static void wait(std::atomic<int> *done) {
+    int spins = 0;
+    while (!done->load(std::memory_order_acquire))
+      if (++spins > 2000) std::this_thread::yield();
+  }
+ private:
+  CopyPool() {
+    int n = 0;
+    if (const char *e = getenv("GRITAS_B200_COPY_THREADS")) n = atoi(e);
+    else {
+      const unsigned hw = std::thread::hardware_concurrency();
+      n = (int)std::min(8u, std::max(1u, hw / 2));
+    }
+    for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+    for (auto &t : th_) t.detach();
+  }
+  void run() {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return !q_.empty(); });
+        t = q_.front();
+        q_.pop_front();
+      }
+      memcpy(t.dst, t.src, t.n);
+      t.done->store(1, std::memory_order_release);
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<Task> q_;
+};
+
+struct PendingCopy {   // one chunk of a pageable column: copied into the pinned slot buffer by the pool, then DMA'd
+  void *dev; const void *pin; size_t n; std::atomic<int> *done;
+};
+
 struct Slot {
+  std::vector<PendingCopy> pending;
+  std::vector<std::atomic<int>> flags;
+  size_t nflags = 0;
   void *dev[NCOL] = {};
   void *pin[NCOL] = {};
   size_t dev_cap[NCOL] = {};
@@ -153,6 +221,12 @@ struct gritas_b200_ctx {
   unsigned *fill_snap = nullptr;      // local snapshot of every rank's fill / dirty / records-touched words
   size_t fill_snap_cap = 0;
   double *bar_buf = nullptr;          // operand of the stream-ordered barrier (a one-element all-reduce)
+  // device -> pageable host: ring of pinned bounce buffers (copy_out_pageable)
+  static constexpr int NBOUNCE = 8;
+  static constexpr size_t BOUNCE_BYTES = (size_t)4 << 20;
+  void *bounce[NBOUNCE] = {};
+  cudaEvent_t bounce_ev[NBOUNCE] = {};
+  std::atomic<int> bounce_done[NBOUNCE];
   // counters
   uint64_t launches = 0, h2d = 0, d2h = 0;
   char err[512] = {0};
@@ -232,6 +306,8 @@ int grow_pin(gritas_b200_handle h, void **p, size_t *cap, size_t bytes) {
   return 0;
 }
 
+int flush_pending(gritas_b200_handle h, Slot &s);
+
 // Makes column `c` of this call available on the device; returns the device pointer in *out.
 // Device-resident inputs are used in place.  Pinned inputs are DMA'd straight from the caller's
 // array; pageable inputs go through the slot's pinned buffer.
@@ -245,17 +321,72 @@ int stage(gritas_b200_handle h, Slot &s, int c, const void *src, size_t bytes, c
   }
   int rc = grow_dev(h, &s.dev[c], &s.dev_cap[c], bytes);
   if (rc) return rc;
-  const void *from = src;
   if (kind == 0) {
+    // pageable: the pool copies chunk by chunk into the slot's pinned buffer; flush_pending() issues each chunk's DMA as
+    // soon as it has landed there (the other chunks are still being copied)
     rc = grow_pin(h, &s.pin[c], &s.pin_cap[c], bytes);
     if (rc) return rc;
-    memcpy(s.pin[c], src, bytes);
-    from = s.pin[c];
+    for (size_t off = 0; off < bytes; off += COPY_CHUNK) {
+      const size_t n = std::min(COPY_CHUNK, bytes - off);
+      if (s.nflags >= s.flags.size() && (rc = flush_pending(h, s))) return rc;   // (a very large call: DMA what is there, reuse the flags)
+      std::atomic<int> *done = &s.flags[s.nflags++];
+      done->store(0, std::memory_order_relaxed);
+      CopyPool::get().submit((char *)s.pin[c] + off, (const char *)src + off, n, done);
+      s.pending.push_back(PendingCopy{(char *)s.dev[c] + off, (const char *)s.pin[c] + off, n, done});
+    }
+  } else {
+    CU(cudaMemcpyAsync(s.dev[c], src, bytes, cudaMemcpyHostToDevice, h->copy));
   }
-  CU(cudaMemcpyAsync(s.dev[c], from, bytes, cudaMemcpyHostToDevice, h->copy));
   h->h2d += bytes;
   *any_copy = true;
   *out = s.dev[c];
+  return 0;
+}
+
+// DMA of the pageable chunks in the order they were submitted (each as soon as the pool has copied it).
+int flush_pending(gritas_b200_handle h, Slot &s) {
+  for (const PendingCopy &pc : s.pending) {
+    CopyPool::wait(pc.done);
+    CU(cudaMemcpyAsync(pc.dev, pc.pin, pc.n, cudaMemcpyHostToDevice, h->copy));
+  }
+  s.pending.clear();
+  s.nflags = 0;
+  return 0;
+}
+
+// Device -> pageable host array: DMA into a ring of pinned bounce buffers, the pool copies them out while the next
+// chunks are in flight (cudaMemcpyAsync to pageable memory would stage through the driver on one thread).
+// Synchronous: the data is in `user` on return.  Stream order is kept (the DMAs are queued on `sm`).
+int copy_out_pageable(gritas_b200_handle h, void *user, const void *dev, size_t bytes, cudaStream_t sm) {
+  constexpr int NB = gritas_b200_ctx::NBOUNCE, LAG = 2;
+  constexpr size_t CB = gritas_b200_ctx::BOUNCE_BYTES;
+  if (!h->bounce[0]) {
+    for (int b = 0; b < NB; ++b) {
+      CU(cudaMallocHost(&h->bounce[b], CB));
+      CU(cudaEventCreateWithFlags(&h->bounce_ev[b], cudaEventDisableTiming));
+      h->bounce_done[b].store(1);
+    }
+  }
+  const size_t nchunk = (bytes + CB - 1) / CB;
+  auto retire = [&](size_t j) -> int {      // chunk j has landed in its bounce buffer: hand it to the pool
+    const int b = (int)(j % NB);
+    CU(cudaEventSynchronize(h->bounce_ev[b]));
+    const size_t off = j * CB, n = std::min(CB, bytes - off);
+    h->bounce_done[b].store(0, std::memory_order_relaxed);
+    CopyPool::get().submit((char *)user + off, h->bounce[b], n, &h->bounce_done[b]);
+    return 0;
+  };
+  for (size_t i = 0; i < nchunk; ++i) {
+    const int b = (int)(i % NB);
+    CopyPool::wait(&h->bounce_done[b]);      // the copy out of chunk i - NB is complete: the buffer is free
+    const size_t off = i * CB, n = std::min(CB, bytes - off);
+    CU(cudaMemcpyAsync(h->bounce[b], (const char *)dev + off, n, cudaMemcpyDeviceToHost, sm));
+    CU(cudaEventRecord(h->bounce_ev[b], sm));
+    if (i >= (size_t)LAG) { int rc = retire(i - LAG); if (rc) return rc; }
+  }
+  for (size_t j = nchunk > (size_t)LAG ? nchunk - LAG : 0; j < nchunk; ++j) { int rc = retire(j); if (rc) return rc; }
+  for (int b = 0; b < NB; ++b) CopyPool::wait(&h->bounce_done[b]);
+  h->d2h += bytes;
   return 0;
 }
 
@@ -476,6 +607,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     CU(cudaStreamWaitEvent(run, h->main_ev, 0));   // not before the last reset / flush
   }
   if (any_copy) {
+    if (int pr = flush_pending(h, s)) return pr;
     CU(cudaEventRecord(s.copied, h->copy));
     CU(cudaStreamWaitEvent(run, s.copied, 0));
   }
@@ -573,8 +705,12 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
   }
 
   if (flag_to_host) {
-    CU(cudaMemcpyAsync(flag_host_or_dev, s.flag_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, run));
-    h->d2h += sizeof(int) * (size_t)n;
+    if (mem_kind(flag_host_or_dev) == 0 && (size_t)n * sizeof(int) >= ((size_t)1 << 20)) {
+      if (int cr = copy_out_pageable(h, flag_host_or_dev, s.flag_out, sizeof(int) * (size_t)n, run)) return cr;
+    } else {
+      CU(cudaMemcpyAsync(flag_host_or_dev, s.flag_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, run));
+      h->d2h += sizeof(int) * (size_t)n;
+    }
   }
   if (tiled) {
     CU(cudaEventRecord(h->wk_done[w], run));
@@ -684,6 +820,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
   CUC(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
   for (int i = 0; i < NSLOT; ++i) {
+    h->slot[i].flags = std::vector<std::atomic<int>>(4096);
     CUC(cudaEventCreateWithFlags(&h->slot[i].consumed, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&h->slot[i].copied, cudaEventDisableTiming));
   }
@@ -809,6 +946,10 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (h->ev_red[c]) cudaEventDestroy(h->ev_red[c]);
   }
   if (h->ev_fin) cudaEventDestroy(h->ev_fin);
+  for (int b = 0; b < gritas_b200_ctx::NBOUNCE; ++b) {
+    if (h->bounce[b]) cudaFreeHost(h->bounce[b]);
+    if (h->bounce_ev[b]) cudaEventDestroy(h->bounce_ev[b]);
+  }
   for (int r = 0; r < MAX_PEERS; ++r)
     if (h->peer_ipc[r])
       for (void *p : {h->peer_lists[r], h->peer_fill[r], h->peer_acc[r]})
@@ -859,6 +1000,14 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   Slot &s = h->slot[h->next_slot];
   h->next_slot = (h->next_slot + 1) % NSLOT;
 
+  struct PendingGuard {   // an error return must not leave pool tasks reading the caller's arrays
+    Slot &s;
+    ~PendingGuard() {
+      for (const PendingCopy &pc : s.pending) CopyPool::wait(pc.done);
+      s.pending.clear();
+      s.nflags = 0;
+    }
+  } guard{s};
   ObsCols c = {};
   c.n = nobs;
   bool any = false;
@@ -905,7 +1054,8 @@ int gritas_b200_accum(gritas_b200_handle h, int nobs, const double *lat, const d
   if (nobs > 0 && !del) return fail(h, GRITAS_B200_ERR_ARG, "null del");
   const double *d[3] = {del, h->g.nr > 1 ? del + (size_t)nobs : nullptr, h->g.nr > 2 ? del + 2 * (size_t)nobs : nullptr};
   FilterDesc f = {};
-  return accum_common(h, nobs, lat, lon, lev, d, nullptr, nullptr, nullptr, kx, kt, ob_flag, nullptr, f, ob_flag, bad_lev);
+  int32_t *flag_out = (h->flags & GRITAS_B200_FLAG_NO_WRITEBACK) ? nullptr : ob_flag;
+  return accum_common(h, nobs, lat, lon, lev, d, nullptr, nullptr, nullptr, kx, kt, ob_flag, nullptr, f, flag_out, bad_lev);
 }
 
 int gritas_b200_accum_ods(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
@@ -1264,8 +1414,13 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
   for (int a = 0; a < 10; ++a) {
     if (dev_out) dev_out[a] = dst[a];
     else if (bounce[a]) {
-      CU(cudaMemcpyAsync(user[a], dst[a], sizeof(double) * sz[a], cudaMemcpyDeviceToHost, h->compute));
-      h->d2h += sizeof(double) * sz[a];
+      if (mem_kind(user[a]) == 0 && sz[a] * sizeof(double) >= ((size_t)1 << 20)) {
+        int rc = copy_out_pageable(h, user[a], dst[a], sizeof(double) * sz[a], h->compute);
+        if (rc) return rc;
+      } else {
+        CU(cudaMemcpyAsync(user[a], dst[a], sizeof(double) * sz[a], cudaMemcpyDeviceToHost, h->compute));
+        h->d2h += sizeof(double) * sz[a];
+      }
     }
   }
   if (piped) return drain(h, nullptr);

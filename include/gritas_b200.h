@@ -42,6 +42,9 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
                                             deciding from the locality of the first large call */
 #define GRITAS_B200_FLAG_MINMAX 0x2000      /* the handle implements GrITAS_MinMax_ (m_gritas_grids.f:1019-1167, -minmax):
                                             accum keeps min / max / count per box instead of sums; nr must be 1 */
+#define GRITAS_B200_FLAG_NO_WRITEBACK 0x4000 /* gritas_b200_accum reads ob_flag but does not write it back: only GrITAS_LBTally
+                                            (-lb, gritas.f:791-796) consumes the flags GrITAS_Accum_ sets (m_gritas_grids.f:413-416);
+                                            without it the download and, with ASYNC, the synchronisation per call go away */
 #define GRITAS_B200_FLAG_HOLD_INPUTS 0x400  /* with ASYNC: the caller keeps pinned input arrays valid until the
                                             next sync/norm, so accum does not even wait for the H2D copies */
 

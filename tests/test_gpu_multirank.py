@@ -105,8 +105,11 @@ def _worker_sharded(rank, world, nfiles, uid_q, blob_qs, out_q, mode):
         out = G.alloc_grids()
         G.norm_sharded_into(out)
         outs.append(out)
-    for k in outs[0]:
-        assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True) or not (mode & 0x1000), k
+    for k in outs[0]:          # same inputs, same slab; the fast path is order-free, so only the counts repeat bit for bit
+        if k.startswith("nobs"):
+            assert np.array_equal(outs[0][k], outs[1][k]), k
+        else:
+            assert np.allclose(outs[0][k], outs[1][k], rtol=1e-9, atol=1e-9, equal_nan=True), k
     out_q.put((rank, G.slab(rank, world), {k: v.copy() for k, v in outs[1].items()}))
     G.close()
 

@@ -775,3 +775,37 @@ def test_multi_rank_norm_pipeline_on_one_rank(case, monkeypatch):
         G.norm_into(again)
         H.compare(again, ref, l2d, l3d, 2, exact=False, tol=TOL_FAST)
     G.close()
+
+
+def test_no_writeback_flag_leaves_ob_flag_untouched():
+    """GRITAS_B200_FLAG_NO_WRITEBACK: ob_flag is an input only (what a driver without -lb needs, gritas.f:791-796);
+    the grids are the same as with the write-back."""
+    cfg, files = small("cfg1", 0.05, 2)
+    fin = [flags_of(cfg, c) for c in files]
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    ref, rflags = H.oracle_run(cfg, files, 1, fin)
+    assert any(not np.array_equal(a, b) for a, b in zip(fin, rflags))       # the oracle does set flags (not-in-table obs)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_DETERMINISTIC | cabi.FLAG_NO_WRITEBACK | cabi.FLAG_ASYNC)
+    for c, f0 in zip(files, fin):
+        fl = f0.copy()
+        G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 1), len(fl), 1, table, p1, p2, fl, l2d, l3d=l3d)
+        assert np.array_equal(fl, f0)
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.close()
+    H.compare(out, ref, l2d, l3d, 1, exact=True, tol=0.0)
+
+
+def test_pageable_columns_through_the_copy_pool_full_size():
+    """One full-size file (1.21 M obs, ~10 MB per column) from pageable arrays: the staging copies run chunk by chunk on
+    the library's host threads, the grids and the ob_flag write-back come back through the pinned bounce ring."""
+    cfg = synth.get_config("cfg2", 1.0)
+    cfg.im, cfg.jm = 72, 46
+    c = synth.make_file(cfg, 3)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    fin = H.filter_in(c, 101)
+    ref, rflags = H.oracle_run(cfg, [c], 2, [fin])
+    for mode in (cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, cabi.MODE_DETERMINISTIC):
+        out, gflags = H.gpu_run(cfg, [c], 2, mode, [fin])
+        assert np.array_equal(gflags[0], rflags[0])
+        H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)

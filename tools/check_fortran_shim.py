@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Syntax-level checks of the Fortran drop-in that need no Fortran compiler (the image has none).
+
+1. Every `bind(C, name='...')` interface of fortran/m_gritas_b200.F90 matches its prototype in
+   include/gritas_b200.h argument for argument: same count, same order, same C type class
+   (handle by value / handle by reference, int by value, double by value, int32 array, double
+   array, scalar double by reference, opaque byte buffer).
+2. The module dependency graph of the drop-in has no cycle: m_gritas_grids (with
+   fortran/m_gritas_grids_b200.inc substituted for its four routines) -> m_gritas_b200 ->
+   { iso_c_binding, m_odsmeta }.  When the reference tree is present its m_gritas_grids.f is read
+   for the modules it already uses.
+3. Every procedure the include file calls is public in the shim, with the same number of arguments.
+4. The replacement routines keep the reference's argument lists (checked against the reference
+   source when /root/reference is present).
+
+Exit code 0 = all checks pass; prints one line per failure otherwise.
+"""
+from __future__ import annotations
+
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "fortran", "m_gritas_b200.F90")
+INC = os.path.join(ROOT, "fortran", "m_gritas_grids_b200.inc")
+HEADER = os.path.join(ROOT, "include", "gritas_b200.h")
+REF_GRIDS = "/root/reference/src/Components/gritas/m_gritas_grids.f"
+
+
+def strip_fortran(text):
+    """drop comments, join continuation lines, lower-case"""
+    out, cur = [], ""
+    for raw in text.splitlines():
+        line = raw.split("!")[0].rstrip()
+        if not line.strip():
+            continue
+        s = line.strip()
+        if s.startswith("&"):
+            s = s[1:].lstrip()
+        if cur:
+            cur += " " + s
+        else:
+            cur = s
+        if cur.endswith("&"):
+            cur = cur[:-1].rstrip()
+            continue
+        out.append(cur.lower())
+        cur = ""
+    if cur:
+        out.append(cur.lower())
+    return out
+
+
+def strip_fixed_form(text):
+    """fixed-form reference source: comment lines start with c/C/*/! in column 1, continuation = non-blank column 6"""
+    out = []
+    for raw in text.splitlines():
+        if not raw.strip() or raw[0] in "cC*!":
+            continue
+        line = raw.split("!")[0].rstrip()
+        if not line.strip():
+            continue
+        if len(line) > 5 and line[5] not in " 0" and line[:5].strip() == "":
+            out[-1] += " " + line[6:].strip().lstrip("&").strip()
+        else:
+            s = line.strip()
+            if s.startswith("&") and out:
+                out[-1] += " " + s[1:].strip()
+            else:
+                out.append(s)
+    return [l.rstrip("&").strip().lower() for l in out]
+
+
+def split_args(s):
+    return [a.strip() for a in s.split(",") if a.strip()]
+
+
+# ---------------------------------------------------------------- C header
+def c_prototypes():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|void|uint64_t|const char \*|void \*)\s*(gritas_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(2), " ".join(m.group(3).split())
+        kinds = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                base = re.sub(r"\b[a-z_0-9]+$", "", a).strip() if not a.endswith("*") else a   # drop the parameter name
+                base = base.replace("const ", "").strip()
+                kinds.append(classify_c(base))
+        protos[name] = kinds
+    return protos
+
+
+def classify_c(t):
+    t = " ".join(t.split())
+    return {
+        "gritas_b200_handle": "handle", "gritas_b200_handle *": "handle*", "int": "int", "double": "double",
+        "size_t": "size_t", "int32_t *": "int*", "int *": "int*", "double *": "double*", "void *": "bytes",
+        "gritas_b200_ods *": "struct*", "double **": "double**",
+    }.get(t, "?" + t)
+
+
+# ---------------------------------------------------------------- Fortran interfaces
+def fortran_interfaces(lines):
+    """name -> list of kinds in dummy-argument order, for every bind(C) interface body"""
+    res = {}
+    i = 0
+    while i < len(lines):
+        m = re.match(r"(?:integer\(c_int\)\s+function|subroutine)\s+(\w+)\s*\((.*?)\)\s*bind\s*\(\s*c\s*,\s*name\s*=\s*'(\w+)'\s*\)", lines[i])
+        if not m:
+            i += 1
+            continue
+        dummies, cname = split_args(m.group(2)), m.group(3)
+        decl = {}
+        i += 1
+        while i < len(lines) and not re.match(r"end\s+(function|subroutine)", lines[i]):
+            d = re.match(r"(type\(c_ptr\)|integer\(c_int\)|real\(c_double\)|character\(kind=c_char\))\s*(?:,\s*([^:]*?))?\s*::\s*(.*)", lines[i])
+            if d:
+                typ, attrs, names = d.group(1), (d.group(2) or ""), d.group(3)
+                for nm in re.findall(r"(\w+)\s*(\(\*\))?", names):
+                    if nm[0]:
+                        decl[nm[0]] = (typ, attrs, bool(nm[1]))
+            i += 1
+        kinds = []
+        for a in dummies:
+            if a not in decl:
+                kinds.append("undeclared:" + a)
+                continue
+            typ, attrs, arr = decl[a]
+            val = "value" in attrs
+            if typ == "type(c_ptr)":
+                kinds.append("handle" if val else "handle*")
+            elif typ == "integer(c_int)":
+                kinds.append("int" if val else "int*")          # scalar by reference == pointer to int
+            elif typ == "real(c_double)":
+                kinds.append("double" if val else "double*")
+            else:
+                kinds.append("bytes")
+        res[cname] = kinds
+    return res
+
+
+def used_modules(lines):
+    mods = set()
+    for l in lines:
+        m = re.match(r"use\s*(?:,\s*intrinsic\s*::)?\s*(\w+)", l)
+        if m:
+            mods.add(m.group(1))
+    return mods
+
+
+def public_procs(lines):
+    pub = set()
+    for l in lines:
+        m = re.match(r"public\s*::\s*(.*)", l)
+        if m:
+            pub.update(split_args(m.group(1)))
+    return pub
+
+
+def subroutine_args(lines):
+    res = {}
+    for l in lines:
+        m = re.match(r"subroutine\s+(\w+)\s*\((.*)\)\s*$", l)
+        if m:
+            res[m.group(1)] = split_args(m.group(2))
+    return res
+
+
+def calls(lines):
+    res = []
+    for l in lines:
+        m = re.match(r"call\s+(\w+)\s*\((.*)\)\s*$", l)
+        if m:
+            res.append((m.group(1), split_args(m.group(2))))
+    return res
+
+
+def find_cycle(graph):
+    seen, stack = {}, []
+
+    def dfs(u):
+        seen[u] = 1
+        stack.append(u)
+        for v in graph.get(u, ()):
+            if seen.get(v) == 1:
+                return stack[stack.index(v):] + [v]
+            if v not in seen:
+                c = dfs(v)
+                if c:
+                    return c
+        stack.pop()
+        seen[u] = 2
+        return None
+    for n in list(graph):
+        if n not in seen:
+            c = dfs(n)
+            if c:
+                return c
+    return None
+
+
+def run():
+    errors = []
+    shim = strip_fortran(open(SHIM).read())
+    inc = strip_fortran(open(INC).read())
+    protos = c_prototypes()
+    ifaces = fortran_interfaces(shim)
+    if len(ifaces) < 15:
+        errors.append(f"only {len(ifaces)} bind(C) interfaces parsed from the shim")
+    for name, kinds in ifaces.items():
+        if name not in protos:
+            errors.append(f"{name}: bound in the shim, not declared in include/gritas_b200.h")
+            continue
+        want = protos[name]
+        if len(want) != len(kinds):
+            errors.append(f"{name}: {len(kinds)} arguments in the shim, {len(want)} in the header")
+            continue
+        for pos, (a, b) in enumerate(zip(kinds, want)):
+            ok = a == b or (a == "handle" and b == "bytes") or (a == "bytes" and b == "bytes")
+            if not ok:
+                errors.append(f"{name}: argument {pos + 1} is {a} in the shim, {b} in the header")
+    # module graph
+    graph = {"m_gritas_b200": used_modules(shim)}
+    grids_uses = used_modules(inc)
+    if os.path.exists(REF_GRIDS):
+        grids_uses |= used_modules(strip_fixed_form(open(REF_GRIDS, errors="replace").read()))
+    graph["m_gritas_grids"] = grids_uses
+    if "m_gritas_grids" in graph["m_gritas_b200"]:
+        errors.append("m_gritas_b200 uses m_gritas_grids (and m_gritas_grids uses m_gritas_b200): circular")
+    if "m_gritas_b200" not in graph["m_gritas_grids"]:
+        errors.append("the include file does not use m_gritas_b200")
+    cyc = find_cycle(graph)
+    if cyc:
+        errors.append("module dependency cycle: " + " -> ".join(cyc))
+    allowed = {"iso_c_binding", "m_odsmeta"}
+    extra = graph["m_gritas_b200"] - allowed
+    if extra:
+        errors.append(f"the shim uses modules beyond iso_c_binding / m_odsmeta: {sorted(extra)}")
+    # calls of the include file resolve to public shim procedures of the same arity
+    pub = public_procs(shim)
+    sargs = subroutine_args(shim)
+    for name, args in calls(inc):
+        if not name.startswith("b200_"):
+            continue
+        if name not in pub:
+            errors.append(f"{name}: called by the include file, not public in the shim")
+        elif name not in sargs:
+            errors.append(f"{name}: public but not defined in the shim")
+        elif len(sargs[name]) != len(args):
+            errors.append(f"{name}: called with {len(args)} arguments, defined with {len(sargs[name])}")
+    for name in pub:
+        if name.startswith("b200_") and name not in sargs and name != "b200_peer_blob_bytes":
+            errors.append(f"{name}: public but not defined")
+    # the replacement routines keep the reference's dummy-argument lists
+    if os.path.exists(REF_GRIDS):
+        ref_args = subroutine_args(strip_fixed_form(open(REF_GRIDS, errors="replace").read()))
+        for name, args in subroutine_args(inc).items():
+            if name not in ref_args:
+                errors.append(f"{name}: not a routine of the reference's m_gritas_grids.f")
+            elif ref_args[name] != args:
+                errors.append(f"{name}: dummy arguments differ from the reference: {args} vs {ref_args[name]}")
+    return errors, ifaces, graph
+
+
+if __name__ == "__main__":
+    errs, ifaces, graph = run()
+    print(f"{len(ifaces)} bind(C) interfaces checked against include/gritas_b200.h")
+    print("module graph:", {k: sorted(v) for k, v in graph.items()})
+    for e in errs:
+        print("FAIL:", e)
+    sys.exit(1 if errs else 0)
