@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.environ.get("GRITAS_B200_LIBDIR") or os.path.join(HERE, "lib")   # override: experiments with alternative builds
 LIB = os.path.join(LIBDIR, "libgritas_b200.so")
-SOURCES = ["gritas_b200.cu"]
+SOURCES = ["gritas_b200.cu", "xcov.cu"]
 HEADERS = ["kernels.cuh", os.path.join("..", "..", "include", "gritas_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -46,7 +46,10 @@ SYMBOLS = [
     "gritas_b200_d2h_bytes", "gritas_b200_version",
     "gritas_b200_peer_export", "gritas_b200_peer_attach", "gritas_b200_slab", "gritas_b200_norm_sharded",
     "gritas_b200_norm_sharded_device", "gritas_b200_host_register", "gritas_b200_host_unregister", "gritas_b200_wait",
+    "gritas_b200_xcov_create", "gritas_b200_xcov_destroy", "gritas_b200_xcov_reset", "gritas_b200_xcov_accum",
+    "gritas_b200_xcov_norm", "gritas_b200_xcov_get_raw", "gritas_b200_xcov_last_error", "gritas_b200_xcov_launch_count",
 ]
+ERR_PROFILE = 9
 PEER_BLOB_BYTES = 512
 
 OPT_TCH = 1
@@ -108,6 +111,17 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_norm_sharded_device.argtypes = [_P, _I, _I, C.POINTER(_P)]
     L.gritas_b200_host_register.argtypes = [_P, C.c_size_t]
     L.gritas_b200_host_unregister.argtypes = [_P]
+    L.gritas_b200_xcov_create.argtypes = [C.POINTER(_P), _I, _I, _P, _I, _I, _I, _P, _I, _I, _I]
+    L.gritas_b200_xcov_destroy.argtypes = [_P]
+    L.gritas_b200_xcov_destroy.restype = None
+    L.gritas_b200_xcov_reset.argtypes = [_P]
+    L.gritas_b200_xcov_accum.argtypes = [_P, _I, _P, _P, _P, _P, _P, C.POINTER(_I)]
+    L.gritas_b200_xcov_norm.argtypes = [_P, _I, _I, _I, _P, _P, _P]
+    L.gritas_b200_xcov_get_raw.argtypes = [_P, _P, _P, _P]
+    L.gritas_b200_xcov_last_error.argtypes = [_P]
+    L.gritas_b200_xcov_last_error.restype = C.c_char_p
+    L.gritas_b200_xcov_launch_count.argtypes = [_P]
+    L.gritas_b200_xcov_launch_count.restype = C.c_uint64
     L.gritas_b200_host_alloc.argtypes = [C.c_size_t]
     L.gritas_b200_host_alloc.restype = _P
     L.gritas_b200_host_free.argtypes = [_P]

@@ -388,3 +388,79 @@ def nccl_unique_id() -> bytes:
     if rc:
         raise RuntimeError(f"gritas_b200_nccl_unique_id rc={rc}")
     return buf.raw
+
+
+class XCov:
+    """GrITAS_XCov_Accum / GrITAS_XCov_Norm of m_gritas_grids (m_gritas_grids.f:667-1008) on the GPU: channel
+    cross-covariances from complete profiles of km observations.  achan: the active channels (the achan(:, ichan_version)
+    column); nr = 2 (Desroziers) or nr = 3 with tch (three-cornered hat)."""
+
+    def __init__(self, km, achan, l3d, nr, tch, kxkt_table, device=-1):
+        L = cabi.load()
+        self.km, self.nchan, self.l3d, self.nr, self.tch = int(km), len(achan), int(l3d), int(nr), bool(tch)
+        a = _i32(achan)
+        table = np.asfortranarray(kxkt_table, dtype=np.int32)
+        h = C.c_void_p()
+        rc = L.gritas_b200_xcov_create(C.byref(h), self.km, self.nchan, a.ctypes.data, self.l3d, self.nr, 1 if tch else 0,
+                                       table.ctypes.data, table.shape[0], table.shape[1], device)
+        self._h = None
+        if rc == cabi.ERR_NR:
+            raise GritasPerror("GrITAS_XCov_Accum_: improper dim settings / setting inconsistent w/ dims")   # :734-745
+        if rc == cabi.ERR_CUDA:
+            raise RuntimeError("gritas_b200_xcov_create: no usable CUDA device (there is no CPU fallback)")
+        if rc:
+            raise ValueError(f"gritas_b200_xcov_create rc={rc}")
+        self._h = h
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = cabi.load().gritas_b200_xcov_last_error(self._h).decode()
+        if rc == cabi.ERR_PROFILE:
+            raise GritasPerror(msg, 7)
+        raise RuntimeError(f"gritas_b200_xcov rc={rc}: {msg}")
+
+    def GrITAS_XCov_Accum(self, lat, lon, lev, kx, kt, del_, nobs, nr, kxkt_table, ob_flag, l3d, bias_lv=None, xcov_lv=None,
+                          nobs_lv=None, tch=None):
+        """Reference argument list (m_gritas_grids.f:667-670); lat / lon / the host arrays are accepted and ignored (the
+        reference never reads lat / lon either; the accumulators live on the device).  Returns nprof."""
+        assert nr == self.nr and l3d == self.l3d
+        if isinstance(del_, np.ndarray) and not del_.flags.f_contiguous:
+            del_ = np.asfortranarray(del_)
+        n = C.c_int(0)
+        self._check(cabi.load().gritas_b200_xcov_accum(self._h, int(nobs), cabi.ptr(lev, np.float64), cabi.ptr(kx, np.int32),
+                                                       cabi.ptr(kt, np.int32), cabi.ptr(del_, np.float64),
+                                                       cabi.ptr(ob_flag, np.int32), C.byref(n)))
+        return n.value
+
+    def alloc(self):
+        return (np.zeros((self.nchan, self.l3d, self.nr), order="F"), np.zeros((self.nchan, self.nchan, self.l3d, self.nr), order="F"),
+                np.zeros((self.nchan, self.l3d), order="F"))
+
+    def GrITAS_XCov_Norm(self, nr, nrmlz, tch, self_, l3d, bias_3d, xcov_3d, nobs_3d, ntresh=None):
+        """m_gritas_grids.f:859-861: fills the three arrays with the normalised statistics."""
+        assert nr == self.nr and bool(tch) == self.tch and l3d == self.l3d
+        self._check(cabi.load().gritas_b200_xcov_norm(self._h, 1 if nrmlz else 0, 1 if self_ else 0, -1 if ntresh is None else int(ntresh),
+                                                      cabi.ptr(bias_3d, np.float64), cabi.ptr(xcov_3d, np.float64),
+                                                      cabi.ptr(nobs_3d, np.float64)))
+
+    def get_raw(self, bias_lv, xcov_lv, nobs_lv):
+        self._check(cabi.load().gritas_b200_xcov_get_raw(self._h, cabi.ptr(bias_lv, np.float64), cabi.ptr(xcov_lv, np.float64),
+                                                         cabi.ptr(nobs_lv, np.float64)))
+
+    def reset(self):
+        self._check(cabi.load().gritas_b200_xcov_reset(self._h))
+
+    def launches(self):
+        return cabi.load().gritas_b200_xcov_launch_count(self._h)
+
+    def close(self):
+        if self._h is not None:
+            cabi.load().gritas_b200_xcov_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -53,6 +53,8 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
 #define GRITAS_B200_ERR_LEVEL 7   /* 'Accum: could not find level' -- the reference exits with 7
                                      (m_gritas_grids.f:458-459 -> gritas_etc.f:54-60) */
 #define GRITAS_B200_ERR_NR 8      /* 'could not handle more then 2 residuals' (m_gritas_grids.f:395, 555) */
+#define GRITAS_B200_ERR_PROFILE 9 /* 'XCov_Accum: not all profiles complete' / 'error in channel matching'
+                                     (m_gritas_grids.f:754-757, 789-790) */
 #define GRITAS_B200_ERR_CUDA (-1) /* CUDA failure or no device; see gritas_b200_last_error */
 #define GRITAS_B200_ERR_ARG (-2)  /* bad argument */
 #define GRITAS_B200_ERR_NCCL (-3) /* NCCL not loadable / NCCL failure */
@@ -272,6 +274,37 @@ int gritas_b200_norm_sharded_device(gritas_b200_handle h, int nrmlz, int ntresh,
  * it are then direct DMA, no staging memcpy (replaces nothing in the reference; gritas.f:336-348 allocates the arrays). */
 int gritas_b200_host_register(void *p, size_t bytes);
 int gritas_b200_host_unregister(void *p);
+
+/*
+ * Channel cross-covariances ("a la Desroziers" with two residual series, three-cornered hat with three):
+ *   gritas_b200_xcov_accum  replaces GrITAS_XCov_Accum_ (m_gritas_grids.f:667-848; called per synoptic time like
+ *                           GrITAS_Accum).  The observations come as complete profiles of km consecutive entries; a
+ *                           profile counts when each of the nchan active channels (achan = the achan(:, ichan_version)
+ *                           column, m_gritas_grids.f:69-71; matched against NINT(lev)) is present, not flagged and in the
+ *                           kx-kt table; such a profile adds the outer product of its residual vectors to xcov_lv.
+ *                           ob_flag is inout as in the reference (set to 1 for active channels not in the table); the
+ *                           reference's lat / lon arguments are unused there and absent here.  *nprof = accepted profiles.
+ *                           rc GRITAS_B200_ERR_PROFILE: nobs is not a multiple of km, or a profile matched more than
+ *                           nchan observations (both fatal in the reference).
+ *   gritas_b200_xcov_norm   replaces GrITAS_XCov_Norm_ (m_gritas_grids.f:859-1008): means, covariances m/(m-1)(<xy> - ...)
+ *                           (the symmetrised Desroziers form, or per series with tch) and, with tch and not self, the
+ *                           three-cornered-hat combination.  Works on copies: the accumulators stay as they are.
+ * Arrays, column-major: bias_lv (nchan, l3d, nr), xcov_lv (nchan, nchan, l3d, nr), nobs_lv (nchan, l3d); host or device.
+ * The sums are formed profile by profile in input order with one multiply and one add per element: bit-identical to the
+ * reference loop.  nr = 2 (tch = 0) or nr = 3 (tch = 1), as the reference demands (:737-745).
+ */
+typedef struct gritas_b200_xcov_ctx *gritas_b200_xcov_handle;
+int gritas_b200_xcov_create(gritas_b200_xcov_handle *h, int km, int nchan, const int32_t *achan, int l3d, int nr, int tch,
+                            const int32_t *kxkt_table, int kxmax, int ktmax, int device);
+void gritas_b200_xcov_destroy(gritas_b200_xcov_handle h);
+int gritas_b200_xcov_reset(gritas_b200_xcov_handle h);
+int gritas_b200_xcov_accum(gritas_b200_xcov_handle h, int nobs, const double *lev, const int32_t *kx, const int32_t *kt,
+                           const double *del, int32_t *ob_flag, int *nprof);
+int gritas_b200_xcov_norm(gritas_b200_xcov_handle h, int nrmlz, int self, int ntresh, double *bias_lv, double *xcov_lv,
+                          double *nobs_lv);
+int gritas_b200_xcov_get_raw(gritas_b200_xcov_handle h, double *bias_lv, double *xcov_lv, double *nobs_lv);
+const char *gritas_b200_xcov_last_error(gritas_b200_xcov_handle h);
+uint64_t gritas_b200_xcov_launch_count(gritas_b200_xcov_handle h);
 
 /* Pinned host memory for the caller's column arrays (direct DMA, no staging copy). */
 void *gritas_b200_host_alloc(size_t bytes);

@@ -662,3 +662,196 @@ int orc_maskout(int im, int jm, int nobs, const double *lat, const double *lon, 
   }
   return nexcl;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Channel / level cross-covariance family (m_gritas_grids.f:667-1008, 1862-2059).  Arrays:
+ *   bias_lv(ndim, l3d, nr), xcov_lv(ndim, ndim, l3d, nr), nobs_lv(ndim, l3d), column-major, 1-based. */
+#define XB(k, l, r) bias_lv[((size_t)((k) - 1)) + (size_t)ndim * (((size_t)((l) - 1)) + (size_t)l3d * ((size_t)((r) - 1)))]
+#define XC(a, b, l, r) \
+  xcov_lv[((size_t)((a) - 1)) + (size_t)ndim * (((size_t)((b) - 1)) + (size_t)ndim * (((size_t)((l) - 1)) + (size_t)l3d * ((size_t)((r) - 1))))]
+#define XN(k, l) nobs_lv[((size_t)((k) - 1)) + (size_t)ndim * ((size_t)((l) - 1))]
+
+/* m_gritas_grids.f:667-848 (GrITAS_XCov_Accum_).  km = profile length (module variable), achan = the
+ * achan(:, ichan_version) column of the active channels (m_gritas_grids.f:69-71), ndim = nchan.
+ * Returns 0, or 1 'improper dim settings' (:734-736), 2 'TCH setting inconsistent w/ dims' (:738-740),
+ * 3 'Desroziers setting inconsistent w/ dims' (:742-744), 4 'not all profiles complete' (:754-757),
+ * 5 'error in channel matching' (:789-790).  lat / lon are arguments of the reference routine but never used. */
+int orc_xcov_accum(int km, int nchan, const int *achan, int nobs, int nr, const double *lev, const int *kx,
+                   const int *kt, const double *del, const int *kxkt_table, int kxmax, int ktmax, int *ob_flag,
+                   int l3d, double *bias_lv, double *xcov_lv, double *nobs_lv, int *nprof, int tch) {
+  const int ndim = nchan;
+  int n1, ii, kk, k, m1, l, ir, rc = 0;
+  int *indx, *ll, *reject_ob;
+  double *rdel;
+  (void)ktmax;
+  if (nr > 3) return 1;
+  if (tch) { if (nr != 3) return 2; } else { if (nr != 2) return 3; }
+  if (nobs % km != 0) return 4;                                        /* :751-757 */
+  indx = (int *)calloc((size_t)nchan, sizeof(int));
+  ll = (int *)calloc((size_t)nchan, sizeof(int));
+  reject_ob = (int *)calloc((size_t)nchan, sizeof(int));
+  rdel = (double *)malloc(sizeof(double) * (size_t)nchan * (size_t)nr);
+  *nprof = 0;
+  for (n1 = 1; n1 <= nobs && !rc; n1 += km) {                          /* :774 */
+    const int n2 = n1 + km - 1;
+    int any_rej = 0;
+    m1 = 0;
+    for (kk = 0; kk < nchan; ++kk) reject_ob[kk] = 0;                  /* :777 */
+    for (ii = n1; ii <= n2; ++ii) {                                    /* :778 */
+      k = 0;
+      for (kk = 1; kk <= nchan; ++kk)                                  /* :780-785: integer |achan - nint(lev)| < 1e-5 */
+        if (labs((long)achan[kk - 1] - orc_nint(lev[ii - 1])) < 1e-5) { k = kk; break; }
+      if (k > 0) {                                                     /* :787 */
+        m1 = m1 + 1;
+        if (m1 > nchan) { rc = 5; break; }                             /* :789-790 */
+        indx[m1 - 1] = ii;
+        reject_ob[m1 - 1] = ob_flag[ii - 1] != 0;
+        ll[m1 - 1] = kxkt_table[(size_t)(kx[ii - 1] - 1) + (size_t)kxmax * (size_t)(kt[ii - 1] - 1)];
+        ll[m1 - 1] = abs(ll[m1 - 1]);
+        if (ll[m1 - 1] <= 0) {                                         /* :795-798 */
+          ob_flag[ii - 1] = 1;
+          reject_ob[m1 - 1] = 1;
+        }
+      }
+    }
+    if (rc) break;
+    for (kk = 0; kk < nchan; ++kk) any_rej |= reject_ob[kk];
+    if (any_rej) continue;                                             /* :801 */
+    if (m1 != nchan) continue;                                         /* :802 */
+    for (kk = 0; kk < nchan; ++kk)                                     /* :809 rdel(:,:) = del(indx(:),:) */
+      for (ir = 0; ir < nr; ++ir) rdel[kk + (size_t)nchan * ir] = del[(size_t)(indx[kk] - 1) + (size_t)nobs * ir];
+    *nprof = *nprof + 1;
+    for (kk = 1; kk <= nchan; ++kk) {                                  /* :815 */
+      l = ll[kk - 1];
+      for (ir = 1; ir <= nr; ++ir) XB(kk, l, ir) = XB(kk, l, ir) + rdel[(kk - 1) + (size_t)nchan * (ir - 1)];
+      if (tch) {                                                       /* :821-824 */
+        for (ii = 1; ii <= nchan; ++ii)
+          for (ir = 1; ir <= nr; ++ir)
+            XC(ii, kk, l, ir) = XC(ii, kk, l, ir) + rdel[(ii - 1) + (size_t)nchan * (ir - 1)] * rdel[(kk - 1) + (size_t)nchan * (ir - 1)];
+      } else {                                                         /* :826-830 */
+        for (ii = 1; ii <= nchan; ++ii)
+          XC(ii, kk, l, 1) = XC(ii, kk, l, 1) + rdel[(ii - 1)] * rdel[(kk - 1) + (size_t)nchan];
+      }
+      XN(kk, l) = XN(kk, l) + 1.0;                                     /* :832 */
+    }
+  }
+  free(indx); free(ll); free(reject_ob); free(rdel);
+  return rc;
+}
+
+/* m_gritas_grids.f:859-1008 (GrITAS_XCov_Norm_).  INTEGER m (:903); `m = n` truncates; m keeps its last value between
+ * iterations when nrmlz is false (= 1: nothing is normalised).  Returns 0 or the gritas_perror cases 1..3 as above. */
+int orc_xcov_norm(int ndim, int nr, int nrmlz, int tch, int self, int l3d, double *bias_lv, double *xcov_lv,
+                  const double *nobs_lv, int ntresh) {
+  int k1, k2, k3, l, m, i1, i2, nrr, ir;
+  double xtmp = 0.0, n;
+  if (nr > 3) return 1;
+  if (tch) { if (nr != 3) return 2; } else { if (nr != 2) return 3; }
+  nrr = tch ? 3 : 1;                                                   /* :936-937 */
+  for (k3 = 1; k3 <= nrr; ++k3) {                                      /* :938-958 */
+    m = 1;
+    for (l = 1; l <= l3d; ++l)
+      for (k2 = 1; k2 <= ndim; ++k2) {
+        n = XN(k2, l);
+        if (nrmlz) m = (int)n;
+        if (m > 1 && m >= ntresh) {
+          if (tch) XB(k2, l, k3) = XB(k2, l, k3) / m;
+          else for (ir = 1; ir <= nr; ++ir) XB(k2, l, ir) = XB(k2, l, ir) / m;
+        }
+      }
+    m = 1;
+  }
+  m = 1;
+  for (k3 = 1; k3 <= nrr; ++k3) {                                      /* :959-989 */
+    i1 = 1; i2 = 2;
+    if (nrr == 3) { i1 = k3; i2 = k3; }
+    for (l = 1; l <= l3d; ++l)
+      for (k2 = 1; k2 <= ndim; ++k2)
+        for (k1 = 1; k1 <= ndim; ++k1) {
+          n = XN(k2, l);
+          if (nrmlz) m = (int)n;
+          if (m > 1 && m >= ntresh) {
+            xtmp = XC(k1, k2, l, k3) / m;
+            if (tch) xtmp = xtmp - XB(k1, l, i1) * XB(k2, l, i2);
+            else xtmp = xtmp - 0.5 * (XB(k1, l, i1) * XB(k2, l, i2) + XB(k2, l, i1) * XB(k1, l, i2));
+          }
+          if (m > 1 && m >= ntresh) XC(k1, k2, l, k3) = m * xtmp / (m - 1);
+        }
+  }
+  if (!tch) return 0;                                                  /* :991 */
+  if (self) return 0;                                                  /* :992 */
+  {                                                                    /* :994-1002 three-cornered hat */
+    const size_t plane = (size_t)ndim * ndim * l3d;
+    size_t e;
+    for (e = 0; e < plane; ++e) {
+      const double v1 = xcov_lv[e], v2 = xcov_lv[e + plane], v3 = xcov_lv[e + 2 * plane];
+      xcov_lv[e] = 0.5 * (v1 + v2 - v3);
+      xcov_lv[e + plane] = 0.5 * (v3 + v1 - v2);
+      xcov_lv[e + 2 * plane] = 0.5 * (v2 + v3 - v1);
+    }
+  }
+  return 0;
+}
+
+/* m_gritas_grids.f:1862-2059 (GrITAS_XCov_Prs_Accum_): profiles are runs of equal sounding index ks; every
+ * sounding index met gathers ALL observations that carry it (:1973-1979), so an index that comes back later is
+ * processed once per run.  ndim = nlevs, l = 1 (:2026).  kx / kt / kxkt_table / ob_flag are arguments of the reference
+ * routine but never used.  (The reference sizes its scratch with a count that is off by one at run boundaries,
+ * :1953-1963 -- undefined behaviour there; the restatement allocates what the gather needs.)
+ * Returns 0, 1..3 as above, or 7 'could not find level' (:1990, :2012) with *bad_lev set. */
+int orc_xcov_prs_accum(int nlevs, int nobs, int nr, const double *lev, const int *ks, const double *del,
+                       const double *p1, const double *p2, int l3d, double *bias_lv, double *xcov_lv,
+                       double *nobs_lv, int *nprof, int tch, double *bad_lev) {
+  const int ndim = nlevs;
+  int n, m, np, ip, kk, ks1, ir, *uks, *kindx;
+  double *rdel;
+  if (nr > 3) return 1;
+  if (tch) { if (nr != 3) return 2; } else { if (nr != 2) return 3; }
+  *nprof = 0;
+  if (nobs <= 0) return 0;
+  *nprof = 1;                                                          /* :1942-1949 */
+  ks1 = ks[0];
+  for (n = 1; n <= nobs; ++n)
+    if (ks[n - 1] != ks1) { ks1 = ks[n - 1]; *nprof = *nprof + 1; }
+  uks = (int *)malloc(sizeof(int) * (size_t)(*nprof));
+  np = 1; ks1 = ks[0]; uks[0] = ks1;                                   /* :1952-1964 */
+  for (n = 1; n <= nobs; ++n)
+    if (ks[n - 1] != ks1) { ks1 = ks[n - 1]; np = np + 1; uks[np - 1] = ks1; }
+  kindx = (int *)malloc(sizeof(int) * (size_t)nobs);
+  rdel = (double *)malloc(sizeof(double) * (size_t)nobs * (size_t)nr);
+  for (np = 1; np <= *nprof; ++np) {                                   /* :1974 */
+    ip = 0;
+    for (n = 1; n <= nobs; ++n) {                                      /* :1977-1982 */
+      if (ks[n - 1] != uks[np - 1]) continue;
+      ip = ip + 1;
+      kindx[ip - 1] = 0;
+      for (kk = 1; kk <= nlevs; ++kk)                                  /* :2004-2013 */
+        if (lev[n - 1] <= p1[kk - 1] && lev[n - 1] > p2[kk - 1]) { kindx[ip - 1] = kk; break; }
+      if (kindx[ip - 1] == 0) {
+        if (bad_lev) *bad_lev = lev[n - 1];
+        free(uks); free(kindx); free(rdel);
+        return 7;
+      }
+      for (ir = 0; ir < nr; ++ir) rdel[(ip - 1) + (size_t)nobs * ir] = del[(n - 1) + (size_t)nobs * ir];
+    }
+    {
+      const int l = 1;                                                 /* :2026 */
+      for (n = 1; n <= ip; ++n) {                                      /* :2027 */
+        const int k1 = kindx[n - 1];
+        XN(k1, l) = XN(k1, l) + 1.0;                                   /* :2034 */
+        for (ir = 1; ir <= nr; ++ir) XB(k1, l, ir) = XB(k1, l, ir) + rdel[(n - 1) + (size_t)nobs * (ir - 1)];
+        for (m = 1; m <= ip; ++m) {                                    /* :2036 */
+          const int k2 = kindx[m - 1];
+          if (tch) {
+            for (ir = 1; ir <= nr; ++ir)
+              XC(k1, k2, l, ir) = XC(k1, k2, l, ir) + rdel[(n - 1) + (size_t)nobs * (ir - 1)] * rdel[(m - 1) + (size_t)nobs * (ir - 1)];
+          } else {
+            XC(k1, k2, l, 1) = XC(k1, k2, l, 1) + 0.5 * (rdel[(n - 1)] * rdel[(m - 1) + (size_t)nobs] + rdel[(n - 1) + (size_t)nobs] * rdel[(m - 1)]);
+          }
+        }
+      }
+    }
+  }
+  free(uks); free(kindx); free(rdel);
+  return 0;
+}

@@ -277,3 +277,64 @@ def minmax_init(g: Grids):
 def maskout(im, jm, lat, lon, maskfld, qcx):
     """m_gritas_masks.F90:137-186; qcx int32 inout, returns the number of observations excluded."""
     return lib().orc_maskout(im, jm, len(lat), *_c(np.float64, lat, lon), np.asfortranarray(maskfld, dtype=np.float64), qcx)
+
+
+# ---- channel / level cross-covariances (m_gritas_grids.f:667-1008, 1862-2059) ------------------------------
+_XC_ERR = {1: "improper dim settings", 2: "TCH setting inconsistent w/ dims", 3: "Desroziers setting inconsistent w/ dims",
+           4: "XCov_Accum: not all profiles complete, aborting ...", 5: "XCov-Accum: error in channel matching"}
+
+
+def _xc_protos():
+    L = lib()
+    if getattr(L, "_xc_ready", False):
+        return L
+    L.orc_xcov_accum.argtypes = [C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _f64p, _i32p, _i32p, _f64p, _i32p, C.c_int, C.c_int,
+                                 _i32p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.c_int]
+    L.orc_xcov_accum.restype = C.c_int
+    L.orc_xcov_norm.argtypes = [C.c_int] * 6 + [_f64p, _f64p, _f64p, C.c_int]
+    L.orc_xcov_norm.restype = C.c_int
+    L.orc_xcov_prs_accum.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p,
+                                     C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
+    L.orc_xcov_prs_accum.restype = C.c_int
+    L._xc_ready = True
+    return L
+
+
+def xcov_alloc(ndim, l3d, nr):
+    return (np.zeros((ndim, l3d, nr), order="F"), np.zeros((ndim, ndim, l3d, nr), order="F"), np.zeros((ndim, l3d), order="F"))
+
+
+def xcov_accum(km, achan, lev, kx, kt, del_, kxkt_table, ob_flag, l3d, bias_lv, xcov_lv, nobs_lv, tch):
+    """GrITAS_XCov_Accum_ (m_gritas_grids.f:667-848).  ob_flag int32 inout.  Returns nprof."""
+    L = _xc_protos()
+    table = np.asfortranarray(kxkt_table, dtype=np.int32)
+    d = np.asfortranarray(del_, dtype=np.float64)
+    nprof = C.c_int(0)
+    rc = L.orc_xcov_accum(km, len(achan), np.ascontiguousarray(achan, dtype=np.int32), len(lev), d.shape[1],
+                          *_c(np.float64, lev), *_c(np.int32, kx, kt), d, table, table.shape[0], table.shape[1], ob_flag, l3d,
+                          bias_lv, xcov_lv, nobs_lv, C.byref(nprof), 1 if tch else 0)
+    if rc:
+        raise ValueError(_XC_ERR[rc])
+    return nprof.value
+
+
+def xcov_norm(nr, nrmlz, tch, self_, l3d, bias_lv, xcov_lv, nobs_lv, ntresh=0):
+    """GrITAS_XCov_Norm_ (m_gritas_grids.f:859-1008), in place."""
+    rc = _xc_protos().orc_xcov_norm(bias_lv.shape[0], nr, 1 if nrmlz else 0, 1 if tch else 0, 1 if self_ else 0, l3d, bias_lv,
+                                    xcov_lv, nobs_lv, ntresh)
+    if rc:
+        raise ValueError(_XC_ERR[rc])
+
+
+def xcov_prs_accum(nlevs, lev, ks, del_, p1, p2, l3d, bias_lv, xcov_lv, nobs_lv, tch):
+    """GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-2059).  Returns nprof; raises LevelMiss."""
+    L = _xc_protos()
+    d = np.asfortranarray(del_, dtype=np.float64)
+    nprof, bad = C.c_int(0), C.c_double(0.0)
+    rc = L.orc_xcov_prs_accum(nlevs, len(lev), d.shape[1], *_c(np.float64, lev), *_c(np.int32, ks), d, *_c(np.float64, p1, p2), l3d,
+                              bias_lv, xcov_lv, nobs_lv, C.byref(nprof), 1 if tch else 0, C.byref(bad))
+    if rc == 7:
+        raise LevelMiss(bad.value, -1)
+    if rc:
+        raise ValueError(_XC_ERR[rc])
+    return nprof.value
