@@ -268,8 +268,8 @@ struct gritas_b200_ctx {
   cudaStream_t comm_stream = nullptr, fin_stream = nullptr;
   cudaEvent_t ev_acc[NCHUNK] = {}, ev_red[NCHUNK] = {}, ev_fin = nullptr;
   // pre-sort scratch (gritas_b200_presort)
-  void *ps_cols = nullptr, *ps_key[2] = {}, *ps_idx[2] = {};
-  size_t ps_cols_cap = 0, ps_key_cap[2] = {}, ps_idx_cap[2] = {};
+  void *ps_cols = nullptr, *ps_key[2] = {}, *ps_idx[2] = {}, *ps_sorted = nullptr;
+  size_t ps_cols_cap = 0, ps_key_cap[2] = {}, ps_idx_cap[2] = {}, ps_sorted_cap = 0;
   // finalize scratch (reference-layout planes on the device)
   double *out = nullptr;
   size_t out_cap = 0;
@@ -1030,7 +1030,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
         if (p) cudaIpcCloseMemHandle(p);
   for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red, (void *)h->fill_snap, (void *)h->bar_buf})
     if (p) cudaFree(p);
-  for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1]})
+  for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1], h->ps_sorted})
     if (p) cudaFree(p);
   for (auto &db : h->det) {
     if (db.st) { cudaStreamSynchronize(db.st); cudaStreamDestroy(db.st); }
@@ -1583,6 +1583,59 @@ int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, 
   return finalize_to(h, 1, 0, 0, u, nullptr);
 }
 
+// Scorecard of one synoptic time (scores1_ / scores2_ / ave_nomiss, m_gritas_grids.f:1526-1826, minus the CSV writing of the
+// un-vendored m_obs_stats): Norm with nrmlz = .true. (:1632-1634) on the device, then the regional averages; only the
+// (mregs, km, l2d + l3d, 3) real(4) table crosses PCIe, the finalized grids stay on the device.
+int gritas_b200_scores(gritas_b200_handle h, int nregs, const int32_t *regindx, int lon0, int lon1, float *collect_stats) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (h->g.nr != 1) return fail(h, GRITAS_B200_ERR_NR, "GrITAS_scores_: incorrec number of residuals, aborting ...");   // :1704-1706
+  if (nregs < 1 || nregs > 64 || !regindx || !collect_stats) return fail(h, GRITAS_B200_ERR_ARG, "scores: bad arguments");
+  for (int r = 0; r < nregs; ++r)
+    if (regindx[2 * r] < 1 || regindx[2 * r + 1] > h->g.jm) return fail(h, GRITAS_B200_ERR_ARG, "scores: region %d outside the grid", r + 1);
+  if (lon0 < 1 || lon1 > h->g.im) return fail(h, GRITAS_B200_ERR_ARG, "scores: longitude range outside the grid");
+  if ((rc = settle(h, fused_norm_ok(h), nullptr))) return rc;
+  double *const u[10] = {};
+  const double *d[10] = {};
+  if ((rc = finalize_to(h, 0, 1, -1, u, d))) return rc;
+  const size_t total = (size_t)nregs * h->g.km * (h->g.l2d + h->g.l3d) * 3;
+  // scratch after the output planes: region table + result
+  void *scr = nullptr;
+  CU(cudaMalloc(&scr, sizeof(int) * 2 * nregs + sizeof(float) * total + 64));
+  int *d_reg = (int *)scr;
+  float *d_out = (float *)((char *)scr + ((sizeof(int) * 2 * nregs + 15) & ~(size_t)15));
+  CU(cudaMemcpyAsync(d_reg, regindx, sizeof(int) * 2 * nregs, cudaMemcpyHostToDevice, h->compute));
+  if (mem_kind(collect_stats) == 2) CU(cudaMemcpyAsync(d_out, collect_stats, sizeof(float) * total, cudaMemcpyDeviceToDevice, h->compute));
+  else CU(cudaMemcpyAsync(d_out, collect_stats, sizeof(float) * total, cudaMemcpyHostToDevice, h->compute));   // untouched entries keep the caller's values
+  const Planes3 a2 = {{d[0], d[1], d[2]}}, a3 = {{d[5], d[6], d[7]}};
+  k_scores<<<(int)((total + 127) / 128), 128, 0, h->compute>>>(h->g, a2, a3, d[4], d[9], d_reg, nregs, lon0, lon1, d_out);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(collect_stats, d_out, sizeof(float) * total, cudaMemcpyDefault, h->compute));
+  h->d2h += sizeof(float) * total;
+  CU(cudaStreamSynchronize(h->compute));
+  CU(cudaFree(scr));
+  return 0;
+}
+
+// Region rows of the scorecard as init_ derives them (m_gritas_grids.f:163-175): for every region the last latitude row
+// at or below its southern bound and the last one at or below its northern bound (glat(j) = -90 + (j-1) dLat).
+int gritas_b200_score_regions(int jm, int nregs, const double *regbounds, int32_t *regindx) {
+  if (jm < 2 || nregs < 1 || !regbounds || !regindx) return 1;
+  const double dlat = 180.0 / (double)(jm - 1);
+  for (int i = 0; i < nregs; ++i) {
+    regindx[2 * i] = 0;
+    regindx[2 * i + 1] = 0;
+    for (int j = 1; j <= jm; ++j) {
+      const double glat = -90.0 + (double)(j - 1) * dlat;
+      if (glat <= regbounds[2 * i]) regindx[2 * i] = j;
+      if (glat > 0.0 && glat <= regbounds[2 * i + 1]) regindx[2 * i + 1] = j;
+      if (glat < 0.0 && glat <= regbounds[2 * i + 1]) regindx[2 * i + 1] = j;
+    }
+  }
+  return 0;
+}
+
 // GrITAS_MinMax results (m_gritas_grids.f:1019-1167): minv (AMISS where nothing fell), maxv (-AMISS where
 // nothing fell; gritas.f:997-1000 turns those into AMISS afterwards) and the counts, reference layout.
 int gritas_b200_get_minmax(gritas_b200_handle h, double *minv_2d, double *maxv_2d, double *nobs_2d, double *minv_3d,
@@ -1661,6 +1714,43 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
   return mark_main(h);
 }
 
+// IndexSet + the eight stable sorts on device-resident columns (order: qcexcl lat lon lev time kt ks kx); *fin = the
+// permutation (0-based) in one of the handle's index buffers.
+static int presort_core(gritas_b200_handle h, int nobs, const void *const dev[8], int **fin_out) {
+  const size_t n = (size_t)nobs;
+  const size_t esz[8] = {4, 8, 8, 8, 4, 4, 4, 4};
+  cudaStream_t sm = h->compute;
+  int rc;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = grow_dev(h, &h->ps_key[b], &h->ps_key_cap[b], 8 * n))) return rc;
+    if ((rc = grow_dev(h, &h->ps_idx[b], &h->ps_idx_cap[b], 4 * n))) return rc;
+  }
+  size_t t32 = 0, t64 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t32, (unsigned *)nullptr, (unsigned *)nullptr, (int *)nullptr, (int *)nullptr, nobs, 0, 32, sm);
+  cub::DeviceRadixSort::SortPairs(nullptr, t64, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int *)nullptr,
+                                  (int *)nullptr, nobs, 0, 64, sm);
+  if ((rc = grow_dev(h, &h->cub_tmp, &h->cub_cap, std::max(t32, t64)))) return rc;
+  const int nblk = grid_for(n, 256, 8);
+  int cur = 0;
+  k_iota<<<nblk, 256, 0, sm>>>((int *)h->ps_idx[0], nobs);
+  for (int p = 0; p < 8; ++p) {
+    int *idx = (int *)h->ps_idx[cur], *idx2 = (int *)h->ps_idx[cur ^ 1];
+    size_t tmp = h->cub_cap;
+    if (esz[p] == 4) {
+      k_sortkey_i32<<<nblk, 256, 0, sm>>>((const int *)dev[p], idx, (unsigned *)h->ps_key[0], nobs);
+      CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, (unsigned *)h->ps_key[0], (unsigned *)h->ps_key[1], idx, idx2, nobs, 0, 32, sm));
+    } else {
+      k_sortkey_f64<<<nblk, 256, 0, sm>>>((const double *)dev[p], idx, (unsigned long long *)h->ps_key[0], nobs);
+      CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, (unsigned long long *)h->ps_key[0], (unsigned long long *)h->ps_key[1], idx,
+                                         idx2, nobs, 0, 64, sm));
+    }
+    cur ^= 1;
+    h->launches += 1 + (esz[p] == 4 ? 9 : 17);   // key kernel + radix passes (approx.)
+  }
+  *fin_out = (int *)h->ps_idx[cur];
+  return 0;
+}
+
 // ---- pre-sort (gritas.f:499-508) ------------------------------------------------------------------
 // IndexSet followed by eight stable ascending IndexSorts -- qcexcl, lat, lon, lev, time, kt, ks, kx, in this order, so
 // that the final order is (kx, ks, kt, time, lev, lon, lat, qcexcl, original position).  The reference spends seconds
@@ -1713,33 +1803,10 @@ int gritas_b200_presort(gritas_b200_handle h, int nobs, const int32_t *qcexcl, c
     dev[c] = d;
     off += (esz[c] * n + 15) & ~(size_t)15;
   }
-  for (int b = 0; b < 2; ++b) {
-    if ((rc = grow_dev(h, &h->ps_key[b], &h->ps_key_cap[b], 8 * n))) return rc;
-    if ((rc = grow_dev(h, &h->ps_idx[b], &h->ps_idx_cap[b], 4 * n))) return rc;
-  }
-  size_t t32 = 0, t64 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, t32, (unsigned *)nullptr, (unsigned *)nullptr, (int *)nullptr, (int *)nullptr, nobs, 0, 32, sm);
-  cub::DeviceRadixSort::SortPairs(nullptr, t64, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int *)nullptr,
-                                  (int *)nullptr, nobs, 0, 64, sm);
-  if ((rc = grow_dev(h, &h->cub_tmp, &h->cub_cap, std::max(t32, t64)))) return rc;
+  int *fin = nullptr;
+  if ((rc = presort_core(h, nobs, dev, &fin))) return rc;
+  const int cur = (fin == (int *)h->ps_idx[0]) ? 0 : 1;
   const int nblk = grid_for(n, 256, 8);
-  int cur = 0;
-  k_iota<<<nblk, 256, 0, sm>>>((int *)h->ps_idx[0], nobs);
-  for (int p = 0; p < 8; ++p) {
-    int *idx = (int *)h->ps_idx[cur], *idx2 = (int *)h->ps_idx[cur ^ 1];
-    size_t tmp = h->cub_cap;
-    if (esz[p] == 4) {
-      k_sortkey_i32<<<nblk, 256, 0, sm>>>((const int *)dev[p], idx, (unsigned *)h->ps_key[0], nobs);
-      CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, (unsigned *)h->ps_key[0], (unsigned *)h->ps_key[1], idx, idx2, nobs, 0, 32, sm));
-    } else {
-      k_sortkey_f64<<<nblk, 256, 0, sm>>>((const double *)dev[p], idx, (unsigned long long *)h->ps_key[0], nobs);
-      CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, (unsigned long long *)h->ps_key[0], (unsigned long long *)h->ps_key[1], idx,
-                                         idx2, nobs, 0, 64, sm));
-    }
-    cur ^= 1;
-    h->launches += 1 + (esz[p] == 4 ? 9 : 17);   // key kernel + radix passes (approx.)
-  }
-  int *fin = (int *)h->ps_idx[cur];
   if (mem_kind(is) == 2) {
     k_add_base<<<nblk, 256, 0, sm>>>(fin, is, index_base, nobs);
   } else {
@@ -1752,6 +1819,80 @@ int gritas_b200_presort(gritas_b200_handle h, int nobs, const int32_t *qcexcl, c
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(sm));
   return 0;
+}
+
+// The whole per-file preamble of gritas.f on the device: the 8-key pre-sort (gritas.f:499-508), the column gathers
+// (gritas.f:510-523), residual selection (gritas.f:562-704), the QC filter (gritas.f:710-739) and GrITAS_Accum_.  Columns come
+// in as ODS_Get left them (unsorted, host or device); they are copied to the device once, sorted and gathered there, and the
+// accumulate kernels read the gathered copies.  In deterministic mode the sums are then formed in the reference's order.
+// ob_flag_out (may be NULL) is in SORTED order, as the reference's ob_flag is; is_out (may be NULL) receives the 1-based
+// permutation.
+int gritas_b200_accum_odsx_sorted(gritas_b200_handle h, int nobs, const gritas_b200_ods *o, const int32_t *ks, int iopt, int options,
+                                  int scale_res, int ioptn, int t1, int t2, double lona, double lonb, int x_passive, int x_pre_bad,
+                                  int32_t *ob_flag_out, int32_t *is_out, double *bad_lev) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!o || nobs < 0) return fail(h, GRITAS_B200_ERR_ARG, "accum_odsx_sorted: bad arguments");
+  if (nobs == 0) return gritas_b200_accum_odsx(h, 0, o, iopt, options, scale_res, ioptn, t1, t2, lona, lonb, x_passive, x_pre_bad, ob_flag_out, bad_lev);
+  if (!o->lat || !o->lon || !o->lev || !o->time || !o->kt || !o->kx || !o->qcexcl || !ks)
+    return fail(h, GRITAS_B200_ERR_ARG, "accum_odsx_sorted: the pre-sort needs qcexcl, lat, lon, lev, time, kt, ks, kx");
+  const size_t n = (size_t)nobs;
+  // the accumulate of an earlier call may still read the gathered columns of that call
+  if ((rc = join_workers(h))) return rc;
+  CU(cudaStreamSynchronize(h->compute));
+  const void *fsrc[8] = {o->lat, o->lon, o->lev, o->obs, o->omf, o->oma, o->xvec, o->xm};
+  const void *isrc[5] = {o->time, o->kt, o->kx, o->qcexcl, ks};
+  const size_t f8 = (8 * n + 255) & ~(size_t)255, i4 = (4 * n + 255) & ~(size_t)255;
+  size_t need_in = 0, need_out = 0;
+  for (const void *p : fsrc) if (p) { need_out += f8; if (mem_kind(p) != 2) need_in += f8; }
+  for (const void *p : isrc) if (p) { need_out += i4; if (mem_kind(p) != 2) need_in += i4; }
+  if ((rc = grow_dev(h, &h->ps_cols, &h->ps_cols_cap, need_in + 256))) return rc;
+  if ((rc = grow_dev(h, &h->ps_sorted, &h->ps_sorted_cap, need_out + 256))) return rc;
+  const void *fdev[8] = {}, *idev[5] = {};
+  size_t off = 0;
+  auto upload = [&](const void *p, size_t bytes, size_t slot, const void **dev) -> int {
+    if (!p) return 0;
+    if (mem_kind(p) == 2) { *dev = p; return 0; }
+    void *d = (char *)h->ps_cols + off;
+    CU(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, h->compute));
+    h->h2d += bytes;
+    *dev = d;
+    off += slot;
+    return 0;
+  };
+  for (int q = 0; q < 8; ++q) if ((rc = upload(fsrc[q], 8 * n, f8, &fdev[q]))) return rc;
+  for (int q = 0; q < 5; ++q) if ((rc = upload(isrc[q], 4 * n, i4, &idev[q]))) return rc;
+  const void *keys[8] = {idev[3], fdev[0], fdev[1], fdev[2], idev[0], idev[1], idev[4], idev[2]};   // qcexcl lat lon lev time kt ks kx
+  int *fin = nullptr;
+  if ((rc = presort_core(h, nobs, keys, &fin))) return rc;
+  GatherCols g = {};
+  double *fs[8] = {};
+  int *is5[5] = {};
+  size_t so = 0;
+  for (int q = 0; q < 8; ++q)
+    if (fdev[q]) { fs[q] = (double *)((char *)h->ps_sorted + so); so += f8; g.f_src[g.nf] = (const double *)fdev[q]; g.f_dst[g.nf] = fs[q]; ++g.nf; }
+  for (int q = 0; q < 5; ++q)
+    if (idev[q]) { is5[q] = (int *)((char *)h->ps_sorted + so); so += i4; g.i_src[g.ni] = (const int *)idev[q]; g.i_dst[g.ni] = is5[q]; ++g.ni; }
+  const int nblk = grid_for(n, 256, 8);
+  k_gather_cols<<<nblk, 256, 0, h->compute>>>(g, fin, nobs);
+  h->launches++;
+  if (is_out) {
+    const int cur = (fin == (int *)h->ps_idx[0]) ? 0 : 1;
+    if (mem_kind(is_out) == 2) {
+      k_add_base<<<nblk, 256, 0, h->compute>>>(fin, is_out, 1, nobs);
+    } else {
+      int *out = (int *)h->ps_idx[cur ^ 1];
+      k_add_base<<<nblk, 256, 0, h->compute>>>(fin, out, 1, nobs);
+      CU(cudaMemcpyAsync(is_out, out, 4 * n, cudaMemcpyDeviceToHost, h->compute));
+      h->d2h += 4 * n;
+    }
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  if ((rc = mark_main(h))) return rc;           // the accumulate (possibly on a worker stream) starts after the gathers
+  gritas_b200_ods sorted = {fs[0], fs[1], fs[2], fs[3], fs[4], fs[5], fs[6], fs[7], is5[0], is5[1], is5[2], is5[3]};
+  return gritas_b200_accum_odsx(h, nobs, &sorted, iopt, options, scale_res, ioptn, t1, t2, lona, lonb, x_passive, x_pre_bad,
+                                ob_flag_out, bad_lev);
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------------------

@@ -1509,6 +1509,20 @@ k_sortkey_f64(const double *__restrict__ col, const int *__restrict__ idx, unsig
     key[i] = (unsigned long long)f64_order_key(x) ^ 0x8000000000000000ull;
   }
 }
+// The column gathers of gritas.f:510-523: dst(i) = src(is(i)) for up to 8 fp64 and 5 int32 columns in one pass.
+struct GatherCols {
+  const double *f_src[8]; double *f_dst[8];
+  const int *i_src[5]; int *i_dst[5];
+  int nf, ni;
+};
+__global__ void __launch_bounds__(256)
+k_gather_cols(const GatherCols c, const int *__restrict__ is, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = is[i];
+    for (int q = 0; q < c.nf; ++q) c.f_dst[q][i] = c.f_src[q][j];
+    for (int q = 0; q < c.ni; ++q) c.i_dst[q][i] = c.i_src[q][j];
+  }
+}
 __global__ void __launch_bounds__(256)
 k_add_base(const int *__restrict__ idx, int *__restrict__ out, int base, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = idx[i] + base;
@@ -1526,6 +1540,39 @@ k_zero_dirty_tiles(double *__restrict__ acc, size_t ndouble, int rs, const Stage
     const size_t n = min(((size_t)1 << sg.tile_shift) * (size_t)rs, ndouble - first);
     double2 *a2 = reinterpret_cast<double2 *>(acc + first);
     for (size_t e = threadIdx.x; e < (n >> 1); e += blockDim.x) a2[e] = make_double2(0.0, 0.0);
+  }
+}
+
+// Scorecard (m_gritas_grids.f:1671-1826, scores2_ + ave_nomiss): regional averages of the finalized mean / rms / stdv
+// grids over the boxes that are not AMISS.  One thread per (region, level, variable, statistic) walks its region in the
+// reference's order (latitude outer, longitude inner) and sums in fp64 exactly as ave_nomiss does; the result is the
+// reference's real(4) collect_stats(mregs, km, l2d + l3d, nevals) entry.  Variables: the l2d surface grids first (level
+// slot 1 only), then the l3d upper-air grids (:1718-1731).
+struct Planes3 { const double *p[3]; };    // mean, rms, stdv
+__global__ void __launch_bounds__(128)
+k_scores(const GridDesc g, const Planes3 s2, const Planes3 s3, const double *__restrict__ nobs_2d,
+         const double *__restrict__ nobs_3d, const int *__restrict__ regindx, int nregs, int lon0, int lon1,
+         float *__restrict__ collect) {
+  const int nvar = g.l2d + g.l3d, total = nregs * g.km * nvar * 3;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int mr = e % nregs, kk = (e / nregs) % g.km, nv = (e / (nregs * g.km)) % nvar, ne = e / (nregs * g.km * nvar);
+    const bool surf = nv < g.l2d;
+    if (surf && kk != 0) continue;                          // collect_stats(mr,1,nv,ne) only; the other levels stay as they were
+    const size_t plane = (size_t)g.im * g.jm;
+    const double *x = surf ? s2.p[ne] + plane * nv : s3.p[ne] + plane * ((size_t)kk + (size_t)g.km * (nv - g.l2d));
+    const double *nb = surf ? nobs_2d + plane * nv : nobs_3d + plane * ((size_t)kk + (size_t)g.km * (nv - g.l2d));
+    double add = -AMISS, counter = 0.0;                     // :1806-1807
+    const int j0 = regindx[2 * mr], j1 = regindx[2 * mr + 1];
+    for (int jj = j0; jj <= j1; ++jj)
+      for (int ii = lon0; ii <= lon1; ++ii) {
+        const size_t o = (size_t)(ii - 1) + (size_t)g.im * (size_t)(jj - 1);
+        const double v = x[o];
+        if (nb[o] >= 0.0 && fabs(__dsub_rn(v, AMISS)) > 0.01) {   // threshold = 0 (:1803), :1810
+          add = (add == -AMISS) ? v : __dadd_rn(add, v);
+          counter = __dadd_rn(counter, 1.0);
+        }
+      }
+    collect[e] = (float)((add == -AMISS) ? AMISS : __ddiv_rn(add, counter));   // :1820-1824, stored as real(4)
   }
 }
 

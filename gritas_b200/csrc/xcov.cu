@@ -28,8 +28,6 @@
 
 namespace {
 
-constexpr double XC_AMISS = 1.0e15;
-
 struct XcDesc {
   int km, nchan, l3d, nr, tch;
   int kxmax, ktmax;

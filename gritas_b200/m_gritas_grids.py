@@ -192,6 +192,21 @@ class Grids:
                                                 cabi.ptr(ob_flag_out, np.int32), C.byref(bad))
         self._check(rc, bad)
 
+    def accum_odsx_sorted(self, ods, iopt, options=0, scale_res=0, ioptn=None, t1=0, t2=-1, lona=-999.0, lonb=999.0, x_passive=7,
+                          x_pre_bad=1, ob_flag_out=None, is_out=None):
+        """gritas.f:499-523 (pre-sort + gathers) + 562-739 + GrITAS_Accum_ on the device, from unsorted ODS columns (needs ks)."""
+        cols = cabi.OdsCols()
+        dt = {"time": np.int32, "kt": np.int32, "kx": np.int32, "qcexcl": np.int32}
+        for k, _ in cabi.OdsCols._fields_:
+            v = ods.get(k)
+            setattr(cols, k, cabi.ptr(v, dt.get(k, np.float64)) if v is not None else None)
+        bad = C.c_double(0.0)
+        rc = cabi.load().gritas_b200_accum_odsx_sorted(self._h, int(ods["lat"].shape[0]), C.byref(cols), cabi.ptr(ods["ks"], np.int32),
+                                                       iopt, options, scale_res, iopt if ioptn is None else ioptn, t1, t2, lona, lonb,
+                                                       x_passive, x_pre_bad, cabi.ptr(ob_flag_out, np.int32), cabi.ptr(is_out, np.int32),
+                                                       C.byref(bad))
+        self._check(rc, bad)
+
     def sync(self):
         bad = C.c_double(0.0)
         self._check(cabi.load().gritas_b200_sync(self._h, C.byref(bad)), bad)
@@ -285,6 +300,30 @@ class Grids:
             maskfld = np.asfortranarray(maskfld, dtype=np.float64)
             assert maskfld.shape == (self.im, self.jm)
         self._check(cabi.load().gritas_b200_set_mask(self._h, cabi.ptr(maskfld, np.float64)))
+
+    # ---- scorecard (m_gritas_grids.f:1526-1826) --------------------------------------------
+    REGNAMES = ("global", "n.hem", "tropics", "s.hem")                       # m_gritas_grids.f:58
+    REGBOUNDS = ((-90.0, 90.0), (20.0, 80.0), (-20.0, 20.0), (-80.0, -20.0))  # :146-157
+
+    def score_regions(self, regbounds=None):
+        """regindx(2, mregs) as init_ derives it (m_gritas_grids.f:163-175)."""
+        rb = np.asfortranarray(np.array(self.REGBOUNDS if regbounds is None else regbounds, dtype=np.float64).T)
+        out = np.zeros((2, rb.shape[1]), np.int32, order="F")
+        rc = cabi.load().gritas_b200_score_regions(self.jm, rb.shape[1], rb.ctypes.data, out.ctypes.data)
+        if rc:
+            raise ValueError(f"gritas_b200_score_regions rc={rc}")
+        return out
+
+    def GrITAS_Scores(self, regindx=None, collect_stats=None):
+        """scores2_ on the current accumulators (Norm with nrmlz = .true. + ave_nomiss per region / level / variable);
+        returns collect_stats(mregs, km, l2d + l3d, nevals = 3) real(4).  The handle must have nr = 1 (:1704-1706)."""
+        if self.nr != 1:
+            raise GritasPerror("GrITAS_scores_: incorrec number of residuals, aborting ...", 98)
+        reg = self.score_regions() if regindx is None else np.asfortranarray(regindx, dtype=np.int32)
+        if collect_stats is None:
+            collect_stats = np.zeros((reg.shape[1], self.km, self.l2d + self.l3d, 3), np.float32, order="F")
+        self._check(cabi.load().gritas_b200_scores(self._h, reg.shape[1], reg.ctypes.data, 1, self.im, collect_stats.ctypes.data))
+        return collect_stats
 
     def alloc_grids(self, nr=None, pinned=False):
         """Host arrays shaped like gritas.f:336-348, zero-initialised (gritas.f:352-363)."""

@@ -199,6 +199,21 @@ int gritas_b200_norm_device(gritas_b200_handle h, int nrmlz, int ntresh, const d
 int gritas_b200_get_raw(gritas_b200_handle h, double *bias_2d, double *rtms_2d, double *xcov_2d, double *nobs_2d,
                         double *bias_3d, double *rtms_3d, double *xcov_3d, double *nobs_3d);
 
+/*
+ * Scorecard of one synoptic time: replaces scores2_ + ave_nomiss (m_gritas_grids.f:1671-1826) and, together with
+ * gritas_b200_reset + gritas_b200_accum on a scratch handle (nr = 1), the Accum + Norm of scores1_ (:1619-1634); the CSV
+ * writing through the un-vendored m_obs_stats stays with the caller.  Finalizes with nrmlz = .true. on the device and
+ * averages mean / rms / stdv over every region's boxes that are not AMISS, in the reference's summation order.
+ *   regindx (2, nregs) first / last latitude row of each region, 1-based (init_, m_gritas_grids.f:163-175:
+ *           gritas_b200_score_regions derives them from regbounds (2, nregs) exactly as init_ does);
+ *   lon0, lon1  the longitude slot lonindx(:,1) = (1, im) (:180-181);
+ *   collect_stats (nregs, km, l2d + l3d, 3) real(4), column-major: surface variables first, level slot 1 only
+ *           (entries the reference leaves untouched are left untouched here).
+ * Only that table is copied to the host; the handle's accumulation state is unchanged.
+ */
+int gritas_b200_scores(gritas_b200_handle h, int nregs, const int32_t *regindx, int lon0, int lon1, float *collect_stats);
+int gritas_b200_score_regions(int jm, int nregs, const double *regbounds, int32_t *regindx);
+
 /* Replaces GrITAS_MinMax_ (m_gritas_grids.f:1019-1167) together with gritas_b200_accum on a handle created with
  * GRITAS_B200_FLAG_MINMAX: minv (AMISS where empty), maxv (-AMISS where empty, gritas.f:997-1000 flips those)
  * and the counts, reference layout (im,jm,l2d) / (im,jm,km,l3d). */
@@ -227,6 +242,17 @@ int gritas_b200_add_raw(gritas_b200_handle h, const double *bias_2d, const doubl
 int gritas_b200_presort(gritas_b200_handle h, int nobs, const int32_t *qcexcl, const double *lat, const double *lon,
                         const double *lev, const int32_t *time, const int32_t *kt, const int32_t *ks, const int32_t *kx,
                         int index_base, int32_t *is);
+
+/*
+ * The whole per-file preamble of gritas.f in one call: the pre-sort (gritas.f:499-508), the column gathers that follow it
+ * (gritas.f:510-523), residual selection, QC filter and GrITAS_Accum_ as gritas_b200_accum_odsx.  `ods` holds the columns as
+ * ODS_Get left them (unsorted), ks the sounding index column.  Nothing is sorted or gathered on the host.  In deterministic
+ * mode the sums are formed in exactly the order the reference's sorted loop forms them.  ob_flag_out (may be NULL) is in
+ * sorted order like the reference's ob_flag; is_out (may be NULL) receives the 1-based permutation `is`.
+ */
+int gritas_b200_accum_odsx_sorted(gritas_b200_handle h, int nobs, const gritas_b200_ods *ods, const int32_t *ks, int iopt,
+                                  int options, int scale_res, int ioptn, int t1, int t2, double lona, double lonb,
+                                  int x_passive, int x_pre_bad, int32_t *ob_flag_out, int32_t *is_out, double *bad_lev);
 
 /* Multi-GPU (one process per GPU): partial count / sum / sum-of-squares grids are summed over
  * all ranks with one NCCL all-reduce before _norm.  The reference is single-process; this is new. */

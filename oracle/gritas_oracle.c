@@ -855,3 +855,65 @@ int orc_xcov_prs_accum(int nlevs, int nobs, int nr, const double *lev, const int
   free(uks); free(kindx); free(rdel);
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Scorecard reductions.  m_gritas_grids.f:163-175 (init_): first / last latitude row of a region. */
+void orc_score_regions(int jm, int nregs, const double *regbounds, int *regindx) {
+  const double dlat = 180.0 / (double)(jm - 1);
+  int i, j;
+  for (i = 0; i < nregs; ++i) {
+    regindx[2 * i] = 0; regindx[2 * i + 1] = 0;
+    for (j = 1; j <= jm; ++j) {
+      const double glat = ORC_LATMIN + (j - 1) * dlat;              /* :136-138 */
+      if (glat <= regbounds[2 * i]) regindx[2 * i] = j;
+      if (glat > 0.0 && glat <= regbounds[2 * i + 1]) regindx[2 * i + 1] = j;
+      if (glat < 0.0 && glat <= regbounds[2 * i + 1]) regindx[2 * i + 1] = j;
+    }
+  }
+}
+
+/* m_gritas_grids.f:1797-1826 (ave_nomiss): mean of x over the box range where nobs >= 0 and x is not AMISS. */
+static double orc_ave_nomiss(const double *x, const double *nobs, int im, const int *xregion, const int *yregion) {
+  const double threshold = 0.0;
+  double add = -ORC_AMISS, counter = 0.0;
+  int ii, jj;
+  for (jj = yregion[0]; jj <= yregion[1]; ++jj)
+    for (ii = xregion[0]; ii <= xregion[1]; ++ii) {
+      const size_t o = (size_t)(ii - 1) + (size_t)im * (size_t)(jj - 1);
+      if (nobs[o] >= threshold && fabs(x[o] - ORC_AMISS) > 0.01) {
+        if (add == -ORC_AMISS) add = x[o]; else add = add + x[o];
+        counter = counter + 1.0;
+      }
+    }
+  return add == -ORC_AMISS ? ORC_AMISS : add / counter;
+}
+
+/* m_gritas_grids.f:1671-1795 (scores2_), nr = 1, nt = 1: collect_stats(nregs, km, nv2d + nv3d, nevals) real(4);
+ * type_stats = mean, rms, stdv (:64); surface variables first, level slot 1 only. */
+void orc_scores2(int im, int jm, int km, int nv2d, int nv3d, int nregs, const int *regindx, const int *lonindx,
+                 const double *bias_2d, const double *rtms_2d, const double *stdv_2d, const double *nobs_2d,
+                 const double *bias_3d, const double *rtms_3d, const double *stdv_3d, const double *nobs_3d,
+                 float *collect_stats) {
+  const size_t plane = (size_t)im * jm;
+  const int nvar = nv2d + nv3d;
+  int ne, mr, lm, kk, nv;
+  for (ne = 1; ne <= 3; ++ne) {
+    const double *s2 = ne == 1 ? bias_2d : (ne == 2 ? rtms_2d : stdv_2d);
+    const double *s3 = ne == 1 ? bias_3d : (ne == 2 ? rtms_3d : stdv_3d);
+    for (mr = 1; mr <= nregs; ++mr) {
+      nv = 0;
+      for (lm = 1; lm <= nv2d; ++lm) {
+        nv = nv + 1;
+        collect_stats[(mr - 1) + (size_t)nregs * (0 + (size_t)km * ((nv - 1) + (size_t)nvar * (ne - 1)))] =
+            (float)orc_ave_nomiss(s2 + plane * (lm - 1), nobs_2d + plane * (lm - 1), im, lonindx, regindx + 2 * (mr - 1));
+      }
+      for (lm = 1; lm <= nv3d; ++lm) {
+        nv = nv + 1;
+        for (kk = 1; kk <= km; ++kk)
+          collect_stats[(mr - 1) + (size_t)nregs * ((kk - 1) + (size_t)km * ((nv - 1) + (size_t)nvar * (ne - 1)))] =
+              (float)orc_ave_nomiss(s3 + plane * ((kk - 1) + (size_t)km * (lm - 1)), nobs_3d + plane * ((kk - 1) + (size_t)km * (lm - 1)),
+                                    im, lonindx, regindx + 2 * (mr - 1));
+      }
+    }
+  }
+}

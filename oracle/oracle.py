@@ -338,3 +338,32 @@ def xcov_prs_accum(nlevs, lev, ks, del_, p1, p2, l3d, bias_lv, xcov_lv, nobs_lv,
     if rc:
         raise ValueError(_XC_ERR[rc])
     return nprof.value
+
+
+# ---- scorecard (m_gritas_grids.f:163-175, 1671-1826) ------------------------------------------------------------
+REGBOUNDS = ((-90.0, 90.0), (20.0, 80.0), (-20.0, 20.0), (-80.0, -20.0))   # global, n.hem, tropics, s.hem (:58, :146-157)
+
+
+def score_regions(jm, regbounds=REGBOUNDS):
+    L = lib()
+    L.orc_score_regions.argtypes = [C.c_int, C.c_int, _f64p, _i32p]
+    L.orc_score_regions.restype = None
+    rb = np.asfortranarray(np.array(regbounds, dtype=np.float64).T)
+    out = np.zeros((2, rb.shape[1]), np.int32, order="F")
+    L.orc_score_regions(jm, rb.shape[1], rb, out)
+    return out
+
+
+def scores2(g, regindx):
+    """scores2_ on finalized grids (nr = 1) -> collect_stats(mregs, km, l2d + l3d, 3) float32."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="F_CONTIGUOUS")
+    L.orc_scores2.argtypes = [C.c_int] * 6 + [_i32p, _i32p] + [_f64p] * 8 + [f32p]
+    L.orc_scores2.restype = None
+    nreg = regindx.shape[1]
+    out = np.zeros((nreg, g.km, g.l2d + g.l3d, 3), np.float32, order="F")
+    lon = np.array([1, g.im], np.int32)
+    sl = lambda a: np.asfortranarray(a[..., 0]) if a.ndim in (4, 5) else a
+    L.orc_scores2(g.im, g.jm, g.km, g.l2d, g.l3d, nreg, np.asfortranarray(regindx, dtype=np.int32), lon,
+                  sl(g.bias_2d), sl(g.rtms_2d), sl(g.stdv_2d), g.nobs_2d, sl(g.bias_3d), sl(g.rtms_3d), sl(g.stdv_3d), g.nobs_3d, out)
+    return out

@@ -809,3 +809,37 @@ def test_pageable_columns_through_the_copy_pool_full_size():
         out, gflags = H.gpu_run(cfg, [c], 2, mode, [fin])
         assert np.array_equal(gflags[0], rflags[0])
         H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
+
+
+@pytest.mark.parametrize("mode", H.MODES)
+@pytest.mark.parametrize("device_inputs", [False, True])
+def test_fused_presort_gather_accum_matches_the_sorted_reference_loop(mode, device_inputs):
+    """gritas_b200_accum_odsx_sorted = gritas.f:499-523 (8-key pre-sort + the column gathers) + 562-739 + GrITAS_Accum_, all on
+    the device from UNSORTED columns.  Oracle: sort on the host, gather, filter, Accum in sorted order; in deterministic mode
+    the GPU sums are bit-identical to that sorted sequential loop; ob_flag and `is` come back in the reference's form."""
+    cfg, files = small("cfg5", 0.05, 2)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    ref = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, 2)
+    G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=mode)
+    G._ensure(2, table, p1, p2, l2d, l3d)
+    keep = []
+    for c in files:
+        is0 = oracle.presort(c["qcexcl"], c["lat"], c["lon"], c["lev"], c["time"], c["kt"], c["ks"], c["kx"])
+        s = {k: np.ascontiguousarray(v[is0]) for k, v in c.items() if isinstance(v, np.ndarray) and v.shape == c["lat"].shape}
+        fl = H.filter_in(s, 101)
+        oracle.accum(ref, cfg.nlevs, s["lat"], s["lon"], s["lev"], s["kx"], s["kt"], H.del_of(s, 2), table, p1, p2, fl)
+        cols = c
+        if device_inputs:
+            import torch
+            cols = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in c.items() if isinstance(v, np.ndarray)}
+            keep.append(cols)
+        fo = np.full(len(fl), -5, np.int32)
+        iso = np.zeros(len(fl), np.int32)
+        G.accum_odsx_sorted(cols, iopt=101, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD, ob_flag_out=fo, is_out=iso)
+        assert np.array_equal(iso, is0 + 1)
+        assert np.array_equal(fo, fl)
+    oracle.norm(ref, cfg.nlevs, True, 0)
+    out = G.alloc_grids()
+    G.norm_into(out)
+    G.close()
+    H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
