@@ -251,6 +251,15 @@ struct gritas_b200_ctx {
   size_t tf_smem = 0;            // shared memory of the tile kernel (K2f / K2t)
   int tf_ctas = 148, tf_per_sm = 1;
   bool fused_norm = true;        // Norm consumes the tile lists itself (K2f) instead of flush (K2t) + K3
+  bool det_tiled = false;        // deterministic mode on the tiled path (k_tile_det): entries carry sequence numbers
+  size_t td_smem = 0;            // shared memory of k_tile_det
+  int td_ctas = 148;
+  unsigned long long det_calls = 0;    // Accum calls since the reset
+  unsigned *h_ctrl = nullptr;          // pinned [NWK][4]: the control words after the fill / dirty arrays, per worker stream
+  bool ctrl_valid[NWK] = {};
+  unsigned long long call_order = 0;   // order of the next Accum call (deterministic mode): calls since the reset, or what
+  bool call_order_set = false;         // gritas_b200_set_call_order gave for it (multi-rank: the global file index)
+
   double *red = nullptr;         // multi-rank Norm: compact {n, sums} planes per tile, the operand of ncclReduce
   size_t red_cap = 0;
   // Worker streams: the K1 launch of one Accum call (1.2 M observations, two waves of short CTAs) cannot fill
@@ -505,7 +514,19 @@ int drain(gritas_b200_handle h, double *bad_lev) {
   int jr = join_workers(h);
   if (jr) return jr;
   CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status) * (NWK + 1), cudaMemcpyDeviceToHost, h->compute));
+  if (h->det_tiled)
+    CU(cudaMemcpyAsync(h->h_ctrl + 4 * NWK, h->sg.fill + 2 * (size_t)h->sg.ntiles, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaStreamSynchronize(h->compute));
+  if (h->det_tiled && h->h_ctrl[4 * NWK + 1] != 0u) {
+    const unsigned why = h->h_ctrl[4 * NWK + 1];
+    CU(cudaMemsetAsync(h->sg.fill + 2 * (size_t)h->sg.ntiles + 1, 0, sizeof(unsigned), h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    return fail(h, GRITAS_B200_ERR_ORDER,
+                why == 2u ? "deterministic mode: one box holds more parked observations than a chunk of the tile kernel; its sums were "
+                            "formed out of order (complete, not reproducible).  Use GRITAS_B200_FLAG_DET_SORT for such data"
+                          : "deterministic mode: a tile list overflowed; the observations that did not fit were added out of order "
+                            "(complete, not reproducible).  Raise GRITAS_B200_STAGE_SLOTS or use GRITAS_B200_FLAG_DET_SORT");
+  }
   int best = 0;  // earliest (call, observation) over the streams
   for (int q = 1; q <= NWK; ++q)
     if (h->h_status[q].first_bad < h->h_status[best].first_bad) best = q;
@@ -559,10 +580,38 @@ void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDes
   const int g1 = grid_for((size_t)nvec, K1_THREADS, per_sm);
   const size_t smem = levtab_smem_bytes(h->g);
   Status *st = h->d_status + 1 + w;
+  if (h->det_tiled) {
+    const unsigned long long sb = h->call_order << SEQ_IDX_BITS;
+    switch (filter_mode(f)) {
+      case 0: k_list_obs<NR, 0, true><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg, sb); break;
+      case 1: k_list_obs<NR, 1, true><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg, sb); break;
+      default: k_list_obs<NR, 2, true><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg, sb); break;
+    }
+    return;
+  }
   switch (filter_mode(f)) {
     case 0: k_list_obs<NR, 0><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg); break;
     case 1: k_list_obs<NR, 1><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg); break;
     default: k_list_obs<NR, 2><<<g1, K1_THREADS, smem, h->wk[w]>>>(h->g, c, f, st, h->call_seq, h->sg); break;
+  }
+}
+
+// K2d launches (deterministic tiled path).
+template <int NR, int MODE>
+void launch_det(gritas_b200_handle h, cudaStream_t sm, unsigned t0, unsigned t1, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
+                int raw2, int raw3, const PeerSet &ps) {
+  if (t1 <= t0) return;
+  const int ctas = (int)std::min((unsigned)h->td_ctas, t1 - t0);
+  k_tile_det<NR, MODE><<<ctas, TileDet<NR>::THREADS, h->td_smem, sm>>>(h->g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, ntr, raw2, raw3,
+                                                                      h->acc_fresh ? 1 : 0, t0, t1, ps);
+}
+template <int MODE>
+void launch_det_nr(gritas_b200_handle h, cudaStream_t sm, unsigned t0, unsigned t1, const OutPlanes &o2, const OutPlanes &o3, int nrmlz, int ntr,
+                   int raw2, int raw3, const PeerSet &ps) {
+  switch (h->g.nr) {
+    case 1: launch_det<1, MODE>(h, sm, t0, t1, o2, o3, nrmlz, ntr, raw2, raw3, ps); break;
+    case 2: launch_det<2, MODE>(h, sm, t0, t1, o2, o3, nrmlz, ntr, raw2, raw3, ps); break;
+    default: launch_det<3, MODE>(h, sm, t0, t1, o2, o3, nrmlz, ntr, raw2, raw3, ps); break;
   }
 }
 
@@ -590,7 +639,12 @@ int flush_stage(gritas_b200_handle h) {
   if (!h->staging || h->staged_upper == 0) return 0;
   int jr = join_workers(h);
   if (jr) return jr;
-  launch_tiles_nr(h, 0u, h->sg.ntiles);
+  if (h->det_tiled) {
+    const OutPlanes none = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    launch_det_nr<DET_FLUSH>(h, h->compute, 0u, h->sg.ntiles, none, none, 0, 0, 0, 0, PeerSet{});
+  } else {
+    launch_tiles_nr(h, 0u, h->sg.ntiles);
+  }
   CU(cudaGetLastError());
   h->launches += 1;
   h->staged_upper = 0;
@@ -673,7 +727,25 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
   // least 64 Ki observations runs the direct kernel with a locality probe (both paths add into the same records).
   bool probe = false;
   if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice < 0 && !h->minmax) probe = n >= 65536;
-  const bool tiled = (h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice == 1;
+  const bool tiled = h->staging && (h->det_tiled || ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->tiled_choice == 1));
+  if (h->det_tiled) {
+    if (!h->call_order_set) h->call_order = h->det_calls;
+    h->call_order_set = false;
+    h->det_calls += 1;
+    if (h->call_order >= (1ull << 20) || (unsigned long long)n >= (1ull << SEQ_IDX_BITS))
+      return fail(h, GRITAS_B200_ERR_ARG, "deterministic mode: at most 2^20 calls between resets and 2^28 observations per call");
+    // a tile list about to fill up (clustered data)?  flush in time: what does not fit a list is added out of order
+    unsigned seen = 0;
+    for (int q = 0; q < h->nwk; ++q)
+      if (h->ctrl_valid[q] && cudaEventQuery(h->wk_done[q]) == cudaSuccess) { seen = std::max(seen, h->h_ctrl[4 * q + 2]); h->ctrl_valid[q] = false; }
+    cudaGetLastError();
+    if (seen > h->sg.cap / 2) {
+      int rc = flush_stage(h);
+      if (rc) return rc;
+      CU(cudaMemsetAsync(h->sg.fill + 2 * (size_t)h->sg.ntiles + 2, 0, sizeof(unsigned), h->compute));
+      if ((rc = mark_main(h))) return rc;
+    }
+  }
   const int w = h->next_wk;
   cudaStream_t run = tiled ? h->wk[w] : h->compute;
   if (tiled) {
@@ -787,6 +859,10 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     }
   }
   if (tiled) {
+    if (h->det_tiled) {   // the fullest list so far, for the flush decision of a later call
+      CU(cudaMemcpyAsync(h->h_ctrl + 4 * w, h->sg.fill + 2 * (size_t)h->sg.ntiles, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, run));
+      h->ctrl_valid[w] = true;
+    }
     CU(cudaEventRecord(h->wk_done[w], run));
     h->wk_pending[w] = true;
   }
@@ -930,7 +1006,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
                *e_slots = getenv("GRITAS_B200_STAGE_SLOTS"), *e_max = getenv("GRITAS_B200_STAGE_MAX_GRID_MB");
     // (with K2f a Norm no longer moves the records, so large grids profit too: cfg4's 32 GB of records 28 -> 19 ms/step)
     const size_t max_grid = (e_max ? (size_t)atoll(e_max) : (size_t)65536) << 20;
-    bool want = m == GRITAS_B200_MODE_FAST && !h->minmax && !(h->flags & GRITAS_B200_FLAG_NO_STAGING) && acc_bytes <= max_grid &&
+    const bool det_tiles = m == GRITAS_B200_MODE_DETERMINISTIC && !(h->flags & GRITAS_B200_FLAG_DET_SORT);
+    bool want = (m == GRITAS_B200_MODE_FAST || det_tiles) && !h->minmax && !(h->flags & GRITAS_B200_FLAG_NO_STAGING) && acc_bytes <= max_grid &&
                 h->nrec >= 4096;
     if (e_on && atoi(e_on) == 0) want = false;
     if (want) {
@@ -938,7 +1015,9 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
       if (e_shift) shift = atoi(e_shift);
       const size_t T = (size_t)1 << shift;
       // the tile kernel (K2f / K2t) keeps the tile's sum planes and one sort chunk of its list in shared memory
-      const size_t smem = nr == 1 ? TileFinal<1>::smem_bytes(T) : (nr == 2 ? TileFinal<2>::smem_bytes(T) : TileFinal<3>::smem_bytes(T));
+      const size_t smem_f = nr == 1 ? TileFinal<1>::smem_bytes(T) : (nr == 2 ? TileFinal<2>::smem_bytes(T) : TileFinal<3>::smem_bytes(T));
+      const size_t smem_d = nr == 1 ? TileDet<1>::smem_bytes(T) : (nr == 2 ? TileDet<2>::smem_bytes(T) : TileDet<3>::smem_bytes(T));
+      const size_t smem = std::max(smem_f, det_tiles ? smem_d : (size_t)0);
       size_t free_b = 0, total_b = 0;
       CUC(cudaMemGetInfo(&free_b, &total_b));
       const size_t entry = (nr == 1) ? ListEntry<1>::BYTES : ListEntry<2>::BYTES;
@@ -975,8 +1054,28 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         else if (nr == 2) TF_SETUP(2);
         else TF_SETUP(3);
 #undef TF_SETUP
-        h->tf_smem = smem;
+        h->tf_smem = smem_f;
         h->tf_per_sm = std::max(per_sm, 1);
+        if (det_tiles) {
+          int dps = 1;
+#define TD_SETUP(NR_)                                                                                                           \
+  do {                                                                                                                           \
+    CUC(cudaFuncSetAttribute(k_tile_det<NR_, DET_FINALIZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));         \
+    CUC(cudaFuncSetAttribute(k_tile_det<NR_, DET_FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));            \
+    CUC(cudaFuncSetAttribute(k_tile_det<NR_, DET_PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));            \
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dps, k_tile_det<NR_, DET_FINALIZE>, TileDet<NR_>::THREADS, smem_d));     \
+  } while (0)
+          if (nr == 1) TD_SETUP(1);
+          else if (nr == 2) TD_SETUP(2);
+          else TD_SETUP(3);
+#undef TD_SETUP
+          h->td_smem = smem_d;
+          h->td_ctas = (int)std::min((size_t)nsm * (size_t)std::max(dps, 1), ntiles);
+          h->det_tiled = true;
+          h->tiled_choice = 1;
+          CUC(cudaMallocHost(&h->h_ctrl, sizeof(unsigned) * 4 * (NWK + 1)));
+          memset(h->h_ctrl, 0, sizeof(unsigned) * 4 * (NWK + 1));
+        }
         h->tf_ctas = (int)std::min((size_t)nsm * (size_t)h->tf_per_sm, ntiles);   // persistent: all CTAs resident
         // GRITAS_B200_FUSED_NORM=0: Norm flushes the lists into the records (K2t) and finalizes them with K3
         const char *e_f = getenv("GRITAS_B200_FUSED_NORM");
@@ -1045,6 +1144,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
                   h->cub_tmp, (void *)h->out})
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->compute && h->own_compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);
   cudaGetLastError();
@@ -1255,6 +1355,14 @@ int gritas_b200_wait(gritas_b200_handle h, double *bad_lev) {
   return settle(h, true, bad_lev);
 }
 
+int gritas_b200_set_call_order(gritas_b200_handle h, uint64_t order) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  h->call_order = order;
+  h->call_order_set = true;
+  return 0;
+}
+
 int gritas_b200_flush(gritas_b200_handle h) {
   int rc = check_handle(h);
   if (rc) return rc;
@@ -1275,6 +1383,9 @@ int gritas_b200_reset(gritas_b200_handle h) {
     CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   }
   h->acc_fresh = true;
+  h->det_calls = 0;
+  h->call_order_set = false;
+  for (bool &v : h->ctrl_valid) v = false;
   if (h->staging) {
     CU(cudaMemsetAsync(h->sg.fill, 0, sizeof(unsigned) * (2 * (size_t)h->sg.ntiles + 4), h->compute));   // tickets, dirty words, records-touched word
     h->staged_upper = 0;
@@ -1378,10 +1489,14 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
     const OutPlanes o2 = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
     const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], (raw3 && (raw == 0 || raw == 3)) ? 1 : xpl};
     const int r3 = raw3 ? 1 : raw;
-    switch (nr) {
-      case 1: launch_tile_final<1>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
-      case 2: launch_tile_final<2>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
-      default: launch_tile_final<3>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
+    if (h->det_tiled) {
+      launch_det_nr<DET_FINALIZE>(h, h->compute, 0u, h->sg.ntiles, o2, o3, nrmlz, ntr, raw, r3, PeerSet{});
+    } else {
+      switch (nr) {
+        case 1: launch_tile_final<1>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
+        case 2: launch_tile_final<2>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
+        default: launch_tile_final<3>(h, h->compute, o2, o3, nrmlz, ntr, raw, r3); break;
+      }
     }
     CU(cudaGetLastError());
     h->launches++;
@@ -2072,7 +2187,9 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
     const int r3 = raw3 ? 1 : 0;
     const unsigned T = 1u << h->sg.tile_shift;
     const unsigned t0 = (unsigned)(sl.lo >> h->sg.tile_shift), t1 = (unsigned)((sl.hi + T - 1) >> h->sg.tile_shift);
-    if (t1 > t0) {
+    if (t1 > t0 && h->det_tiled) {
+      launch_det_nr<DET_PEERS>(h, h->compute, t0, t1, o2, o3, nrmlz, ntr, 0, r3, ps);
+    } else if (t1 > t0) {
       const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
 #define PEER_LAUNCH(NR_)                                                                                                      \
   k_tile_final<NR_, TILE_PEERS><<<ctas, TileFinal<NR_>::THREADS, h->tf_smem, h->compute>>>(g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, \

@@ -803,10 +803,13 @@ __device__ __forceinline__ size_t list_slot(const StageDesc &sg, unsigned tile, 
   return ((size_t)(pos / LIST_G) * sg.ntiles + tile) * LIST_G + (pos % LIST_G);
 }
 
+// Deterministic path: the first 8 bytes of an entry carry the box number within the tile (16 bits) and the observation's
+// sequence number (48 bits: call order << 28 | index within the call) -- the tile kernel sums every box in that order.
+constexpr int SEQ_IDX_BITS = 28;
 template <int NR>
-__device__ __forceinline__ void entry_store(unsigned char *lists, size_t idx, unsigned key, const double (&d)[NR]) {
+__device__ __forceinline__ void entry_store(unsigned char *lists, size_t idx, unsigned long long word0, const double (&d)[NR]) {
   unsigned char *p = lists + idx * (size_t)ListEntry<NR>::BYTES;
-  const double k = __longlong_as_double((long long)key);
+  const double k = __longlong_as_double((long long)word0);
   if (NR == 1) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(k), "d"(d[0]) : "memory");
   } else {
@@ -831,6 +834,28 @@ __device__ __forceinline__ unsigned entry_load(const unsigned char *lists, size_
   return (unsigned)__double_as_longlong(k);
 }
 
+// Deterministic path: the entry's first word (see entry_store) and its residuals.
+template <int NR>
+__device__ __forceinline__ unsigned long long entry_load64(const unsigned char *lists, size_t idx, double (&d)[NR]) {
+  const unsigned char *p = lists + idx * (size_t)ListEntry<NR>::BYTES;
+  double k, a, b, c;
+  if (NR == 1) {
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(k), "=d"(a) : "l"(p));
+    d[0] = a;
+  } else {
+    asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(k), "=d"(a), "=d"(b), "=d"(c) : "l"(p));
+    d[0] = a;
+    d[1] = b;
+    if (NR == 3) d[NR - 1] = c;
+  }
+  return (unsigned long long)__double_as_longlong(k);
+}
+__device__ __forceinline__ unsigned long long entry_word0(const unsigned char *lists, size_t idx, int bytes) {
+  unsigned long long w;
+  asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(w) : "l"(lists + idx * (size_t)bytes));
+  return w;
+}
+
 // Direct accumulate of one entry (a full list): the same fp64 RED the direct path uses.
 template <int NR>
 __device__ __forceinline__ void red_entry(const GridDesc &g, unsigned key, const double (&d)[NR]) {
@@ -846,10 +871,10 @@ constexpr int K1_THREADS = 256;
 #define GB_K1_MINB 4
 #endif
 
-template <int NR, int FMODE>
+template <int NR, int FMODE, bool DET = false>
 __global__ void __launch_bounds__(K1_THREADS, GB_K1_MINB)
 k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__restrict__ st, unsigned call_seq,
-           const StageDesc sg) {
+           const StageDesc sg, unsigned long long seq_base = 0ull) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LevTab p2s = load_p2(g, reinterpret_cast<double *>(smem_raw));
   const unsigned lane = threadIdx.x & 31u;
@@ -899,10 +924,14 @@ k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
       for (int ir = 0; ir < NR; ++ir) d[ir] = (f.scale_res | f.expr) ? residual_value(f, c, ir, dd[ir][j], base + j) : dd[ir][j];
       const unsigned tile = key >> sg.tile_shift;
       if (pos[j] < sg.cap) {
-        entry_store<NR>(sg.lists, list_slot(sg, tile, pos[j]), key, d);
+        const unsigned long long w0 = DET ? (((seq_base + (unsigned long long)(base + j)) << 16) | (unsigned long long)(key & ((1u << sg.tile_shift) - 1u)))
+                                          : (unsigned long long)key;
+        entry_store<NR>(sg.lists, list_slot(sg, tile, pos[j]), w0, d);
+        if (DET && pos[j] >= sg.cap / 2u) atomicMax(sg.fill + 2u * sg.ntiles + 2u, pos[j] + 1u);   // the host flushes before a list fills up
       } else {
         red_entry<NR>(g, key, d);       // the list is full: accumulate directly
         sg.dirty[tile] = 1u;
+        if (DET) sg.fill[2u * sg.ntiles + 1u] = 1u;   // ... which is not in input order: the host reports it (GRITAS_B200_ERR_ORDER)
       }
     }
   }
@@ -1143,6 +1172,101 @@ k_add_raw(const GridDesc g, OutPlanes in, int is3d) {
   }
 }
 
+// The finalize step of a tile whose sums sit in shared memory (m_gritas_grids.f:566-654): shared by the tile kernels of the
+// fast path (k_tile_final) and of the deterministic path (k_tile_det).  s_val: [NV][T] sums; the count of box b is s_nd[b]
+// (IMPORTN) or s_tot[b]; addrec: the records of the box (of every rank in recmask when PEER) are added on top.
+template <int NR, bool PEER, bool IMPORTN, int NTH>
+__device__ __forceinline__ void tile_finalize_out(const GridDesc &g, size_t first, unsigned nb, unsigned T, const double *s_val,
+                                                  const unsigned *s_tot, const double *s_nd, bool addrec, unsigned recmask,
+                                                  const PeerSet &peers, const OutPlanes &o2, const OutPlanes &o3, int raw2, int raw3,
+                                                  int nrmlz, int ntresh, unsigned tid) {
+  constexpr int NV = TilePlanes<NR>::NV;
+  const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
+  auto box = [&](unsigned b, bool is3d, bool zero, int raw, const OutPlanes &out, size_t o, size_t plane) {
+    double r[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q] = 0.0;
+    if (!zero) {
+      r[0] = IMPORTN ? s_nd[b] : (double)s_tot[b];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) r[1 + q] = s_val[(size_t)q * T + b];
+      if (addrec) {
+        // PEER: the records of every rank that accumulated part of this tile directly, in rank order
+        for (int src = 0; src < (PEER ? peers.n : 1); ++src) {
+          if (PEER && !(recmask & (1u << src))) continue;
+          const double *rec = (PEER ? peers.acc[src] : g.acc) + (first + b) * (size_t)g.rs;
+          const double2 a0 = *reinterpret_cast<const double2 *>(rec), a1 = *reinterpret_cast<const double2 *>(rec + 2);
+          r[0] = __dadd_rn(a0.x, r[0]); r[1] = __dadd_rn(a0.y, r[1]); r[2] = __dadd_rn(a1.x, r[2]);
+          if (NR > 1) {
+            const double2 a2 = *reinterpret_cast<const double2 *>(rec + 4), a3 = *reinterpret_cast<const double2 *>(rec + 6);
+            r[3] = __dadd_rn(a1.y, r[3]); r[4] = __dadd_rn(a2.x, r[4]); r[5] = __dadd_rn(a2.y, r[5]);
+            if (NR > 2) r[6] = __dadd_rn(a3.x, r[6]);
+          }
+        }
+      }
+    }
+    double bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs = 0.0;
+    if (zero) {
+#pragma unroll
+      for (int ir = 0; ir < NR; ++ir) { bias[ir] = 0.0; rtms[ir] = 0.0; stdv[ir] = 0.0; xcov[ir] = 0.0; }
+    } else {
+      finalize_box<NR>(r, is3d, nrmlz, ntresh, raw, bias, rtms, stdv, xcov, nobs);
+    }
+#pragma unroll
+    for (int ir = 0; ir < NR; ++ir) {
+      if (out.bias) __stcs(out.bias + o + plane * ir, bias[ir]);
+      if (out.rtms) __stcs(out.rtms + o + plane * ir, rtms[ir]);
+      if (out.stdv) __stcs(out.stdv + o + plane * ir, stdv[ir]);
+      if (out.xcov && ir < out.xcov_planes) __stcs(out.xcov + o + plane * ir, xcov[ir]);
+    }
+    if (out.nobs) __stcs(out.nobs + o, nobs);
+  };
+  const size_t end3 = min(first + nb, plane3);
+  if (first < end3) {
+    // the tile's span of level-fastest records covers columns c0..c1 (column = i + im*(j + jm*l)); walk it level
+    // by level so that consecutive threads write consecutive longitudes
+    const unsigned km = (unsigned)g.km;
+    const size_t c0 = first / km, c1 = (end3 - 1) / km;
+    const unsigned ncol = (unsigned)(c1 - c0 + 1);
+    const unsigned head = (unsigned)(first - c0 * km), span = (unsigned)(end3 - first);
+    // The span is enumerated without holes, so that a full tile is exactly T / NTH rounds: first the interior columns
+    // level by level (consecutive threads -> consecutive longitudes), then the valid levels of the partial first
+    // and last column.  Divisions by the column count, im and jm are multiplications: floor((x + 0.5) / d) =
+    // trunc((x + 0.5) * (1/d)) as long as the rounding error stays below 0.5/d -- q < 2^16 in fp32, col < 2^32 in
+    // fp64 (error < 2e-6 for any im)
+    const unsigned nin = ncol > 2u ? ncol - 2u : 0u;                         // interior columns
+    const unsigned nA = nin * km, nB = (ncol == 1u) ? span : km - head;     // interior cells, cells of the first column
+    const float rnin = 1.0f / (float)max(nin, 1u);
+    for (unsigned q = tid; q < span; q += NTH) {
+      unsigned k, ci;
+      if (q < nA) {
+        k = (unsigned)(((float)q + 0.5f) * rnin);
+        ci = 1u + (q - k * nin);
+      } else if (q < nA + nB) {
+        k = head + (q - nA);
+        ci = 0u;
+      } else {
+        k = q - nA - nB;
+        ci = ncol - 1u;
+      }
+      const unsigned rel = ci * km + k;
+      if (PEER) {                                           // a tile straddling the slab boundary: the neighbour rank has the rest
+        const size_t recno = first + (rel - head);
+        if (recno < peers.own_lo || recno >= peers.own_hi) continue;
+      }
+      const unsigned col = (unsigned)c0 + ci;               // < nbox3 / km: 32 bits
+      const unsigned jl = (unsigned)(((double)col + 0.5) * g.rim), i = col - jl * (unsigned)g.im;
+      const unsigned l = (unsigned)(((double)jl + 0.5) * g.rjm), j = jl - l * (unsigned)g.jm;
+      const size_t o = (size_t)i + (size_t)g.im * ((size_t)j + (size_t)g.jm * ((size_t)k + (size_t)km * (size_t)l));
+      box(rel - head, true, (int)k >= g.nlevs, raw3, o3, o, plane3);   // levels nlevs..km-1: never touched, zeros
+    }
+  }
+  for (size_t rec = max(first, plane3) + tid; rec < first + nb; rec += NTH) {
+    if (PEER && (rec < peers.own_lo || rec >= peers.own_hi)) continue;
+    box((unsigned)(rec - first), false, false, raw2, o2, rec - plane3, plane2);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Tiled fast path, part 2: one CTA per tile accumulates the tile's list in shared memory, then either
 //   K2f (FLUSH = false): finalizes straight from shared memory -- what GrITAS_Norm runs when the month is still
@@ -1200,7 +1324,6 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   unsigned *s_warp = s_cnt + T + 4;                        // [32]
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
-  const size_t plane3 = (size_t)g.nbox3, plane2 = (size_t)g.nbox2;
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     if (PEER) {
       // the tile's list is the concatenation of every rank's list of this tile (a chunk of the counting sort may span
@@ -1401,89 +1524,305 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       continue;
     }
     // ---- finalize (m_gritas_grids.f:566-654) straight from the planes ----
-    auto box = [&](unsigned b, bool is3d, bool zero, int raw, const OutPlanes &out, size_t o, size_t plane) {
-      double r[8];
+    tile_finalize_out<NR, PEER, MODE == TILE_IMPORT, TF::THREADS>(g, first, nb, T, s_val, s_tot, s_nd, addrec, recmask, peers, o2, o3, raw2, raw3,
+                                                                  nrmlz, ntresh, tid);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic mode on the tiled path (K2d).  Same parking of the accepted observations as the fast path, but every
+// entry carries its sequence number (call order, index within the call) and the tile kernel adds the entries of a box
+// IN THAT ORDER, continuing from the sums the box already has: the same sequence of fp64 additions as the reference's
+// sequential loop (m_gritas_grids.f:405-474) -- bit-identical sums, whatever order the tickets were handed out in,
+// however many Accum calls overlapped, and (sharded Norm, no flush in between) however many ranks parked the entries.
+// Replaces the radix sort of whole files (CUB) + one-thread-per-run segment sums of round 1.
+//
+// Per tile: (1) count the entries per box (all ranks' lists when PEER), (2) scan, (3) cut the boxes into groups of at
+// most CH entries (usually one group), (4) per group: scatter the entries to start(box) + ticket, rank every entry within
+// its box by sequence number (each entry scans its box's short run), (5) the owner of a box walks its run in rank order.
+// Lists longer than a chunk are re-read once per group; a single box with more than CH parked entries is summed in
+// arbitrary order and reported (order_lost, GRITAS_B200_ERR_ORDER).
+template <int NR>
+struct TileDet {
+  static constexpr int THREADS = 512;
+  static constexpr int EPT = (NR == 3) ? 3 : 4;
+  static constexpr int CH = EPT * THREADS;
+  static constexpr int NV = TilePlanes<NR>::NV;
+  __host__ __device__ static constexpr size_t smem_bytes(size_t T) {
+    return sizeof(double) * ((size_t)NV * T + (size_t)NR * CH) + (size_t)CH * (4 + 2 + 2 + 2) + sizeof(unsigned) * (3 * T + 8);
+  }
+};
+constexpr int DET_FINALIZE = 0, DET_FLUSH = 1, DET_PEERS = 2;
+
+template <int NR, int MODE>
+__global__ void __launch_bounds__(TileDet<NR>::THREADS, 2)
+k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, OutPlanes o3, int nrmlz, int ntresh, int raw2, int raw3,
+           int fresh, unsigned tile0, unsigned tile1, const PeerSet peers) {
+  constexpr bool FLUSH = MODE == DET_FLUSH, PEER = MODE == DET_PEERS;
+  using TD = TileDet<NR>;
+  constexpr int NV = TD::NV, EPT = TD::EPT, CH = TD::CH, NTH = TD::THREADS, EB = ListEntry<NR>::BYTES;
+  extern __shared__ __align__(16) double s_dyn[];
+  const unsigned T = 1u << sg.tile_shift;
+  double *s_val = s_dyn;                                             // [NV][T] running sums of the tile
+  double *s_stage = s_val + (size_t)NV * T;                          // [NR][CH] residuals of the group at start(box) + ticket
+  unsigned *s_seq_lo = reinterpret_cast<unsigned *>(s_stage + (size_t)NR * CH);   // [CH] sequence numbers (48 bits: lo, hi)
+  unsigned *s_tot = s_seq_lo + CH;                                   // [T] entries per box (whole list); + record count at the end
+  unsigned *s_off = s_tot + T;                                       // [T + 1] exclusive scan of s_tot
+  unsigned *s_cur = s_off + T + 4;                                   // [T] tickets within the current group
+  unsigned short *s_seq_hi = reinterpret_cast<unsigned short *>(s_cur + T + 4);   // [CH]
+  unsigned short *s_inv = s_seq_hi + CH;                             // [CH] position of the entry with rank k of its box
+  unsigned short *s_boxof = s_inv + CH;                              // [CH] box of the entry at a position
+  __shared__ unsigned s_srcoff[MAX_PEERS + 1];
+  __shared__ unsigned s_recmask, s_b1, s_warp[32];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const unsigned PT = (T + NTH - 1) / NTH;
+  const int nsrc = PEER ? peers.n : 1;
+  for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
+    if (tid == 0u) {
+      unsigned tot = 0u, mask = 0u;
+      for (int s = 0; s < nsrc; ++s) {
+        const unsigned *f = PEER ? peers.fill[s] : sg.fill;
+        s_srcoff[s] = tot;
+        tot += min(f[tile], sg.cap);
+        if (PEER && (f[2u * sg.ntiles] != 0u || f[sg.ntiles + tile] != 0u)) mask |= 1u << s;
+      }
+      s_srcoff[nsrc] = tot;
+      s_recmask = mask;
+    }
+    __syncthreads();
+    const unsigned n = s_srcoff[nsrc];
+    if (FLUSH && n == 0u) { __syncthreads(); continue; }
+    const size_t first = (size_t)tile << sg.tile_shift;
+    const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
+    // the sums continue from this rank's records (in order: everything in them is older than anything parked); other
+    // ranks' records (PEER, only after a flush there) are partial sums of their own and are added at the end
+    const bool ownrec = PEER ? false : (!fresh || sg.dirty[tile] != 0u);
+    const unsigned recmask = PEER ? s_recmask : 0u;
+    for (unsigned e = tid; e < NV * T; e += NTH) {
+      const unsigned q = e >> sg.tile_shift, b = e & (T - 1u);
+      s_val[e] = (ownrec && b < nb) ? g.acc[(first + b) * (size_t)g.rs + 1u + q] : 0.0;
+    }
+    for (unsigned e = tid; e < T; e += NTH) s_tot[e] = 0u;
+    __syncthreads();
+    if (n > 0u) {
+      const bool single = n <= (unsigned)CH;                          // the whole list fits one chunk: entries stay in registers
+      unsigned long long w[EPT];
+      double d[EPT][NR];
+      auto load = [&](unsigned e, unsigned long long &w0, double (&dd)[NR], bool full) {
+        int src = 0;
+        while (src + 1 < nsrc && e >= s_srcoff[src + 1]) ++src;
+        const unsigned char *base = PEER ? peers.lists[src] : sg.lists;
+        const size_t slot = list_slot(sg, tile, e - s_srcoff[src]);
+        if (full) w0 = entry_load64<NR>(base, slot, dd);
+        else w0 = entry_word0(base, slot, EB);
+      };
+      // ---- (1) entries per box ----
+      if (single) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) r[q] = 0.0;
-      if (!zero) {
-        r[0] = (MODE == TILE_IMPORT) ? s_nd[b] : (double)s_tot[b];
+        for (int u = 0; u < EPT; ++u) {
+          const unsigned e = (unsigned)u * NTH + tid;
+          w[u] = ~0ull;
+          if (e < n) load(e, w[u], d[u], true);
+        }
 #pragma unroll
-        for (int q = 0; q < NV; ++q) r[1 + q] = s_val[(size_t)q * T + b];
-        if (addrec) {
-          // PEER: the records of every rank that accumulated part of this tile directly, in rank order
-          for (int src = 0; src < (PEER ? peers.n : 1); ++src) {
-            if (PEER && !(recmask & (1u << src))) continue;
-            const double *rec = (PEER ? peers.acc[src] : g.acc) + (first + b) * (size_t)g.rs;
-            const double2 a0 = *reinterpret_cast<const double2 *>(rec), a1 = *reinterpret_cast<const double2 *>(rec + 2);
-            r[0] = __dadd_rn(a0.x, r[0]); r[1] = __dadd_rn(a0.y, r[1]); r[2] = __dadd_rn(a1.x, r[2]);
-            if (NR > 1) {
-              const double2 a2 = *reinterpret_cast<const double2 *>(rec + 4), a3 = *reinterpret_cast<const double2 *>(rec + 6);
-              r[3] = __dadd_rn(a1.y, r[3]); r[4] = __dadd_rn(a2.x, r[4]); r[5] = __dadd_rn(a2.y, r[5]);
-              if (NR > 2) r[6] = __dadd_rn(a3.x, r[6]);
+        for (int u = 0; u < EPT; ++u)
+          if (w[u] != ~0ull) atomicAdd(s_tot + ((unsigned)w[u] & (T - 1u)), 1u);
+      } else {
+        for (unsigned c0 = 0; c0 < n; c0 += CH) {
+#pragma unroll
+          for (int u = 0; u < EPT; ++u) {
+            const unsigned e = c0 + (unsigned)u * NTH + tid;
+            w[u] = ~0ull;
+            double dummy[NR];
+            if (e < n) load(e, w[u], dummy, false);
+          }
+#pragma unroll
+          for (int u = 0; u < EPT; ++u)
+            if (w[u] != ~0ull) atomicAdd(s_tot + ((unsigned)w[u] & (T - 1u)), 1u);
+        }
+      }
+      __syncthreads();
+      // ---- (2) exclusive scan: s_off[b] = entries of the boxes before b, s_off[T] = n ----
+      {
+        unsigned sum = 0u;
+        for (unsigned q = 0; q < PT; ++q) {
+          const unsigned i = tid * PT + q;
+          if (i < T) sum += s_tot[i];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31u) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0u) {
+          const unsigned wv = s_warp[lane];
+          unsigned wi = wv;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (unsigned)o) wi += t;
+          }
+          s_warp[lane] = wi - wv;
+        }
+        __syncthreads();
+        unsigned excl = incl - sum + s_warp[wid];
+        for (unsigned q = 0; q < PT; ++q) {
+          const unsigned i = tid * PT + q;
+          if (i < T) { s_off[i] = excl; excl += s_tot[i]; }
+        }
+        if (tid == NTH - 1u) s_off[T] = excl;
+      }
+      __syncthreads();
+      // ---- (3) groups of boxes [b0, b1) with at most CH entries; (4), (5) per group ----
+      unsigned b0 = 0u;
+      while (b0 < T) {
+        if (tid == 0u) {
+          // largest b1 with s_off[b1] - s_off[b0] <= CH (s_off is non-decreasing)
+          const unsigned lim = s_off[b0] + (unsigned)CH;
+          unsigned lo = b0, hi = T;
+          while (lo < hi) { const unsigned mid = (lo + hi + 1u) >> 1; if (s_off[mid] <= lim) lo = mid; else hi = mid - 1u; }
+          s_b1 = (lo == b0) ? b0 + 1u : lo;                           // one box alone exceeds a chunk: taken window by window
+        }
+        __syncthreads();
+        const unsigned b1 = s_b1;
+        const unsigned gbase = s_off[b0], cnt = s_off[b1] - gbase;
+        const bool giant = cnt > (unsigned)CH;
+        if (giant) {
+          // One box alone holds more entries than a chunk: its order cannot be kept here.  The entries are added with
+          // shared-memory atomics (no order) and the host reports GRITAS_B200_ERR_ORDER; counts and sums stay complete.
+          if (tid == 0u) sg.fill[2u * sg.ntiles + 1u] = 2u;
+          for (unsigned c0 = 0; c0 < n; c0 += CH) {
+#pragma unroll 1
+            for (int u = 0; u < EPT; ++u) {
+              const unsigned e = c0 + (unsigned)u * NTH + tid;
+              if (e >= n) continue;
+              unsigned long long wv;
+              double x[NR];
+              load(e, wv, x, true);
+              if (((unsigned)wv & (T - 1u)) != b0) continue;
+              if (NR == 2) {
+                atomicAdd(s_val + 0 * T + b0, x[0]); atomicAdd(s_val + 1 * T + b0, __dmul_rn(x[0], x[0]));
+                atomicAdd(s_val + 2 * T + b0, x[NR - 1]); atomicAdd(s_val + 3 * T + b0, __dmul_rn(x[NR - 1], x[NR - 1]));
+                atomicAdd(s_val + 4 * T + b0, __dmul_rn(x[0], x[NR - 1]));
+              } else {
+#pragma unroll
+                for (int ir = 0; ir < NR; ++ir) {
+                  atomicAdd(s_val + (size_t)(2 * ir) * T + b0, x[ir]);
+                  atomicAdd(s_val + (size_t)(2 * ir + 1) * T + b0, __dmul_rn(x[ir], x[ir]));
+                }
+              }
             }
           }
+          __syncthreads();
+          b0 = b1;
+          continue;
         }
-      }
-      double bias[NR], rtms[NR], stdv[NR], xcov[NR], nobs = 0.0;
-      if (zero) {
+        {
+          for (unsigned b = b0 + tid; b < b1; b += NTH) s_cur[b] = 0u;
+          __syncthreads();
+          auto place = [&](unsigned long long wv, const double (&dd)[NR]) {
+            const unsigned box = (unsigned)wv & (T - 1u);
+            if (box < b0 || box >= b1) return;
+            const unsigned rel = s_off[box] - gbase + atomicAdd(s_cur + box, 1u);
+            s_seq_lo[rel] = (unsigned)(wv >> 16);
+            s_seq_hi[rel] = (unsigned short)(wv >> 48);
+            s_boxof[rel] = (unsigned short)box;
 #pragma unroll
-        for (int ir = 0; ir < NR; ++ir) { bias[ir] = 0.0; rtms[ir] = 0.0; stdv[ir] = 0.0; xcov[ir] = 0.0; }
-      } else {
-        finalize_box<NR>(r, is3d, nrmlz, ntresh, raw, bias, rtms, stdv, xcov, nobs);
-      }
+            for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + rel] = dd[ir];
+          };
+          if (single) {
 #pragma unroll
-      for (int ir = 0; ir < NR; ++ir) {
-        if (out.bias) __stcs(out.bias + o + plane * ir, bias[ir]);
-        if (out.rtms) __stcs(out.rtms + o + plane * ir, rtms[ir]);
-        if (out.stdv) __stcs(out.stdv + o + plane * ir, stdv[ir]);
-        if (out.xcov && ir < out.xcov_planes) __stcs(out.xcov + o + plane * ir, xcov[ir]);
-      }
-      if (out.nobs) __stcs(out.nobs + o, nobs);
-    };
-    const size_t end3 = min(first + nb, plane3);
-    if (first < end3) {
-      // the tile's span of level-fastest records covers columns c0..c1 (column = i + im*(j + jm*l)); walk it level
-      // by level so that consecutive threads write consecutive longitudes
-      const unsigned km = (unsigned)g.km;
-      const size_t c0 = first / km, c1 = (end3 - 1) / km;
-      const unsigned ncol = (unsigned)(c1 - c0 + 1);
-      const unsigned head = (unsigned)(first - c0 * km), span = (unsigned)(end3 - first);
-      // The span is enumerated without holes, so that a full tile is exactly T / NTH rounds: first the interior columns
-      // level by level (consecutive threads -> consecutive longitudes), then the valid levels of the partial first
-      // and last column.  Divisions by the column count, im and jm are multiplications: floor((x + 0.5) / d) =
-      // trunc((x + 0.5) * (1/d)) as long as the rounding error stays below 0.5/d -- q < 2^16 in fp32, col < 2^32 in
-      // fp64 (error < 2e-6 for any im)
-      const unsigned nin = ncol > 2u ? ncol - 2u : 0u;                         // interior columns
-      const unsigned nA = nin * km, nB = (ncol == 1u) ? span : km - head;     // interior cells, cells of the first column
-      const float rnin = 1.0f / (float)max(nin, 1u);
-      for (unsigned q = tid; q < span; q += NTH) {
-        unsigned k, ci;
-        if (q < nA) {
-          k = (unsigned)(((float)q + 0.5f) * rnin);
-          ci = 1u + (q - k * nin);
-        } else if (q < nA + nB) {
-          k = head + (q - nA);
-          ci = 0u;
-        } else {
-          k = q - nA - nB;
-          ci = ncol - 1u;
+            for (int u = 0; u < EPT; ++u)
+              if (w[u] != ~0ull) place(w[u], d[u]);
+          } else {
+            for (unsigned c0 = 0; c0 < n; c0 += CH) {
+              unsigned long long wv[EPT];
+              double dv[EPT][NR];
+#pragma unroll
+              for (int u = 0; u < EPT; ++u) {
+                const unsigned e = c0 + (unsigned)u * NTH + tid;
+                wv[u] = ~0ull;
+                if (e < n) load(e, wv[u], dv[u], true);
+              }
+#pragma unroll
+              for (int u = 0; u < EPT; ++u)
+                if (wv[u] != ~0ull) place(wv[u], dv[u]);
+            }
+          }
+          __syncthreads();
+          const unsigned m = cnt;                                      // entries placed
+          // ---- rank of every entry within its box by sequence number ----
+          for (unsigned pos = tid; pos < m; pos += NTH) {
+            const unsigned box = s_boxof[pos];
+            const unsigned st = s_off[box] - gbase, r = s_tot[box];
+            const unsigned lo = s_seq_lo[pos], hi = s_seq_hi[pos];
+            unsigned rank = 0u;
+            for (unsigned q = st; q < st + r; ++q) {
+              const unsigned ql = s_seq_lo[q], qh = s_seq_hi[q];
+              rank += (qh < hi || (qh == hi && ql < lo)) ? 1u : 0u;
+            }
+            s_inv[st + rank] = (unsigned short)pos;
+          }
+          __syncthreads();
+          // ---- the owner of a box adds its run in sequence order, continuing the box's sums (one multiply and one add
+          // per term, as the reference: no fused multiply-add) ----
+          for (unsigned b = b0 + tid; b < b1; b += NTH) {
+            const unsigned st = s_off[b] - gbase, r = s_tot[b];
+            if (r == 0u) continue;
+            double a[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) a[q] = s_val[(size_t)q * T + b];
+#pragma unroll 1
+            for (unsigned k = 0; k < r; ++k) {
+              const unsigned pos = s_inv[st + k];
+              double x[NR];
+#pragma unroll
+              for (int ir = 0; ir < NR; ++ir) x[ir] = s_stage[(size_t)ir * CH + pos];
+              if (NR == 2) {
+                a[0] = __dadd_rn(a[0], x[0]); a[1] = __dadd_rn(a[1], __dmul_rn(x[0], x[0]));
+                a[2] = __dadd_rn(a[2], x[NR - 1]); a[3] = __dadd_rn(a[3], __dmul_rn(x[NR - 1], x[NR - 1]));
+                a[4] = __dadd_rn(a[4], __dmul_rn(x[0], x[NR - 1]));
+              } else {
+#pragma unroll
+                for (int ir = 0; ir < NR; ++ir) {
+                  a[2 * ir] = __dadd_rn(a[2 * ir], x[ir]);
+                  a[2 * ir + 1] = __dadd_rn(a[2 * ir + 1], __dmul_rn(x[ir], x[ir]));
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < NV; ++q) s_val[(size_t)q * T + b] = a[q];
+          }
+          __syncthreads();
         }
-        const unsigned rel = ci * km + k;
-        if (PEER) {                                           // a tile straddling the slab boundary: the neighbour rank has the rest
-          const size_t recno = first + (rel - head);
-          if (recno < peers.own_lo || recno >= peers.own_hi) continue;
-        }
-        const unsigned col = (unsigned)c0 + ci;               // < nbox3 / km: 32 bits
-        const unsigned jl = (unsigned)(((double)col + 0.5) * g.rim), i = col - jl * (unsigned)g.im;
-        const unsigned l = (unsigned)(((double)jl + 0.5) * g.rjm), j = jl - l * (unsigned)g.jm;
-        const size_t o = (size_t)i + (size_t)g.im * ((size_t)j + (size_t)g.jm * ((size_t)k + (size_t)km * (size_t)l));
-        box(rel - head, true, (int)k >= g.nlevs, raw3, o3, o, plane3);   // levels nlevs..km-1: never touched, zeros
+        __syncthreads();
+        b0 = b1;
       }
     }
-    for (size_t rec = max(first, plane3) + tid; rec < first + nb; rec += NTH) {
-      if (PEER && (rec < peers.own_lo || rec >= peers.own_hi)) continue;
-      box((unsigned)(rec - first), false, false, raw2, o2, rec - plane3, plane2);
+    // counts: parked entries + what this rank's records already held (an integer below 2^32)
+    if (ownrec) {
+      for (unsigned b = tid; b < nb; b += NTH) s_tot[b] += (unsigned)g.acc[(first + b) * (size_t)g.rs];
+      __syncthreads();
     }
+    if (FLUSH) {
+      for (unsigned b = tid; b < nb; b += NTH) {
+        double *rec = g.acc + (first + b) * (size_t)g.rs;
+        if (s_tot[b] == 0u && !ownrec) continue;                       // untouched records are zero already
+        rec[0] = (double)s_tot[b];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) rec[1 + q] = s_val[(size_t)q * T + b];
+      }
+      __syncthreads();
+      if (tid == 0u) { sg.fill[tile] = 0u; sg.dirty[tile] = 1u; }      // the tile's records now hold sums
+      __syncthreads();
+      continue;
+    }
+    tile_finalize_out<NR, PEER, false, NTH>(g, first, nb, T, s_val, s_tot, nullptr, PEER && recmask != 0u, recmask, peers, o2, o3, raw2, raw3,
+                                            nrmlz, ntresh, tid);
     __syncthreads();
   }
 }

@@ -207,6 +207,10 @@ class Grids:
                                                        C.byref(bad))
         self._check(rc, bad)
 
+    def set_call_order(self, order):
+        """Deterministic mode: the place of the next Accum call in the summation order (multi-rank: the global file index)."""
+        self._check(cabi.load().gritas_b200_set_call_order(self._h, int(order)))
+
     def sync(self):
         bad = C.c_double(0.0)
         self._check(cabi.load().gritas_b200_sync(self._h, C.byref(bad)), bad)

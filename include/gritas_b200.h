@@ -30,8 +30,11 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
 /* accumulation mode (low byte of `mode`) */
 #define GRITAS_B200_MODE_FAST 0          /* summation order not fixed (<= 1e-6, measured ~1e-15): tiled accumulate (tile lists +
                                             shared-memory histograms) or warp-aggregated fp64 atomics, chosen from the data */
-#define GRITAS_B200_MODE_DETERMINISTIC 1 /* stable sort by box key + in-order segment sums: bit-reproducible,
-                                            same summation order as the reference's sequential loop */
+#define GRITAS_B200_MODE_DETERMINISTIC 1 /* every box is summed in input order (call order, then index within the call):
+                                            bit-reproducible, the same sequence of fp64 additions as the reference's
+                                            sequential loop.  Tiled path: the parked entries carry sequence numbers and the
+                                            tile kernel orders every box's run by them; GRITAS_B200_FLAG_DET_SORT selects
+                                            the older whole-file radix sort + in-order segment sums instead */
 /* flags OR-ed into `mode` */
 #define GRITAS_B200_FLAG_ASYNC 0x100     /* accum returns once inputs are consumed/staged; a level miss is
                                             reported by the next accum/sync/norm instead */
@@ -45,6 +48,8 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
 #define GRITAS_B200_FLAG_NO_WRITEBACK 0x4000 /* gritas_b200_accum reads ob_flag but does not write it back: only GrITAS_LBTally
                                             (-lb, gritas.f:791-796) consumes the flags GrITAS_Accum_ sets (m_gritas_grids.f:413-416);
                                             without it the download and, with ASYNC, the synchronisation per call go away */
+#define GRITAS_B200_FLAG_DET_SORT 0x8000     /* deterministic mode: sort every call by box key (stable radix sort) and add the runs in
+                                            order to the records, instead of the tiled path */
 #define GRITAS_B200_FLAG_HOLD_INPUTS 0x400  /* with ASYNC: the caller keeps pinned input arrays valid until the
                                             next sync/norm, so accum does not even wait for the H2D copies */
 
@@ -55,6 +60,9 @@ typedef struct gritas_b200_ctx *gritas_b200_handle;
 #define GRITAS_B200_ERR_NR 8      /* 'could not handle more then 2 residuals' (m_gritas_grids.f:395, 555) */
 #define GRITAS_B200_ERR_PROFILE 9 /* 'XCov_Accum: not all profiles complete' / 'error in channel matching'
                                      (m_gritas_grids.f:754-757, 789-790) */
+#define GRITAS_B200_ERR_ORDER 10  /* deterministic mode, tiled path: a tile list overflowed, or one box held more parked
+                                     observations than the tile kernel can order at once -- the statistics are complete but
+                                     those observations were added out of input order (not reproducible) */
 #define GRITAS_B200_ERR_CUDA (-1) /* CUDA failure or no device; see gritas_b200_last_error */
 #define GRITAS_B200_ERR_ARG (-2)  /* bad argument */
 #define GRITAS_B200_ERR_NCCL (-3) /* NCCL not loadable / NCCL failure */
@@ -152,6 +160,11 @@ int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
 /* Same wait, but the tile lists of the tiled fast path stay parked (nothing is flushed into the records): what a host
  * that drives several handles needs before a sharded Norm, and what an ASYNC caller uses to pick up a level miss. */
 int gritas_b200_wait(gritas_b200_handle h, double *bad_lev);
+
+/* Deterministic mode: the place of the NEXT accumulate call in the summation order (default: calls since the last
+ * reset).  A multi-rank run that shards one month f mod nranks passes the global file index, so that the sharded Norm adds
+ * every box's observations in the order of the single-process file loop (gritas.f:389-393) whatever the rank count. */
+int gritas_b200_set_call_order(gritas_b200_handle h, uint64_t order);
 
 /* Tiled fast path only: accumulate every staged observation into the HBM records now (asynchronous;
  * sync / norm / get_raw / allreduce do it implicitly).  A no-op in the other modes. */

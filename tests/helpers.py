@@ -8,8 +8,10 @@ from gritas_b200 import cabi, synth
 from gritas_b200.m_gritas_grids import Grids
 from oracle import oracle
 
-# fast (tiled/staged accumulate), fast with the direct fp64-RED accumulate, deterministic
-MODES = [cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, cabi.MODE_FAST | cabi.FLAG_NO_STAGING, cabi.MODE_DETERMINISTIC]
+# fast (tiled/staged accumulate), fast with the direct fp64-RED accumulate, deterministic on the tiled path (sequence
+# numbers in the parked entries, k_tile_det), deterministic with the whole-file radix sort + in-order segment sums
+MODES = [cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, cabi.MODE_FAST | cabi.FLAG_NO_STAGING, cabi.MODE_DETERMINISTIC,
+         cabi.MODE_DETERMINISTIC | cabi.FLAG_DET_SORT]
 
 
 def is_det(mode):
