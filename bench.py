@@ -324,6 +324,7 @@ def run_b200(args):
                         p("qcexcl"), p("omf"), p("oma") if NR == 2 else None, None, None, IOPT, 0, IOPT, 0, -1,
                         -999.0, 999.0, synth.X_PASSIVE, synth.X_PRE_BAD, None, None))
         return out
+    det_order = args.mode == "deterministic" and world > 1
     dptr = [C_void() for _ in range(10)]
     outs10 = (ctypes.c_void_p * 10)()
     host_enqueue = []
@@ -366,7 +367,9 @@ def run_b200(args):
         if marks is not None:
             marks[0].record(stream)
         th = time.perf_counter()
-        for a in cols:
+        for ci, a in enumerate(cols):
+            if det_order:      # deterministic mode on several ranks: every call carries its global file index
+                L.gritas_b200_set_call_order(G.handle, mine[ci] if ci < len(mine) else ci)
             rc = L.gritas_b200_accum_ods(*a)
             if rc:
                 raise RuntimeError(f"accum_ods rc={rc}: {G._err()}")

@@ -635,13 +635,20 @@ void launch_tiles_nr(gritas_b200_handle h, unsigned t0, unsigned t1, int free_sm
   }
 }
 
-int flush_stage(gritas_b200_handle h) {
+int flush_stage(gritas_b200_handle h, unsigned min_fill = 0) {
   if (!h->staging || h->staged_upper == 0) return 0;
   int jr = join_workers(h);
   if (jr) return jr;
   if (h->det_tiled) {
     const OutPlanes none = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-    launch_det_nr<DET_FLUSH>(h, h->compute, 0u, h->sg.ntiles, none, none, 0, 0, 0, 0, PeerSet{});
+    launch_det_nr<DET_FLUSH>(h, h->compute, 0u, h->sg.ntiles, none, none, 0, 0, (int)min_fill, 0, PeerSet{});
+    if (min_fill > 0) {
+      // only the long lists (hot tiles of clustered data) went to their records; the tile kernel marked those tiles dirty,
+      // everything else is still parked and the records of the other tiles are still zero
+      CU(cudaGetLastError());
+      h->launches += 1;
+      return mark_main(h);
+    }
   } else {
     launch_tiles_nr(h, 0u, h->sg.ntiles);
   }
@@ -740,7 +747,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
       if (h->ctrl_valid[q] && cudaEventQuery(h->wk_done[q]) == cudaSuccess) { seen = std::max(seen, h->h_ctrl[4 * q + 2]); h->ctrl_valid[q] = false; }
     cudaGetLastError();
     if (seen > h->sg.cap / 2) {
-      int rc = flush_stage(h);
+      int rc = flush_stage(h, h->sg.cap / 4);
       if (rc) return rc;
       CU(cudaMemsetAsync(h->sg.fill + 2 * (size_t)h->sg.ntiles + 2, 0, sizeof(unsigned), h->compute));
       if ((rc = mark_main(h))) return rc;
@@ -1614,7 +1621,7 @@ static int finalize_to(gritas_b200_handle h, int raw, int nrmlz, int ntresh, dou
       }
     }
   }
-  if (piped) return drain(h, nullptr);
+  if (piped || h->det_tiled) return drain(h, nullptr);     // (deterministic tiled path: the tile kernel may have lost the order of a box)
   CU(cudaStreamSynchronize(h->compute));
   return 0;
 }

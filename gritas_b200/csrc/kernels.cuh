@@ -1550,7 +1550,7 @@ struct TileDet {
   static constexpr int CH = EPT * THREADS;
   static constexpr int NV = TilePlanes<NR>::NV;
   __host__ __device__ static constexpr size_t smem_bytes(size_t T) {
-    return sizeof(double) * ((size_t)NV * T + (size_t)NR * CH) + (size_t)CH * (4 + 2 + 2 + 2) + sizeof(unsigned) * (3 * T + 8);
+    return sizeof(double) * ((size_t)NV * T + (size_t)NR * CH + (size_t)CH) + (size_t)CH * (2 + 2) + sizeof(unsigned) * (3 * T + 8);
   }
 };
 constexpr int DET_FINALIZE = 0, DET_FLUSH = 1, DET_PEERS = 2;
@@ -1566,12 +1566,11 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
   const unsigned T = 1u << sg.tile_shift;
   double *s_val = s_dyn;                                             // [NV][T] running sums of the tile
   double *s_stage = s_val + (size_t)NV * T;                          // [NR][CH] residuals of the group at start(box) + ticket
-  unsigned *s_seq_lo = reinterpret_cast<unsigned *>(s_stage + (size_t)NR * CH);   // [CH] sequence numbers (48 bits: lo, hi)
-  unsigned *s_tot = s_seq_lo + CH;                                   // [T] entries per box (whole list); + record count at the end
+  unsigned long long *s_seq = reinterpret_cast<unsigned long long *>(s_stage + (size_t)NR * CH);   // [CH] sequence numbers
+  unsigned *s_tot = reinterpret_cast<unsigned *>(s_seq + CH);        // [T] entries per box (whole list); + record count at the end
   unsigned *s_off = s_tot + T;                                       // [T + 1] exclusive scan of s_tot
   unsigned *s_cur = s_off + T + 4;                                   // [T] tickets within the current group
-  unsigned short *s_seq_hi = reinterpret_cast<unsigned short *>(s_cur + T + 4);   // [CH]
-  unsigned short *s_inv = s_seq_hi + CH;                             // [CH] position of the entry with rank k of its box
+  unsigned short *s_inv = reinterpret_cast<unsigned short *>(s_cur + T + 4);   // [CH] position of the entry with rank k of its box
   unsigned short *s_boxof = s_inv + CH;                              // [CH] box of the entry at a position
   __shared__ unsigned s_srcoff[MAX_PEERS + 1];
   __shared__ unsigned s_recmask, s_b1, s_warp[32];
@@ -1592,7 +1591,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
     }
     __syncthreads();
     const unsigned n = s_srcoff[nsrc];
-    if (FLUSH && n == 0u) { __syncthreads(); continue; }
+    if (FLUSH && (n == 0u || n < (unsigned)raw2)) { __syncthreads(); continue; }   // FLUSH: raw2 = flush only lists at least this long
     const size_t first = (size_t)tile << sg.tile_shift;
     const unsigned nb = (unsigned)min((size_t)T, (size_t)nrec - first);
     // the sums continue from this rank's records (in order: everything in them is older than anything parked); other
@@ -1608,6 +1607,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
     if (n > 0u) {
       const bool single = n <= (unsigned)CH;                          // the whole list fits one chunk: entries stay in registers
       unsigned long long w[EPT];
+      unsigned tk[EPT];
       double d[EPT][NR];
       auto load = [&](unsigned e, unsigned long long &w0, double (&dd)[NR], bool full) {
         int src = 0;
@@ -1627,7 +1627,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
         }
 #pragma unroll
         for (int u = 0; u < EPT; ++u)
-          if (w[u] != ~0ull) atomicAdd(s_tot + ((unsigned)w[u] & (T - 1u)), 1u);
+          if (w[u] != ~0ull) tk[u] = atomicAdd(s_tot + ((unsigned)w[u] & (T - 1u)), 1u);   // count and ticket in one
       } else {
         for (unsigned c0 = 0; c0 < n; c0 += CH) {
 #pragma unroll
@@ -1722,14 +1722,15 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
           continue;
         }
         {
-          for (unsigned b = b0 + tid; b < b1; b += NTH) s_cur[b] = 0u;
-          __syncthreads();
-          auto place = [&](unsigned long long wv, const double (&dd)[NR]) {
+          if (!single) {
+            for (unsigned b = b0 + tid; b < b1; b += NTH) s_cur[b] = 0u;
+            __syncthreads();
+          }
+          auto place = [&](unsigned long long wv, const double (&dd)[NR], unsigned ticket, bool have_ticket) {
             const unsigned box = (unsigned)wv & (T - 1u);
             if (box < b0 || box >= b1) return;
-            const unsigned rel = s_off[box] - gbase + atomicAdd(s_cur + box, 1u);
-            s_seq_lo[rel] = (unsigned)(wv >> 16);
-            s_seq_hi[rel] = (unsigned short)(wv >> 48);
+            const unsigned rel = s_off[box] - gbase + (have_ticket ? ticket : atomicAdd(s_cur + box, 1u));
+            s_seq[rel] = wv >> 16;
             s_boxof[rel] = (unsigned short)box;
 #pragma unroll
             for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + rel] = dd[ir];
@@ -1737,7 +1738,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
           if (single) {
 #pragma unroll
             for (int u = 0; u < EPT; ++u)
-              if (w[u] != ~0ull) place(w[u], d[u]);
+              if (w[u] != ~0ull) place(w[u], d[u], tk[u], true);
           } else {
             for (unsigned c0 = 0; c0 < n; c0 += CH) {
               unsigned long long wv[EPT];
@@ -1750,22 +1751,60 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
               }
 #pragma unroll
               for (int u = 0; u < EPT; ++u)
-                if (wv[u] != ~0ull) place(wv[u], dv[u]);
+                if (wv[u] != ~0ull) place(wv[u], dv[u], 0u, false);
             }
           }
           __syncthreads();
           const unsigned m = cnt;                                      // entries placed
-          // ---- rank of every entry within its box by sequence number ----
+          // ---- order of every box's run by sequence number: s_inv[start + k] = position of the k-th entry.  Short runs: every
+          // entry counts the smaller sequence numbers of its run.  Long runs (clustered data: a radiosonde site's box holds
+          // hundreds of entries) would make that quadratic: one warp sorts such a run with a bitonic network instead ----
+          constexpr unsigned R0 = 192u;
           for (unsigned pos = tid; pos < m; pos += NTH) {
             const unsigned box = s_boxof[pos];
             const unsigned st = s_off[box] - gbase, r = s_tot[box];
-            const unsigned lo = s_seq_lo[pos], hi = s_seq_hi[pos];
+            if (r > R0) { s_inv[pos] = (unsigned short)pos; continue; }
+            const unsigned long long mine = s_seq[pos];
             unsigned rank = 0u;
-            for (unsigned q = st; q < st + r; ++q) {
-              const unsigned ql = s_seq_lo[q], qh = s_seq_hi[q];
-              rank += (qh < hi || (qh == hi && ql < lo)) ? 1u : 0u;
-            }
+            for (unsigned q = st; q < st + r; ++q) rank += (s_seq[q] < mine) ? 1u : 0u;
             s_inv[st + rank] = (unsigned short)pos;
+          }
+          __syncthreads();
+          for (unsigned b = b0 + wid; b < b1; b += NTH / 32u) {
+            const unsigned r = s_tot[b];
+            if (r <= R0) continue;                                   // (uniform across the warp)
+            const unsigned st = s_off[b] - gbase;
+            unsigned np2 = 64u;
+            while (np2 < r) np2 <<= 1;
+            // bitonic sort, every compare-exchange ascending (mirror step, then half-cleaners): elements beyond r act as
+            // +infinity and never move, so the run needs no padding.  Keys s_seq, payload s_inv.
+            auto cmpx = [&](unsigned a, unsigned c) {
+              if (c >= r) return;
+              const unsigned ia = st + a, ic = st + c;
+              const unsigned long long ka = s_seq[ia], kc = s_seq[ic];
+              if (ka > kc) {
+                s_seq[ia] = kc;
+                s_seq[ic] = ka;
+                const unsigned short t = s_inv[ia];
+                s_inv[ia] = s_inv[ic];
+                s_inv[ic] = t;
+              }
+            };
+            for (unsigned kk = 2u; kk <= np2; kk <<= 1) {
+              const unsigned hk = kk >> 1;
+              for (unsigned i = lane; i < (np2 >> 1); i += 32u) {
+                const unsigned blk = i / hk, off = i - blk * hk;
+                cmpx(blk * kk + off, blk * kk + kk - 1u - off);
+              }
+              __syncwarp();
+              for (unsigned j = kk >> 2; j >= 1u; j >>= 1) {
+                for (unsigned i = lane; i < (np2 >> 1); i += 32u) {
+                  const unsigned a = (i / j) * 2u * j + (i % j);
+                  cmpx(a, a + j);
+                }
+                __syncwarp();
+              }
+            }
           }
           __syncthreads();
           // ---- the owner of a box adds its run in sequence order, continuing the box's sums (one multiply and one add

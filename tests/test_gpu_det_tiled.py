@@ -97,8 +97,7 @@ def test_one_box_beyond_a_chunk_is_reported():
     G.GrITAS_Accum(c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], H.del_of(c, 1), n, 1, table, p1, p2, None, l2d, l3d=l3d)
     out = G.alloc_grids()
     with pytest.raises(RuntimeError, match="out of order"):
-        G.norm_into(out)
-    G.norm_into(out)                                             # the condition is reported once; the sums are complete
+        G.norm_into(out)                                         # reported, and the arrays are filled all the same
     G.close()
     assert out["nobs_3d"].sum() == n
     ref, _ = H.oracle_run(cfg, [c], 1)
@@ -132,4 +131,29 @@ def test_sharded_norm_is_bit_identical_to_one_process(world):
         G.norm_sharded_into(out)
     for G in Gs:
         G.close()
+    H.compare(out, ref, l2d, l3d, 2, exact=True, tol=0.0)
+
+
+@pytest.mark.parametrize("per_box", [33, 192, 193, 256, 257, 700, 1900])
+def test_long_runs_in_few_boxes_bit_exact(per_box):
+    """Hundreds of observations of the same box between two flushes (a radiosonde site): the run is ordered by a warp-level
+    bitonic network instead of the quadratic rank count; lengths around the powers of two and just below a chunk."""
+    cfg = _tiny_grid_cfg(0.004, 24, 13)
+    files = []
+    rng = np.random.default_rng(per_box)
+    for i in range(2):
+        c = synth.make_file(cfg, i)
+        n = len(c["lat"])
+        hot = rng.permutation(n)[: per_box // 2 + (per_box % 2) * (i == 0)]     # the hot box's entries are spread over the file
+        c["lat"][hot], c["lon"][hot], c["lev"][hot] = 33.0, -77.0, 500.0
+        c["kt"][hot], c["kx"][hot], c["qcexcl"][hot] = 44, 120, 0
+        hot2 = np.setdiff1d(rng.permutation(n)[:300], hot)[:250]
+        c["lat"][hot2], c["lon"][hot2], c["lev"][hot2] = 33.0, -77.0, 850.0        # a second long run in the same tile
+        c["kt"][hot2], c["kx"][hot2], c["qcexcl"][hot2] = 44, 120, 0
+        files.append(c)
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    fin = [H.filter_in(c, 101) for c in files]
+    ref, _ = H.oracle_run(cfg, files, 2, fin)
+    assert ref.nobs_3d.max() >= per_box, ref.nobs_3d.max()
+    out, _ = H.gpu_run(cfg, files, 2, DET | cabi.FLAG_ASYNC, fin)
     H.compare(out, ref, l2d, l3d, 2, exact=True, tol=0.0)
