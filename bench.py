@@ -226,7 +226,7 @@ def run_reference(args):
             "config": {"workload": workload_name(cfg, cfg.nfiles), "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -605,7 +605,7 @@ def run_b200(args):
                                           f"pre-sort (gritas.f:499-523) is not included",
                                 "host_cores": os.cpu_count()}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     G.close()
     if world > 1:
         dist.destroy_process_group()
@@ -616,8 +616,19 @@ def C_void():
     return ctypes.pointer(ctypes.c_void_p())
 
 
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    # libraries (NCCL prints its version banner) write to stdout: keep fd 1 for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -291,6 +291,10 @@ struct gritas_b200_ctx {
   bool peer_ipc[MAX_PEERS] = {};      // pointers of rank s came from cudaIpcOpenMemHandle (close them on destroy)
   unsigned *fill_snap = nullptr;      // local snapshot of every rank's fill / dirty / records-touched words
   size_t fill_snap_cap = 0;
+  unsigned long long *slab_prefix = nullptr;   // scratch of k_slab_bounds
+  unsigned *d_bounds = nullptr, *h_bounds = nullptr;   // slab boundaries of the last sharded Norm (device / pinned)
+  cudaEvent_t bounds_ev = nullptr;
+  bool bounds_valid = false;
   double *bar_buf = nullptr;          // operand of the stream-ordered barrier (a one-element all-reduce)
   // device -> pageable host: ring of pinned bounce buffers (copy_out_pageable)
   static constexpr int NBOUNCE = 8;
@@ -1134,8 +1138,11 @@ void gritas_b200_destroy(gritas_b200_handle h) {
     if (h->peer_ipc[r])
       for (void *p : {h->peer_lists[r], h->peer_fill[r], h->peer_acc[r]})
         if (p) cudaIpcCloseMemHandle(p);
-  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red, (void *)h->fill_snap, (void *)h->bar_buf})
+  for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red, (void *)h->fill_snap, (void *)h->bar_buf, (void *)h->slab_prefix,
+                  (void *)h->d_bounds})
     if (p) cudaFree(p);
+  if (h->h_bounds) cudaFreeHost(h->h_bounds);
+  if (h->bounds_ev) cudaEventDestroy(h->bounds_ev);
   for (void *p : {h->ps_cols, h->ps_key[0], h->ps_key[1], h->ps_idx[0], h->ps_idx[1], h->ps_sorted})
     if (p) cudaFree(p);
   for (auto &db : h->det) {
@@ -2093,6 +2100,18 @@ size_t slab_bound(const GridDesc &g, size_t nrec, int r, int n) {
   return (size_t)g.nbox3 + (x - g.nbox3) / g.im * g.im;
 }
 
+Slab slab_from(const GridDesc &g, size_t lo, size_t hi) {
+  Slab s;
+  s.lo = lo;
+  s.hi = hi;
+  const size_t row3 = (size_t)g.im * g.km, n3 = g.nbox3;
+  s.jl3_0 = (int)(std::min(s.lo, n3) / row3);
+  s.jl3_1 = (int)(std::min(s.hi, n3) / row3);
+  s.jl2_0 = (int)((std::max(s.lo, n3) - n3) / g.im);
+  s.jl2_1 = (int)((std::max(s.hi, n3) - n3) / g.im);
+  return s;
+}
+
 Slab slab_of(const GridDesc &g, size_t nrec, int r, int n) {
   Slab s;
   s.lo = slab_bound(g, nrec, r, n);
@@ -2154,7 +2173,7 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
   const int xpl = nr;
   const size_t sz[10] = {n2 * nr, n2 * nr, n2 * nr, n2 * xpl, n2, n3 * nr, n3 * nr, n3 * nr, n3 * xpl, n3};
   const bool raw3 = g.nlevs < 2;   // m_gritas_grids.f:607: the 3-D sums stay raw
-  const Slab sl = slab_of(g, h->nrec, h->prank, h->np);
+  Slab sl = slab_of(g, h->nrec, h->prank, h->np);
   double *dst[10];
   bool bounce[10];
   size_t need = 0;
@@ -2189,11 +2208,29 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
     if ((rc = grow_dev(h, (void **)&h->fill_snap, &h->fill_snap_cap, sizeof(unsigned) * (size_t)nwords * h->np))) return rc;
     k_gather_words<<<148, 256, 0, h->compute>>>(h->fill_snap, ps, nwords);
     for (int s = 0; s < h->np; ++s) ps.fill[s] = h->fill_snap + (size_t)s * nwords;
+    // slabs balanced by parked entries (every rank computes the same boundaries from the same snapshot)
+    static const bool balance = !(getenv("GRITAS_B200_SLAB_BALANCE") && atoi(getenv("GRITAS_B200_SLAB_BALANCE")) == 0);
+    if (balance) {
+      if (!h->d_bounds) {
+        CU(cudaMalloc(&h->d_bounds, sizeof(unsigned) * (MAX_PEERS + 2)));
+        CU(cudaMallocHost(&h->h_bounds, sizeof(unsigned) * (MAX_PEERS + 2)));
+        CU(cudaMalloc(&h->slab_prefix, sizeof(unsigned long long) * ((size_t)h->sg.ntiles + 2)));
+        CU(cudaEventCreateWithFlags(&h->bounds_ev, cudaEventDisableTiming));
+      }
+      k_slab_bounds<<<1, 1024, 0, h->compute>>>(h->fill_snap, nwords, h->np, h->sg, (unsigned)h->nrec, g.nbox3, (unsigned)(g.im * g.km),
+                                              (unsigned)g.im, h->slab_prefix, h->d_bounds);
+      CU(cudaMemcpyAsync(h->h_bounds, h->d_bounds, sizeof(unsigned) * (h->np + 1), cudaMemcpyDeviceToHost, h->compute));
+      CU(cudaEventRecord(h->bounds_ev, h->compute));
+      ps.bounds = h->d_bounds;
+      ps.self = h->prank;
+      h->launches += 1;
+    }
     const OutPlanes o2 = {dst[0], dst[1], dst[2], dst[3], dst[4], xpl};
     const OutPlanes o3 = {dst[5], dst[6], dst[7], dst[8], dst[9], raw3 ? 1 : xpl};
     const int r3 = raw3 ? 1 : 0;
     const unsigned T = 1u << h->sg.tile_shift;
-    const unsigned t0 = (unsigned)(sl.lo >> h->sg.tile_shift), t1 = (unsigned)((sl.hi + T - 1) >> h->sg.tile_shift);
+    unsigned t0 = (unsigned)(sl.lo >> h->sg.tile_shift), t1 = (unsigned)((sl.hi + T - 1) >> h->sg.tile_shift);
+    if (balance) { t0 = 0u; t1 = h->sg.ntiles; }        // the kernel takes its tile range from the device-side boundaries
     if (t1 > t0 && h->det_tiled) {
       launch_det_nr<DET_PEERS>(h, h->compute, t0, t1, o2, o3, nrmlz, ntr, 0, r3, ps);
     } else if (t1 > t0) {
@@ -2207,7 +2244,13 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
     }
     h->launches += 2;
     CU(cudaGetLastError());
+    if (balance) {
+      CU(cudaEventSynchronize(h->bounds_ev));             // (long done: the tile kernel is still running)
+      sl = slab_from(g, h->h_bounds[h->prank], h->h_bounds[h->prank + 1]);
+      h->bounds_valid = true;
+    }
   } else {
+    h->bounds_valid = false;
     // no lists on this path (deterministic mode, GRITAS_B200_FLAG_NO_STAGING): the records of this rank's rows are summed
     // over the ranks in rank order, then finalized by K3.  One-shot: this rank's records then hold the total of its rows.
     const size_t d0 = sl.lo * (size_t)g.rs, d1 = sl.hi * (size_t)g.rs;
@@ -2315,7 +2358,9 @@ int gritas_b200_peer_attach(gritas_b200_handle h, int nranks, int rank, const vo
 
 int gritas_b200_slab(gritas_b200_handle h, int rank, int nranks, int *jl3_0, int *jl3_1, int *jl2_0, int *jl2_1) {
   if (!h || nranks < 1 || rank < 0 || rank >= nranks) return GRITAS_B200_ERR_ARG;
-  const Slab s = slab_of(h->g, h->nrec, rank, nranks);
+  // after a sharded Norm on the tiled path: the boundaries that Norm used (balanced by parked entries, the same on every rank)
+  const Slab s = (h->bounds_valid && nranks == h->np) ? slab_from(h->g, h->h_bounds[rank], h->h_bounds[rank + 1])
+                                                      : slab_of(h->g, h->nrec, rank, nranks);
   if (jl3_0) *jl3_0 = s.jl3_0;
   if (jl3_1) *jl3_1 = s.jl3_1;
   if (jl2_0) *jl2_0 = s.jl2_0;

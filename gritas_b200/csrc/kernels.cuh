@@ -105,7 +105,10 @@ struct StageDesc {
 constexpr int MAX_PEERS = 8;
 struct PeerSet {
   int n;                                  // ranks (sources); lists[self] is this rank's own buffer
-  unsigned own_lo, own_hi;                // records this rank finalizes
+  unsigned own_lo, own_hi;                // records this rank finalizes (from `bounds` when that is set)
+  int self;
+  const unsigned *bounds;                 // [n + 1] record boundaries of the ranks' slabs, computed on the device from the fill
+                                          // counts (k_slab_bounds), or null
   const unsigned char *lists[MAX_PEERS];  // every rank's tile lists (same ntiles / cap / tile_shift on all ranks)
   const unsigned *fill[MAX_PEERS];        // local snapshot of every rank's [tickets | dirty words | records-touched word]
   const double *acc[MAX_PEERS];           // every rank's records (read only where a rank accumulated directly)
@@ -1324,6 +1327,13 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   unsigned *s_warp = s_cnt + T + 4;                        // [32]
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
+  PeerSet pown = peers;                                    // PEER: slab boundaries balanced on the device
+  if (PEER && peers.bounds) {
+    pown.own_lo = peers.bounds[peers.self];
+    pown.own_hi = peers.bounds[peers.self + 1];
+    tile0 = pown.own_lo >> sg.tile_shift;
+    tile1 = (unsigned)(((size_t)pown.own_hi + T - 1u) >> sg.tile_shift);
+  }
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     if (PEER) {
       // the tile's list is the concatenation of every rank's list of this tile (a chunk of the counting sort may span
@@ -1524,7 +1534,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       continue;
     }
     // ---- finalize (m_gritas_grids.f:566-654) straight from the planes ----
-    tile_finalize_out<NR, PEER, MODE == TILE_IMPORT, TF::THREADS>(g, first, nb, T, s_val, s_tot, s_nd, addrec, recmask, peers, o2, o3, raw2, raw3,
+    tile_finalize_out<NR, PEER, MODE == TILE_IMPORT, TF::THREADS>(g, first, nb, T, s_val, s_tot, s_nd, addrec, recmask, pown, o2, o3, raw2, raw3,
                                                                   nrmlz, ntresh, tid);
     __syncthreads();
   }
@@ -1577,6 +1587,13 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;
   const int nsrc = PEER ? peers.n : 1;
+  PeerSet pown = peers;
+  if (PEER && peers.bounds) {
+    pown.own_lo = peers.bounds[peers.self];
+    pown.own_hi = peers.bounds[peers.self + 1];
+    tile0 = pown.own_lo >> sg.tile_shift;
+    tile1 = (unsigned)(((size_t)pown.own_hi + T - 1u) >> sg.tile_shift);
+  }
   for (unsigned tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
     if (tid == 0u) {
       unsigned tot = 0u, mask = 0u;
@@ -1860,7 +1877,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
       __syncthreads();
       continue;
     }
-    tile_finalize_out<NR, PEER, false, NTH>(g, first, nb, T, s_val, s_tot, nullptr, PEER && recmask != 0u, recmask, peers, o2, o3, raw2, raw3,
+    tile_finalize_out<NR, PEER, false, NTH>(g, first, nb, T, s_val, s_tot, nullptr, PEER && recmask != 0u, recmask, pown, o2, o3, raw2, raw3,
                                             nrmlz, ntresh, tid);
     __syncthreads();
   }
@@ -1961,6 +1978,76 @@ k_gather_words(unsigned *__restrict__ dst, const PeerSet src, unsigned nwords) {
   for (int s = 0; s < src.n; ++s)
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < nwords; e += gridDim.x * blockDim.x)
       dst[(size_t)s * nwords + e] = src.fill[s][e];
+}
+
+// Sharded Norm: slab boundaries that give every rank about the same number of parked entries (the tile kernel's time
+// follows the entries, and rows near the equator / frequent variables hold many more than polar rows).  Every rank runs this
+// on the same snapshot of all ranks' fill counts, so every rank gets the same boundaries.  Boundaries are whole rows
+// ((j,l) rows of im*km records in the 3-D part, of im records in the 2-D part).  One block.
+__global__ void __launch_bounds__(1024)
+k_slab_bounds(const unsigned *__restrict__ fills, unsigned nwords, int nranks, StageDesc sg, unsigned nrec, unsigned nbox3, unsigned row3,
+              unsigned row2, unsigned long long *__restrict__ prefix, unsigned *__restrict__ bounds) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_base;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  if (tid == 0u) s_base = 0ull;
+  __syncthreads();
+  // weight of a tile: its parked entries on all ranks, plus one per box for the finalize work it carries anyway
+  for (unsigned o = 0; o < sg.ntiles; o += 1024u) {
+    const unsigned t = o + tid;
+    unsigned long long v = 0ull;
+    if (t < sg.ntiles) {
+      for (int r = 0; r < nranks; ++r) v += min(fills[(size_t)r * nwords + t], sg.cap);
+      v += 1ull << sg.tile_shift;
+    }
+    unsigned long long inc = v;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, sft);
+      if (lane >= (unsigned)sft) inc += x;
+    }
+    if (lane == 31u) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0u) {
+      const unsigned long long w = s_w[lane];
+      unsigned long long wi = w;
+#pragma unroll
+      for (int sft = 1; sft < 32; sft <<= 1) {
+        const unsigned long long x = __shfl_up_sync(0xffffffffu, wi, sft);
+        if (lane >= (unsigned)sft) wi += x;
+      }
+      s_w[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned long long excl = s_base + s_w[wid] + inc - v;
+    if (t < sg.ntiles) prefix[t] = excl;
+    __syncthreads();
+    if (tid == 1023u) s_base = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0u) prefix[sg.ntiles] = s_base;
+  __syncthreads();
+  if (tid <= (unsigned)nranks) {
+    unsigned b;
+    if (tid == 0u) b = 0u;
+    else if (tid == (unsigned)nranks) b = nrec;
+    else {
+      const unsigned long long total = prefix[sg.ntiles], target = total / (unsigned)nranks * tid + total % (unsigned)nranks * tid / (unsigned)nranks;
+      unsigned lo = 0u, hi = sg.ntiles;                       // last tile whose prefix <= target
+      while (lo < hi) { const unsigned mid = (lo + hi + 1u) >> 1; if (prefix[mid] <= target) lo = mid; else hi = mid - 1u; }
+      const unsigned T = 1u << sg.tile_shift;
+      const unsigned long long wt = prefix[min(lo + 1u, sg.ntiles)] - prefix[lo];
+      unsigned long long rec = (unsigned long long)lo * T + (wt ? (target - prefix[lo]) * T / wt : 0ull);
+      if (rec > nrec) rec = nrec;
+      if (rec <= nbox3) rec = (rec + row3 / 2u) / row3 * row3;                      // nearest row of the 3-D part
+      else rec = nbox3 + (rec - nbox3 + row2 / 2u) / row2 * row2;
+      b = (unsigned)min(rec, (unsigned long long)nrec);
+    }
+    bounds[tid] = b;
+  }
+  __syncthreads();
+  if (tid == 0u)                                              // monotone whatever the rounding did
+    for (int r = 1; r <= nranks; ++r) bounds[r] = max(bounds[r], bounds[r - 1]);
 }
 
 // Sharded Norm on the direct / deterministic path (no lists): the records of rows this rank owns are summed over the
