@@ -1355,6 +1355,71 @@ int gritas_b200_accum_odsx(gritas_b200_handle h, int nobs, const gritas_b200_ods
                       o->time, f, ob_flag_out, bad_lev, &rs);
 }
 
+// The -meanres variants of gritas.f:653-677 and 680-691 (a member ODS against the ensemble-mean ODS, both matched to the same
+// order): |iopt| 24/25 del = <omf> - omf, 26/27 del(:,1) = <omf> - omf, del(:,2) = xvec (nr = 2), 30/31 del = <oma> - oma.
+// Where the observation value differs between the two files the reference makes the observation passive and leaves del
+// unset (:656-662); here del is the same difference, which only matters if passive data are kept (ioptn > 0).
+int gritas_b200_accum_odsx_meanres(gritas_b200_handle h, int nobs, const gritas_b200_ods *o, const double *mean_obs,
+                                   const double *mean_omf, const double *mean_oma, int iopt, int ioptn, int t1, int t2, double lona,
+                                   double lonb, int x_passive, int x_pre_bad, int32_t *ob_flag_out, double *bad_lev) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!o || nobs < 0) return fail(h, GRITAS_B200_ERR_ARG, "accum_odsx_meanres: bad arguments");
+  const int a = iopt < 0 ? -iopt : iopt;
+  const bool f24 = a == 24 || a == 25, f26 = a == 26 || a == 27, f30 = a == 30 || a == 31;
+  if (!f24 && !f26 && !f30) return fail(h, GRITAS_B200_ERR_ARG, "iopt %d has no -meanres variant (gritas.f:653-691)", iopt);
+  const int nr = f26 ? 2 : 1;
+  if (nr != h->g.nr) return fail(h, GRITAS_B200_ERR_ARG, "iopt %d needs nr=%d, handle has nr=%d", iopt, nr, h->g.nr);
+  if (nobs == 0) {
+    const double *none[3] = {nullptr, nullptr, nullptr};
+    FilterDesc f0 = {};
+    return accum_common(h, 0, nullptr, nullptr, nullptr, none, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, f0, nullptr, bad_lev);
+  }
+  const double *mres = f30 ? mean_oma : mean_omf, *res = f30 ? o->oma : o->omf;
+  if (!o->obs || !mean_obs || !mres || !res || !o->qcexcl || (f26 && !o->xvec)) return fail(h, GRITAS_B200_ERR_ARG, "accum_odsx_meanres: a column it needs is null");
+  const size_t n = (size_t)nobs;
+  // qcexcl with the mismatches made passive, on the device (scratch of the pre-sort)
+  if ((rc = join_workers(h))) return rc;
+  CU(cudaStreamSynchronize(h->compute));
+  const size_t f8 = (8 * n + 255) & ~(size_t)255, i4 = (4 * n + 255) & ~(size_t)255;
+  if ((rc = grow_dev(h, &h->ps_cols, &h->ps_cols_cap, 2 * f8 + 2 * i4 + 256))) return rc;
+  char *scr = (char *)h->ps_cols;
+  const void *src[3] = {o->obs, mean_obs, o->qcexcl};
+  const size_t bytes[3] = {8 * n, 8 * n, 4 * n}, slot[3] = {f8, f8, i4};
+  const void *dev[3];
+  size_t off = 0;
+  for (int q = 0; q < 3; ++q) {
+    if (mem_kind(src[q]) == 2) { dev[q] = src[q]; continue; }
+    CU(cudaMemcpyAsync(scr + off, src[q], bytes[q], cudaMemcpyHostToDevice, h->compute));
+    h->h2d += bytes[q];
+    dev[q] = scr + off;
+    off += slot[q];
+  }
+  int *qc2 = (int *)(scr + 2 * f8 + i4);
+  k_meanres_qc<<<grid_for(n, 256, 8), 256, 0, h->compute>>>((const double *)dev[0], (const double *)dev[1], (const int *)dev[2], x_passive,
+                                                             qc2, nobs);
+  h->launches++;
+  CU(cudaGetLastError());
+  if ((rc = mark_main(h))) return rc;
+  const double *A[3] = {mres, f26 ? o->xvec : nullptr, nullptr};
+  ResidualSpec rs;
+  rs.b[0] = res;            // del(:,1) = <res> - res
+  rs.sb[0] = -1;
+  rs.expr = 1;
+  FilterDesc f = {};
+  const bool filtered = (a & 1) != 0;                         // gritas.f:710: the filter runs for odd iopt only
+  f.ods = filtered ? 1 : 0;
+  f.ioptn = ioptn;
+  f.t1 = t1; f.t2 = t2;
+  f.use_time = (!filtered || t2 < t1) ? 0 : 1;
+  f.use_lon = (!filtered || (lona < -180.0 && lonb > 180.0)) ? 0 : 1;
+  f.lona = lona; f.lonb = lonb;
+  f.x_passive = x_passive; f.x_pre_bad = x_pre_bad;
+  if (f.use_time && !o->time) return fail(h, GRITAS_B200_ERR_ARG, "time window needs the time column");
+  return accum_common(h, nobs, o->lat, o->lon, o->lev, A, o->obs, o->xvec, o->omf, o->kx, o->kt, filtered ? qc2 : nullptr, o->time, f,
+                      ob_flag_out, bad_lev, &rs);
+}
+
 int gritas_b200_sync(gritas_b200_handle h, double *bad_lev) {
   int rc = check_handle(h);
   if (rc) return rc;

@@ -1904,6 +1904,15 @@ k_sortkey_f64(const double *__restrict__ col, const int *__restrict__ idx, unsig
     key[i] = (unsigned long long)f64_order_key(x) ^ 0x8000000000000000ull;
   }
 }
+// -meanres (gritas.f:653-664, 665-677, 680-691): an observation whose value differs between the member and the ensemble-mean
+// ODS is made passive before the filter runs (qcexcl = X_PASSIVE).
+__global__ void __launch_bounds__(256)
+k_meanres_qc(const double *__restrict__ obs, const double *__restrict__ mean_obs, const int *__restrict__ qcexcl, int x_passive,
+             int *__restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = (obs[i] == mean_obs[i]) ? qcexcl[i] : x_passive;
+}
+
 // The column gathers of gritas.f:510-523: dst(i) = src(is(i)) for up to 8 fp64 and 5 int32 columns in one pass.
 struct GatherCols {
   const double *f_src[8]; double *f_dst[8];

@@ -207,6 +207,21 @@ class Grids:
                                                        C.byref(bad))
         self._check(rc, bad)
 
+    def accum_odsx_meanres(self, ods, mods, iopt, ioptn=None, t1=0, t2=-1, lona=-999.0, lonb=999.0, x_passive=7, x_pre_bad=1,
+                           ob_flag_out=None):
+        """-meanres variants of gritas.f:653-691: `ods` the member, `mods` the ensemble mean (obs, omf, oma)."""
+        cols = cabi.OdsCols()
+        dt = {"time": np.int32, "kt": np.int32, "kx": np.int32, "qcexcl": np.int32}
+        for k, _ in cabi.OdsCols._fields_:
+            v = ods.get(k)
+            setattr(cols, k, cabi.ptr(v, dt.get(k, np.float64)) if v is not None else None)
+        bad = C.c_double(0.0)
+        g = lambda k: cabi.ptr(mods.get(k), np.float64) if mods.get(k) is not None else None
+        rc = cabi.load().gritas_b200_accum_odsx_meanres(self._h, int(ods["lat"].shape[0]), C.byref(cols), g("obs"), g("omf"), g("oma"),
+                                                        iopt, iopt if ioptn is None else ioptn, t1, t2, lona, lonb, x_passive,
+                                                        x_pre_bad, cabi.ptr(ob_flag_out, np.int32), C.byref(bad))
+        self._check(rc, bad)
+
     def set_call_order(self, order):
         """Deterministic mode: the place of the next Accum call in the summation order (multi-rank: the global file index)."""
         self._check(cabi.load().gritas_b200_set_call_order(self._h, int(order)))

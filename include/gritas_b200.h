@@ -154,6 +154,18 @@ int gritas_b200_accum_odsx(gritas_b200_handle h, int nobs, const gritas_b200_ods
                            int ioptn, int t1, int t2, double lona, double lonb, int x_passive, int x_pre_bad,
                            int32_t *ob_flag_out, double *bad_lev);
 
+/*
+ * The -meanres variants (gritas.f:653-677, 680-691: a member ODS against the ensemble-mean ODS in the same order):
+ * |iopt| 24/25 del = <omf> - omf; 26/27 del(:,1) = <omf> - omf, del(:,2) = xvec (nr = 2); 30/31 del = <oma> - oma.
+ * mean_obs / mean_omf / mean_oma are the mean file's columns.  Where obs differs between the two files the observation is
+ * made passive before the filter, as the reference does (the reference leaves del unset there; here it is the same
+ * difference -- it only matters when passive data are kept).
+ */
+int gritas_b200_accum_odsx_meanres(gritas_b200_handle h, int nobs, const gritas_b200_ods *ods, const double *mean_obs,
+                                   const double *mean_omf, const double *mean_oma, int iopt, int ioptn, int t1, int t2,
+                                   double lona, double lonb, int x_passive, int x_pre_bad, int32_t *ob_flag_out,
+                                   double *bad_lev);
+
 /* Wait for all queued work; returns a pending GRITAS_B200_ERR_LEVEL (and its level) if any. */
 int gritas_b200_sync(gritas_b200_handle h, double *bad_lev);
 
