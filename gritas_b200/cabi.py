@@ -47,7 +47,7 @@ SYMBOLS = [
     "gritas_b200_d2h_bytes", "gritas_b200_version",
     "gritas_b200_peer_export", "gritas_b200_peer_attach", "gritas_b200_slab", "gritas_b200_norm_sharded",
     "gritas_b200_norm_sharded_device", "gritas_b200_host_register", "gritas_b200_host_unregister", "gritas_b200_wait",
-    "gritas_b200_scores", "gritas_b200_score_regions", "gritas_b200_accum_odsx_sorted", "gritas_b200_set_call_order", "gritas_b200_accum_odsx_meanres",
+    "gritas_b200_scores", "gritas_b200_score_regions", "gritas_b200_accum_odsx_sorted", "gritas_b200_set_call_order", "gritas_b200_accum_odsx_meanres", "gritas_b200_export_planes",
     "gritas_b200_xcov_create", "gritas_b200_xcov_destroy", "gritas_b200_xcov_reset", "gritas_b200_xcov_accum",
     "gritas_b200_xcov_norm", "gritas_b200_xcov_get_raw", "gritas_b200_xcov_last_error", "gritas_b200_xcov_launch_count",
 ]
@@ -116,6 +116,7 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_host_unregister.argtypes = [_P]
     L.gritas_b200_accum_odsx_sorted.argtypes = [_P, _I, _P, _P] + [_I] * 6 + [_D, _D, _I, _I, _P, _P, C.POINTER(_D)]
     L.gritas_b200_accum_odsx_meanres.argtypes = [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _D, _D, _I, _I, _P, C.POINTER(_D)]
+    L.gritas_b200_export_planes.argtypes = [_P]
     L.gritas_b200_set_call_order.argtypes = [_P, C.c_uint64]
     L.gritas_b200_scores.argtypes = [_P, _I, _P, _I, _I, _P]
     L.gritas_b200_score_regions.argtypes = [_I, _I, _P, _P]

@@ -128,13 +128,17 @@ class CopyPool {
     }
     cv_.notify_all();
   }
-  void submit(void *dst, const void *src, size_t n, std::atomic<int> *done) {
-    const Task t{dst, src, n, done};
-    submit_batch(&t, 1);
+  // one large copy as `parts` tasks: *done starts at 1 - parts and reaches 1 when the last part has landed
+  void submit_split(void *dst, const void *src, size_t n, std::atomic<int> *done, size_t part = (size_t)512 << 10) {
+    const size_t parts = std::max<size_t>(1, (n + part - 1) / part);
+    done->store(1 - (int)parts, std::memory_order_relaxed);
+    std::vector<Task> t(parts);
+    for (size_t i = 0; i < parts; ++i) t[i] = Task{(char *)dst + i * part, (const char *)src + i * part, std::min(part, n - i * part), done};
+    submit_batch(t.data(), parts);
   }
   // the waiting thread copies too instead of spinning
   void wait(std::atomic<int> *done) {
-    while (!done->load(std::memory_order_acquire))
+    while (done->load(std::memory_order_acquire) < 1)
       if (!run_one()) std::this_thread::yield();
   }
  private:
@@ -161,7 +165,7 @@ class CopyPool {
     Task t;
     if (!pop(t)) return false;
     copy_large(t.dst, t.src, t.n);
-    t.done->store(1, std::memory_order_release);
+    t.done->fetch_add(1, std::memory_order_release);   // wait() returns when the counter reaches 1 (or above: see submit_split)
     return true;
   }
   void run() {
@@ -287,7 +291,7 @@ struct gritas_b200_ctx {
   int nranks = 1, rank = 0;
   // sharded Norm over peer memory (gritas_b200_peer_attach): every rank's lists / fill words / records
   int np = 1, prank = 0;
-  void *peer_lists[MAX_PEERS] = {}, *peer_fill[MAX_PEERS] = {}, *peer_acc[MAX_PEERS] = {};
+  void *peer_lists[MAX_PEERS] = {}, *peer_fill[MAX_PEERS] = {}, *peer_acc[MAX_PEERS] = {}, *peer_red[MAX_PEERS] = {};
   bool peer_ipc[MAX_PEERS] = {};      // pointers of rank s came from cudaIpcOpenMemHandle (close them on destroy)
   unsigned *fill_snap = nullptr;      // local snapshot of every rank's fill / dirty / records-touched words
   size_t fill_snap_cap = 0;
@@ -295,6 +299,7 @@ struct gritas_b200_ctx {
   unsigned *d_bounds = nullptr, *h_bounds = nullptr;   // slab boundaries of the last sharded Norm (device / pinned)
   cudaEvent_t bounds_ev = nullptr;
   bool bounds_valid = false;
+  bool export_valid = false;          // h->red holds the planes of the current accumulation state (gritas_b200_export_planes)
   double *bar_buf = nullptr;          // operand of the stream-ordered barrier (a one-element all-reduce)
   // device -> pageable host: ring of pinned bounce buffers (copy_out_pageable)
   static constexpr int NBOUNCE = 8;
@@ -459,8 +464,7 @@ int copy_out_pageable(gritas_b200_handle h, void *user, const void *dev, size_t 
     const int b = (int)(j % NB);
     CU(cudaEventSynchronize(h->bounce_ev[b]));
     const size_t off = j * CB, n = std::min(CB, bytes - off);
-    h->bounce_done[b].store(0, std::memory_order_relaxed);
-    CopyPool::get().submit((char *)user + off, h->bounce[b], n, &h->bounce_done[b]);
+    CopyPool::get().submit_split((char *)user + off, h->bounce[b], n, &h->bounce_done[b]);
     return 0;
   };
   for (size_t i = 0; i < nchunk; ++i) {
@@ -1059,6 +1063,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
     CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_EXPORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_IMPORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    CUC(cudaFuncSetAttribute(k_tile_final<NR_, TILE_IMPORT_PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_final<NR_, TILE_FINALIZE>, TileFinal<NR_>::THREADS, smem)); \
   } while (0)
         if (nr == 1) TF_SETUP(1);
@@ -1136,7 +1141,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
   }
   for (int r = 0; r < MAX_PEERS; ++r)
     if (h->peer_ipc[r])
-      for (void *p : {h->peer_lists[r], h->peer_fill[r], h->peer_acc[r]})
+      for (void *p : {h->peer_lists[r], h->peer_fill[r], h->peer_acc[r], h->peer_red[r]})
         if (p) cudaIpcCloseMemHandle(p);
   for (void *p : {(void *)h->sg.fill, (void *)h->sg.lists, (void *)h->red, (void *)h->fill_snap, (void *)h->bar_buf, (void *)h->slab_prefix,
                   (void *)h->d_bounds})
@@ -1180,6 +1185,7 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   if (rc) return rc;
   if (nobs < 0) return fail(h, GRITAS_B200_ERR_ARG, "nobs < 0");
   h->call_seq += 1;
+  h->export_valid = false;
   if (nobs == 0) return GRITAS_B200_OK;
   if (!lat || !lon || !lev || !kx || !kt) return fail(h, GRITAS_B200_ERR_ARG, "null column");
   for (int ir = 0; ir < h->g.nr; ++ir)
@@ -1462,6 +1468,7 @@ int gritas_b200_reset(gritas_b200_handle h) {
     CU(cudaMemsetAsync(h->g.acc, 0, sizeof(double) * h->nrec * h->g.rs, h->compute));
   }
   h->acc_fresh = true;
+  h->export_valid = false;
   h->det_calls = 0;
   h->call_order_set = false;
   for (bool &v : h->ctrl_valid) v = false;
@@ -2142,9 +2149,9 @@ struct PeerBlob {
   int32_t pid, device, staging, nr, tile_shift, mode;
   uint32_t ntiles, cap;
   uint64_t nrec;
-  uint64_t raw_lists, raw_fill, raw_acc;
+  uint64_t raw_lists, raw_fill, raw_acc, raw_red;
   int32_t ipc_ok, pad;
-  cudaIpcMemHandle_t ipc_lists, ipc_fill, ipc_acc;
+  cudaIpcMemHandle_t ipc_lists, ipc_fill, ipc_acc, ipc_red;
   char host[64];
 };
 static_assert(sizeof(PeerBlob) <= GRITAS_B200_PEER_BLOB_BYTES, "PeerBlob must fit the ABI blob");
@@ -2267,6 +2274,7 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
     ps.lists[s] = (const unsigned char *)h->peer_lists[s];
     ps.fill[s] = (const unsigned *)h->peer_fill[s];
     ps.acc[s] = (const double *)h->peer_acc[s];
+    ps.red[s] = (const double *)h->peer_red[s];
   }
   if (h->staging) {
     const unsigned nwords = 2u * h->sg.ntiles + 4u;
@@ -2284,7 +2292,7 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
       }
       k_slab_bounds<<<1, 1024, 0, h->compute>>>(h->fill_snap, nwords, h->np, h->sg, (unsigned)h->nrec, g.nbox3, (unsigned)(g.im * g.km),
                                               (unsigned)g.im, h->slab_prefix, h->d_bounds);
-      CU(cudaMemcpyAsync(h->h_bounds, h->d_bounds, sizeof(unsigned) * (h->np + 1), cudaMemcpyDeviceToHost, h->compute));
+      CU(cudaMemcpyAsync(h->h_bounds, h->d_bounds, sizeof(unsigned) * (h->np + 2), cudaMemcpyDeviceToHost, h->compute));
       CU(cudaEventRecord(h->bounds_ev, h->compute));
       ps.bounds = h->d_bounds;
       ps.self = h->prank;
@@ -2296,7 +2304,37 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
     const unsigned T = 1u << h->sg.tile_shift;
     unsigned t0 = (unsigned)(sl.lo >> h->sg.tile_shift), t1 = (unsigned)((sl.hi + T - 1) >> h->sg.tile_shift);
     if (balance) { t0 = 0u; t1 = h->sg.ntiles; }        // the kernel takes its tile range from the device-side boundaries
-    if (t1 > t0 && h->det_tiled) {
+    // Entry pull or planes exchange?  A rank that parked more than ~1.5 entries per box moves fewer bytes as sum planes
+    // (48 B per box at nr = 2) than as entries (32 B each).  Every rank sees the same total, hence decides alike.
+    bool planes = false;
+    if (balance && !h->det_tiled && h->peer_red[h->prank] && h->red) {
+      const double thr = getenv("GRITAS_B200_PLANES_ABOVE") ? atof(getenv("GRITAS_B200_PLANES_ABOVE")) : 1.5;
+      CU(cudaEventSynchronize(h->bounds_ev));
+      planes = (double)h->h_bounds[h->np + 1] > thr * (double)h->nrec * (double)h->np;
+      for (int s2 = 0; s2 < h->np; ++s2) planes = planes && h->peer_red[s2] != nullptr;
+    }
+    if (planes) {
+      // K2x: this rank's lists -> its export planes (all tiles); barrier; K3p: the slab's planes summed over the ranks
+      if (!h->comm && !h->export_valid)
+        return fail(h, GRITAS_B200_ERR_ARG, "norm_sharded without a communicator (several handles in one process): the ranks hold "
+                                            "enough entries for the planes exchange -- call gritas_b200_export_planes on every handle first");
+      if (!h->export_valid) {
+        switch (nr) {
+          case 1: launch_tile_export<1>(h, h->compute, 0u, h->sg.ntiles); break;
+          default: launch_tile_export<2>(h, h->compute, 0u, h->sg.ntiles); break;
+        }
+        h->launches += 1;
+      }
+      if ((rc = stream_barrier(h))) return rc;
+      const int ctas = h->tf_ctas;
+#define PIMP_LAUNCH(NR_)                                                                                                              \
+  k_tile_final<NR_, TILE_IMPORT_PEERS><<<ctas, TileFinal<NR_>::THREADS, h->tf_smem, h->compute>>>(g, h->sg, (unsigned)h->nrec, o2, o3, nrmlz, \
+                                                                                                 ntr, 0, r3, 1, t0, t1, nullptr, ps)
+      if (nr == 1) PIMP_LAUNCH(1);
+      else PIMP_LAUNCH(2);
+#undef PIMP_LAUNCH
+      h->launches += 1;
+    } else if (t1 > t0 && h->det_tiled) {
       launch_det_nr<DET_PEERS>(h, h->compute, t0, t1, o2, o3, nrmlz, ntr, 0, r3, ps);
     } else if (t1 > t0) {
       const int ctas = (int)std::min((unsigned)h->tf_ctas, t1 - t0);
@@ -2357,12 +2395,20 @@ int gritas_b200_peer_export(gritas_b200_handle h, void *blob) {
   b.raw_lists = (uint64_t)(uintptr_t)h->sg.lists;
   b.raw_fill = (uint64_t)(uintptr_t)h->sg.fill;
   b.raw_acc = (uint64_t)(uintptr_t)h->g.acc;
+  if (h->staging && h->fused_norm && !h->det_tiled) {
+    // export buffer of the planes exchange (what K2x writes): its address must be known to the peers now
+    const int nv1 = 1 + (h->g.nr == 1 ? 2 : (h->g.nr == 2 ? 5 : 6));
+    const size_t T = (size_t)1 << h->sg.tile_shift;
+    if ((rc = grow_dev(h, (void **)&h->red, &h->red_cap, sizeof(double) * (size_t)nv1 * T * h->sg.ntiles))) return rc;
+  }
+  b.raw_red = (uint64_t)(uintptr_t)h->red;
   gethostname(b.host, sizeof(b.host) - 1);
   b.ipc_ok = 1;
   if (cudaIpcGetMemHandle(&b.ipc_acc, h->g.acc) != cudaSuccess) b.ipc_ok = 0;
   if (h->staging && (cudaIpcGetMemHandle(&b.ipc_lists, h->sg.lists) != cudaSuccess ||
                      cudaIpcGetMemHandle(&b.ipc_fill, h->sg.fill) != cudaSuccess))
     b.ipc_ok = 0;
+  if (h->red && cudaIpcGetMemHandle(&b.ipc_red, h->red) != cudaSuccess) b.ipc_ok = 0;
   cudaGetLastError();
   memset(blob, 0, GRITAS_B200_PEER_BLOB_BYTES);
   memcpy(blob, &b, sizeof(b));
@@ -2403,6 +2449,7 @@ int gritas_b200_peer_attach(gritas_b200_handle h, int nranks, int rank, const vo
       h->peer_lists[s] = (void *)(uintptr_t)b[s].raw_lists;
       h->peer_fill[s] = (void *)(uintptr_t)b[s].raw_fill;
       h->peer_acc[s] = (void *)(uintptr_t)b[s].raw_acc;
+      h->peer_red[s] = (void *)(uintptr_t)b[s].raw_red;
       continue;
     }
     if (strncmp(b[s].host, b[rank].host, sizeof(b[s].host)) != 0)
@@ -2415,6 +2462,7 @@ int gritas_b200_peer_attach(gritas_b200_handle h, int nranks, int rank, const vo
       CU(cudaIpcOpenMemHandle(&h->peer_lists[s], b[s].ipc_lists, cudaIpcMemLazyEnablePeerAccess));
       CU(cudaIpcOpenMemHandle(&h->peer_fill[s], b[s].ipc_fill, cudaIpcMemLazyEnablePeerAccess));
     }
+    if (b[s].raw_red) CU(cudaIpcOpenMemHandle(&h->peer_red[s], b[s].ipc_red, cudaIpcMemLazyEnablePeerAccess));
   }
   h->np = nranks;
   h->prank = rank;
@@ -2458,6 +2506,25 @@ int gritas_b200_norm_sharded_device(gritas_b200_handle h, int nrmlz, int ntresh,
     return finalize_to(h, 0, nrmlz ? 1 : 0, ntresh, u, outs10);
   }
   return finalize_sharded(h, nrmlz ? 1 : 0, ntresh, u, outs10);
+}
+
+// Phase 1 of the planes exchange on its own, for a host that drives several handles without a communicator: every handle
+// exports its tile sums, then every handle runs gritas_b200_norm_sharded.  (With a communicator norm_sharded does both.)
+int gritas_b200_export_planes(gritas_b200_handle h) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->staging || !h->red || h->det_tiled) return 0;      // nothing to export on this path
+  if ((rc = settle(h, true, nullptr))) return rc;
+  switch (h->g.nr) {
+    case 1: launch_tile_export<1>(h, h->compute, 0u, h->sg.ntiles); break;
+    case 2: launch_tile_export<2>(h, h->compute, 0u, h->sg.ntiles); break;
+    default: return 0;
+  }
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->compute));
+  h->export_valid = true;
+  return 0;
 }
 
 int gritas_b200_host_register(void *p, size_t bytes) {

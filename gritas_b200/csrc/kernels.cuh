@@ -112,6 +112,7 @@ struct PeerSet {
   const unsigned char *lists[MAX_PEERS];  // every rank's tile lists (same ntiles / cap / tile_shift on all ranks)
   const unsigned *fill[MAX_PEERS];        // local snapshot of every rank's [tickets | dirty words | records-touched word]
   const double *acc[MAX_PEERS];           // every rank's records (read only where a rank accumulated directly)
+  const double *red[MAX_PEERS];           // every rank's exported tile sums (compact planes), for the planes exchange
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1304,6 +1305,8 @@ constexpr int TILE_FLUSH = 1;      // K2t: add to the HBM records, empty the lis
 constexpr int TILE_EXPORT = 2;     // K2x: write {n, sums} (+ the tile's records, if any) as compact planes: the operand of the
                                    //      reduction across ranks -- 8*(1+NV) bytes per box instead of a 64-byte record
 constexpr int TILE_IMPORT = 3;     // K3x: no list; the planes come from the reduced buffer, then the statistics as K2f
+constexpr int TILE_IMPORT_PEERS = 5;   // K3p: sharded Norm, planes exchange: the tile's {n, sums} planes are summed over every rank's export buffer
+                                       //      (peer memory over NVLink) and finalized -- used when the ranks park more entries than boxes
 constexpr int TILE_PEERS = 4;      // K2p: K2f of a sharded multi-rank Norm -- the tile's entries are pulled from the lists of
                                    //      every rank (peer memory over NVLink), only the boxes this rank owns are finalized
 
@@ -1314,6 +1317,8 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
              int raw2, int raw3, int fresh, unsigned tile0, unsigned tile1, double *__restrict__ red, const PeerSet peers) {
   constexpr bool FLUSH = MODE == TILE_FLUSH;
   constexpr bool PEER = MODE == TILE_PEERS;
+  constexpr bool PIMP = MODE == TILE_IMPORT_PEERS;
+  constexpr bool IMPORT = MODE == TILE_IMPORT || PIMP;
   __shared__ unsigned s_off[MAX_PEERS + 1];                // PEER: start of every rank's entries in the tile's virtual list
   __shared__ unsigned s_recmask;                           // PEER: ranks whose records hold part of this tile
   using TF = TileFinal<NR>;
@@ -1328,7 +1333,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const unsigned PT = (T + NTH - 1) / NTH;                 // counters per thread in the scan
   PeerSet pown = peers;                                    // PEER: slab boundaries balanced on the device
-  if (PEER && peers.bounds) {
+  if ((PEER || PIMP) && peers.bounds) {
     pown.own_lo = peers.bounds[peers.self];
     pown.own_hi = peers.bounds[peers.self + 1];
     tile0 = pown.own_lo >> sg.tile_shift;
@@ -1351,15 +1356,23 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       }
       __syncthreads();
     }
-    const unsigned n = (MODE == TILE_IMPORT) ? 0u : (PEER ? s_off[peers.n] : min(sg.fill[tile], sg.cap));
+    const unsigned n = IMPORT ? 0u : (PEER ? s_off[peers.n] : min(sg.fill[tile], sg.cap));
     if (FLUSH && n == 0u) continue;                       // uniform across the CTA
     // records untouched since the reset (no flush, no direct accumulate into this tile): they are zero, do not read them
     const unsigned recmask = PEER ? s_recmask : 0u;
-    const bool addrec = PEER ? (recmask != 0u) : ((MODE != TILE_IMPORT) && (!fresh || sg.dirty[tile] != 0u));
+    const bool addrec = PEER ? (recmask != 0u) : (!IMPORT && (!fresh || sg.dirty[tile] != 0u));
     // compact planes of this tile in the reduction buffer: [1 + NV][T] doubles, the counts first
     double *rplanes = (MODE == TILE_EXPORT || MODE == TILE_IMPORT) ? red + (size_t)tile * (size_t)(1 + NV) * T : nullptr;
-    double *s_nd = s_stage;                                 // TILE_IMPORT: [T] counts as doubles (the staging area is idle)
-    if (MODE == TILE_IMPORT) {
+    double *s_nd = s_stage;                                 // IMPORT: [T] counts as doubles (the staging area is idle)
+    if (PIMP) {
+      // every rank's planes of this tile, summed in rank order (reproducible), straight from peer memory
+      const size_t toff = (size_t)tile * (size_t)(1 + NV) * T;
+      for (unsigned e = tid; e < (1u + NV) * T; e += NTH) {
+        double v = 0.0;
+        for (int src = 0; src < peers.n; ++src) v = __dadd_rn(v, __ldcs(peers.red[src] + toff + e));
+        if (e < T) s_nd[e] = v; else s_val[e - T] = v;
+      }
+    } else if (MODE == TILE_IMPORT) {
       for (unsigned e = tid; e < T; e += NTH) s_nd[e] = __ldcs(rplanes + e);
       for (unsigned e = tid; e < NV * T; e += NTH) s_val[e] = __ldcs(rplanes + T + e);
     } else if (n == 0u) {                                   // empty list: nothing will store the planes
@@ -1534,8 +1547,8 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       continue;
     }
     // ---- finalize (m_gritas_grids.f:566-654) straight from the planes ----
-    tile_finalize_out<NR, PEER, MODE == TILE_IMPORT, TF::THREADS>(g, first, nb, T, s_val, s_tot, s_nd, addrec, recmask, pown, o2, o3, raw2, raw3,
-                                                                  nrmlz, ntresh, tid);
+    tile_finalize_out<NR, PEER || PIMP, IMPORT, TF::THREADS>(g, first, nb, T, s_val, s_tot, s_nd, addrec, recmask, pown, o2, o3, raw2, raw3,
+                                                             nrmlz, ntresh, tid);
     __syncthreads();
   }
 }
@@ -2055,8 +2068,11 @@ k_slab_bounds(const unsigned *__restrict__ fills, unsigned nwords, int nranks, S
     bounds[tid] = b;
   }
   __syncthreads();
-  if (tid == 0u)                                              // monotone whatever the rounding did
+  if (tid == 0u) {                                            // monotone whatever the rounding did
     for (int r = 1; r <= nranks; ++r) bounds[r] = max(bounds[r], bounds[r - 1]);
+    const unsigned long long entries = prefix[sg.ntiles] - ((unsigned long long)sg.ntiles << sg.tile_shift);
+    bounds[nranks + 1] = (unsigned)min(entries, 0xFFFFFFFFull);   // parked entries of all ranks: entry pull or planes exchange?
+  }
 }
 
 // Sharded Norm on the direct / deterministic path (no lists): the records of rows this rank owns are summed over the

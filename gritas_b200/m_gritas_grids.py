@@ -396,6 +396,10 @@ class Grids:
         assert len(raw) == nranks * cabi.PEER_BLOB_BYTES
         self._check(cabi.load().gritas_b200_peer_attach(self._h, nranks, rank, C.create_string_buffer(raw, len(raw))))
 
+    def export_planes(self):
+        """Phase 1 of the planes exchange for a host that drives several handles without a communicator."""
+        self._check(cabi.load().gritas_b200_export_planes(self._h))
+
     def slab(self, rank, nranks):
         """Rows (jl = j + jm*l, 0-based, half-open) of the 3-D and the 2-D grids that `rank` finalizes and writes."""
         v = [C.c_int(0) for _ in range(4)]

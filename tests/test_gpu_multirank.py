@@ -114,12 +114,16 @@ def _worker_sharded(rank, world, nfiles, uid_q, blob_qs, out_q, mode):
     G.close()
 
 
-@pytest.mark.parametrize("mode", [0x1000, 1])     # fast on the tiled path (entries pulled over NVLink), deterministic (records)
-def test_two_rank_sharded_norm_over_ipc_matches_oracle(mode):
+# fast on the tiled path (entries pulled over NVLink), the same with the planes exchange forced, deterministic (entries merged
+# by sequence number)
+@pytest.mark.parametrize("mode,planes", [(0x1000, False), (0x1000, True), (1, False)])
+def test_two_rank_sharded_norm_over_ipc_matches_oracle(mode, planes, monkeypatch):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
+    if planes:
+        monkeypatch.setenv("GRITAS_B200_PLANES_ABOVE", "0")      # inherited by the spawned ranks
 
     from gritas_b200 import synth
     world, nfiles = 2, 5

@@ -28,6 +28,8 @@ def _run(cfg, files, nr, world, mode, iopt, nrmlz=True, ntresh=None, env_slots=N
             G.accum_ods(files[fi], iopt=iopt, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
     for G in Gs:
         G.sync_no_flush()
+    for G in Gs:
+        G.export_planes()        # (no communicator here: phase 1 of the planes exchange, used when the data are dense)
     out = Gs[0].alloc_grids()
     for a in out.values():
         a[...] = -777.0          # every box must be written by exactly one rank
@@ -150,3 +152,28 @@ def test_peer_attach_rejects_mismatched_ranks():
             G.peer_attach(2, r, blobs)
     A.close()
     B.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_norm_planes_exchange(world, monkeypatch):
+    """When the ranks park more entries than ~1.5 per box, the sharded Norm exchanges sum planes instead of entries: every rank
+    exports its tiles' {n, sums} (K2x) and the owner of a slab sums the ranks' planes through peer memory (K3p).  Forced here
+    with GRITAS_B200_PLANES_ABOVE=0; the threshold itself is exercised with dense data (few boxes, many observations)."""
+    monkeypatch.setenv("GRITAS_B200_PLANES_ABOVE", "0")
+    cfg = synth.get_config("cfg2", 0.02)
+    cfg.im, cfg.jm = 72, 46
+    files = [synth.make_file(cfg, i) for i in range(9)]
+    out, slabs, tiled, (l2d, l3d) = _run(cfg, files, 2, world, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, 101)
+    ref, _ = H.oracle_run(cfg, files, 2, [H.filter_in(c, 101) for c in files])
+    H.compare(out, ref, l2d, l3d, 2, exact=False, tol=1e-6)
+    monkeypatch.delenv("GRITAS_B200_PLANES_ABOVE")
+
+
+def test_sharded_norm_dense_data_takes_the_planes_path():
+    """8 x 5 x 26 x 16 boxes, ~290 K accepted observations on 3 ranks: ~6 entries per box and rank -> planes."""
+    cfg = synth.get_config("cfg2", 0.1)
+    cfg.im, cfg.jm = 8, 5
+    files = [synth.make_file(cfg, i) for i in range(3)]
+    out, slabs, tiled, (l2d, l3d) = _run(cfg, files, 1, 3, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, 1)
+    ref, _ = H.oracle_run(cfg, files, 1, [H.filter_in(c, 1) for c in files])
+    H.compare(out, ref, l2d, l3d, 1, exact=False, tol=1e-6)
