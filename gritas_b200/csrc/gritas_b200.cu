@@ -2304,11 +2304,13 @@ int finalize_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double *const 
     const unsigned T = 1u << h->sg.tile_shift;
     unsigned t0 = (unsigned)(sl.lo >> h->sg.tile_shift), t1 = (unsigned)((sl.hi + T - 1) >> h->sg.tile_shift);
     if (balance) { t0 = 0u; t1 = h->sg.ntiles; }        // the kernel takes its tile range from the device-side boundaries
-    // Entry pull or planes exchange?  A rank that parked more than ~1.5 entries per box moves fewer bytes as sum planes
-    // (48 B per box at nr = 2) than as entries (32 B each).  Every rank sees the same total, hence decides alike.
+    // Entry pull or planes exchange?  Per rank the entry pull moves 32 B x (entries the rank parked) x (N-1)/N over NVLink, the
+    // planes exchange 48 B x boxes x (N-1)/N (nr = 2) plus one more pass over the rank's lists and the planes (K2x).  Measured
+    // at cfg2: the pull wins at 2.25 entries per box and rank (N = 2 month: 1.9 against 2.7 ms), the planes win at 4.5 (eight
+    // months on 8 ranks).  Every rank sees the same total, hence decides alike.
     bool planes = false;
     if (balance && !h->det_tiled && h->peer_red[h->prank] && h->red) {
-      const double thr = getenv("GRITAS_B200_PLANES_ABOVE") ? atof(getenv("GRITAS_B200_PLANES_ABOVE")) : 1.5;
+      const double thr = getenv("GRITAS_B200_PLANES_ABOVE") ? atof(getenv("GRITAS_B200_PLANES_ABOVE")) : 3.0;
       CU(cudaEventSynchronize(h->bounds_ev));
       planes = (double)h->h_bounds[h->np + 1] > thr * (double)h->nrec * (double)h->np;
       for (int s2 = 0; s2 < h->np; ++s2) planes = planes && h->peer_red[s2] != nullptr;

@@ -320,9 +320,9 @@ int gritas_b200_norm_sharded(gritas_b200_handle h, int nrmlz, int ntresh, double
                              double *xcov_2d, double *nobs_2d, double *bias_3d, double *rtms_3d, double *stdv_3d,
                              double *xcov_3d, double *nobs_3d);
 int gritas_b200_norm_sharded_device(gritas_b200_handle h, int nrmlz, int ntresh, const double **outs10);
-/* The sharded Norm exchanges parked ENTRIES (32 B each) while a rank parks fewer than ~1.5 per box, and sum PLANES
+/* The sharded Norm exchanges parked ENTRIES (32 B each) while a rank parks fewer than ~3 per box, and sum PLANES
  * (8*(1+2nr+...) B per box: each rank exports its tiles' {n, sums}, the owner of a slab sums the ranks' planes through peer
- * memory) beyond -- every rank sees the same totals and decides alike (GRITAS_B200_PLANES_ABOVE overrides 1.5).  With a
+ * memory) beyond -- every rank sees the same totals and decides alike (GRITAS_B200_PLANES_ABOVE overrides 3).  With a
  * communicator norm_sharded does the export itself; a host that drives several handles without one calls this on every
  * handle before the first norm_sharded. */
 int gritas_b200_export_planes(gritas_b200_handle h);
