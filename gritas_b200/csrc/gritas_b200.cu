@@ -2117,6 +2117,25 @@ int gritas_b200_comm_init(gritas_b200_handle h, int nranks, int rank, const void
   if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
   h->nranks = nranks;
   h->rank = rank;
+  // What shapes the collectives of the multi-rank Norm (tiled or not, tile size, list capacity, pipeline settings from the
+  // GRITAS_B200_* environment) must be the same on every rank: a max-reduction of (sig, -sig) tells every rank alike.
+  if (nranks > 1) {
+    const char *e_c = getenv("GRITAS_B200_PIPE_CHUNKS"), *e_r = getenv("GRITAS_B200_COMPACT_REDUCE");
+    const double sig = (double)((h->staging ? 1 : 0) + 2 * (h->fused_norm ? 1 : 0) + 4 * (h->det_tiled ? 1 : 0)) + 8.0 * h->g.nr +
+                       64.0 * (h->staging ? h->sg.tile_shift : 0) + 4096.0 * (e_c ? atoi(e_c) : 8) + 65536.0 * (e_r ? atoi(e_r) : 1) +
+                       1048576.0 * (double)((h->staging ? h->sg.cap : 0) % 1000003u) + 1.0e13 * (double)(h->nrec % 100003u);
+    double host[2] = {sig, -sig};
+    if (!h->bar_buf) CU(cudaMalloc(&h->bar_buf, 64));
+    CU(cudaMemcpyAsync(h->bar_buf, host, sizeof(host), cudaMemcpyHostToDevice, h->compute));
+    e = g_nccl.AllReduce(h->bar_buf, h->bar_buf, 2, NCCL_FLOAT64, /*ncclMax*/ 2, h->comm, h->compute);
+    if (e != 0) return fail(h, GRITAS_B200_ERR_NCCL, "ncclAllReduce (settings check): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    CU(cudaMemcpyAsync(host, h->bar_buf, sizeof(host), cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    CU(cudaMemsetAsync(h->bar_buf, 0, 64, h->compute));
+    if (host[0] != -host[1])
+      return fail(h, GRITAS_B200_ERR_ARG, "comm_init: the ranks were created with different grids, modes or GRITAS_B200_* settings "
+                                          "(the collectives of the multi-rank Norm would not match)");
+  }
   return 0;
 }
 

@@ -1294,6 +1294,9 @@ struct TileFinal {
   static constexpr int EPT = (NR == 3) ? 4 : 6;           // entries per thread and chunk
   static constexpr int CH = EPT * THREADS;                // chunk of the list sorted at a time
   static constexpr int NV = TilePlanes<NR>::NV;
+  // an entry's box within the tile and its rank within the box are packed into 16 + 16 bits while the chunk is sorted: tiles hold
+  // at most 2^15 records (GRITAS_B200_TILE_SHIFT <= 15, checked in create) and a chunk fewer than 2^16 entries
+  static_assert(CH < 65536, "rank within a chunk must fit 16 bits");
   __host__ __device__ static constexpr size_t smem_bytes(size_t T) {
     return sizeof(double) * ((size_t)NV * T + (size_t)NR * CH) + sizeof(unsigned) * (2 * T + 4 + 32);
   }
@@ -1800,9 +1803,14 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
             s_inv[st + rank] = (unsigned short)pos;
           }
           __syncthreads();
-          for (unsigned b = b0 + wid; b < b1; b += NTH / 32u) {
+          // (the lanes of a warp look at 32 boxes at a time; the long runs among them are then sorted one after the other)
+          for (unsigned bb = b0 + wid * 32u; bb < b1; bb += NTH) {
+            const unsigned bl = bb + lane;
+            unsigned longs = __ballot_sync(0xffffffffu, bl < b1 && s_tot[bl] > R0);
+            while (longs) {
+            const unsigned b = bb + (unsigned)__ffs(longs) - 1u;
+            longs &= longs - 1u;
             const unsigned r = s_tot[b];
-            if (r <= R0) continue;                                   // (uniform across the warp)
             const unsigned st = s_off[b] - gbase;
             unsigned np2 = 64u;
             while (np2 < r) np2 <<= 1;
@@ -1834,6 +1842,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
                 }
                 __syncwarp();
               }
+            }
             }
           }
           __syncthreads();
