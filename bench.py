@@ -466,6 +466,14 @@ def run_b200(args):
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "note": "bytes summed over the ranks; pinned host columns -> gritas_b200_accum_ods -> Norm -> pinned host "
                        "mean/rms/stdv/xcov/nobs grids" + ("" if world == 1 else " (every rank copies its slab of rows)")}
+        try:   # the box's host <-> device copy ceiling with this many ranks copying at once (tools/h2d_probe.py, committed runs)
+            pr = json.load(open(os.path.join(ROOT, "profiles", f"r2_h2d_probe_n{world}.json")))
+            floor = h2d / (pr["h2d_all_gbs_total"] * 1e9) + d2h / (pr["d2h_all_gbs_total"] * 1e9)
+            e2e["copy_floor_ms"] = floor * 1e3
+            e2e["frac_of_copy_floor"] = floor / dt
+            e2e["copy_floor_source"] = f"profiles/r2_h2d_probe_n{world}.json: {pr['h2d_all_gbs_total']:.0f} GB/s H2D, {pr['d2h_all_gbs_total']:.0f} GB/s D2H in total with {world} rank(s) copying"
+        except Exception:
+            pass
         del pin_files
 
     # ---- the drop-in's end to end: what an untouched gritas.f gets through fortran/m_gritas_b200.F90 ----

@@ -177,3 +177,19 @@ def test_sharded_norm_dense_data_takes_the_planes_path():
     out, slabs, tiled, (l2d, l3d) = _run(cfg, files, 1, 3, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, 1)
     ref, _ = H.oracle_run(cfg, files, 1, [H.filter_in(c, 1) for c in files])
     H.compare(out, ref, l2d, l3d, 1, exact=False, tol=1e-6)
+
+
+def test_static_slab_matches_the_python_twin():
+    """gritas_b200_slab before any sharded Norm = shard.slab_rows (the partition the CPU gloo test uses)."""
+    for (im, jm, lists) in ((72, 46, None), (24, 13, None)):
+        cfg = synth.get_config("cfg1", 0.01)
+        cfg.im, cfg.jm = im, jm
+        cfg.kt_list = [44, 4, 5, 1, 2, 3, 44]
+        cfg.kx_lists = [[120, 130], [220], [220], [181, 187], [181], [180], [130]]
+        table, l2d, l3d, p1, p2 = H.setup(cfg)
+        G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_FAST | cabi.FLAG_FORCE_TILED)
+        G._ensure(1, table, p1, p2, l2d, l3d)
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert G.slab(r, world) == shard.slab_rows(cfg.im, cfg.jm, cfg.km, l2d, l3d, r, world)
+        G.close()
