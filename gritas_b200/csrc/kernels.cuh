@@ -1572,7 +1572,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
 template <int NR>
 struct TileDet {
   static constexpr int THREADS = 512;
-  static constexpr int EPT = (NR == 3) ? 3 : 4;
+  static constexpr int EPT = (NR == 1) ? 5 : ((NR == 3) ? 3 : 4);   // as many as leave two CTAs per SM (tiles: 2048 / 1024 / 1024 boxes)
   static constexpr int CH = EPT * THREADS;
   static constexpr int NV = TilePlanes<NR>::NV;
   __host__ __device__ static constexpr size_t smem_bytes(size_t T) {

@@ -193,3 +193,54 @@ def test_static_slab_matches_the_python_twin():
             for r in range(world):
                 assert G.slab(r, world) == shard.slab_rows(cfg.im, cfg.jm, cfg.km, l2d, l3d, r, world)
         G.close()
+
+
+def test_sharded_norm_with_an_idle_rank_and_a_direct_path_rank():
+    """Rank 2 gets no file at all; rank 1 runs the direct kernel (its files are too small for the locality probe, so its
+    data sit in its records, not in lists): the owners add those records on top of the entries they pull."""
+    cfg = synth.get_config("cfg2", 0.02)
+    cfg.im, cfg.jm = 72, 46
+    files = [synth.make_file(cfg, i) for i in range(4)]
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    modes = [cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, cabi.MODE_FAST, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED]
+    Gs = [Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=m) for m in modes]
+    for G in Gs:
+        G._ensure(2, table, p1, p2, l2d, l3d)
+    blobs = [G.peer_export() for G in Gs]
+    for r, G in enumerate(Gs):
+        G.peer_attach(3, r, blobs)
+    for fi, c in enumerate(files):
+        Gs[fi % 2].accum_ods(c, iopt=101, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
+    assert cabi.load().gritas_b200_tiled(Gs[1].handle) != 1          # undecided / direct: nothing parked on rank 1
+    for G in Gs:
+        G.sync_no_flush()
+    for G in Gs:
+        G.export_planes()
+    out = Gs[0].alloc_grids()
+    for a in out.values():
+        a[...] = -777.0
+    for G in Gs:
+        G.norm_sharded_into(out)
+    for G in Gs:
+        G.close()
+    ref, _ = H.oracle_run(cfg, files, 2, [H.filter_in(c, 101) for c in files])
+    H.compare(out, ref, l2d, l3d, 2, exact=False, tol=1e-6)
+
+
+def test_sharded_norm_surface_grids_only():
+    cfg = synth.get_config("cfg1", 0.03)
+    cfg.im, cfg.jm = 144, 91
+    cfg.kt_list = [1, 2, 3, -44]
+    cfg.kx_lists = [[181, 187], [181], [180], [120]]
+    files = []
+    for i in range(3):
+        c = synth.make_file(synth.get_config("cfg1", 0.03), i)
+        rng = np.random.default_rng(200 + i)
+        row = rng.integers(0, 4, len(c["lat"]))
+        c["kt"] = np.asarray([1, 2, 3, 44], np.int32)[row]
+        c["kx"] = np.asarray([181, 181, 180, 120], np.int32)[row]
+        files.append(c)
+    out, slabs, tiled, (l2d, l3d) = _run(cfg, files, 1, 3, cabi.MODE_FAST | cabi.FLAG_FORCE_TILED, 1)
+    assert (l2d, l3d) == (4, 0)
+    ref, _ = H.oracle_run(cfg, files, 1, [H.filter_in(c, 1) for c in files])
+    H.compare(out, ref, l2d, l3d, 1, exact=False, tol=1e-6)
