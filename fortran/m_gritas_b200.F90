@@ -38,6 +38,7 @@
       public :: B200_GetRaw, B200_Reset, B200_Wait, B200_Clean, B200_PreSort
       public :: B200_UniqueId, B200_CommInit, B200_PeerExport, B200_PeerAttach, B200_Slab
       public :: B200_Norm_Sharded, B200_Norm_Reduce
+      public :: B200_XCov_Accum, B200_XCov_Prs_Accum, B200_XCov_Norm, B200_XCov_Clean
       public :: B200_PEER_BLOB_BYTES
 
       integer(c_int), parameter :: MODE_FAST = 0, MODE_DETERMINISTIC = 1
@@ -47,6 +48,7 @@
       real(c_double), parameter :: AMISS = 1.0D15                      ! m_gritas_grids.f:72
 
       type(c_ptr), save      :: handle = c_null_ptr
+      type(c_ptr), save      :: xhandle = c_null_ptr            ! cross-covariance context (GrITAS_XCov_*)
       integer(c_int), save   :: mode   = MODE_FAST
       integer(c_int), save   :: flags  = 0
 !     host count grids filled by the last B200_Norm: position of one non-zero count (0: none)
@@ -204,6 +206,57 @@
             integer(c_int), value             :: rank, nranks
             integer(c_int), intent(out)       :: jl3_0, jl3_1, jl2_0, jl2_1
          end function
+         integer(c_int) function gritas_b200_xcov_create ( h, km, nchan, achan, l3d, nr, tch, kxkt_table, kxmax, ktmax, device ) &
+                                  bind(C, name='gritas_b200_xcov_create')
+            import :: c_ptr, c_int
+            type(c_ptr),    intent(out)       :: h
+            integer(c_int), value             :: km, nchan
+            integer(c_int), intent(in)        :: achan(*)
+            integer(c_int), value             :: l3d, nr, tch
+            integer(c_int), intent(in)        :: kxkt_table(*)
+            integer(c_int), value             :: kxmax, ktmax, device
+         end function
+         integer(c_int) function gritas_b200_xcov_prs_create ( h, nlevs, p1, p2, l3d, nr, tch, device )                         &
+                                  bind(C, name='gritas_b200_xcov_prs_create')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    intent(out)       :: h
+            integer(c_int), value             :: nlevs
+            real(c_double), intent(in)        :: p1(*), p2(*)
+            integer(c_int), value             :: l3d, nr, tch, device
+         end function
+         integer(c_int) function gritas_b200_xcov_accum ( h, nobs, lev, kx, kt, del, ob_flag, nprof )                           &
+                                  bind(C, name='gritas_b200_xcov_accum')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            integer(c_int), value             :: nobs
+            real(c_double), intent(in)        :: lev(*)
+            integer(c_int), intent(in)        :: kx(*), kt(*)
+            real(c_double), intent(in)        :: del(*)
+            integer(c_int), intent(inout)     :: ob_flag(*)
+            integer(c_int), intent(out)       :: nprof
+         end function
+         integer(c_int) function gritas_b200_xcov_prs_accum ( h, nobs, lev, ks, del, nprof, bad_lev )                           &
+                                  bind(C, name='gritas_b200_xcov_prs_accum')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            integer(c_int), value             :: nobs
+            real(c_double), intent(in)        :: lev(*)
+            integer(c_int), intent(in)        :: ks(*)
+            real(c_double), intent(in)        :: del(*)
+            integer(c_int), intent(out)       :: nprof
+            real(c_double), intent(out)       :: bad_lev
+         end function
+         integer(c_int) function gritas_b200_xcov_norm ( h, nrmlz, self, ntresh, bias_lv, xcov_lv, nobs_lv )                    &
+                                  bind(C, name='gritas_b200_xcov_norm')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr),    value             :: h
+            integer(c_int), value             :: nrmlz, self, ntresh
+            real(c_double), intent(inout)     :: bias_lv(*), xcov_lv(*), nobs_lv(*)
+         end function
+         subroutine gritas_b200_xcov_destroy ( h ) bind(C, name='gritas_b200_xcov_destroy')
+            import :: c_ptr
+            type(c_ptr), value :: h
+         end subroutine
       end interface
 
       contains
@@ -575,6 +628,74 @@
       rc = gritas_b200_wait ( handle, bad_lev )
       call check_accum_ ( rc, bad_lev )
       end subroutine B200_Wait
+
+!     GrITAS_XCov_Accum_ (m_gritas_grids.f:667-670) plus the module variables km, nchan and the achan(:,ichan_version) column
+!     (m_gritas_grids.f:26, 28, 69-71).  lat / lon are arguments of the reference routine that it never reads.
+      subroutine B200_XCov_Accum ( km, nchan, achan, lev, kx, kt, del, nobs, nr, kxkt_table, ob_flag, l3d, nprof, tch )
+      use m_odsmeta, only : KTMAX, KXMAX
+      integer, intent(in)           :: km, nchan, nobs, nr, l3d
+      integer(c_int), intent(in)    :: achan(*), kx(*), kt(*), kxkt_table(*)
+      real(c_double), intent(in)    :: lev(*), del(*)
+      integer(c_int), intent(inout) :: ob_flag(*)
+      integer, intent(out)          :: nprof
+      logical, intent(in)           :: tch
+      integer(c_int) :: rc, itch, np
+      itch = 0
+      if ( tch ) itch = 1
+      if ( .not. c_associated(xhandle) ) then
+         rc = gritas_b200_xcov_create ( xhandle, km, nchan, achan, l3d, nr, itch, kxkt_table, KXMAX, KTMAX, -1_c_int )
+         if ( rc /= 0 ) call gritas_perror ('XCov_Accum: improper dim settings / cannot create the B200 context')   ! :734-745
+      end if
+      rc = gritas_b200_xcov_accum ( xhandle, nobs, lev, kx, kt, del, ob_flag, np )
+      if ( rc /= 0 ) call gritas_perror ('XCov_Accum: not all profiles complete, aborting ...')                   ! :754-757
+      nprof = np
+      print *, 'GrITAS_XCov_Accum, total profiles processed = ', nprof                                              ! :840
+      end subroutine B200_XCov_Accum
+
+!     GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-1865) plus nlevs; kx / kt / kxkt_table / ob_flag are unused by the reference.
+      subroutine B200_XCov_Prs_Accum ( nlevs, lev, ks, del, nobs, nr, p1, p2, l3d, nprof, tch )
+      integer, intent(in)        :: nlevs, nobs, nr, l3d
+      real(c_double), intent(in) :: lev(*), del(*), p1(*), p2(*)
+      integer(c_int), intent(in) :: ks(*)
+      integer, intent(out)       :: nprof
+      logical, intent(in)        :: tch
+      integer(c_int) :: rc, itch, np
+      real(c_double) :: bad_lev
+      itch = 0
+      if ( tch ) itch = 1
+      if ( .not. c_associated(xhandle) ) then
+         rc = gritas_b200_xcov_prs_create ( xhandle, nlevs, p1, p2, l3d, nr, itch, -1_c_int )
+         if ( rc /= 0 ) call gritas_perror ('XCov_Prs_Accum: improper dim settings / cannot create the B200 context')
+      end if
+      rc = gritas_b200_xcov_prs_accum ( xhandle, nobs, lev, ks, del, np, bad_lev )
+      if ( rc == ERR_LEVEL ) call gritas_perror ('Accum: could not find level(1)')                                 ! :1990
+      if ( rc /= 0 ) call gritas_perror ('XCov_Prs_Accum: B200 accumulate failed')
+      nprof = np
+      end subroutine B200_XCov_Prs_Accum
+
+!     GrITAS_XCov_Norm_ (m_gritas_grids.f:859-861).
+      subroutine B200_XCov_Norm ( nr, nrmlz, tch, self, bias_3d, xcov_3d, nobs_3d, ntresh )
+      integer, intent(in)           :: nr
+      logical, intent(in)           :: nrmlz, tch, self
+      integer, OPTIONAL, intent(in) :: ntresh
+      real(c_double), intent(inout) :: bias_3d(*), xcov_3d(*), nobs_3d(*)
+      integer(c_int) :: rc, inrm, iself, intr
+      if ( nr > 3 ) call gritas_perror ('GrITAS_XCov_Norm_: improper dim settings')                               ! :907-909
+      if ( .not. c_associated(xhandle) ) return                         ! nothing accumulated: the arrays stay as they are
+      inrm = 0
+      if ( nrmlz ) inrm = 1
+      iself = 0
+      if ( self ) iself = 1
+      intr = -1
+      if ( present(ntresh) ) intr = ntresh
+      rc = gritas_b200_xcov_norm ( xhandle, inrm, iself, intr, bias_3d, xcov_3d, nobs_3d )
+      if ( rc /= 0 ) call gritas_perror ('XCov_Norm: B200 finalize failed')
+      end subroutine B200_XCov_Norm
+
+      subroutine B200_XCov_Clean ( )
+      if ( c_associated(xhandle) ) call gritas_b200_xcov_destroy ( xhandle )
+      xhandle = c_null_ptr
+      end subroutine B200_XCov_Clean
 
 !     GrITAS_Clean (gritas.f:2017-2026).
       subroutine B200_Clean ( )

@@ -50,6 +50,7 @@ SYMBOLS = [
     "gritas_b200_scores", "gritas_b200_score_regions", "gritas_b200_accum_odsx_sorted", "gritas_b200_set_call_order", "gritas_b200_accum_odsx_meanres", "gritas_b200_export_planes",
     "gritas_b200_xcov_create", "gritas_b200_xcov_destroy", "gritas_b200_xcov_reset", "gritas_b200_xcov_accum",
     "gritas_b200_xcov_norm", "gritas_b200_xcov_get_raw", "gritas_b200_xcov_last_error", "gritas_b200_xcov_launch_count",
+    "gritas_b200_xcov_prs_create", "gritas_b200_xcov_prs_accum",
 ]
 ERR_PROFILE = 9
 ERR_ORDER = 10
@@ -121,6 +122,8 @@ def load(build_if_missing: bool = False):
     L.gritas_b200_scores.argtypes = [_P, _I, _P, _I, _I, _P]
     L.gritas_b200_score_regions.argtypes = [_I, _I, _P, _P]
     L.gritas_b200_xcov_create.argtypes = [C.POINTER(_P), _I, _I, _P, _I, _I, _I, _P, _I, _I, _I]
+    L.gritas_b200_xcov_prs_create.argtypes = [C.POINTER(_P), _I, _P, _P, _I, _I, _I, _I]
+    L.gritas_b200_xcov_prs_accum.argtypes = [_P, _I, _P, _P, _P, C.POINTER(_I), C.POINTER(_D)]
     L.gritas_b200_xcov_destroy.argtypes = [_P]
     L.gritas_b200_xcov_destroy.restype = None
     L.gritas_b200_xcov_reset.argtypes = [_P]

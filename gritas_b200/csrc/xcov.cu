@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
@@ -283,6 +284,138 @@ k_xc_norm_cov(const XcDesc d, int nrmlz, int ntresh, int self, const double *__r
   }
 }
 
+
+// ---- GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-2059): level cross-covariances of conventional soundings ---------------
+// Profiles are runs of equal sounding index ks; every run gathers ALL observations that carry its index (:1973-1979), so an
+// index that comes back later is processed once per run -- as in the reference.  ndim = nlevs, grid l = 1.
+
+// level of every observation (:2004-2013, literal scan of the GrITAS_Pint intervals); the earliest miss is recorded
+__global__ void __launch_bounds__(256)
+k_xp_levels(int n, int nlevs, const double *__restrict__ lev, const double *__restrict__ p1, const double *__restrict__ p2,
+            int *__restrict__ kidx, int *__restrict__ first_miss) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = lev[i];
+    int k = -1;
+    for (int kk = 0; kk < nlevs; ++kk)
+      if (x <= p1[kk] && x > p2[kk]) { k = kk; break; }
+    kidx[i] = k;
+    if (k < 0) atomicMin(first_miss, i);
+  }
+}
+
+// run starts (:1942-1964) and the order-preserving sort key of ks
+__global__ void __launch_bounds__(256)
+k_xp_runs(int n, const int *__restrict__ ks, unsigned *__restrict__ start, unsigned *__restrict__ key, int *__restrict__ idx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    start[i] = (i == 0 || ks[i] != ks[i - 1]) ? 1u : 0u;
+    key[i] = (unsigned)ks[i] ^ 0x80000000u;
+    idx[i] = i;
+  }
+}
+
+// compaction of the run starts: run_ks[r] = ks at the r-th start
+__global__ void __launch_bounds__(256)
+k_xp_run_ks(int n, const int *__restrict__ ks, const unsigned *__restrict__ start, const unsigned *__restrict__ rank,
+            unsigned *__restrict__ run_key) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (start[i]) run_key[rank[i]] = (unsigned)ks[i] ^ 0x80000000u;
+}
+
+// GROUP = all observations of one sounding index, in input order after the stable sort; groups are the distinct keys of the sorted list.
+__global__ void __launch_bounds__(256)
+k_xp_gstart(int n, const unsigned *__restrict__ skey, unsigned *__restrict__ gstart) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) gstart[i] = (i == 0 || skey[i] != skey[i - 1]) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+k_xp_groups(int n, const unsigned *__restrict__ gstart, const unsigned *__restrict__ grank, int ngroups, unsigned *__restrict__ gbeg) {
+  // group begin positions in the sorted list
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (gstart[i]) gbeg[grank[i]] = (unsigned)i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) gbeg[ngroups] = (unsigned)n;
+}
+
+// one thread per group: its members bucketed by level, stably, into lm[]; goff[g][k] = start of level k (positions in lm)
+__global__ void __launch_bounds__(256)
+k_xp_bucket(int nlevs, const int *__restrict__ sidx, const int *__restrict__ kidx, int ngroups, const unsigned *__restrict__ gbeg,
+            unsigned *__restrict__ goff, int *__restrict__ lm) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+    const unsigned a = gbeg[g], b = gbeg[g + 1];
+    unsigned pos = a;
+    for (int k = 0; k < nlevs; ++k) {
+      goff[(size_t)g * (nlevs + 1) + k] = pos;
+      for (unsigned q = a; q < b; ++q) {
+        const int i = sidx[q];
+        if (kidx[i] == k) lm[pos++] = i;
+      }
+    }
+    goff[(size_t)g * (nlevs + 1) + nlevs] = pos;
+  }
+}
+
+// run -> group: position of the run's key among the distinct sorted keys
+__global__ void __launch_bounds__(256)
+k_xp_run_group(int nruns, int ngroups, const unsigned *__restrict__ run_key, const unsigned *__restrict__ skey,
+               const unsigned *__restrict__ gbeg, int *__restrict__ run_group) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += gridDim.x * blockDim.x) {
+    const unsigned key = run_key[r];
+    int lo = 0, hi = ngroups - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (skey[gbeg[mid]] < key) lo = mid + 1; else hi = mid;
+    }
+    run_group[r] = lo;
+  }
+}
+
+// One thread per cell (k1, k2, series): the runs in order, the level-k1 members of the run in order, the level-k2 members in
+// order -- the (n, m) order of the reference's nested loops (:2027-2049) restricted to this cell: bit-identical sums.
+// Cells with k2 == 0 also carry bias_lv(k1,1,:) and nobs_lv(k1,1) (:2034-2035).
+__global__ void __launch_bounds__(128)
+k_xp_accum(int nlevs, int l3d, int nr, int tch, int nobs, int nruns, const int *__restrict__ run_group, const unsigned *__restrict__ goff,
+           const int *__restrict__ lm, const double *__restrict__ del, double *__restrict__ bias, double *__restrict__ xcov,
+           double *__restrict__ nobsv) {
+  const int nser = tch ? nr : 1;
+  const int total = nlevs * nlevs * nser;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int k2 = e % nlevs, k1 = (e / nlevs) % nlevs, s = e / (nlevs * nlevs);
+    double *xc = xcov + (size_t)k1 + (size_t)nlevs * ((size_t)k2 + (size_t)nlevs * ((size_t)0 + (size_t)l3d * s));
+    double acc = *xc;
+    const bool edge = k2 == 0;                                   // this thread also owns bias(k1, 1, s...) and nobs(k1, 1)
+    double bsum[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
+    if (edge && s == 0) {
+      for (int ir = 0; ir < nr; ++ir) bsum[ir] = bias[(size_t)k1 + (size_t)nlevs * ((size_t)0 + (size_t)l3d * ir)];
+      cnt = nobsv[k1];
+    }
+    for (int r = 0; r < nruns; ++r) {
+      const unsigned *go = goff + (size_t)run_group[r] * (nlevs + 1);
+      const unsigned a0 = go[k1], a1 = go[k1 + 1];
+      if (a1 == a0) continue;
+      const unsigned b0 = go[k2], b1 = go[k2 + 1];
+      for (unsigned a = a0; a < a1; ++a) {
+        const int n = lm[a];
+        if (edge && s == 0) {
+          cnt = __dadd_rn(cnt, 1.0);
+          for (int ir = 0; ir < nr; ++ir) bsum[ir] = __dadd_rn(bsum[ir], del[(size_t)n + (size_t)nobs * ir]);
+        }
+        for (unsigned b = b0; b < b1; ++b) {
+          const int m = lm[b];
+          if (tch) {
+            acc = __dadd_rn(acc, __dmul_rn(del[(size_t)n + (size_t)nobs * s], del[(size_t)m + (size_t)nobs * s]));
+          } else {
+            const double t1 = __dmul_rn(del[n], del[(size_t)m + nobs]), t2 = __dmul_rn(del[(size_t)n + nobs], del[m]);
+            acc = __dadd_rn(acc, __dmul_rn(0.5, __dadd_rn(t1, t2)));
+          }
+        }
+      }
+    }
+    *xc = acc;
+    if (edge && s == 0) {
+      for (int ir = 0; ir < nr; ++ir) bias[(size_t)k1 + (size_t)nlevs * ((size_t)0 + (size_t)l3d * ir)] = bsum[ir];
+      nobsv[k1] = cnt;
+    }
+  }
+}
+
 }  // namespace
 
 struct gritas_b200_xcov_ctx {
@@ -300,6 +433,12 @@ struct gritas_b200_xcov_ctx {
   double *X = nullptr; size_t x_cap = 0;
   int *L = nullptr; size_t l_cap = 0;
   int *d_small = nullptr;                                         // [0] accepted count, [1] too-many flag
+  // pressure-level variant (GrITAS_XCov_Prs_Accum_): the handle was made by gritas_b200_xcov_prs_create
+  bool prs = false;
+  int nlevs = 0;
+  double *d_p1 = nullptr, *d_p2 = nullptr;
+  void *prs_scr = nullptr; size_t prs_cap = 0;
+  void *prs_tmp = nullptr; size_t prs_tmp_cap = 0;
   uint64_t launches = 0;
   char err[256] = {0};
 };
@@ -402,7 +541,8 @@ void gritas_b200_xcov_destroy(gritas_b200_xcov_handle h) {
   cudaSetDevice(h->device);
   if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
   for (void *p : {(void *)h->d_lut, (void *)h->d_table, (void *)h->bias, (void *)h->xcov, (void *)h->nobs, (void *)h->w_bias,
-                  (void *)h->w_xcov, h->cols, (void *)h->accept, (void *)h->rank, (void *)h->X, (void *)h->L, (void *)h->d_small})
+                  (void *)h->w_xcov, h->cols, (void *)h->accept, (void *)h->rank, (void *)h->X, (void *)h->L, (void *)h->d_small,
+                  (void *)h->d_p1, (void *)h->d_p2, h->prs_scr, h->prs_tmp})
     if (p) cudaFree(p);
   cudaGetLastError();
   delete h;
@@ -422,6 +562,7 @@ int gritas_b200_xcov_reset(gritas_b200_xcov_handle h) {
 int gritas_b200_xcov_accum(gritas_b200_xcov_handle h, int nobs, const double *lev, const int32_t *kx, const int32_t *kt,
                            const double *del, int32_t *ob_flag, int *nprof_out) {
   if (!h) return GRITAS_B200_ERR_ARG;
+  if (h->prs) return xfail(h, GRITAS_B200_ERR_ARG, "this handle accumulates level covariances: use gritas_b200_xcov_prs_accum");
   XCU(cudaSetDevice(h->device));
   const XcDesc &d = h->d;
   if (nprof_out) *nprof_out = 0;
@@ -482,6 +623,113 @@ int gritas_b200_xcov_accum(gritas_b200_xcov_handle h, int nobs, const double *le
   XCU(cudaGetLastError());
   XCU(cudaStreamSynchronize(h->st));
   if (nprof_out) *nprof_out = nacc;
+  return 0;
+}
+
+// GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-2059).  The Norm, get_raw, reset and destroy entries are shared with the channel variant.
+int gritas_b200_xcov_prs_create(gritas_b200_xcov_handle *hp, int nlevs, const double *p1, const double *p2, int l3d, int nr, int tch,
+                                int device) {
+  if (!hp) return GRITAS_B200_ERR_ARG;
+  *hp = nullptr;
+  if (nlevs < 1 || nlevs > 4096 || !p1 || !p2 || l3d < 1) return GRITAS_B200_ERR_ARG;
+  std::vector<int32_t> achan(nlevs), table(1, 0);
+  for (int k = 0; k < nlevs; ++k) achan[k] = k + 1;
+  int rc = gritas_b200_xcov_create(hp, nlevs, nlevs, achan.data(), l3d, nr, tch, table.data(), 1, 1, device);
+  if (rc) return rc;
+  gritas_b200_xcov_handle h = *hp;
+  h->prs = true;
+  h->nlevs = nlevs;
+  if (cudaMalloc(&h->d_p1, sizeof(double) * nlevs) != cudaSuccess || cudaMalloc(&h->d_p2, sizeof(double) * nlevs) != cudaSuccess ||
+      cudaMemcpy(h->d_p1, p1, sizeof(double) * nlevs, cudaMemcpyDefault) != cudaSuccess ||
+      cudaMemcpy(h->d_p2, p2, sizeof(double) * nlevs, cudaMemcpyDefault) != cudaSuccess) {
+    cudaGetLastError();
+    gritas_b200_xcov_destroy(h);
+    *hp = nullptr;
+    return GRITAS_B200_ERR_CUDA;
+  }
+  return 0;
+}
+
+int gritas_b200_xcov_prs_accum(gritas_b200_xcov_handle h, int nobs, const double *lev, const int32_t *ks, const double *del, int *nprof_out,
+                               double *bad_lev) {
+  if (!h) return GRITAS_B200_ERR_ARG;
+  if (!h->prs) return xfail(h, GRITAS_B200_ERR_ARG, "this handle accumulates channel covariances: use gritas_b200_xcov_accum");
+  XCU(cudaSetDevice(h->device));
+  const XcDesc &d = h->d;
+  if (nprof_out) *nprof_out = 0;
+  if (nobs < 0) return xfail(h, GRITAS_B200_ERR_ARG, "nobs < 0");
+  if (nobs == 0) return 0;
+  if (!lev || !ks || !del) return xfail(h, GRITAS_B200_ERR_ARG, "null column");
+  const size_t n = (size_t)nobs;
+  const int nl = h->nlevs;
+  // columns onto the device
+  const void *src[3] = {lev, ks, del};
+  const size_t bytes[3] = {8 * n, 4 * n, 8 * n * d.nr};
+  size_t need = 0;
+  for (int c = 0; c < 3; ++c)
+    if (!is_device_ptr(src[c])) need += (bytes[c] + 255) & ~(size_t)255;
+  int rc;
+  if (need && (rc = xgrow(h, (char **)&h->cols, &h->cols_cap, need))) return rc;
+  const void *dev[3] = {};
+  size_t off = 0;
+  for (int c = 0; c < 3; ++c) {
+    if (is_device_ptr(src[c])) { dev[c] = src[c]; continue; }
+    void *p = (char *)h->cols + off;
+    XCU(cudaMemcpyAsync(p, src[c], bytes[c], cudaMemcpyHostToDevice, h->st));
+    dev[c] = p;
+    off += (bytes[c] + 255) & ~(size_t)255;
+  }
+  // scratch: nine int-sized columns of n
+  const size_t col = (4 * n + 255) & ~(size_t)255;
+  if ((rc = xgrow(h, (char **)&h->prs_scr, &h->prs_cap, 10 * col + 256))) return rc;
+  char *scr = (char *)h->prs_scr;
+  int *kidx = (int *)(scr + 0 * col);
+  unsigned *start = (unsigned *)(scr + 1 * col), *srank = (unsigned *)(scr + 2 * col), *key = (unsigned *)(scr + 3 * col);
+  int *idx = (int *)(scr + 4 * col);
+  unsigned *skey = (unsigned *)(scr + 5 * col);
+  int *sidx = (int *)(scr + 6 * col);
+  unsigned *gstart = (unsigned *)(scr + 7 * col), *grank = (unsigned *)(scr + 8 * col);
+  int *lm = (int *)(scr + 9 * col);
+  const int nb = (int)std::min<size_t>(148 * 8, (n + 255) / 256);
+  const int big = 0x7fffffff;
+  XCU(cudaMemcpyAsync(h->d_small, &big, sizeof(int), cudaMemcpyHostToDevice, h->st));
+  k_xp_levels<<<nb, 256, 0, h->st>>>(nobs, nl, (const double *)dev[0], h->d_p1, h->d_p2, kidx, h->d_small);
+  k_xp_runs<<<nb, 256, 0, h->st>>>(nobs, (const int *)dev[1], start, key, idx);
+  k_xc_rank<<<1, 1024, 0, h->st>>>(start, srank, nobs, h->d_small + 1);
+  size_t tmpb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmpb, key, skey, idx, sidx, nobs, 0, 32, h->st);
+  if ((rc = xgrow(h, (char **)&h->prs_tmp, &h->prs_tmp_cap, tmpb + 256))) return rc;
+  size_t tb = h->prs_tmp_cap;
+  XCU(cub::DeviceRadixSort::SortPairs(h->prs_tmp, tb, key, skey, idx, sidx, nobs, 0, 32, h->st));   // stable: members keep their input order
+  k_xp_gstart<<<nb, 256, 0, h->st>>>(nobs, skey, gstart);
+  k_xc_rank<<<1, 1024, 0, h->st>>>(gstart, grank, nobs, h->d_small + 2);
+  int small[3] = {0, 0, 0};
+  XCU(cudaMemcpyAsync(small, h->d_small, sizeof(small), cudaMemcpyDeviceToHost, h->st));
+  XCU(cudaStreamSynchronize(h->st));
+  h->launches += 6;
+  if (small[0] != big) {                                               // 'Accum: could not find level(1)' (:1990)
+    double lv = 0.0;
+    XCU(cudaMemcpy(&lv, (const double *)dev[0] + small[0], sizeof(double), cudaMemcpyDefault));
+    if (bad_lev) *bad_lev = lv;
+    return xfail(h, GRITAS_B200_ERR_LEVEL, "Accum: could not find level(1) (obs level %.17g hPa)", lv);
+  }
+  const int nruns = small[1], ngroups = small[2];
+  // run keys, group begins, level buckets, run -> group
+  const size_t g_off = (size_t)ngroups * (nl + 1);
+  if ((rc = xgrow(h, &h->rank, &h->rank_cap, (size_t)nruns * 2 + (size_t)ngroups + 2 + g_off))) return rc;
+  unsigned *run_key = h->rank, *gbeg = run_key + nruns, *goff = gbeg + ngroups + 1;
+  int *run_group = (int *)(goff + g_off);
+  k_xp_run_ks<<<nb, 256, 0, h->st>>>(nobs, (const int *)dev[1], start, srank, run_key);
+  k_xp_groups<<<nb, 256, 0, h->st>>>(nobs, gstart, grank, ngroups, gbeg);
+  k_xp_bucket<<<(ngroups + 255) / 256, 256, 0, h->st>>>(nl, sidx, kidx, ngroups, gbeg, goff, lm);
+  k_xp_run_group<<<(nruns + 255) / 256, 256, 0, h->st>>>(nruns, ngroups, run_key, skey, gbeg, run_group);
+  const int cells = nl * nl * (d.tch ? d.nr : 1);
+  k_xp_accum<<<(cells + 127) / 128, 128, 0, h->st>>>(nl, d.l3d, d.nr, d.tch, nobs, nruns, run_group, goff, lm, (const double *)dev[2], h->bias,
+                                                    h->xcov, h->nobs);
+  h->launches += 5;
+  XCU(cudaGetLastError());
+  XCU(cudaStreamSynchronize(h->st));
+  if (nprof_out) *nprof_out = nruns;
   return 0;
 }
 

@@ -474,6 +474,42 @@ class XCov:
             raise ValueError(f"gritas_b200_xcov_create rc={rc}")
         self._h = h
 
+    @classmethod
+    def for_levels(cls, p1, p2, l3d, nr, tch, device=-1):
+        """Handle for GrITAS_XCov_Prs_Accum (m_gritas_grids.f:1862-2059): level cross-covariances of soundings; p1 / p2 from
+        GrITAS_Pint.  Norm / get_raw / reset as for the channel variant (nchan = nlevs)."""
+        self = cls.__new__(cls)
+        p1, p2 = _f64(p1), _f64(p2)
+        self.km = self.nchan = int(p1.size)
+        self.l3d, self.nr, self.tch = int(l3d), int(nr), bool(tch)
+        self._h = None
+        h = C.c_void_p()
+        rc = cabi.load().gritas_b200_xcov_prs_create(C.byref(h), self.nchan, p1.ctypes.data, p2.ctypes.data, self.l3d, self.nr,
+                                                     1 if tch else 0, device)
+        if rc == cabi.ERR_NR:
+            raise GritasPerror("GrITAS_XCov_Prs_Accum_: improper dim settings / setting inconsistent w/ dims")   # :1929-1940
+        if rc == cabi.ERR_CUDA:
+            raise RuntimeError("gritas_b200_xcov_prs_create: no usable CUDA device (there is no CPU fallback)")
+        if rc:
+            raise ValueError(f"gritas_b200_xcov_prs_create rc={rc}")
+        self._h = h
+        return self
+
+    def GrITAS_XCov_Prs_Accum(self, lev, kx, kt, ks, del_, nobs, nr, kxkt_table=None, p1=None, p2=None, ob_flag=None, l3d=None,
+                              bias_lv=None, xcov_lv=None, nobs_lv=None, tch=None):
+        """Reference argument list (m_gritas_grids.f:1862-1865); kx / kt / kxkt_table / ob_flag / the host arrays are accepted and
+        ignored, as the reference ignores them.  Returns nprof."""
+        assert nr == self.nr
+        if isinstance(del_, np.ndarray) and not del_.flags.f_contiguous:
+            del_ = np.asfortranarray(del_)
+        n, bad = C.c_int(0), C.c_double(0.0)
+        rc = cabi.load().gritas_b200_xcov_prs_accum(self._h, int(nobs), cabi.ptr(lev, np.float64), cabi.ptr(ks, np.int32),
+                                                    cabi.ptr(del_, np.float64), C.byref(n), C.byref(bad))
+        if rc == cabi.ERR_LEVEL:
+            raise GritasPerror(f"Accum: could not find level(1) ({bad.value} hPa)", 7, bad.value)
+        self._check(rc)
+        return n.value
+
     def _check(self, rc):
         if rc == 0:
             return

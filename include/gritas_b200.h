@@ -360,6 +360,18 @@ int gritas_b200_xcov_accum(gritas_b200_xcov_handle h, int nobs, const double *le
 int gritas_b200_xcov_norm(gritas_b200_xcov_handle h, int nrmlz, int self, int ntresh, double *bias_lv, double *xcov_lv,
                           double *nobs_lv);
 int gritas_b200_xcov_get_raw(gritas_b200_xcov_handle h, double *bias_lv, double *xcov_lv, double *nobs_lv);
+/*
+ * Level cross-covariances of conventional soundings: replaces GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-2059).  Profiles
+ * are runs of equal sounding index ks; each gathers all observations carrying its index (an index that returns later is
+ * processed once per run, as the reference does); levels from the GrITAS_Pint intervals p1 / p2; grid l = 1; the reference's
+ * kx / kt / kxkt_table / ob_flag arguments are unused there and absent here.  Arrays as above with nchan = nlevs.  Sums are
+ * formed in the reference's (n, m) order with separate multiplies and adds: bit-identical.  rc GRITAS_B200_ERR_LEVEL +
+ * *bad_lev: 'could not find level' (:1990).  Norm / get_raw / reset / destroy: the gritas_b200_xcov_* entries above.
+ */
+int gritas_b200_xcov_prs_create(gritas_b200_xcov_handle *h, int nlevs, const double *p1, const double *p2, int l3d, int nr, int tch,
+                                int device);
+int gritas_b200_xcov_prs_accum(gritas_b200_xcov_handle h, int nobs, const double *lev, const int32_t *ks, const double *del, int *nprof,
+                               double *bad_lev);
 const char *gritas_b200_xcov_last_error(gritas_b200_xcov_handle h);
 uint64_t gritas_b200_xcov_launch_count(gritas_b200_xcov_handle h);
 

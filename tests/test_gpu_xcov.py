@@ -79,3 +79,41 @@ def test_xcov_errors_like_the_reference():
     with pytest.raises(GritasPerror, match="channel matching"):
         G.GrITAS_XCov_Accum(None, None, lev, d["kx"], d["kt"], d["del_"], len(lev), 2, d["table"], np.zeros(len(lev), np.int32), 1)
     G.close()
+
+
+@pytest.mark.parametrize("tch,nr", [(False, 2), (True, 3)])
+def test_xcov_prs_accum_bit_exact(tch, nr):
+    """GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-2059): soundings by ks, several observations of a sounding on the same level,
+    two files accumulated one after the other, and a sounding index that comes back later in the file (processed once per run)."""
+    plevs = np.array([1000, 925, 850, 700, 500, 400, 300, 250, 200, 150, 100, 70, 50, 30, 20, 10], dtype=np.float64)
+    p1, p2 = oracle.pint(plevs)
+    nl = len(plevs)
+    G = XCov.for_levels(p1, p2, 1, nr, tch)
+    b, x, n = oracle.xcov_alloc(nl, 1, nr)
+    rng = np.random.default_rng(11)
+    for f in range(2):
+        ks_list, lev_list = [], []
+        for s in range(300):
+            m = int(rng.integers(1, 40))
+            ks_list += [1000 + s] * m
+            lev_list += list(np.exp(rng.uniform(np.log(8.0), np.log(1040.0), m)))
+        if f == 1:                                   # sounding 1005 again at the end of the file
+            ks_list += [1005] * 7
+            lev_list += list(np.exp(rng.uniform(np.log(8.0), np.log(1040.0), 7)))
+        ks = np.array(ks_list, np.int32)
+        lev = np.array(lev_list)
+        d = np.asfortranarray(rng.normal(0.1, 1.0, (len(ks), nr)))
+        np_o = oracle.xcov_prs_accum(nl, lev, ks, d, p1, p2, 1, b, x, n, tch)
+        np_g = G.GrITAS_XCov_Prs_Accum(lev, None, None, ks, d, len(ks), nr)
+        assert np_g == np_o
+    gb, gx, gn = G.alloc()
+    G.get_raw(gb, gx, gn)
+    assert n.sum() > 0
+    assert np.array_equal(gn, n) and np.array_equal(gb, b) and np.array_equal(gx, x)
+    rb, rx = b.copy(order="F"), x.copy(order="F")
+    oracle.xcov_norm(nr, True, tch, False, 1, rb, rx, n)
+    G.GrITAS_XCov_Norm(nr, True, tch, False, 1, gb, gx, gn)
+    assert np.array_equal(gb, rb) and np.array_equal(gx, rx)
+    with pytest.raises(GritasPerror, match="could not find level"):
+        G.GrITAS_XCov_Prs_Accum(np.array([500.0, 2500.0]), None, None, np.array([1, 1], np.int32), np.zeros((2, nr), order="F"), 2, nr)
+    G.close()

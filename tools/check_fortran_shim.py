@@ -73,7 +73,20 @@ def strip_fixed_form(text):
 
 
 def split_args(s):
-    return [a.strip() for a in s.split(",") if a.strip()]
+    """top-level commas only: achan(:,ichan_version) is one argument"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return [a for a in out if a]
 
 
 # ---------------------------------------------------------------- C header
@@ -97,7 +110,8 @@ def c_prototypes():
 def classify_c(t):
     t = " ".join(t.split())
     return {
-        "gritas_b200_handle": "handle", "gritas_b200_handle *": "handle*", "int": "int", "double": "double",
+        "gritas_b200_handle": "handle", "gritas_b200_handle *": "handle*", "gritas_b200_xcov_handle": "handle",
+        "gritas_b200_xcov_handle *": "handle*", "int": "int", "double": "double",
         "size_t": "size_t", "int32_t *": "int*", "int *": "int*", "double *": "double*", "void *": "bytes",
         "gritas_b200_ods *": "struct*", "double **": "double**",
     }.get(t, "?" + t)
