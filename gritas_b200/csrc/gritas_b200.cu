@@ -21,6 +21,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -33,7 +34,7 @@ using namespace gb200;
 namespace {
 
 constexpr int NSLOT = 2;   // staging slots (double buffering)
-constexpr int NWK = 8;     // max worker streams of the tiled path (GRITAS_B200_WORKERS, default 3): the K1 launches
+constexpr int NWK = 8;     // max worker streams of the tiled path (GRITAS_B200_WORKERS, default 6): the K1 launches
                            // of consecutive calls overlap
 constexpr int NCOL = 18;   // staged columns per slot
 enum Col { C_LAT, C_LON, C_LEV, C_D0, C_D1, C_D2, C_OBS, C_XVEC, C_KX, C_KT, C_FLAG, C_TIME, C_B0, C_B1, C_B2, C_C0, C_C1, C_C2 };
@@ -205,6 +206,10 @@ struct Slot {
   size_t pin_cap[NCOL] = {};
   int *flag_out = nullptr;
   size_t flag_out_cap = 0;
+  void *flag_pin = nullptr;        // early ob_flag write-back: pinned landing buffer when the caller's array is pageable
+  size_t flag_pin_cap = 0;
+  cudaEvent_t ints_copied = nullptr, flags_ready = nullptr;
+  std::atomic<int> flag_done{1};
   cudaEvent_t consumed = nullptr;  // kernel that read this slot has finished
   cudaEvent_t copied = nullptr;    // H2D copies into this slot have finished
   bool in_use = false;             // staging buffers of this slot are referenced by a queued kernel
@@ -224,6 +229,7 @@ struct gritas_b200_ctx {
   Status *d_status = nullptr;
   Status *h_status = nullptr;  // pinned
   cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t early_st = nullptr;   // early ob_flag write-back (k_early_flags + its D2H), next to the upload of the fp64 columns
   bool own_compute = true;
   Slot slot[NSLOT];
   int next_slot = 0;
@@ -254,6 +260,7 @@ struct gritas_b200_ctx {
   size_t staged_upper = 0;     // upper bound of entries appended since the last flush
   size_t tf_smem = 0;            // shared memory of the tile kernel (K2f / K2t)
   int tf_ctas = 148, tf_per_sm = 1;
+  int k1_per_sm = 2;             // CTAs per SM of one K1 launch (GRITAS_B200_K1_CTAS_PER_SM; its launch bounds keep 4 resident: two launches fill an SM)
   bool fused_norm = true;        // Norm consumes the tile lists itself (K2f) instead of flush (K2t) + K3
   bool det_tiled = false;        // deterministic mode on the tiled path (k_tile_det): entries carry sequence numbers
   size_t td_smem = 0;            // shared memory of k_tile_det
@@ -273,7 +280,7 @@ struct gritas_b200_ctx {
   cudaEvent_t wk_done[NWK] = {};
   bool wk_pending[NWK] = {};
   int next_wk = 0;
-  int nwk = 3;
+  int nwk = 6;                    // measured on the cfg2 month: 3 streams x 4 CTAs/SM 3.09 ms, 6 x 2 and 8 x 2 3.03 ms, 2 x 4 3.43 ms (profiles/r2b_k1_k2f_experiments.txt)
   cudaEvent_t main_ev = nullptr;  // last accumulator-wide operation queued on `compute`
   // reduce + finalize pipeline (multi-GPU): chunk c is tile-accumulated on `compute`, reduced to the root on
   // `comm_stream`, finalized on `fin_stream` while later chunks are still being accumulated / reduced
@@ -386,7 +393,7 @@ int grow_pin(gritas_b200_handle h, void **p, size_t *cap, size_t bytes) {
   return 0;
 }
 
-int flush_pending(gritas_b200_handle h, Slot &s);
+int flush_pending(gritas_b200_handle h, Slot &s, size_t hook_at = (size_t)-1, const std::function<int()> *hook = nullptr);
 
 // Makes column `c` of this call available on the device; returns the device pointer in *out.
 // Device-resident inputs are used in place.  Pinned inputs are DMA'd straight from the caller's
@@ -426,7 +433,8 @@ int stage(gritas_b200_handle h, Slot &s, int c, const void *src, size_t bytes, c
 }
 
 // DMA of the pageable chunks in the order they were submitted (each as soon as the pool has copied it).
-int flush_pending(gritas_b200_handle h, Slot &s) {
+// `hook` runs once the DMAs of the first `hook_at` chunks are queued (the early ob_flag write-back: after the integer columns).
+int flush_pending(gritas_b200_handle h, Slot &s, size_t hook_at, const std::function<int()> *hook) {
   {   // hand every chunk of the call to the pool in one go
     std::vector<CopyPool::Task> batch;
     batch.reserve(s.pending.size());
@@ -437,10 +445,14 @@ int flush_pending(gritas_b200_handle h, Slot &s) {
       }
     CopyPool::get().submit_batch(batch.data(), batch.size());
   }
+  size_t issued = 0;
   for (const PendingCopy &pc : s.pending) {
+    if (hook && issued == hook_at) { if (int hr = (*hook)()) return hr; }
     CopyPool::get().wait(pc.done);
     CU(cudaMemcpyAsync(pc.dev, pc.pin, pc.n, cudaMemcpyHostToDevice, h->copy));
+    ++issued;
   }
+  if (hook && issued <= hook_at) { if (int hr = (*hook)()) return hr; }
   s.pending.clear();
   s.nflags = 0;
   return 0;
@@ -584,8 +596,7 @@ template <int NR>
 void launch_lists(gritas_b200_handle h, int w, const ObsCols &c, const FilterDesc &f) {
   const int nvec = (c.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
   // one resident wave (4 CTAs per SM, launch bounds of k_list_obs), grid-stride over the file
-  static const int per_sm = getenv("GRITAS_B200_K1_CTAS_PER_SM") ? std::max(1, atoi(getenv("GRITAS_B200_K1_CTAS_PER_SM"))) : 4;
-  const int g1 = grid_for((size_t)nvec, K1_THREADS, per_sm);
+  const int g1 = grid_for((size_t)nvec, K1_THREADS, h->k1_per_sm);
   const size_t smem = levtab_smem_bytes(h->g);
   Status *st = h->d_status + 1 + w;
   if (h->det_tiled) {
@@ -1050,6 +1061,7 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
         h->sg.dirty = h->sg.fill + ntiles;
         CUC(cudaMalloc(&h->sg.lists, entry * h->stage_slots));
         if (const char *e_w = getenv("GRITAS_B200_WORKERS")) h->nwk = std::max(1, std::min(NWK, atoi(e_w)));
+        if (const char *e_k = getenv("GRITAS_B200_K1_CTAS_PER_SM")) h->k1_per_sm = std::max(1, atoi(e_k));
         for (int w = 0; w < h->nwk; ++w) {                // one stream, event and level-miss record per worker
           CUC(cudaStreamCreateWithFlags(&h->wk[w], cudaStreamNonBlocking));
           CUC(cudaEventCreateWithFlags(&h->wk_done[w], cudaEventDisableTiming));
@@ -1112,6 +1124,7 @@ void gritas_b200_destroy(gritas_b200_handle h) {
   cudaSetDevice(h->device);
   if (h->compute) cudaStreamSynchronize(h->compute);
   if (h->copy) cudaStreamSynchronize(h->copy);
+  if (h->early_st) { cudaStreamSynchronize(h->early_st); cudaStreamDestroy(h->early_st); }
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int i = 0; i < NSLOT; ++i) {
     Slot &s = h->slot[i];
@@ -1120,6 +1133,9 @@ void gritas_b200_destroy(gritas_b200_handle h) {
       if (s.pin[c]) cudaFreeHost(s.pin[c]);
     }
     if (s.flag_out) cudaFree(s.flag_out);
+    if (s.flag_pin) cudaFreeHost(s.flag_pin);
+    if (s.ints_copied) cudaEventDestroy(s.ints_copied);
+    if (s.flags_ready) cudaEventDestroy(s.flags_ready);
     if (s.consumed) cudaEventDestroy(s.consumed);
     if (s.copied) cudaEventDestroy(s.copied);
   }
@@ -1177,6 +1193,45 @@ struct ResidualSpec {
   int expr = 0, post = 0;
 };
 
+// Early ob_flag write-back (see accum_common).  begin: once the integer columns' DMAs are queued -- k_early_flags and the
+// download of its result on a stream of their own; end: the flags are in the caller's array.
+static int early_flags_begin(gritas_b200_handle h, Slot &s, const ObsCols &c, bool any_copy, int32_t *flag_user) {
+  const size_t nb4 = sizeof(int) * (size_t)c.n;
+  if (!h->early_st) CU(cudaStreamCreateWithFlags(&h->early_st, cudaStreamNonBlocking));
+  if (!s.ints_copied) {
+    CU(cudaEventCreateWithFlags(&s.ints_copied, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.flags_ready, cudaEventDisableTiming));
+  }
+  if (any_copy) {
+    CU(cudaEventRecord(s.ints_copied, h->copy));
+    CU(cudaStreamWaitEvent(h->early_st, s.ints_copied, 0));
+  }
+  int rc = grow_dev(h, (void **)&s.flag_out, &s.flag_out_cap, nb4);
+  if (rc) return rc;
+  k_early_flags<<<grid_for((size_t)c.n, 256, 4), 256, 0, h->early_st>>>(h->g, c.kx, c.kt, c.flag, s.flag_out, c.n);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  void *dst = flag_user;
+  if (mem_kind(flag_user) == 0) {                        // pageable: land in a pinned buffer, the copy pool finishes the job
+    if ((rc = grow_pin(h, &s.flag_pin, &s.flag_pin_cap, nb4))) return rc;
+    dst = s.flag_pin;
+  }
+  CU(cudaMemcpyAsync(dst, s.flag_out, nb4, cudaMemcpyDeviceToHost, h->early_st));
+  CU(cudaEventRecord(s.flags_ready, h->early_st));
+  return 0;
+}
+
+static int early_flags_end(gritas_b200_handle h, Slot &s, int32_t *flag_user, int nobs) {
+  const size_t nb4 = sizeof(int) * (size_t)nobs;
+  CU(cudaEventSynchronize(s.flags_ready));
+  if (mem_kind(flag_user) == 0) {
+    CopyPool::get().submit_split(flag_user, s.flag_pin, nb4, &s.flag_done);
+    CopyPool::get().wait(&s.flag_done);
+  }
+  h->d2h += nb4;
+  return 0;
+}
+
 static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,
                         const double *const dcol[3], const double *obs, const double *xvec, const double *omf_for_scale,
                         const int32_t *kx, const int32_t *kt, const int32_t *flag_in, const int32_t *time,
@@ -1218,6 +1273,20 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
     if (!r && nseen < NCOL) { seen_src[nseen] = src; seen_dev[nseen] = *out; ++nseen; }
     return r;
   };
+  // The integer columns go first.  GrITAS_Accum's ob_flag (inout) depends on them alone (m_gritas_grids.f:406-416), so for
+  // a host caller the flags are computed and sent back while the fp64 columns are still on their way up (early write-back):
+  // the call no longer ends with a download that nothing overlaps.
+  if ((rc = stage1(C_KX, kx, nb4, (const void **)&c.kx))) return rc;
+  if ((rc = stage1(C_KT, kt, nb4, (const void **)&c.kt))) return rc;
+  if (flag_in && (rc = stage1(C_FLAG, flag_in, nb4, (const void **)&c.flag))) return rc;
+  static const bool early_off = getenv("GRITAS_B200_EARLY_FLAGS") && atoi(getenv("GRITAS_B200_EARLY_FLAGS")) == 0;
+  const bool early = flag_out && flag_in == flag_out && !f.ods && !h->g.mask && !h->minmax && !early_off && nobs >= 4096 &&
+                     mem_kind(flag_out) != 2;
+  const std::function<int()> early_hook = [&]() -> int { return early_flags_begin(h, s, c, any, flag_out); };
+  const size_t n_int_chunks = s.pending.size();
+  if (early && n_int_chunks == 0) {                      // pinned (or device) integer columns: their DMAs are queued already
+    if ((rc = early_hook())) return rc;
+  }
   if ((rc = stage1(C_LAT, lat, nb8, (const void **)&c.lat))) return rc;
   if ((rc = stage1(C_LON, lon, nb8, (const void **)&c.lon))) return rc;
   if ((rc = stage1(C_LEV, lev, nb8, (const void **)&c.lev))) return rc;
@@ -1237,11 +1306,12 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   if ((f.scale_res == 1 || f.post) && (rc = stage1(C_XVEC, xvec, nb8, (const void **)&c.xvec))) return rc;
   if (f.scale_res >= 2 && (rc = stage1(C_OBS, obs, nb8, (const void **)&c.obs))) return rc;
   if (f.scale_res == 3 && (rc = stage1(C_D2, omf_for_scale, nb8, (const void **)&c.omf))) return rc;   // obs - omf
-  if ((rc = stage1(C_KX, kx, nb4, (const void **)&c.kx))) return rc;
-  if ((rc = stage1(C_KT, kt, nb4, (const void **)&c.kt))) return rc;
-  if (flag_in && (rc = stage1(C_FLAG, flag_in, nb4, (const void **)&c.flag))) return rc;
   if (f.use_time && (rc = stage1(C_TIME, time, nb4, (const void **)&c.time))) return rc;
-  return run_accum(h, c, f, s, any, flag_out, bad_lev);
+  if (!early) return run_accum(h, c, f, s, any, flag_out, bad_lev);
+  if (n_int_chunks > 0 && (rc = flush_pending(h, s, n_int_chunks, &early_hook))) return rc;
+  // every upload is queued; the flags came down long ago: hand them to the caller while the last DMAs and K1 run
+  if ((rc = early_flags_end(h, s, flag_out, nobs))) return rc;
+  return run_accum(h, c, f, s, any, nullptr, bad_lev);
 }
 
 int gritas_b200_accum(gritas_b200_handle h, int nobs, const double *lat, const double *lon, const double *lev,

@@ -1935,6 +1935,25 @@ k_meanres_qc(const double *__restrict__ obs, const double *__restrict__ mean_obs
     out[i] = (obs[i] == mean_obs[i]) ? qcexcl[i] : x_passive;
 }
 
+// ob_flag as GrITAS_Accum_ leaves it (m_gritas_grids.f:406-416), from the three integer columns alone: an observation
+// that came in flagged keeps its flag, one whose (kx, kt) is not in the table gets 1 -- the same value every accumulate
+// kernel writes (classify4: flag_after).  Run as soon as kx / kt / ob_flag have reached the device, so that the
+// write-back of ob_flag to the caller overlaps the upload of the fp64 columns (host callers without a land mask).
+__global__ void __launch_bounds__(256)
+k_early_flags(const GridDesc g, const int *__restrict__ kx, const int *__restrict__ kt, const int *__restrict__ flag_in,
+              int *__restrict__ flag_out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int fl = flag_in[i];
+    if (fl == 0) {
+      const unsigned kx1 = (unsigned)(kx[i] - 1), kt1 = (unsigned)(kt[i] - 1);
+      const bool inr = kx1 < (unsigned)g.kxmax && kt1 < (unsigned)g.ktmax;
+      const int l = inr ? __ldg(g.table + (kx1 + (unsigned)g.kxmax * kt1)) : 0;
+      if (l == 0) fl = 1;
+    }
+    flag_out[i] = fl;
+  }
+}
+
 // The column gathers of gritas.f:510-523: dst(i) = src(is(i)) for up to 8 fp64 and 5 int32 columns in one pass.
 struct GatherCols {
   const double *f_src[8]; double *f_dst[8];

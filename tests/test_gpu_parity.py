@@ -811,6 +811,39 @@ def test_pageable_columns_through_the_copy_pool_full_size():
         H.compare(out, ref, l2d, l3d, 2, exact=H.is_det(mode), tol=TOL_FAST)
 
 
+@pytest.mark.parametrize("flags", [0, cabi.FLAG_ASYNC])
+def test_early_ob_flag_write_back_pinned_and_pageable(flags):
+    """Host callers get ob_flag back while the fp64 columns are still being uploaded (k_early_flags, from kx / kt / the
+    incoming flags alone): same flags and statistics as the oracle for pageable and for pinned columns, synchronous and
+    ASYNC calls, several files in a row (slot reuse), incoming flags partly set."""
+    import torch
+    cfg = synth.get_config("cfg2", 0.25)
+    cfg.im, cfg.jm = 72, 46
+    files = [synth.make_file(cfg, i) for i in range(5)]
+    table, l2d, l3d, p1, p2 = H.setup(cfg)
+    fins = [H.filter_in(c, 101) for c in files]
+    ref, rflags = H.oracle_run(cfg, files, 2, fins)
+    for pinned in (False, True):
+        G = Grids(cfg.im, cfg.jm, cfg.km, cfg.plevs, mode=cabi.MODE_DETERMINISTIC | flags)
+        got = []
+        keep = []
+        for c, fin in zip(files, fins):
+            n = len(c["lat"])
+            d = H.del_of(c, 2)
+            cols = [c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], np.ascontiguousarray(d.ravel(order="F")), fin.copy()]
+            if pinned:
+                cols = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in cols]
+            keep.append(cols)
+            G.GrITAS_Accum(*cols[:6], n, 2, table, p1, p2, cols[6], l2d, l3d=l3d)
+            got.append(cols[6])
+        out = G.alloc_grids()
+        G.norm_into(out)
+        G.close()
+        for g, r in zip(got, rflags):
+            assert np.array_equal(g, r)
+        H.compare(out, ref, l2d, l3d, 2, exact=True, tol=0.0)
+
+
 @pytest.mark.parametrize("mode", H.MODES)
 @pytest.mark.parametrize("device_inputs", [False, True])
 def test_fused_presort_gather_accum_matches_the_sorted_reference_loop(mode, device_inputs):
