@@ -77,6 +77,8 @@ constexpr int NCCL_SUM = 0;      // ncclSum
 // at a fraction of PCIe; a handful of threads copying 1 MB chunks keep the DMA engine fed while it already moves
 // the chunks that are done.
 constexpr size_t COPY_CHUNK = (size_t)2 << 20;
+constexpr size_t COPY_CHUNK_SMALL = (size_t)256 << 10;   // the first COPY_SMALL_FIRST chunks of a call (see stage())
+constexpr int COPY_SMALL_FIRST = 8;
 
 // Large host copies with non-temporal stores: the destination (pinned staging read next by the DMA engine, or a grid
 // far larger than the caches) is not going to be read by this core, so the copy should not pull it into the cache
@@ -415,8 +417,10 @@ int stage(gritas_b200_handle h, Slot &s, int c, const void *src, size_t bytes, c
     // soon as it has landed there (the other chunks are still being copied)
     rc = grow_pin(h, &s.pin[c], &s.pin_cap[c], bytes);
     if (rc) return rc;
-    for (size_t off = 0; off < bytes; off += COPY_CHUNK) {
-      const size_t n = std::min(COPY_CHUNK, bytes - off);
+    // the first chunks of a call are small: the pool's threads all start at once, and the DMA engine idles until the
+    // FIRST chunk has landed in pinned memory (2 MB at one thread's share of the copy rate is ~0.3 ms of a 1.2 ms upload)
+    for (size_t off = 0, n = 0; off < bytes; off += n) {
+      n = std::min(s.pending.size() < (size_t)COPY_SMALL_FIRST ? COPY_CHUNK_SMALL : COPY_CHUNK, bytes - off);
       if (s.nflags >= s.flags.size() && (rc = flush_pending(h, s))) return rc;   // (a very large call: DMA what is there, reuse the flags)
       std::atomic<int> *done = &s.flags[s.nflags++];
       done->store(0, std::memory_order_relaxed);
@@ -494,6 +498,31 @@ int copy_out_pageable(gritas_b200_handle h, void *user, const void *dev, size_t 
 }
 
 bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// GRITAS_B200_TRACE=1: host-clock phase times of every Accum call on stderr (where does a synchronous call spend its time?)
+struct CallTrace {
+  bool on;
+  double t0, last;
+  char buf[256];
+  int len = 0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  CallTrace() {
+    static const bool v = getenv("GRITAS_B200_TRACE") && atoi(getenv("GRITAS_B200_TRACE")) != 0;
+    on = v;
+    if (on) t0 = last = now();
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    const double t = now();
+    len += snprintf(buf + len, sizeof(buf) - (size_t)len, " %s %.3f", what, t - last);
+    last = t;
+  }
+  ~CallTrace() {
+    if (on) fprintf(stderr, "[gritas_b200 trace] total %.3f ms:%s\n", now() - t0, buf);
+  }
+};
+thread_local CallTrace *g_trace = nullptr;
+inline void trace_mark(const char *what) { if (g_trace) g_trace->mark(what); }
 
 int clear_status(gritas_b200_handle h) {
   Status st[NWK + 1];
@@ -782,6 +811,7 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     if (int pr = flush_pending(h, s)) return pr;
     CU(cudaEventRecord(s.copied, h->copy));
     CU(cudaStreamWaitEvent(run, s.copied, 0));
+    trace_mark("flush2");
   }
   const size_t smem = levtab_smem_bytes(h->g);
   if (h->minmax) {
@@ -893,7 +923,12 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
     h->wk_pending[w] = true;
   }
   const bool async = (h->flags & GRITAS_B200_FLAG_ASYNC) != 0;
-  if (!async || flag_to_host) return drain(h, bad_lev);
+  trace_mark("launch");
+  if (!async || flag_to_host) {
+    const int dr = drain(h, bad_lev);
+    trace_mark("drain");
+    return dr;
+  }
   // async: the caller's arrays must be reusable on return -> wait for the copies, not the kernel
   if (any_copy && s.direct_dma && !(h->flags & GRITAS_B200_FLAG_HOLD_INPUTS)) CU(cudaEventSynchronize(s.copied));
   return 0;
@@ -1249,6 +1284,8 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   Slot &s = h->slot[h->next_slot];
   h->next_slot = (h->next_slot + 1) % NSLOT;
   s.direct_dma = false;
+  CallTrace trace;
+  struct TraceScope { CallTrace *prev; TraceScope(CallTrace *t) : prev(g_trace) { g_trace = t->on ? t : nullptr; } ~TraceScope() { g_trace = prev; } } trace_scope(&trace);
 
   struct PendingGuard {   // an error return must not leave pool tasks reading the caller's arrays
     Slot &s;
@@ -1280,7 +1317,7 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   if ((rc = stage1(C_KT, kt, nb4, (const void **)&c.kt))) return rc;
   if (flag_in && (rc = stage1(C_FLAG, flag_in, nb4, (const void **)&c.flag))) return rc;
   static const bool early_off = getenv("GRITAS_B200_EARLY_FLAGS") && atoi(getenv("GRITAS_B200_EARLY_FLAGS")) == 0;
-  const bool early = flag_out && flag_in == flag_out && !f.ods && !h->g.mask && !h->minmax && !early_off && nobs >= 4096 &&
+  const bool early = flag_out && flag_in == flag_out && !f.ods && !h->g.mask && !h->minmax && !early_off && nobs >= 4096 && nobs <= (1 << 27) &&
                      mem_kind(flag_out) != 2;
   const std::function<int()> early_hook = [&]() -> int { return early_flags_begin(h, s, c, any, flag_out); };
   const size_t n_int_chunks = s.pending.size();
@@ -1307,10 +1344,13 @@ static int accum_common(gritas_b200_handle h, int nobs, const double *lat, const
   if (f.scale_res >= 2 && (rc = stage1(C_OBS, obs, nb8, (const void **)&c.obs))) return rc;
   if (f.scale_res == 3 && (rc = stage1(C_D2, omf_for_scale, nb8, (const void **)&c.omf))) return rc;   // obs - omf
   if (f.use_time && (rc = stage1(C_TIME, time, nb4, (const void **)&c.time))) return rc;
+  trace_mark("stage");
   if (!early) return run_accum(h, c, f, s, any, flag_out, bad_lev);
   if (n_int_chunks > 0 && (rc = flush_pending(h, s, n_int_chunks, &early_hook))) return rc;
+  trace_mark("flush");
   // every upload is queued; the flags came down long ago: hand them to the caller while the last DMAs and K1 run
   if ((rc = early_flags_end(h, s, flag_out, nobs))) return rc;
+  trace_mark("flags");
   return run_accum(h, c, f, s, any, nullptr, bad_lev);
 }
 
