@@ -221,7 +221,7 @@ def run_reference(args):
     sample = (f"{nfiles} of {cfg.nfiles} files ({nobs} obs) per step, sharded over {nthreads} threads with private "
               f"grids, partial grids summed, then Norm; pre-sort (gritas.f:499-523) not included")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, cfg.nfiles), "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
@@ -587,7 +587,7 @@ def run_b200(args):
                        if norm_kind == "sharded-peer" else
                        "K2x (tile sums as compact planes) + ncclReduce to rank 0 + K3x (finalize) pipelined in 8 chunks"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, nfiles), "mode": args.mode, "sharding": per_rank,
                        "l2": f"inputs ({nobs_rank * b_obs(NR) / 1e9:.2f} GB/step per rank) exceed the 126 MB L2; no flush needed"},
