@@ -509,10 +509,11 @@ struct CallTrace {
   CallTrace() {
     static const bool v = getenv("GRITAS_B200_TRACE") && atoi(getenv("GRITAS_B200_TRACE")) != 0;
     on = v;
-    if (on) t0 = last = now();
+    buf[0] = 0;
+    t0 = last = on ? now() : 0.0;
   }
   void mark(const char *what) {
-    if (!on) return;
+    if (!on || len >= (int)sizeof(buf) - 32) return;
     const double t = now();
     len += snprintf(buf + len, sizeof(buf) - (size_t)len, " %s %.3f", what, t - last);
     last = t;
