@@ -780,9 +780,34 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
   for (int ir = 0; ir < h->g.nr; ++ir) c.aligned = c.aligned && aligned16(c.d[ir]);
 
   // Fast mode picks between the tiled and the direct accumulate by looking at the data: the first call with at
-  // least 64 Ki observations runs the direct kernel with a locality probe (both paths add into the same records).
-  bool probe = false;
-  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice < 0 && !h->minmax) probe = n >= 65536;
+  // least 64 Ki observations is classified by a locality probe first.
+  if ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->staging && h->tiled_choice < 0 && !h->minmax && n >= 65536) {
+    // the probe looks at the first 256 Ki observations of this call (classification only, nothing is accumulated) ...
+    if (any_copy) {
+      if (int pr = flush_pending(h, s)) return pr;
+      CU(cudaEventRecord(s.copied, h->copy));
+      CU(cudaStreamWaitEvent(h->compute, s.copied, 0));
+    }
+    ObsCols cp = c;
+    cp.n = std::min(n, 1 << 18);
+    cp.flag_out = nullptr;
+    const int nvec = (cp.n + OBS_PER_THREAD - 1) / OBS_PER_THREAD;
+    const int nblk = grid_for((size_t)nvec, ACC_THREADS, 8);
+    const size_t psmem = levtab_smem_bytes(h->g);
+    switch (h->g.nr) {
+      case 1: launch_fast<1>(h, cp, f, nblk, psmem, true); break;
+      case 2: launch_fast<2>(h, cp, f, nblk, psmem, true); break;
+      default: launch_fast<3>(h, cp, f, nblk, psmem, true); break;
+    }
+    CU(cudaGetLastError());
+    h->launches += 1;
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status), cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    const unsigned pairs = h->h_status[0].pairs, nearp = h->h_status[0].near_pairs;
+    h->tiled_choice = (pairs > 0 && (double)nearp < 0.5 * (double)pairs) ? 1 : 0;
+    // ... and the whole call then runs on the path it picked
+  }
+  const bool probe = false;
   const bool tiled = h->staging && (h->det_tiled || ((h->mode & 0xff) == GRITAS_B200_MODE_FAST && h->tiled_choice == 1));
   if (h->det_tiled) {
     if (!h->call_order_set) h->call_order = h->det_calls;
@@ -849,12 +874,6 @@ int run_accum(gritas_b200_handle h, ObsCols c, const FilterDesc &f, Slot &s, boo
       default: launch_fast<3>(h, c, f, nblk, smem, probe); break;
     }
     h->launches += 1;
-    if (probe) {
-      CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(Status), cudaMemcpyDeviceToHost, h->compute));
-      CU(cudaStreamSynchronize(h->compute));
-      const unsigned pairs = h->h_status[0].pairs, nearp = h->h_status[0].near_pairs;
-      h->tiled_choice = (pairs > 0 && (double)nearp < 0.5 * (double)pairs) ? 1 : 0;
-    }
   } else {
     if (int tr = touch_records(h)) return tr;
     // keys -> stable LSD radix sort of (key, obs index) on a sort stream -> in-order segment sums on `compute`

@@ -612,6 +612,9 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
       pairc = __reduce_add_sync(0xffffffffu, pairc);
       if (lane == 0 && pairc) { atomicAdd(&st->near_pairs, nearc); atomicAdd(&st->pairs, pairc); }
     }
+    // the probe only looks: the call is then accumulated on the path the host picks (nothing reaches the records, so a
+    // tiled month's Norm does not have to read them)
+    if constexpr (!PROBE) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const unsigned key = k4[j];
@@ -664,6 +667,7 @@ k_accum_fast(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__re
           if (base + j < c.n) c.flag_out[base + j] = fa[j];
       }
     }
+    }   // !PROBE
   }
 }
 
