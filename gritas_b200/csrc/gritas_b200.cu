@@ -1108,6 +1108,8 @@ int gritas_b200_create(gritas_b200_handle *hp, int im, int jm, int km, int nlevs
       size_t cap = (slots / ntiles) & ~(size_t)31;
       if (cap >= 256 && smem <= (size_t)227 * 1024 && shift >= 8 && shift <= 15) {
         h->sg.tile_shift = shift;
+        h->sg.det_r0 = 192u;
+        if (const char *e_r0 = getenv("GRITAS_B200_DET_R0")) h->sg.det_r0 = (unsigned)std::max(32, atoi(e_r0));
         h->sg.ntiles = (unsigned)ntiles;
         h->sg.cap = (unsigned)std::min(cap, (size_t)0x7fffffe0);
         h->stage_slots = ntiles * (size_t)h->sg.cap;

@@ -95,6 +95,7 @@ struct StageDesc {
   unsigned char *lists;  // [cap / LIST_G][ntiles][LIST_G] entries of ListEntry<nr>::BYTES bytes, see list_slot()
   unsigned cap, ntiles;
   int tile_shift;
+  unsigned det_r0;       // deterministic tile kernel: runs longer than this are ordered by a warp's bitonic network, shorter ones by counting
   unsigned *dirty;       // [ntiles] set when an entry of the tile was accumulated directly (list overflow): the tile's
                          // records are no longer all zero
 };
@@ -1796,7 +1797,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
           // ---- order of every box's run by sequence number: s_inv[start + k] = position of the k-th entry.  Short runs: every
           // entry counts the smaller sequence numbers of its run.  Long runs (clustered data: a radiosonde site's box holds
           // hundreds of entries) would make that quadratic: one warp sorts such a run with a bitonic network instead ----
-          constexpr unsigned R0 = 192u;
+          const unsigned R0 = sg.det_r0;
           for (unsigned pos = tid; pos < m; pos += NTH) {
             const unsigned box = s_boxof[pos];
             const unsigned st = s_off[box] - gbase, r = s_tot[box];
