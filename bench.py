@@ -267,6 +267,19 @@ def run_b200(args):
     nobs_rank = sum(len(c["lat"]) for c in files)
     expected_rank = accepted(files)
 
+    def expected_sums(fs):
+        # what the finalized grids must add up to: sum x, sum x^2 (per residual column) and sum x1*x2 over the accepted
+        # observations, and the sums of their absolute values (the scale of the comparison)
+        out = np.zeros(10)
+        for c in fs:
+            m = np.isin(c["qcexcl"], (0, synth.X_PASSIVE, synth.X_PRE_BAD)) & (table0[c["kx"] - 1, c["kt"] - 1] != 0)
+            x1 = c["omf"][m]
+            x2 = c["oma"][m] if cfg.nr == 2 else x1
+            out += [x1.sum(), x2.sum(), (x1 * x1).sum(), (x2 * x2).sum(), (x1 * x2).sum(),
+                    np.abs(x1).sum(), np.abs(x2).sum(), (x1 * x1).sum(), (x2 * x2).sum(), np.abs(x1 * x2).sum()]
+        return out
+    sums_rank = expected_sums(files)
+
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -381,16 +394,30 @@ def run_b200(args):
         if marks is not None:
             marks[2].record(stream)
 
-    def slab_count(host):
-        """accepted observations in this rank's slab of the count grid (whole grid at N=1)"""
+    def slab_sums(host):
+        """[accepted observations, n*mean (x1, x2), n*rms^2 (x1, x2), n*<x1 x2>] summed over this rank's slab of the finalized
+        3-D grids (the whole grids at N=1): the statistics of every box, folded back into the sums they came from"""
         if world == 1 or norm_kind != "sharded-peer":
-            return float(host["nobs_3d"].sum()) if (world == 1 or rank == 0) else 0.0
-        a3, b3, _, _ = G.slab(rank, world)
-        tot3 = 0.0
-        for l in range(a3 // cfg.jm, (b3 - 1) // cfg.jm + 1 if b3 > a3 else 0):
-            ja, jb = max(a3, l * cfg.jm) - l * cfg.jm, min(b3, (l + 1) * cfg.jm) - l * cfg.jm
-            tot3 += float(host["nobs_3d"][:, ja:jb, :, l].sum())
-        return tot3
+            if not (world == 1 or rank == 0):
+                return np.zeros(6)
+            pieces = [(slice(None), slice(None))]
+        else:
+            a3, b3, _, _ = G.slab(rank, world)
+            pieces = []
+            for l in range(a3 // cfg.jm, (b3 - 1) // cfg.jm + 1 if b3 > a3 else 0):
+                ja, jb = max(a3, l * cfg.jm) - l * cfg.jm, min(b3, (l + 1) * cfg.jm) - l * cfg.jm
+                pieces.append((slice(ja, jb), l))
+        tot = np.zeros(6)
+        for js, ls in pieces:
+            n = host["nobs_3d"][:, js, :, ls]
+            w = np.where(n > 0, n, 0.0)
+            i2 = NR - 1
+            b1, b2 = host["bias_3d"][:, js, :, ls, 0], host["bias_3d"][:, js, :, ls, i2]
+            r1, r2 = host["rtms_3d"][:, js, :, ls, 0], host["rtms_3d"][:, js, :, ls, i2]
+            xy = host["xcov_3d"][:, js, :, ls, 0] if NR == 2 else r1 * r1
+            z = lambda a: np.where(n > 0, a, 0.0)
+            tot += [n.sum(), (w * z(b1)).sum(), (w * z(b2)).sum(), (w * z(r1) ** 2).sum(), (w * z(r2) ** 2).sum(), (w * z(xy)).sum()]
+        return tot
 
     def timed_device(calls, steps, warmup):
         for _ in range(warmup):
@@ -452,12 +479,17 @@ def run_b200(args):
     # every accepted observation of the month is in exactly one box (count grid vs the host-side filter)
     host_out = G.alloc_grids(pinned=True)
     step(dev_calls, host_out)
-    cnt = torch.tensor([slab_count(host_out)], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor(np.concatenate([slab_sums(host_out), sums_rank]), dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt)
+    cnt = cnt.cpu().numpy()
     check = bool(int(cnt[0]) == expected_total)
     if not check:
         raise SystemExit(f"count check failed: {int(cnt[0])} binned, {expected_total} expected")
+    # ... and the means / mean squares / mean products of all boxes add up to the month's sums (every rank's slab, any N)
+    sum_err = float(np.max(np.abs(cnt[1:6] - cnt[6:11]) / np.maximum(cnt[11:16], 1e-300)))
+    if not sum_err < 1e-9:
+        raise SystemExit(f"sum check failed: finalized grids do not add up to the month's sums (relative error {sum_err:.3e})")
 
     # ---- end-to-end arm: pinned host columns in, finalized grids out to pinned host arrays ----
     e2e = None
@@ -594,6 +626,9 @@ def run_b200(args):
             "accumulate_ms_per_step": accum_ms, "norm_ms_per_step": norm_ms,
             "spread": {"accumulate_ms": dev["accum_spread"], "norm_ms": dev["norm_spread"], "note": "rank 0, per timed step"},
             "host_enqueue_ms_per_step": dev["host_enqueue_ms"], "count_check": check,
+            "sum_check": {"ok": True, "max_rel_err": sum_err,
+                          "what": "sum over all boxes of n*mean, n*rms^2, n*<x1 x2> of the finalized grids (every rank's slab) against "
+                                  "the sums over the accepted observations, relative to the sums of absolute values"},
             "accepted_obs": expected_total, "gpu_launches": int(dev["launches_per_step"] * args.steps),
             "gpu_launches_per_step": int(dev["launches_per_step"]), "clocks": clocks, "roofline": roofline}
     if world == 1:
