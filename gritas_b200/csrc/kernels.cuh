@@ -24,6 +24,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <assert.h>
+
+// -DGRITAS_B200_BOUNDS: every data-dependent index into shared memory, the tile lists, the records and the output planes is
+// asserted (a debug build for the GPU tests; compute-sanitizer is not available on every pool).  Off by default: no code.
+#ifdef GRITAS_B200_BOUNDS
+#define GB_ASSERT(c) assert(c)
+#else
+#define GB_ASSERT(c) ((void)0)
+#endif
 
 namespace gb200 {
 
@@ -932,7 +941,9 @@ k_list_obs(const GridDesc g, const ObsCols c, const FilterDesc f, Status *__rest
 #pragma unroll
       for (int ir = 0; ir < NR; ++ir) d[ir] = (f.scale_res | f.expr) ? residual_value(f, c, ir, dd[ir][j], base + j) : dd[ir][j];
       const unsigned tile = key >> sg.tile_shift;
+      GB_ASSERT(tile < sg.ntiles && (size_t)key < (size_t)g.nbox3 + (size_t)g.nbox2);
       if (pos[j] < sg.cap) {
+        GB_ASSERT(list_slot(sg, tile, pos[j]) < (size_t)sg.cap * sg.ntiles);
         const unsigned long long w0 = DET ? (((seq_base + (unsigned long long)(base + j)) << 16) | (unsigned long long)(key & ((1u << sg.tile_shift) - 1u)))
                                           : (unsigned long long)key;
         entry_store<NR>(sg.lists, list_slot(sg, tile, pos[j]), w0, d);
@@ -1267,11 +1278,14 @@ __device__ __forceinline__ void tile_finalize_out(const GridDesc &g, size_t firs
       const unsigned jl = (unsigned)(((double)col + 0.5) * g.rim), i = col - jl * (unsigned)g.im;
       const unsigned l = (unsigned)(((double)jl + 0.5) * g.rjm), j = jl - l * (unsigned)g.jm;
       const size_t o = (size_t)i + (size_t)g.im * ((size_t)j + (size_t)g.jm * ((size_t)k + (size_t)km * (size_t)l));
+      GB_ASSERT(rel >= head && rel - head < T && first + (rel - head) < plane3 && o < plane3 && i < (unsigned)g.im && j < (unsigned)g.jm &&
+                k < km && l < (unsigned)g.l3d);
       box(rel - head, true, (int)k >= g.nlevs, raw3, o3, o, plane3);   // levels nlevs..km-1: never touched, zeros
     }
   }
   for (size_t rec = max(first, plane3) + tid; rec < first + nb; rec += NTH) {
     if (PEER && (rec < peers.own_lo || rec >= peers.own_hi)) continue;
+    GB_ASSERT(rec - first < T && rec - plane3 < plane2);
     box((unsigned)(rec - first), false, false, raw2, o2, rec - plane3, plane2);
   }
 }
@@ -1406,6 +1420,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
             while (src + 1 < peers.n && e >= s_off[src + 1]) ++src;
             pk[u] = entry_load<NR>(peers.lists[src], list_slot(sg, tile, e - s_off[src]), d[u]) & (T - 1u);
           } else {
+            GB_ASSERT(tile < sg.ntiles && e < sg.cap);
             pk[u] = entry_load<NR>(sg.lists, list_slot(sg, tile, e), d[u]) & (T - 1u);
           }
         }
@@ -1457,6 +1472,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       for (int u = 0; u < EPT; ++u) {
         if ((unsigned)u >= live_u || pk[u] == KEY_NONE) continue;
         const unsigned pos = s_cnt[pk[u] & 0xFFFFu] + (pk[u] >> 16);
+        GB_ASSERT((pk[u] & 0xFFFFu) < T && pos < (unsigned)CH && pos < s_cnt[(pk[u] & 0xFFFFu) + 1u]);
 #pragma unroll
         for (int ir = 0; ir < NR; ++ir) s_stage[(size_t)ir * CH + pos] = d[u][ir];
       }
@@ -1466,6 +1482,7 @@ k_tile_final(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, 
       const bool first_chunk = c0 == 0u;
       for (unsigned b = tid; b < T; b += NTH) {
         const unsigned s0 = s_cnt[b], e0 = s_cnt[b + 1u];
+        GB_ASSERT(s0 <= e0 && e0 <= (unsigned)CH);
         if (!first_chunk && e0 == s0) continue;
         double a[NV];
 #pragma unroll
@@ -1768,6 +1785,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
             const unsigned box = (unsigned)wv & (T - 1u);
             if (box < b0 || box >= b1) return;
             const unsigned rel = s_off[box] - gbase + (have_ticket ? ticket : atomicAdd(s_cur + box, 1u));
+            GB_ASSERT(rel < (unsigned)CH && rel < s_off[box + 1u] - gbase);
             s_seq[rel] = wv >> 16;
             s_boxof[rel] = (unsigned short)box;
 #pragma unroll
@@ -1805,6 +1823,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
             const unsigned long long mine = s_seq[pos];
             unsigned rank = 0u;
             for (unsigned q = st; q < st + r; ++q) rank += (s_seq[q] < mine) ? 1u : 0u;
+            GB_ASSERT(rank < r && st + r <= (unsigned)CH);
             s_inv[st + rank] = (unsigned short)pos;
           }
           __syncthreads();
@@ -1824,6 +1843,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
             auto cmpx = [&](unsigned a, unsigned c) {
               if (c >= r) return;
               const unsigned ia = st + a, ic = st + c;
+              GB_ASSERT(a < c && ic < (unsigned)CH);
               const unsigned long long ka = s_seq[ia], kc = s_seq[ic];
               if (ka > kc) {
                 s_seq[ia] = kc;
@@ -1862,6 +1882,7 @@ k_tile_det(const GridDesc g, const StageDesc sg, unsigned nrec, OutPlanes o2, Ou
 #pragma unroll 1
             for (unsigned k = 0; k < r; ++k) {
               const unsigned pos = s_inv[st + k];
+              GB_ASSERT(st + r <= (unsigned)CH && pos < (unsigned)CH && pos >= st && pos < st + r);
               double x[NR];
 #pragma unroll
               for (int ir = 0; ir < NR; ++ir) x[ir] = s_stage[(size_t)ir * CH + pos];
