@@ -5,12 +5,21 @@
  * and bench.py's cpu_baseline / --impl reference legs may build, load or call it.  The product
  * (gritas_b200/, include/) never links against or falls back to anything in oracle/.
  *
- * PARITY UNPINNED: the reference (GEOS-ESM/GrITAS) ships no tests, golden vectors or sample
- * data for this path and cannot be built here (no Fortran compiler; GMAO_Shared / ESMA_cmake
- * are un-vendored externals).  The restatement below follows the reference source literally,
- * one routine per reference routine, and is cross-checked against an independently written
- * numpy twin (oracle/oracle_np.py) and the known-answer tests derived from the source
- * (SURVEY.md section 4).  All citations are relative to /root/reference/.
+ * PARITY: the reference (GEOS-ESM/GrITAS) ships no tests, golden vectors or sample data for this path and cannot be
+ * built here (no Fortran compiler; GMAO_Shared / ESMA_cmake are un-vendored externals).  What this restatement is
+ * pinned against instead:
+ *   - PINNED against the reference's own source text: oracle/f2c_subset.py translates GrITAS_Pint_, GrITAS_Accum_,
+ *     GrITAS_Norm_, GrITAS_MinMax_, GrITAS_3CH_Norm_, the mesh statements of init_ (m_gritas_grids.f), GrITAS_KxKt
+ *     (gritas_kxkt.f), the residual selection chain, the QC / time / longitude filter loop and the Jo scaling
+ *     (gritas.f:562-704, 712-735, 738) to C STATEMENT BY STATEMENT from the files where they lie, gcc compiles the
+ *     result (oracle/_ref, git-ignored), and tests/test_oracle_vs_ref.py demands bit-for-bit agreement with the
+ *     routines below -- flags, sums, statistics, tables, error statements, on random inputs, the committed golden
+ *     fixtures and the edge cases of SURVEY.md section 4;
+ *   - still UNPINNED (hand restatement only, cross-checked against an independently written numpy twin and
+ *     hand-computed answers): the pre-sort (m_MergeSorts is un-vendored), the mask gather, the three cross-covariance
+ *     routines and the scorecard reductions.
+ * The restatement follows the reference source literally, one routine per reference routine.  All citations are
+ * relative to /root/reference/.
  *
  * Conventions kept from the reference build:
  *   - every `real` is 64-bit (FREAL8: src/Components/gritas/CMakeLists.txt:3-4), `integer` is

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  Never imported by the gritas_b200 package.
-PARITY UNPINNED (see gritas_oracle.c header): the reference ships no golden vectors.
+Pinned against the reference's own routines translated to C (oracle/ref.py, tests/test_oracle_vs_ref.py) for the
+gridding path; the rest is unpinned (see the header of gritas_oracle.c).
 """
 from __future__ import annotations
 

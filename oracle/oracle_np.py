@@ -2,7 +2,7 @@
 
 Written separately from oracle/gritas_oracle.c (vectorised, no shared code) so that the two
 restatements of the reference pin each other: tests/test_oracle.py requires them to agree
-bit-for-bit.  PARITY UNPINNED against the reference itself (it has no tests or goldens).
+bit-for-bit.  The C oracle is additionally pinned against the reference's own routines translated to C (oracle/ref.py).
 Citations are relative to /root/reference/src/Components/gritas/ unless noted.
 """
 from __future__ import annotations

@@ -1,0 +1,97 @@
+/* Glue around oracle/_ref/gritas_ref_gen.c -- the C that oracle/f2c_subset.py generates from the reference's own
+ * Fortran source (m_gritas_grids.f), statement by statement.  TEST INFRASTRUCTURE: it pins the hand-written oracle
+ * (tests/test_oracle_vs_ref.py) and the golden vectors (tests/golden/make_golden.py); nothing under gritas_b200/ uses it.
+ *
+ * Only what a Fortran caller supplies is written here: the module state grids_init / the rc file set up
+ * (m_gritas_grids.f:105-190: im, jm, km, nlevs, plevs; KXMAX / KTMAX of m_odsmeta), the optional argument, and
+ * gritas_perror (etc.f:54-60: print and exit(7)) turned into a return code of 7. */
+#include "_ref/gritas_ref_gen.c"
+#include <string.h>
+
+int ref_init(int im_, int jm_, int km_, int nlevs_, const double *plevs_, int kxmax_, int ktmax_) {
+  im = im_; jm = jm_; km = km_; nlevs = nlevs_; kxmax = kxmax_; ktmax = ktmax_;
+  free(plevs);
+  plevs = (double *)malloc(sizeof(double) * (size_t)(km_ > 0 ? km_ : 1));      /* allocate ( ..., plevs(km), ... ) :120 */
+  memcpy(plevs, plevs_, sizeof(double) * (size_t)nlevs_);
+  gritas_ref_mesh();                                                            /* dLon, dLat :128-129 */
+  return 0;
+}
+double ref_dlon(void) { return dlon; }
+double ref_dlat(void) { return dlat; }
+int ref_error_line(void) { return gritas_ref_error_line; }
+
+#define GUARD() do { gritas_ref_error_line = 0; if (setjmp(gritas_ref_jmp)) return 7; } while (0)
+
+int ref_pint(double *p1, double *p2) { GUARD(); gritas_pint_(p1, p2); return 0; }
+
+int ref_accum(double *lat, double *lon, double *lev, int *kx, int *kt, double *del, int nobs, int nr, int *kxkt_table,
+              double *p1, double *p2, int *ob_flag, int l2d, double *bias_2d, double *rtms_2d, double *xcov_2d,
+              double *nobs_2d, int l3d, double *bias_3d, double *rtms_3d, double *xcov_3d, double *nobs_3d) {
+  GUARD();
+  gritas_accum_(lat, lon, lev, kx, kt, del, nobs, nr, kxkt_table, p1, p2, ob_flag, l2d, bias_2d, rtms_2d, xcov_2d, nobs_2d,
+                l3d, bias_3d, rtms_3d, xcov_3d, nobs_3d);
+  return 0;
+}
+
+int ref_minmax(double *lat, double *lon, double *lev, int *kx, int *kt, double *del, int nobs, int nr, int *kxkt_table,
+               double *p1, double *p2, int *ob_flag, int l2d, double *minv_2d, double *maxv_2d, double *nobs_2d, int l3d,
+               double *minv_3d, double *maxv_3d, double *nobs_3d) {
+  GUARD();
+  gritas_minmax_(lat, lon, lev, kx, kt, del, nobs, nr, kxkt_table, p1, p2, ob_flag, l2d, minv_2d, maxv_2d, nobs_2d, l3d,
+                 minv_3d, maxv_3d, nobs_3d);
+  return 0;
+}
+
+/* has_ntresh = 0: the optional argument is absent (gritas.f:885-887 calls GrITAS_Norm without it) */
+int ref_norm(int nr, int nrmlz, int l2d, double *bias_2d, double *rtms_2d, double *stdv_2d, double *xcov_2d, double *nobs_2d,
+             int l3d, double *bias_3d, double *rtms_3d, double *stdv_3d, double *xcov_3d, double *nobs_3d, int ntresh,
+             int has_ntresh) {
+  GUARD();
+  gritas_norm_(nr, nrmlz, l2d, bias_2d, rtms_2d, stdv_2d, xcov_2d, nobs_2d, l3d, bias_3d, rtms_3d, stdv_3d, xcov_3d, nobs_3d,
+               has_ntresh ? &ntresh : (int *)0);
+  return 0;
+}
+
+int ref_norm_3ch(int nr, int nrmlz, int l2d, double *bias_2d, double *rtms_2d, double *var_2d, double *xcov_2d,
+                 double *nobs_2d, int l3d, double *bias_3d, double *rtms_3d, double *var_3d, double *xcov_3d, double *nobs_3d,
+                 int ntresh, int has_ntresh) {
+  GUARD();
+  gritas_3ch_norm_(nr, nrmlz, l2d, bias_2d, rtms_2d, var_2d, xcov_2d, nobs_2d, l3d, bias_3d, rtms_3d, var_3d, xcov_3d, nobs_3d,
+                   has_ntresh ? &ntresh : (int *)0);
+  return 0;
+}
+
+/* is_surface (gritas_kxkt.f:121-171): kt < 0 or kt among ktSurfAll of m_odsmeta (GMAO_ods, not in the tree: the list is
+ * an input of the harness, as it is of the oracle) */
+static int n_surf_ = 0, kt_surf_[64];
+void ref_set_surface_kts(const int *kts, int n) { n_surf_ = n > 64 ? 64 : n; memcpy(kt_surf_, kts, sizeof(int) * (size_t)n_surf_); }
+int is_surface_(int kt) {
+  int ic = 0;
+  for (int i = 0; i < n_surf_; ++i) ic += kt_surf_[i] == kt;   /* ic(1) = count(ktSurfAll.eq.kt) */
+  return ic > 0 || kt < 0;
+}
+
+int ref_kxkt(int ktmax_, int kxmax_, int l2d_max, int l3d_max, int listsz, int *kt_list, int *kx_list, int *kxkt_table,
+             int *list_2d, int *list_3d, int *l2d, int *l3d) {
+  GUARD();
+  gritas_kxkt_(ktmax_, kxmax_, l2d_max, l3d_max, listsz, kt_list, kx_list, kxkt_table, list_2d, list_3d, l2d, l3d);
+  return 0;
+}
+
+int ref_select(int iopt, int scale_res, int xcov, int pxcov, int tch, int self, int meanres, int nobs, int nr, int x_passive,
+               int *nstat, double *del, double *omf, double *oma, double *obs, double *xvec, double *xm, int *qcexcl,
+               double *m_obs, double *m_omf, double *m_oma) {
+  GUARD();
+  gritas_select_(iopt, scale_res, xcov, pxcov, tch, self, meanres, nobs, nr, x_passive, nstat, del, omf, oma, obs, xvec, xm,
+                 qcexcl, m_obs, m_omf, m_oma);
+  return 0;
+}
+
+int ref_filter(int nobs, int ioptn, int t1, int t2, double lona, double lonb, int x_passive, int x_pre_bad, int *qcexcl,
+               int *time, double *lon, int *ob_flag) {
+  GUARD();
+  gritas_filter_(nobs, ioptn, t1, t2, lona, lonb, x_passive, x_pre_bad, qcexcl, time, lon, ob_flag);
+  return 0;
+}
+
+int ref_jo_scale(int iopt, int nobs, int nr, double *del) { GUARD(); gritas_jo_scale_(iopt, nobs, nr, del); return 0; }

@@ -1,9 +1,11 @@
 """Generates tests/golden/*.npz: small seeded inputs + the CPU oracle's outputs for them.
 
-PARITY UNPINNED: the reference ships no golden vectors and cannot be built here (Fortran, un-vendored
-GMAO_Shared), so these fixtures freeze the ORACLE's answers (oracle/gritas_oracle.c, cross-checked
-against the independent numpy twin before writing).  They travel to the GPU box, where the CUDA path
-must reproduce them, and they pin the oracle itself against regressions.
+The reference ships no golden vectors and cannot be built here (Fortran, un-vendored GMAO_Shared).  These fixtures hold
+the answers of the CPU oracle (oracle/gritas_oracle.c), cross-checked before writing against the independent numpy twin
+AND -- where /root/reference is present -- against the reference's own GrITAS_Pint_ / GrITAS_Accum_ / GrITAS_Norm_
+translated to C statement by statement (oracle/ref.py): every array of every fixture is what the reference's routines
+return for these inputs (tests/test_oracle_vs_ref.py::test_golden_inputs_through_the_translated_reference re-checks the
+committed files).  They travel to the GPU box, where the CUDA path must reproduce them.
 
     python tests/golden/make_golden.py
 """
@@ -16,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from gritas_b200 import synth  # noqa: E402
-from oracle import oracle, oracle_np  # noqa: E402
+from oracle import oracle, oracle_np, ref  # noqa: E402
 
 CASES = {
     # name: (config, scale, nfiles, nr, im, jm, kt_list, kx_lists)
@@ -69,7 +71,27 @@ def run_oracle(cfg, files, nr):
                                                 "xcov_3d", "nobs_3d")}
     for nm in raw:   # the two independent restatements must agree bit for bit before a golden is written
         assert np.array_equal(raw[nm], tw[nm]), nm
+    if ref.available():   # the reference's own routines (translated): same flags and raw sums, then the same statistics
+        ref.init(cfg.im, cfg.jm, cfg.km, cfg.nlevs, cfg.plevs, table.shape[0], table.shape[1])
+        r1, r2 = ref.pint(cfg.nlevs)
+        assert np.array_equal(r1, p1) and np.array_equal(r2, p2)
+        gr = oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, nr)
+        for c, fo in zip(files, flags):
+            fr = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=1, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
+            d = np.zeros((len(fr), nr), order="F")
+            d[:, 0] = c["omf"]
+            if nr > 1:
+                d[:, 1] = c["oma"]
+            ref.accum(gr, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], d, table, r1, r2, fr)
+            assert np.array_equal(fr, fo)
+        for nm in raw:
+            assert np.array_equal(raw[nm], getattr(gr, nm)), nm
+        ref.norm(gr, True, None)
     oracle.norm(g, cfg.nlevs, True, 0)
+    if ref.available():
+        for nm in g.names():
+            if not ((nm.endswith("2d") and l2d == 0) or (nm.endswith("3d") and l3d == 0)):
+                assert np.array_equal(getattr(g, nm), getattr(gr, nm)), nm
     twn = oracle_np.norm(tw, cfg.nlevs, nr, True, 0)
     for nm in g.names():
         if (nm.endswith("2d") and l2d == 0) or (nm.endswith("3d") and l3d == 0):

@@ -1,7 +1,8 @@
 """The CPU oracle (oracle/gritas_oracle.c) pinned against: the committed golden fixtures, an
 independently written numpy twin (bit for bit), and the known-answer tests that follow from the
-reference source.  PARITY UNPINNED against gritas.x itself: the reference
-ships no tests/goldens and cannot be built here (no Fortran compiler, un-vendored GMAO_Shared)."""
+reference source.  gritas.x itself cannot be built here (no Fortran compiler, un-vendored
+GMAO_Shared) and ships no tests; tests/test_oracle_vs_ref.py pins the oracle against the reference's own routines
+translated to C statement by statement."""
 import numpy as np
 import pytest
 
