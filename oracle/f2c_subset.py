@@ -26,7 +26,7 @@ from __future__ import annotations
 import re
 import sys
 
-INTRINSICS = {"nint", "abs", "min", "max", "sqrt", "exp", "log", "real", "present", "dble", "int", "mod"}
+INTRINSICS = {"nint", "abs", "min", "max", "sqrt", "exp", "log", "real", "present", "dble", "int", "mod", "any", "sum", "size"}
 RELOPS = {".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".eq.": "==", ".ne.": "!=", ".and.": "&&", ".or.": "||",
           ".not.": "!", ".true.": "1", ".false.": "0", "/=": "!=", "==": "==", "<=": "<=", ">=": ">=", "<": "<", ">": ">"}
 
@@ -85,7 +85,31 @@ def logical_lines(text: str, first: int, last: int):
         label = head.strip() if head.strip().isdigit() else None
         body = line[6:] if label or not head.strip() else line    # free-ish lines that start before column 7
         res.append((label, lower_outside_strings(body.strip()), no))
-    return [(lab, normalise(st), no) for lab, st, no in res]
+    out = []
+    for lab, st, no in res:
+        parts = split_semicolons(normalise(st))
+        for k, p_ in enumerate(parts):
+            out.append((lab if k == 0 else None, p_, no))
+    return out
+
+
+def split_semicolons(st: str):
+    parts, cur, q = [], [], None
+    for ch in st:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            cur.append(ch)
+        elif ch == ";":
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur).strip())
+    return [p_ for p_ in parts if p_]
 
 
 DOTOPS = "lt|le|gt|ge|eq|ne|and|or|not|true|false"
@@ -162,6 +186,13 @@ class Scope:
         v = self.vars.get(name)
         return bool(v and v["dims"])
 
+    def extent(self, name, q):
+        """C expression of the extent of dimension q (0-based) of array `name`"""
+        return expr_c(self.vars[name]["dims"][q], self)
+
+    def total(self, name):
+        return " * ".join(f"(size_t)({self.extent(name, q)})" for q in range(len(self.vars[name]["dims"])))
+
 
 def number_c(tok: str) -> str:
     t = tok.replace("d", "e")
@@ -208,9 +239,29 @@ def expr_c(tokens, sc: Scope) -> str:
                             lo = [t for t in a[:a.index(("op", ":"))]]
                             v = next(sec)                     # section: the loop variable runs over lo..hi
                             idx.append(f"({expr_c(lo, sc) if lo else '1'}) + {v}")
+                        elif any(t == ("op", ":") for t in a):
+                            # vector subscript `x(indx(:))`: this dimension is a section too; the subscript array runs
+                            # over the same loop variable
+                            v = next(sec)
+                            keep = sc.section_vars
+                            sc.section_vars = [v]
+                            try:
+                                idx.append(expr_c(a, sc))
+                            finally:
+                                sc.section_vars = keep
                         else:
                             idx.append(expr_c(a, sc))
                     out.append(f"{val}({', '.join(idx)})")
+                elif val in ("any", "sum", "size"):
+                    nm = args[0][0][1]
+                    if len(args[0]) != 1 or not sc.is_array(nm):
+                        raise ValueError(f"{val}() of something other than a whole array")
+                    if val == "size":
+                        out.append(f"((int)({sc.total(nm)}))" if len(args) == 1 else f"({sc.extent(nm, int(args[1][0][1]) - 1)})")
+                    else:
+                        t = sc.vars[nm]["type"]
+                        op = "r_ = r_ || " if val == "any" else "r_ += "
+                        out.append(f"({{ {'int' if val == 'any' else t} r_ = 0; for (size_t z_ = 0; z_ < {sc.total(nm)}; ++z_) {op}{nm}[z_]; r_; }})")
                 elif val in INTRINSICS:
                     a = [expr_c(x, sc) for x in args]
                     if val == "nint":
@@ -266,10 +317,26 @@ def parse_decl(stmt):
     if rest.startswith("(") and typ == "char":                           # character(len=*)
         rest = rest[rest.index(")") + 1:].strip()
     attrs = []
+    dim_attr = None
     if "::" in rest:
         a, rest = rest.split("::", 1)
-        attrs = [x.strip() for x in a.strip(" ,").split(",") if x.strip()]
-        # attributes like intent(in) contain no top-level commas; dimension(...) is not used in the subset
+        attrs, depth, cur = [], 0, ""
+        for ch in a.strip(" ,") + ",":
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            if ch == "," and depth == 0:
+                if cur.strip():
+                    attrs.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        for x in attrs:
+            if x.startswith("dimension"):
+                t = tokenize(x[len("dimension"):])
+                dim_attr = split_top(t[1:matching_paren(t, 0)])
+        attrs = [re.sub(r"\s+", "", x) for x in attrs]
     toks = tokenize(rest)
     ents = []
     for part in split_top(toks):
@@ -284,7 +351,7 @@ def parse_decl(stmt):
             k = j + 1
         if k < len(part) and part[k] == ("op", "="):
             init = part[k + 1:]
-        ents.append((name, dims, init))
+        ents.append((name, dims if dims is not None else dim_attr, init))
     return typ, attrs, ents
 
 
@@ -325,9 +392,17 @@ class Translator:
                 if "parameter" in attrs or typ == "char":
                     continue                                            # myname_ strings: only used in messages
                 for nm, dims, init in ents:
-                    if "allocatable" in attrs:
-                        continue                                        # declared, never touched in the subset
-                    sc.vars[nm] = {"type": typ, "dims": dims, "optional": "optional" in attrs, "arg": nm in args}
+                    deferred = dims is not None and all(d == [("op", ":")] for d in dims)
+                    if "allocatable" in attrs and not any(re.search(rf"\b{nm}\b", st2) for _, st2, _ in ll[1:-1] if not parse_decl(st2)):
+                        continue                                        # declared, never touched
+                    v = {"type": typ, "dims": dims, "optional": "optional" in attrs, "arg": nm in args,
+                         "alloc": "allocatable" in attrs, "assumed": deferred and nm in args,
+                         "byref": nm in args and dims is None and any(a_ in ("intent(out)", "intent(inout)") for a_ in attrs)}
+                    if deferred:                                        # extents live in variables nm_n1, nm_n2, ...
+                        v["dims"] = [[("id", f"{nm}_n{q + 1}")] for q in range(len(dims))]
+                        for q in range(len(dims)):
+                            sc.vars[f"{nm}_n{q + 1}"] = {"type": "int", "dims": None, "optional": False, "arg": False}
+                    sc.vars[nm] = v
                     decl_order.append(nm)
                 continue
             if st.startswith(("use ", "implicit ")):
@@ -346,6 +421,8 @@ class Translator:
         for a in args:
             v = sc.vars[a]
             params.append(f"{v['type']} *{a}" if (v["dims"] or v["optional"] or v.get("byref")) else f"{v['type']} {a}")
+            if v.get("assumed"):                                        # assumed shape: the extents follow the pointer
+                params += [f"int {a}_n{q + 1}" for q in range(len(v["dims"]))]
         w = self.out.append
         w(f"/* {name}: translated from lines {first}-{last} */")
         w(f"void {cname}({', '.join(params) or 'void'}) {{")
@@ -353,7 +430,9 @@ class Translator:
         for nm in decl_order:
             v = sc.vars[nm]
             if not v["arg"]:
-                if v["dims"]:
+                if v.get("alloc"):
+                    w(f"  {v['type']} *{nm} = 0; int " + ", ".join(f"{nm}_n{q + 1} = 0" for q in range(len(v["dims"]))) + ";")
+                elif v["dims"]:
                     ext = " * ".join(f"({expr_c(d, sc)})" for d in v["dims"])
                     w(f"  {v['type']} {nm}_store[{ext}]; {v['type']} *{nm} = {nm}_store;")
                     w(f"  for (size_t z_ = 0; z_ < (size_t)({ext}); ++z_) {nm}_store[z_] = 0;   /* undefined in Fortran: zero here */")
@@ -429,6 +508,20 @@ class Translator:
         if st in ("endwhere", "end where"):
             sc.where = None
             return []
+        m = re.match(r"^allocate\s*\((.*)\)$", st)
+        if m:
+            lines = []
+            for part in split_top(tokenize(m.group(1))):
+                nm = part[0][1]
+                v = sc.vars[nm]
+                ext = split_top(part[2:matching_paren(part, 1)])
+                for q, e in enumerate(ext):
+                    lines.append(f"{nm}_n{q + 1} = {expr_c(e, sc)};")
+                lines.append(f"{nm} = ({v['type']} *)calloc({sc.total(nm)} + 1, sizeof({v['type']}));   /* undefined in Fortran: zero here */")
+            return lines
+        m = re.match(r"^deallocate\s*\((.*)\)$", st)
+        if m:
+            return [f"free({x.strip()}); {x.strip()} = 0;" for x in m.group(1).split(",")]
         if st in ("end do", "enddo"):
             if not do_stack or do_stack[-1] is not None:
                 raise ValueError(f"line {no}: end do without do")
@@ -449,10 +542,10 @@ class Translator:
             parts = split_top(toks[k + 2:])
             lo, hi = expr_c(parts[0], sc), expr_c(parts[1], sc)
             step = expr_c(parts[2], sc) if len(parts) > 2 else "1"
-            if step != "1":
-                raise ValueError("do loops with a stride are not in the subset")
             do_stack.append(lab)
-            # Fortran evaluates the bounds once
+            # Fortran evaluates the bounds (and the stride) once; strides in the subset are positive
+            if step != "1":
+                return [f"for (int do_hi_{no} = ({var} = {lo}, {hi}), do_st_{no} = {step}; {var} <= do_hi_{no}; {var} += do_st_{no}) {{"]
             return [f"for (int do_hi_{no} = ({var} = {lo}, {hi}); {var} <= do_hi_{no}; ++{var}) {{"]
         if toks[0] == ("id", "else") and len(toks) > 1 and toks[1] == ("id", "if"):
             j = matching_paren(toks, 2)
@@ -488,6 +581,12 @@ class Translator:
         if eq is None:
             raise ValueError(f"line {no}: statement not in the subset: {st!r}")
         lhs, rhs = toks[:eq], toks[eq + 1:]
+        if len(lhs) == 1 and sc.is_array(lhs[0][1]):
+            # whole-array assignment: array = array of the same shape (element by element) or array = scalar
+            nm = lhs[0][1]
+            if len(rhs) == 1 and rhs[0][0] == "id" and sc.is_array(rhs[0][1]):
+                return [f"for (size_t z_ = 0; z_ < {sc.total(nm)}; ++z_) {nm}[z_] = {rhs[0][1]}[z_];"]
+            return [f"for (size_t z_ = 0; z_ < {sc.total(nm)}; ++z_) {nm}[z_] = {expr_c(rhs, sc)};"]
         # array section on the left: a loop nest, innermost = first dimension (Fortran's array element order)
         sections = len(lhs) > 1 and lhs[1] == ("op", "(") and any(
             any(t == ("op", ":") for t in a) for a in split_top(lhs[2:matching_paren(lhs, 1)]))
@@ -552,11 +651,15 @@ def module_globals(text, first, last):
                 c.append(f"static const {typ} {nm} = {expr_c(init, sc)};   /* line {no} */")
                 g[nm] = {"type": typ, "dims": None, "optional": False, "arg": False}
             elif "allocatable" in attrs:
-                if nm != "plevs":
-                    continue                                          # only the level list is used by the subset
-                c.append(f"{typ} *{nm};   /* line {no}: allocatable, 1-based */")
-                c.append(f"#define {nm}(i1) {nm}[(size_t)(i1) - 1]")
-                g[nm] = {"type": typ, "dims": [[("id", "nlevs")]], "optional": False, "arg": False}
+                if nm == "plevs":
+                    c.append(f"{typ} *{nm};   /* line {no}: allocatable, 1-based */")
+                    c.append(f"#define {nm}(i1) {nm}[(size_t)(i1) - 1]")
+                    g[nm] = {"type": typ, "dims": [[("id", "nlevs")]], "optional": False, "arg": False}
+                elif nm == "achan":                                   # (nchan, 2): channel index / channel number
+                    c.append(f"{typ} *{nm}; int {nm}_n1;   /* line {no}: allocatable, 1-based, column-major */")
+                    c.append(f"#define {nm}(i1, i2) {nm}[(size_t)(i1) - 1 + (size_t)({nm}_n1) * ((size_t)(i2) - 1)]")
+                    g[nm] = {"type": typ, "dims": [[("id", f"{nm}_n1")], [("num", "2")]], "optional": False, "arg": False}
+                    g[f"{nm}_n1"] = {"type": "int", "dims": None, "optional": False, "arg": False}
             else:
                 c.append(f"{typ} {nm};   /* line {no} */")
                 g[nm] = {"type": typ, "dims": None, "optional": False, "arg": False}
@@ -616,7 +719,8 @@ def main(ref_root, dst):
     i0 = find_line(grids, r"^\s*dLon\s*=\s*360\.")
     out += ["/* ===== m_gritas_grids.f ===== */"] + statements_range(grids, i0, i0 + 1, g, "gritas_ref_mesh")
     tr = Translator(grids, g)
-    for name in ("GrITAS_Pint_", "GrITAS_Accum_", "GrITAS_Norm_", "GrITAS_MinMax_", "GrITAS_3CH_Norm_"):
+    for name in ("GrITAS_Pint_", "GrITAS_Accum_", "GrITAS_Norm_", "GrITAS_MinMax_", "GrITAS_3CH_Norm_",
+                 "GrITAS_XCov_Accum_", "GrITAS_XCov_Norm_", "GrITAS_XCov_Prs_Accum_"):
         tr.routine(name, name.lower())
     out += tr.out
 

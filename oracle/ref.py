@@ -74,6 +74,13 @@ def lib():
         L.ref_select.argtypes = [C.c_int] * 10 + [C.POINTER(C.c_int), _f64p] + [_f64p] * 5 + [_i32p] + [_f64p] * 3
         L.ref_filter.argtypes = [C.c_int] * 4 + [C.c_double] * 2 + [C.c_int] * 2 + [_i32p, _i32p, _f64p, _i32p]
         L.ref_jo_scale.argtypes = [C.c_int] * 3 + [_f64p]
+        L.ref_set_channels.argtypes = [_i32p, C.c_int, C.c_int]
+        L.ref_xcov_accum.argtypes = ([_f64p] * 3 + [_i32p, _i32p, _f64p, C.c_int, C.c_int, _i32p, _i32p, C.c_int, _f64p] + [C.c_int] * 3
+                                     + [_f64p, _f64p, C.POINTER(C.c_int), C.c_int])
+        L.ref_xcov_norm.argtypes = ([C.c_int] * 5 + [_f64p] + [C.c_int] * 3 + [_f64p] + [C.c_int] * 4 + [_f64p] + [C.c_int] * 2
+                                    + [C.c_int, C.c_int])
+        L.ref_xcov_prs_accum.argtypes = ([_f64p, _i32p, _i32p, _i32p, _f64p, C.c_int, C.c_int, _i32p, _f64p, _f64p, _i32p, C.c_int, _f64p]
+                                         + [C.c_int] * 3 + [_f64p] + [C.c_int] * 4 + [_f64p] + [C.c_int] * 2 + [C.POINTER(C.c_int), C.c_int])
         _lib = L
     return _lib
 
@@ -184,3 +191,33 @@ def filter_flags(qcexcl, time, lon, ioptn=1, t1=0, t2=-1, lona=-999.0, lonb=999.
     flag = np.full(n, -9, dtype=np.int32)
     _check(lib().ref_filter(n, ioptn, t1, t2, lona, lonb, x_passive, x_pre_bad, _i(qcexcl), _i(time), _f(lon), flag))
     return flag
+
+
+def xcov_accum(achan, lev, kx, kt, del_, kxkt_table, ob_flag, l3d, bias_lv, xcov_lv, nobs_lv, tch):
+    """GrITAS_XCov_Accum_ (m_gritas_grids.f:667-848); the profile length is the module's km (ref.init).  Returns nprof."""
+    d = np.asfortranarray(del_, dtype=np.float64)
+    n = len(lev)
+    lib().ref_set_channels(_i(achan), len(achan), 1)
+    nprof = C.c_int(0)
+    z = np.zeros(n)
+    _check(lib().ref_xcov_accum(z, z, _f(lev), _i(kx), _i(kt), d, n, d.shape[1], np.asfortranarray(kxkt_table, dtype=np.int32), ob_flag,
+                                l3d, bias_lv, *bias_lv.shape, xcov_lv, nobs_lv, C.byref(nprof), int(bool(tch))))
+    return nprof.value
+
+
+def xcov_norm(nr, nrmlz, tch, self_, l3d, bias_lv, xcov_lv, nobs_lv, ntresh=None):
+    """GrITAS_XCov_Norm_ (m_gritas_grids.f:859-1008), in place"""
+    _check(lib().ref_xcov_norm(nr, int(bool(nrmlz)), int(bool(tch)), int(bool(self_)), l3d, bias_lv, *bias_lv.shape, xcov_lv,
+                               *xcov_lv.shape, nobs_lv, *nobs_lv.shape, ntresh or 0, int(ntresh is not None)))
+
+
+def xcov_prs_accum(lev, ks, del_, p1, p2, l3d, bias_lv, xcov_lv, nobs_lv, tch):
+    """GrITAS_XCov_Prs_Accum_ (m_gritas_grids.f:1862-2059); levels from the module's nlevs (ref.init).  Returns nprof."""
+    d = np.asfortranarray(del_, dtype=np.float64)
+    n = len(lev)
+    zi = np.zeros(max(n, 1), np.int32)
+    nprof = C.c_int(0)
+    _check(lib().ref_xcov_prs_accum(_f(lev), zi, zi, _i(ks), d, n, d.shape[1], np.zeros((1, 1), np.int32, order="F"), _f(p1), _f(p2),
+                                    zi.copy(), l3d, bias_lv, *bias_lv.shape, xcov_lv, *xcov_lv.shape, nobs_lv, *nobs_lv.shape,
+                                    C.byref(nprof), int(bool(tch))))
+    return nprof.value

@@ -95,3 +95,38 @@ int ref_filter(int nobs, int ioptn, int t1, int t2, double lona, double lonb, in
 }
 
 int ref_jo_scale(int iopt, int nobs, int nr, double *del) { GUARD(); gritas_jo_scale_(iopt, nobs, nr, del); return 0; }
+
+/* ---- channel / level cross-covariances (m_gritas_grids.f:667-848, 859-1008, 1862-2059) ----
+ * active channels: achan(nchan, 2) = {index, number} columns and ichan_version pick one (set up by grids_init from the rc
+ * file); the harness fills both columns with the same list, as the oracle's single list does */
+void ref_set_channels(const int *ach, int n, int version) {
+  free(achan);
+  nchan = n; achan_n1 = n; ichan_version = version;
+  achan = (int *)malloc(sizeof(int) * (size_t)(2 * (n > 0 ? n : 1)));
+  for (int i = 0; i < n; ++i) { achan[i] = ach[i]; achan[n + i] = ach[i]; }
+}
+
+int ref_xcov_accum(double *lat, double *lon, double *lev, int *kx, int *kt, double *del, int nobs, int nr, int *kxkt_table,
+                   int *ob_flag, int l3d, double *bias_lv, int b1, int b2, int b3, double *xcov_lv, double *nobs_lv, int *nprof,
+                   int tch) {
+  GUARD();
+  gritas_xcov_accum_(lat, lon, lev, kx, kt, del, nobs, nr, kxkt_table, ob_flag, l3d, bias_lv, b1, b2, b3, xcov_lv, nobs_lv, nprof, tch);
+  return 0;
+}
+
+int ref_xcov_norm(int nr, int nrmlz, int tch, int self, int l3d, double *bias_3d, int b1, int b2, int b3, double *xcov_3d, int x1,
+                  int x2, int x3, int x4, double *nobs_3d, int n1, int n2, int ntresh, int has_ntresh) {
+  GUARD();
+  gritas_xcov_norm_(nr, nrmlz, tch, self, l3d, bias_3d, b1, b2, b3, xcov_3d, x1, x2, x3, x4, nobs_3d, n1, n2,
+                    has_ntresh ? &ntresh : (int *)0);
+  return 0;
+}
+
+int ref_xcov_prs_accum(double *lev, int *kx, int *kt, int *ks, double *del, int nobs, int nr, int *kxkt_table, double *p1,
+                       double *p2, int *ob_flag, int l3d, double *bias_lv, int b1, int b2, int b3, double *xcov_lv, int x1, int x2,
+                       int x3, int x4, double *nobs_lv, int n1, int n2, int *nprof, int tch) {
+  GUARD();
+  gritas_xcov_prs_accum_(lev, kx, kt, ks, del, nobs, nr, kxkt_table, p1, p2, ob_flag, l3d, bias_lv, b1, b2, b3, xcov_lv, x1, x2, x3,
+                         x4, nobs_lv, n1, n2, nprof, tch);
+  return 0;
+}

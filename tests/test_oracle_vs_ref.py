@@ -284,3 +284,89 @@ def test_qc_time_longitude_filter(ioptn, window):
     want = oracle.filter_flags(qcexcl, time, lon, ioptn=ioptn, t1=t1, t2=t2, lona=lona, lonb=lonb, x_passive=7, x_pre_bad=1)
     got = ref.filter_flags(qcexcl, time, lon, ioptn=ioptn, t1=t1, t2=t2, lona=lona, lonb=lonb, x_passive=7, x_pre_bad=1)
     assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# channel / level cross-covariances: GrITAS_XCov_Accum_ (:667-848), GrITAS_XCov_Norm_ (:859-1008), GrITAS_XCov_Prs_Accum_ (:1862-2059)
+
+@pytest.mark.parametrize("tch", [False, True])
+@pytest.mark.parametrize("two_grids", [False, True])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_xcov_accum_and_norm(seed, two_grids, tch):
+    from tests import xcov_data
+    km, nr = 24, (3 if tch else 2)
+    achan = np.array([2, 3, 5, 8, 9, 13, 20], np.int32)
+    d = xcov_data.make_profiles(seed, 60, km, achan, nr, two_grids=two_grids)
+    ref.init(4, 3, km, 1, np.array([500.0]), d["table"].shape[0], d["table"].shape[1])
+    bo, xo, no = oracle.xcov_alloc(len(achan), d["l3d"], nr)
+    br, xr, nr_ = oracle.xcov_alloc(len(achan), d["l3d"], nr)
+    f1, f2 = d["flag"].copy(), d["flag"].copy()
+    for rep in range(2):                                                  # two files into the same sums
+        p1 = oracle.xcov_accum(km, achan, d["lev"], d["kx"], d["kt"], d["del_"], d["table"], f1, d["l3d"], bo, xo, no, tch)
+        p2 = ref.xcov_accum(achan, d["lev"], d["kx"], d["kt"], d["del_"], d["table"], f2, d["l3d"], br, xr, nr_, tch)
+        assert p1 == p2 and np.array_equal(f1, f2)
+    for a, b in ((bo, br), (xo, xr), (no, nr_)):
+        assert np.array_equal(a, b)
+    raw = [a.copy() for a in (bo, xo, no)]
+    for self_ in ((False, True) if tch else (False,)):
+        for nrmlz, ntresh in ((True, None), (False, None), (True, 5)):
+            for dst, src in zip((bo, xo, no, br, xr, nr_), raw + raw):
+                dst[...] = src
+            oracle.xcov_norm(nr, nrmlz, tch, self_, d["l3d"], bo, xo, no, ntresh or 0)
+            ref.xcov_norm(nr, nrmlz, tch, self_, d["l3d"], br, xr, nr_, ntresh)
+            for a, b, nm in ((bo, br, "bias"), (xo, xr, "xcov"), (no, nr_, "nobs")):
+                assert np.array_equal(a, b, equal_nan=True), (nm, self_, nrmlz, ntresh)
+
+
+def test_xcov_accum_incomplete_profiles_are_fatal():
+    ref.init(4, 3, 24, 1, np.array([500.0]), 8, 8)
+    b, x, n = oracle.xcov_alloc(3, 1, 2)
+    lev = np.arange(1.0, 26.0)                                            # 25 observations, km = 24
+    z = np.zeros(25, np.int32)
+    with pytest.raises(ref.RefError):
+        ref.xcov_accum(np.array([1, 2, 3], np.int32), lev, z + 1, z + 1, np.zeros((25, 2), order="F"), np.ones((8, 8), np.int32), z.copy(),
+                       1, b, x, n, False)
+
+
+@pytest.mark.parametrize("tch", [False, True])
+@pytest.mark.parametrize("seed", [3, 4])
+def test_xcov_prs_accum(seed, tch):
+    rng = np.random.default_rng(seed)
+    nlev, nr = 9, (3 if tch else 2)
+    plevs = np.sort(rng.uniform(20.0, 1000.0, nlev))[::-1].copy()
+    ref.init(4, 3, nlev, nlev, plevs, 4, 4)
+    p1, p2 = ref.pint(nlev)
+    # soundings: runs of equal ks, 3..12 levels each, some levels twice in a sounding.
+    # A DEFECT OF THE REFERENCE shapes this input: its run-length count (:1961-1975) books the first observation of a run
+    # to the run before it, so the LAST sounding of a call is allocated one element short and gathered past the end of
+    # rlev / rdel (and a sounding index that comes back later overflows by a whole run): undefined behaviour, the sums of
+    # that sounding depend on what the heap holds.  The oracle and the CUDA path compute what the loop intends.  To pin
+    # everything else bit for bit the call ends with a one-observation sounding whose residuals are zero: whatever the
+    # reference reads for it, it adds one count and nothing else -- in both implementations.
+    ks, lev = [], []
+    for s in range(40):
+        m = int(rng.integers(3, 13))
+        ks += [100 + s] * m
+        lev += list(np.exp(rng.uniform(np.log(25.0), np.log(1500.0), m)))
+    ks.append(999)
+    lev.append(500.0)
+    ks, lev = np.array(ks, np.int32), np.array(lev)
+    d = np.asfortranarray(rng.normal(0.1, 1.0, (len(ks), nr)))
+    d[-1, :] = 0.0
+    bo, xo, no = oracle.xcov_alloc(nlev, 1, nr)
+    br, xr, nr_ = oracle.xcov_alloc(nlev, 1, nr)
+    for rep in range(2):
+        q1 = oracle.xcov_prs_accum(nlev, lev, ks, d, p1, p2, 1, bo, xo, no, tch)
+        q2 = ref.xcov_prs_accum(lev, ks, d, p1, p2, 1, br, xr, nr_, tch)
+        assert q1 == q2
+    for a, b, nm in ((bo, br, "bias"), (xo, xr, "xcov"), (no, nr_, "nobs")):
+        assert np.array_equal(a, b), nm
+
+
+def test_xcov_prs_accum_level_miss():
+    plevs = np.array([850.0, 500.0, 250.0])
+    ref.init(4, 3, 3, 3, plevs, 4, 4)
+    p1, p2 = ref.pint(3)
+    b, x, n = oracle.xcov_alloc(3, 1, 2)
+    with pytest.raises(ref.RefError):
+        ref.xcov_prs_accum(np.array([2500.0]), np.array([1], np.int32), np.zeros((1, 2), order="F"), p1, p2, 1, b, x, n, False)
