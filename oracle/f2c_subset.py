@@ -64,11 +64,26 @@ def lower_outside_strings(s: str) -> str:
     return "".join(out)
 
 
-def logical_lines(text: str, first: int, last: int):
-    """(label or None, statement, first physical line number) of the fixed-form lines first..last (1-based, inclusive)."""
+def logical_lines(text: str, first: int, last: int, free: bool = False):
+    """(label or None, statement, first physical line number) of the source lines first..last (1-based, inclusive);
+    fixed form (column-6 continuation) unless `free` (trailing `&`)."""
     res = []
+    pending = False
     for no, raw in enumerate(text.split("\n"), 1):
         if no < first or no > last:
+            continue
+        if free:
+            line = strip_comment(raw).strip()
+            if not line:
+                continue
+            more = line.endswith("&")
+            line = lower_outside_strings(line.rstrip("&").strip().lstrip("&").strip())
+            if pending:
+                lab, st, n0 = res[-1]
+                res[-1] = (lab, st + " " + line, n0)
+            else:
+                res.append((None, line, no))
+            pending = more
             continue
         if not raw.strip() or raw[0] in "cC*!":
             continue
@@ -365,8 +380,8 @@ class Translator:
     def find_routine(self, name):
         lines = self.text.split("\n")
         start = end = None
-        pat = re.compile(rf"^\s*subroutine\s+{re.escape(name)}\b", re.I)
-        pend = re.compile(rf"^\s*end(\s+subroutine(\s+{re.escape(name)})?)?\s*(!.*)?$", re.I)
+        pat = re.compile(rf"^\s*(subroutine|real\s+function)\s+{re.escape(name)}\b", re.I)
+        pend = re.compile(rf"^\s*end(\s+(subroutine|function)(\s+{re.escape(name)})?)?\s*(!.*)?$", re.I)
         for no, l in enumerate(lines, 1):
             if start is None and pat.match(l):
                 start = no
@@ -381,9 +396,12 @@ class Translator:
         first, last = self.find_routine(name)
         ll = logical_lines(self.text, first, last)
         head = ll[0][1]
-        m = re.match(r"subroutine\s+\w+\s*\((.*)\)\s*$", head)
+        m = re.match(r"(?:subroutine|real\s+function)\s+\w+\s*\((.*)\)\s*$", head)
         args = [a.strip() for a in m.group(1).split(",")] if m and m.group(1).strip() else []
+        is_function = head.startswith("real")
         sc = Scope(self.globals)
+        if is_function:                                                 # the result variable carries the function's name
+            sc.vars[name.lower()] = {"type": "double", "dims": None, "optional": False, "arg": False}
         body, decl_order = [], []
         for label, st, no in ll[1:-1]:
             d = parse_decl(st)
@@ -425,7 +443,9 @@ class Translator:
                 params += [f"int {a}_n{q + 1}" for q in range(len(v["dims"]))]
         w = self.out.append
         w(f"/* {name}: translated from lines {first}-{last} */")
-        w(f"void {cname}({', '.join(params) or 'void'}) {{")
+        w(f"{'double' if is_function else 'void'} {cname}({', '.join(params) or 'void'}) {{")
+        if is_function:
+            w(f"  double {name.lower()} = 0;")
         macros = []
         for nm in decl_order:
             v = sc.vars[nm]
@@ -443,8 +463,8 @@ class Translator:
             if v["dims"]:
                 macros.append(nm)
                 w(self.accessor(nm, v["dims"], sc))
-        self.statements(body, sc)
-        w("  return;")
+        self.statements(body, sc, ret=(name.lower() if is_function else None))
+        w(f"  return {name.lower()};" if is_function else "  return;")
         for nm in macros:
             w(f"#undef {nm}")
         w("}")
@@ -461,7 +481,8 @@ class Translator:
         return f"#define {nm}({', '.join(idx)}) {nm}[{e}]"
 
     # ------------------------------------------------------------------------------------------ statements
-    def statements(self, body, sc):
+    def statements(self, body, sc, ret=None):
+        self.ret = ret
         w = self.out.append
         do_stack = []                 # label (or None) of every open do loop
         ind = "  "
@@ -487,7 +508,7 @@ class Translator:
         if st.startswith(("print", "format", "write")) or re.match(r"^\d+\s+format", st):
             return [f"/* line {no}: output statement dropped */"]
         if st == "return":
-            return ["return;"]
+            return [f"return {self.ret};" if getattr(self, "ret", None) else "return;"]
         if st == "cycle":
             return ["continue;"]
         if st == "exit":
@@ -498,6 +519,22 @@ class Translator:
         m = re.match(r"^call\s+(gritas_perror|die)\b", st)
         if m:
             return [f'gritas_ref_perror({no});']
+        m = re.match(r"^call\s+(indexset|indexsort)\s*\((.*)\)$", st)
+        if m:
+            # m_MergeSorts (GMAO_mpeu, not in the tree): the harness supplies a stable ascending / descending index sort; the
+            # key sequence, the key arrays and the direction are what is translated.  Array sections starting at 1 pass the array
+            args = []
+            typ = ""
+            for a in split_top(tokenize(m.group(2))):
+                if len(a) > 2 and a[1] == ("op", "=") and a[0][0] == "id":
+                    a = a[2:]                                          # keyword argument: descend=.false.
+                if a[0][0] == "id" and sc.is_array(a[0][1]):
+                    if m.group(1) == "indexsort" and len(args) == 2:
+                        typ = "_i" if sc.vars[a[0][1]]["type"] == "int" else "_d"
+                    args.append(a[0][1])
+                else:
+                    args.append(expr_c(a, sc))
+            return [f"{m.group(1)}{typ}_({', '.join(args)});"]
         m = re.match(r"^where\s*\((.*)\)$", st)
         if m:                                                  # masked section assignments until endwhere
             sc.where = (tokenize(m.group(1)), False)
@@ -666,7 +703,7 @@ def module_globals(text, first, last):
     return g, c
 
 
-def statements_range(text, first, last, globals_, cname, params=(), locals_=()):
+def statements_range(text, first, last, globals_, cname, params=(), locals_=(), free=False):
     """a run of plain statements (no declarations) as a C function.  params / locals_: (ctype, name, dims or None, byref)
     -- the declarations the statements rely on, stated by the caller (they sit far away in the program unit)."""
     tr = Translator(text, globals_)
@@ -686,7 +723,7 @@ def statements_range(text, first, last, globals_, cname, params=(), locals_=()):
         if dims:
             macros.append(nm)
             tr.out.append(Translator.accessor(nm, sc.vars[nm]["dims"], sc))
-    tr.statements(logical_lines(text, first, last), sc)
+    tr.statements(logical_lines(text, first, last, free), sc)
     for nm in macros:
         tr.out.append(f"#undef {nm}")
     tr.out.append("}")
@@ -722,7 +759,39 @@ def main(ref_root, dst):
     for name in ("GrITAS_Pint_", "GrITAS_Accum_", "GrITAS_Norm_", "GrITAS_MinMax_", "GrITAS_3CH_Norm_",
                  "GrITAS_XCov_Accum_", "GrITAS_XCov_Norm_", "GrITAS_XCov_Prs_Accum_"):
         tr.routine(name, name.lower())
+    tr.routine("ave_nomiss", "gritas_ave_nomiss_")
     out += tr.out
+    # the scorecard's latitude rows: the grid latitudes (:136-138) and the row search of init_ (:165-175)
+    r0 = find_line(grids, r"^\s*glat\(j\) = LatMin")
+    out += statements_range(grids, r0 - 1, r0 + 1, g, "gritas_glat_", params=[("double", "glat", ["jm"], False)],
+                            locals_=[("int", "j", None, False)])
+    r1 = find_line(grids, r"^\s*do j = 1, jm\s*$", find_line(grids, r"Wired regions"))
+    r2 = find_line(grids, r"^\s*end do\s*$", r1)
+    out += statements_range(grids, r1, r2, g, "gritas_region_rows_", params=[
+        ("int", "i", None, False), ("int", "nreg", None, False), ("double", "glat", ["jm"], False),
+        ("double", "regbounds", ["2", "nreg"], False), ("int", "regindx", ["2", "nreg"], False)],
+        locals_=[("int", "j", None, False)])
+
+    # m_gritas_masks.F90 (free form): the mesh of the mask grid (:152-153) and the loop of maskout_ (:164-183)
+    masks = open(os.path.join(ref_root, "Components/gritas/m_gritas_masks.F90")).read()
+    out += ["/* ===== m_gritas_masks.F90 ===== */"]
+    gm = dict(g)
+    for pat_ in (r"^\s*real\s*::\s*lonMin_", r"^\s*real\s*::\s*latMin_"):
+        no = find_line(masks, pat_)
+        typ, attrs, ents = parse_decl(logical_lines(masks, no, no, free=True)[0][1])
+        nm, _, init = ents[0]
+        out.append(f"static const {typ} {nm} = {expr_c(init, Scope(g))};   /* line {no} */")
+        gm[nm] = {"type": typ, "dims": None, "optional": False, "arg": False}
+    m0 = find_line(masks, r"^\s*dLon = 360\. / im")
+    out += statements_range(masks, m0, m0 + 1, gm, "gritas_mask_mesh_", params=[
+        ("int", "im", None, False), ("int", "jm", None, False), ("double", "dlon", None, True), ("double", "dlat", None, True)], free=True)
+    m1 = find_line(masks, r"^\s*do n=1,nobs", m0)
+    m2 = find_line(masks, r"^\s*enddo\s*$", m1)
+    out += statements_range(masks, m1, m2, gm, "gritas_mask_loop_", params=[
+        ("int", "nobs", None, False), ("int", "im", None, False), ("int", "jm", None, False), ("double", "dlon", None, False),
+        ("double", "dlat", None, False), ("double", "lat", ["nobs"], False), ("double", "lon", ["nobs"], False),
+        ("int", "qcx", ["nobs"], False), ("double", "maskfld", ["im", "jm"], False), ("int", "nexcl", None, True)],
+        locals_=[("int", "n", None, False), ("int", "i", None, False), ("int", "j", None, False)], free=True)
 
     # gritas_kxkt.f: GrITAS_KxKt
     out += ["/* ===== gritas_kxkt.f ===== */"]
@@ -755,6 +824,17 @@ def main(ref_root, dst):
         col("double", "ods_data_lon"), col("int", "ob_flag")],
         locals_=[("int", "i", None, False), ("int", "iampassive", None, False), ("int", "iwantpassive", None, False),
                  ("int", "timeselect", None, False), ("int", "lonselect", None, False)])
+    # gritas.f:500-508: the eight index sorts before the accumulation (key order and direction; the sort itself is m_MergeSorts')
+    s0 = find_line(app, r"^\s*call IndexSet\s*\(\s*nobs, is\s*\)")
+    s1 = s0
+    while re.match(r"^\s*call IndexSort", app.split("\n")[s1]):      # s1 is 1-based: index s1 is the following line
+        s1 += 1
+    out += ["void indexset_(int n, int *is); void indexsort_i_(int n, int *is, int *key, int descend); "
+            "void indexsort_d_(int n, int *is, double *key, int descend);   /* m_MergeSorts: supplied by the harness */"]
+    out += statements_range(app, s0, s1, g, "gritas_presort_", params=[
+        ("int", "nobs", None, False), ("int", "is", ["nobs"], False), col("int", "ods_data_qcexcl"), col("double", "ods_data_lat"),
+        col("double", "ods_data_lon"), col("double", "ods_data_lev"), col("int", "ods_data_time"), col("int", "ods_data_kt"),
+        col("int", "ods_data_ks"), col("int", "ods_data_kx")])
     # gritas.f:738, right after the filter loop: omf / sigo for the Jo options
     j0 = find_line(app, r"if\(iopt==17 \.or\. iopt==19\)", f1)
     out += statements_range(app, j0, j0, g, "gritas_jo_scale_", params=[

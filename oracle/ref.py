@@ -24,7 +24,7 @@ _LIB = os.path.join(_DIR, "libgritas_ref.so")
 _GEN = os.path.join(_DIR, "gritas_ref_gen.c")
 REF_ROOT = "/root/reference/src"
 REF_FILES = [os.path.join(REF_ROOT, f) for f in ("Components/gritas/m_gritas_grids.f", "Components/gritas/gritas_kxkt.f",
-                                                 "Applications/GrITAS_App/gritas.f")]
+                                                 "Components/gritas/m_gritas_masks.F90", "Applications/GrITAS_App/gritas.f")]
 CFLAGS = ["-O2", "-march=x86-64-v2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-Wall", "-Wno-unused-label",
           "-Wno-unused-variable", "-Wno-unused-but-set-variable"]
 
@@ -75,6 +75,11 @@ def lib():
         L.ref_filter.argtypes = [C.c_int] * 4 + [C.c_double] * 2 + [C.c_int] * 2 + [_i32p, _i32p, _f64p, _i32p]
         L.ref_jo_scale.argtypes = [C.c_int] * 3 + [_f64p]
         L.ref_set_channels.argtypes = [_i32p, C.c_int, C.c_int]
+        L.ref_ave_nomiss.argtypes = [_f64p, _f64p, C.c_int, C.c_int, _i32p, _i32p]
+        L.ref_ave_nomiss.restype = C.c_double
+        L.ref_region_rows.argtypes = [C.c_int, _f64p, _i32p]
+        L.ref_maskout.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _f64p, _i32p]
+        L.ref_presort.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p]
         L.ref_xcov_accum.argtypes = ([_f64p] * 3 + [_i32p, _i32p, _f64p, C.c_int, C.c_int, _i32p, _i32p, C.c_int, _f64p] + [C.c_int] * 3
                                      + [_f64p, _f64p, C.POINTER(C.c_int), C.c_int])
         L.ref_xcov_norm.argtypes = ([C.c_int] * 5 + [_f64p] + [C.c_int] * 3 + [_f64p] + [C.c_int] * 4 + [_f64p] + [C.c_int] * 2
@@ -221,3 +226,30 @@ def xcov_prs_accum(lev, ks, del_, p1, p2, l3d, bias_lv, xcov_lv, nobs_lv, tch):
                                     zi.copy(), l3d, bias_lv, *bias_lv.shape, xcov_lv, *xcov_lv.shape, nobs_lv, *nobs_lv.shape,
                                     C.byref(nprof), int(bool(tch))))
     return nprof.value
+
+
+def ave_nomiss(x, nobs, xregion, yregion):
+    """ave_nomiss (m_gritas_grids.f:1797-1826) on one (im, jm) slab"""
+    x, nobs = np.asfortranarray(x, dtype=np.float64), np.asfortranarray(nobs, dtype=np.float64)
+    return lib().ref_ave_nomiss(x, nobs, x.shape[0], x.shape[1], _i(xregion), _i(yregion))
+
+
+def score_regions(regbounds=oracle.REGBOUNDS):
+    """first / last latitude row of every region as init_ finds them (m_gritas_grids.f:136-138, 163-175; jm from ref.init)"""
+    rb = np.asfortranarray(np.array(regbounds, dtype=np.float64).T)
+    out = np.zeros((2, rb.shape[1]), np.int32, order="F")
+    lib().ref_region_rows(rb.shape[1], rb, out)
+    return out
+
+
+def maskout(im, jm, lat, lon, maskfld, qcx):
+    """maskout_ (m_gritas_masks.F90:137-186); qcx int32 inout, returns the number of observations excluded"""
+    return lib().ref_maskout(im, jm, len(lat), _f(lat), _f(lon), np.asfortranarray(maskfld, dtype=np.float64), qcx)
+
+
+def presort(qcexcl, lat, lon, lev, time, kt, ks, kx):
+    """gritas.f:500-508 -> 0-based permutation (the sort itself, m_MergeSorts, is a stable merge sort by assumption)"""
+    n = len(lat)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    lib().ref_presort(n, out, _i(qcexcl), _f(lat), _f(lon), _f(lev), _i(time), _i(kt), _i(ks), _i(kx))
+    return out[:n] - 1

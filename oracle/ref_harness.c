@@ -130,3 +130,58 @@ int ref_xcov_prs_accum(double *lev, int *kx, int *kt, int *ks, double *del, int 
                          x4, nobs_lv, n1, n2, nprof, tch);
   return 0;
 }
+
+/* ---- scorecard: ave_nomiss (m_gritas_grids.f:1797-1826) and the latitude rows of the regions (init_, :136-138, 163-175) ---- */
+double ref_ave_nomiss(double *x, double *nobs, int n1, int n2, int *xregion, int *yregion) {
+  return gritas_ave_nomiss_(x, n1, n2, nobs, n1, n2, xregion, yregion);
+}
+
+/* regbounds (2, nreg): what init_ wires for its region names (:146-157); regindx (2, nreg) starts at zero */
+void ref_region_rows(int nreg, double *regbounds, int *regindx) {
+  double *glat = (double *)malloc(sizeof(double) * (size_t)(jm > 0 ? jm : 1));
+  gritas_glat_(glat);
+  for (int i = 1; i <= nreg; ++i) gritas_region_rows_(i, nreg, glat, regbounds, regindx);   /* do i=1,size(regnames) :162 */
+  free(glat);
+}
+
+/* ---- land / ocean mask gather: maskout_ (m_gritas_masks.F90:137-186) on a mask field the caller holds ---- */
+int ref_maskout(int im_, int jm_, int nobs, double *lat, double *lon, double *maskfld, int *qcx) {
+  double dlon_ = 0, dlat_ = 0;
+  int nexcl = 0;                                     /* nexcl=0 :148 */
+  gritas_mask_mesh_(im_, jm_, &dlon_, &dlat_);      /* dLon, dLat :152-153 */
+  gritas_mask_loop_(nobs, im_, jm_, dlon_, dlat_, lat, lon, qcx, maskfld, &nexcl);
+  return nexcl;
+}
+
+/* ---- the pre-sort (gritas.f:500-508).  IndexSet / IndexSort are m_MergeSorts of GMAO_mpeu (not in the tree): a STABLE merge
+ * sort of the index by the key is ASSUMED here as in the oracle; what the translation pins is the sequence of keys, their
+ * arrays and the direction.  is() is 1-based, as the Fortran index. ---- */
+void indexset_(int n, int *is) { for (int i = 0; i < n; ++i) is[i] = i + 1; }
+static void merge_sort_idx(int n, int *is, const double *key, int descend) {
+  int *tmp = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  for (int w = 1; w < n; w *= 2) {
+    for (int lo = 0; lo < n; lo += 2 * w) {
+      int mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n, a = lo, b = mid, o = lo;
+      while (a < mid && b < hi) {
+        const double ka = key[is[a] - 1], kb = key[is[b] - 1];
+        const int take_b = descend ? (kb > ka) : (kb < ka);               /* ties keep the earlier entry: stable */
+        tmp[o++] = take_b ? is[b++] : is[a++];
+      }
+      while (a < mid) tmp[o++] = is[a++];
+      while (b < hi) tmp[o++] = is[b++];
+    }
+    memcpy(is, tmp, sizeof(int) * (size_t)n);
+  }
+  free(tmp);
+}
+void indexsort_d_(int n, int *is, double *key, int descend) { merge_sort_idx(n, is, key, descend); }
+void indexsort_i_(int n, int *is, int *key, int descend) {
+  double *k = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) k[i] = (double)key[i];
+  merge_sort_idx(n, is, k, descend);
+  free(k);
+}
+int ref_presort(int nobs, int *is, int *qcexcl, double *lat, double *lon, double *lev, int *time, int *kt, int *ks, int *kx) {
+  gritas_presort_(nobs, is, qcexcl, lat, lon, lev, time, kt, ks, kx);
+  return 0;
+}

@@ -1,11 +1,15 @@
 """The hand-written CPU oracle (oracle/gritas_oracle.c) against the reference's OWN Fortran routines, translated to C
-statement by statement (oracle/f2c_subset.py reads m_gritas_grids.f where it lies under /root/reference; oracle/ref.py
-loads the compiled result).  Everything must agree BIT FOR BIT: level intervals, ob_flag, raw sums, statistics,
-min / max, the three-cornered-hat Norm, the mesh sizes, and the statement at which gritas_perror is called.
+statement by statement (oracle/f2c_subset.py reads the sources where they lie under /root/reference; oracle/ref.py loads
+the compiled result).  Everything must agree BIT FOR BIT: level intervals, ob_flag, raw sums, statistics, min / max, the
+three-cornered-hat Norm, the channel / level cross-covariances, the (kx,kt) table, every residual option, the QC filter,
+the mask gather, the pre-sort permutation, the scorecard means and region rows, the mesh sizes, and the statement at which
+gritas_perror is called.
 
-This is what pins the oracle: GrITAS_Pint_ (m_gritas_grids.f:217-296), GrITAS_Accum_ (:307-478), GrITAS_Norm_ (:490-656),
-GrITAS_MinMax_ (:1019-1167), GrITAS_3CH_Norm_ (:1178-1341), dLon / dLat (:128-129).  Skipped where neither the reference
-sources nor a built oracle/_ref/libgritas_ref.so exist."""
+This is what pins the oracle: m_gritas_grids.f GrITAS_Pint_ (:217-296), GrITAS_Accum_ (:307-478), GrITAS_Norm_ (:490-656),
+GrITAS_XCov_Accum_ (:667-848), GrITAS_XCov_Norm_ (:859-1008), GrITAS_MinMax_ (:1019-1167), GrITAS_3CH_Norm_ (:1178-1341),
+ave_nomiss (:1797-1826), GrITAS_XCov_Prs_Accum_ (:1862-2059), init_ (:128-129, 136-138, 163-175); gritas_kxkt.f GrITAS_KxKt
+(:10-119); m_gritas_masks.F90 maskout_ (:152-153, 164-183); gritas.f :500-508, :562-704, :712-735, :738.  Skipped where
+neither the reference sources nor a built oracle/_ref/libgritas_ref.so exist."""
 import numpy as np
 import pytest
 
@@ -370,3 +374,79 @@ def test_xcov_prs_accum_level_miss():
     b, x, n = oracle.xcov_alloc(3, 1, 2)
     with pytest.raises(ref.RefError):
         ref.xcov_prs_accum(np.array([2500.0]), np.array([1], np.int32), np.zeros((1, 2), order="F"), p1, p2, 1, b, x, n, False)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# scorecard: the latitude rows of the regions (init_, :136-138, 163-175), ave_nomiss (:1797-1826) under scores2_'s loop nest
+
+@pytest.mark.parametrize("jm", [181, 91, 46, 721, 25])
+def test_region_rows(jm):
+    ref.init(8, jm, 1, 1, np.array([500.0]), 4, 4)
+    assert np.array_equal(ref.score_regions(), oracle.score_regions(jm))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_scorecard_reductions(seed):
+    """scores2_ (:1671-1795) is a loop nest around ave_nomiss: surface variables first (level slot 1), then every level of
+    every upper-air variable, for mean / rms / stdv and every region; collect_stats is real(4)."""
+    rng = np.random.default_rng(seed)
+    im, jm, km, l2d, l3d = 24, 19, 4, 2, 3
+    ref.init(im, jm, km, km, np.array([850.0, 500.0, 250.0, 100.0]), 4, 4)
+    g = oracle.Grids(im, jm, km, l2d, l3d, 1)
+    for nm in g.names():
+        a = getattr(g, nm)
+        a[...] = rng.normal(0.0, 2.0, a.shape) if not nm.startswith("nobs") else rng.integers(0, 5, a.shape)
+    for nm in ("bias", "rtms", "stdv"):                      # missing boxes
+        for tag in ("2d", "3d"):
+            a = getattr(g, f"{nm}_{tag}")
+            a[rng.random(a.shape) < 0.3] = oracle.AMISS
+    g.bias_3d[:, :, 2, 1, 0] = oracle.AMISS                  # a level without any valid box
+    regindx = ref.score_regions()
+    want = oracle.scores2(g, regindx)
+    lon = np.array([1, im], np.int32)
+    got = np.zeros_like(want)
+    for ne, nm in enumerate(("bias", "rtms", "stdv")):
+        for mr in range(regindx.shape[1]):
+            nv = 0
+            for lm in range(l2d):
+                got[mr, 0, nv, ne] = ref.ave_nomiss(getattr(g, nm + "_2d")[:, :, lm, 0], g.nobs_2d[:, :, lm], lon, regindx[:, mr])
+                nv += 1
+            for lm in range(l3d):
+                for kk in range(km):
+                    got[mr, kk, nv, ne] = ref.ave_nomiss(getattr(g, nm + "_3d")[:, :, kk, lm, 0], g.nobs_3d[:, :, kk, lm], lon,
+                                                         regindx[:, mr])
+                nv += 1
+    assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# land / ocean mask gather: maskout_ (m_gritas_masks.F90:137-186)
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_maskout(seed):
+    rng = np.random.default_rng(seed)
+    im, jm = int(rng.integers(6, 80)), int(rng.integers(4, 50))
+    n = 5000
+    lat = rng.uniform(-95, 95, n)
+    lon = rng.uniform(-200, 380, n)
+    lon[:100] = -180.0 + (rng.integers(0, 2 * im, 100) + 0.5) * (360.0 / im)        # NINT ties, +-180
+    lat[:100] = -90.0 + (rng.integers(0, 2 * jm, 100) * 0.5) * (180.0 / (jm - 1))
+    mask = np.asfortranarray(rng.choice(np.array([0.0, 0.5, 0.98, 0.99, 0.995, 1.0]), (im, jm)))
+    q0 = (rng.random(n) < 0.3).astype(np.int32)
+    q1, q2 = q0.copy(), q0.copy()
+    n1 = oracle.maskout(im, jm, lat, lon, mask, q1)
+    n2 = ref.maskout(im, jm, lat, lon, mask, q2)
+    assert n1 == n2 and np.array_equal(q1, q2)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the pre-sort (gritas.f:500-508): key sequence and direction from the source; the sort itself (m_MergeSorts, un-vendored) is a
+# stable merge sort by assumption on both sides
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg5"])
+def test_presort_key_sequence(name):
+    cfg = synth.get_config(name, 0.01)
+    c = synth.make_file(cfg, 1)
+    a = oracle.presort(c["qcexcl"], c["lat"], c["lon"], c["lev"], c["time"], c["kt"], c["ks"], c["kx"])
+    b = ref.presort(c["qcexcl"], c["lat"], c["lon"], c["lev"], c["time"], c["kt"], c["ks"], c["kx"])
+    assert np.array_equal(a, b)
