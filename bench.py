@@ -224,7 +224,7 @@ def run_reference(args):
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, cfg.nfiles), "sample": sample},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "pinned": "the port agrees bit for bit with the reference's own routines translated to C statement by statement (oracle/f2c_subset.py, tests/test_oracle_vs_ref.py)", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -644,7 +644,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(32, len(files))
         v, dt, nobs = time_cpu(cfg, files[:ns], 1, 1, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "pinned": "the port agrees bit for bit with the reference's own routines translated to C statement by statement (oracle/f2c_subset.py, tests/test_oracle_vs_ref.py)",
                                 "sample": f"{ns} of {nfiles} files ({nobs} obs): QC filter + GrITAS_Accum per file, "
                                           f"then GrITAS_Norm, single thread (the reference is serial); its 8-key "
                                           f"pre-sort (gritas.f:499-523) is not included",

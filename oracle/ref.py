@@ -40,6 +40,8 @@ def build(force: bool = False) -> str | None:
             os.makedirs(_DIR, exist_ok=True)
             subprocess.check_call([sys.executable, os.path.join(_HERE, "f2c_subset.py"), REF_ROOT, _GEN])
             subprocess.check_call(["gcc"] + CFLAGS + ["-shared", "-o", _LIB, os.path.join(_HERE, "ref_harness.c"), "-lm"], cwd=_HERE)
+            if not os.environ.get("GRITAS_KEEP_REF_C"):
+                os.remove(_GEN)        # the translated text is an intermediate: only the compiled library stays (and travels)
     return _LIB if os.path.exists(_LIB) else None
 
 
