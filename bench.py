@@ -134,17 +134,21 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(cfg, files, table, l2d, l3d, p1, p2, nthreads, grids):
+def cpu_reference_step(cfg, files, table, l2d, l3d, p1, p2, nthreads, grids, use_ref=False):
     """One CPU step: the files sharded over `nthreads` workers (private grids each, like independent
     gritas.x processes), QC filter + GrITAS_Accum per file, partial grids summed, GrITAS_Norm."""
     from gritas_b200 import synth
-    from oracle import oracle
+    from oracle import oracle, ref
 
     def work(t):
         g = grids[t]
         for a in (g.bias_3d, g.rtms_3d, g.xcov_3d, g.nobs_3d, g.bias_2d, g.rtms_2d, g.xcov_2d, g.nobs_2d):
             a[...] = 0.0
         for c in files[t::nthreads]:
+            if use_ref:    # the reference's own filter loop and GrITAS_Accum_ (translated to C, oracle/_ref)
+                fl = ref.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=1, x_passive=synth.X_PASSIVE, x_pre_bad=synth.X_PRE_BAD)
+                ref.accum(g, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], c["del"], table, p1, p2, fl)
+                continue
             fl = oracle.filter_flags(c["qcexcl"], c["time"], c["lon"], ioptn=1, x_passive=synth.X_PASSIVE,
                                      x_pre_bad=synth.X_PRE_BAD)
             oracle.accum(g, cfg.nlevs, c["lat"], c["lon"], c["lev"], c["kx"], c["kt"], c["del"], table, p1, p2, fl)
@@ -161,7 +165,10 @@ def cpu_reference_step(cfg, files, table, l2d, l3d, p1, p2, nthreads, grids):
                 np.add(a, getattr(grids[t], name), out=a)
         with ThreadPoolExecutor(max_workers=nthreads) as ex:
             list(ex.map(red, ["bias_3d", "rtms_3d", "xcov_3d", "nobs_3d", "bias_2d", "rtms_2d", "xcov_2d", "nobs_2d"]))
-    oracle.norm(grids[0], cfg.nlevs, True, 0)
+    if use_ref:
+        ref.norm(grids[0], True, None)       # GrITAS_Norm_ without the optional threshold, as gritas.f:885-887 calls it
+    else:
+        oracle.norm(grids[0], cfg.nlevs, True, 0)
 
 
 def prepare_cpu_files(files, nr=2):
@@ -179,26 +186,29 @@ def prepare_cpu_files(files, nr=2):
     return out
 
 
-def time_cpu(cfg, files, nthreads, steps, warmup):
+def time_cpu(cfg, files, nthreads, steps, warmup, use_ref=False):
     from gritas_b200 import synth
-    from oracle import oracle
+    from oracle import oracle, ref
     table, l2d, l3d = synth.kxkt_table(cfg)
     p1, p2 = oracle.pint(cfg.plevs)
+    if use_ref:
+        ref.init(cfg.im, cfg.jm, cfg.km, cfg.nlevs, cfg.plevs, table.shape[0], table.shape[1])
     grids = [oracle.Grids(cfg.im, cfg.jm, cfg.km, l2d, l3d, cfg.nr) for _ in range(nthreads)]
     cf = prepare_cpu_files(files, cfg.nr)
     nobs = sum(len(c["lat"]) for c in cf)
     for _ in range(warmup):
-        cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids)
+        cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids, use_ref)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids)
+        cpu_reference_step(cfg, cf, table, l2d, l3d, p1, p2, nthreads, grids, use_ref)
     dt = (time.perf_counter() - t0) / steps
     return nobs / dt, dt, nobs
 
 
 def run_reference(args):
-    """--impl reference: CPU restatement of the reference loops on the host cores (kind = "port":
-    gritas.x itself needs a Fortran compiler and un-vendored GMAO_Shared, neither is in this image)."""
+    """--impl reference: the reference's own routines on the host cores -- oracle/_ref, its Fortran translated to C statement
+    by statement and compiled here (kind = "reference"); where that library is missing, the hand-written port (kind = "port").
+    gritas.x itself needs a Fortran compiler and un-vendored GMAO_Shared, neither is in this image."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -217,14 +227,19 @@ def run_reference(args):
     nfiles = max(nthreads, (nfiles // nthreads) * nthreads)
     files = gen_files(cfg, 0, nfiles)
     steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-    v, dt, nobs = time_cpu(cfg, files, nthreads, steps, warmup)
+    from oracle import ref
+    use_ref = ref.available()      # oracle/_ref: built where /root/reference is, travels to the GPU box as a built library
+    v, dt, nobs = time_cpu(cfg, files, nthreads, steps, warmup, use_ref)
+    what = ("the reference's own filter loop (gritas.f:712-735), GrITAS_Accum_ and GrITAS_Norm_ (m_gritas_grids.f:307-478, 490-656), "
+            "translated to C statement by statement (oracle/f2c_subset.py) and compiled with gcc -O2" if use_ref else
+            "the hand-written CPU port of the reference loops (oracle/gritas_oracle.c; pinned bit for bit against the translated reference)")
     sample = (f"{nfiles} of {cfg.nfiles} files ({nobs} obs) per step, sharded over {nthreads} threads with private "
-              f"grids, partial grids summed, then Norm; pre-sort (gritas.f:499-523) not included")
+              f"grids, partial grids summed, then Norm; pre-sort (gritas.f:499-523) not included; {what}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, cfg.nfiles), "sample": sample},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "pinned": "the port agrees bit for bit with the reference's own routines translated to C statement by statement (oracle/f2c_subset.py, tests/test_oracle_vs_ref.py)", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "reference" if use_ref else "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -643,11 +658,16 @@ def run_b200(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): single thread, like gritas.x ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(32, len(files))
-        v, dt, nobs = time_cpu(cfg, files[:ns], 1, 1, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "pinned": "the port agrees bit for bit with the reference's own routines translated to C statement by statement (oracle/f2c_subset.py, tests/test_oracle_vs_ref.py)",
+        from oracle import ref
+        use_ref = ref.available()          # oracle/_ref: the reference's own routines, translated to C and compiled (else the port)
+        v, dt, nobs = time_cpu(cfg, files[:ns], 1, 1, 1, use_ref)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
                                 "sample": f"{ns} of {nfiles} files ({nobs} obs): QC filter + GrITAS_Accum per file, "
                                           f"then GrITAS_Norm, single thread (the reference is serial); its 8-key "
-                                          f"pre-sort (gritas.f:499-523) is not included",
+                                          f"pre-sort (gritas.f:499-523) is not included; " +
+                                          ("the reference's own gritas.f:712-735 / GrITAS_Accum_ / GrITAS_Norm_ translated to C "
+                                           "statement by statement (oracle/f2c_subset.py), gcc -O2" if use_ref else
+                                           "hand-written port (oracle/gritas_oracle.c), pinned bit for bit against the translated reference"),
                                 "host_cores": os.cpu_count()}
     if rank == 0:
         emit(line)

@@ -666,8 +666,8 @@ PRELUDE = r"""/* GENERATED by oracle/f2c_subset.py from the reference's Fortran 
 #define F_ABS(x) _Generic((x), int: abs, long: labs, default: fabs)(x)
 #define F_MIN(a, b) ((a) < (b) ? (a) : (b))
 #define F_MAX(a, b) ((a) > (b) ? (a) : (b))
-jmp_buf gritas_ref_jmp;
-int gritas_ref_error_line = 0;
+__thread jmp_buf gritas_ref_jmp;            /* per thread: bench.py times the routines on several host threads */
+__thread int gritas_ref_error_line = 0;
 static void gritas_ref_perror(int line) { gritas_ref_error_line = line; longjmp(gritas_ref_jmp, 7); }
 """
 
