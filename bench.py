@@ -12,8 +12,9 @@ An extra weak-scaling leg (every rank its own month) is reported under "weak".
   value  : whole-job obs/s with the columns already resident in HBM (CUDA events on the library stream)
   e2e    : same step through the C ABI with pinned HOST columns (H2D inside) and the finalized
            grids copied back to pinned host arrays (D2H inside)
-  --impl reference : the CPU restatement of the reference loops (oracle/, the reference itself cannot
-           be built here: Fortran + un-vendored GMAO_Shared), file-sharded over the host cores.
+  --impl reference : the reference's own loops on the host cores, file-sharded over the threads: oracle/_ref (its Fortran
+           routines translated to C statement by statement and compiled here; the reference itself cannot be built:
+           Fortran + un-vendored GMAO_Shared), or the hand-written port in oracle/ where that library is missing.
 """
 from __future__ import annotations
 
