@@ -135,7 +135,6 @@ def normalise(st: str) -> str:
     st = re.sub(rf"\.\s*({DOTOPS})\s*\.", r".\1.", st)
     st = re.sub(r"\s*%\s*", "_", st) if "'" not in st and '"' not in st else st
     st = re.sub(r"^elseif\b", "else if", st)
-    st = re.sub(r"^elsewhere\b", "elsewhere", st)
     return st
 
 

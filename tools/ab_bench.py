@@ -10,7 +10,6 @@ A different libgritas_b200.so is a different process: GRITAS_B200_LIBDIR=... pyt
 from __future__ import annotations
 
 import argparse
-import ctypes
 import os
 import sys
 
