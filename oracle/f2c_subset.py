@@ -26,7 +26,9 @@ from __future__ import annotations
 import re
 import sys
 
-INTRINSICS = {"nint", "abs", "min", "max", "sqrt", "exp", "log", "real", "present", "dble", "int", "mod", "any", "sum", "size"}
+INTRINSICS = {"nint", "abs", "min", "max", "sqrt", "exp", "log", "real", "present", "dble", "int", "mod", "any", "sum", "size",
+              "f_streq"}
+FUNCTIONS = {}      # translated functions: lower-case name -> (C name, [number of assumed-shape dimensions or 0 per argument])
 RELOPS = {".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".eq.": "==", ".ne.": "!=", ".and.": "&&", ".or.": "||",
           ".not.": "!", ".true.": "1", ".false.": "0", "/=": "!=", "==": "==", "<=": "<=", ">=": ">=", "<": "<", ">": ">"}
 
@@ -135,6 +137,7 @@ def normalise(st: str) -> str:
     st = re.sub(rf"\.\s*({DOTOPS})\s*\.", r".\1.", st)
     st = re.sub(r"\s*%\s*", "_", st) if "'" not in st and '"' not in st else st
     st = re.sub(r"^elseif\b", "else if", st)
+    st = re.sub(r"trim\s*\(\s*(\w+\s*\(\s*\w+\s*\))\s*\)\s*==\s*('[^']*')", r"f_streq(\1, \2)", st)
     return st
 
 
@@ -297,8 +300,27 @@ def expr_c(tokens, sc: Scope) -> str:
                         out.append(f"(({a[0]}) % ({a[1]}))")
                     elif val == "present":
                         out.append(f"({a[0].strip('(*)')} != 0)")
+                    elif val == "f_streq":
+                        out.append(f"(strcmp({a[0]}, {a[1].strip()}) == 0)")
                     else:
                         raise ValueError(val)
+                elif val in FUNCTIONS:
+                    cname, kinds = FUNCTIONS[val]
+                    cargs = []
+                    for a, nd in zip(args, kinds):
+                        nm = a[0][1]
+                        if a[0][0] == "id" and sc.is_array(nm) and len(a) > 1:
+                            sub = split_top(a[2:matching_paren(a, 1)])
+                            secs = [q for q, x in enumerate(sub) if x == [("op", ":")]]
+                            if secs != list(range(len(secs))):
+                                raise ValueError("only leading whole-dimension sections can be passed on")
+                            first = ", ".join("1" if x == [("op", ":")] else expr_c(x, sc) for x in sub)
+                            cargs.append(f"&{nm}({first})")              # contiguous: the address of its first element ...
+                            if nd:
+                                cargs += [f"{sc.extent(nm, q)}" for q in secs]      # ... and, for an assumed-shape dummy, the extents
+                        else:
+                            cargs.append(expr_c(a, sc))
+                    out.append(f"{cname}({', '.join(cargs)})")
                 elif val in sc.vars and not sc.vars[val]["dims"]:
                     # declared like a scalar, used with arguments: an external function (the harness supplies it)
                     out.append(f"{val}_({', '.join(expr_c(x, sc) for x in args)})")
@@ -329,6 +351,9 @@ def parse_decl(stmt):
         re.sub(r"\s+", " ", m.group(1))]
     rest = m.group(2).strip()
     if rest.startswith("(") and typ == "char":                           # character(len=*)
+        rest = rest[rest.index(")") + 1:].strip()
+    if typ == "double" and re.match(r"^\(\s*4\s*\)", rest):                # real(4)
+        typ = "float"
         rest = rest[rest.index(")") + 1:].strip()
     attrs = []
     dim_attr = None
@@ -462,10 +487,16 @@ class Translator:
             if v["dims"]:
                 macros.append(nm)
                 w(self.accessor(nm, v["dims"], sc))
+        if is_function:
+            FUNCTIONS[name.lower()] = (cname, [len(sc.vars[a]["dims"]) if sc.vars[a].get("assumed") else 0 for a in args])
         self.statements(body, sc, ret=(name.lower() if is_function else None))
         w(f"  return {name.lower()};" if is_function else "  return;")
         for nm in macros:
-            w(f"#undef {nm}")
+            if nm in self.globals and self.globals[nm].get("define"):
+                w(f"#undef {nm}")
+                w(self.globals[nm]["define"])                           # a dummy of the same name shadowed the module's array
+            else:
+                w(f"#undef {nm}")
         w("}")
         w("")
 
@@ -662,6 +693,7 @@ PRELUDE = r"""/* GENERATED by oracle/f2c_subset.py from the reference's Fortran 
 #include <setjmp.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 #define F_ABS(x) _Generic((x), int: abs, long: labs, default: fabs)(x)
 #define F_MIN(a, b) ((a) < (b) ? (a) : (b))
 #define F_MAX(a, b) ((a) > (b) ? (a) : (b))
@@ -680,6 +712,12 @@ def module_globals(text, first, last):
             continue
         typ, attrs, ents = d
         if typ == "char":
+            for nm, dims, init in ents:
+                if nm == "type_stats":                                # (/'mean','rms','stdv'/): compared after trim()
+                    lits = [t[1][1:-1].strip() for t in init if t[0] == "str"]
+                    c.append("static const char *" + nm + "[] = {" + ", ".join(f'"{x}"' for x in lits) + "};   /* line " + str(no) + " */")
+                    c.append(f"#define {nm}(i1) {nm}[(size_t)(i1) - 1]")
+                    g[nm] = {"type": "char", "dims": [[("num", str(len(lits)))]], "optional": False, "arg": False, "define": c[-1]}
             continue
         for nm, dims, init in ents:
             if "parameter" in attrs:
@@ -690,11 +728,16 @@ def module_globals(text, first, last):
                 if nm == "plevs":
                     c.append(f"{typ} *{nm};   /* line {no}: allocatable, 1-based */")
                     c.append(f"#define {nm}(i1) {nm}[(size_t)(i1) - 1]")
-                    g[nm] = {"type": typ, "dims": [[("id", "nlevs")]], "optional": False, "arg": False}
+                    g[nm] = {"type": typ, "dims": [[("id", "nlevs")]], "optional": False, "arg": False, "define": c[-1]}
+                elif nm in ("lonindx", "regindx"):                    # (2, nslots) / (2, nregions)
+                    c.append(f"{typ} *{nm}; int {nm}_n2;   /* line {no}: allocatable, 1-based, column-major */")
+                    c.append(f"#define {nm}(i1, i2) {nm}[(size_t)(i1) - 1 + (size_t)2 * ((size_t)(i2) - 1)]")
+                    g[nm] = {"type": typ, "dims": [[("num", "2")], [("id", f"{nm}_n2")]], "optional": False, "arg": False, "define": c[-1]}
+                    g[f"{nm}_n2"] = {"type": "int", "dims": None, "optional": False, "arg": False}
                 elif nm == "achan":                                   # (nchan, 2): channel index / channel number
                     c.append(f"{typ} *{nm}; int {nm}_n1;   /* line {no}: allocatable, 1-based, column-major */")
                     c.append(f"#define {nm}(i1, i2) {nm}[(size_t)(i1) - 1 + (size_t)({nm}_n1) * ((size_t)(i2) - 1)]")
-                    g[nm] = {"type": typ, "dims": [[("id", f"{nm}_n1")], [("num", "2")]], "optional": False, "arg": False}
+                    g[nm] = {"type": typ, "dims": [[("id", f"{nm}_n1")], [("num", "2")]], "optional": False, "arg": False, "define": c[-1]}
                     g[f"{nm}_n1"] = {"type": "int", "dims": None, "optional": False, "arg": False}
             else:
                 c.append(f"{typ} {nm};   /* line {no} */")
@@ -721,10 +764,14 @@ def statements_range(text, first, last, globals_, cname, params=(), locals_=(), 
     for typ, nm, dims, byref in params:
         if dims:
             macros.append(nm)
+            if nm in globals_ and globals_[nm].get("define"):
+                tr.out.append(f"#undef {nm}")
             tr.out.append(Translator.accessor(nm, sc.vars[nm]["dims"], sc))
     tr.statements(logical_lines(text, first, last, free), sc)
     for nm in macros:
         tr.out.append(f"#undef {nm}")
+        if nm in globals_ and globals_[nm].get("define"):
+            tr.out.append(globals_[nm]["define"])                       # a parameter of the same name shadowed the module's array
     tr.out.append("}")
     tr.out.append("")
     return tr.out
@@ -759,6 +806,7 @@ def main(ref_root, dst):
                  "GrITAS_XCov_Accum_", "GrITAS_XCov_Norm_", "GrITAS_XCov_Prs_Accum_"):
         tr.routine(name, name.lower())
     tr.routine("ave_nomiss", "gritas_ave_nomiss_")
+    tr.routine("scores2_", "gritas_scores2_")
     out += tr.out
     # the scorecard's latitude rows: the grid latitudes (:136-138) and the row search of init_ (:165-175)
     r0 = find_line(grids, r"^\s*glat\(j\) = LatMin")

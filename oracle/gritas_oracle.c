@@ -10,16 +10,15 @@
  * pinned against instead:
  *   - PINNED against the reference's own source text: oracle/f2c_subset.py translates to C, STATEMENT BY STATEMENT and from
  *     the files where they lie: GrITAS_Pint_, GrITAS_Accum_, GrITAS_Norm_, GrITAS_MinMax_, GrITAS_3CH_Norm_,
- *     GrITAS_XCov_Accum_, GrITAS_XCov_Norm_, GrITAS_XCov_Prs_Accum_, ave_nomiss, the mesh statements and the region rows of
+ *     GrITAS_XCov_Accum_, GrITAS_XCov_Norm_, GrITAS_XCov_Prs_Accum_, scores2_, ave_nomiss, the mesh statements and the region rows of
  *     init_ (m_gritas_grids.f), GrITAS_KxKt (gritas_kxkt.f), the loop of maskout_ (m_gritas_masks.F90), the pre-sort call
  *     sequence, the residual selection chain, the QC / time / longitude filter loop and the Jo scaling (gritas.f:500-508,
- *     562-704, 712-735, 738).  gcc compiles the result (oracle/_ref, git-ignored) and tests/test_oracle_vs_ref.py (118
+ *     562-704, 712-735, 738).  gcc compiles the result (oracle/_ref, git-ignored) and tests/test_oracle_vs_ref.py (119
  *     cases) demands bit-for-bit agreement with the routines below -- flags, sums, statistics, tables, permutations,
  *     error statements -- on random inputs, the committed golden fixtures and the edge cases of SURVEY.md section 4;
  *   - ASSUMED, because their sources are not in the reference tree: a stable merge sort for m_MergeSorts' IndexSort
  *     (GMAO_mpeu), X_PASSIVE = 7 / X_PRE_BAD = 1 / ktSurfAll of m_odsmeta (GMAO_ods; parameters everywhere), the ODS file
- *     format.  scores2_'s loop nest around ave_nomiss is restated by hand (its character comparisons are outside the
- *     translator's subset).
+ *     format.
  *   - one DEFECT OF THE REFERENCE found this way and not reproduced: GrITAS_XCov_Prs_Accum_ books the first observation of
  *     a sounding to the sounding before it (:1961-1975), allocates the last sounding of a call one element short and
  *     gathers past the end of its work arrays (undefined behaviour); the oracle and the CUDA path compute what the loop

@@ -80,6 +80,7 @@ def lib():
         L.ref_ave_nomiss.argtypes = [_f64p, _f64p, C.c_int, C.c_int, _i32p, _i32p]
         L.ref_ave_nomiss.restype = C.c_double
         L.ref_region_rows.argtypes = [C.c_int, _f64p, _i32p]
+        L.ref_scores2.argtypes = [np.ctypeslib.ndpointer(dtype=np.float32, flags="F_CONTIGUOUS")] + [C.c_int] * 7 + [_i32p] + [_f64p] * 8
         L.ref_maskout.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _f64p, _i32p]
         L.ref_presort.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p]
         L.ref_xcov_accum.argtypes = ([_f64p] * 3 + [_i32p, _i32p, _f64p, C.c_int, C.c_int, _i32p, _i32p, C.c_int, _f64p] + [C.c_int] * 3
@@ -255,3 +256,12 @@ def presort(qcexcl, lat, lon, lev, time, kt, ks, kx):
     out = np.zeros(max(n, 1), dtype=np.int32)
     lib().ref_presort(n, out, _i(qcexcl), _f(lat), _f(lon), _f(lev), _i(time), _i(kt), _i(ks), _i(kx))
     return out[:n] - 1
+
+
+def scores2(g: oracle.Grids, regindx):
+    """scores2_ (m_gritas_grids.f:1671-1795) on finalized grids with nr = 1 -> collect_stats (nreg, km, l2d + l3d, 3) float32"""
+    nreg = regindx.shape[1]
+    out = np.zeros((nreg, g.km, g.l2d + g.l3d, 3), np.float32, order="F")
+    _check(lib().ref_scores2(out, nreg, g.im, g.jm, g.km, g.l2d, g.l3d, g.nr, np.asfortranarray(regindx, dtype=np.int32),
+                             g.bias_2d, g.rtms_2d, g.stdv_2d, g.nobs_2d, g.bias_3d, g.rtms_3d, g.stdv_3d, g.nobs_3d))
+    return out

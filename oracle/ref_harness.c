@@ -185,3 +185,20 @@ int ref_presort(int nobs, int *is, int *qcexcl, double *lat, double *lon, double
   gritas_presort_(nobs, is, qcexcl, lat, lon, lev, time, kt, ks, kx);
   return 0;
 }
+
+/* scores2_ (m_gritas_grids.f:1671-1795).  Module state it reads: lonindx(2, ntslots) = (1, im) as init_ leaves it (:181-186)
+ * and regindx(2, nreg) (the caller's, e.g. from ref_region_rows).  Shapes: 2-D arrays (im, jm, l2d, nr), counts (im, jm, l2d);
+ * 3-D arrays (im, jm, km, l3d, nr), counts (im, jm, km, l3d); collect_stats (nreg, km, l2d + l3d, 3) real(4). */
+int ref_scores2(float *collect_stats, int nreg, int im_, int jm_, int km_, int l2d, int l3d, int nr, int *regindx_,
+                double *bias_2d, double *rtms_2d, double *stdv_2d, double *nobs_2d, double *bias_3d, double *rtms_3d,
+                double *stdv_3d, double *nobs_3d) {
+  static int lon_[2];
+  lon_[0] = 1; lon_[1] = im_;
+  lonindx = lon_; lonindx_n2 = 1;
+  regindx = regindx_; regindx_n2 = nreg;
+  GUARD();
+  gritas_scores2_(collect_stats, nreg, km_, l2d + l3d, 3, bias_2d, im_, jm_, l2d, nr, rtms_2d, im_, jm_, l2d, nr, stdv_2d, im_, jm_, l2d, nr,
+                  nobs_2d, im_, jm_, l2d, bias_3d, im_, jm_, km_, l3d, nr, rtms_3d, im_, jm_, km_, l3d, nr, stdv_3d, im_, jm_, km_, l3d, nr,
+                  nobs_3d, im_, jm_, km_, l3d);
+  return 0;
+}

@@ -7,7 +7,7 @@ gritas_perror is called.
 
 This is what pins the oracle: m_gritas_grids.f GrITAS_Pint_ (:217-296), GrITAS_Accum_ (:307-478), GrITAS_Norm_ (:490-656),
 GrITAS_XCov_Accum_ (:667-848), GrITAS_XCov_Norm_ (:859-1008), GrITAS_MinMax_ (:1019-1167), GrITAS_3CH_Norm_ (:1178-1341),
-ave_nomiss (:1797-1826), GrITAS_XCov_Prs_Accum_ (:1862-2059), init_ (:128-129, 136-138, 163-175); gritas_kxkt.f GrITAS_KxKt
+scores2_ (:1671-1795), ave_nomiss (:1797-1826), GrITAS_XCov_Prs_Accum_ (:1862-2059), init_ (:128-129, 136-138, 163-175); gritas_kxkt.f GrITAS_KxKt
 (:10-119); m_gritas_masks.F90 maskout_ (:152-153, 164-183); gritas.f :500-508, :562-704, :712-735, :738.  Skipped where
 neither the reference sources nor a built oracle/_ref/libgritas_ref.so exist."""
 import numpy as np
@@ -403,7 +403,8 @@ def test_scorecard_reductions(seed):
     g.bias_3d[:, :, 2, 1, 0] = oracle.AMISS                  # a level without any valid box
     regindx = ref.score_regions()
     want = oracle.scores2(g, regindx)
-    lon = np.array([1, im], np.int32)
+    assert np.array_equal(ref.scores2(g, regindx), want)     # scores2_ itself, translated
+    lon = np.array([1, im], np.int32)                        # ... and its loop nest spelled out around ave_nomiss
     got = np.zeros_like(want)
     for ne, nm in enumerate(("bias", "rtms", "stdv")):
         for mr in range(regindx.shape[1]):
