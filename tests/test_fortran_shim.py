@@ -65,3 +65,15 @@ def test_checker_catches_a_wrong_prototype(tmp_path):
 def test_checker_catches_a_wrong_call_arity(tmp_path):
     errs = _mutated(tmp_path, inc_edit=lambda s: s.replace("call B200_Accum ( im, jm, km, nlevs, lat,", "call B200_Accum ( im, jm, km, lat,", 1))
     assert any("b200_accum: called with" in e for e in errs), errs
+
+
+def test_checker_catches_what_implicit_none_would(tmp_path):
+    """an undeclared variable, a misspelt module variable, a lost `end if`, a lost parenthesis"""
+    errs = _mutated(tmp_path, lambda s: s.replace("      integer(c_int) :: rc\n", "      integer(c_int) :: rcx\n", 1))
+    assert any("`rc` is not declared" in e for e in errs), errs
+    errs = _mutated(tmp_path, lambda s: s.replace("      normed = .true.", "      normd = .true.", 1))
+    assert any("`normd` is not declared" in e for e in errs), errs
+    errs = _mutated(tmp_path, lambda s: s.replace("      end if\n", "\n", 1))
+    assert any("unterminated" in e or "unbalanced" in e for e in errs), errs
+    errs = _mutated(tmp_path, lambda s: s.replace("      sent3 = 0\n", "      sent3 = max(0, 1\n", 1))
+    assert any("unbalanced parentheses" in e for e in errs), errs

@@ -12,6 +12,10 @@
 3. Every procedure the include file calls is public in the shim, with the same number of arguments.
 4. The replacement routines keep the reference's argument lists (checked against the reference
    source when /root/reference is present).
+5. Every procedure of the shim has balanced if / do / select blocks and parentheses, and every identifier its
+   executable statements and declarations use is a dummy argument, a local or module variable, a `use ... only` name, a
+   procedure of the module or of its bind(C) interfaces, an iso_c_binding name or an intrinsic (what `implicit none`
+   would reject).
 
 Exit code 0 = all checks pass; prints one line per failure otherwise.
 """
@@ -217,6 +221,146 @@ def find_cycle(graph):
     return None
 
 
+# ---------------------------------------------------------------------------------------------- check 5
+KEYWORDS = set("""if then else elseif endif end do enddo call return subroutine function module contains use only implicit none
+    integer real logical character type intent in out inout value optional save parameter allocatable dimension pointer target
+    interface import public private bind c name result select case default exit cycle while where elsewhere allocate
+    deallocate stat kind len intrinsic program stop print write read format continue go to goto associated""".split())
+INTRINSIC_NAMES = set("""abs min max mod size present allocated trim len_trim sqrt exp log nint int dble real merge any all count sum
+    product maxval minval reshape shape lbound ubound transfer huge tiny epsilon sign floor ceiling adjustl adjustr index iand ior
+    ishft ieor not btest""".split())
+ISO_C = set("""c_ptr c_int c_double c_float c_char c_size_t c_int32_t c_int64_t c_null_ptr c_null_char c_loc c_associated c_f_pointer
+    c_funptr c_bool c_long c_short c_signed_char c_sizeof""".split())
+DECL_START = re.compile(r"^(integer|real|logical|character|type\s*\(|double\s+precision|complex)")
+
+
+def _names_declared(stmt):
+    """names an entity declaration introduces"""
+    rest = stmt.split("::", 1)[1] if "::" in stmt else re.sub(r"^(integer|real|logical|double\s+precision)\s*(\([^)]*\))?", "", stmt)
+    out, depth, cur = [], 0, ""
+    for ch in rest + ",":
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            m = re.match(r"\s*([a-z_][a-z0-9_]*)", cur)
+            if m:
+                out.append(m.group(1))
+            cur = ""
+        else:
+            cur += ch
+    return out
+
+
+def _identifiers(stmt):
+    """identifiers an executable statement refers to (no string contents, no component names, no keyword-argument names)"""
+    stmt = re.sub(r"'[^']*'|\"[^\"]*\"", " ", stmt)
+    stmt = re.sub(r"%\s*[a-z_][a-z0-9_]*", " ", stmt)                 # a%b: b is a component
+    stmt = re.sub(r"\.(true|false|and|or|not|eq|ne|lt|le|gt|ge|eqv|neqv)\.", " ", stmt)
+    stmt = re.sub(r"\b\d+(\.\d*)?([de][+-]?\d+)?(_[a-z_0-9]+)?\b", " ", stmt)      # numbers, with kind suffix
+    stmt = re.sub(r"(?<=[(,])\s*[a-z_][a-z0-9_]*\s*=(?!=)", " ", stmt)              # keyword arguments: f(name=...)
+    stmt = re.sub(r"\bcall\s+[a-z_][a-z0-9_]*", " ", stmt)             # an external subroutine needs no declaration
+    return set(re.findall(r"[a-z_][a-z0-9_]*", stmt))
+
+
+def lint_units(lines, extra_known=()):
+    """block balance of every program unit and an `implicit none` lint of its executable statements"""
+    errors = []
+    module_names, procs = set(extra_known), set()
+    # pass 1: module-level names and all procedure names (module procedures, interface bodies)
+    depth_iface, in_unit = 0, 0
+    for st in lines:
+        if re.match(r"^interface\b", st):
+            depth_iface += 1
+        elif re.match(r"^end\s*interface", st):
+            depth_iface -= 1
+        m = re.match(r"^(?:[a-z_()0-9 ]*?\b)?(subroutine|function)\s+([a-z_][a-z0-9_]*)", st)
+        if m and not st.startswith("end"):
+            procs.add(m.group(2))
+            if not depth_iface:
+                in_unit += 1
+            continue
+        if re.match(r"^end\s*(subroutine|function)", st) and not depth_iface:
+            in_unit -= 1
+            continue
+        if not in_unit and not depth_iface and DECL_START.match(st):
+            module_names.update(_names_declared(st))
+        m = re.match(r"^use\b.*\bonly\s*:\s*(.*)$", st)
+        if m and not in_unit:
+            module_names.update(x.split("=>")[0].strip() for x in m.group(1).split(","))
+    # pass 2: every module procedure
+    i, n = 0, len(lines)
+    depth_iface = 0
+    while i < n:
+        st = lines[i]
+        if re.match(r"^interface\b", st):
+            depth_iface += 1
+        elif re.match(r"^end\s*interface", st):
+            depth_iface -= 1
+        m = re.match(r"^(?:[a-z_()0-9 ]*?\b)?(subroutine|function)\s+([a-z_][a-z0-9_]*)\s*(?:\(([^)]*)\))?", st)
+        if not m or st.startswith("end") or depth_iface:
+            i += 1
+            continue
+        name = m.group(2)
+        local = {a.strip() for a in (m.group(3) or "").split(",") if a.strip()} | {name}
+        mres = re.search(r"result\s*\(\s*([a-z_][a-z0-9_]*)\s*\)", st)
+        if mres:
+            local.add(mres.group(1))
+        stack = []
+        j = i + 1
+        inner_iface = 0
+        while j < n and not re.match(r"^end\s*(subroutine|function)", lines[j]):
+            s2 = lines[j]
+            if re.match(r"^interface\b", s2):
+                inner_iface += 1
+            elif re.match(r"^end\s*interface", s2):
+                inner_iface -= 1
+            elif inner_iface:
+                pass
+            elif re.match(r"^use\b", s2):
+                mo = re.match(r"^use\b.*\bonly\s*:\s*(.*)$", s2)
+                if mo:
+                    local.update(x.split("=>")[0].strip() for x in mo.group(1).split(","))
+            elif DECL_START.match(s2) and "::" in s2 or re.match(r"^(integer|real|logical)\s+[a-z_]", s2):
+                local.update(_names_declared(s2))
+                # initialisers and bounds may refer to other names: check them too
+                unknown = _identifiers(s2.split("::", 1)[1] if "::" in s2 else "") - local - module_names - procs - KEYWORDS - INTRINSIC_NAMES - ISO_C
+                for u in sorted(unknown):
+                    errors.append(f"{name}: `{u}` in a declaration is not declared ({s2[:70]})")
+            elif s2.startswith(("implicit", "import")):
+                pass
+            else:
+                # block structure
+                if re.match(r"^(?:[a-z_0-9]+\s*:\s*)?if\s*\(.*\)\s*then$", s2):
+                    stack.append("if")
+                elif re.match(r"^(?:[a-z_0-9]+\s*:\s*)?do\b", s2):
+                    stack.append("do")
+                elif re.match(r"^select\s+case", s2):
+                    stack.append("select")
+                elif re.match(r"^end\s*if\b", s2):
+                    if not stack or stack.pop() != "if":
+                        errors.append(f"{name}: unbalanced `end if`")
+                elif re.match(r"^end\s*do\b", s2):
+                    if not stack or stack.pop() != "do":
+                        errors.append(f"{name}: unbalanced `end do`")
+                elif re.match(r"^end\s*select\b", s2):
+                    if not stack or stack.pop() != "select":
+                        errors.append(f"{name}: unbalanced `end select`")
+                if s2.count("(") != s2.count(")"):
+                    errors.append(f"{name}: unbalanced parentheses ({s2[:70]})")
+                unknown = _identifiers(s2) - local - module_names - procs - KEYWORDS - INTRINSIC_NAMES - ISO_C
+                for u in sorted(unknown):
+                    errors.append(f"{name}: `{u}` is not declared ({s2[:70]})")
+            j += 1
+        if stack:
+            errors.append(f"{name}: unterminated {stack}")
+        if j >= n:
+            errors.append(f"{name}: no end subroutine / end function")
+        i = j + 1
+    return errors
+
+
 def run():
     errors = []
     shim = strip_fortran(open(SHIM).read())
@@ -277,6 +421,12 @@ def run():
                 errors.append(f"{name}: not a routine of the reference's m_gritas_grids.f")
             elif ref_args[name] != args:
                 errors.append(f"{name}: dummy arguments differ from the reference: {args} vs {ref_args[name]}")
+    # 5. block structure and an `implicit none` lint of every procedure of the shim
+    errors += lint_units(shim)
+    # ... and of the reference-side bodies, which see the module variables of m_gritas_grids (m_gritas_grids.f:21-72) and
+    # the public procedures of the shim
+    grids_names = {"im", "jm", "km", "nlevs", "nchan", "achan", "ichan_version", "plevs", "amiss", "myname"}
+    errors += lint_units(inc, set(pub) | grids_names)
     return errors, ifaces, graph
 
 
